@@ -1,0 +1,127 @@
+"""ctypes binding of libfcn8s_sm100.so (include/fcn8s_b200.h).
+
+Loading never falls back to anything: a missing library raises, and every non-zero status raises Fcn8Error with the
+library's own message. PyTorch tensors are used only as device-memory owners (``tensor.data_ptr()``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfcn8s_sm100.so")
+
+BF16, F32 = 0, 1
+EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL = 1, 2, 4, 8, 16
+
+EXPORTS = [
+    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_debug_set", "fcn8_preprocess_im2col",
+    "fcn8_conv_gemm_workspace_bytes", "fcn8_conv_gemm", "fcn8_wgrad_gemm_workspace_bytes", "fcn8_wgrad_gemm",
+    "fcn8_pack_weights", "fcn8_split_tf32", "fcn8_maxpool_fwd", "fcn8_maxpool_bwd", "fcn8_bias_grad_workspace_bytes",
+    "fcn8_bias_grad", "fcn8_score_head_fwd", "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
+    "fcn8_upscore_fwd", "fcn8_upscore_bwd_workspace_bytes", "fcn8_upscore_bwd", "fcn8_softmax_xent",
+    "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
+]
+
+
+class Fcn8Error(RuntimeError):
+    pass
+
+
+class PreprocessParams(C.Structure):
+    _fields_ = [("images", C.c_void_p), ("out", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("dtype", C.c_int32)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("wp", C.c_void_p), ("wp_lo", C.c_void_p),
+                ("out", C.c_void_p), ("bias", C.c_void_p), ("mask_src", C.c_void_p), ("residual", C.c_void_p),
+                ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
+                ("ksize", C.c_int32), ("dtype", C.c_int32), ("nseg", C.c_int32), ("flags", C.c_int32),
+                ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
+                ("force_splits", C.c_int32), ("force_bn", C.c_int32)]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("dy", C.c_void_p), ("dy_lo", C.c_void_p),
+                ("dw", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+                ("Cout", C.c_int32), ("ksize", C.c_int32), ("rows_valid", C.c_int32), ("dtype", C.c_int32),
+                ("nseg", C.c_int32), ("force_splits", C.c_int32), ("force_bn", C.c_int32)]
+
+
+class PackParams(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("out_lo", C.c_void_p), ("ksize", C.c_int32),
+                ("Cin", C.c_int32), ("Cout", C.c_int32), ("CinPad", C.c_int32), ("mode", C.c_int32),
+                ("dtype", C.c_int32)]
+
+
+class PoolParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("dx", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32),
+                ("W", C.c_int32), ("C", C.c_int32), ("dtype", C.c_int32)]
+
+
+class BiasGradParams(C.Structure):
+    _fields_ = [("dy", C.c_void_p), ("db", C.c_void_p), ("P", C.c_int64), ("C", C.c_int32), ("dtype", C.c_int32)]
+
+
+class HeadParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("K", C.c_void_p), ("b", C.c_void_p), ("s", C.c_void_p), ("dK", C.c_void_p),
+                ("db", C.c_void_p), ("dx", C.c_void_p), ("P", C.c_int64), ("Cin", C.c_int32), ("C", C.c_int32),
+                ("scale", C.c_float), ("dtype", C.c_int32), ("mask", C.c_int32), ("mask_scale", C.c_float)]
+
+
+class UpscoreParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("T", C.c_void_p), ("bias", C.c_void_p), ("skip", C.c_void_p), ("y", C.c_void_p),
+                ("dx", C.c_void_p), ("dT", C.c_void_p), ("dbias", C.c_void_p), ("N", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("C", C.c_int32), ("stride", C.c_int32)]
+
+
+class SoftmaxParams(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("labels", C.c_void_p), ("loss_sum", C.c_void_p), ("dlogits", C.c_void_p),
+                ("softmax", C.c_void_p), ("argmax", C.c_void_p), ("P", C.c_int64), ("C", C.c_int32),
+                ("grad_scale", C.c_float)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built: there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Fcn8Error("libfcn8s_sm100.so is not built (run `python -m fcn8s_tensorflow_b200.build`); "
+                        "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.fcn8_version.restype = C.c_int32
+    lib.fcn8_last_error.restype = C.c_char_p
+    lib.fcn8_device_check.argtypes = [C.c_int32]
+    lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
+    vp, sz = C.c_void_p, C.c_size_t
+    for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
+                     ("fcn8_score_head_bwd", HeadParams), ("fcn8_upscore_bwd", UpscoreParams)]:
+        getattr(lib, name).argtypes = [C.POINTER(pt), vp, sz, vp]
+        getattr(lib, name).restype = C.c_int32
+        getattr(lib, name + "_workspace_bytes").argtypes = [C.POINTER(pt)]
+        getattr(lib, name + "_workspace_bytes").restype = sz
+    for name, pt in [("fcn8_preprocess_im2col", PreprocessParams), ("fcn8_pack_weights", PackParams),
+                     ("fcn8_maxpool_fwd", PoolParams), ("fcn8_maxpool_bwd", PoolParams),
+                     ("fcn8_score_head_fwd", HeadParams), ("fcn8_upscore_fwd", UpscoreParams),
+                     ("fcn8_softmax_xent", SoftmaxParams)]:
+        getattr(lib, name).argtypes = [C.POINTER(pt), vp]
+        getattr(lib, name).restype = C.c_int32
+    lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
+    lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
+    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.fcn8_l2_reg.argtypes = [vp, vp, vp, sz, C.c_float, vp]
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise Fcn8Error("fcn8 error %d: %s" % (status, load().fcn8_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,595 @@
+// C ABI of libfcn8s_sm100.so (declared in include/fcn8s_b200.h): argument validation, TMA tensor-map encoding,
+// tile / split-K heuristics and kernel launches.  No allocation, no synchronisation, no torch types.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fcn8s_b200.h"
+#include "conv_gemm.cuh"
+#include "kernels.h"
+
+using namespace fcn8;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_debug[16] = {0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(FCN8_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC activation map: dims (C, W, H, N), box (CH, bw, bh, bn), 128B swizzle, OOB -> 0 (= SAME zero padding).
+int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int W, int C, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int es = dtype == FCN8_BF16 ? 2 : 4;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  const cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, dtype == FCN8_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(act N%d H%d W%d C%d box %d,%d,%d) failed: %d", N, H, W, C, bw,
+                bh, bn, (int)r);
+  return 0;
+}
+// Packed weight map: rows = Cout, cols = Ktot (K-major), box (CH, BN).
+int encode_w_map(CUtensorMap* m, const void* ptr, int dtype, int rows, int ktot, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int es = dtype == FCN8_BF16 ? 2 : 4;
+  const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ktot * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)bn};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dtype == FCN8_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(w rows %d k %d bn %d) failed: %d", rows, ktot, bn, (int)r);
+  return 0;
+}
+
+int ilog2_ceil(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+// Choose a power-of-two patch (bw, bh, bn) with bw*bh*bn = 2^total_log covering [N,H,W] with the fewest tiles.
+void choose_patch(int N, int H, int W, int total_log, int* lbw, int* lbh, int* lbn) {
+  long long best = -1;
+  for (int lw = total_log; lw >= 0; --lw)
+    for (int lh = total_log - lw; lh >= 0; --lh) {
+      const int ln = total_log - lw - lh;
+      const long long tiles = (long long)((W + (1 << lw) - 1) >> lw) * ((H + (1 << lh) - 1) >> lh) *
+                              ((N + (1 << ln) - 1) >> ln);
+      if (best < 0 || tiles < best) {
+        best = tiles;
+        *lbw = lw;
+        *lbh = lh;
+        *lbn = ln;
+      }
+    }
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+struct ConvPlan {
+  int BN, splits, kb_per_split, total_kb;
+  int lbw, lbh, lbn, tiles_x, tiles_y, tiles_b, m_tiles, tiles_n;
+  size_t out_elems;
+};
+
+int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
+  const int CH = p->dtype == FCN8_BF16 ? 64 : 32;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "conv: empty tensor");
+  if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cin=%d must be a multiple of %d", p->Cin, CH);
+  if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cout=%d must be a multiple of 64", p->Cout);
+  if (!(p->ksize & 1)) return fail(FCN8_ERR_BAD_SHAPE, "conv: ksize must be odd");
+  if (p->nseg != 1 && !(p->nseg == 3 && p->dtype == FCN8_F32))
+    return fail(FCN8_ERR_UNSUPPORTED, "conv: nseg must be 1 (or 3 with FCN8_F32)");
+  choose_patch(p->N, p->H, p->W, 7, &pl->lbw, &pl->lbh, &pl->lbn);
+  pl->tiles_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
+  pl->tiles_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
+  pl->tiles_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
+  pl->m_tiles = pl->tiles_x * pl->tiles_y * pl->tiles_b;
+  pl->total_kb = p->nseg * p->ksize * p->ksize * (p->Cin / CH);
+  const int sms = num_sms();
+  int bn = 0;
+  if (p->force_bn) {
+    bn = p->force_bn;
+    if ((bn != 64 && bn != 128 && bn != 256) || p->Cout % bn)
+      return fail(FCN8_ERR_BAD_SHAPE, "conv: force_bn=%d invalid for Cout=%d", bn, p->Cout);
+  } else {
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      if (p->Cout % cands[i]) continue;
+      if (!bn) bn = cands[i];  // largest valid
+      if ((long long)pl->m_tiles * (p->Cout / cands[i]) >= (sms * 4) / 5) {
+        bn = cands[i];
+        break;
+      }
+      if (cands[i] == 128) break;  // never go below 128 just to get more tiles; split-K handles the rest
+    }
+    if (p->Cout % 128) bn = 64;
+  }
+  pl->BN = bn;
+  pl->tiles_n = p->Cout / bn;
+  const long long tiles = (long long)pl->m_tiles * pl->tiles_n;
+  int splits = 1;
+  if (p->force_splits > 0) {
+    splits = p->force_splits;
+  } else if (tiles * 2 <= sms) {
+    splits = (int)(sms / tiles);
+    const int max_by_k = pl->total_kb / 16 > 0 ? pl->total_kb / 16 : 1;  // keep >= 16 k-blocks per split
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 16) splits = 16;
+  }
+  if (splits > pl->total_kb) splits = pl->total_kb;
+  pl->kb_per_split = (pl->total_kb + splits - 1) / splits;
+  pl->splits = (pl->total_kb + pl->kb_per_split - 1) / pl->kb_per_split;
+  pl->out_elems = (size_t)p->N * p->H * p->W * p->Cout;
+  return 0;
+}
+
+template <int BN, bool TF32>
+cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  conv_gemm_kernel<BN, TF32><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, a);
+  return cudaGetLastError();
+}
+
+template <int BN, bool TF32>
+constexpr int wgrad_smem_bytes() {
+  constexpr int CH = TF32 ? 32 : 64;
+  constexpr int stage = (128 / CH) * 8192 + (BN / CH) * 8192;
+  constexpr int stages = (200 * 1024) / stage;
+  return stages * stage + 1024 + 1024;
+}
+template <int BN, bool TF32>
+cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int smem = wgrad_smem_bytes<BN, TF32>();
+  if (!attr_done) {
+    cudaError_t e =
+        cudaFuncSetAttribute(wgrad_gemm_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  wgrad_gemm_kernel<BN, TF32><<<grid, kGemmThreads, smem, st>>>(maps, a);
+  return cudaGetLastError();
+}
+
+struct WgradPlan {
+  int BN, splits, pb_per_split, total_pb;
+  int lbw, lbh, lbn, pb_x, pb_y, pb_b;
+  int m_tiles, tiles_n, total_chunks;
+  size_t rows_pad;
+};
+int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
+  const int CH = p->dtype == FCN8_BF16 ? 64 : 32;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: empty tensor");
+  if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cin=%d must be a multiple of %d", p->Cin, CH);
+  if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cout=%d must be a multiple of 64", p->Cout);
+  if (p->nseg != 1 && !(p->nseg == 3 && p->dtype == FCN8_F32))
+    return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 (or 3 with FCN8_F32)");
+  int bn = p->force_bn ? p->force_bn : (p->Cout % 256 == 0 ? 256 : (p->Cout % 128 == 0 ? 128 : 64));
+  if (p->dtype == FCN8_F32 && bn == 256 && !p->force_bn) bn = 128;  // keep >= 3 smem stages with 4-byte operands
+  if ((bn != 64 && bn != 128 && bn != 256) || p->Cout % bn)
+    return fail(FCN8_ERR_BAD_SHAPE, "wgrad: BN=%d invalid for Cout=%d", bn, p->Cout);
+  pl->BN = bn;
+  pl->tiles_n = p->Cout / bn;
+  pl->total_chunks = p->ksize * p->ksize * (p->Cin / CH);
+  const int mch = 128 / CH;
+  pl->m_tiles = (pl->total_chunks + mch - 1) / mch;
+  pl->rows_pad = (size_t)pl->m_tiles * 128;
+  choose_patch(p->N, p->H, p->W, 6, &pl->lbw, &pl->lbh, &pl->lbn);
+  pl->pb_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
+  pl->pb_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
+  pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
+  pl->total_pb = p->nseg * pl->pb_x * pl->pb_y * pl->pb_b;
+  const int sms = num_sms();
+  const long long tiles = (long long)pl->m_tiles * pl->tiles_n;
+  int splits = 1;
+  if (p->force_splits > 0) {
+    splits = p->force_splits;
+  } else if (tiles < sms) {
+    splits = (int)((sms + tiles - 1) / tiles);
+    const int max_by_k = pl->total_pb / 8 > 0 ? pl->total_pb / 8 : 1;
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits > 64) splits = 64;
+  }
+  if (splits > pl->total_pb) splits = pl->total_pb;
+  pl->pb_per_split = (pl->total_pb + splits - 1) / splits;
+  pl->splits = (pl->total_pb + pl->pb_per_split - 1) / pl->pb_per_split;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fcn8_version(void) { return FCN8_VERSION; }
+const char* fcn8_last_error(void) { return g_err; }
+
+int32_t fcn8_device_check(int32_t dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+  if (prop.major != 10) return fail(FCN8_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a-only", dev,
+                                    prop.major, prop.minor);
+  return 0;
+}
+int32_t fcn8_debug_set(int32_t key, int32_t value) {
+  if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
+  g_debug[key] = value;
+  return 0;
+}
+
+int32_t fcn8_preprocess_im2col(const Fcn8PreprocessParams* p, void* stream) {
+  if (!p || !p->images || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "preprocess: null pointer");
+  if (!aligned16(p->out)) return fail(FCN8_ERR_BAD_ALIGN, "preprocess: out not 16-byte aligned");
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "preprocess: empty tensor");
+  cudaError_t e = launch_preprocess(p->images, p->out, p->N, p->H, p->W, p->dtype, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "preprocess launch");
+}
+
+size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p) {
+  ConvPlan pl;
+  if (plan_conv(p, &pl)) return 0;
+  return pl.splits > 1 ? (size_t)pl.splits * pl.out_elems * sizeof(float) : 0;
+}
+
+int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->x || !p->wp || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "conv: null pointer");
+  if (!aligned16(p->x) || !aligned16(p->wp) || !aligned16(p->out) || (p->bias && !aligned16(p->bias)) ||
+      (p->mask_src && !aligned16(p->mask_src)) || (p->residual && !aligned16(p->residual)))
+    return fail(FCN8_ERR_BAD_ALIGN, "conv: pointers must be 16-byte aligned");
+  if ((p->flags & FCN8_EPI_BIAS) && !p->bias) return fail(FCN8_ERR_BAD_SHAPE, "conv: BIAS flag without bias");
+  if ((p->flags & FCN8_EPI_MASK) && !p->mask_src) return fail(FCN8_ERR_BAD_SHAPE, "conv: MASK flag without mask_src");
+  if ((p->flags & FCN8_EPI_RESIDUAL) && !p->residual)
+    return fail(FCN8_ERR_BAD_SHAPE, "conv: RESIDUAL flag without residual");
+  if (p->nseg == 3 && (!p->x_lo || !p->wp_lo)) return fail(FCN8_ERR_BAD_SHAPE, "conv: nseg=3 needs x_lo and wp_lo");
+  ConvPlan pl;
+  int rc = plan_conv(p, &pl);
+  if (rc) return rc;
+  const size_t need = pl.splits > 1 ? (size_t)pl.splits * pl.out_elems * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(FCN8_ERR_WORKSPACE, "conv: workspace %zu < required %zu", workspace_bytes, need);
+
+  TensorMaps3 maps;
+  memset(&maps, 0, sizeof(maps));
+  const int ktot = p->ksize * p->ksize * p->Cin;
+  const void* xs[3] = {p->x, p->x, p->x_lo};
+  const void* ws[3] = {p->wp, p->wp_lo, p->wp};
+  for (int s = 0; s < p->nseg; ++s) {
+    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn);
+    if (rc) return rc;
+    rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
+    if (rc) return rc;
+  }
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = p->out;
+  a.bias = p->bias;
+  a.mask_src = p->mask_src;
+  a.residual = p->residual;
+  a.partial = static_cast<float*>(workspace);
+  a.N = p->N;
+  a.H = p->H;
+  a.W = p->W;
+  a.ldc = p->Cout;
+  a.taps = p->ksize * p->ksize;
+  a.taps_w = p->ksize;
+  a.pad = p->ksize / 2;
+  a.cblocks = p->Cin / (p->dtype == FCN8_BF16 ? 64 : 32);
+  a.nseg = p->nseg;
+  a.lbw = pl.lbw;
+  a.lbh = pl.lbh;
+  a.lbn = pl.lbn;
+  a.tiles_x = pl.tiles_x;
+  a.tiles_y = pl.tiles_y;
+  a.tiles_b = pl.tiles_b;
+  a.tiles_n = pl.tiles_n;
+  a.splits = pl.splits;
+  a.kb_per_split = pl.kb_per_split;
+  a.flags = p->flags & 31;
+  a.mask_scale = p->mask_scale;
+  a.seed = p->seed;
+  if (p->flags & FCN8_EPI_DROPOUT) {
+    if (!(p->keep_prob > 0.f && p->keep_prob <= 1.f)) return fail(FCN8_ERR_BAD_SHAPE, "conv: keep_prob out of (0,1]");
+    a.inv_keep = 1.f / p->keep_prob;
+    a.keep_threshold = (uint32_t)((double)p->keep_prob * 16777216.0);
+  }
+  ConvGemmArgs kernel_args = a;
+  if (pl.splits > 1) kernel_args.flags = EPI_PARTIAL;
+  const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
+  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  const bool tf32 = p->dtype == FCN8_F32;
+#define FCN8_DISPATCH(BNV)                                                    \
+  e = tf32 ? launch_conv_t<BNV, true>(maps, kernel_args, grid, st)          \
+           : launch_conv_t<BNV, false>(maps, kernel_args, grid, st)
+  if (pl.BN == 256) {
+    FCN8_DISPATCH(256);
+  } else if (pl.BN == 128) {
+    FCN8_DISPATCH(128);
+  } else {
+    FCN8_DISPATCH(64);
+  }
+#undef FCN8_DISPATCH
+  if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
+  if (pl.splits > 1) {
+    e = launch_conv_splitk_reduce(static_cast<const float*>(workspace), pl.splits, pl.out_elems, p->Cout, a, p->dtype,
+                                  st);
+    if (e != cudaSuccess) return cuda_fail(e, "conv split-K reduce launch");
+  }
+  return 0;
+}
+
+size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p) {
+  WgradPlan pl;
+  if (plan_wgrad(p, &pl)) return 0;
+  return pl.splits > 1 ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
+}
+
+int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->x || !p->dy || !p->dw) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: null pointer");
+  if (!aligned16(p->x) || !aligned16(p->dy) || !aligned16(p->dw))
+    return fail(FCN8_ERR_BAD_ALIGN, "wgrad: pointers must be 16-byte aligned");
+  if (p->nseg == 3 && (!p->x_lo || !p->dy_lo)) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: nseg=3 needs x_lo and dy_lo");
+  WgradPlan pl;
+  int rc = plan_wgrad(p, &pl);
+  if (rc) return rc;
+  const size_t need = pl.splits > 1 ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(FCN8_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu", workspace_bytes, need);
+  const int rows_all = p->ksize * p->ksize * p->Cin;
+  const int rows_valid = (p->rows_valid > 0 && p->rows_valid < rows_all) ? p->rows_valid : rows_all;
+
+  TensorMaps3 maps;
+  memset(&maps, 0, sizeof(maps));
+  const void* xs[3] = {p->x, p->x, p->x_lo};
+  const void* ds[3] = {p->dy, p->dy_lo, p->dy};
+  for (int s = 0; s < p->nseg; ++s) {
+    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn);
+    if (rc) return rc;
+    rc = encode_act_map(&maps.b[s], ds[s], p->dtype, p->N, p->H, p->W, p->Cout, 1 << pl.lbw, 1 << pl.lbh,
+                        1 << pl.lbn);
+    if (rc) return rc;
+  }
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = p->dw;
+  a.partial = static_cast<float*>(workspace);
+  a.N = p->N;
+  a.H = p->H;
+  a.W = p->W;
+  a.Cin = p->Cin;
+  a.ldc = p->Cout;
+  a.taps = p->ksize * p->ksize;
+  a.taps_w = p->ksize;
+  a.pad = p->ksize / 2;
+  a.nseg = p->nseg;
+  a.rows_valid = rows_valid;
+  a.total_chunks = pl.total_chunks;
+  a.m_tiles = pl.m_tiles;
+  a.tiles_n = pl.tiles_n;
+  a.lbw = pl.lbw;
+  a.lbh = pl.lbh;
+  a.lbn = pl.lbn;
+  a.pb_x = pl.pb_x;
+  a.pb_y = pl.pb_y;
+  a.pb_b = pl.pb_b;
+  a.splits = pl.splits;
+  a.pb_per_split = pl.pb_per_split;
+  a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
+  const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
+  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  const bool tf32 = p->dtype == FCN8_F32;
+#define FCN8_DISPATCH(BNV) \
+  e = tf32 ? launch_wgrad_t<BNV, true>(maps, a, grid, st) : launch_wgrad_t<BNV, false>(maps, a, grid, st)
+  if (pl.BN == 256) {
+    FCN8_DISPATCH(256);
+  } else if (pl.BN == 128) {
+    FCN8_DISPATCH(128);
+  } else {
+    FCN8_DISPATCH(64);
+  }
+#undef FCN8_DISPATCH
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad_gemm launch");
+  if (pl.splits > 1) {
+    e = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, pl.splits, pl.rows_pad, rows_valid,
+                                   p->Cout, st);
+    if (e != cudaSuccess) return cuda_fail(e, "wgrad split-K reduce launch");
+  }
+  return 0;
+}
+
+int32_t fcn8_pack_weights(const Fcn8PackParams* p, void* stream) {
+  if (!p || !p->w || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "pack: null pointer");
+  if (p->mode != 0 && p->mode != 1) return fail(FCN8_ERR_BAD_SHAPE, "pack: mode must be 0 or 1");
+  if (p->mode == 0 && p->CinPad < p->Cin) return fail(FCN8_ERR_BAD_SHAPE, "pack: CinPad < Cin");
+  if (p->dtype == FCN8_BF16 && p->out_lo) return fail(FCN8_ERR_UNSUPPORTED, "pack: out_lo only with FCN8_F32");
+  cudaError_t e = launch_pack(p->w, p->out, p->out_lo, p->ksize, p->Cin, p->Cout, p->CinPad, p->mode, p->dtype,
+                              (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "pack launch");
+}
+
+int32_t fcn8_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+  if (!x || !hi || !lo) return fail(FCN8_ERR_BAD_SHAPE, "split_tf32: null pointer");
+  if (n % 4) return fail(FCN8_ERR_BAD_SHAPE, "split_tf32: n must be a multiple of 4");
+  if (!aligned16(x) || !aligned16(hi) || !aligned16(lo)) return fail(FCN8_ERR_BAD_ALIGN, "split_tf32: alignment");
+  cudaError_t e = launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "split_tf32 launch");
+}
+
+static int check_pool(const Fcn8PoolParams* p) {
+  if (!p || !p->x || !p->y) return fail(FCN8_ERR_BAD_SHAPE, "pool: null pointer");
+  const int vec = p->dtype == FCN8_BF16 ? 8 : 4;
+  if (p->C % vec) return fail(FCN8_ERR_BAD_SHAPE, "pool: C=%d must be a multiple of %d", p->C, vec);
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "pool: empty tensor");
+  if (!aligned16(p->x) || !aligned16(p->y)) return fail(FCN8_ERR_BAD_ALIGN, "pool: alignment");
+  return 0;
+}
+int32_t fcn8_maxpool_fwd(const Fcn8PoolParams* p, void* stream) {
+  int rc = check_pool(p);
+  if (rc) return rc;
+  cudaError_t e = launch_maxpool_fwd(p->x, p->y, p->N, p->H, p->W, p->C, p->dtype, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "maxpool_fwd launch");
+}
+int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream) {
+  int rc = check_pool(p);
+  if (rc) return rc;
+  if (!p->dx || !aligned16(p->dx)) return fail(FCN8_ERR_BAD_SHAPE, "pool bwd: dx missing / unaligned");
+  cudaError_t e = launch_maxpool_bwd(p->x, p->y, p->dx, p->N, p->H, p->W, p->C, p->dtype, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "maxpool_bwd launch");
+}
+
+size_t fcn8_bias_grad_workspace_bytes(const Fcn8BiasGradParams* p) {
+  return (size_t)bias_grad_blocks(p->P, p->C) * p->C * sizeof(float);
+}
+int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->dy || !p->db) return fail(FCN8_ERR_BAD_SHAPE, "bias_grad: null pointer");
+  const int vec = p->dtype == FCN8_BF16 ? 8 : 4;
+  const int CV = p->C / vec;
+  if (p->C % vec || (CV & (CV - 1))) return fail(FCN8_ERR_BAD_SHAPE, "bias_grad: C/%d must be a power of two", vec);
+  if (workspace_bytes < fcn8_bias_grad_workspace_bytes(p) || !workspace)
+    return fail(FCN8_ERR_WORKSPACE, "bias_grad: workspace too small");
+  cudaError_t e = launch_bias_grad(p->dy, p->db, p->P, p->C, p->dtype, static_cast<float*>(workspace),
+                                   (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "bias_grad launch");
+}
+
+int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* stream) {
+  if (!p || !p->x || !p->K || !p->b || !p->s) return fail(FCN8_ERR_BAD_SHAPE, "head fwd: null pointer");
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head: num_classes=%d not in [1,32]", p->C);
+  cudaError_t e = launch_head_fwd(p->x, p->K, p->b, p->s, p->P, p->Cin, p->C, p->scale, p->dtype,
+                                  (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "head fwd launch");
+}
+size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p) {
+  const size_t nb = head_bwd_blocks(p->P);
+  return (nb * p->Cin * p->C + nb * p->C) * sizeof(float);
+}
+int32_t fcn8_score_head_bwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !p->x || !p->K || !p->s || !p->dK || !p->db) return fail(FCN8_ERR_BAD_SHAPE, "head bwd: null pointer");
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head: num_classes=%d not in [1,32]", p->C);
+  if (workspace_bytes < fcn8_score_head_bwd_workspace_bytes(p) || !workspace)
+    return fail(FCN8_ERR_WORKSPACE, "head bwd: workspace too small");
+  cudaError_t e = launch_head_bwd(p->x, p->K, p->s, p->dK, p->db, p->dx, p->P, p->Cin, p->C, p->scale, p->dtype,
+                                  p->mask, p->mask_scale, static_cast<float*>(workspace), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "head bwd launch");
+}
+
+static int check_upscore(const Fcn8UpscoreParams* p) {
+  if (!p || !p->x || !p->T || !p->y) return fail(FCN8_ERR_BAD_SHAPE, "upscore: null pointer");
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "upscore: num_classes=%d not in [1,32]", p->C);
+  if (p->stride < 2 || (p->stride & 1)) return fail(FCN8_ERR_BAD_SHAPE, "upscore: stride must be even");
+  if (p->N <= 0 || p->h <= 0 || p->w <= 0) return fail(FCN8_ERR_BAD_SHAPE, "upscore: empty tensor");
+  return 0;
+}
+int32_t fcn8_upscore_fwd(const Fcn8UpscoreParams* p, void* stream) {
+  int rc = check_upscore(p);
+  if (rc) return rc;
+  if (!p->bias) return fail(FCN8_ERR_BAD_SHAPE, "upscore fwd: bias missing");
+  cudaError_t e = launch_upscore_fwd(p->x, p->T, p->bias, p->skip, p->y, p->N, p->h, p->w, p->C, p->stride,
+                                     (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore fwd launch");
+}
+size_t fcn8_upscore_bwd_workspace_bytes(const Fcn8UpscoreParams* p) {
+  return upscore_bwd_ws_floats(p->N, p->h, p->w, p->C, p->stride) * sizeof(float);
+}
+int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_upscore(p);
+  if (rc) return rc;
+  if (!p->dT || !p->dbias) return fail(FCN8_ERR_BAD_SHAPE, "upscore bwd: dT / dbias missing");
+  if (workspace_bytes < fcn8_upscore_bwd_workspace_bytes(p) || !workspace)
+    return fail(FCN8_ERR_WORKSPACE, "upscore bwd: workspace too small");
+  cudaError_t e = launch_upscore_bwd(p->x, p->T, p->y, p->dx, p->dT, p->dbias, p->N, p->h, p->w, p->C, p->stride,
+                                     static_cast<float*>(workspace), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore bwd launch");
+}
+
+int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream) {
+  if (!p || !p->logits) return fail(FCN8_ERR_BAD_SHAPE, "softmax: null pointer");
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "softmax: num_classes=%d not in [1,32]", p->C);
+  if ((p->loss_sum || p->dlogits) && !p->labels) return fail(FCN8_ERR_BAD_SHAPE, "softmax: loss needs labels");
+  cudaError_t e = launch_softmax_xent(p->logits, p->labels, p->loss_sum, p->dlogits, p->softmax,
+                                      reinterpret_cast<long long*>(p->argmax), p->P, p->C, p->grad_scale,
+                                      (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "softmax launch");
+}
+
+int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot, unsigned long long* conf, int64_t P,
+                              int32_t C, void* stream) {
+  if (!pred || !labels_onehot || !conf) return fail(FCN8_ERR_BAD_SHAPE, "confusion: null pointer");
+  if (C < 1 || C > 32) return fail(FCN8_ERR_UNSUPPORTED, "confusion: num_classes=%d not in [1,32]", C);
+  cudaError_t e = launch_confusion(reinterpret_cast<const long long*>(pred), labels_onehot, conf, P, C,
+                                   (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "confusion launch");
+}
+
+int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v) return fail(FCN8_ERR_BAD_SHAPE, "adam: null pointer");
+  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v))
+    return fail(FCN8_ERR_BAD_ALIGN, "adam: pointers must be 16-byte aligned");
+  cudaError_t e = launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "adam launch");
+}
+int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float rate, void* stream) {
+  if (!w) return fail(FCN8_ERR_BAD_SHAPE, "l2_reg: null pointer");
+  cudaError_t e = launch_l2_reg(w, g, loss_sum, n, rate, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "l2_reg launch");
+}
+
+}  // extern "C"

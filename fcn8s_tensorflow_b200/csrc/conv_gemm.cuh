@@ -1,0 +1,607 @@
+// Implicit-GEMM convolution kernels on tcgen05 (sm_100a) -- device side.
+//
+//   conv_gemm_kernel : stride-1 SAME k x k convolution of an NHWC tensor as a GEMM
+//        D[pixels, Cout] = sum_{tap, cblock} A_tap[pixels, CH] * Bp[Cout, (tap, cblock)]^T
+//     used for fprop (Bp = packed forward weights) and for dgrad (Bp = rotated / in-out swapped weights).
+//     Replaces TF's Conv2D / Conv2DBackpropInput behind the external VGG-16 graph the reference loads at
+//     fcn8s_tensorflow.py:127-152 and differentiates at :256-257.
+//   wgrad_gemm_kernel : D[(tap, ci), co] = sum_{pixels} X[pixel + tap, ci] * dY[pixel, co]
+//     (TF's Conv2DBackpropFilter, implied by fcn8s_tensorflow.py:257), both operands MN-major.
+//
+// Shared design: one CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+// (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> global). Persistent over tiles, smem ring of
+// kStages operand stages, 2 accumulator stages in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// Everything is expressed in bytes: an operand row is always 128 B (64 bf16 or 32 tf32/fp32 values) with the
+// 128-byte swizzle, so one code path serves kind::f16 (bf16) and kind::tf32.
+#pragma once
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "ptx.cuh"
+
+namespace fcn8 {
+
+enum EpilogueFlags : int {
+  EPI_BIAS = 1,      // + bias[col]
+  EPI_RELU = 2,      // max(.,0)
+  EPI_DROPOUT = 4,   // * keep(seed, index) / keep_prob   (forward dropout, fcn8s_tensorflow.py:561 feeds keep_prob)
+  EPI_MASK = 8,      // * (mask_src[index] > 0) * mask_scale   (ReLU / dropout backward)
+  EPI_RESIDUAL = 16, // + residual[index]                      (gradient fan-in at pool3 / pool4)
+  EPI_PARTIAL = 32,  // raw fp32 partial sums to the split-K workspace, no epilogue math
+};
+
+// Counter-based uniform in [0,1): one 32-bit mix of (seed, element index). Shared by the forward dropout epilogue,
+// the split-K reduce epilogue and (host side, numpy) the parity tests that inject the same mask into the oracle.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t seed, uint64_t idx) {
+  uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B9u) ^ seed;
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  x += seed * 0x9E3779B9u;
+  x ^= x >> 15;
+  x *= 0x2c1b3c6du;
+  x ^= x >> 12;
+  return x;
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint64_t idx, uint32_t keep_threshold) {
+  // keep iff the top 24 bits are below keep_prob * 2^24
+  return (mix32(seed, idx) >> 8) < keep_threshold;
+}
+
+struct ConvGemmArgs {
+  void* out;             // [N,H,W,ldc] OutT
+  const float* bias;     // [ldc]
+  const void* mask_src;  // same shape/type as out
+  const void* residual;  // same shape/type as out
+  float* partial;        // [splits][N*H*W*ldc] fp32 (EPI_PARTIAL)
+  int N, H, W, ldc;
+  int taps, taps_w, pad;
+  int cblocks;  // Cin / CH
+  int nseg;     // 1, or 3 for the error-compensated tf32 product (hi*hi + hi*lo + lo*hi)
+  int lbw, lbh, lbn;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int splits, kb_per_split;
+  int flags;
+  float mask_scale;
+  float inv_keep;
+  uint32_t keep_threshold;
+  uint32_t seed;
+};
+
+struct TensorMaps3 {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = 128 * 128;  // 128 rows x 128 B
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 for manual alignment
+};
+
+constexpr int kGemmThreads = 192;
+
+template <bool TF32>
+__device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (TF32)
+    umma_tf32(d, a, b, idesc, acc);
+  else
+    umma_f16(d, a, b, idesc, acc);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Epilogue math on 32 consecutive columns of one output row. `idx` = element index of column c0 of this row.
+template <bool TF32>
+__device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0) {
+  using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (g.flags & EPI_PARTIAL) {
+    // handled by caller
+  }
+  if (g.flags & EPI_BIAS) {
+    const float4* b4 = reinterpret_cast<const float4*>(g.bias + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 b = __ldg(b4 + i);
+      f[4 * i + 0] += b.x;
+      f[4 * i + 1] += b.y;
+      f[4 * i + 2] += b.z;
+      f[4 * i + 3] += b.w;
+    }
+  }
+  if (g.flags & EPI_RESIDUAL) {
+    const OutT* r = reinterpret_cast<const OutT*>(g.residual) + idx;
+    if constexpr (TF32) {
+      const float4* r4 = reinterpret_cast<const float4*>(r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(r4 + i);
+        f[4 * i + 0] += b.x;
+        f[4 * i + 1] += b.y;
+        f[4 * i + 2] += b.z;
+        f[4 * i + 3] += b.w;
+      }
+    } else {
+      const uint4* r4 = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = __ldg(r4 + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __bfloat1622float2(h[j]);
+          f[8 * i + 2 * j] += t.x;
+          f[8 * i + 2 * j + 1] += t.y;
+        }
+      }
+    }
+  }
+  if (g.flags & EPI_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (g.flags & EPI_DROPOUT) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      f[i] = dropout_keep(g.seed, static_cast<uint64_t>(idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
+  }
+  if (g.flags & EPI_MASK) {
+    const OutT* m = reinterpret_cast<const OutT*>(g.mask_src) + idx;
+    if constexpr (TF32) {
+      const float4* m4 = reinterpret_cast<const float4*>(m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b = __ldg(m4 + i);
+        f[4 * i + 0] = b.x > 0.f ? f[4 * i + 0] * g.mask_scale : 0.f;
+        f[4 * i + 1] = b.y > 0.f ? f[4 * i + 1] * g.mask_scale : 0.f;
+        f[4 * i + 2] = b.z > 0.f ? f[4 * i + 2] * g.mask_scale : 0.f;
+        f[4 * i + 3] = b.w > 0.f ? f[4 * i + 3] * g.mask_scale : 0.f;
+      }
+    } else {
+      const uint4* m4 = reinterpret_cast<const uint4*>(m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = __ldg(m4 + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 t = __bfloat1622float2(h[j]);
+          f[8 * i + 2 * j] = t.x > 0.f ? f[8 * i + 2 * j] * g.mask_scale : 0.f;
+          f[8 * i + 2 * j + 1] = t.y > 0.f ? f[8 * i + 2 * j + 1] * g.mask_scale : 0.f;
+        }
+      }
+    }
+  }
+  OutT* o = reinterpret_cast<OutT*>(g.out) + idx;
+  if constexpr (TF32) {
+    float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                         pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* acc_full = empty_bar + Cfg::kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  const int total_tiles = m_tiles * g.tiles_n * g.splits;
+  const int kb_per_seg = g.taps * g.cblocks;
+  const int total_kb = g.nseg * kb_per_seg;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nb = t % g.tiles_n;
+        const int mt = (t / g.tiles_n) % m_tiles;
+        const int sp = t / (g.tiles_n * m_tiles);
+        const int tx = mt % g.tiles_x;
+        const int ty = (mt / g.tiles_x) % g.tiles_y;
+        const int tb = mt / (g.tiles_x * g.tiles_y);
+        const int x0 = tx << g.lbw, y0 = ty << g.lbh, n0 = tb << g.lbn;
+        const int kb0 = sp * g.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+        int seg = kb0 / kb_per_seg;
+        int rem = kb0 - seg * kb_per_seg;
+        int tap = rem / g.cblocks;
+        int cb = rem - tap * g.cblocks;
+        int kh = tap / g.taps_w;
+        int kw = tap - kh * g.taps_w;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
+          tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++cb == g.cblocks) {
+            cb = 0;
+            ++tap;
+            if (++kw == g.taps_w) {
+              kw = 0;
+              ++kh;
+            }
+            if (tap == g.taps) {
+              tap = 0;
+              kh = 0;
+              kw = 0;
+              ++seg;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, 0u, 128u, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t / (g.tiles_n * m_tiles);
+        const int kb0 = sp * g.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const size_t out_elems = static_cast<size_t>(g.N) * g.H * g.W * g.ldc;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nb = t % g.tiles_n;
+      const int mt = (t / g.tiles_n) % m_tiles;
+      const int sp = t / (g.tiles_n * m_tiles);
+      const int tx = mt % g.tiles_x;
+      const int ty = (mt / g.tiles_x) % g.tiles_y;
+      const int tb = mt / (g.tiles_x * g.tiles_y);
+      const int x = (tx << g.lbw) + (row & ((1 << g.lbw) - 1));
+      const int y = (ty << g.lbh) + ((row >> g.lbw) & ((1 << g.lbh) - 1));
+      const int n = (tb << g.lbn) + (row >> (g.lbw + g.lbh));
+      const bool valid = (x < g.W) && (y < g.H) && (n < g.N);
+      const size_t pix = (static_cast<size_t>(n) * g.H + y) * g.W + x;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int c0 = nb * BN + c;
+          const size_t idx = pix * g.ldc + c0;
+          if (g.flags & EPI_PARTIAL) {
+            float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+            epilogue_row32<TF32>(g, v, idx, c0);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad: D[(tap,ci) rows, co cols] = sum over pixels.  A = X (shifted per tap), B = dY, both MN-major:
+// a smem "chunk" is [64 pixels][128 B of channels], 128B-swizzled, exactly what a TMA box {CH, pbw, pbh, pbn} gives.
+struct WgradArgs {
+  float* out;      // [rows_valid, ldc] fp32 (HWIO flattened: row = tap*Cin + ci)
+  float* partial;  // [splits][rows_pad][ldc]
+  int N, H, W;
+  int Cin, ldc;  // ldc = Cout
+  int taps, taps_w, pad;
+  int nseg;
+  int rows_valid;    // taps*Cin, or 27 for the im2col'ed conv1_1
+  int total_chunks;  // taps*Cin/CH
+  int m_tiles, tiles_n;
+  int lbw, lbh, lbn;           // 64-pixel patch
+  int pb_x, pb_y, pb_b;        // pixel blocks per dim
+  int splits, pb_per_split;
+  int flags;  // EPI_PARTIAL or 0
+};
+
+template <int BN, bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int CH = TF32 ? 32 : 64;
+  constexpr int kChunkBytes = 64 * 128;        // 64 pixels x 128 B
+  constexpr int MCH = 128 / CH;                // A chunks per M tile
+  constexpr int NCH = BN / CH;                 // B chunks per N tile
+  constexpr int kAStage = MCH * kChunkBytes;   // 16 KB bf16 / 32 KB tf32
+  constexpr int kBStage = NCH * kChunkBytes;
+  constexpr int kStage = kAStage + kBStage;
+  constexpr int kStages = (200 * 1024) / kStage;
+  constexpr int KPM = TF32 ? 8 : 16;           // K (pixels) per MMA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + kStages * kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.m_tiles * g.tiles_n * g.splits;
+  const int pb_per_seg = g.pb_x * g.pb_y * g.pb_b;
+  const int total_pb = g.nseg * pb_per_seg;
+  const int cin_chunks = g.Cin / CH;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nb = t % g.tiles_n;
+        const int mt = (t / g.tiles_n) % g.m_tiles;
+        const int sp = t / (g.tiles_n * g.m_tiles);
+        // per-chunk tap offsets for this M tile
+        int ccb[MCH], cdx[MCH], cdy[MCH];
+        int nvalid = 0;
+#pragma unroll
+        for (int c = 0; c < MCH; ++c) {
+          const int gch = mt * MCH + c;
+          if (gch < g.total_chunks) {
+            const int tap = gch / cin_chunks;
+            ccb[c] = (gch - tap * cin_chunks) * CH;
+            cdy[c] = tap / g.taps_w - g.pad;
+            cdx[c] = tap % g.taps_w - g.pad;
+            nvalid = c + 1;
+          } else {
+            ccb[c] = 0;
+            cdx[c] = 0;
+            cdy[c] = 0;
+          }
+        }
+        const uint32_t tx_bytes = nvalid * kChunkBytes + kBStage;
+        const int pb0 = sp * g.pb_per_split;
+        const int pb1 = min(total_pb, pb0 + g.pb_per_split);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int seg = pb / pb_per_seg;
+          const int r = pb - seg * pb_per_seg;
+          const int bx = r % g.pb_x;
+          const int by = (r / g.pb_x) % g.pb_y;
+          const int bb = r / (g.pb_x * g.pb_y);
+          const int x0 = bx << g.lbw, y0 = by << g.lbh, n0 = bb << g.lbn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStage;
+          uint8_t* sb = sa + kAStage;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+          for (int c = 0; c < MCH; ++c)
+            if (c < nvalid)
+              tma_load_4d(&maps.a[seg], &full_bar[stage], sa + c * kChunkBytes, ccb[c], x0 + cdx[c], y0 + cdy[c], n0);
+#pragma unroll
+          for (int j = 0; j < NCH; ++j)
+            tma_load_4d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, nb * BN + j * CH, x0, y0, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int sp = t / (g.tiles_n * g.m_tiles);
+        const int pb0 = sp * g.pb_per_split;
+        const int pb1 = min(total_pb, pb0 + g.pb_per_split);
+        mbar_wait(&acc_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int pb = pb0; pb < pb1; ++pb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStage);
+          const uint32_t sb = sa + kAStage;
+          // MN-major, 128B swizzle: LBO = stride between 128-byte channel chunks, SBO = stride between 8-pixel groups
+          const uint64_t adesc = make_smem_desc_sw128(sa, kChunkBytes, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, kChunkBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < 64 / KPM; ++k) {
+            const uint32_t adv = (k * KPM * 128) >> 4;
+            umma_issue<TF32>(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const size_t rows_pad = static_cast<size_t>(g.m_tiles) * 128;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nb = t % g.tiles_n;
+      const int mt = (t / g.tiles_n) % g.m_tiles;
+      const int sp = t / (g.tiles_n * g.m_tiles);
+      const int grow = mt * 128 + row;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      float* dst = (g.flags & EPI_PARTIAL) ? g.partial + (static_cast<size_t>(sp) * rows_pad + grow) * g.ldc
+                                           : g.out + static_cast<size_t>(grow) * g.ldc;
+      const bool valid = (g.flags & EPI_PARTIAL) ? true : (grow < g.rows_valid);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* o4 = reinterpret_cast<float4*>(dst + nb * BN + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace fcn8

@@ -1,0 +1,498 @@
+// FCN-8s decoder kernels (fcn8s_tensorflow.py:154-237), loss / predictor (:253, :268-269) and metrics (:280-301).
+// The decoder is 0.4 % of the step's FLOPs and HBM-bound (C = num_classes channels per pixel), so these are fp32
+// CUDA-core kernels organised for coalescing and shared-memory reuse of the small filter tensors.
+// Limit: num_classes <= 32 (register tiles); larger C returns FCN8_ERR_UNSUPPORTED at the C ABI.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace fcn8 {
+
+constexpr int CMAX = 32;
+
+static inline int grid_for(size_t work, int threads, int max_blocks = 148 * 16) {
+  size_t b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > static_cast<size_t>(max_blocks)) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+template <typename T>
+__device__ __forceinline__ float ld_act(const T* p) {
+  if constexpr (sizeof(T) == 2)
+    return __bfloat162float(*p);
+  else
+    return *p;
+}
+template <typename T>
+__device__ __forceinline__ void st_act(T* p, float v) {
+  if constexpr (sizeof(T) == 2)
+    *p = __float2bfloat16_rn(v);
+  else
+    *p = v;
+}
+
+// ------------------------------------------------------------------------------------------------ score heads
+// One warp per pixel: lanes stride over Cin, each keeps C partial sums, then a butterfly reduction.
+template <typename T>
+__global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
+                                float* __restrict__ s, long long P, int Cin, int C, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long p = warp0; p < P; p += nwarps) {
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+    const T* xp = x + p * Cin;
+    for (int ci = lane; ci < Cin; ci += 32) {
+      const float xv = ld_act(xp + ci);
+      const float* kr = K + static_cast<size_t>(ci) * C;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) acc[c] = fmaf(xv, __ldg(kr + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        float v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[c] = v;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) s[p * C + c] = scale * acc[c] + b[c];
+    }
+  }
+}
+
+// dK / db partials: block (bx, by) covers pixels [bx*ppb, ...) and input channels [by*blockDim, ...).
+template <typename T>
+__global__ void head_bwd_w_kernel(const T* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws,
+                                  long long P, int Cin, int C, long long ppb) {
+  __shared__ float sds[64][CMAX];
+  const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long p0 = blockIdx.x * ppb;
+  const long long p1 = (p0 + ppb < P) ? p0 + ppb : P;
+  float acc[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+  for (long long pc = p0; pc < p1; pc += 64) {
+    const int np = static_cast<int>((p1 - pc < 64) ? (p1 - pc) : 64);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * C; i += blockDim.x) sds[i / C][i % C] = ds[pc * C + i];
+    __syncthreads();
+    if (ci < Cin) {
+      for (int q = 0; q < np; ++q) {
+        const float xv = ld_act(x + (pc + q) * Cin + ci);
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) acc[c] = fmaf(xv, sds[q][c], acc[c]);
+      }
+    }
+  }
+  if (ci < Cin) {
+    float* o = ws + (static_cast<size_t>(blockIdx.x) * Cin + ci) * C;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) o[c] = acc[c];
+  }
+}
+// column sums of ds [P][C] -> partial [nb][C]
+__global__ void rows_colsum_kernel(const float* __restrict__ ds, float* __restrict__ ws, long long P, int C,
+                                   long long ppb) {
+  const long long p0 = blockIdx.x * ppb;
+  const long long p1 = (p0 + ppb < P) ? p0 + ppb : P;
+  __shared__ float red[256];
+  // thread t handles column t % C, row lane t / C
+  const int c = threadIdx.x % C;
+  const int rl = threadIdx.x / C;
+  const int RL = blockDim.x / C;
+  float a = 0.f;
+  if (rl < RL)
+    for (long long p = p0 + rl; p < p1; p += RL) a += ds[p * C + c];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int k = 0; k < RL; ++k) t += red[k * C + threadIdx.x];
+    ws[static_cast<size_t>(blockIdx.x) * C + threadIdx.x] = t;
+  }
+}
+// dx[p][ci] = scale * sum_c ds[p][c] * K[ci][c]  (* relu/dropout mask of x)
+template <typename T>
+__global__ void head_bwd_x_kernel(const T* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
+                                  T* __restrict__ dx, long long P, int Cin, int C, float scale, int mask,
+                                  float mask_scale) {
+  const size_t total = static_cast<size_t>(P) * Cin;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const long long p = i / Cin;
+    const int ci = static_cast<int>(i - p * Cin);
+    const float* kr = K + static_cast<size_t>(ci) * C;
+    const float* dp = ds + p * C;
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) a = fmaf(__ldg(dp + c), __ldg(kr + c), a);
+    a *= scale;
+    if (mask) a = (ld_act(x + i) > 0.f) ? a * mask_scale : 0.f;
+    st_act(dx + i, a);
+  }
+}
+
+cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
+                            float scale, int dtype, cudaStream_t st) {
+  const int blocks = grid_for(static_cast<size_t>(P) * 32, 256);
+  if (dtype == 0)
+    head_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, b, s, P, Cin, C,
+                                                           scale);
+  else
+    head_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, b, s, P, Cin, C, scale);
+  return cudaGetLastError();
+}
+int head_bwd_blocks(long long P) {
+  long long nb = (P + 127) / 128;
+  if (nb > 128) nb = 128;
+  if (nb < 1) nb = 1;
+  return static_cast<int>(nb);
+}
+cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, float* dK, float* db, void* dx,
+                            long long P, int Cin, int C, float scale, int dtype, int mask, float mask_scale, float* ws,
+                            cudaStream_t st) {
+  const int nb = head_bwd_blocks(P);
+  const long long ppb = (P + nb - 1) / nb;
+  float* ws_k = ws;                                          // [nb][Cin][C]
+  float* ws_b = ws + static_cast<size_t>(nb) * Cin * C;      // [nb][C]
+  dim3 grid(nb, (Cin + 255) / 256);
+  if (dtype == 0)
+    head_bwd_w_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ds, ws_k, P, Cin, C,
+                                                           ppb);
+  else
+    head_bwd_w_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ds, ws_k, P, Cin, C, ppb);
+  rows_colsum_kernel<<<nb, 256, 0, st>>>(ds, ws_b, P, C, ppb);
+  cudaError_t e = launch_colsum(ws_k, dK, nb, Cin * C, scale, 0, st);
+  if (e != cudaSuccess) return e;
+  e = launch_colsum(ws_b, db, nb, C, 1.f, 0, st);
+  if (e != cudaSuccess) return e;
+  if (dx) {
+    const int blocks = grid_for(static_cast<size_t>(P) * Cin, 256);
+    if (dtype == 0)
+      head_bwd_x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, ds,
+                                                               static_cast<__nv_bfloat16*>(dx), P, Cin, C, scale, mask,
+                                                               mask_scale);
+    else
+      head_bwd_x_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, ds, static_cast<float*>(dx), P,
+                                                       Cin, C, scale, mask, mask_scale);
+  }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ transposed conv
+// Phase decomposition: for stride s, kernel 2s, pad s/2, the output pixel (s*J - p + dy, s*I - p + dx)
+// of block (J, I), J in [0,h], I in [0,w], depends on the 2x2 inputs (J-1+ty, I-1+tx) through taps
+// a = dy + s*(1-ty), b = dx + s*(1-tx).  One CTA handles one phase (dy,dx): its 4 filter slices [4][C][C] live in
+// shared memory and every thread produces all C channels of one output pixel.
+__global__ void upscore_fwd_kernel(const float* __restrict__ x, const float* __restrict__ T,
+                                   const float* __restrict__ bias, const float* __restrict__ skip,
+                                   float* __restrict__ y, int N, int h, int w, int C, int s) {
+  extern __shared__ float sT[];  // [4][C][C]  (tap = ty*2+tx, co, ci)
+  const int p = s / 2, k = 2 * s;
+  const int dy = blockIdx.y / s, dx = blockIdx.y % s;
+  for (int i = threadIdx.x; i < 4 * C * C; i += blockDim.x) {
+    const int tap = i / (C * C), r = i % (C * C);
+    const int ty = tap >> 1, tx = tap & 1;
+    const int a = dy + s * (1 - ty), b = dx + s * (1 - tx);
+    sT[i] = T[(static_cast<size_t>(a) * k + b) * C * C + r];
+  }
+  __syncthreads();
+  const int HB = h + 1, WB = w + 1;
+  const int H = h * s, W = w * s;
+  const size_t total = static_cast<size_t>(N) * HB * WB;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int I = static_cast<int>(i % WB);
+    const int J = static_cast<int>((i / WB) % HB);
+    const int n = static_cast<int>(i / (static_cast<size_t>(WB) * HB));
+    const int oy = s * J - p + dy, ox = s * I - p + dx;
+    if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = (c < C) ? bias[c] : 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int iy = J - 1 + (tap >> 1), ix = I - 1 + (tap & 1);
+      if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+      const float* xp = x + ((static_cast<size_t>(n) * h + iy) * w + ix) * C;
+      const float* tp = sT + tap * C * C;
+      for (int ci = 0; ci < C; ++ci) {
+        const float xv = __ldg(xp + ci);
+#pragma unroll
+        for (int co = 0; co < CMAX; ++co)
+          if (co < C) acc[co] = fmaf(xv, tp[co * C + ci], acc[co]);
+      }
+    }
+    const size_t o = ((static_cast<size_t>(n) * H + oy) * W + ox) * C;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) y[o + c] = acc[c] + (skip ? skip[o + c] : 0.f);
+  }
+}
+
+// dx[n,i,j,ci] = sum_{a,b,co} dy[n, s*i+a-p, s*j+b-p, co] * T[a,b,co,ci]; one thread per input pixel, filter rows
+// staged through shared memory one `a` at a time.
+__global__ void upscore_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ T, float* __restrict__ dx,
+                                     int N, int h, int w, int C, int s) {
+  extern __shared__ float sT[];  // [k][C][C] for the current a
+  const int p = s / 2, k = 2 * s;
+  const int H = h * s, W = w * s;
+  const size_t total = static_cast<size_t>(N) * h * w;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const bool active = i < total;
+  const int jx = static_cast<int>(i % w);
+  const int iy = static_cast<int>((i / w) % h);
+  const int n = static_cast<int>(i / (static_cast<size_t>(w) * h));
+  float acc[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
+  for (int a = 0; a < k; ++a) {
+    __syncthreads();
+    for (int q = threadIdx.x; q < k * C * C; q += blockDim.x) sT[q] = T[static_cast<size_t>(a) * k * C * C + q];
+    __syncthreads();
+    const int oy = s * iy + a - p;
+    if (!active || oy < 0 || oy >= H) continue;
+    for (int b = 0; b < k; ++b) {
+      const int ox = s * jx + b - p;
+      if (ox < 0 || ox >= W) continue;
+      const float* dp = dy + ((static_cast<size_t>(n) * H + oy) * W + ox) * C;
+      const float* tp = sT + b * C * C;
+      for (int co = 0; co < C; ++co) {
+        const float g = __ldg(dp + co);
+#pragma unroll
+        for (int ci = 0; ci < CMAX; ++ci)
+          if (ci < C) acc[ci] = fmaf(g, tp[co * C + ci], acc[ci]);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) dx[i * C + c] = acc[c];
+  }
+}
+
+// dT[a,b,co,ci] partials: CTA (tap, split) reduces its share of the input pixels; thread owns a 2x2 (co,ci) tile.
+__global__ void upscore_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ ws,
+                                     int N, int h, int w, int C, int s, int nsplit) {
+  __shared__ float sx[32][CMAX];
+  __shared__ float sg[32][CMAX];
+  const int p = s / 2, k = 2 * s;
+  const int H = h * s, W = w * s;
+  const int tap = blockIdx.x;
+  const int a = tap / k, b = tap % k;
+  const int CT = (C + 1) / 2;
+  const int tco = (threadIdx.x / CT) * 2, tci = (threadIdx.x % CT) * 2;
+  const bool owner = threadIdx.x < CT * CT;
+  float acc00 = 0.f, acc01 = 0.f, acc10 = 0.f, acc11 = 0.f;
+  const long long total = static_cast<long long>(N) * h * w;
+  const long long per = (total + nsplit - 1) / nsplit;
+  const long long q0 = blockIdx.y * per;
+  const long long q1 = (q0 + per < total) ? q0 + per : total;
+  for (long long qc = q0; qc < q1; qc += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * C; t += blockDim.x) {
+      const int r = t / C, c = t % C;
+      const long long q = qc + r;
+      float xv = 0.f, gv = 0.f;
+      if (q < q1) {
+        const int jx = static_cast<int>(q % w);
+        const int iy = static_cast<int>((q / w) % h);
+        const int n = static_cast<int>(q / (static_cast<long long>(w) * h));
+        const int oy = s * iy + a - p, ox = s * jx + b - p;
+        if (oy >= 0 && oy < H && ox >= 0 && ox < W) {
+          xv = x[q * C + c];
+          gv = dy[((static_cast<size_t>(n) * H + oy) * W + ox) * C + c];
+        }
+      }
+      sx[r][c] = xv;
+      sg[r][c] = gv;
+    }
+    __syncthreads();
+    if (owner) {
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const float g0 = sg[r][tco], g1 = sg[r][tco + 1];
+        const float x0 = sx[r][tci], x1 = sx[r][tci + 1];
+        acc00 = fmaf(g0, x0, acc00);
+        acc01 = fmaf(g0, x1, acc01);
+        acc10 = fmaf(g1, x0, acc10);
+        acc11 = fmaf(g1, x1, acc11);
+      }
+    }
+  }
+  if (owner) {
+    float* o = ws + (static_cast<size_t>(blockIdx.y) * k * k + tap) * C * C;
+    o[tco * C + tci] = acc00;
+    if (tci + 1 < C) o[tco * C + tci + 1] = acc01;
+    if (tco + 1 < C) {
+      o[(tco + 1) * C + tci] = acc10;
+      if (tci + 1 < C) o[(tco + 1) * C + tci + 1] = acc11;
+    }
+  }
+}
+
+cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias, const float* skip, float* y, int N,
+                               int h, int w, int C, int s, cudaStream_t st) {
+  const size_t blocks_total = static_cast<size_t>(N) * (h + 1) * (w + 1);
+  int gx = grid_for(blocks_total, 128, (148 * 8) / (s * s) + 1);
+  dim3 grid(gx, s * s);
+  const size_t sm = static_cast<size_t>(4) * C * C * sizeof(float);
+  upscore_fwd_kernel<<<grid, 128, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s);
+  return cudaGetLastError();
+}
+int upscore_bwd_splits(int N, int h, int w, int s) {
+  const long long total = static_cast<long long>(N) * h * w;
+  const int taps = 4 * s * s;
+  long long want = (148 * 4 + taps - 1) / taps;
+  long long maxs = (total + 255) / 256;
+  if (want > maxs) want = maxs;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, float* dx, float* dT, float* dbias,
+                               int N, int h, int w, int C, int s, float* ws, cudaStream_t st) {
+  const int k = 2 * s;
+  const long long Pout = static_cast<long long>(N) * h * s * w * s;
+  // dbias
+  {
+    const int nb = head_bwd_blocks(Pout);
+    const long long ppb = (Pout + nb - 1) / nb;
+    rows_colsum_kernel<<<nb, 256, 0, st>>>(dy, ws, Pout, C, ppb);
+    cudaError_t e = launch_colsum(ws, dbias, nb, C, 1.f, 0, st);
+    if (e != cudaSuccess) return e;
+  }
+  // dT
+  {
+    const int nsplit = upscore_bwd_splits(N, h, w, s);
+    dim3 grid(k * k, nsplit);
+    upscore_bwd_w_kernel<<<grid, 256, 0, st>>>(x, dy, ws + 128 * CMAX, N, h, w, C, s, nsplit);
+    cudaError_t e = launch_colsum(ws + 128 * CMAX, dT, nsplit, k * k * C * C, 1.f, 0, st);
+    if (e != cudaSuccess) return e;
+  }
+  if (dx) {
+    const size_t total = static_cast<size_t>(N) * h * w;
+    const size_t sm = static_cast<size_t>(k) * C * C * sizeof(float);
+    cudaFuncSetAttribute(upscore_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
+    upscore_bwd_x_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, sm, st>>>(dy, T, dx, N, h, w, C, s);
+  }
+  return cudaGetLastError();
+}
+size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s) {
+  return static_cast<size_t>(128) * CMAX + static_cast<size_t>(upscore_bwd_splits(N, h, w, s)) * 4 * s * s * C * C;
+}
+
+// ------------------------------------------------------------------------------------------------ softmax / xent
+__global__ void softmax_xent_kernel(const float* __restrict__ z, const uint8_t* __restrict__ labels,
+                                    float* __restrict__ loss_sum, float* __restrict__ dz, float* __restrict__ sm,
+                                    long long* __restrict__ amax, long long P, int C, float gscale) {
+  float local = 0.f;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[CMAX];
+    float mx = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        v[c] = z[p * C + c];
+        if (v[c] > mx) {
+          mx = v[c];
+          am = c;
+        }
+      }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) {
+        v[c] = expf(v[c] - mx);
+        se += v[c];
+      }
+    const float inv = 1.f / se;
+    if (amax) amax[p] = am;
+    if (sm) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) sm[p * C + c] = v[c] * inv;
+    }
+    if (labels) {
+      const float lse = mx + logf(se);
+      float ysum = 0.f, yz = 0.f;
+      float yv[CMAX];
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          yv[c] = static_cast<float>(labels[p * C + c]);
+          ysum += yv[c];
+          yz += yv[c] * z[p * C + c];
+        }
+      local += ysum * lse - yz;
+      if (dz) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) dz[p * C + c] = (v[c] * inv * ysum - yv[c]) * gscale;
+      }
+    }
+  }
+  if (loss_sum) {
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ float wsum[8];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) t += wsum[k];
+      atomicAdd(loss_sum, t);
+    }
+  }
+}
+cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* sm,
+                                long long* amax, long long P, int C, float gscale, cudaStream_t st) {
+  softmax_xent_kernel<<<grid_for(P, 256, 148 * 8), 256, 0, st>>>(z, labels, loss_sum, dz, sm, amax, P, C, gscale);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ confusion matrix
+__global__ void confusion_kernel(const long long* __restrict__ pred, const uint8_t* __restrict__ onehot,
+                                 unsigned long long* __restrict__ conf, long long P, int C) {
+  __shared__ unsigned int hist[CMAX * CMAX];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int gt = 0;
+    uint8_t best = 0;
+    for (int c = 0; c < C; ++c) {
+      const uint8_t v = onehot[p * C + c];
+      if (v > best) {
+        best = v;
+        gt = c;
+      }
+    }
+    const int pr = static_cast<int>(pred[p]);
+    atomicAdd(&hist[gt * C + pr], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (hist[i]) atomicAdd(&conf[i], static_cast<unsigned long long>(hist[i]));
+}
+cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
+                             cudaStream_t st) {
+  confusion_kernel<<<grid_for(P, 256, 148 * 4), 256, 0, st>>>(pred, onehot, conf, P, C);
+  return cudaGetLastError();
+}
+
+}  // namespace fcn8

@@ -1,0 +1,535 @@
+// HBM-bound helper kernels of the FCN-8s step: feed pre-processing, pooling, bias gradient, weight packing,
+// split-K reduction, Adam.  All are coalesced, 128-bit vectorised grid-stride kernels; none has data reuse that
+// would justify shared-memory staging except the packing transpose.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_gemm.cuh"
+#include "kernels.h"
+
+namespace fcn8 {
+
+static inline int grid_for(size_t work, int threads, int max_blocks = 148 * 16) {
+  size_t b = (work + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > static_cast<size_t>(max_blocks)) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------------------------------ preprocess
+// One thread per 16-byte output vector (8 bf16 / 4 fp32 im2col columns).
+template <typename T>
+__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, int N, int H, int W) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int KP = 128 / sizeof(T);  // padded im2col width: one 128-byte operand row
+  constexpr int VPP = KP / VEC;        // vectors per pixel (8)
+  const size_t total = static_cast<size_t>(N) * H * W * VPP;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % VPP);
+    const size_t pix = i / VPP;
+    const int x = static_cast<int>(pix % W);
+    const int y = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float f[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const int col = v * VEC + e;
+      float val = 0.f;
+      if (col < 27) {
+        const int tap = col / 3, c = col - tap * 3;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          // c = 0,1,2 -> B,G,R = RGB channel 2,1,0 minus the ImageNet means
+          const float mean = (c == 0) ? 103.939f : (c == 1 ? 116.779f : 123.68f);
+          val = static_cast<float>(img[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + (2 - c)]) - mean;
+        }
+      }
+      f[e] = val;
+    }
+    if constexpr (sizeof(T) == 2) {
+      uint4 q = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                           pack_bf16x2(f[6], f[7]));
+      reinterpret_cast<uint4*>(out)[i] = q;
+    } else {
+      reinterpret_cast<float4*>(out)[i] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * H * W * 8;
+  const int blocks = grid_for(total, 256);
+  if (dtype == 0)
+    preprocess_im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(out), N, H, W);
+  else
+    preprocess_im2col_kernel<float><<<blocks, 256, 0, st>>>(img, static_cast<float*>(out), N, H, W);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ vector helpers
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = __bfloat1622float2(h[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    float4 q = *reinterpret_cast<const float4*>(p);
+    f[0] = q.x;
+    f[1] = q.y;
+    f[2] = q.z;
+    f[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ max pool
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  using V = Vec16<T>;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    size_t r = i / CV;
+    const int xo = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int yo = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float m[V::N];
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) m[e] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * yo + dy, xx = 2 * xo + dx;
+        if (yy < H && xx < W) {
+          float f[V::N];
+          V::load(x + ((static_cast<size_t>(n) * H + yy) * W + xx) * C + cv * V::N, f);
+#pragma unroll
+          for (int e = 0; e < V::N; ++e) m[e] = fmaxf(m[e], f[e]);
+        }
+      }
+    V::store(y + i * V::N, m);
+  }
+}
+
+// dx[window position] = dy if it is the first maximum of the window (scan order) and x > 0, else 0.
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
+                                   int W, int C) {
+  using V = Vec16<T>;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    size_t r = i / CV;
+    const int xo = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int yo = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float g[V::N];
+    V::load(dy + i * V::N, g);
+    float f[4][V::N];
+    bool inb[4];
+    size_t off[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+      inb[k] = (yy < H) && (xx < W);
+      off[k] = ((static_cast<size_t>(n) * H + yy) * W + xx) * C + cv * V::N;
+      if (inb[k]) {
+        V::load(x + off[k], f[k]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) f[k][e] = -INFINITY;
+      }
+    }
+    float o[4][V::N];
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) {
+      int best = 0;
+      float bm = f[0][e];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (f[k][e] > bm) {
+          bm = f[k][e];
+          best = k;
+        }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][e] = (k == best && bm > 0.f) ? g[e] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (inb[k]) V::store(dx + off[k], o[k]);
+  }
+}
+
+cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st) {
+  const int vec = dtype == 0 ? 8 : 4;
+  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
+  const int blocks = grid_for(total, 256);
+  if (dtype == 0)
+    maxpool_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<__nv_bfloat16*>(y), N, H, W, C);
+  else
+    maxpool_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), N, H, W,
+                                                      C);
+  return cudaGetLastError();
+}
+cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                               cudaStream_t st) {
+  const int vec = dtype == 0 ? 8 : 4;
+  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
+  const int blocks = grid_for(total, 256);
+  if (dtype == 0)
+    maxpool_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<const __nv_bfloat16*>(dy),
+                                                              static_cast<__nv_bfloat16*>(dx), N, H, W, C);
+  else
+    maxpool_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy),
+                                                      static_cast<float*>(dx), N, H, W, C);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ bias gradient
+// Stage 1: block (bx, by) sums rows [bx*rpb, (bx+1)*rpb) of column-vector group by into ws[bx][C].
+template <typename T>
+__global__ void bias_grad_stage1(const T* __restrict__ dy, float* __restrict__ ws, long long P, int C, int cvb,
+                                 long long rpb) {
+  using V = Vec16<T>;
+  extern __shared__ float sred[];  // [RL][cvb*VN]
+  const int RL = blockDim.x / cvb;
+  const int cvl = threadIdx.x % cvb;
+  const int rl = threadIdx.x / cvb;
+  const int cv = blockIdx.y * cvb + cvl;
+  float acc[V::N];
+#pragma unroll
+  for (int e = 0; e < V::N; ++e) acc[e] = 0.f;
+  const long long r0 = blockIdx.x * rpb;
+  const long long r1 = (r0 + rpb < P) ? r0 + rpb : P;
+  if (rl < RL) {
+    for (long long r = r0 + rl; r < r1; r += RL) {
+      float f[V::N];
+      V::load(dy + static_cast<size_t>(r) * C + cv * V::N, f);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) acc[e] += f[e];
+    }
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) sred[(rl * cvb + cvl) * V::N + e] = acc[e];
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < RL; ++k)
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) acc[e] += sred[(k * cvb + cvl) * V::N + e];
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) ws[static_cast<size_t>(blockIdx.x) * C + cv * V::N + e] = acc[e];
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ ws, float* __restrict__ out, int nb, int C, float scale,
+                              int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += ws[static_cast<size_t>(b) * C + c];
+  s *= scale;
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+int bias_grad_blocks(long long P, int C) {
+  long long nb = (P + 255) / 256;
+  if (nb > 592) nb = 592;
+  if (nb < 1) nb = 1;
+  return static_cast<int>(nb);
+}
+cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st) {
+  const int vec = dtype == 0 ? 8 : 4;
+  const int CV = C / vec;
+  const int cvb = CV < 256 ? CV : 256;
+  const int nb = bias_grad_blocks(P, C);
+  const long long rpb = (P + nb - 1) / nb;
+  dim3 grid(nb, CV / cvb);
+  const int RL = 256 / cvb;
+  const size_t sm = static_cast<size_t>(RL) * cvb * vec * sizeof(float);
+  if (dtype == 0)
+    bias_grad_stage1<__nv_bfloat16><<<grid, 256, sm, st>>>(static_cast<const __nv_bfloat16*>(dy), ws, P, C, cvb, rpb);
+  else
+    bias_grad_stage1<float><<<grid, 256, sm, st>>>(static_cast<const float*>(dy), ws, P, C, cvb, rpb);
+  colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, db, nb, C, 1.f, 0);
+  return cudaGetLastError();
+}
+cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st) {
+  colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, out, nb, C, scale, accumulate);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <typename T>
+__device__ __forceinline__ void store_packed(T* out, T* out_lo, size_t idx, float v) {
+  if constexpr (sizeof(T) == 2) {
+    out[idx] = __float2bfloat16_rn(v);
+  } else {
+    if (out_lo) {
+      const float h = tf32_hi(v);
+      out[idx] = h;
+      out_lo[idx] = v - h;
+    } else {
+      out[idx] = v;
+    }
+  }
+}
+
+// mode 0: out[co][tap*CinPad + ci] = w[(tap*Cin + ci)*Cout + co]; 32x32 smem transpose per (tap, ci-tile, co-tile).
+template <typename T>
+__global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ out, T* __restrict__ out_lo, int taps,
+                                  int Cin, int Cout, int CinPad) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    tile[r][threadIdx.x] = (ci < Cin && co < Cout) ? w[(static_cast<size_t>(tap) * Cin + ci) * Cout + co] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < CinPad)
+      store_packed<T>(out, out_lo, static_cast<size_t>(co) * taps * CinPad + static_cast<size_t>(tap) * CinPad + ci,
+                      tile[threadIdx.x][r]);
+  }
+}
+// mode 1: out[ci][tap'*Cout + co] = w[((taps-1-tap')*Cin + ci)*Cout + co]
+template <typename T>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, T* __restrict__ out_lo, int taps,
+                                  int Cin, int Cout) {
+  const size_t total = static_cast<size_t>(taps) * Cin * Cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);
+    const size_t r = i / Cout;
+    const int tp = static_cast<int>(r % taps);
+    const int ci = static_cast<int>(r / taps);
+    store_packed<T>(out, out_lo, i, w[(static_cast<size_t>(taps - 1 - tp) * Cin + ci) * Cout + co]);
+  }
+}
+
+cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int Cin, int Cout, int CinPad, int mode,
+                        int dtype, cudaStream_t st) {
+  const int taps = ksize * ksize;
+  if (mode == 0) {
+    dim3 grid((Cout + 31) / 32, (CinPad + 31) / 32, taps), block(32, 8);
+    if (dtype == 0)
+      pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+                                                               Cout, CinPad);
+    else
+      pack_fprop_kernel<float><<<grid, block, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+                                                       Cin, Cout, CinPad);
+  } else {
+    const size_t total = static_cast<size_t>(taps) * Cin * Cout;
+    const int blocks = grid_for(total, 256);
+    if (dtype == 0)
+      pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+                                                               Cout);
+    else
+      pack_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+                                                       Cin, Cout);
+  }
+  return cudaGetLastError();
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                  size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  split_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, hi, lo, n / 4);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ split-K reduce
+// conv: out = epilogue(sum_s partial[s][i]); same flag semantics as the in-kernel epilogue (epilogue_row32).
+template <typename T>
+__global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n_elems, int ldc,
+                                          ConvGemmArgs g) {
+  using V = Vec16<T>;
+  const size_t nv = n_elems / V::N;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t idx = i * V::N;
+    float f[V::N];
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) f[e] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+#pragma unroll
+      for (int q = 0; q < V::N / 4; ++q) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + static_cast<size_t>(s) * n_elems + idx + 4 * q);
+        f[4 * q] += p.x;
+        f[4 * q + 1] += p.y;
+        f[4 * q + 2] += p.z;
+        f[4 * q + 3] += p.w;
+      }
+    }
+    const int c0 = static_cast<int>(idx % ldc);
+    if (g.flags & EPI_BIAS) {
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) f[e] += g.bias[c0 + e];
+    }
+    if (g.flags & EPI_RESIDUAL) {
+      float r[V::N];
+      V::load(reinterpret_cast<const T*>(g.residual) + idx, r);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) f[e] += r[e];
+    }
+    if (g.flags & EPI_RELU) {
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) f[e] = fmaxf(f[e], 0.f);
+    }
+    if (g.flags & EPI_DROPOUT) {
+#pragma unroll
+      for (int e = 0; e < V::N; ++e)
+        f[e] = dropout_keep(g.seed, static_cast<uint64_t>(idx) + e, g.keep_threshold) ? f[e] * g.inv_keep : 0.f;
+    }
+    if (g.flags & EPI_MASK) {
+      float m[V::N];
+      V::load(reinterpret_cast<const T*>(g.mask_src) + idx, m);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) f[e] = m[e] > 0.f ? f[e] * g.mask_scale : 0.f;
+    }
+    V::store(reinterpret_cast<T*>(g.out) + idx, f);
+  }
+}
+cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n_elems, int ldc,
+                                      const ConvGemmArgs& g, int dtype, cudaStream_t st) {
+  const int vec = dtype == 0 ? 8 : 4;
+  const int blocks = grid_for(n_elems / vec, 256);
+  if (dtype == 0)
+    conv_splitk_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g);
+  else
+    conv_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g);
+  return cudaGetLastError();
+}
+
+// wgrad: out[r][c] = sum_s partial[s][r][c] for r < rows_valid (partial has rows_pad rows per split).
+__global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
+                                           size_t rows_pad, int rows_valid, int ldc) {
+  const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
+  const size_t split_stride = rows_pad * ldc;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 p = *reinterpret_cast<const float4*>(partial + s * split_stride + i * 4);
+      a.x += p.x;
+      a.y += p.y;
+      a.z += p.z;
+      a.w += p.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
+cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
+                                       int ldc, cudaStream_t st) {
+  const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
+  wgrad_splitk_reduce_kernel<<<grid_for(n4, 256), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ Adam / L2
+// 28 B/param of HBM traffic (read p,g,m,v; write p,m,v): the floor for an fp32 Adam step.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps,
+                            float gscale) {
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define FCN8_ADAM1(c)                                  \
+  {                                                    \
+    const float gr = gg.c * gscale;                    \
+    mm.c = b1 * mm.c + (1.f - b1) * gr;                \
+    vv.c = b2 * vv.c + (1.f - b2) * gr * gr;           \
+    pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);         \
+  }
+    FCN8_ADAM1(x) FCN8_ADAM1(y) FCN8_ADAM1(z) FCN8_ADAM1(w)
+#undef FCN8_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  // tail (n not a multiple of 4)
+  if (blockIdx.x == 0) {
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      const float gr = g[i] * gscale;
+      m[i] = b1 * m[i] + (1.f - b1) * gr;
+      v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
+      p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+    }
+  }
+}
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
+                        float eps, float gscale, cudaStream_t st) {
+  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+  return cudaGetLastError();
+}
+
+__global__ void l2_reg_kernel(const float* __restrict__ w, float* __restrict__ g, float* __restrict__ loss, size_t n,
+                              float rate) {
+  float s = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float x = w[i];
+    if (g) g[i] += rate * x;
+    s += x * x;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float t = 0.f;
+    for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) t += ws[k];
+    atomicAdd(loss, 0.5f * rate * t);
+  }
+}
+cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st) {
+  l2_reg_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(w, g, loss, n, rate);
+  return cudaGetLastError();
+}
+
+}  // namespace fcn8

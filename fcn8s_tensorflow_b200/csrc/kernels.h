@@ -1,0 +1,47 @@
+// Internal launcher declarations shared by the translation units of libfcn8s_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fcn8 {
+
+struct ConvGemmArgs;
+
+// elementwise.cu
+cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st);
+cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
+cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
+                               cudaStream_t st);
+int bias_grad_blocks(long long P, int C);
+cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st);
+cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st);
+cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int Cin, int Cout, int CinPad, int mode,
+                        int dtype, cudaStream_t st);
+cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n_elems, int ldc,
+                                      const ConvGemmArgs& g, int dtype, cudaStream_t st);
+cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
+                                       int ldc, cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
+                        float eps, float gscale, cudaStream_t st);
+cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st);
+
+// decoder.cu
+cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
+                            float scale, int dtype, cudaStream_t st);
+int head_bwd_blocks(long long P);
+cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, float* dK, float* db, void* dx,
+                            long long P, int Cin, int C, float scale, int dtype, int mask, float mask_scale, float* ws,
+                            cudaStream_t st);
+cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias, const float* skip, float* y, int N,
+                               int h, int w, int C, int s, cudaStream_t st);
+size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s);
+cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, float* dx, float* dT, float* dbias,
+                               int N, int h, int w, int C, int s, float* ws, cudaStream_t st);
+cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* sm,
+                                long long* amax, long long P, int C, float gscale, cudaStream_t st);
+cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
+                             cudaStream_t st);
+
+}  // namespace fcn8

@@ -1,0 +1,227 @@
+"""Operator layer: one Python function per C-ABI entry point, taking/returning torch CUDA tensors.
+
+torch is used for device memory and the current stream only; every computation goes through
+libfcn8s_sm100.so. Shapes follow the reference's NHWC convention (fcn8s_tensorflow.py:429-433).
+"""
+import ctypes as C
+
+import torch
+
+from . import _capi as capi
+from ._capi import BF16, F32, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL  # noqa: F401
+
+_workspaces = {}
+
+
+def torch_dtype(dtype):
+    return torch.bfloat16 if dtype == BF16 else torch.float32
+
+
+def dtype_of(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError("activation tensors must be bfloat16 or float32, got %s" % t.dtype)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch buffer per device (caller-provided workspace of the C ABI)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise capi.Fcn8Error("tensor is not on a CUDA device; there is no CPU path")
+            if not t.is_contiguous():
+                raise capi.Fcn8Error("tensor must be contiguous")
+
+
+def preprocess_im2col(images, dtype):
+    """uint8 RGB [N,H,W,3] -> mean-subtracted BGR im2col [N,H,W,KP] for conv1_1 (KP = 64 bf16 / 32 f32)."""
+    _chk_cuda(images)
+    if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
+        raise ValueError("images must be uint8 [N,H,W,3]")
+    N, H, W, _ = images.shape
+    kp = 64 if dtype == BF16 else 32
+    out = torch.empty((N, H, W, kp), dtype=torch_dtype(dtype), device=images.device)
+    p = capi.PreprocessParams(capi.ptr(images), capi.ptr(out), N, H, W, dtype)
+    capi.check(capi.load().fcn8_preprocess_im2col(C.byref(p), _stream()))
+    return out
+
+
+def pack_weights(w, ksize, cin, cout, mode, dtype, cin_pad=None, split=False):
+    """fp32 HWIO weights -> tensor-core operand layout (mode 0 fprop [Cout][taps*CinPad], mode 1 dgrad
+    [Cin][taps*Cout]). Returns (packed, packed_lo or None)."""
+    _chk_cuda(w)
+    taps = ksize * ksize
+    if cin_pad is None:
+        cin_pad = cin
+    shape = (cout, taps * cin_pad) if mode == 0 else (cin, taps * cout)
+    out = torch.empty(shape, dtype=torch_dtype(dtype), device=w.device)
+    lo = torch.empty_like(out) if split else None
+    p = capi.PackParams(capi.ptr(w), capi.ptr(out), capi.ptr(lo), ksize, cin, cout, cin_pad, mode, dtype)
+    capi.check(capi.load().fcn8_pack_weights(C.byref(p), _stream()))
+    return out, lo
+
+
+def split_tf32(x):
+    _chk_cuda(x)
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    capi.check(capi.load().fcn8_split_tf32(capi.ptr(x), capi.ptr(hi), capi.ptr(lo), x.numel(), _stream()))
+    return hi, lo
+
+
+def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0):
+    """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h)."""
+    _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo)
+    N, H, W, cin = x.shape
+    dtype = dtype_of(x)
+    if out is None:
+        out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
+    nseg = 3 if x_lo is not None else 1
+    p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
+                        capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
+                        mask_scale, keep_prob, seed, force_splits, force_bn)
+    lib = capi.load()
+    nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device) if nbytes else None
+    capi.check(lib.fcn8_conv_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    return out
+
+
+def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0):
+    """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows)."""
+    _chk_cuda(x, dy, out, x_lo, dy_lo)
+    N, H, W, cin = x.shape
+    cout = dy.shape[3]
+    nseg = 3 if x_lo is not None else 1
+    p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin,
+                         cout, ksize, rows_valid, dtype_of(x), nseg, force_splits, force_bn)
+    lib = capi.load()
+    nbytes = lib.fcn8_wgrad_gemm_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device) if nbytes else None
+    capi.check(lib.fcn8_wgrad_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    return out
+
+
+def maxpool_fwd(x, out=None):
+    _chk_cuda(x, out)
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, Cc), dtype=x.dtype, device=x.device)
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(out), None, N, H, W, Cc, dtype_of(x))
+    capi.check(capi.load().fcn8_maxpool_fwd(C.byref(p), _stream()))
+    return out
+
+
+def maxpool_bwd(x, dy, out=None):
+    """Gradient w.r.t. the pre-ReLU producer of x: routes dy to the first arg-max where x > 0."""
+    _chk_cuda(x, dy, out)
+    N, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(dy), capi.ptr(out), N, H, W, Cc, dtype_of(x))
+    capi.check(capi.load().fcn8_maxpool_bwd(C.byref(p), _stream()))
+    return out
+
+
+def bias_grad(dy, out):
+    _chk_cuda(dy, out)
+    Cc = dy.shape[-1]
+    P = dy.numel() // Cc
+    p = capi.BiasGradParams(capi.ptr(dy), capi.ptr(out), P, Cc, dtype_of(dy))
+    lib = capi.load()
+    nbytes = lib.fcn8_bias_grad_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, dy.device)
+    capi.check(lib.fcn8_bias_grad(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    return out
+
+
+def score_head_fwd(x, K, b, scale, out=None):
+    _chk_cuda(x, K, b, out)
+    cin = x.shape[-1]
+    Cc = K.shape[-1]
+    P = x.numel() // cin
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (Cc,), dtype=torch.float32, device=x.device)
+    p = capi.HeadParams(capi.ptr(x), capi.ptr(K), capi.ptr(b), capi.ptr(out), None, None, None, P, cin, Cc, scale,
+                        dtype_of(x), 0, 1.0)
+    capi.check(capi.load().fcn8_score_head_fwd(C.byref(p), _stream()))
+    return out
+
+
+def score_head_bwd(x, K, ds, scale, dK, db, dx=None, mask=False, mask_scale=1.0):
+    _chk_cuda(x, K, ds, dK, db, dx)
+    cin = x.shape[-1]
+    Cc = K.shape[-1]
+    P = x.numel() // cin
+    p = capi.HeadParams(capi.ptr(x), capi.ptr(K), None, capi.ptr(ds), capi.ptr(dK), capi.ptr(db), capi.ptr(dx), P, cin,
+                        Cc, scale, dtype_of(x), 1 if mask else 0, mask_scale)
+    lib = capi.load()
+    nbytes = lib.fcn8_score_head_bwd_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device)
+    capi.check(lib.fcn8_score_head_bwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    return dx
+
+
+def upscore_fwd(x, T, bias, stride, skip=None, out=None):
+    _chk_cuda(x, T, bias, skip, out)
+    N, h, w, Cc = x.shape
+    if out is None:
+        out = torch.empty((N, h * stride, w * stride, Cc), dtype=torch.float32, device=x.device)
+    p = capi.UpscoreParams(capi.ptr(x), capi.ptr(T), capi.ptr(bias), capi.ptr(skip), capi.ptr(out), None, None, None,
+                           N, h, w, Cc, stride)
+    capi.check(capi.load().fcn8_upscore_fwd(C.byref(p), _stream()))
+    return out
+
+
+def upscore_bwd(x, T, dy, stride, dT, dbias, dx=None):
+    _chk_cuda(x, T, dy, dT, dbias, dx)
+    N, h, w, Cc = x.shape
+    p = capi.UpscoreParams(capi.ptr(x), capi.ptr(T), None, None, capi.ptr(dy), capi.ptr(dx), capi.ptr(dT),
+                           capi.ptr(dbias), N, h, w, Cc, stride)
+    lib = capi.load()
+    nbytes = lib.fcn8_upscore_bwd_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device)
+    capi.check(lib.fcn8_upscore_bwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    return dx
+
+
+def softmax_xent(logits, labels=None, loss_sum=None, dlogits=None, softmax=None, argmax=None, grad_scale=1.0):
+    _chk_cuda(logits, labels, loss_sum, dlogits, softmax, argmax)
+    Cc = logits.shape[-1]
+    P = logits.numel() // Cc
+    p = capi.SoftmaxParams(capi.ptr(logits), capi.ptr(labels), capi.ptr(loss_sum), capi.ptr(dlogits),
+                           capi.ptr(softmax), capi.ptr(argmax), P, Cc, grad_scale)
+    capi.check(capi.load().fcn8_softmax_xent(C.byref(p), _stream()))
+
+
+def confusion_matrix(pred, labels_onehot, conf):
+    _chk_cuda(pred, labels_onehot, conf)
+    Cc = labels_onehot.shape[-1]
+    capi.check(capi.load().fcn8_confusion_matrix(capi.ptr(pred), capi.ptr(labels_onehot), capi.ptr(conf),
+                                                 pred.numel(), Cc, _stream()))
+
+
+def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _chk_cuda(p, g, m, v)
+    capi.check(capi.load().fcn8_adam(capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), p.numel(), lr_t, beta1,
+                                     beta2, eps, grad_scale, _stream()))
+
+
+def l2_reg(w, g, loss_sum, rate):
+    _chk_cuda(w, g, loss_sum)
+    capi.check(capi.load().fcn8_l2_reg(capi.ptr(w), capi.ptr(g), capi.ptr(loss_sum), w.numel(), rate, _stream()))

@@ -1,0 +1,230 @@
+/*
+ * fcn8s_b200.h -- C ABI of libfcn8s_sm100.so: the B200 (sm_100a) kernels behind the FCN-8s forward+backward path.
+ *
+ * The reference (pierluigiferrari/fcn8s_tensorflow) has no FFI: its hot path is the set of TensorFlow-1.x ops that
+ * `tf.Session.run` executes for the graph built in fcn8s_tensorflow.py.  Each entry point below replaces one group
+ * of those ops; the comment above each names the reference call site (file:line under the reference root) whose
+ * arithmetic it implements.  A maintainer binds them with ctypes; this repo's own binding is
+ * fcn8s_tensorflow_b200/_capi.py.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative FCN8_ERR_* code; fcn8_last_error() gives the message
+ *     (thread-local).
+ *   - the library never allocates, frees or synchronises: all pointers are device pointers owned by the caller
+ *     (torch.Tensor.data_ptr()), 16-byte aligned, NHWC contiguous; `stream` is a cudaStream_t passed as void*.
+ *   - `dtype` selects the activation storage / tensor-core operand type: FCN8_BF16 (bf16 operands, kind::f16) or
+ *     FCN8_F32 (fp32 storage, kind::tf32; with `nseg == 3` the error-compensated 3xTF32 product hi*hi+hi*lo+lo*hi).
+ *     Accumulation is always fp32 (TMEM).  Parameters, gradients, Adam state and the decoder are fp32.
+ *   - workspaces are caller-provided; the *_workspace_bytes query never launches anything.
+ */
+#ifndef FCN8S_B200_H_
+#define FCN8S_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCN8_VERSION 100
+
+enum {
+  FCN8_OK = 0,
+  FCN8_ERR_BAD_SHAPE = -1,
+  FCN8_ERR_BAD_ALIGN = -2,
+  FCN8_ERR_WORKSPACE = -3,
+  FCN8_ERR_CUDA = -4,
+  FCN8_ERR_UNSUPPORTED = -5
+};
+
+enum { FCN8_BF16 = 0, FCN8_F32 = 1 };
+
+/* epilogue flags of fcn8_conv_gemm (bit-or) */
+enum {
+  FCN8_EPI_BIAS = 1,
+  FCN8_EPI_RELU = 2,
+  FCN8_EPI_DROPOUT = 4,
+  FCN8_EPI_MASK = 8,
+  FCN8_EPI_RESIDUAL = 16
+};
+
+int32_t fcn8_version(void);
+const char* fcn8_last_error(void);
+/* 0 iff device `dev` is compute capability 10.x (B200); the kernels are sm_100a-only. */
+int32_t fcn8_device_check(int32_t dev);
+/* bring-up knobs (descriptor variants) -- tests only. */
+int32_t fcn8_debug_set(int32_t key, int32_t value);
+
+/* ---- feed: fcn8s_tensorflow.py:558,686,765 (image_input) + the encoder graph's RGB->BGR / mean subtraction [EXT].
+ * uint8 RGB [N,H,W,3] -> im2col of the mean-subtracted BGR image for conv1_1: out[N,H,W,KP], column tap*3+c
+ * (tap = kh*3+kw, c in B,G,R order) = value at (y+kh-1, x+kw-1) or 0 outside (SAME padding), columns 27..KP-1 = 0.
+ * KP = 64 (bf16) / 32 (f32).  conv1_1 then runs as a 1x1 fcn8_conv_gemm over it. */
+typedef struct {
+  const uint8_t* images;
+  void* out;
+  int32_t N, H, W;
+  int32_t dtype;
+} Fcn8PreprocessParams;
+int32_t fcn8_preprocess_im2col(const Fcn8PreprocessParams* p, void* stream);
+
+/* ---- encoder convolutions (external VGG-16 graph loaded at fcn8s_tensorflow.py:127-152; conv kxk stride 1 SAME):
+ * out[N,H,W,Cout] = epilogue( sum_{kh,kw,ci} x[N, y+kh-pad, x+kw-pad, ci] * wp[co][(kh*k+kw)*Cin + ci] ).
+ * fprop: wp from fcn8_pack_weights(mode 0), flags BIAS|RELU(|DROPOUT).  dgrad (autodiff of the same op, :257):
+ * x = dY, wp from fcn8_pack_weights(mode 1), flags MASK (ReLU/dropout backward against `mask_src`) and/or RESIDUAL.
+ * nseg == 3 (FCN8_F32 only): x_lo / wp_lo are the low halves of the tf32 split (fcn8_split_tf32). */
+typedef struct {
+  const void* x;
+  const void* x_lo;
+  const void* wp;
+  const void* wp_lo;
+  void* out;
+  const float* bias;
+  const void* mask_src;
+  const void* residual;
+  int32_t N, H, W, Cin, Cout, ksize;
+  int32_t dtype, nseg, flags;
+  float mask_scale;
+  float keep_prob;
+  uint32_t seed;
+  int32_t force_splits; /* 0 = heuristic */
+  int32_t force_bn;     /* 0 = heuristic, else 64/128/256 */
+} Fcn8ConvParams;
+size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
+int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- filter gradient (autodiff of the conv, fcn8s_tensorflow.py:257):
+ * dw[(kh*k+kw)*Cin + ci][co] (fp32, TF HWIO order) = sum_{n,y,x} x[n,y+kh-pad,x+kw-pad,ci] * dy[n,y,x,co].
+ * rows_valid < ksize*ksize*Cin keeps only the first rows (27 for the im2col'ed conv1_1).
+ * accumulate != 0 adds into dw instead of overwriting. */
+typedef struct {
+  const void* x;
+  const void* x_lo;
+  const void* dy;
+  const void* dy_lo;
+  float* dw;
+  int32_t N, H, W, Cin, Cout, ksize;
+  int32_t rows_valid;
+  int32_t dtype, nseg;
+  int32_t force_splits;
+  int32_t force_bn;
+} Fcn8WgradParams;
+size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p);
+int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- weight packing: fp32 master weights in TF layout [k,k,Cin,Cout] (HWIO) -> tensor-core operand layout.
+ * mode 0 (fprop): out[co][tap*CinPad + ci] = w[tap][ci][co]           (CinPad >= Cin, zero filled)
+ * mode 1 (dgrad): out[ci][tap'*Cout + co]  = w[taps-1-tap'][ci][co]    (180-degree rotation, in/out swapped)
+ * dtype BF16: out bf16.  dtype F32: out fp32; if out_lo != NULL, out = tf32-exact high part and out_lo the rest. */
+typedef struct {
+  const float* w;
+  void* out;
+  void* out_lo;
+  int32_t ksize, Cin, Cout, CinPad;
+  int32_t mode, dtype;
+} Fcn8PackParams;
+int32_t fcn8_pack_weights(const Fcn8PackParams* p, void* stream);
+
+/* x (fp32) -> hi (top 19 bits, exact in tf32) and lo = x - hi. */
+int32_t fcn8_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+
+/* ---- 2x2 / stride 2 SAME max pooling of the encoder graph [EXT] and its gradient.
+ * bwd: dx = (first arg-max of the window && x > 0) ? dy : 0  -- MaxPoolGrad fused with the ReLUGrad of the producer. */
+typedef struct {
+  const void* x;  /* [N,H,W,C]   */
+  void* y;        /* fwd: out [N,ceil(H/2),ceil(W/2),C];  bwd: dy (same shape) */
+  void* dx;       /* bwd only */
+  int32_t N, H, W, C;
+  int32_t dtype;
+} Fcn8PoolParams;
+int32_t fcn8_maxpool_fwd(const Fcn8PoolParams* p, void* stream);
+int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream);
+
+/* ---- bias gradient: db[c] = sum_p dy[p][c]  (BiasAddGrad).  dy [P][C] in `dtype`, db fp32. */
+typedef struct {
+  const void* dy;
+  float* db;
+  int64_t P;
+  int32_t C;
+  int32_t dtype;
+} Fcn8BiasGradParams;
+size_t fcn8_bias_grad_workspace_bytes(const Fcn8BiasGradParams* p);
+int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- decoder 1x1 score heads: fcn8s_tensorflow.py:171-200 (tf.multiply scale + tf.layers.conv2d 1x1 + bias).
+ * fwd: s[p][c] = scale * sum_ci x[p][ci] * K[ci][c] + b[c]            (x in `dtype`, everything else fp32)
+ * bwd: dK[ci][c] = scale * sum_p x[p][ci]*ds[p][c]; db[c] = sum_p ds[p][c];
+ *      dx[p][ci] = scale * sum_c ds[p][c]*K[ci][c]  (* (x>0)*mask_scale if mask != 0: dropout+ReLU backward of fc7) */
+typedef struct {
+  const void* x;
+  const float* K;
+  const float* b;
+  float* s;        /* fwd out / bwd: ds in */
+  float* dK;
+  float* db;
+  void* dx;        /* `dtype` */
+  int64_t P;
+  int32_t Cin, C;
+  float scale;
+  int32_t dtype;
+  int32_t mask;
+  float mask_scale;
+} Fcn8HeadParams;
+int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* stream);
+size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p);
+int32_t fcn8_score_head_bwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- transposed convolutions: fcn8s_tensorflow.py:204-233 (tf.layers.conv2d_transpose k=2s, stride s, 'same')
+ * plus the skip adds :213,:224.   T[a][b][co][ci] (TF layout), all fp32.
+ * fwd: y[n, s*i+a-p, s*j+b-p, co] = sum x[n,i,j,ci]*T[a,b,co,ci] + bias[co] (+ skip[...]),  p = s/2.
+ * bwd: dx = strided conv of dy with T;  dT[a,b,co,ci] = sum x*dy;  dbias = sum dy. */
+typedef struct {
+  const float* x;  /* [N,h,w,C] */
+  const float* T;  /* [2s,2s,C,C] */
+  const float* bias;
+  const float* skip; /* [N,h*s,w*s,C] or NULL */
+  float* y;        /* fwd out / bwd: dy in */
+  float* dx;
+  float* dT;
+  float* dbias;
+  int32_t N, h, w, C, stride;
+} Fcn8UpscoreParams;
+int32_t fcn8_upscore_fwd(const Fcn8UpscoreParams* p, void* stream);
+size_t fcn8_upscore_bwd_workspace_bytes(const Fcn8UpscoreParams* p);
+int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- loss / predictor: fcn8s_tensorflow.py:253 (softmax_cross_entropy_with_logits + reduce_mean), :268-269.
+ * labels: uint8 [P][C] one-hot as yielded by the generators (numpy bool), used as fp32 weights y_c like TF does.
+ * loss_sum (fp32 scalar, accumulated; caller zeroes) += sum_p (sum_c y_c)*lse(z) - sum_c y_c z_c;
+ * dlogits[p][c] = (softmax_c * sum_c y_c - y_c) * grad_scale   (grad_scale = 1/(N*H*W) [* 1/world]).
+ * softmax / argmax(int64, first max) for predict().  Any output pointer may be NULL. */
+typedef struct {
+  const float* logits;
+  const uint8_t* labels;
+  float* loss_sum;
+  float* dlogits;
+  float* softmax;
+  int64_t* argmax;
+  int64_t P;
+  int32_t C;
+  float grad_scale;
+} Fcn8SoftmaxParams;
+int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream);
+
+/* ---- streaming metrics: fcn8s_tensorflow.py:280-301 (labels_argmax, tf.metrics.mean_iou / accuracy); the device
+ * analogue of cityscapesscripts/evaluation/addToConfusionMatrix_impl.c:3-16: conf[gt*C + pred] += 1 (uint64). */
+int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot, unsigned long long* conf, int64_t P,
+                              int32_t C, void* stream);
+
+/* ---- optimiser: tf.train.AdamOptimizer.minimize, fcn8s_tensorflow.py:256-257 (TF form: eps outside sqrt(v)):
+ * g' = g*grad_scale;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;  p -= lr_t * m / (sqrt(v) + eps),
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
+int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, void* stream);
+/* L2 regulariser of the six decoder kernels (:179..232, :250-251): g += rate*w;  loss_sum += 0.5*rate*sum w^2. */
+int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float rate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCN8S_B200_H_ */

@@ -1,0 +1,435 @@
+"""GPU bring-up of the individual kernels against torch references (run on the B200 box via gpurun).
+
+    python scripts/bringup.py list            -> case names
+    python scripts/bringup.py <case> [...]    -> run cases in this process
+    python scripts/bringup.py all             -> run every case, each in its own subprocess with a timeout
+
+Diagnostics are verbose on purpose: this is the tool for finding descriptor / layout mistakes with few GPU calls.
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def rel_err(a, b):
+    a = a.double().cpu()
+    b = b.double().cpu()
+    denom = b.abs().max().item()
+    return ((a - b).abs().max().item() / (denom if denom > 0 else 1.0)), denom
+
+
+def report(name, got, ref, tol):
+    e, d = rel_err(got, ref)
+    ok = e <= tol and torch.isfinite(got.float()).all().item()
+    print("  %-44s max|d|/max|ref| = %.3e (ref max %.3e) tol %.1e  %s" % (name, e, d, tol, "OK" if ok else "FAIL"))
+    if not ok:
+        g = got.double().cpu()
+        r = ref.double().cpu()
+        bad = ((g - r).abs() > tol * max(d, 1e-30))
+        print("    mismatching elements: %d / %d" % (bad.sum().item(), bad.numel()))
+        idx = bad.nonzero()[:8]
+        for i in idx:
+            t = tuple(i.tolist())
+            print("     at %s got %.6g ref %.6g" % (t, g[t].item(), r[t].item()))
+        if g.dim() == 4 and g.shape[-1] % 8 == 0:
+            print("    bad count per channel-block of 8 (first 16):", bad.sum(dim=(0, 1, 2)).view(-1, 8).sum(1)[:16].tolist())
+            print("    bad count per row y (first 16):", bad.sum(dim=(0, 2, 3))[:16].tolist())
+            print("    bad count per col x (first 16):", bad.sum(dim=(0, 1, 3))[:16].tolist())
+        if g.dim() == 2 and g.shape[0] % 8 == 0 and g.shape[1] % 8 == 0:
+            print("    bad rows (first 16 blocks of 8):", bad.sum(1).view(-1)[:128].view(-1, 8).sum(1).tolist())
+            print("    bad cols (first 16 blocks of 8):", bad.sum(0).view(-1)[:128].view(-1, 8).sum(1).tolist())
+    return ok
+
+
+def ref_conv(x, w_hwio, bias=None, relu=False):
+    """NHWC x, HWIO w -> NHWC, stride 1 SAME, computed in fp64 on the GPU."""
+    k = w_hwio.shape[0]
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w_hwio.double().permute(3, 2, 0, 1), padding=k // 2)
+    y = y.permute(0, 2, 3, 1)
+    if bias is not None:
+        y = y + bias.double()
+    if relu:
+        y = y.clamp_min(0)
+    return y
+
+
+def conv_case(N, H, W, cin, cout, k, dtype, tol, seed=0, force_bn=0, force_splits=0, flags_extra=0, nseg=1):
+    from fcn8s_tensorflow_b200 import ops
+    torch.manual_seed(seed)
+    dev = torch.device("cuda")
+    tdt = ops.torch_dtype(dtype)
+    x = torch.randn(N, H, W, cin, device=dev).to(tdt)
+    w = (torch.randn(k, k, cin, cout, device=dev) / (k * k * cin) ** 0.5)
+    b = torch.randn(cout, device=dev)
+    if nseg == 3:
+        wp, wlo = ops.pack_weights(w, k, cin, cout, 0, dtype, split=True)
+        xh, xl = ops.split_tf32(x)
+        y = ops.conv_gemm(xh, wp, cout, k, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, x_lo=xl, wp_lo=wlo,
+                          force_bn=force_bn, force_splits=force_splits)
+        wq = w
+    else:
+        wp, _ = ops.pack_weights(w, k, cin, cout, 0, dtype)
+        y = ops.conv_gemm(x, wp, cout, k, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, force_bn=force_bn,
+                          force_splits=force_splits)
+        wq = w.to(tdt) if dtype == ops.BF16 else w
+    torch.cuda.synchronize()
+    ref = ref_conv(x, wq, b, relu=True)
+    return report("conv N%d %dx%d Cin%d Cout%d k%d dt%d bn%d sp%d seg%d" %
+                  (N, H, W, cin, cout, k, dtype, force_bn, force_splits, nseg), y, ref, tol)
+
+
+@case
+def conv_bf16_1x1_single_tile():
+    return conv_case(1, 8, 16, 64, 64, 1, 0, 1e-2)
+
+
+@case
+def conv_bf16_1x1_k128():
+    return conv_case(1, 8, 16, 128, 64, 1, 0, 1e-2)
+
+
+@case
+def conv_bf16_3x3_single_tile():
+    return conv_case(1, 8, 16, 64, 64, 3, 0, 1e-2)
+
+
+@case
+def conv_bf16_3x3_bn128_bn256():
+    ok = conv_case(2, 16, 32, 128, 128, 3, 0, 1e-2)
+    ok &= conv_case(2, 16, 32, 128, 256, 3, 0, 1e-2)
+    ok &= conv_case(2, 16, 32, 64, 512, 3, 0, 1e-2, force_bn=256)
+    return ok
+
+
+@case
+def conv_bf16_persistent_many_tiles():
+    ok = conv_case(2, 64, 128, 64, 64, 3, 0, 1e-2)      # 128 m-tiles
+    ok &= conv_case(4, 64, 128, 64, 128, 3, 0, 1e-2)    # 256 m-tiles > 148 CTAs: persistent loop + TMEM double buffer
+    ok &= conv_case(3, 40, 72, 128, 256, 3, 0, 1e-2)    # ragged: partial tiles in every dim
+    return ok
+
+
+@case
+def conv_bf16_splitk_and_7x7():
+    ok = conv_case(1, 8, 16, 512, 256, 3, 0, 1e-2, force_splits=3)
+    ok &= conv_case(2, 4, 8, 512, 256, 7, 0, 1e-2)       # fc6 geometry (heuristic split-K)
+    ok &= conv_case(1, 1, 2, 512, 512, 7, 0, 1e-2)       # tiny spatial: box larger than the tensor
+    return ok
+
+
+@case
+def conv_tf32_basic():
+    ok = conv_case(1, 8, 16, 32, 64, 1, 1, 2e-3)
+    ok &= conv_case(1, 8, 16, 64, 64, 3, 1, 2e-3)
+    ok &= conv_case(2, 16, 32, 128, 256, 3, 1, 2e-3)
+    return ok
+
+
+@case
+def conv_tf32x3():
+    ok = conv_case(1, 8, 16, 64, 64, 3, 1, 2e-6, nseg=3)
+    ok &= conv_case(2, 16, 32, 128, 256, 3, 1, 2e-6, nseg=3)
+    return ok
+
+
+@case
+def conv_epilogues():
+    """dgrad-style epilogue: residual add + relu mask with scale; and dropout."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    ok = True
+    for dtype, tol in ((0, 1e-2), (1, 2e-3)):
+        torch.manual_seed(1)
+        tdt = ops.torch_dtype(dtype)
+        N, H, W, cin, cout, k = 2, 16, 16, 128, 128, 3
+        x = torch.randn(N, H, W, cin, device=dev).to(tdt)
+        w = torch.randn(k, k, cin, cout, device=dev) / (k * k * cin) ** 0.5
+        msrc = torch.randn(N, H, W, cout, device=dev).to(tdt)
+        res = torch.randn(N, H, W, cout, device=dev).to(tdt)
+        wp, _ = ops.pack_weights(w, k, cin, cout, 0, dtype)
+        wq = w.to(tdt) if dtype == 0 else w
+        for splits in (0, 2):
+            y = ops.conv_gemm(x, wp, cout, k, flags=ops.EPI_MASK | ops.EPI_RESIDUAL, mask_src=msrc, residual=res,
+                              mask_scale=2.0, force_splits=splits)
+            ref = (ref_conv(x, wq) + res.double()) * (msrc.double() > 0) * 2.0
+            ok &= report("epilogue mask+residual dt%d splits%d" % (dtype, splits), y, ref, tol)
+            b = torch.randn(cout, device=dev)
+            y = ops.conv_gemm(x, wp, cout, k, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU | ops.EPI_DROPOUT,
+                              keep_prob=0.5, seed=1234, force_splits=splits)
+            from fcn8s_tensorflow_b200.rng import dropout_keep_mask
+            keep = dropout_keep_mask(1234, y.numel(), 0.5).view(y.shape).to(dev)
+            ref = ref_conv(x, wq, b, relu=True) * keep.double() * 2.0
+            ok &= report("epilogue dropout dt%d splits%d (keep frac %.3f)" % (dtype, splits, keep.float().mean().item()),
+                         y, ref, tol)
+    return ok
+
+
+def dgrad_case(N, H, W, cin, cout, k, dtype, tol):
+    from fcn8s_tensorflow_b200 import ops
+    torch.manual_seed(3)
+    dev = torch.device("cuda")
+    tdt = ops.torch_dtype(dtype)
+    w = torch.randn(k, k, cin, cout, device=dev) / (k * k * cout) ** 0.5
+    dy = torch.randn(N, H, W, cout, device=dev).to(tdt)
+    wp, _ = ops.pack_weights(w, k, cin, cout, 1, dtype)
+    dx = ops.conv_gemm(dy, wp, cin, k)
+    wq = (w.to(tdt) if dtype == 0 else w).double()
+    ref = F.conv_transpose2d(dy.double().permute(0, 3, 1, 2), wq.permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
+    return report("dgrad N%d %dx%d Cin%d Cout%d k%d dt%d" % (N, H, W, cin, cout, k, dtype), dx, ref, tol)
+
+
+@case
+def dgrad_pack_and_conv():
+    ok = dgrad_case(2, 16, 32, 64, 128, 3, 0, 1e-2)
+    ok &= dgrad_case(1, 4, 8, 512, 256, 7, 0, 1e-2)
+    ok &= dgrad_case(2, 16, 32, 64, 128, 3, 1, 2e-3)
+    return ok
+
+
+def wgrad_case(N, H, W, cin, cout, k, dtype, tol, force_splits=0, force_bn=0, rows_valid=0, nseg=1):
+    from fcn8s_tensorflow_b200 import ops
+    torch.manual_seed(4)
+    dev = torch.device("cuda")
+    tdt = ops.torch_dtype(dtype)
+    x = torch.randn(N, H, W, cin, device=dev).to(tdt)
+    dy = torch.randn(N, H, W, cout, device=dev).to(tdt)
+    rows = k * k * cin
+    rv = rows_valid if rows_valid else rows
+    dw = torch.full((rv, cout), float("nan"), device=dev)
+    if nseg == 3:
+        xh, xl = ops.split_tf32(x)
+        dh, dl = ops.split_tf32(dy)
+        ops.wgrad_gemm(xh, dh, k, dw, rows_valid=rows_valid, x_lo=xl, dy_lo=dl, force_splits=force_splits,
+                       force_bn=force_bn)
+    else:
+        ops.wgrad_gemm(x, dy, k, dw, rows_valid=rows_valid, force_splits=force_splits, force_bn=force_bn)
+    torch.cuda.synchronize()
+    # reference: dW[kh,kw,ci,co] = sum x[n,y+kh-p,x+kw-p,ci] dy[n,y,x,co]
+    xp = F.pad(x.double().permute(0, 3, 1, 2), (k // 2,) * 4)
+    cols = F.unfold(xp, k).view(N, cin, k * k, H * W)             # [N, ci, tap, P]
+    ref = torch.einsum("nctp,npo->tco", cols, dy.double().reshape(N, H * W, cout)).reshape(rows, cout)[:rv]
+    return report("wgrad N%d %dx%d Cin%d Cout%d k%d dt%d sp%d bn%d seg%d" %
+                  (N, H, W, cin, cout, k, dtype, force_splits, force_bn, nseg), dw, ref, tol)
+
+
+@case
+def wgrad_bf16_1x1_single():
+    return wgrad_case(1, 8, 8, 128, 64, 1, 0, 1e-2)
+
+
+@case
+def wgrad_bf16_1x1_m64():
+    return wgrad_case(1, 8, 8, 64, 64, 1, 0, 1e-2)
+
+
+@case
+def wgrad_bf16_3x3():
+    ok = wgrad_case(1, 8, 8, 64, 64, 3, 0, 1e-2)
+    ok &= wgrad_case(2, 16, 32, 128, 256, 3, 0, 1e-2)
+    ok &= wgrad_case(3, 20, 36, 64, 128, 3, 0, 1e-2)
+    return ok
+
+
+@case
+def wgrad_bf16_splits_7x7_rows():
+    ok = wgrad_case(2, 32, 32, 64, 64, 3, 0, 1e-2, force_splits=1)
+    ok &= wgrad_case(2, 32, 32, 64, 64, 3, 0, 1e-2, force_splits=5)
+    ok &= wgrad_case(2, 4, 8, 512, 256, 7, 0, 1e-2)
+    ok &= wgrad_case(2, 16, 16, 64, 64, 1, 0, 1e-2, rows_valid=27)
+    return ok
+
+
+@case
+def wgrad_tf32():
+    ok = wgrad_case(1, 8, 8, 32, 64, 1, 1, 2e-3)
+    ok &= wgrad_case(2, 16, 32, 128, 256, 3, 1, 2e-3)
+    ok &= wgrad_case(2, 16, 32, 64, 128, 3, 1, 2e-6, nseg=3)
+    return ok
+
+
+@case
+def elementwise_kernels():
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    ok = True
+    torch.manual_seed(5)
+    # preprocess
+    img = torch.randint(0, 256, (2, 10, 14, 3), dtype=torch.uint8, device=dev)
+    mean = torch.tensor([103.939, 116.779, 123.68], device=dev, dtype=torch.float64)
+    bgr = img.double().flip(-1) - mean
+    xp = F.pad(bgr.permute(0, 3, 1, 2), (1, 1, 1, 1))
+    cols = F.unfold(xp, 3).view(2, 3, 9, 10, 14).permute(0, 3, 4, 2, 1).reshape(2, 10, 14, 27)
+    for dtype, tol in ((0, 4e-3), (1, 1e-7)):
+        out = ops.preprocess_im2col(img, dtype)
+        ok &= report("preprocess dt%d" % dtype, out[..., :27], cols, tol)
+        ok &= bool((out[..., 27:] == 0).all().item())
+    # pool fwd / bwd (odd sizes)
+    for dtype in (0, 1):
+        tdt = ops.torch_dtype(dtype)
+        x = torch.randn(2, 9, 13, 64, device=dev).clamp_min(0).to(tdt)
+        y = ops.maxpool_fwd(x)
+        xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = F.max_pool2d(xr, 2, 2, ceil_mode=True)
+        ok &= report("maxpool fwd dt%d" % dtype, y, yr.permute(0, 2, 3, 1), 0.0)
+        dy = torch.randn_like(y.float()).to(tdt)
+        dx = ops.maxpool_bwd(x, dy)
+        yr.backward(dy.double().permute(0, 3, 1, 2))
+        ref = xr.grad.permute(0, 2, 3, 1) * (x.double() > 0)
+        ok &= report("maxpool bwd dt%d" % dtype, dx, ref, 0.0)
+        # bias grad
+        for Cc in (64, 512, 4096):
+            g = torch.randn(1000, Cc, device=dev).to(tdt)
+            db = torch.empty(Cc, device=dev)
+            ops.bias_grad(g, db)
+            ok &= report("bias_grad C%d dt%d" % (Cc, dtype), db, g.double().sum(0), 1e-5)
+    # adam
+    n = 1000003
+    p = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev)
+    m = torch.randn(n, device=dev) * 0.1
+    v = torch.rand(n, device=dev) * 0.1
+    pr, mr, vr = p.double(), m.double(), v.double()
+    gs = 0.5
+    mr = 0.9 * mr + 0.1 * g.double() * gs
+    vr = 0.999 * vr + 0.001 * (g.double() * gs) ** 2
+    pr = pr - 1e-3 * mr / (vr.sqrt() + 1e-8)
+    ops.adam(p, g, m, v, 1e-3, grad_scale=gs)
+    ok &= report("adam p", p, pr, 1e-6)
+    ok &= report("adam m", m, mr, 1e-6)
+    ok &= report("adam v", v, vr, 1e-6)
+    # l2
+    w = torch.randn(5000, device=dev)
+    g2 = torch.zeros(5000, device=dev)
+    ls = torch.zeros(1, device=dev)
+    ops.l2_reg(w, g2, ls, 0.01)
+    ok &= report("l2 grad", g2, 0.01 * w.double(), 1e-6)
+    ok &= report("l2 loss", ls, (0.005 * (w.double() ** 2).sum()).view(1), 1e-5)
+    return ok
+
+
+@case
+def decoder_kernels():
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    ok = True
+    torch.manual_seed(6)
+    for Cc in (20, 3, 2):
+        for dtype in (0, 1):
+            tdt = ops.torch_dtype(dtype)
+            x = torch.randn(2, 6, 10, 256, device=dev).clamp_min(0).to(tdt)
+            K = torch.randn(256, Cc, device=dev) * 0.05
+            b = torch.randn(Cc, device=dev)
+            s = ops.score_head_fwd(x, K, b, 0.01)
+            ref = 0.01 * (x.double().reshape(-1, 256) @ K.double()) + b.double()
+            ok &= report("head fwd C%d dt%d" % (Cc, dtype), s.reshape(-1, Cc), ref, 1e-5)
+            ds = torch.randn_like(s)
+            dK = torch.empty_like(K)
+            db = torch.empty_like(b)
+            dx = torch.empty_like(x)
+            ops.score_head_bwd(x, K, ds, 0.01, dK, db, dx, mask=True, mask_scale=2.0)
+            ok &= report("head bwd dK", dK, 0.01 * x.double().reshape(-1, 256).t() @ ds.double().reshape(-1, Cc), 1e-5)
+            ok &= report("head bwd db", db, ds.double().reshape(-1, Cc).sum(0), 1e-5)
+            refdx = 0.01 * (ds.double().reshape(-1, Cc) @ K.double().t()).reshape(x.shape) * (x.double() > 0) * 2.0
+            ok &= report("head bwd dx", dx, refdx, 1e-5 if dtype else 5e-3)
+        for s_, (h, w) in ((2, (5, 7)), (8, (4, 6))):
+            k = 2 * s_
+            x = torch.randn(2, h, w, Cc, device=dev)
+            T = torch.randn(k, k, Cc, Cc, device=dev) * 0.1
+            bias = torch.randn(Cc, device=dev)
+            skip = torch.randn(2, h * s_, w * s_, Cc, device=dev)
+            y = ops.upscore_fwd(x, T, bias, s_, skip=skip)
+            xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
+            Tr = T.double().permute(3, 2, 0, 1).contiguous().requires_grad_(True)   # [ci, co, a, b]
+            yr = F.conv_transpose2d(xr, Tr, stride=s_, padding=s_ // 2) + bias.double().view(1, -1, 1, 1)
+            ok &= report("upscore fwd C%d s%d" % (Cc, s_), y, yr.permute(0, 2, 3, 1) + skip.double(), 1e-5)
+            dy = torch.randn_like(y)
+            yr.backward(dy.double().permute(0, 3, 1, 2))
+            dT = torch.empty_like(T)
+            dbias = torch.empty_like(bias)
+            dx = torch.empty_like(x)
+            ops.upscore_bwd(x, T, dy, s_, dT, dbias, dx)
+            ok &= report("upscore bwd dx", dx, xr.grad.permute(0, 2, 3, 1), 1e-5)
+            ok &= report("upscore bwd dT", dT, Tr.grad.permute(2, 3, 1, 0), 1e-5)
+            ok &= report("upscore bwd dbias", dbias, dy.double().sum((0, 1, 2)), 1e-5)
+        # softmax / xent
+        P = 5000
+        z = torch.randn(P, Cc, device=dev) * 3
+        ids = torch.randint(0, Cc, (P,), device=dev)
+        onehot = F.one_hot(ids, Cc).to(torch.uint8)
+        loss = torch.zeros(1, device=dev)
+        dz = torch.empty_like(z)
+        sm = torch.empty_like(z)
+        am = torch.empty(P, dtype=torch.int64, device=dev)
+        ops.softmax_xent(z, onehot, loss, dz, sm, am, grad_scale=1.0 / P)
+        zr = z.double().requires_grad_(True)
+        lr = F.cross_entropy(zr, ids, reduction="sum")
+        lr.backward()
+        ok &= report("xent loss C%d" % Cc, loss, lr.detach().view(1), 1e-5)
+        ok &= report("xent dz", dz, zr.grad / P, 1e-5)
+        ok &= report("softmax", sm, F.softmax(z.double(), -1), 1e-5)
+        ok &= bool((am == z.argmax(-1)).all().item())
+        conf = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
+        ops.confusion_matrix(am, onehot, conf)
+        refc = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
+        refc.view(-1).index_add_(0, ids * Cc + am, torch.ones(P, dtype=torch.int64, device=dev))
+        ok &= bool((conf == refc).all().item())
+        print("  confusion matrix C%d exact: %s" % (Cc, bool((conf == refc).all().item())))
+    return ok
+
+
+def main():
+    args = sys.argv[1:]
+    if not args or args[0] == "list":
+        print("\n".join(CASES))
+        return 0
+    if args[0] == "all":
+        results = {}
+        per_case_timeout = int(os.environ.get("BRINGUP_TIMEOUT", "240"))
+        for name in CASES:
+            t0 = time.time()
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), name], timeout=per_case_timeout,
+                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                out, code = r.stdout, r.returncode
+            except subprocess.TimeoutExpired as e:
+                out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+                code = -999
+            results[name] = code
+            print("==== %s: exit %d (%.1fs)" % (name, code, time.time() - t0))
+            print(out[-6000:])
+            sys.stdout.flush()
+        print(json.dumps(results))
+        return 0 if all(v == 0 for v in results.values()) else 1
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ok = True
+    for name in args:
+        print("case %s" % name)
+        try:
+            r = CASES[name]()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            r = False
+        print("case %s -> %s" % (name, "PASS" if r else "FAIL"))
+        ok &= bool(r)
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
