@@ -46,7 +46,8 @@ EncodeTiledFn get_encode() {
 }
 
 // NHWC activation map: dims (C, W, H, N), box (CH, bw, bh, bn), 128B swizzle, OOB -> 0 (= SAME zero padding).
-int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int W, int C, int bw, int bh, int bn) {
+int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int W, int C, int bw, int bh, int bn,
+                   bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int es = dtype == FCN8_BF16 ? 2 : 4;
@@ -56,7 +57,8 @@ int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dtype == FCN8_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(act N%d H%d W%d C%d box %d,%d,%d) failed: %d", N, H, W, C, bw,
                 bh, bn, (int)r);
@@ -398,10 +400,12 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   const void* xs[3] = {p->x, p->x, p->x_lo};
   const void* ds[3] = {p->dy, p->dy_lo, p->dy};
   for (int s = 0; s < p->nseg; ++s) {
-    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn);
+    const bool atom32 = p->dtype == FCN8_F32;  // MN-major tf32 operands need the 32-byte-granule swizzle
+    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
+                        atom32);
     if (rc) return rc;
     rc = encode_act_map(&maps.b[s], ds[s], p->dtype, p->N, p->H, p->W, p->Cout, 1 << pl.lbw, 1 << pl.lbh,
-                        1 << pl.lbn);
+                        1 << pl.lbn, atom32);
     if (rc) return rc;
   }
   WgradArgs a;

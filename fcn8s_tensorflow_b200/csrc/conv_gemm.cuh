@@ -536,8 +536,9 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
           const uint32_t sa = smem_u32(smem + stage * kStage);
           const uint32_t sb = sa + kAStage;
           // MN-major, 128B swizzle: LBO = stride between 128-byte channel chunks, SBO = stride between 8-pixel groups
-          const uint64_t adesc = make_smem_desc_sw128(sa, kChunkBytes, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, kChunkBytes, 1024);
+          // (tf32: 32-byte-granule swizzle, 4-pixel / 512-byte atoms -- the only MN-major layout the tf32 MMA accepts)
+          const uint64_t adesc = make_smem_desc_sw128(sa, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
+          const uint64_t bdesc = make_smem_desc_sw128(sb, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
 #pragma unroll
           for (int k = 0; k < 64 / KPM; ++k) {
             const uint32_t adv = (k * KPM * 128) >> 4;

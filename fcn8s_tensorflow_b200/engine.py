@@ -1,0 +1,387 @@
+"""FCN-8s forward / backward / Adam engine on libfcn8s_sm100.so.
+
+This is the replacement for what `tf.Session.run` executes in the reference: the external VGG-16 encoder graph
+(fcn8s_tensorflow.py:127-152), `_build_decoder` (:154-237), `_build_optimizer` (:239-259) and `_build_predictor`
+(:261-271).  torch owns the device memory (flat parameter / gradient / Adam buffers, a per-shape activation arena) and
+the stream; every arithmetic operation is a hand-written sm_100a kernel reached through the C ABI
+(include/fcn8s_b200.h).  There is no CPU path: constructing an Engine without a CUDA device or without the built
+library raises.
+
+Precision modes (`precision=`):
+  "bf16"   activations + tensor-core operands bf16, fp32 accumulate (TMEM), fp32 master weights / grads / Adam.
+  "tf32"   activations fp32, operands read as tf32 (10-bit mantissa), fp32 accumulate.
+  "fp32"   activations fp32, error-compensated 3xTF32 products (hi*hi + hi*lo + lo*hi): fp32-faithful (~1e-6).
+The decoder (score heads, transposed convs, loss) is fp32 in every mode.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from . import ops
+
+VGG_BLOCKS = [(1, 64, 2), (2, 128, 2), (3, 256, 3), (4, 512, 3), (5, 512, 3)]
+POOL3_SCALE, POOL4_SCALE = 1e-4, 1e-2          # fcn8s_tensorflow.py:171,182
+BETA1, BETA2, EPS = 0.9, 0.999, 1e-8           # tf.train.AdamOptimizer defaults (:256)
+DECODER_KERNELS = ["pool3_1x1/kernel", "pool4_1x1/kernel", "fc7_1x1/kernel", "fc7_conv2d_trans/kernel",
+                   "fc7_pool4_conv2d_trans/kernel", "fc7_pool4_pool3_conv2d_trans/kernel"]
+
+
+def encoder_layers():
+    """[(name, ksize, cin, cout)] in forward order, fc6/fc7 included."""
+    out = []
+    cin = 3
+    for b, cout, n in VGG_BLOCKS:
+        for i in range(1, n + 1):
+            out.append(("conv%d_%d" % (b, i), 3, cin, cout))
+            cin = cout
+    out.append(("fc6", 7, 512, 4096))
+    out.append(("fc7", 1, 4096, 4096))
+    return out
+
+
+def _wname(layer):
+    return layer + ("/weights" if layer.startswith("fc") else "/filter")
+
+
+def variable_shapes(num_classes):
+    """name -> TF-layout shape of the 42 trainable variables, forward order."""
+    C = num_classes
+    s = OrderedDict()
+    for name, k, cin, cout in encoder_layers():
+        s[_wname(name)] = (k, k, cin, cout)
+        s[name + "/biases"] = (cout,)
+    s["pool3_1x1/kernel"] = (1, 1, 256, C)
+    s["pool3_1x1/bias"] = (C,)
+    s["pool4_1x1/kernel"] = (1, 1, 512, C)
+    s["pool4_1x1/bias"] = (C,)
+    s["fc7_1x1/kernel"] = (1, 1, 4096, C)
+    s["fc7_1x1/bias"] = (C,)
+    s["fc7_conv2d_trans/kernel"] = (4, 4, C, C)
+    s["fc7_conv2d_trans/bias"] = (C,)
+    s["fc7_pool4_conv2d_trans/kernel"] = (4, 4, C, C)
+    s["fc7_pool4_conv2d_trans/bias"] = (C,)
+    s["fc7_pool4_pool3_conv2d_trans/kernel"] = (16, 16, C, C)
+    s["fc7_pool4_pool3_conv2d_trans/bias"] = (C,)
+    return s
+
+
+def flat_layout(num_classes):
+    """Flat-buffer layout in backward-completion order (decoder | fc7 | fc6 | conv5_3 ... conv1_1) so that a gradient
+    all-reduce can start on the big fc6/fc7 blocks while the conv backward still runs.  Every tensor starts on a
+    256-byte boundary.  Returns (OrderedDict name -> (offset_elems, shape), total_elems)."""
+    shapes = variable_shapes(num_classes)
+    order = []
+    for base in ["fc7_pool4_pool3_conv2d_trans", "pool3_1x1", "fc7_pool4_conv2d_trans", "pool4_1x1",
+                 "fc7_conv2d_trans", "fc7_1x1"]:
+        order += [base + "/kernel", base + "/bias"]
+    for name, _, _, _ in reversed(encoder_layers()):
+        order += [_wname(name), name + "/biases"]
+    assert set(order) == set(shapes)
+    layout = OrderedDict()
+    off = 0
+    for n in order:
+        layout[n] = (off, shapes[n])
+        off += int(np.prod(shapes[n]))
+        off = (off + 63) // 64 * 64
+    return layout, off
+
+
+class Engine:
+    def __init__(self, num_classes, precision="bf16", device=None):
+        if not torch.cuda.is_available():
+            raise capi.Fcn8Error("fcn8s_tensorflow_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if precision not in ("bf16", "tf32", "fp32"):
+            raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")
+        if not (1 <= num_classes <= 32):
+            raise ValueError("num_classes must be in [1, 32]")
+        self.lib = capi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        capi.check(self.lib.fcn8_device_check(self.device.index or 0))
+        self.C = num_classes
+        self.precision = precision
+        self.dt = ops.BF16 if precision == "bf16" else ops.F32
+        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.x3 = precision == "fp32"
+        self.kp = 64 if self.dt == ops.BF16 else 32   # padded im2col width of conv1_1
+        self.layers = encoder_layers()
+        self.layout, self.n_flat = flat_layout(num_classes)
+        z = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(self.n_flat, **z)
+        self.grads = torch.zeros(self.n_flat, **z)
+        self.adam_m = torch.zeros(self.n_flat, **z)
+        self.adam_v = torch.zeros(self.n_flat, **z)
+        self.global_step = 0
+        self.loss_buf = torch.zeros(2, **z)   # [0] = sum of per-pixel CE, [1] = L2 regularisation loss
+        self.packed = {}
+        self._packed_dirty = True
+        self._arenas = {}
+        self.world = 1
+        self.allreduce = None  # callable(flat_grad) installed by the data-parallel wrapper
+
+    # ------------------------------------------------------------------ parameters
+    def view(self, name, buf=None):
+        off, shape = self.layout[name]
+        buf = self.params if buf is None else buf
+        return buf[off:off + int(np.prod(shape))].view(shape)
+
+    def load_weights(self, weights):
+        """weights: mapping TF variable name -> array/tensor in TF layout. Missing names raise KeyError."""
+        for name in self.layout:
+            w = weights[name]
+            t = torch.as_tensor(np.asarray(w) if not torch.is_tensor(w) else w).to(torch.float32)
+            if tuple(t.shape) != tuple(self.layout[name][1]):
+                raise ValueError("shape mismatch for %s: %s vs %s" % (name, tuple(t.shape), self.layout[name][1]))
+            self.view(name).copy_(t.to(self.device))
+        self._packed_dirty = True
+
+    def state_dict(self):
+        return OrderedDict((n, self.view(n).detach().cpu().clone()) for n in self.layout)
+
+    def grad_dict(self):
+        return OrderedDict((n, self.view(n, self.grads).detach().cpu().clone()) for n in self.layout)
+
+    def repack(self):
+        """fp32 master weights (TF HWIO) -> tensor-core operand layouts (fprop + dgrad) of every encoder layer."""
+        for name, k, cin, cout in self.layers:
+            w = self.view(_wname(name))
+            if name == "conv1_1":
+                # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
+                self.packed[name] = ops.pack_weights(w, 1, 27, cout, 0, self.dt, cin_pad=self.kp, split=self.x3) + (None, None)
+            else:
+                f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3)
+                d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3)
+                self.packed[name] = f + d
+        self._packed_dirty = False
+
+    # ------------------------------------------------------------------ activation arena
+    def _arena(self, N, H, W):
+        key = (N, H, W)
+        a = self._arenas.get(key)
+        if a is None:
+            if H % 32 or W % 32:
+                raise ValueError("image height and width must be multiples of 32 (got %dx%d): the reference graph's "
+                                 "skip additions (fcn8s_tensorflow.py:213,224) only align for such sizes" % (H, W))
+            a = {}
+            self._arenas[key] = a
+        return a
+
+    def _buf(self, arena, name, shape, dtype):
+        t = arena.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            arena[name] = t
+        return t
+
+    def _split(self, arena, name, x):
+        """3xTF32 operands of x: (hi, lo) in arena buffers; (x, None) in the single-pass modes."""
+        if not self.x3:
+            return x, None
+        hi = self._buf(arena, name + ".hi", x.shape, torch.float32)
+        lo = self._buf(arena, name + ".lo", x.shape, torch.float32)
+        capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), capi.ptr(hi), capi.ptr(lo), x.numel(), ops._stream()))
+        return hi, lo
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, images, keep_prob=1.0, seed=0, train=False):
+        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (an arena buffer)."""
+        if self._packed_dirty:
+            self.repack()
+        N, H, W, _ = images.shape
+        A = self._arena(N, H, W)
+        A["_shape"] = (N, H, W)
+        x = self._buf(A, "im2col", (N, H, W, self.kp), self.tdt)
+        p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, self.dt)
+        capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
+        h, w = H, W
+        li = 0
+        for b, cout, n in VGG_BLOCKS:
+            for i in range(1, n + 1):
+                name, k, cin, _ = self.layers[li]
+                li += 1
+                wp, wlo = self.packed[name][0], self.packed[name][1]
+                out = self._buf(A, name, (N, h, w, cout), self.tdt)
+                xh, xl = self._split(A, "in_" + name, x)
+                bias = self.view(name + "/biases")
+                ops.conv_gemm(xh, wp, cout, 1 if name == "conv1_1" else 3, bias=bias,
+                              flags=ops.EPI_BIAS | ops.EPI_RELU, out=out, x_lo=xl, wp_lo=wlo)
+                x = out
+            h, w = (h + 1) // 2, (w + 1) // 2
+            pooled = self._buf(A, "pool%d" % b, (N, h, w, cout), self.tdt)
+            ops.maxpool_fwd(x, out=pooled)
+            x = pooled
+        drop = train and keep_prob < 1.0
+        for name, k, cin, cout in self.layers[-2:]:
+            wp, wlo = self.packed[name][0], self.packed[name][1]
+            out = self._buf(A, name, (N, h, w, cout), self.tdt)
+            xh, xl = self._split(A, "in_" + name, x)
+            flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0)
+            ops.conv_gemm(xh, wp, cout, k, bias=self.view(name + "/biases"), flags=flags, out=out, x_lo=xl, wp_lo=wlo,
+                          keep_prob=keep_prob if drop else 1.0, seed=self.dropout_seed(seed, name))
+            x = out
+        C = self.C
+        f32 = torch.float32
+        s3 = ops.score_head_fwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), self.view("pool3_1x1/bias"),
+                                POOL3_SCALE, out=self._buf(A, "s3", (N, H // 8, W // 8, C), f32))
+        s4 = ops.score_head_fwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), self.view("pool4_1x1/bias"),
+                                POOL4_SCALE, out=self._buf(A, "s4", (N, H // 16, W // 16, C), f32))
+        s7 = ops.score_head_fwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), self.view("fc7_1x1/bias"), 1.0,
+                                out=self._buf(A, "s7", (N, H // 32, W // 32, C), f32))
+        f4 = ops.upscore_fwd(s7, self.view("fc7_conv2d_trans/kernel"), self.view("fc7_conv2d_trans/bias"), 2, skip=s4,
+                             out=self._buf(A, "f4", (N, H // 16, W // 16, C), f32))
+        f3 = ops.upscore_fwd(f4, self.view("fc7_pool4_conv2d_trans/kernel"), self.view("fc7_pool4_conv2d_trans/bias"),
+                             2, skip=s3, out=self._buf(A, "f3", (N, H // 8, W // 8, C), f32))
+        logits = ops.upscore_fwd(f3, self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
+                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8,
+                                 out=self._buf(A, "logits", (N, H, W, C), f32))
+        return logits
+
+    @staticmethod
+    def dropout_seed(seed, layer):
+        return (int(seed) * 2 + (1 if layer == "fc7" else 0)) & 0xFFFFFFFF
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0):
+        """Forward + backward of optimizer/total_loss (fcn8s_tensorflow.py:250-257) into self.grads.
+        labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2)."""
+        N, H, W, _ = images.shape
+        C = self.C
+        logits = self.forward(images, keep_prob, seed, train=True)
+        A = self._arena(N, H, W)
+        G = self.grads
+        f32 = torch.float32
+        self.loss_buf.zero_()
+        dz = self._buf(A, "dlogits", (N, H, W, C), f32)
+        npx = N * H * W
+        ops.softmax_xent(logits, labels.view(torch.uint8), self.loss_buf[0:1], dz, grad_scale=1.0 / npx)
+        # decoder backward
+        df3 = self._buf(A, "df3", A["f3"].shape, f32)
+        ops.upscore_bwd(A["f3"], self.view("fc7_pool4_pool3_conv2d_trans/kernel"), dz, 8,
+                        self.view("fc7_pool4_pool3_conv2d_trans/kernel", G),
+                        self.view("fc7_pool4_pool3_conv2d_trans/bias", G), df3)
+        df4 = self._buf(A, "df4", A["f4"].shape, f32)
+        ops.upscore_bwd(A["f4"], self.view("fc7_pool4_conv2d_trans/kernel"), df3, 2,
+                        self.view("fc7_pool4_conv2d_trans/kernel", G), self.view("fc7_pool4_conv2d_trans/bias", G), df4)
+        ds7 = self._buf(A, "ds7", A["s7"].shape, f32)
+        ops.upscore_bwd(A["s7"], self.view("fc7_conv2d_trans/kernel"), df4, 2,
+                        self.view("fc7_conv2d_trans/kernel", G), self.view("fc7_conv2d_trans/bias", G), ds7)
+        inv_keep = 1.0 / keep_prob if keep_prob < 1.0 else 1.0
+        # score heads: ds3 = df3, ds4 = df4 (the adds fan the gradient out unchanged)
+        dpool3 = self._buf(A, "d_pool3_head", A["pool3"].shape, self.tdt)
+        ops.score_head_bwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), df3, POOL3_SCALE,
+                           self.view("pool3_1x1/kernel", G).view(256, C), self.view("pool3_1x1/bias", G), dpool3)
+        dpool4 = self._buf(A, "d_pool4_head", A["pool4"].shape, self.tdt)
+        ops.score_head_bwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), df4, POOL4_SCALE,
+                           self.view("pool4_1x1/kernel", G).view(512, C), self.view("pool4_1x1/bias", G), dpool4)
+        # fc7 output: dropout + ReLU backward folded into the head's dx (mask = fc7 > 0, scale 1/keep_prob)
+        dy = self._buf(A, "d_fc7", A["fc7"].shape, self.tdt)
+        ops.score_head_bwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), ds7, 1.0,
+                           self.view("fc7_1x1/kernel", G).view(4096, C), self.view("fc7_1x1/bias", G), dy,
+                           mask=True, mask_scale=inv_keep)
+        if l2_rate != 0.0:
+            for kname in DECODER_KERNELS:
+                ops.l2_reg(self.view(kname).reshape(-1), self.view(kname, G).reshape(-1), self.loss_buf[1:2], l2_rate)
+        # encoder backward
+        for li in range(len(self.layers) - 1, -1, -1):
+            name, k, cin, cout = self.layers[li]
+            x_in = self._layer_input(A, li)
+            gw = self.view(_wname(name), G)
+            ops.bias_grad(dy, self.view(name + "/biases", G))
+            dyh, dyl = self._split(A, "dy_" + name, dy)
+            if name == "conv1_1":
+                xh, xl = (A["in_conv1_1.hi"], A["in_conv1_1.lo"]) if self.x3 else (x_in, None)
+                ops.wgrad_gemm(xh, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl)
+                break
+            xh, xl = (A["in_%s.hi" % name], A["in_%s.lo" % name]) if self.x3 else (x_in, None)
+            ops.wgrad_gemm(xh, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl)
+            wpd, wpd_lo = self.packed[name][2], self.packed[name][3]
+            dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
+            prev_name = self.layers[li - 1][0]
+            if self._input_is_pool(li):
+                # x_in is a pool output: no ReLU mask here (the pool backward applies it); add the score-head
+                # gradient at pool3 / pool4 (AddN of the two consumers)
+                pool_idx = self._pool_index(li)
+                res = dpool3 if pool_idx == 3 else (dpool4 if pool_idx == 4 else None)
+                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_RESIDUAL if res is not None else 0, residual=res, out=dx,
+                              x_lo=dyl, wp_lo=wpd_lo)
+                src = A[prev_name]  # pre-pool activation (post-ReLU)
+                dpre = self._buf(A, "dpre_" + prev_name, src.shape, self.tdt)
+                ops.maxpool_bwd(src, dx, out=dpre)
+                dy = dpre
+            else:
+                # ReLU (and for fc6 -> dropout) backward of the producer fused as an epilogue mask on its output
+                scale = inv_keep if prev_name == "fc6" else 1.0
+                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_MASK, mask_src=x_in, mask_scale=scale, out=dx,
+                              x_lo=dyl, wp_lo=wpd_lo)
+                dy = dx
+        return self.loss_buf
+
+    def _input_is_pool(self, li):
+        name = self.layers[li][0]
+        return name == "fc6" or (name.startswith("conv") and name.endswith("_1") and name != "conv1_1")
+
+    def _pool_index(self, li):
+        name = self.layers[li][0]
+        return 5 if name == "fc6" else int(name[4]) - 1
+
+    def _layer_input(self, A, li):
+        name = self.layers[li][0]
+        if name == "conv1_1":
+            return A["im2col"]
+        if self._input_is_pool(li):
+            return A["pool%d" % self._pool_index(li)]
+        return A[self.layers[li - 1][0]]
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, lr):
+        """TF-form Adam over the flat buffer (one launch), then global_step += 1 (fcn8s_tensorflow.py:256-257)."""
+        if self.allreduce is not None:
+            self.allreduce(self.grads)
+        t = self.global_step + 1
+        lr_t = float(lr) * float(np.sqrt(1.0 - BETA2 ** t) / (1.0 - BETA1 ** t))
+        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world)
+        self.global_step = t
+        self._packed_dirty = True
+
+    def train_step(self, images, labels, lr, keep_prob=0.5, l2_rate=0.0, seed=None):
+        """One `sess.run([train_op, total_loss, global_step])` (fcn8s_tensorflow.py:565-572).
+        Returns the device tensor loss_buf; total_loss = loss_buf[0] / (N*H*W) + loss_buf[1] (see `loss_value`)."""
+        if seed is None:
+            seed = self.global_step
+        self.loss_and_backward(images, labels, keep_prob, l2_rate, seed)
+        self.adam_step(lr)
+        return self.loss_buf
+
+    def loss_value(self, images_shape):
+        N, H, W = images_shape[0], images_shape[1], images_shape[2]
+        v = self.loss_buf.tolist()
+        return v[0] / float(N * H * W) + v[1]
+
+    # ------------------------------------------------------------------ predictor / evaluation
+    def predict(self, images, argmax=True):
+        """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1."""
+        N, H, W, _ = images.shape
+        logits = self.forward(images, 1.0, 0, train=False)
+        if argmax:
+            out = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
+            ops.softmax_xent(logits, argmax=out)
+        else:
+            out = torch.empty((N, H, W, self.C), dtype=torch.float32, device=self.device)
+            ops.softmax_xent(logits, softmax=out)
+        return out
+
+    def eval_step(self, images, labels, conf, l2_rate=0.0):
+        """One metric update (fcn8s_tensorflow.py:685-689): forward at keep_prob 1, total_loss, argmax, confusion
+        matrix accumulate (conf: int64 [C,C] device tensor, conf[label, prediction])."""
+        N, H, W, _ = images.shape
+        logits = self.forward(images, 1.0, 0, train=False)
+        self.loss_buf.zero_()
+        am = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
+        lab = labels.view(torch.uint8)
+        ops.softmax_xent(logits, lab, self.loss_buf[0:1], argmax=am)
+        if l2_rate != 0.0:
+            for kname in DECODER_KERNELS:
+                ops.l2_reg(self.view(kname).reshape(-1), None, self.loss_buf[1:2], l2_rate)
+        ops.confusion_matrix(am, lab, conf)
+        return self.loss_buf

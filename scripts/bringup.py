@@ -147,6 +147,27 @@ def conv_tf32x3():
 
 
 @case
+def tf32_truncation_probe():
+    """Does kind::tf32 truncate or round the low 13 mantissa bits of its fp32 operands?  (Decides whether the hi part
+    of the 3xTF32 split has to be materialised.)"""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    x = torch.randn(1, 8, 16, 64, device=dev)
+    w = torch.randn(3, 3, 64, 64, device=dev) / 24.0
+    wp, _ = ops.pack_weights(w, 3, 64, 64, 0, 1)
+    xh, _ = ops.split_tf32(x)
+    wph = (wp.view(torch.int32) & -8192).view(torch.float32)
+    y_full = ops.conv_gemm(x, wp, 64, 3)
+    y_trunc = ops.conv_gemm(xh, wph.contiguous(), 64, 3)
+    torch.cuda.synchronize()
+    same = torch.equal(y_full, y_trunc)
+    print("  tf32 operands truncated by hardware (bitwise equal outputs): %s; max diff %.3e" %
+          (same, (y_full - y_trunc).abs().max().item()))
+    return True
+
+
+@case
 def conv_epilogues():
     """dgrad-style epilogue: residual add + relu mask with scale; and dropout."""
     from fcn8s_tensorflow_b200 import ops
