@@ -10,10 +10,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfcn8s_sm100.so")
 
 BF16, F32 = 0, 1
-EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32 = 1, 2, 4, 8, 16, 64
 
 EXPORTS = [
-    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_debug_set", "fcn8_preprocess_im2col",
+    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_preprocess_im2col",
     "fcn8_conv_gemm_workspace_bytes", "fcn8_conv_gemm", "fcn8_wgrad_gemm_workspace_bytes", "fcn8_wgrad_gemm",
     "fcn8_pack_weights", "fcn8_split_tf32", "fcn8_maxpool_fwd", "fcn8_maxpool_bwd", "fcn8_bias_grad_workspace_bytes",
     "fcn8_bias_grad", "fcn8_score_head_fwd", "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
@@ -95,6 +95,7 @@ def load():
     lib.fcn8_version.restype = C.c_int32
     lib.fcn8_last_error.restype = C.c_char_p
     lib.fcn8_device_check.argtypes = [C.c_int32]
+    lib.fcn8_launch_count.restype = C.c_uint64
     lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),

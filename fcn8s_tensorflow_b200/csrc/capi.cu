@@ -13,6 +13,10 @@
 
 using namespace fcn8;
 
+namespace fcn8 {
+unsigned long long g_launch_count = 0;
+}
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -182,7 +186,7 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  conv_gemm_kernel<BN, TF32><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, a);
+  { count_launch(); conv_gemm_kernel<BN, TF32><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, a); }
   return cudaGetLastError();
 }
 
@@ -203,7 +207,7 @@ cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  wgrad_gemm_kernel<BN, TF32><<<grid, kGemmThreads, smem, st>>>(maps, a);
+  { count_launch(); wgrad_gemm_kernel<BN, TF32><<<grid, kGemmThreads, smem, st>>>(maps, a); }
   return cudaGetLastError();
 }
 
@@ -267,6 +271,7 @@ int32_t fcn8_device_check(int32_t dev) {
                                     prop.major, prop.minor);
   return 0;
 }
+uint64_t fcn8_launch_count(void) { return g_launch_count; }
 int32_t fcn8_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
   g_debug[key] = value;
@@ -340,7 +345,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.tiles_n = pl.tiles_n;
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
-  a.flags = p->flags & 31;
+  a.flags = p->flags & (31 | 64);
   a.mask_scale = p->mask_scale;
   a.seed = p->seed;
   if (p->flags & FCN8_EPI_DROPOUT) {
@@ -469,9 +474,10 @@ int32_t fcn8_pack_weights(const Fcn8PackParams* p, void* stream) {
 }
 
 int32_t fcn8_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
-  if (!x || !hi || !lo) return fail(FCN8_ERR_BAD_SHAPE, "split_tf32: null pointer");
+  if (!x || (!hi && !lo)) return fail(FCN8_ERR_BAD_SHAPE, "split_tf32: null pointer");
   if (n % 4) return fail(FCN8_ERR_BAD_SHAPE, "split_tf32: n must be a multiple of 4");
-  if (!aligned16(x) || !aligned16(hi) || !aligned16(lo)) return fail(FCN8_ERR_BAD_ALIGN, "split_tf32: alignment");
+  if (!aligned16(x) || (hi && !aligned16(hi)) || (lo && !aligned16(lo)))
+    return fail(FCN8_ERR_BAD_ALIGN, "split_tf32: alignment");
   cudaError_t e = launch_split_tf32(x, hi, lo, n, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "split_tf32 launch");
 }

@@ -29,7 +29,14 @@ enum EpilogueFlags : int {
   EPI_MASK = 8,      // * (mask_src[index] > 0) * mask_scale   (ReLU / dropout backward)
   EPI_RESIDUAL = 16, // + residual[index]                      (gradient fan-in at pool3 / pool4)
   EPI_PARTIAL = 32,  // raw fp32 partial sums to the split-K workspace, no epilogue math
+  EPI_ROUND_TF32 = 64,  // fp32 outputs rounded to the nearest tf32 (single-pass tf32 mode: the MMA truncates operands)
 };
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 // Counter-based uniform in [0,1): one 32-bit mix of (seed, element index). Shared by the forward dropout epilogue,
 // the split-K reduce epilogue and (host side, numpy) the parity tests that inject the same mask into the oracle.
@@ -189,6 +196,10 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
   }
   OutT* o = reinterpret_cast<OutT*>(g.out) + idx;
   if constexpr (TF32) {
+    if (g.flags & EPI_ROUND_TF32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = round_tf32(f[i]);
+    }
     float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);

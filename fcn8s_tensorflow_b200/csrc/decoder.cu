@@ -149,10 +149,10 @@ cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float
                             float scale, int dtype, cudaStream_t st) {
   const int blocks = grid_for(static_cast<size_t>(P) * 32, 256);
   if (dtype == 0)
-    head_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, b, s, P, Cin, C,
-                                                           scale);
+    { count_launch(); head_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, b, s, P, Cin, C,
+                                                           scale); }
   else
-    head_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, b, s, P, Cin, C, scale);
+    { count_launch(); head_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, b, s, P, Cin, C, scale); }
   return cudaGetLastError();
 }
 int head_bwd_blocks(long long P) {
@@ -170,11 +170,11 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   float* ws_b = ws + static_cast<size_t>(nb) * Cin * C;      // [nb][C]
   dim3 grid(nb, (Cin + 255) / 256);
   if (dtype == 0)
-    head_bwd_w_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ds, ws_k, P, Cin, C,
-                                                           ppb);
+    { count_launch(); head_bwd_w_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ds, ws_k, P, Cin, C,
+                                                           ppb); }
   else
-    head_bwd_w_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ds, ws_k, P, Cin, C, ppb);
-  rows_colsum_kernel<<<nb, 256, 0, st>>>(ds, ws_b, P, C, ppb);
+    { count_launch(); head_bwd_w_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ds, ws_k, P, Cin, C, ppb); }
+  { count_launch(); rows_colsum_kernel<<<nb, 256, 0, st>>>(ds, ws_b, P, C, ppb); }
   cudaError_t e = launch_colsum(ws_k, dK, nb, Cin * C, scale, 0, st);
   if (e != cudaSuccess) return e;
   e = launch_colsum(ws_b, db, nb, C, 1.f, 0, st);
@@ -182,12 +182,12 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   if (dx) {
     const int blocks = grid_for(static_cast<size_t>(P) * Cin, 256);
     if (dtype == 0)
-      head_bwd_x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, ds,
+      { count_launch(); head_bwd_x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, ds,
                                                                static_cast<__nv_bfloat16*>(dx), P, Cin, C, scale, mask,
-                                                               mask_scale);
+                                                               mask_scale); }
     else
-      head_bwd_x_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, ds, static_cast<float*>(dx), P,
-                                                       Cin, C, scale, mask, mask_scale);
+      { count_launch(); head_bwd_x_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, ds, static_cast<float*>(dx), P,
+                                                       Cin, C, scale, mask, mask_scale); }
   }
   return cudaGetLastError();
 }
@@ -351,7 +351,7 @@ cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias
   int gx = grid_for(blocks_total, 128, (148 * 8) / (s * s) + 1);
   dim3 grid(gx, s * s);
   const size_t sm = static_cast<size_t>(4) * C * C * sizeof(float);
-  upscore_fwd_kernel<<<grid, 128, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s);
+  { count_launch(); upscore_fwd_kernel<<<grid, 128, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s); }
   return cudaGetLastError();
 }
 int upscore_bwd_splits(int N, int h, int w, int s) {
@@ -371,7 +371,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
   {
     const int nb = head_bwd_blocks(Pout);
     const long long ppb = (Pout + nb - 1) / nb;
-    rows_colsum_kernel<<<nb, 256, 0, st>>>(dy, ws, Pout, C, ppb);
+    { count_launch(); rows_colsum_kernel<<<nb, 256, 0, st>>>(dy, ws, Pout, C, ppb); }
     cudaError_t e = launch_colsum(ws, dbias, nb, C, 1.f, 0, st);
     if (e != cudaSuccess) return e;
   }
@@ -379,7 +379,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
   {
     const int nsplit = upscore_bwd_splits(N, h, w, s);
     dim3 grid(k * k, nsplit);
-    upscore_bwd_w_kernel<<<grid, 256, 0, st>>>(x, dy, ws + 128 * CMAX, N, h, w, C, s, nsplit);
+    { count_launch(); upscore_bwd_w_kernel<<<grid, 256, 0, st>>>(x, dy, ws + 128 * CMAX, N, h, w, C, s, nsplit); }
     cudaError_t e = launch_colsum(ws + 128 * CMAX, dT, nsplit, k * k * C * C, 1.f, 0, st);
     if (e != cudaSuccess) return e;
   }
@@ -387,7 +387,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
     const size_t total = static_cast<size_t>(N) * h * w;
     const size_t sm = static_cast<size_t>(k) * C * C * sizeof(float);
     cudaFuncSetAttribute(upscore_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-    upscore_bwd_x_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, sm, st>>>(dy, T, dx, N, h, w, C, s);
+    { count_launch(); upscore_bwd_x_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, sm, st>>>(dy, T, dx, N, h, w, C, s); }
   }
   return cudaGetLastError();
 }
@@ -461,7 +461,7 @@ __global__ void softmax_xent_kernel(const float* __restrict__ z, const uint8_t* 
 }
 cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* sm,
                                 long long* amax, long long P, int C, float gscale, cudaStream_t st) {
-  softmax_xent_kernel<<<grid_for(P, 256, 148 * 8), 256, 0, st>>>(z, labels, loss_sum, dz, sm, amax, P, C, gscale);
+  { count_launch(); softmax_xent_kernel<<<grid_for(P, 256, 148 * 8), 256, 0, st>>>(z, labels, loss_sum, dz, sm, amax, P, C, gscale); }
   return cudaGetLastError();
 }
 
@@ -491,7 +491,7 @@ __global__ void confusion_kernel(const long long* __restrict__ pred, const uint8
 }
 cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
                              cudaStream_t st) {
-  confusion_kernel<<<grid_for(P, 256, 148 * 4), 256, 0, st>>>(pred, onehot, conf, P, C);
+  { count_launch(); confusion_kernel<<<grid_for(P, 256, 148 * 4), 256, 0, st>>>(pred, onehot, conf, P, C); }
   return cudaGetLastError();
 }
 

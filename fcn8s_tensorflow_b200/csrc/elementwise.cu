@@ -62,9 +62,9 @@ cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W
   const size_t total = static_cast<size_t>(N) * H * W * 8;
   const int blocks = grid_for(total, 256);
   if (dtype == 0)
-    preprocess_im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(out), N, H, W);
+    { count_launch(); preprocess_im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(out), N, H, W); }
   else
-    preprocess_im2col_kernel<float><<<blocks, 256, 0, st>>>(img, static_cast<float*>(out), N, H, W);
+    { count_launch(); preprocess_im2col_kernel<float><<<blocks, 256, 0, st>>>(img, static_cast<float*>(out), N, H, W); }
   return cudaGetLastError();
 }
 
@@ -194,11 +194,11 @@ cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int 
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
   const int blocks = grid_for(total, 256);
   if (dtype == 0)
-    maxpool_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
-                                                              static_cast<__nv_bfloat16*>(y), N, H, W, C);
+    { count_launch(); maxpool_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                              static_cast<__nv_bfloat16*>(y), N, H, W, C); }
   else
-    maxpool_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), N, H, W,
-                                                      C);
+    { count_launch(); maxpool_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), N, H, W,
+                                                      C); }
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
@@ -207,12 +207,12 @@ cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, i
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
   const int blocks = grid_for(total, 256);
   if (dtype == 0)
-    maxpool_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+    { count_launch(); maxpool_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                               static_cast<const __nv_bfloat16*>(dy),
-                                                              static_cast<__nv_bfloat16*>(dx), N, H, W, C);
+                                                              static_cast<__nv_bfloat16*>(dx), N, H, W, C); }
   else
-    maxpool_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy),
-                                                      static_cast<float*>(dx), N, H, W, C);
+    { count_launch(); maxpool_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy),
+                                                      static_cast<float*>(dx), N, H, W, C); }
   return cudaGetLastError();
 }
 
@@ -277,19 +277,27 @@ cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int 
   const int RL = 256 / cvb;
   const size_t sm = static_cast<size_t>(RL) * cvb * vec * sizeof(float);
   if (dtype == 0)
-    bias_grad_stage1<__nv_bfloat16><<<grid, 256, sm, st>>>(static_cast<const __nv_bfloat16*>(dy), ws, P, C, cvb, rpb);
+    { count_launch(); bias_grad_stage1<__nv_bfloat16><<<grid, 256, sm, st>>>(static_cast<const __nv_bfloat16*>(dy), ws, P, C, cvb, rpb); }
   else
-    bias_grad_stage1<float><<<grid, 256, sm, st>>>(static_cast<const float*>(dy), ws, P, C, cvb, rpb);
-  colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, db, nb, C, 1.f, 0);
+    { count_launch(); bias_grad_stage1<float><<<grid, 256, sm, st>>>(static_cast<const float*>(dy), ws, P, C, cvb, rpb); }
+  { count_launch(); colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, db, nb, C, 1.f, 0); }
   return cudaGetLastError();
 }
 cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st) {
-  colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, out, nb, C, scale, accumulate);
+  { count_launch(); colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, out, nb, C, scale, accumulate); }
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// fp32 -> nearest tf32 (10-bit mantissa, low 13 bits zero).  The tensor core TRUNCATES fp32 operands to tf32
+// (measured: scripts/bringup.py tf32_truncation_probe), which is a biased error; rounding here first makes the
+// hardware's truncation exact and the split hi + lo unbiased.
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 template <typename T>
 __device__ __forceinline__ void store_packed(T* out, T* out_lo, size_t idx, float v) {
@@ -297,11 +305,11 @@ __device__ __forceinline__ void store_packed(T* out, T* out_lo, size_t idx, floa
     out[idx] = __float2bfloat16_rn(v);
   } else {
     if (out_lo) {
-      const float h = tf32_hi(v);
-      out[idx] = h;
-      out_lo[idx] = v - h;
-    } else {
+      // 3xTF32 operands: the MMA itself truncates `out` to its tf32 high part; lo = the exact remainder, rounded
       out[idx] = v;
+      out_lo[idx] = tf32_hi(v - tf32_trunc(v));
+    } else {
+      out[idx] = tf32_hi(v);  // single-pass tf32: pre-round so that the MMA's truncation is exact
     }
   }
 }
@@ -346,36 +354,44 @@ cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int 
   if (mode == 0) {
     dim3 grid((Cout + 31) / 32, (CinPad + 31) / 32, taps), block(32, 8);
     if (dtype == 0)
-      pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
-                                                               Cout, CinPad);
+      { count_launch(); pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+                                                               Cout, CinPad); }
     else
-      pack_fprop_kernel<float><<<grid, block, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
-                                                       Cin, Cout, CinPad);
+      { count_launch(); pack_fprop_kernel<float><<<grid, block, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+                                                       Cin, Cout, CinPad); }
   } else {
     const size_t total = static_cast<size_t>(taps) * Cin * Cout;
     const int blocks = grid_for(total, 256);
     if (dtype == 0)
-      pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
-                                                               Cout);
+      { count_launch(); pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+                                                               Cout); }
     else
-      pack_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
-                                                       Cin, Cout);
+      { count_launch(); pack_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+                                                       Cin, Cout); }
   }
   return cudaGetLastError();
 }
 
+// hi == nullptr: lo = rna(x - trunc(x))  (the MMA truncates x itself, so x is its own "hi" operand)
+// lo == nullptr: hi = rna(x)               (single-pass tf32 operand rounding)
+// both:          hi = trunc(x), lo = rna(x - hi)
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
                                   size_t n4) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    reinterpret_cast<float4*>(hi)[i] = h;
-    reinterpret_cast<float4*>(lo)[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (!lo) {
+      reinterpret_cast<float4*>(hi)[i] = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      continue;
+    }
+    const float4 h = make_float4(tf32_trunc(v.x), tf32_trunc(v.y), tf32_trunc(v.z), tf32_trunc(v.w));
+    if (hi) reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] =
+        make_float4(tf32_hi(v.x - h.x), tf32_hi(v.y - h.y), tf32_hi(v.z - h.z), tf32_hi(v.w - h.w));
   }
 }
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
-  split_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, hi, lo, n / 4);
+  { count_launch(); split_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, hi, lo, n / 4); }
   return cudaGetLastError();
 }
 
@@ -428,6 +444,12 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[e] = m[e] > 0.f ? f[e] * g.mask_scale : 0.f;
     }
+    if constexpr (sizeof(T) == 4) {
+      if (g.flags & EPI_ROUND_TF32) {
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) f[e] = round_tf32(f[e]);
+      }
+    }
     V::store(reinterpret_cast<T*>(g.out) + idx, f);
   }
 }
@@ -436,9 +458,9 @@ cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n
   const int vec = dtype == 0 ? 8 : 4;
   const int blocks = grid_for(n_elems / vec, 256);
   if (dtype == 0)
-    conv_splitk_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g);
+    { count_launch(); conv_splitk_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
   else
-    conv_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g);
+    { count_launch(); conv_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
   return cudaGetLastError();
 }
 
@@ -463,7 +485,7 @@ __global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, fl
 cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
                                        int ldc, cudaStream_t st) {
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
-  wgrad_splitk_reduce_kernel<<<grid_for(n4, 256), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc);
+  { count_launch(); wgrad_splitk_reduce_kernel<<<grid_for(n4, 256), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc); }
   return cudaGetLastError();
 }
 
@@ -504,7 +526,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
                         float eps, float gscale, cudaStream_t st) {
-  adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale); }
   return cudaGetLastError();
 }
 
@@ -528,7 +550,7 @@ __global__ void l2_reg_kernel(const float* __restrict__ w, float* __restrict__ g
   }
 }
 cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st) {
-  l2_reg_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(w, g, loss, n, rate);
+  { count_launch(); l2_reg_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(w, g, loss, n, rate); }
   return cudaGetLastError();
 }
 

@@ -8,6 +8,11 @@ namespace fcn8 {
 
 struct ConvGemmArgs;
 
+// Every kernel launch of the library goes through this counter (fcn8_launch_count() in the C ABI): it is what
+// bench.py reports as gpu_launches.
+extern unsigned long long g_launch_count;
+inline void count_launch() { ++g_launch_count; }
+
 // elementwise.cu
 cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st);
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);

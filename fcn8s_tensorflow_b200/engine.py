@@ -105,6 +105,7 @@ class Engine:
         self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.x3 = precision == "fp32"
         self.kp = 64 if self.dt == ops.BF16 else 32   # padded im2col width of conv1_1
+        self.rnd = ops.EPI_ROUND_TF32 if precision == "tf32" else 0
         self.layers = encoder_layers()
         self.layout, self.n_flat = flat_layout(num_classes)
         z = dict(dtype=torch.float32, device=self.device)
@@ -175,13 +176,13 @@ class Engine:
         return t
 
     def _split(self, arena, name, x):
-        """3xTF32 operands of x: (hi, lo) in arena buffers; (x, None) in the single-pass modes."""
+        """3xTF32 operands of x: (x, lo) with lo = round_tf32(x - trunc_tf32(x)) in an arena buffer -- the tensor core
+        truncates x to its tf32 high part by itself; (x, None) in the single-pass modes."""
         if not self.x3:
             return x, None
-        hi = self._buf(arena, name + ".hi", x.shape, torch.float32)
         lo = self._buf(arena, name + ".lo", x.shape, torch.float32)
-        capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), capi.ptr(hi), capi.ptr(lo), x.numel(), ops._stream()))
-        return hi, lo
+        capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), None, capi.ptr(lo), x.numel(), ops._stream()))
+        return x, lo
 
     # ------------------------------------------------------------------ forward
     def forward(self, images, keep_prob=1.0, seed=0, train=False):
@@ -194,6 +195,8 @@ class Engine:
         x = self._buf(A, "im2col", (N, H, W, self.kp), self.tdt)
         p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, self.dt)
         capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
+        if self.precision == "tf32":   # single-pass tf32: operands pre-rounded (the MMA truncates)
+            capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), capi.ptr(x), None, x.numel(), ops._stream()))
         h, w = H, W
         li = 0
         for b, cout, n in VGG_BLOCKS:
@@ -205,7 +208,7 @@ class Engine:
                 xh, xl = self._split(A, "in_" + name, x)
                 bias = self.view(name + "/biases")
                 ops.conv_gemm(xh, wp, cout, 1 if name == "conv1_1" else 3, bias=bias,
-                              flags=ops.EPI_BIAS | ops.EPI_RELU, out=out, x_lo=xl, wp_lo=wlo)
+                              flags=ops.EPI_BIAS | ops.EPI_RELU | self.rnd, out=out, x_lo=xl, wp_lo=wlo)
                 x = out
             h, w = (h + 1) // 2, (w + 1) // 2
             pooled = self._buf(A, "pool%d" % b, (N, h, w, cout), self.tdt)
@@ -216,7 +219,7 @@ class Engine:
             wp, wlo = self.packed[name][0], self.packed[name][1]
             out = self._buf(A, name, (N, h, w, cout), self.tdt)
             xh, xl = self._split(A, "in_" + name, x)
-            flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0)
+            flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0) | self.rnd
             ops.conv_gemm(xh, wp, cout, k, bias=self.view(name + "/biases"), flags=flags, out=out, x_lo=xl, wp_lo=wlo,
                           keep_prob=keep_prob if drop else 1.0, seed=self.dropout_seed(seed, name))
             x = out
@@ -290,10 +293,10 @@ class Engine:
             ops.bias_grad(dy, self.view(name + "/biases", G))
             dyh, dyl = self._split(A, "dy_" + name, dy)
             if name == "conv1_1":
-                xh, xl = (A["in_conv1_1.hi"], A["in_conv1_1.lo"]) if self.x3 else (x_in, None)
+                xh, xl = (x_in, A["in_conv1_1.lo"]) if self.x3 else (x_in, None)
                 ops.wgrad_gemm(xh, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl)
                 break
-            xh, xl = (A["in_%s.hi" % name], A["in_%s.lo" % name]) if self.x3 else (x_in, None)
+            xh, xl = (x_in, A["in_%s.lo" % name]) if self.x3 else (x_in, None)
             ops.wgrad_gemm(xh, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl)
             wpd, wpd_lo = self.packed[name][2], self.packed[name][3]
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
@@ -303,7 +306,8 @@ class Engine:
                 # gradient at pool3 / pool4 (AddN of the two consumers)
                 pool_idx = self._pool_index(li)
                 res = dpool3 if pool_idx == 3 else (dpool4 if pool_idx == 4 else None)
-                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_RESIDUAL if res is not None else 0, residual=res, out=dx,
+                ops.conv_gemm(dyh, wpd, cin, k, flags=(ops.EPI_RESIDUAL if res is not None else 0) | self.rnd,
+                              residual=res, out=dx,
                               x_lo=dyl, wp_lo=wpd_lo)
                 src = A[prev_name]  # pre-pool activation (post-ReLU)
                 dpre = self._buf(A, "dpre_" + prev_name, src.shape, self.tdt)
@@ -312,7 +316,7 @@ class Engine:
             else:
                 # ReLU (and for fc6 -> dropout) backward of the producer fused as an epilogue mask on its output
                 scale = inv_keep if prev_name == "fc6" else 1.0
-                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_MASK, mask_src=x_in, mask_scale=scale, out=dx,
+                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
                               x_lo=dyl, wp_lo=wpd_lo)
                 dy = dx
         return self.loss_buf

@@ -69,9 +69,9 @@ def _load_npz_weights(path, num_classes):
 class FCN8s:
 
     def __init__(self, model_load_dir=None, tags=None, vgg16_dir=None, num_classes=None, variables_load_dir=None, *,
-                 precision="bf16", device=None, seed=2):
+                 precision="bf16", device=None, seed=2, weights=None, data_parallel=False):
         # fcn8s_tensorflow.py:40-41
-        if (model_load_dir is None) and (vgg16_dir is None or num_classes is None):
+        if (weights is None) and (model_load_dir is None) and (vgg16_dir is None or num_classes is None):
             raise ValueError("You must provide either both `model_load_dir` and `tags` or both `vgg16_dir` and `num_classes`.")
 
         self.variables_load_dir = variables_load_dir
@@ -91,7 +91,9 @@ class FCN8s:
         self.g_step = None
 
         adam_state = None
-        if model_load_dir is not None:
+        if weights is not None:
+            self.num_classes = num_classes = int(np.asarray(weights["fc7_1x1/bias"]).shape[0])
+        elif model_load_dir is not None:
             weights = _load_npz_weights(model_load_dir, None)
             self.num_classes = num_classes = int(weights["fc7_1x1/bias"].shape[0])
             adam_state = weights
@@ -107,6 +109,10 @@ class FCN8s:
 
         self.engine = Engine(num_classes, precision=precision, device=device)
         self.engine.load_weights(weights)
+        if data_parallel:
+            from . import dist as _dist
+            _dist.attach(self.engine)
+            _dist.broadcast_parameters(self.engine)
         if adam_state is not None:
             self._restore_optimizer(adam_state)
         if variables_load_dir is not None and model_load_dir is None:

@@ -8,9 +8,46 @@ import ctypes as C
 import torch
 
 from . import _capi as capi
-from ._capi import BF16, F32, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL  # noqa: F401
+from ._capi import BF16, F32, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32  # noqa: F401
 
 _workspaces = {}
+
+
+class KernelTimer:
+    """Optional per-launch CUDA-event timing of the tensor-core GEMM kernels on the launching stream (bench.py's
+    roofline numbers). Install with `ops.TIMER = KernelTimer()`; records (tag, algorithmic flops, start, end)."""
+
+    def __init__(self):
+        self.records = []
+        self._pool = []
+
+    def _event(self):
+        return self._pool.pop() if self._pool else torch.cuda.Event(enable_timing=True)
+
+    def start(self):
+        e = self._event()
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def stop(self, tag, flops, e0):
+        e1 = self._event()
+        e1.record(torch.cuda.current_stream())
+        self.records.append((tag, flops, e0, e1))
+
+    def summary(self):
+        """tag -> dict(launches, flops, ms); call after a synchronize. Clears the records."""
+        out = {}
+        for tag, flops, e0, e1 in self.records:
+            d = out.setdefault(tag, dict(launches=0, flops=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += flops
+            d["ms"] += e0.elapsed_time(e1)
+            self._pool += [e0, e1]
+        self.records = []
+        return out
+
+
+TIMER = None
 
 
 def torch_dtype(dtype):
@@ -77,6 +114,7 @@ def pack_weights(w, ksize, cin, cout, mode, dtype, cin_pad=None, split=False):
 
 
 def split_tf32(x):
+    """(trunc_tf32(x), round_tf32(x - trunc_tf32(x)))"""
     _chk_cuda(x)
     hi, lo = torch.empty_like(x), torch.empty_like(x)
     capi.check(capi.load().fcn8_split_tf32(capi.ptr(x), capi.ptr(hi), capi.ptr(lo), x.numel(), _stream()))
@@ -98,7 +136,10 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
+    e0 = TIMER.start() if TIMER is not None else None
     capi.check(lib.fcn8_conv_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    if e0 is not None:
+        TIMER.stop("conv_gemm", 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
     return out
 
 
@@ -113,7 +154,10 @@ def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_spl
     lib = capi.load()
     nbytes = lib.fcn8_wgrad_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
+    e0 = TIMER.start() if TIMER is not None else None
     capi.check(lib.fcn8_wgrad_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    if e0 is not None:
+        TIMER.stop("wgrad_gemm", 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
     return out
 
 

@@ -46,13 +46,16 @@ enum {
   FCN8_EPI_RELU = 2,
   FCN8_EPI_DROPOUT = 4,
   FCN8_EPI_MASK = 8,
-  FCN8_EPI_RESIDUAL = 16
+  FCN8_EPI_RESIDUAL = 16,
+  FCN8_EPI_ROUND_TF32 = 64 /* FCN8_F32 only: round outputs to the nearest tf32 (the MMA truncates its operands) */
 };
 
 int32_t fcn8_version(void);
 const char* fcn8_last_error(void);
 /* 0 iff device `dev` is compute capability 10.x (B200); the kernels are sm_100a-only. */
 int32_t fcn8_device_check(int32_t dev);
+/* number of CUDA kernels this library has launched in this process so far (what bench.py reports as gpu_launches). */
+uint64_t fcn8_launch_count(void);
 /* bring-up knobs (descriptor variants) -- tests only. */
 int32_t fcn8_debug_set(int32_t key, int32_t value);
 
@@ -115,7 +118,8 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
 /* ---- weight packing: fp32 master weights in TF layout [k,k,Cin,Cout] (HWIO) -> tensor-core operand layout.
  * mode 0 (fprop): out[co][tap*CinPad + ci] = w[tap][ci][co]           (CinPad >= Cin, zero filled)
  * mode 1 (dgrad): out[ci][tap'*Cout + co]  = w[taps-1-tap'][ci][co]    (180-degree rotation, in/out swapped)
- * dtype BF16: out bf16.  dtype F32: out fp32; if out_lo != NULL, out = tf32-exact high part and out_lo the rest. */
+ * dtype BF16: out bf16.  dtype F32: out_lo == NULL -> out = round_tf32(w); out_lo != NULL -> out = w (the MMA
+ * truncates it to its tf32 high part) and out_lo = round_tf32(w - trunc_tf32(w)). */
 typedef struct {
   const float* w;
   void* out;
@@ -125,7 +129,10 @@ typedef struct {
 } Fcn8PackParams;
 int32_t fcn8_pack_weights(const Fcn8PackParams* p, void* stream);
 
-/* x (fp32) -> hi (top 19 bits, exact in tf32) and lo = x - hi. */
+/* tf32 operand preparation (the tf32 MMA truncates fp32 operands to their top 19 bits):
+ *   hi != NULL, lo != NULL: hi = trunc_tf32(x), lo = round_tf32(x - hi)
+ *   hi == NULL:             lo only (x is its own high operand: the MMA truncates it)
+ *   lo == NULL:             hi = round_tf32(x)  (single-pass tf32: makes the MMA's truncation exact) */
 int32_t fcn8_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
 
 /* ---- 2x2 / stride 2 SAME max pooling of the encoder graph [EXT] and its gradient.

@@ -1,0 +1,168 @@
+"""CPU tier for the host side: C-ABI library loads and exports every declared symbol (no compute calls), flat-buffer
+layout, dropout RNG replica, loud failure without a GPU, data-parallel host logic over gloo (world size 2)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from fcn8s_tensorflow_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "fcn8s_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(fcn8_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    names = declared_symbols()
+    assert len(names) >= 25
+    lib = ctypes.CDLL(lib_path)
+    for n in names:
+        assert hasattr(lib, n), n
+    from fcn8s_tensorflow_b200 import _capi
+    assert sorted(_capi.EXPORTS) == names
+    lib.fcn8_version.restype = ctypes.c_int32
+    assert lib.fcn8_version() == 100
+
+
+def test_ctypes_structs_match_header_layout():
+    """Field order / count of the ctypes mirrors against the C structs in the header."""
+    from fcn8s_tensorflow_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "fcn8s_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for cname, cls in [("Fcn8PreprocessParams", _capi.PreprocessParams), ("Fcn8ConvParams", _capi.ConvParams),
+                       ("Fcn8WgradParams", _capi.WgradParams), ("Fcn8PackParams", _capi.PackParams),
+                       ("Fcn8PoolParams", _capi.PoolParams), ("Fcn8BiasGradParams", _capi.BiasGradParams),
+                       ("Fcn8HeadParams", _capi.HeadParams), ("Fcn8UpscoreParams", _capi.UpscoreParams),
+                       ("Fcn8SoftmaxParams", _capi.SoftmaxParams)]:
+        body = dict((n, b) for b, n in re.findall(r"typedef struct \{([^}]*)\}\s*(\w+);", hdr))[cname]
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(",")
+            first = names[0].split()[-1]
+            fields.append(first.lstrip("*"))
+            fields += [n.strip().lstrip("*") for n in names[1:]]
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+def test_flat_layout_is_aligned_complete_and_backward_ordered():
+    from fcn8s_tensorflow_b200.engine import flat_layout, variable_shapes
+    layout, total = flat_layout(20)
+    shapes = variable_shapes(20)
+    assert set(layout) == set(shapes) and len(layout) == 42
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 134473144
+    end = 0
+    for name, (off, shape) in layout.items():
+        assert off % 64 == 0 and off >= end
+        end = off + int(np.prod(shape))
+    assert total >= end
+    names = list(layout)
+    assert names[0].startswith("fc7_pool4_pool3_conv2d_trans") and names[-1] == "conv1_1/biases"
+    assert names.index("fc7/weights") < names.index("fc6/weights") < names.index("conv5_3/filter")
+
+
+def test_variable_shapes_agree_with_oracle():
+    from fcn8s_tensorflow_b200.engine import variable_shapes
+    from oracle import fcn8s_oracle as oracle
+    for c in (2, 3, 20):
+        assert dict(variable_shapes(c)) == dict(oracle.variable_shapes(c))
+
+
+def test_dropout_rng_host_replica_statistics():
+    from fcn8s_tensorflow_b200.rng import dropout_keep_mask, mix32
+    m = dropout_keep_mask(1234, 1 << 16, 0.5)
+    assert abs(m.float().mean().item() - 0.5) < 0.01
+    assert dropout_keep_mask(1234, 64, 1.0).all()
+    a = mix32(1, np.arange(8, dtype=np.uint64))
+    b = mix32(2, np.arange(8, dtype=np.uint64))
+    assert a.dtype == np.uint32 and (a != b).any()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    from fcn8s_tensorflow_b200 import _capi
+    from fcn8s_tensorflow_b200.engine import Engine
+    from fcn8s_tensorflow_b200.fcn8s import FCN8s
+    with pytest.raises(_capi.Fcn8Error):
+        Engine(20)
+    with pytest.raises(_capi.Fcn8Error):
+        FCN8s(vgg16_dir="synthetic", num_classes=2)
+    with pytest.raises(ValueError):
+        FCN8s()          # fcn8s_tensorflow.py:40-41
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fcn8s_tensorflow_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_shard_bounds():
+    from fcn8s_tensorflow_b200.dist import shard_batch, shard_bounds
+    assert [shard_bounds(16, r, 8) for r in (0, 7)] == [(0, 2), (14, 16)]
+    with pytest.raises(ValueError):
+        shard_bounds(6, 0, 4)
+    x = np.arange(8)
+    parts = [shard_batch(x, x, r, 4)[0] for r in range(4)]
+    assert np.array_equal(np.concatenate(parts), x)
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fcn8s_tensorflow_b200 import dist as fdist
+    r, _, w = fdist.init("gloo")
+
+    class FakeEngine:
+        pass
+    e = FakeEngine()
+    e.params = torch.full((10,), float(rank))
+    e.adam_m = torch.zeros(10)
+    e.adam_v = torch.zeros(10)
+    e.world, e.allreduce, e._packed_dirty = 1, None, False
+    fdist.attach(e)
+    fdist.broadcast_parameters(e, src=0)
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    e.allreduce(g)
+    avg = g / e.world     # what Adam's grad_scale = 1/world does
+    t = fdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
+    out.put((rank, e.world, e.params.tolist(), avg.tolist(), t, e._packed_dirty))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_gloo_world2():
+    """N>1 path on CPU: attach() + one all-reduce of the flat gradient + broadcast of the replicas, gloo backend."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect_avg = (np.arange(10) * 1.5).tolist()     # mean of g*(1) and g*(2)
+    for rank, world, params, avg, tmax, dirty in res:
+        assert world == 2
+        assert params == [0.0] * 10                  # broadcast from rank 0
+        assert np.allclose(avg, expect_avg)
+        assert tmax == 2.0 and dirty
