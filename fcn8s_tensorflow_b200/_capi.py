@@ -19,6 +19,8 @@ EXPORTS = [
     "fcn8_bias_grad", "fcn8_score_head_fwd", "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
     "fcn8_upscore_fwd", "fcn8_upscore_bwd_workspace_bytes", "fcn8_upscore_bwd", "fcn8_softmax_xent",
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
+    "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
+    "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw",
 ]
 
 
@@ -76,8 +78,22 @@ class UpscoreParams(C.Structure):
 
 class SoftmaxParams(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("labels", C.c_void_p), ("loss_sum", C.c_void_p), ("dlogits", C.c_void_p),
-                ("softmax", C.c_void_p), ("argmax", C.c_void_p), ("P", C.c_int64), ("C", C.c_int32),
+                ("dbias", C.c_void_p), ("softmax", C.c_void_p), ("argmax", C.c_void_p), ("N", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("CP", C.c_int32), ("pad", C.c_int32),
                 ("grad_scale", C.c_float)]
+
+
+class UpscorePackParams(C.Structure):
+    _fields_ = [("T", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_fwd_lo", C.c_void_p),
+                ("w_dx", C.c_void_p), ("w_dx_lo", C.c_void_p), ("bias_big", C.c_void_p), ("C", C.c_int32),
+                ("stride", C.c_int32)]
+
+
+class UpscoreTcParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("w", C.c_void_p), ("w_lo", C.c_void_p),
+                ("bias_big", C.c_void_p), ("zp", C.c_void_p), ("zp_lo", C.c_void_p), ("dx", C.c_void_p),
+                ("dT", C.c_void_p), ("N", C.c_int32), ("h", C.c_int32), ("wd", C.c_int32), ("C", C.c_int32),
+                ("stride", C.c_int32), ("ldx", C.c_int32), ("nseg", C.c_int32)]
 
 
 _lib = None
@@ -99,7 +115,8 @@ def load():
     lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
-                     ("fcn8_score_head_bwd", HeadParams), ("fcn8_upscore_bwd", UpscoreParams)]:
+                     ("fcn8_score_head_bwd", HeadParams), ("fcn8_upscore_bwd", UpscoreParams),
+                     ("fcn8_upscore_tc_dw", UpscoreTcParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp, sz, vp]
         getattr(lib, name).restype = C.c_int32
         getattr(lib, name + "_workspace_bytes").argtypes = [C.POINTER(pt)]
@@ -107,9 +124,12 @@ def load():
     for name, pt in [("fcn8_preprocess_im2col", PreprocessParams), ("fcn8_pack_weights", PackParams),
                      ("fcn8_maxpool_fwd", PoolParams), ("fcn8_maxpool_bwd", PoolParams),
                      ("fcn8_score_head_fwd", HeadParams), ("fcn8_upscore_fwd", UpscoreParams),
-                     ("fcn8_softmax_xent", SoftmaxParams)]:
+                     ("fcn8_softmax_xent", SoftmaxParams), ("fcn8_upscore_tc_pack", UpscorePackParams),
+                     ("fcn8_upscore_tc_fwd", UpscoreTcParams), ("fcn8_upscore_tc_dx", UpscoreTcParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp]
         getattr(lib, name).restype = C.c_int32
+    lib.fcn8_upscore_tc_cp.argtypes = [C.c_int32, C.c_int32]
+    lib.fcn8_upscore_tc_cp.restype = C.c_int32
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]

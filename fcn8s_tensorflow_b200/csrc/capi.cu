@@ -211,6 +211,42 @@ cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid
   return cudaGetLastError();
 }
 
+cudaError_t dispatch_conv(int BN, bool tf32, const TensorMaps3& maps, const ConvGemmArgs& a, int grid,
+                          cudaStream_t st) {
+  if (BN == 256) return tf32 ? launch_conv_t<256, true>(maps, a, grid, st) : launch_conv_t<256, false>(maps, a, grid, st);
+  if (BN == 128) return tf32 ? launch_conv_t<128, true>(maps, a, grid, st) : launch_conv_t<128, false>(maps, a, grid, st);
+  return tf32 ? launch_conv_t<64, true>(maps, a, grid, st) : launch_conv_t<64, false>(maps, a, grid, st);
+}
+cudaError_t dispatch_wgrad(int BN, bool tf32, const TensorMaps3& maps, const WgradArgs& a, int grid, cudaStream_t st) {
+  if (BN == 256)
+    return tf32 ? launch_wgrad_t<256, true>(maps, a, grid, st) : launch_wgrad_t<256, false>(maps, a, grid, st);
+  if (BN == 128)
+    return tf32 ? launch_wgrad_t<128, true>(maps, a, grid, st) : launch_wgrad_t<128, false>(maps, a, grid, st);
+  return tf32 ? launch_wgrad_t<64, true>(maps, a, grid, st) : launch_wgrad_t<64, false>(maps, a, grid, st);
+}
+
+// Blocked view of the padded output (or output gradient) of a stride-s transposed convolution:
+// zp[N][s*Hb][s*Wb][CP] fp32 seen as dims (s*CP, Wb, s, Hb, N); box (32, bw, 1, bh, bn) = bw*bh*bn blocks x 128 B.
+int encode_blocked_map(CUtensorMap* m, const void* ptr, int N, int Hb, int Wb, int s, int CP, int bw, int bh, int bn,
+                       bool atom32) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t row = (cuuint64_t)s * CP * 4;       // bytes of one block row
+  const cuuint64_t line = (cuuint64_t)Wb * row;        // bytes of one padded image row
+  const cuuint64_t dims[5] = {(cuuint64_t)s * CP, (cuuint64_t)Wb, (cuuint64_t)s, (cuuint64_t)Hb, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {row, line, (cuuint64_t)s * line, (cuuint64_t)s * Hb * line};
+  const cuuint32_t box[5] = {32, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(blocked N%d Hb%d Wb%d s%d CP%d) failed: %d", N, Hb, Wb, s, CP,
+                (int)r);
+  return 0;
+}
+
 struct WgradPlan {
   int BN, splits, pb_per_split, total_pb;
   int lbw, lbh, lbn, pb_x, pb_y, pb_b;
@@ -346,6 +382,9 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
   a.flags = p->flags & (31 | 64);
+  a.osW = p->Cout;
+  a.osH = (long long)p->W * p->Cout;
+  a.osN = (long long)p->H * p->W * p->Cout;
   a.mask_scale = p->mask_scale;
   a.seed = p->seed;
   if (p->flags & FCN8_EPI_DROPOUT) {
@@ -572,10 +611,15 @@ int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t wor
 int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream) {
   if (!p || !p->logits) return fail(FCN8_ERR_BAD_SHAPE, "softmax: null pointer");
   if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "softmax: num_classes=%d not in [1,32]", p->C);
+  if (p->CP < p->C || p->pad < 0) return fail(FCN8_ERR_BAD_SHAPE, "softmax: CP < C or negative pad");
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "softmax: empty tensor");
   if ((p->loss_sum || p->dlogits) && !p->labels) return fail(FCN8_ERR_BAD_SHAPE, "softmax: loss needs labels");
-  cudaError_t e = launch_softmax_xent(p->logits, p->labels, p->loss_sum, p->dlogits, p->softmax,
-                                      reinterpret_cast<long long*>(p->argmax), p->P, p->C, p->grad_scale,
-                                      (cudaStream_t)stream);
+  if (p->dlogits && p->softmax) return fail(FCN8_ERR_UNSUPPORTED, "softmax: dlogits and softmax are exclusive");
+  if ((p->CP & 3) == 0 && (!aligned16(p->logits) || (p->dlogits && !aligned16(p->dlogits))))
+    return fail(FCN8_ERR_BAD_ALIGN, "softmax: logits / dlogits must be 16-byte aligned");
+  cudaError_t e = launch_softmax_xent(p->logits, p->labels, p->loss_sum, p->dlogits, p->dbias, p->softmax,
+                                      reinterpret_cast<long long*>(p->argmax), p->N, p->H, p->W, p->C, p->CP, p->pad,
+                                      p->grad_scale, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "softmax launch");
 }
 
@@ -600,6 +644,254 @@ int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float r
   if (!w) return fail(FCN8_ERR_BAD_SHAPE, "l2_reg: null pointer");
   cudaError_t e = launch_l2_reg(w, g, loss_sum, n, rate, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "l2_reg launch");
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Transposed convolutions on the tensor cores (phase GEMM).
+namespace {
+int upscore_cp(int C, int s) {
+  const int q = 32 / s > 4 ? 32 / s : 4;  // s*CP must be a whole number of 128-byte chunks
+  return (C + q - 1) / q * q;
+}
+int check_upscore_tc(const Fcn8UpscoreTcParams* p, const char* what) {
+  if (!p) return fail(FCN8_ERR_BAD_SHAPE, "%s: null params", what);
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "%s: num_classes=%d not in [1,32]", what, p->C);
+  if (p->stride != 2 && p->stride != 4 && p->stride != 8)
+    return fail(FCN8_ERR_UNSUPPORTED, "%s: stride must be 2, 4 or 8", what);
+  if (p->N <= 0 || p->h <= 0 || p->wd <= 0) return fail(FCN8_ERR_BAD_SHAPE, "%s: empty tensor", what);
+  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_BAD_SHAPE, "%s: nseg must be 1 or 3", what);
+  if (p->ldx % 4 || p->ldx < p->C) return fail(FCN8_ERR_BAD_SHAPE, "%s: ldx=%d must be a multiple of 4 >= C", what, p->ldx);
+  return 0;
+}
+// x [N,h,w,ldx] fp32 as the (C, W, H, N) map with a 32-float box: channels >= ldx are zero-filled by TMA.
+int encode_dec_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int ld, int bw, int bh, int bn,
+                       bool atom32) {
+  return encode_act_map(m, ptr, FCN8_F32, N, H, W, ld, bw, bh, bn, atom32);
+}
+}  // namespace
+
+extern "C" {
+
+int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride) { return upscore_cp(C, stride); }
+
+int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream) {
+  if (!p || !p->T || !p->bias || !p->w_fwd || !p->w_dx || !p->bias_big)
+    return fail(FCN8_ERR_BAD_SHAPE, "upscore pack: null pointer");
+  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "upscore pack: num_classes=%d not in [1,32]", p->C);
+  if (p->stride != 2 && p->stride != 4 && p->stride != 8)
+    return fail(FCN8_ERR_UNSUPPORTED, "upscore pack: stride must be 2, 4 or 8");
+  cudaError_t e = launch_upscore_pack(p->T, p->bias, p->w_fwd, p->w_fwd_lo, p->w_dx, p->w_dx_lo, p->bias_big, p->C,
+                                      upscore_cp(p->C, p->stride), p->stride, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore pack launch");
+}
+
+// zp[n, s*J + dy, s*I + dx, co] = sum_{ty,tx,ci} x[n, J-1+ty, I-1+tx, ci] * T[dy + s(1-ty), dx + s(1-tx), co, ci] + bias
+int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream) {
+  int rc = check_upscore_tc(p, "upscore_tc_fwd");
+  if (rc) return rc;
+  if (!p->x || !p->w || !p->bias_big || !p->zp) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: null pointer");
+  if (p->nseg == 3 && (!p->x_lo || !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: nseg=3 needs x_lo, w_lo");
+  const int s = p->stride, CP = upscore_cp(p->C, s);
+  const int Hb = p->h + 1, Wb = p->wd + 1;
+  const int ncols = s * s * CP;
+  const int BN = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
+  if (ncols % BN) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: %d columns not tileable", ncols);
+  int lbw, lbh, lbn;
+  choose_patch(p->N, Hb, Wb, 7, &lbw, &lbh, &lbn);
+  TensorMaps3 maps;
+  memset(&maps, 0, sizeof(maps));
+  const void* xs[3] = {p->x, p->x, p->x_lo};
+  const void* ws[3] = {p->w, p->w_lo, p->w};
+  for (int i = 0; i < p->nseg; ++i) {
+    rc = encode_dec_act_map(&maps.a[i], xs[i], p->N, p->h, p->wd, p->ldx, 1 << lbw, 1 << lbh, 1 << lbn, false);
+    if (rc) return rc;
+    rc = encode_w_map(&maps.b[i], ws[i], FCN8_F32, ncols, 128, BN);
+    if (rc) return rc;
+  }
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = p->zp;
+  a.bias = p->bias_big;
+  a.N = p->N;
+  a.H = Hb;
+  a.W = Wb;
+  a.ldc = ncols;
+  a.taps = 4;
+  a.taps_w = 2;
+  a.pad = 1;
+  a.cblocks = 1;
+  a.nseg = p->nseg;
+  a.lbw = lbw;
+  a.lbh = lbh;
+  a.lbn = lbn;
+  a.tiles_x = (Wb + (1 << lbw) - 1) >> lbw;
+  a.tiles_y = (Hb + (1 << lbh) - 1) >> lbh;
+  a.tiles_b = (p->N + (1 << lbn) - 1) >> lbn;
+  a.tiles_n = ncols / BN;
+  a.splits = 1;
+  a.kb_per_split = p->nseg * 4;
+  a.flags = EPI_BIAS;
+  a.out_mode = 1;
+  a.blk_row = s * CP;
+  a.osW = (long long)s * CP;
+  a.os_dy = (long long)Wb * s * CP;
+  a.osH = (long long)s * a.os_dy;
+  a.osN = (long long)Hb * a.osH;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_b * a.tiles_n;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  cudaError_t e = dispatch_conv(BN, true, maps, a, grid, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_fwd launch");
+}
+
+// dx[n,i,j,ci] = sum_{ty,tx} sum_{dy,dx,co} dzp[n, s(i+1-ty)+dy, s(j+1-tx)+dx, co] * T[dy+s(1-ty), dx+s(1-tx), co, ci]
+int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream) {
+  int rc = check_upscore_tc(p, "upscore_tc_dx");
+  if (rc) return rc;
+  if (!p->zp || !p->w || !p->dx) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dx: null pointer");
+  if (p->nseg == 3 && (!p->zp_lo || !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dx: nseg=3 needs zp_lo, w_lo");
+  const int s = p->stride, CP = upscore_cp(p->C, s);
+  const int Hb = p->h + 1, Wb = p->wd + 1;
+  const int chunks_row = s * CP / 32;
+  const int cblocks = s * chunks_row;  // k-blocks per tap
+  int lbw, lbh, lbn;
+  choose_patch(p->N, p->h, p->wd, 7, &lbw, &lbh, &lbn);
+  TensorMaps3 maps;
+  memset(&maps, 0, sizeof(maps));
+  const void* zs[3] = {p->zp, p->zp, p->zp_lo};
+  const void* ws[3] = {p->w, p->w_lo, p->w};
+  for (int i = 0; i < p->nseg; ++i) {
+    rc = encode_blocked_map(&maps.a[i], zs[i], p->N, Hb, Wb, s, CP, 1 << lbw, 1 << lbh, 1 << lbn, false);
+    if (rc) return rc;
+    rc = encode_w_map(&maps.b[i], ws[i], FCN8_F32, 64, 4 * s * s * CP, 64);
+    if (rc) return rc;
+  }
+  ConvGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = p->dx;
+  a.N = p->N;
+  a.H = p->h;
+  a.W = p->wd;
+  a.ldc = p->ldx;
+  a.taps = 4;
+  a.taps_w = 2;
+  a.pad = 1;
+  a.cblocks = cblocks;
+  a.nseg = p->nseg;
+  a.lbw = lbw;
+  a.lbh = lbh;
+  a.lbn = lbn;
+  a.tiles_x = (p->wd + (1 << lbw) - 1) >> lbw;
+  a.tiles_y = (p->h + (1 << lbh) - 1) >> lbh;
+  a.tiles_b = (p->N + (1 << lbn) - 1) >> lbn;
+  a.tiles_n = 1;
+  a.splits = 1;
+  a.kb_per_split = p->nseg * 4 * cblocks;
+  a.flags = 0;
+  a.a_mode = 1;
+  a.blk_chunks = chunks_row;
+  a.store_cols = p->ldx;
+  a.osW = p->ldx;
+  a.osH = (long long)p->wd * p->ldx;
+  a.osN = (long long)p->h * a.osH;
+  const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_b;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  cudaError_t e = dispatch_conv(64, true, maps, a, grid, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_dx launch");
+}
+
+namespace {
+struct UpDwPlan {
+  int BN, splits, pb_per_split, total_pb, lbw, lbh, lbn, pb_x, pb_y, pb_b, tiles_n, ncols;
+};
+void plan_updw(const Fcn8UpscoreTcParams* p, UpDwPlan* pl) {
+  const int s = p->stride, CP = upscore_cp(p->C, s);
+  pl->ncols = s * s * CP;
+  pl->BN = pl->ncols % 128 == 0 ? 128 : 64;
+  pl->tiles_n = pl->ncols / pl->BN;
+  choose_patch(p->N, p->h + 1, p->wd + 1, 6, &pl->lbw, &pl->lbh, &pl->lbn);
+  pl->pb_x = (p->wd + 1 + (1 << pl->lbw) - 1) >> pl->lbw;
+  pl->pb_y = (p->h + 1 + (1 << pl->lbh) - 1) >> pl->lbh;
+  pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
+  pl->total_pb = p->nseg * pl->pb_x * pl->pb_y * pl->pb_b;
+  int splits = (num_sms() + pl->tiles_n - 1) / pl->tiles_n;
+  const int max_by_k = pl->total_pb / 4 > 0 ? pl->total_pb / 4 : 1;
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  pl->pb_per_split = (pl->total_pb + splits - 1) / splits;
+  pl->splits = (pl->total_pb + pl->pb_per_split - 1) / pl->pb_per_split;
+}
+}  // namespace
+
+size_t fcn8_upscore_tc_dw_workspace_bytes(const Fcn8UpscoreTcParams* p) {
+  if (check_upscore_tc(p, "upscore_tc_dw")) return 0;
+  UpDwPlan pl;
+  plan_updw(p, &pl);
+  return (size_t)(pl.splits + 1) * 128 * pl.ncols * sizeof(float);
+}
+
+// dT[a,b,co,ci] = sum_{n,i,j} x[n,i,j,ci] * dz[n, s*i+a-p, s*j+b-p, co], computed as the phase GEMM
+// dWbig[(ty,tx,ci), (dy,dx,co)] = sum_blocks Xnbr * dZblock and un-permuted into the TF layout.
+int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_upscore_tc(p, "upscore_tc_dw");
+  if (rc) return rc;
+  if (!p->x || !p->zp || !p->dT) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dw: null pointer");
+  if (p->nseg == 3 && (!p->x_lo || !p->zp_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dw: nseg=3 needs x_lo, zp_lo");
+  const size_t need = fcn8_upscore_tc_dw_workspace_bytes(p);
+  if (workspace_bytes < need || !workspace) return fail(FCN8_ERR_WORKSPACE, "upscore_tc_dw: workspace too small");
+  const int s = p->stride, CP = upscore_cp(p->C, s);
+  UpDwPlan pl;
+  plan_updw(p, &pl);
+  TensorMaps3 maps;
+  memset(&maps, 0, sizeof(maps));
+  const void* xs[3] = {p->x, p->x, p->x_lo};
+  const void* zs[3] = {p->zp, p->zp_lo, p->zp};
+  for (int i = 0; i < p->nseg; ++i) {
+    rc = encode_dec_act_map(&maps.a[i], xs[i], p->N, p->h, p->wd, p->ldx, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn, true);
+    if (rc) return rc;
+    rc = encode_blocked_map(&maps.b[i], zs[i], p->N, p->h + 1, p->wd + 1, s, CP, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
+                            true);
+    if (rc) return rc;
+  }
+  float* dwbig = static_cast<float*>(workspace);                 // [128][ncols]
+  float* partial = dwbig + (size_t)128 * pl.ncols;               // [splits][128][ncols]
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.out = dwbig;
+  a.partial = partial;
+  a.N = p->N;
+  a.H = p->h + 1;
+  a.W = p->wd + 1;
+  a.Cin = 32;
+  a.ldc = pl.ncols;
+  a.taps = 4;
+  a.taps_w = 2;
+  a.pad = 1;
+  a.nseg = p->nseg;
+  a.rows_valid = 128;
+  a.total_chunks = 4;
+  a.m_tiles = 1;
+  a.tiles_n = pl.tiles_n;
+  a.lbw = pl.lbw;
+  a.lbh = pl.lbh;
+  a.lbn = pl.lbn;
+  a.pb_x = pl.pb_x;
+  a.pb_y = pl.pb_y;
+  a.pb_b = pl.pb_b;
+  a.splits = pl.splits;
+  a.pb_per_split = pl.pb_per_split;
+  a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
+  a.b_mode = 1;
+  a.blk_row = s * CP;
+  const long long tiles = (long long)pl.tiles_n * pl.splits;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = dispatch_wgrad(pl.BN, true, maps, a, grid, st);
+  if (e != cudaSuccess) return cuda_fail(e, "upscore_tc_dw launch");
+  e = launch_upscore_unpack_dw(pl.splits > 1 ? partial : dwbig, pl.splits > 1 ? pl.splits : 1, p->dT, p->C, CP, s, st);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_dw unpack launch");
 }
 
 }  // extern "C"

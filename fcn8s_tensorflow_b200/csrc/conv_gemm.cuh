@@ -76,6 +76,15 @@ struct ConvGemmArgs {
   float inv_keep;
   uint32_t keep_threshold;
   uint32_t seed;
+  // Output addressing: element offset of row (n, y, x) = n*osN + y*osH + x*osW; column c lands at +c (out_mode 0) or,
+  // for the blocked output of a transposed convolution (out_mode 1: a row is one s x s output block whose columns are
+  // (dy, dx, co)), at + (c / blk_row) * os_dy + c % blk_row.  store_cols > 0 keeps only the first store_cols columns.
+  long long osN, osH, osW, os_dy;
+  int out_mode, blk_row, store_cols;
+  // A operand: a_mode 0 = NHWC map (C, W, H, N), tap (kh, kw) shifts the box by (kw - pad, kh - pad);
+  // a_mode 1 = blocked 5-D map (s*CP, Wb, s, Hb, N) of a padded transposed-conv output: k-block (tap, cb) reads row
+  // dy = cb / blk_chunks, chunk cb % blk_chunks of block (y + pad - kh, x + pad - kw).
+  int a_mode, blk_chunks;
 };
 
 struct TensorMaps3 {
@@ -112,7 +121,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // ------------------------------------------------------------------------------------------------------------------
 // Epilogue math on 32 consecutive columns of one output row. `idx` = element index of column c0 of this row.
 template <bool TF32>
-__device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0) {
+__device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
+                                               int ncols = 32) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
@@ -202,7 +212,8 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     }
     float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+    for (int i = 0; i < 8; ++i)
+      if (4 * i < ncols) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   } else {
     uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
@@ -282,7 +293,13 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
+          if (g.a_mode == 0) {
+            tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
+          } else {
+            const int bdy = cb / g.blk_chunks;
+            tma_load_5d(&maps.a[seg], &full_bar[stage], sa, (cb - bdy * g.blk_chunks) * CH, x0 + g.pad - kw, bdy,
+                        y0 + g.pad - kh, n0);
+          }
           tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -364,6 +381,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       const int n = (tb << g.lbn) + (row >> (g.lbw + g.lbh));
       const bool valid = (x < g.W) && (y < g.H) && (n < g.N);
       const size_t pix = (static_cast<size_t>(n) * g.H + y) * g.W + x;
+      const size_t row_off = static_cast<size_t>(n) * g.osN + static_cast<size_t>(y) * g.osH +
+                             static_cast<size_t>(x) * g.osW;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -374,15 +393,21 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         tmem_ld_wait();
         if (valid) {
           const int c0 = nb * BN + c;
-          const size_t idx = pix * g.ldc + c0;
           if (g.flags & EPI_PARTIAL) {
+            const size_t idx = pix * g.ldc + c0;
             float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           } else {
-            epilogue_row32<TF32>(g, v, idx, c0);
+            size_t idx = row_off + c0;
+            if (g.out_mode) {
+              const int bdy = c0 / g.blk_row;
+              idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
+            }
+            const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
+            if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols);
           }
         }
       }
@@ -421,6 +446,9 @@ struct WgradArgs {
   int pb_x, pb_y, pb_b;        // pixel blocks per dim
   int splits, pb_per_split;
   int flags;  // EPI_PARTIAL or 0
+  // b_mode 1: dY is the padded, blocked output gradient of a transposed convolution (5-D map (s*CP, Wb, s, Hb, N));
+  // output column c = (dy, dx, co) reads row dy = c / blk_row, element c % blk_row of the blocks.
+  int b_mode, blk_row;
 };
 
 template <int BN, bool TF32>
@@ -518,8 +546,15 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
             if (c < nvalid)
               tma_load_4d(&maps.a[seg], &full_bar[stage], sa + c * kChunkBytes, ccb[c], x0 + cdx[c], y0 + cdy[c], n0);
 #pragma unroll
-          for (int j = 0; j < NCH; ++j)
-            tma_load_4d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, nb * BN + j * CH, x0, y0, n0);
+          for (int j = 0; j < NCH; ++j) {
+            const int col = nb * BN + j * CH;
+            if (g.b_mode == 0) {
+              tma_load_4d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col, x0, y0, n0);
+            } else {
+              const int bdy = col / g.blk_row;
+              tma_load_5d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col - bdy * g.blk_row, x0, bdy, y0, n0);
+            }
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;

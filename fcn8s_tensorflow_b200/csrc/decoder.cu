@@ -396,72 +396,221 @@ size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s) {
 }
 
 // ------------------------------------------------------------------------------------------------ softmax / xent
-__global__ void softmax_xent_kernel(const float* __restrict__ z, const uint8_t* __restrict__ labels,
-                                    float* __restrict__ loss_sum, float* __restrict__ dz, float* __restrict__ sm,
-                                    long long* __restrict__ amax, long long P, int C, float gscale) {
-  float local = 0.f;
-  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < P;
-       p += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float v[CMAX];
-    float mx = -INFINITY;
-    int am = 0;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) {
-        v[c] = z[p * C + c];
-        if (v[c] > mx) {
-          mx = v[c];
-          am = c;
+// One CTA works on runs of 128 consecutive pixels of one image row.  Logits (and dlogits) may live inside a padded
+// tensor [N, H+2*pad, W+2*pad, CP] (the blocked output of the tensor-core upscore8 stage); labels, softmax and argmax
+// are dense.  All global traffic is coalesced through shared memory; per-class sums of dlogits (the bias gradient of
+// the last transposed convolution) are accumulated on the way.
+constexpr int kLossPix = 128;
+__global__ void __launch_bounds__(kLossPix)
+softmax_xent_kernel(const float* __restrict__ z, const uint8_t* __restrict__ labels, float* __restrict__ loss_sum,
+                    float* __restrict__ dz, float* __restrict__ dbias, float* __restrict__ sm,
+                    long long* __restrict__ amax, int N, int H, int W, int C, int CP, int pad, float gscale) {
+  extern __shared__ float sbuf[];              // [kLossPix * CP] logits -> dlogits / softmax
+  uint8_t* slab = reinterpret_cast<uint8_t*>(sbuf + kLossPix * CP);  // [kLossPix * C]
+  __shared__ float sred[kLossPix / 32];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int runs_per_row = (W + kLossPix - 1) / kLossPix;
+  const long long total_runs = static_cast<long long>(N) * H * runs_per_row;
+  float local_loss = 0.f;
+  float db_acc = 0.f;  // thread c < C accumulates class c
+  for (long long run = blockIdx.x; run < total_runs; run += gridDim.x) {
+    const int rx = static_cast<int>(run % runs_per_row);
+    const int y = static_cast<int>((run / runs_per_row) % H);
+    const int n = static_cast<int>(run / (static_cast<long long>(runs_per_row) * H));
+    const int x0 = rx * kLossPix;
+    const int np = min(kLossPix, W - x0);
+    const size_t zoff = ((static_cast<size_t>(n) * Hp + y + pad) * Wp + x0 + pad) * CP;
+    const size_t poff = (static_cast<size_t>(n) * H + y) * W + x0;
+    __syncthreads();
+    {
+      if ((CP & 3) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(z + zoff);
+        float4* dst = reinterpret_cast<float4*>(sbuf);
+        for (int i = threadIdx.x; i < np * CP / 4; i += kLossPix) dst[i] = __ldg(src + i);
+      } else {
+        for (int i = threadIdx.x; i < np * CP; i += kLossPix) sbuf[i] = __ldg(z + zoff + i);
+      }
+      if (labels) {
+        const uint8_t* ls = labels + poff * C;
+        const int nb = np * C;
+        if ((reinterpret_cast<uintptr_t>(ls) & 3u) == 0 && (nb & 3) == 0) {
+          const uint32_t* s4 = reinterpret_cast<const uint32_t*>(ls);
+          uint32_t* d4 = reinterpret_cast<uint32_t*>(slab);
+          for (int i = threadIdx.x; i < nb / 4; i += kLossPix) d4[i] = __ldg(s4 + i);
+        } else {
+          for (int i = threadIdx.x; i < nb; i += kLossPix) slab[i] = ls[i];
         }
       }
-    float se = 0.f;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) {
-        v[c] = expf(v[c] - mx);
-        se += v[c];
-      }
-    const float inv = 1.f / se;
-    if (amax) amax[p] = am;
-    if (sm) {
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) sm[p * C + c] = v[c] * inv;
     }
-    if (labels) {
-      const float lse = mx + logf(se);
-      float ysum = 0.f, yz = 0.f;
-      float yv[CMAX];
+    __syncthreads();
+    if (threadIdx.x < np) {
+      float* zp = sbuf + threadIdx.x * CP;
+      float v[CMAX];
+      float mx = -INFINITY;
+      int am = 0;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
         if (c < C) {
-          yv[c] = static_cast<float>(labels[p * C + c]);
-          ysum += yv[c];
-          yz += yv[c] * z[p * C + c];
+          v[c] = zp[c];
+          if (v[c] > mx) {
+            mx = v[c];
+            am = c;
+          }
         }
-      local += ysum * lse - yz;
-      if (dz) {
+      float se = 0.f;
+      float e[CMAX];
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          e[c] = expf(v[c] - mx);
+          se += e[c];
+        }
+      const float inv = 1.f / se;
+      if (amax) amax[poff + threadIdx.x] = am;
+      if (labels) {
+        const float lse = mx + logf(se);
+        const uint8_t* lp = slab + threadIdx.x * C;
+        float ysum = 0.f, yz = 0.f;
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) dz[p * C + c] = (v[c] * inv * ysum - yv[c]) * gscale;
+          if (c < C) {
+            const float yv = static_cast<float>(lp[c]);
+            ysum += yv;
+            yz += yv * v[c];
+          }
+        local_loss += ysum * lse - yz;
+        if (dz) {
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) zp[c] = (e[c] * inv * ysum - static_cast<float>(lp[c])) * gscale;
+          for (int c = C; c < CP; ++c) zp[c] = 0.f;
+        }
       }
+      if (sm && !dz) {
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) zp[c] = e[c] * inv;
+      }
+    }
+    __syncthreads();
+    if (dz) {
+      if ((CP & 3) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(sbuf);
+        float4* dst = reinterpret_cast<float4*>(dz + zoff);
+        for (int i = threadIdx.x; i < np * CP / 4; i += kLossPix) dst[i] = src[i];
+      } else {
+        for (int i = threadIdx.x; i < np * CP; i += kLossPix) dz[zoff + i] = sbuf[i];
+      }
+      if (dbias && threadIdx.x < C) {
+        float a = 0.f;
+        for (int q = 0; q < np; ++q) a += sbuf[q * CP + threadIdx.x];
+        db_acc += a;
+      }
+    } else if (sm) {
+      float* dst = sm + poff * C;  // dense [.., C]
+      for (int i = threadIdx.x; i < np * C; i += kLossPix) dst[i] = sbuf[(i / C) * CP + (i % C)];
     }
   }
   if (loss_sum) {
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    __shared__ float wsum[8];
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = local;
+    for (int o = 16; o > 0; o >>= 1) local_loss += __shfl_xor_sync(0xffffffffu, local_loss, o);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = local_loss;
     __syncthreads();
     if (threadIdx.x == 0) {
       float t = 0.f;
-      for (int k = 0; k < static_cast<int>(blockDim.x >> 5); ++k) t += wsum[k];
+      for (int k = 0; k < kLossPix / 32; ++k) t += sred[k];
       atomicAdd(loss_sum, t);
     }
   }
+  if (dz && dbias && threadIdx.x < C) atomicAdd(dbias + threadIdx.x, db_acc);
 }
-cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* sm,
-                                long long* amax, long long P, int C, float gscale, cudaStream_t st) {
-  { count_launch(); softmax_xent_kernel<<<grid_for(P, 256, 148 * 8), 256, 0, st>>>(z, labels, loss_sum, dz, sm, amax, P, C, gscale); }
+cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* dbias,
+                                float* sm, long long* amax, int N, int H, int W, int C, int CP, int pad, float gscale,
+                                cudaStream_t st) {
+  const long long runs = static_cast<long long>(N) * H * ((W + kLossPix - 1) / kLossPix);
+  const int blocks = static_cast<int>(runs < 148 * 8 ? runs : 148 * 8);
+  const size_t smem = static_cast<size_t>(kLossPix) * CP * sizeof(float) + static_cast<size_t>(kLossPix) * C;
+  { count_launch(); softmax_xent_kernel<<<blocks, kLossPix, smem, st>>>(z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ phase-GEMM operands
+// Operand packing for the tensor-core transposed convolution (capi.cu: fcn8_upscore_tc_*).  T[a][b][co][ci] (TF
+// layout), a = dy + s*(1-ty), b = dx + s*(1-tx):
+//   w_fwd[(dy,dx,co)][(ty,tx,ci32)]   rows s*s*CP, row length 128   (zero for co >= C or ci >= C)
+//   w_dx [ci64][(ty,tx,dy,dx,co)]     rows 64,     row length 4*s*s*CP
+//   bias_big[(dy,dx,co)] = bias[co]
+// *_lo != nullptr: 3xTF32 split (hi operand = the fp32 value itself, the MMA truncates it; lo = rna(w - trunc(w)));
+// otherwise the single-pass operand rna_tf32(w).
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float v) {
+  if (lo) {
+    hi[i] = v;
+    lo[i] = rna_tf32(v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u));
+  } else {
+    hi[i] = rna_tf32(v);
+  }
+}
+__global__ void upscore_pack_kernel(const float* __restrict__ T, const float* __restrict__ bias, float* w_fwd,
+                                    float* w_fwd_lo, float* w_dx, float* w_dx_lo, float* bias_big, int C, int CP,
+                                    int s) {
+  const int k = 2 * s;
+  const int ncols = s * s * CP;
+  const size_t n_fwd = static_cast<size_t>(ncols) * 128;
+  const size_t n_dx = static_cast<size_t>(64) * 4 * ncols;
+  const size_t total = n_fwd + n_dx + ncols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    if (i < n_fwd) {
+      const int kk = static_cast<int>(i % 128), col = static_cast<int>(i / 128);
+      const int ci = kk % 32, tap = kk / 32, ty = tap >> 1, tx = tap & 1;
+      const int co = col % CP, dx = (col / CP) % s, dy = col / (CP * s);
+      float v = 0.f;
+      if (co < C && ci < C) v = T[((static_cast<size_t>(dy + s * (1 - ty)) * k + dx + s * (1 - tx)) * C + co) * C + ci];
+      put_split(w_fwd, w_fwd_lo, i, v);
+    } else if (i < n_fwd + n_dx) {
+      const size_t j = i - n_fwd;
+      const int kk = static_cast<int>(j % (4 * ncols)), ci = static_cast<int>(j / (4 * ncols));
+      const int tap = kk / ncols, col = kk % ncols, ty = tap >> 1, tx = tap & 1;
+      const int co = col % CP, dx = (col / CP) % s, dy = col / (CP * s);
+      float v = 0.f;
+      if (co < C && ci < C) v = T[((static_cast<size_t>(dy + s * (1 - ty)) * k + dx + s * (1 - tx)) * C + co) * C + ci];
+      put_split(w_dx, w_dx_lo, j, v);
+    } else {
+      const int col = static_cast<int>(i - n_fwd - n_dx);
+      const int co = col % CP;
+      bias_big[col] = co < C ? bias[co] : 0.f;
+    }
+  }
+}
+cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd, float* w_fwd_lo, float* w_dx,
+                                float* w_dx_lo, float* bias_big, int C, int CP, int s, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(s) * s * CP * (128 + 256 + 1);
+  { count_launch(); upscore_pack_kernel<<<grid_for(total, 256), 256, 0, st>>>(T, bias, w_fwd, w_fwd_lo, w_dx, w_dx_lo, bias_big, C, CP, s); }
+  return cudaGetLastError();
+}
+// dT[a][b][co][ci] = sum_split src[split][(ty,tx,ci)][(dy,dx,co)]
+__global__ void upscore_unpack_dw_kernel(const float* __restrict__ src, int nsplit, float* __restrict__ dT, int C,
+                                         int CP, int s) {
+  const int k = 2 * s;
+  const int ncols = s * s * CP;
+  const int total = k * k * C * C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = i % C, co = (i / C) % C, b = (i / (C * C)) % k, a = i / (C * C * k);
+  const int ty = a < s ? 1 : 0, tx = b < s ? 1 : 0;
+  const int dy = a - s * (1 - ty), dx = b - s * (1 - tx);
+  const size_t off = static_cast<size_t>((ty * 2 + tx) * 32 + ci) * ncols + (dy * s + dx) * CP + co;
+  float acc = 0.f;
+  for (int sp = 0; sp < nsplit; ++sp) acc += src[static_cast<size_t>(sp) * 128 * ncols + off];
+  dT[i] = acc;
+}
+cudaError_t launch_upscore_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st) {
+  const int total = 4 * s * s * C * C;
+  { count_launch(); upscore_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, nsplit, dT, C, CP, s); }
   return cudaGetLastError();
 }
 

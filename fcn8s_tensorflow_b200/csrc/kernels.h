@@ -44,8 +44,12 @@ cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias
 size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s);
 cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, float* dx, float* dT, float* dbias,
                                int N, int h, int w, int C, int s, float* ws, cudaStream_t st);
-cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* sm,
-                                long long* amax, long long P, int C, float gscale, cudaStream_t st);
+cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* dbias,
+                                float* sm, long long* amax, int N, int H, int W, int C, int CP, int pad, float gscale,
+                                cudaStream_t st);
+cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd, float* w_fwd_lo, float* w_dx,
+                                float* w_dx_lo, float* bias_big, int C, int CP, int s, cudaStream_t st);
+cudaError_t launch_upscore_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st);
 cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
                              cudaStream_t st);
 

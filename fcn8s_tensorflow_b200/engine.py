@@ -154,6 +154,9 @@ class Engine:
                 f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3)
                 d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3)
                 self.packed[name] = f + d
+        self.packed["up8"] = ops.upscore_tc_pack(self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
+                                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8, split=self.x3,
+                                                 out=self.packed.get("up8"))
         self._packed_dirty = False
 
     # ------------------------------------------------------------------ activation arena
@@ -235,10 +238,27 @@ class Engine:
                              out=self._buf(A, "f4", (N, H // 16, W // 16, C), f32))
         f3 = ops.upscore_fwd(f4, self.view("fc7_pool4_conv2d_trans/kernel"), self.view("fc7_pool4_conv2d_trans/bias"),
                              2, skip=s3, out=self._buf(A, "f3", (N, H // 8, W // 8, C), f32))
-        logits = ops.upscore_fwd(f3, self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
-                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8,
-                                 out=self._buf(A, "logits", (N, H, W, C), f32))
-        return logits
+        # upscore8 on the tensor cores (phase GEMM): padded blocked logits [N, H+8, W+8, CP]; A["logits"] is the view
+        f3p = self._pad4(A, "f3p", f3)
+        x_lo = self._split(A, "f3p", f3p)[1]
+        zp = A.get("logits_p")
+        if zp is None:
+            zp = A["logits_p"] = ops.upscore_tc_alloc(N, H // 8, W // 8, C, 8, self.device)
+        ops.upscore_tc_fwd(f3p, self.packed["up8"], C, 8, zp, x_lo=x_lo)
+        A["logits"] = ops.upscore_tc_interior(zp, C, 8)
+        return A["logits"]
+
+    def _pad4(self, arena, name, t):
+        """[N,h,w,C] -> the same tensor with the channel stride rounded up to a multiple of 4 (zero filled): the layout
+        the TMA maps of the decoder GEMMs need. No-op (no copy) when C is already a multiple of 4."""
+        Cc = t.shape[-1]
+        if Cc % 4 == 0:
+            return t
+        buf = arena.get(name)
+        if buf is None:
+            buf = arena[name] = torch.zeros(tuple(t.shape[:-1]) + ((Cc + 3) // 4 * 4,), dtype=t.dtype, device=t.device)
+        buf[..., :Cc].copy_(t)
+        return buf
 
     @staticmethod
     def dropout_seed(seed, layer):
@@ -255,14 +275,28 @@ class Engine:
         G = self.grads
         f32 = torch.float32
         self.loss_buf.zero_()
-        dz = self._buf(A, "dlogits", (N, H, W, C), f32)
+        zp = A["logits_p"]
+        dzp = A.get("dlogits_p")
+        if dzp is None:   # zero border, never written again
+            dzp = A["dlogits_p"] = ops.upscore_tc_alloc(N, H // 8, W // 8, C, 8, self.device, zero=True)
         npx = N * H * W
-        ops.softmax_xent(logits, labels.view(torch.uint8), self.loss_buf[0:1], dz, grad_scale=1.0 / npx)
-        # decoder backward
-        df3 = self._buf(A, "df3", A["f3"].shape, f32)
-        ops.upscore_bwd(A["f3"], self.view("fc7_pool4_pool3_conv2d_trans/kernel"), dz, 8,
-                        self.view("fc7_pool4_pool3_conv2d_trans/kernel", G),
-                        self.view("fc7_pool4_pool3_conv2d_trans/bias", G), df3)
+        dc8 = self.view("fc7_pool4_pool3_conv2d_trans/bias", G)
+        dc8.zero_()
+        ops.softmax_xent(zp, labels.view(torch.uint8), self.loss_buf[0:1], dzp, grad_scale=1.0 / npx, dbias=dc8,
+                         pad=4, num_classes=C)
+        # decoder backward; upscore8 on the tensor cores
+        dz_lo = self._split(A, "dlogits_p", dzp)[1]
+        f3p = A["f3p"] if C % 4 else A["f3"]
+        f3_lo = A.get("f3p.lo")
+        ops.upscore_tc_dw(f3p, dzp, C, 8, self.view("fc7_pool4_pool3_conv2d_trans/kernel", G), x_lo=f3_lo,
+                          dzp_lo=dz_lo)
+        df3p = self._buf(A, "df3p", f3p.shape, f32)
+        ops.upscore_tc_dx(dzp, self.packed["up8"], C, 8, df3p, dzp_lo=dz_lo)
+        if C % 4:
+            df3 = self._buf(A, "df3", A["f3"].shape, f32)
+            df3.copy_(df3p[..., :C])
+        else:
+            df3 = df3p
         df4 = self._buf(A, "df4", A["f4"].shape, f32)
         ops.upscore_bwd(A["f4"], self.view("fc7_pool4_conv2d_trans/kernel"), df3, 2,
                         self.view("fc7_pool4_conv2d_trans/kernel", G), self.view("fc7_pool4_conv2d_trans/bias", G), df4)
@@ -366,24 +400,26 @@ class Engine:
     def predict(self, images, argmax=True):
         """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1."""
         N, H, W, _ = images.shape
-        logits = self.forward(images, 1.0, 0, train=False)
+        self.forward(images, 1.0, 0, train=False)
+        zp = self._arena(N, H, W)["logits_p"]
         if argmax:
             out = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
-            ops.softmax_xent(logits, argmax=out)
+            ops.softmax_xent(zp, argmax=out, pad=4, num_classes=self.C)
         else:
             out = torch.empty((N, H, W, self.C), dtype=torch.float32, device=self.device)
-            ops.softmax_xent(logits, softmax=out)
+            ops.softmax_xent(zp, softmax=out, pad=4, num_classes=self.C)
         return out
 
     def eval_step(self, images, labels, conf, l2_rate=0.0):
         """One metric update (fcn8s_tensorflow.py:685-689): forward at keep_prob 1, total_loss, argmax, confusion
         matrix accumulate (conf: int64 [C,C] device tensor, conf[label, prediction])."""
         N, H, W, _ = images.shape
-        logits = self.forward(images, 1.0, 0, train=False)
+        self.forward(images, 1.0, 0, train=False)
+        zp = self._arena(N, H, W)["logits_p"]
         self.loss_buf.zero_()
         am = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
         lab = labels.view(torch.uint8)
-        ops.softmax_xent(logits, lab, self.loss_buf[0:1], argmax=am)
+        ops.softmax_xent(zp, lab, self.loss_buf[0:1], argmax=am, pad=4, num_classes=self.C)
         if l2_rate != 0.0:
             for kname in DECODER_KERNELS:
                 ops.l2_reg(self.view(kname).reshape(-1), None, self.loss_buf[1:2], l2_rate)

@@ -244,13 +244,106 @@ def upscore_bwd(x, T, dy, stride, dT, dbias, dx=None):
     return dx
 
 
-def softmax_xent(logits, labels=None, loss_sum=None, dlogits=None, softmax=None, argmax=None, grad_scale=1.0):
-    _chk_cuda(logits, labels, loss_sum, dlogits, softmax, argmax)
-    Cc = logits.shape[-1]
-    P = logits.numel() // Cc
+def softmax_xent(logits, labels=None, loss_sum=None, dlogits=None, softmax=None, argmax=None, grad_scale=1.0,
+                 dbias=None, pad=0, num_classes=None):
+    """Loss / predictor kernel. `logits` (and `dlogits`) are [N,Hp,Wp,CP] with Hp = H + 2*pad, Wp = W + 2*pad and
+    CP >= num_classes (pad = 0, CP = C: the dense tensor); labels / softmax / argmax are dense over [N,H,W]."""
+    _chk_cuda(logits, labels, loss_sum, dlogits, softmax, argmax, dbias)
+    if logits.dim() != 4:
+        logits = logits.view(1, 1, -1, logits.shape[-1])
+    N, Hp, Wp, CP = logits.shape
+    Cc = CP if num_classes is None else num_classes
     p = capi.SoftmaxParams(capi.ptr(logits), capi.ptr(labels), capi.ptr(loss_sum), capi.ptr(dlogits),
-                           capi.ptr(softmax), capi.ptr(argmax), P, Cc, grad_scale)
+                           capi.ptr(dbias), capi.ptr(softmax), capi.ptr(argmax), N, Hp - 2 * pad, Wp - 2 * pad, Cc,
+                           CP, pad, grad_scale)
     capi.check(capi.load().fcn8_softmax_xent(C.byref(p), _stream()))
+
+
+def upscore_tc_cp(num_classes, stride):
+    """Channel stride of the padded blocked output of the tensor-core transposed convolution."""
+    return capi.load().fcn8_upscore_tc_cp(num_classes, stride)
+
+
+def upscore_tc_pack(T, bias, stride, split=False, out=None):
+    """T [2s,2s,C,C], bias [C] -> dict of tensor-core operands (w_fwd, w_dx, bias_big and their *_lo halves).
+    `out`: a dict returned by an earlier call, refilled in place."""
+    _chk_cuda(T, bias)
+    Cc = T.shape[-1]
+    CP = upscore_tc_cp(Cc, stride)
+    ncols = stride * stride * CP
+    f32 = dict(dtype=torch.float32, device=T.device)
+    if out is None:
+        out = dict(w_fwd=torch.empty((ncols, 128), **f32), w_dx=torch.empty((64, 4 * ncols), **f32),
+                   bias_big=torch.empty(ncols, **f32), w_fwd_lo=None, w_dx_lo=None)
+        if split:
+            out["w_fwd_lo"] = torch.empty_like(out["w_fwd"])
+            out["w_dx_lo"] = torch.empty_like(out["w_dx"])
+    p = capi.UpscorePackParams(capi.ptr(T), capi.ptr(bias), capi.ptr(out["w_fwd"]), capi.ptr(out["w_fwd_lo"]),
+                               capi.ptr(out["w_dx"]), capi.ptr(out["w_dx_lo"]), capi.ptr(out["bias_big"]), Cc, stride)
+    capi.check(capi.load().fcn8_upscore_tc_pack(C.byref(p), _stream()))
+    return out
+
+
+def _tc_params(x, x_lo, w, w_lo, bias_big, zp, zp_lo, dx, dT, Cc, stride):
+    N, h, wd, ldx = x.shape if x is not None else dx.shape
+    nseg = 3 if (w_lo is not None or (x_lo is not None and zp_lo is not None)) else 1
+    return capi.UpscoreTcParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(w), capi.ptr(w_lo), capi.ptr(bias_big),
+                                capi.ptr(zp), capi.ptr(zp_lo), capi.ptr(dx), capi.ptr(dT), N, h, wd, Cc, stride, ldx,
+                                nseg)
+
+
+def upscore_tc_alloc(N, h, w, num_classes, stride, device, zero=False):
+    """Padded blocked tensor [N, s*(h+1), s*(w+1), CP] of the tensor-core transposed convolution."""
+    CP = upscore_tc_cp(num_classes, stride)
+    shape = (N, stride * (h + 1), stride * (w + 1), CP)
+    return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
+
+
+def upscore_tc_interior(zp, num_classes, stride):
+    """[N, s*h, s*w, C] view of the transposed convolution's output inside its padded tensor."""
+    p = stride // 2
+    return zp[:, p:zp.shape[1] - p, p:zp.shape[2] - p, :num_classes]
+
+
+def upscore_tc_fwd(x, packed, num_classes, stride, out, x_lo=None):
+    """x [N,h,w,ldx] fp32 (channels >= C zero) -> padded blocked output `out` (see upscore_tc_alloc)."""
+    _chk_cuda(x, x_lo, out)
+    w_lo = packed["w_fwd_lo"] if x_lo is not None else None
+    p = _tc_params(x, x_lo, packed["w_fwd"], w_lo, packed["bias_big"], out, None, None, None, num_classes, stride)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(capi.load().fcn8_upscore_tc_fwd(C.byref(p), _stream()))
+    if e0 is not None:
+        N, h, w, _ = x.shape
+        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+    return out
+
+
+def upscore_tc_dx(dzp, packed, num_classes, stride, dx, dzp_lo=None):
+    """Input gradient of the transposed convolution from the padded blocked dz (zero border) into dx [N,h,w,ldx]."""
+    _chk_cuda(dzp, dzp_lo, dx)
+    w_lo = packed["w_dx_lo"] if dzp_lo is not None else None
+    p = _tc_params(None, None, packed["w_dx"], w_lo, None, dzp, dzp_lo, dx, None, num_classes, stride)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(capi.load().fcn8_upscore_tc_dx(C.byref(p), _stream()))
+    if e0 is not None:
+        N, h, w, _ = dx.shape
+        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+    return dx
+
+
+def upscore_tc_dw(x, dzp, num_classes, stride, dT, x_lo=None, dzp_lo=None):
+    """Filter gradient dT [2s,2s,C,C] (TF layout) of the transposed convolution."""
+    _chk_cuda(x, dzp, dT, x_lo, dzp_lo)
+    p = _tc_params(x, x_lo, None, None, None, dzp, dzp_lo, None, dT, num_classes, stride)
+    lib = capi.load()
+    nbytes = lib.fcn8_upscore_tc_dw_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(lib.fcn8_upscore_tc_dw(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    if e0 is not None:
+        N, h, w, _ = x.shape
+        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+    return dT
 
 
 def confusion_matrix(pred, labels_onehot, conf):

@@ -201,22 +201,66 @@ size_t fcn8_upscore_bwd_workspace_bytes(const Fcn8UpscoreParams* p);
 int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- loss / predictor: fcn8s_tensorflow.py:253 (softmax_cross_entropy_with_logits + reduce_mean), :268-269.
- * labels: uint8 [P][C] one-hot as yielded by the generators (numpy bool), used as fp32 weights y_c like TF does.
+ * logits (and dlogits, same layout): pixel (n,y,x) at ((n*(H+2*pad) + y+pad)*(W+2*pad) + x+pad)*CP, CP >= C -- pad = 0,
+ * CP = C is the dense [N,H,W,C] tensor; pad = 4, CP = fcn8_upscore_tc_cp(C, 8) is the padded output of
+ * fcn8_upscore_tc_fwd.  labels: uint8 dense [N,H,W,C] one-hot as yielded by the generators (numpy bool), used as fp32
+ * weights y_c like TF does.
  * loss_sum (fp32 scalar, accumulated; caller zeroes) += sum_p (sum_c y_c)*lse(z) - sum_c y_c z_c;
- * dlogits[p][c] = (softmax_c * sum_c y_c - y_c) * grad_scale   (grad_scale = 1/(N*H*W) [* 1/world]).
- * softmax / argmax(int64, first max) for predict().  Any output pointer may be NULL. */
+ * dlogits[p][c] = (softmax_c * sum_c y_c - y_c) * grad_scale   (grad_scale = 1/(N*H*W)), channels C..CP-1 = 0;
+ * dbias[c] (accumulated; caller zeroes) += sum_p dlogits[p][c]  (bias gradient of the last transposed conv);
+ * softmax fp32 dense [N,H,W,C] / argmax int64 dense [N,H,W] (first max) for predict().  Any output may be NULL;
+ * softmax and dlogits are mutually exclusive. */
 typedef struct {
   const float* logits;
   const uint8_t* labels;
   float* loss_sum;
   float* dlogits;
+  float* dbias;
   float* softmax;
   int64_t* argmax;
-  int64_t P;
-  int32_t C;
+  int32_t N, H, W, C, CP, pad;
   float grad_scale;
 } Fcn8SoftmaxParams;
 int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream);
+
+/* ---- transposed convolutions on the tensor cores (tf.layers.conv2d_transpose k=2s, stride s, 'same',
+ * fcn8s_tensorflow.py:204-233, and its autodiff :257) as phase GEMMs on tcgen05 (kind::tf32; nseg = 3: 3xTF32):
+ * an s x s block of outputs depends on a 2x2 input neighbourhood, so with rows = blocks (J,I), J in [0,h], I in [0,w],
+ *   Zblock[(dy,dx,co)] = sum_{(ty,tx,ci)} x[n, J-1+ty, I-1+tx, ci] * T[dy+s(1-ty), dx+s(1-tx), co, ci] + bias[co].
+ * The blocks tile a PADDED tensor zp[N, s*(h+1), s*(w+1), CP] whose interior [s/2 : s/2+s*h, s/2 : s/2+s*w] is the
+ * transposed convolution's output (pixel (oy,ox) at zp[n, oy+s/2, ox+s/2, :]); CP = fcn8_upscore_tc_cp(C, s).
+ * The border of zp holds don't-care values after fwd and MUST be zero in the dz passed to dx / dw.
+ * x / dx: [N,h,w,ldx] fp32, ldx a multiple of 4 >= C, channels >= C zero.
+ * Operands come from fcn8_upscore_tc_pack (w_fwd [s*s*CP][128], w_dx [64][4*s*s*CP], bias_big [s*s*CP]; the *_lo
+ * arrays are the low halves of the tf32 split, NULL for single-pass tf32). */
+typedef struct {
+  const float* T;     /* [2s,2s,C,C] (kh,kw,out,in) */
+  const float* bias;  /* [C] */
+  float* w_fwd;
+  float* w_fwd_lo;
+  float* w_dx;
+  float* w_dx_lo;
+  float* bias_big;
+  int32_t C, stride;
+} Fcn8UpscorePackParams;
+typedef struct {
+  const float* x;
+  const float* x_lo;
+  const float* w;     /* fwd: w_fwd, dx: w_dx */
+  const float* w_lo;
+  const float* bias_big;
+  float* zp;          /* fwd: output; dx / dw: dz input */
+  const float* zp_lo;
+  float* dx;
+  float* dT;          /* dw: [2s,2s,C,C] TF layout */
+  int32_t N, h, wd, C, stride, ldx, nseg; /* x is [N,h,wd,ldx] */
+} Fcn8UpscoreTcParams;
+int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride);
+int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream);
+int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream);
+int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream);
+size_t fcn8_upscore_tc_dw_workspace_bytes(const Fcn8UpscoreTcParams* p);
+int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- streaming metrics: fcn8s_tensorflow.py:280-301 (labels_argmax, tf.metrics.mean_iou / accuracy); the device
  * analogue of cityscapesscripts/evaluation/addToConfusionMatrix_impl.c:3-16: conf[gt*C + pred] += 1 (uint64). */

@@ -386,29 +386,101 @@ def decoder_kernels():
             ok &= report("upscore bwd dx", dx, xr.grad.permute(0, 2, 3, 1), 1e-5)
             ok &= report("upscore bwd dT", dT, Tr.grad.permute(2, 3, 1, 0), 1e-5)
             ok &= report("upscore bwd dbias", dbias, dy.double().sum((0, 1, 2)), 1e-5)
-        # softmax / xent
+        # softmax / xent: dense layout (pad 0, CP = C) and the padded layout of the tensor-core upscore8 stage
         P = 5000
-        z = torch.randn(P, Cc, device=dev) * 3
-        ids = torch.randint(0, Cc, (P,), device=dev)
-        onehot = F.one_hot(ids, Cc).to(torch.uint8)
-        loss = torch.zeros(1, device=dev)
-        dz = torch.empty_like(z)
-        sm = torch.empty_like(z)
-        am = torch.empty(P, dtype=torch.int64, device=dev)
-        ops.softmax_xent(z, onehot, loss, dz, sm, am, grad_scale=1.0 / P)
-        zr = z.double().requires_grad_(True)
-        lr = F.cross_entropy(zr, ids, reduction="sum")
-        lr.backward()
-        ok &= report("xent loss C%d" % Cc, loss, lr.detach().view(1), 1e-5)
-        ok &= report("xent dz", dz, zr.grad / P, 1e-5)
-        ok &= report("softmax", sm, F.softmax(z.double(), -1), 1e-5)
-        ok &= bool((am == z.argmax(-1)).all().item())
+        for pad, CP, (n_, h_, w_) in ((0, Cc, (1, 1, P)), (4, (Cc + 3) // 4 * 4, (2, 24, 160)), (4, (Cc + 3) // 4 * 4, (1, 8, 96))):
+            P = n_ * h_ * w_
+            zfull = torch.randn(n_, h_ + 2 * pad, w_ + 2 * pad, CP, device=dev) * 3
+            z = zfull[:, pad:pad + h_, pad:pad + w_, :Cc].reshape(P, Cc)
+            ids = torch.randint(0, Cc, (P,), device=dev)
+            onehot = F.one_hot(ids, Cc).to(torch.uint8).view(n_, h_, w_, Cc)
+            loss = torch.zeros(1, device=dev)
+            dzfull = torch.zeros_like(zfull)
+            dbias = torch.zeros(Cc, device=dev)
+            sm = torch.empty(n_, h_, w_, Cc, device=dev)
+            am = torch.empty(n_, h_, w_, dtype=torch.int64, device=dev)
+            ops.softmax_xent(zfull, onehot, loss, dzfull, None, am, grad_scale=1.0 / P, dbias=dbias, pad=pad,
+                             num_classes=Cc)
+            ops.softmax_xent(zfull, softmax=sm, pad=pad, num_classes=Cc)
+            zr = z.double().requires_grad_(True)
+            lr = F.cross_entropy(zr, ids, reduction="sum")
+            lr.backward()
+            dz = dzfull[:, pad:pad + h_, pad:pad + w_, :Cc].reshape(P, Cc)
+            ok &= report("xent loss C%d pad%d" % (Cc, pad), loss, lr.detach().view(1), 1e-5)
+            ok &= report("xent dz", dz, zr.grad / P, 1e-5)
+            ok &= report("xent dbias", dbias, (zr.grad / P).sum(0), 1e-4)
+            ok &= report("softmax", sm.view(P, Cc), F.softmax(z.double(), -1), 1e-5)
+            ok &= bool((am.view(P) == z.argmax(-1)).all().item())
+            if pad:
+                border = dzfull.clone()
+                border[:, pad:pad + h_, pad:pad + w_, :] = 0
+                ok &= bool((border == 0).all().item()) and bool((dzfull[..., Cc:] == 0).all().item())
+        am = am.view(-1)
+        onehot = onehot.view(P, Cc)
         conf = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
         ops.confusion_matrix(am, onehot, conf)
         refc = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
         refc.view(-1).index_add_(0, ids * Cc + am, torch.ones(P, dtype=torch.int64, device=dev))
         ok &= bool((conf == refc).all().item())
         print("  confusion matrix C%d exact: %s" % (Cc, bool((conf == refc).all().item())))
+    return ok
+
+
+def upscore_tc_case(Cc, s_, N, h, w, nseg, tol):
+    """Tensor-core transposed convolution (phase GEMM) fwd / dx / dw vs fp64 conv_transpose2d autograd."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    k = 2 * s_
+    ldx = (Cc + 3) // 4 * 4
+    x = torch.zeros(N, h, w, ldx, device=dev)
+    x[..., :Cc] = torch.randn(N, h, w, Cc, device=dev)
+    T = torch.randn(k, k, Cc, Cc, device=dev) * 0.1
+    bias = torch.randn(Cc, device=dev)
+    packed = ops.upscore_tc_pack(T, bias, s_, split=(nseg == 3))
+    zp = ops.upscore_tc_alloc(N, h, w, Cc, s_, dev)
+    x_lo = ops.split_tf32(x)[1] if nseg == 3 else None
+    ops.upscore_tc_fwd(x, packed, Cc, s_, zp, x_lo=x_lo)
+    y = ops.upscore_tc_interior(zp, Cc, s_)
+    xr = x[..., :Cc].double().permute(0, 3, 1, 2).requires_grad_(True)
+    Tr = T.double().permute(3, 2, 0, 1).contiguous().requires_grad_(True)   # [ci, co, a, b]
+    yr = F.conv_transpose2d(xr, Tr, stride=s_, padding=s_ // 2) + bias.double().view(1, -1, 1, 1)
+    tag = "C%d s%d N%d %dx%d seg%d" % (Cc, s_, N, h, w, nseg)
+    ok = report("upscore_tc fwd " + tag, y, yr.permute(0, 2, 3, 1), tol)
+    dy = torch.randn(N, h * s_, w * s_, Cc, device=dev)
+    yr.backward(dy.double().permute(0, 3, 1, 2))
+    dzp = ops.upscore_tc_alloc(N, h, w, Cc, s_, dev, zero=True)
+    ops.upscore_tc_interior(dzp, Cc, s_).copy_(dy)
+    dzp_lo = ops.split_tf32(dzp)[1] if nseg == 3 else None
+    dx = torch.full((N, h, w, ldx), float("nan"), device=dev)
+    ops.upscore_tc_dx(dzp, packed, Cc, s_, dx, dzp_lo=dzp_lo)
+    # dx reduces over K = 4*s*s*CP (5120 at s=8, C=20): the TMEM accumulator rounds toward zero on every MMA, which
+    # costs ~2^-25 per accumulation step (measured: error grows linearly with K), so the 3xTF32 bound here is 1e-4
+    ok &= report("upscore_tc dx  " + tag, dx[..., :Cc], xr.grad.permute(0, 2, 3, 1), max(tol, 1e-4))
+    ok &= bool((dx[..., Cc:] == 0).all().item())
+    dT = torch.full_like(T, float("nan"))
+    ops.upscore_tc_dw(x, dzp, Cc, s_, dT, x_lo=x_lo, dzp_lo=dzp_lo)
+    ok &= report("upscore_tc dT  " + tag, dT, Tr.grad.permute(2, 3, 1, 0), tol)
+    return ok
+
+
+@case
+def upscore_tc_stride8():
+    ok = True
+    for Cc in (20, 3, 2):
+        ok &= upscore_tc_case(Cc, 8, 2, 4, 6, 3, 2e-6)
+        ok &= upscore_tc_case(Cc, 8, 1, 9, 17, 1, 2e-3)
+    ok &= upscore_tc_case(20, 8, 3, 16, 24, 3, 2e-6)      # several m-tiles, ragged
+    ok &= upscore_tc_case(5, 8, 2, 8, 12, 3, 2e-6)
+    return ok
+
+
+@case
+def upscore_tc_stride2():
+    ok = True
+    for Cc in (20, 3):
+        ok &= upscore_tc_case(Cc, 2, 2, 5, 7, 3, 2e-6)
+        ok &= upscore_tc_case(Cc, 2, 2, 16, 32, 1, 2e-3)
     return ok
 
 
