@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfcn8s_sm100.so")
 
-BF16, F32 = 0, 1
+BF16, F32, BF16X2 = 0, 1, 2
 EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32 = 1, 2, 4, 8, 16, 64
 
 EXPORTS = [
@@ -20,7 +20,7 @@ EXPORTS = [
     "fcn8_upscore_fwd", "fcn8_upscore_bwd_workspace_bytes", "fcn8_upscore_bwd", "fcn8_softmax_xent",
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
-    "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw",
+    "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
 ]
 
 
@@ -39,14 +39,16 @@ class ConvParams(C.Structure):
                 ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("ksize", C.c_int32), ("dtype", C.c_int32), ("nseg", C.c_int32), ("flags", C.c_int32),
                 ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
-                ("force_splits", C.c_int32), ("force_bn", C.c_int32)]
+                ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32),
+                ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32)]
 
 
 class WgradParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("dy", C.c_void_p), ("dy_lo", C.c_void_p),
                 ("dw", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
                 ("Cout", C.c_int32), ("ksize", C.c_int32), ("rows_valid", C.c_int32), ("dtype", C.c_int32),
-                ("nseg", C.c_int32), ("force_splits", C.c_int32), ("force_bn", C.c_int32)]
+                ("nseg", C.c_int32), ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32),
+                ("dy_ld", C.c_int32)]
 
 
 class PackParams(C.Structure):
@@ -132,7 +134,8 @@ def load():
     lib.fcn8_upscore_tc_cp.restype = C.c_int32
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
-    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    lib.fcn8_shadow_weights.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_l2_reg.argtypes = [vp, vp, vp, sz, C.c_float, vp]
     _lib = lib
     return lib
@@ -143,6 +146,6 @@ def check(status):
         raise Fcn8Error("fcn8 error %d: %s" % (status, load().fcn8_last_error().decode()))
 
 
-def ptr(t):
-    """Device pointer of a torch tensor (or None)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+def ptr(t, offset_elems=0):
+    """Device pointer of a torch tensor (or None), optionally advanced by a number of elements."""
+    return None if t is None else C.c_void_p(t.data_ptr() + offset_elems * t.element_size())

@@ -51,12 +51,13 @@ EncodeTiledFn get_encode() {
 
 // NHWC activation map: dims (C, W, H, N), box (CH, bw, bh, bn), 128B swizzle, OOB -> 0 (= SAME zero padding).
 int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int W, int C, int bw, int bh, int bn,
-                   bool atom32 = false) {
+                   bool atom32 = false, int ld = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int es = dtype == FCN8_BF16 ? 2 : 4;
+  if (ld <= 0) ld = C;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es};
   const cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dtype == FCN8_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
@@ -82,6 +83,23 @@ int encode_w_map(CUtensorMap* m, const void* ptr, int dtype, int rows, int ktot,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(w rows %d k %d bn %d) failed: %d", rows, ktot, bn, (int)r);
+  return 0;
+}
+
+// bf16 weight tensor in TF layout [taps][Cin_w][Cout_w] as dims (co, ci, tap); box (64 co, box_ci, 1).
+int encode_hwio_map(CUtensorMap* m, const void* ptr, int taps, int cin_w, int cout_w, int box_ci) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t dims[3] = {(cuuint64_t)cout_w, (cuuint64_t)cin_w, (cuuint64_t)taps};
+  const cuuint64_t strides[2] = {(cuuint64_t)cout_w * 2, (cuuint64_t)cin_w * cout_w * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box_ci, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(hwio taps %d ci %d co %d box %d) failed: %d", taps, cin_w, cout_w,
+                box_ci, (int)r);
   return 0;
 }
 
@@ -130,8 +148,11 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cin=%d must be a multiple of %d", p->Cin, CH);
   if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cout=%d must be a multiple of 64", p->Cout);
   if (!(p->ksize & 1)) return fail(FCN8_ERR_BAD_SHAPE, "conv: ksize must be odd");
-  if (p->nseg != 1 && !(p->nseg == 3 && p->dtype == FCN8_F32))
-    return fail(FCN8_ERR_UNSUPPORTED, "conv: nseg must be 1 (or 3 with FCN8_F32)");
+  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "conv: nseg must be 1 or 3");
+  if (p->dtype != FCN8_BF16 && (p->w_mode || p->out_lo || p->residual_lo))
+    return fail(FCN8_ERR_UNSUPPORTED, "conv: w_mode / out_lo / residual_lo need FCN8_BF16 operands");
+  if (p->w_mode < 0 || p->w_mode > 2) return fail(FCN8_ERR_BAD_SHAPE, "conv: w_mode must be 0, 1 or 2");
+  if (p->w_mode == 2 && p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "conv: dgrad w_mode needs Cout %% 64 == 0");
   choose_patch(p->N, p->H, p->W, 7, &pl->lbw, &pl->lbh, &pl->lbn);
   pl->tiles_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->tiles_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
@@ -258,8 +279,7 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: empty tensor");
   if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cin=%d must be a multiple of %d", p->Cin, CH);
   if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cout=%d must be a multiple of 64", p->Cout);
-  if (p->nseg != 1 && !(p->nseg == 3 && p->dtype == FCN8_F32))
-    return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 (or 3 with FCN8_F32)");
+  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 or 3");
   int bn = p->force_bn ? p->force_bn : (p->Cout % 256 == 0 ? 256 : (p->Cout % 128 == 0 ? 128 : 64));
   if (p->dtype == FCN8_F32 && bn == 256 && !p->force_bn) bn = 128;  // keep >= 3 smem stages with 4-byte operands
   if ((bn != 64 && bn != 128 && bn != 256) || p->Cout % bn)
@@ -281,7 +301,7 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   if (p->force_splits > 0) {
     splits = p->force_splits;
   } else if (tiles < sms) {
-    splits = (int)((sms + tiles - 1) / tiles);
+    splits = (int)(sms / tiles);  // floor: tiles * splits <= #SMs, one full wave (ceil would leave a 2nd, ~empty wave)
     const int max_by_k = pl->total_pb / 8 > 0 ? pl->total_pb / 8 : 1;
     if (splits > max_by_k) splits = max_by_k;
     if (splits > 64) splits = 64;
@@ -350,10 +370,17 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   const int ktot = p->ksize * p->ksize * p->Cin;
   const void* xs[3] = {p->x, p->x, p->x_lo};
   const void* ws[3] = {p->wp, p->wp_lo, p->wp};
+  const int taps = p->ksize * p->ksize;
   for (int s = 0; s < p->nseg; ++s) {
-    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn);
+    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
+                        false, p->x_ld);
     if (rc) return rc;
-    rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
+    if (p->w_mode == 0)
+      rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
+    else if (p->w_mode == 1)
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64);
+    else
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, pl.BN);
     if (rc) return rc;
   }
   ConvGemmArgs a;
@@ -382,9 +409,13 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
   a.flags = p->flags & (31 | 64);
-  a.osW = p->Cout;
-  a.osH = (long long)p->W * p->Cout;
-  a.osN = (long long)p->H * p->W * p->Cout;
+  const int out_ld = p->out_ld > 0 ? p->out_ld : p->Cout;
+  a.osW = out_ld;
+  a.osH = (long long)p->W * out_ld;
+  a.osN = (long long)p->H * p->W * out_ld;
+  a.b_mode = p->w_mode == 1 ? 2 : (p->w_mode == 2 ? 1 : 0);
+  a.out_lo = p->out_lo;
+  a.residual_lo = p->residual_lo;
   a.mask_scale = p->mask_scale;
   a.seed = p->seed;
   if (p->flags & FCN8_EPI_DROPOUT) {
@@ -446,10 +477,10 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   for (int s = 0; s < p->nseg; ++s) {
     const bool atom32 = p->dtype == FCN8_F32;  // MN-major tf32 operands need the 32-byte-granule swizzle
     rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
-                        atom32);
+                        atom32, p->x_ld);
     if (rc) return rc;
     rc = encode_act_map(&maps.b[s], ds[s], p->dtype, p->N, p->H, p->W, p->Cout, 1 << pl.lbw, 1 << pl.lbh,
-                        1 << pl.lbn, atom32);
+                        1 << pl.lbn, atom32, p->dy_ld);
     if (rc) return rc;
   }
   WgradArgs a;
@@ -506,7 +537,6 @@ int32_t fcn8_pack_weights(const Fcn8PackParams* p, void* stream) {
   if (!p || !p->w || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "pack: null pointer");
   if (p->mode != 0 && p->mode != 1) return fail(FCN8_ERR_BAD_SHAPE, "pack: mode must be 0 or 1");
   if (p->mode == 0 && p->CinPad < p->Cin) return fail(FCN8_ERR_BAD_SHAPE, "pack: CinPad < Cin");
-  if (p->dtype == FCN8_BF16 && p->out_lo) return fail(FCN8_ERR_UNSUPPORTED, "pack: out_lo only with FCN8_F32");
   cudaError_t e = launch_pack(p->w, p->out, p->out_lo, p->ksize, p->Cin, p->Cout, p->CinPad, p->mode, p->dtype,
                               (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "pack launch");
@@ -523,7 +553,7 @@ int32_t fcn8_split_tf32(const float* x, float* hi, float* lo, size_t n, void* st
 
 static int check_pool(const Fcn8PoolParams* p) {
   if (!p || !p->x || !p->y) return fail(FCN8_ERR_BAD_SHAPE, "pool: null pointer");
-  const int vec = p->dtype == FCN8_BF16 ? 8 : 4;
+  const int vec = p->dtype == FCN8_F32 ? 4 : 8;
   if (p->C % vec) return fail(FCN8_ERR_BAD_SHAPE, "pool: C=%d must be a multiple of %d", p->C, vec);
   if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "pool: empty tensor");
   if (!aligned16(p->x) || !aligned16(p->y)) return fail(FCN8_ERR_BAD_ALIGN, "pool: alignment");
@@ -548,7 +578,7 @@ size_t fcn8_bias_grad_workspace_bytes(const Fcn8BiasGradParams* p) {
 }
 int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t workspace_bytes, void* stream) {
   if (!p || !p->dy || !p->db) return fail(FCN8_ERR_BAD_SHAPE, "bias_grad: null pointer");
-  const int vec = p->dtype == FCN8_BF16 ? 8 : 4;
+  const int vec = p->dtype == FCN8_F32 ? 4 : 8;
   const int CV = p->C / vec;
   if (p->C % vec || (CV & (CV - 1))) return fail(FCN8_ERR_BAD_SHAPE, "bias_grad: C/%d must be a power of two", vec);
   if (workspace_bytes < fcn8_bias_grad_workspace_bytes(p) || !workspace)
@@ -633,12 +663,21 @@ int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot,
 }
 
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* stream) {
+                  float eps, float grad_scale, void* w_hi, void* w_lo, void* stream) {
   if (!p || !g || !m || !v) return fail(FCN8_ERR_BAD_SHAPE, "adam: null pointer");
-  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v))
+  if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (w_hi && !aligned16(w_hi)) ||
+      (w_lo && !aligned16(w_lo)))
     return fail(FCN8_ERR_BAD_ALIGN, "adam: pointers must be 16-byte aligned");
-  cudaError_t e = launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, (cudaStream_t)stream);
+  if (w_lo && !w_hi) return fail(FCN8_ERR_BAD_SHAPE, "adam: w_lo without w_hi");
+  cudaError_t e = launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, w_hi, w_lo, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam launch");
+}
+int32_t fcn8_shadow_weights(const float* p, void* w_hi, void* w_lo, size_t n, void* stream) {
+  if (!p || !w_hi) return fail(FCN8_ERR_BAD_SHAPE, "shadow: null pointer");
+  if (!aligned16(p) || !aligned16(w_hi) || (w_lo && !aligned16(w_lo)))
+    return fail(FCN8_ERR_BAD_ALIGN, "shadow: pointers must be 16-byte aligned");
+  cudaError_t e = launch_shadow(p, w_hi, w_lo, n, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "shadow launch");
 }
 int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float rate, void* stream) {
   if (!w) return fail(FCN8_ERR_BAD_SHAPE, "l2_reg: null pointer");
@@ -815,7 +854,7 @@ void plan_updw(const Fcn8UpscoreTcParams* p, UpDwPlan* pl) {
   pl->pb_y = (p->h + 1 + (1 << pl->lbh) - 1) >> pl->lbh;
   pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
   pl->total_pb = p->nseg * pl->pb_x * pl->pb_y * pl->pb_b;
-  int splits = (num_sms() + pl->tiles_n - 1) / pl->tiles_n;
+  int splits = num_sms() / pl->tiles_n;
   const int max_by_k = pl->total_pb / 4 > 0 ? pl->total_pb / 4 : 1;
   if (splits > max_by_k) splits = max_by_k;
   if (splits > 64) splits = 64;

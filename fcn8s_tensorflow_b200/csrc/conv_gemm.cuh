@@ -85,6 +85,14 @@ struct ConvGemmArgs {
   // a_mode 1 = blocked 5-D map (s*CP, Wb, s, Hb, N) of a padded transposed-conv output: k-block (tap, cb) reads row
   // dy = cb / blk_chunks, chunk cb % blk_chunks of block (y + pad - kh, x + pad - kw).
   int a_mode, blk_chunks;
+  // B operand: b_mode 0 = packed K-major 2-D map [Cout][K]; b_mode 1 / 2 read the TF-layout (HWIO) weight tensor
+  // itself through a 3-D map (co, ci, tap): 1 = dgrad (K = (tap', co) K-major rows ci, tap = taps-1-tap' is the
+  // 180-degree rotation), 2 = fprop (K = (tap, ci), N = co contiguous: MN-major chunks of [64 ci][64 co]).
+  int b_mode;
+  // bf16 hi/lo pair output (fp32-equivalent storage): out_lo != nullptr stores hi = bf16(v) to out, lo = bf16(v - hi)
+  // to out_lo at the same element index; residual_lo is the low half of the residual.
+  void* out_lo;
+  const void* residual_lo;
 };
 
 struct TensorMaps3 {
@@ -122,7 +130,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // Epilogue math on 32 consecutive columns of one output row. `idx` = element index of column c0 of this row.
 template <bool TF32>
 __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
-                                               int ncols = 32) {
+                                               int ncols, size_t dense_idx) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
@@ -166,6 +174,20 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
           f[8 * i + 2 * j + 1] += t.y;
         }
       }
+      if (g.residual_lo) {
+        const uint4* l4 = reinterpret_cast<const uint4*>(reinterpret_cast<const OutT*>(g.residual_lo) + idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q = __ldg(l4 + i);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 t = __bfloat1622float2(h[j]);
+            f[8 * i + 2 * j] += t.x;
+            f[8 * i + 2 * j + 1] += t.y;
+          }
+        }
+      }
     }
   }
   if (g.flags & EPI_RELU) {
@@ -175,7 +197,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
   if (g.flags & EPI_DROPOUT) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      f[i] = dropout_keep(g.seed, static_cast<uint64_t>(idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
+      f[i] = dropout_keep(g.seed, static_cast<uint64_t>(dense_idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
   }
   if (g.flags & EPI_MASK) {
     const OutT* m = reinterpret_cast<const OutT*>(g.mask_src) + idx;
@@ -216,10 +238,22 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
       if (4 * i < ncols) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   } else {
     uint4* o4 = reinterpret_cast<uint4*>(o);
+    uint32_t hi[16];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      o4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]), pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                         pack_bf16x2(f[8 * i + 4], f[8 * i + 5]), pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+    for (int i = 0; i < 16; ++i) hi[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    if (g.out_lo) {
+      uint4* l4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.out_lo) + idx);
+      uint32_t lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[i]));
+        lo[i] = pack_bf16x2(f[2 * i] - h.x, f[2 * i + 1] - h.y);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+    }
   }
 }
 
@@ -300,7 +334,15 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
             tma_load_5d(&maps.a[seg], &full_bar[stage], sa, (cb - bdy * g.blk_chunks) * CH, x0 + g.pad - kw, bdy,
                         y0 + g.pad - kh, n0);
           }
-          tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
+          if (g.b_mode == 0) {
+            tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
+          } else if (g.b_mode == 1) {
+            tma_load_3d(&maps.b[seg], &full_bar[stage], sb, cb * CH, nb * BN, g.taps - 1 - tap);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(&maps.b[seg], &full_bar[stage], sb + j * 8192, nb * BN + j * 64, cb * CH, tap);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -325,7 +367,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, 0u, 128u, BN);
+      const bool b_mn = g.b_mode == 2;  // B = [64 k][64 n] MN-major chunks (bf16 only)
+      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, b_mn ? 1u : 0u, 128u, BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -343,11 +386,14 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, 16, 1024);
+          // K-major B: 128-byte rows, +32 B per MMA; MN-major B: LBO = 8 KB between 64-wide N chunks, SBO = 1 KB
+          // between 8-row K groups, +16 K-rows (2 KB) per MMA
+          const uint64_t bdesc = b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+          const uint32_t badv = b_mn ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            // advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            // A: advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -407,7 +453,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
               idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
             }
             const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
-            if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols);
+            if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0);
           }
         }
       }

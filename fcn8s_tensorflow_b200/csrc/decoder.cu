@@ -19,25 +19,43 @@ static inline int grid_for(size_t work, int threads, int max_blocks = 148 * 16) 
   return static_cast<int>(b);
 }
 
-template <typename T>
-__device__ __forceinline__ float ld_act(const T* p) {
-  if constexpr (sizeof(T) == 2)
-    return __bfloat162float(*p);
-  else
-    return *p;
+// Scalar access to channel c of pixel p in the three activation storage formats (include/fcn8s_b200.h):
+// FMT 0 bf16 [P][C], 1 fp32 [P][C], 2 bf16 hi/lo pair [P][2C] (value = hi + lo).
+template <int FMT>
+__device__ __forceinline__ float ld_px(const void* x, long long p, int C, int c) {
+  if constexpr (FMT == 1) {
+    return static_cast<const float*>(x)[p * C + c];
+  } else if constexpr (FMT == 0) {
+    return __bfloat162float(static_cast<const __nv_bfloat16*>(x)[p * C + c]);
+  } else {
+    const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(x) + p * 2 * C + c;
+    return __bfloat162float(b[0]) + __bfloat162float(b[C]);
+  }
 }
-template <typename T>
-__device__ __forceinline__ void st_act(T* p, float v) {
-  if constexpr (sizeof(T) == 2)
-    *p = __float2bfloat16_rn(v);
-  else
-    *p = v;
+template <int FMT>
+__device__ __forceinline__ void st_px(void* x, long long p, int C, int c, float v) {
+  if constexpr (FMT == 1) {
+    static_cast<float*>(x)[p * C + c] = v;
+  } else if constexpr (FMT == 0) {
+    static_cast<__nv_bfloat16*>(x)[p * C + c] = __float2bfloat16_rn(v);
+  } else {
+    __nv_bfloat16* b = static_cast<__nv_bfloat16*>(x) + p * 2 * C + c;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    b[0] = h;
+    b[C] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
 }
+#define FCN8_FMT_DISPATCH(fmt, CALL)      \
+  do {                                    \
+    if ((fmt) == 0) { CALL(0); }          \
+    else if ((fmt) == 1) { CALL(1); }     \
+    else { CALL(2); }                     \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------ score heads
 // One warp per pixel: lanes stride over Cin, each keeps C partial sums, then a butterfly reduction.
-template <typename T>
-__global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
+template <int FMT>
+__global__ void head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
                                 float* __restrict__ s, long long P, int Cin, int C, float scale) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -46,9 +64,8 @@ __global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict
     float acc[CMAX];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-    const T* xp = x + p * Cin;
     for (int ci = lane; ci < Cin; ci += 32) {
-      const float xv = ld_act(xp + ci);
+      const float xv = ld_px<FMT>(x, p, Cin, ci);
       const float* kr = K + static_cast<size_t>(ci) * C;
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
@@ -71,8 +88,8 @@ __global__ void head_fwd_kernel(const T* __restrict__ x, const float* __restrict
 }
 
 // dK / db partials: block (bx, by) covers pixels [bx*ppb, ...) and input channels [by*blockDim, ...).
-template <typename T>
-__global__ void head_bwd_w_kernel(const T* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws,
+template <int FMT>
+__global__ void head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws,
                                   long long P, int Cin, int C, long long ppb) {
   __shared__ float sds[64][CMAX];
   const int ci = blockIdx.y * blockDim.x + threadIdx.x;
@@ -88,7 +105,7 @@ __global__ void head_bwd_w_kernel(const T* __restrict__ x, const float* __restri
     __syncthreads();
     if (ci < Cin) {
       for (int q = 0; q < np; ++q) {
-        const float xv = ld_act(x + (pc + q) * Cin + ci);
+        const float xv = ld_px<FMT>(x, pc + q, Cin, ci);
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
           if (c < C) acc[c] = fmaf(xv, sds[q][c], acc[c]);
@@ -124,9 +141,9 @@ __global__ void rows_colsum_kernel(const float* __restrict__ ds, float* __restri
   }
 }
 // dx[p][ci] = scale * sum_c ds[p][c] * K[ci][c]  (* relu/dropout mask of x)
-template <typename T>
-__global__ void head_bwd_x_kernel(const T* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
-                                  T* __restrict__ dx, long long P, int Cin, int C, float scale, int mask,
+template <int FMT>
+__global__ void head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
+                                  void* __restrict__ dx, long long P, int Cin, int C, float scale, int mask,
                                   float mask_scale) {
   const size_t total = static_cast<size_t>(P) * Cin;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -140,19 +157,17 @@ __global__ void head_bwd_x_kernel(const T* __restrict__ x, const float* __restri
     for (int c = 0; c < CMAX; ++c)
       if (c < C) a = fmaf(__ldg(dp + c), __ldg(kr + c), a);
     a *= scale;
-    if (mask) a = (ld_act(x + i) > 0.f) ? a * mask_scale : 0.f;
-    st_act(dx + i, a);
+    if (mask) a = (ld_px<FMT>(x, p, Cin, ci) > 0.f) ? a * mask_scale : 0.f;
+    st_px<FMT>(dx, p, Cin, ci, a);
   }
 }
 
 cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
                             float scale, int dtype, cudaStream_t st) {
   const int blocks = grid_for(static_cast<size_t>(P) * 32, 256);
-  if (dtype == 0)
-    { count_launch(); head_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, b, s, P, Cin, C,
-                                                           scale); }
-  else
-    { count_launch(); head_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, b, s, P, Cin, C, scale); }
+#define CALL(F) { count_launch(); head_fwd_kernel<F><<<blocks, 256, 0, st>>>(x, K, b, s, P, Cin, C, scale); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   return cudaGetLastError();
 }
 int head_bwd_blocks(long long P) {
@@ -169,11 +184,9 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   float* ws_k = ws;                                          // [nb][Cin][C]
   float* ws_b = ws + static_cast<size_t>(nb) * Cin * C;      // [nb][C]
   dim3 grid(nb, (Cin + 255) / 256);
-  if (dtype == 0)
-    { count_launch(); head_bwd_w_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ds, ws_k, P, Cin, C,
-                                                           ppb); }
-  else
-    { count_launch(); head_bwd_w_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), ds, ws_k, P, Cin, C, ppb); }
+#define CALL(F) { count_launch(); head_bwd_w_kernel<F><<<grid, 256, 0, st>>>(x, ds, ws_k, P, Cin, C, ppb); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   { count_launch(); rows_colsum_kernel<<<nb, 256, 0, st>>>(ds, ws_b, P, C, ppb); }
   cudaError_t e = launch_colsum(ws_k, dK, nb, Cin * C, scale, 0, st);
   if (e != cudaSuccess) return e;
@@ -181,13 +194,9 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   if (e != cudaSuccess) return e;
   if (dx) {
     const int blocks = grid_for(static_cast<size_t>(P) * Cin, 256);
-    if (dtype == 0)
-      { count_launch(); head_bwd_x_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), K, ds,
-                                                               static_cast<__nv_bfloat16*>(dx), P, Cin, C, scale, mask,
-                                                               mask_scale); }
-    else
-      { count_launch(); head_bwd_x_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), K, ds, static_cast<float*>(dx), P,
-                                                       Cin, C, scale, mask, mask_scale); }
+#define CALL(F) { count_launch(); head_bwd_x_kernel<F><<<blocks, 256, 0, st>>>(x, K, ds, dx, P, Cin, C, scale, mask, mask_scale); }
+    FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   }
   return cudaGetLastError();
 }

@@ -17,13 +17,86 @@ static inline int grid_for(size_t work, int threads, int max_blocks = 148 * 16) 
   return static_cast<int>(b);
 }
 
+// ------------------------------------------------------------------------------------------------ storage formats
+// Act<FMT>: 16-byte vector access to one pixel's channels in the three activation storage formats
+// (include/fcn8s_b200.h): N channels per vector, `ld(C)` elements between pixels, load -> fp32, store <- fp32.
+// FMT 2 (bf16 hi/lo pair, [.., 2C]): value = hi + lo exactly (fp32), stored as hi = bf16(v), lo = bf16(v - hi).
+template <int FMT>
+struct Act;
+template <>
+struct Act<0> {
+  using T = __nv_bfloat16;
+  static constexpr int N = 8;
+  static __device__ __forceinline__ int ld(int C) { return C; }
+  static __device__ __forceinline__ void load(const T* p, int, float (&f)[8]) {
+    uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 t = __bfloat1622float2(h[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ void store(T* p, int, const float (&f)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+template <>
+struct Act<1> {
+  using T = float;
+  static constexpr int N = 4;
+  static __device__ __forceinline__ int ld(int C) { return C; }
+  static __device__ __forceinline__ void load(const T* p, int, float (&f)[4]) {
+    float4 q = *reinterpret_cast<const float4*>(p);
+    f[0] = q.x;
+    f[1] = q.y;
+    f[2] = q.z;
+    f[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(T* p, int, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <>
+struct Act<2> {
+  using T = __nv_bfloat16;
+  static constexpr int N = 8;
+  static __device__ __forceinline__ int ld(int C) { return 2 * C; }
+  static __device__ __forceinline__ void load(const T* p, int C, float (&f)[8]) {
+    float l[8];
+    Act<0>::load(p, C, f);
+    Act<0>::load(p + C, C, l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += l[j];
+  }
+  static __device__ __forceinline__ void store(T* p, int C, const float (&f)[8]) {
+    float l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = f[j] - __bfloat162float(__float2bfloat16_rn(f[j]));
+    Act<0>::store(p, C, f);
+    Act<0>::store(p + C, C, l);
+  }
+};
+// launch helper: FN<FMT>(args...) for a runtime format
+#define FCN8_FMT_DISPATCH(fmt, CALL)      \
+  do {                                    \
+    if ((fmt) == 0) { CALL(0); }          \
+    else if ((fmt) == 1) { CALL(1); }     \
+    else { CALL(2); }                     \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------ preprocess
-// One thread per 16-byte output vector (8 bf16 / 4 fp32 im2col columns).
-template <typename T>
-__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, int N, int H, int W) {
-  constexpr int VEC = 16 / sizeof(T);
-  constexpr int KP = 128 / sizeof(T);  // padded im2col width: one 128-byte operand row
-  constexpr int VPP = KP / VEC;        // vectors per pixel (8)
+// One thread per 16-byte output vector (8 bf16 / 4 fp32 im2col columns).  KP = padded im2col width: one 128-byte
+// operand row (64 bf16 / 32 fp32 columns).
+template <int FMT>
+__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, typename Act<FMT>::T* __restrict__ out, int N,
+                                         int H, int W) {
+  using A = Act<FMT>;
+  constexpr int VEC = A::N;
+  constexpr int KP = FMT == 1 ? 32 : 64;
+  constexpr int VPP = KP / VEC;  // vectors per pixel (8)
   const size_t total = static_cast<size_t>(N) * H * W * VPP;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -48,72 +121,31 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, T* __r
       }
       f[e] = val;
     }
-    if constexpr (sizeof(T) == 2) {
-      uint4 q = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                           pack_bf16x2(f[6], f[7]));
-      reinterpret_cast<uint4*>(out)[i] = q;
-    } else {
-      reinterpret_cast<float4*>(out)[i] = make_float4(f[0], f[1], f[2], f[3]);
-    }
+    A::store(out + pix * A::ld(KP) + v * VEC, KP, f);
   }
 }
 
 cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * H * W * 8;
   const int blocks = grid_for(total, 256);
-  if (dtype == 0)
-    { count_launch(); preprocess_im2col_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(img, static_cast<__nv_bfloat16*>(out), N, H, W); }
-  else
-    { count_launch(); preprocess_im2col_kernel<float><<<blocks, 256, 0, st>>>(img, static_cast<float*>(out), N, H, W); }
+#define CALL(F) { count_launch(); preprocess_im2col_kernel<F><<<blocks, 256, 0, st>>>(img, static_cast<typename Act<F>::T*>(out), N, H, W); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------ vector helpers
-template <typename T>
-struct Vec16;
-template <>
-struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
-    uint4 q = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 t = __bfloat1622float2(h[j]);
-      f[2 * j] = t.x;
-      f[2 * j + 1] = t.y;
-    }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-  }
-};
-template <>
-struct Vec16<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
-    float4 q = *reinterpret_cast<const float4*>(p);
-    f[0] = q.x;
-    f[1] = q.y;
-    f[2] = q.z;
-    f[3] = q.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
-  }
-};
-
 // ------------------------------------------------------------------------------------------------ max pool
-template <typename T>
-__global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
-  using V = Vec16<T>;
-  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N;
+template <int FMT>
+__global__ void maxpool_fwd_kernel(const typename Act<FMT>::T* __restrict__ x, typename Act<FMT>::T* __restrict__ y,
+                                   int N, int H, int W, int C) {
+  using V = Act<FMT>;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % CV);
     size_t r = i / CV;
+    const size_t opix = r;
     const int xo = static_cast<int>(r % Wo);
     r /= Wo;
     const int yo = static_cast<int>(r % Ho);
@@ -128,32 +160,34 @@ __global__ void maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, i
         const int yy = 2 * yo + dy, xx = 2 * xo + dx;
         if (yy < H && xx < W) {
           float f[V::N];
-          V::load(x + ((static_cast<size_t>(n) * H + yy) * W + xx) * C + cv * V::N, f);
+          V::load(x + ((static_cast<size_t>(n) * H + yy) * W + xx) * LD + cv * V::N, C, f);
 #pragma unroll
           for (int e = 0; e < V::N; ++e) m[e] = fmaxf(m[e], f[e]);
         }
       }
-    V::store(y + i * V::N, m);
+    V::store(y + opix * LD + cv * V::N, C, m);
   }
 }
 
 // dx[window position] = dy if it is the first maximum of the window (scan order) and x > 0, else 0.
-template <typename T>
-__global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int N, int H,
-                                   int W, int C) {
-  using V = Vec16<T>;
-  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N;
+template <int FMT>
+__global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
+                                   const typename Act<FMT>::T* __restrict__ dy, typename Act<FMT>::T* __restrict__ dx,
+                                   int N, int H, int W, int C) {
+  using V = Act<FMT>;
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % CV);
     size_t r = i / CV;
+    const size_t opix = r;
     const int xo = static_cast<int>(r % Wo);
     r /= Wo;
     const int yo = static_cast<int>(r % Ho);
     const int n = static_cast<int>(r / Ho);
     float g[V::N];
-    V::load(dy + i * V::N, g);
+    V::load(dy + opix * LD + cv * V::N, C, g);
     float f[4][V::N];
     bool inb[4];
     size_t off[4];
@@ -161,9 +195,9 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
     for (int k = 0; k < 4; ++k) {
       const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
       inb[k] = (yy < H) && (xx < W);
-      off[k] = ((static_cast<size_t>(n) * H + yy) * W + xx) * C + cv * V::N;
+      off[k] = ((static_cast<size_t>(n) * H + yy) * W + xx) * LD + cv * V::N;
       if (inb[k]) {
-        V::load(x + off[k], f[k]);
+        V::load(x + off[k], C, f[k]);
       } else {
 #pragma unroll
         for (int e = 0; e < V::N; ++e) f[k][e] = -INFINITY;
@@ -185,48 +219,42 @@ __global__ void maxpool_bwd_kernel(const T* __restrict__ x, const T* __restrict_
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (inb[k]) V::store(dx + off[k], o[k]);
+      if (inb[k]) V::store(dx + off[k], C, o[k]);
   }
 }
 
+static inline int act_vec(int dtype) { return dtype == 1 ? 4 : 8; }
+
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st) {
-  const int vec = dtype == 0 ? 8 : 4;
-  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
+  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
   const int blocks = grid_for(total, 256);
-  if (dtype == 0)
-    { count_launch(); maxpool_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
-                                                              static_cast<__nv_bfloat16*>(y), N, H, W, C); }
-  else
-    { count_launch(); maxpool_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), N, H, W,
-                                                      C); }
+#define CALL(F) { count_launch(); maxpool_fwd_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<typename Act<F>::T*>(y), N, H, W, C); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
                                cudaStream_t st) {
-  const int vec = dtype == 0 ? 8 : 4;
-  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / vec);
+  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
   const int blocks = grid_for(total, 256);
-  if (dtype == 0)
-    { count_launch(); maxpool_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
-                                                              static_cast<const __nv_bfloat16*>(dy),
-                                                              static_cast<__nv_bfloat16*>(dx), N, H, W, C); }
-  else
-    { count_launch(); maxpool_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy),
-                                                      static_cast<float*>(dx), N, H, W, C); }
+#define CALL(F) { count_launch(); maxpool_bwd_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), N, H, W, C); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ bias gradient
 // Stage 1: block (bx, by) sums rows [bx*rpb, (bx+1)*rpb) of column-vector group by into ws[bx][C].
-template <typename T>
-__global__ void bias_grad_stage1(const T* __restrict__ dy, float* __restrict__ ws, long long P, int C, int cvb,
-                                 long long rpb) {
-  using V = Vec16<T>;
+template <int FMT>
+__global__ void bias_grad_stage1(const typename Act<FMT>::T* __restrict__ dy, float* __restrict__ ws, long long P,
+                                 int C, int cvb, long long rpb) {
+  using V = Act<FMT>;
   extern __shared__ float sred[];  // [RL][cvb*VN]
   const int RL = blockDim.x / cvb;
   const int cvl = threadIdx.x % cvb;
   const int rl = threadIdx.x / cvb;
   const int cv = blockIdx.y * cvb + cvl;
+  const int LD = V::ld(C);
   float acc[V::N];
 #pragma unroll
   for (int e = 0; e < V::N; ++e) acc[e] = 0.f;
@@ -235,7 +263,7 @@ __global__ void bias_grad_stage1(const T* __restrict__ dy, float* __restrict__ w
   if (rl < RL) {
     for (long long r = r0 + rl; r < r1; r += RL) {
       float f[V::N];
-      V::load(dy + static_cast<size_t>(r) * C + cv * V::N, f);
+      V::load(dy + static_cast<size_t>(r) * LD + cv * V::N, C, f);
 #pragma unroll
       for (int e = 0; e < V::N; ++e) acc[e] += f[e];
     }
@@ -251,14 +279,22 @@ __global__ void bias_grad_stage1(const T* __restrict__ dy, float* __restrict__ w
     for (int e = 0; e < V::N; ++e) ws[static_cast<size_t>(blockIdx.x) * C + cv * V::N + e] = acc[e];
   }
 }
+// out[c] = scale * sum_b ws[b][c]: one warp per column group so that the nb partial rows are read in parallel.
 __global__ void colsum_stage2(const float* __restrict__ ws, float* __restrict__ out, int nb, int C, float scale,
                               int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int part = threadIdx.x >> 5, nparts = blockDim.x >> 5;
+  __shared__ float red[8][33];
   float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += ws[static_cast<size_t>(b) * C + c];
-  s *= scale;
-  out[c] = accumulate ? out[c] + s : s;
+  if (c < C)
+    for (int b = part; b < nb; b += nparts) s += ws[static_cast<size_t>(b) * C + c];
+  red[part][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    for (int k = 1; k < nparts; ++k) s += red[k][threadIdx.x & 31];
+    s *= scale;
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 
 int bias_grad_blocks(long long P, int C) {
@@ -267,8 +303,12 @@ int bias_grad_blocks(long long P, int C) {
   if (nb < 1) nb = 1;
   return static_cast<int>(nb);
 }
+cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st) {
+  { count_launch(); colsum_stage2<<<(C + 31) / 32, 256, 0, st>>>(ws, out, nb, C, scale, accumulate); }
+  return cudaGetLastError();
+}
 cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st) {
-  const int vec = dtype == 0 ? 8 : 4;
+  const int vec = act_vec(dtype);
   const int CV = C / vec;
   const int cvb = CV < 256 ? CV : 256;
   const int nb = bias_grad_blocks(P, C);
@@ -276,16 +316,10 @@ cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int 
   dim3 grid(nb, CV / cvb);
   const int RL = 256 / cvb;
   const size_t sm = static_cast<size_t>(RL) * cvb * vec * sizeof(float);
-  if (dtype == 0)
-    { count_launch(); bias_grad_stage1<__nv_bfloat16><<<grid, 256, sm, st>>>(static_cast<const __nv_bfloat16*>(dy), ws, P, C, cvb, rpb); }
-  else
-    { count_launch(); bias_grad_stage1<float><<<grid, 256, sm, st>>>(static_cast<const float*>(dy), ws, P, C, cvb, rpb); }
-  { count_launch(); colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, db, nb, C, 1.f, 0); }
-  return cudaGetLastError();
-}
-cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st) {
-  { count_launch(); colsum_stage2<<<(C + 127) / 128, 128, 0, st>>>(ws, out, nb, C, scale, accumulate); }
-  return cudaGetLastError();
+#define CALL(F) { count_launch(); bias_grad_stage1<F><<<grid, 256, sm, st>>>(static_cast<const typename Act<F>::T*>(dy), ws, P, C, cvb, rpb); }
+  FCN8_FMT_DISPATCH(dtype, CALL);
+#undef CALL
+  return launch_colsum(ws, db, nb, C, 1.f, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
@@ -302,7 +336,9 @@ __device__ __forceinline__ float tf32_hi(float x) {
 template <typename T>
 __device__ __forceinline__ void store_packed(T* out, T* out_lo, size_t idx, float v) {
   if constexpr (sizeof(T) == 2) {
-    out[idx] = __float2bfloat16_rn(v);
+    const T h = __float2bfloat16_rn(v);
+    out[idx] = h;
+    if (out_lo) out_lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));  // bf16 hi/lo pair operand
   } else {
     if (out_lo) {
       // 3xTF32 operands: the MMA itself truncates `out` to its tf32 high part; lo = the exact remainder, rounded
@@ -354,7 +390,7 @@ cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int 
   if (mode == 0) {
     dim3 grid((Cout + 31) / 32, (CinPad + 31) / 32, taps), block(32, 8);
     if (dtype == 0)
-      { count_launch(); pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+      { count_launch(); pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
                                                                Cout, CinPad); }
     else
       { count_launch(); pack_fprop_kernel<float><<<grid, block, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
@@ -363,7 +399,7 @@ cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int 
     const size_t total = static_cast<size_t>(taps) * Cin * Cout;
     const int blocks = grid_for(total, 256);
     if (dtype == 0)
-      { count_launch(); pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), nullptr, taps, Cin,
+      { count_launch(); pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
                                                                Cout); }
     else
       { count_launch(); pack_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
@@ -397,10 +433,12 @@ cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cu
 
 // ------------------------------------------------------------------------------------------------ split-K reduce
 // conv: out = epilogue(sum_s partial[s][i]); same flag semantics as the in-kernel epilogue (epilogue_row32).
-template <typename T>
+// FMT 0 / 1: bf16 / fp32 output; FMT 2: bf16 with the low half also written to g.out_lo (hi/lo pair output).
+template <int FMT>
 __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n_elems, int ldc,
                                           ConvGemmArgs g) {
-  using V = Vec16<T>;
+  using V = Act<FMT == 2 ? 0 : FMT>;
+  using T = typename V::T;
   const size_t nv = n_elems / V::N;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -419,15 +457,21 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int
       }
     }
     const int c0 = static_cast<int>(idx % ldc);
+    const size_t oidx = (idx / ldc) * static_cast<size_t>(g.osW) + c0;  // pixel stride of the output tensors
     if (g.flags & EPI_BIAS) {
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[e] += g.bias[c0 + e];
     }
     if (g.flags & EPI_RESIDUAL) {
       float r[V::N];
-      V::load(reinterpret_cast<const T*>(g.residual) + idx, r);
+      V::load(reinterpret_cast<const T*>(g.residual) + oidx, 0, r);
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[e] += r[e];
+      if (FMT == 2 && g.residual_lo) {
+        V::load(reinterpret_cast<const T*>(g.residual_lo) + oidx, 0, r);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) f[e] += r[e];
+      }
     }
     if (g.flags & EPI_RELU) {
 #pragma unroll
@@ -440,27 +484,32 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int
     }
     if (g.flags & EPI_MASK) {
       float m[V::N];
-      V::load(reinterpret_cast<const T*>(g.mask_src) + idx, m);
+      V::load(reinterpret_cast<const T*>(g.mask_src) + oidx, 0, m);
 #pragma unroll
       for (int e = 0; e < V::N; ++e) f[e] = m[e] > 0.f ? f[e] * g.mask_scale : 0.f;
     }
-    if constexpr (sizeof(T) == 4) {
+    if constexpr (FMT == 1) {
       if (g.flags & EPI_ROUND_TF32) {
 #pragma unroll
         for (int e = 0; e < V::N; ++e) f[e] = round_tf32(f[e]);
       }
     }
-    V::store(reinterpret_cast<T*>(g.out) + idx, f);
+    V::store(reinterpret_cast<T*>(g.out) + oidx, 0, f);
+    if constexpr (FMT == 2) {
+      float l[V::N];
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) l[e] = f[e] - __bfloat162float(__float2bfloat16_rn(f[e]));
+      V::store(reinterpret_cast<T*>(g.out_lo) + oidx, 0, l);
+    }
   }
 }
 cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n_elems, int ldc,
                                       const ConvGemmArgs& g, int dtype, cudaStream_t st) {
-  const int vec = dtype == 0 ? 8 : 4;
-  const int blocks = grid_for(n_elems / vec, 256);
-  if (dtype == 0)
-    { count_launch(); conv_splitk_reduce_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
-  else
-    { count_launch(); conv_splitk_reduce_kernel<float><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
+  const int fmt = dtype == 1 ? 1 : (g.out_lo ? 2 : 0);
+  const int blocks = grid_for(n_elems / act_vec(dtype), 256);
+#define CALL(F) { count_launch(); conv_splitk_reduce_kernel<F><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
+  FCN8_FMT_DISPATCH(fmt, CALL);
+#undef CALL
   return cudaGetLastError();
 }
 
@@ -490,10 +539,21 @@ cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int spl
 }
 
 // ------------------------------------------------------------------------------------------------ Adam / L2
-// 28 B/param of HBM traffic (read p,g,m,v; write p,m,v): the floor for an fp32 Adam step.
+// 28 B/param of HBM traffic (read p,g,m,v; write p,m,v): the floor for an fp32 Adam step; + 2 (4) B/param when the
+// bf16 (hi/lo) tensor-core shadow of the parameters is refreshed in the same pass (w_hi / w_lo != nullptr), which
+// replaces every per-step weight re-packing kernel: the GEMMs read the shadow in TF layout directly.
+__device__ __forceinline__ void store_shadow4(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t i4, const float4& p) {
+  const uint32_t h0 = pack_bf16x2(p.x, p.y), h1 = pack_bf16x2(p.z, p.w);
+  reinterpret_cast<uint2*>(hi)[i4] = make_uint2(h0, h1);
+  if (lo) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h0));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h1));
+    reinterpret_cast<uint2*>(lo)[i4] = make_uint2(pack_bf16x2(p.x - a.x, p.y - a.y), pack_bf16x2(p.z - b.x, p.w - b.y));
+  }
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps,
-                            float gscale) {
+                            float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps, float gscale,
+                            __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
   const size_t n4 = n / 4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -513,6 +573,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    if (w_hi) store_shadow4(w_hi, w_lo, i, pp);
   }
   // tail (n not a multiple of 4)
   if (blockIdx.x == 0) {
@@ -521,12 +582,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
       m[i] = b1 * m[i] + (1.f - b1) * gr;
       v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
       p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+      if (w_hi) {
+        w_hi[i] = __float2bfloat16_rn(p[i]);
+        if (w_lo) w_lo[i] = __float2bfloat16_rn(p[i] - __bfloat162float(w_hi[i]));
+      }
     }
   }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
-                        float eps, float gscale, cudaStream_t st) {
-  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale); }
+                        float eps, float gscale, void* w_hi, void* w_lo, cudaStream_t st) {
+  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo)); }
+  return cudaGetLastError();
+}
+// w_hi = bf16(p), w_lo = bf16(p - w_hi): the tensor-core shadow of the fp32 parameters (after load_weights).
+__global__ void shadow_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                              size_t n) {
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    store_shadow4(hi, lo, i, reinterpret_cast<const float4*>(p)[i]);
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      hi[i] = __float2bfloat16_rn(p[i]);
+      if (lo) lo[i] = __float2bfloat16_rn(p[i] - __bfloat162float(hi[i]));
+    }
+}
+cudaError_t launch_shadow(const float* p, void* hi, void* lo, size_t n, cudaStream_t st) {
+  { count_launch(); shadow_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n); }
   return cudaGetLastError();
 }
 

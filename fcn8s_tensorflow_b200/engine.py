@@ -7,11 +7,7 @@ the stream; every arithmetic operation is a hand-written sm_100a kernel reached 
 (include/fcn8s_b200.h).  There is no CPU path: constructing an Engine without a CUDA device or without the built
 library raises.
 
-Precision modes (`precision=`):
-  "bf16"   activations + tensor-core operands bf16, fp32 accumulate (TMEM), fp32 master weights / grads / Adam.
-  "tf32"   activations fp32, operands read as tf32 (10-bit mantissa), fp32 accumulate.
-  "fp32"   activations fp32, error-compensated 3xTF32 products (hi*hi + hi*lo + lo*hi): fp32-faithful (~1e-6).
-The decoder (score heads, transposed convs, loss) is fp32 in every mode.
+Precision modes: see `Engine`.  The decoder (score heads, transposed convs, loss) is fp32 in every mode.
 """
 from collections import OrderedDict
 
@@ -89,11 +85,24 @@ def flat_layout(num_classes):
 
 
 class Engine:
+    """Precision modes (`precision=`), all with fp32 accumulation in TMEM, fp32 master weights / gradients / Adam:
+
+      "bf16"    activations + tensor-core operands bf16.
+      "fp32"    fp32-equivalent: activations and weights are bf16 hi/lo PAIRS (FCN8_BF16X2: v ~ hi + lo, 16-17
+                mantissa bits) and every GEMM forms the error-compensated hi*hi + hi*lo + lo*hi on the bf16 tensor
+                cores (3 MMAs per product at the bf16 rate = half the cost of 3xTF32).  Meets the 1e-4 logit tolerance.
+      "tf32x3"  fp32 activations, 3xTF32 error-compensated products (kind::tf32, 6x the bf16 cost).
+      "tf32"    fp32 activations, single tf32 pass.
+    In "bf16" / "fp32" the GEMMs read a bf16 (hi/lo) shadow of the flat parameter buffer in its TF layout directly
+    (refreshed by the Adam kernel), so there is no per-step weight packing."""
+
+    MODES = ("bf16", "fp32", "tf32x3", "tf32")
+
     def __init__(self, num_classes, precision="bf16", device=None):
         if not torch.cuda.is_available():
             raise capi.Fcn8Error("fcn8s_tensorflow_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        if precision not in ("bf16", "tf32", "fp32"):
-            raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")
+        if precision not in self.MODES:
+            raise ValueError("precision must be one of %s" % (self.MODES,))
         if not (1 <= num_classes <= 32):
             raise ValueError("num_classes must be in [1, 32]")
         self.lib = capi.load()
@@ -101,10 +110,14 @@ class Engine:
         capi.check(self.lib.fcn8_device_check(self.device.index or 0))
         self.C = num_classes
         self.precision = precision
-        self.dt = ops.BF16 if precision == "bf16" else ops.F32
-        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
-        self.x3 = precision == "fp32"
-        self.kp = 64 if self.dt == ops.BF16 else 32   # padded im2col width of conv1_1
+        self.pair = precision == "fp32"                      # bf16 hi/lo pair activations
+        self.hwio = precision in ("bf16", "fp32")            # GEMMs read the TF-layout weight shadow
+        self.x3 = precision == "tf32x3"                      # legacy 3xTF32 encoder products
+        self.dec3 = precision in ("fp32", "tf32x3")          # 3xTF32 in the (fp32) decoder GEMMs
+        self.dt = ops.BF16 if self.hwio else ops.F32         # tensor-core operand type of the encoder
+        self.tdt = torch.bfloat16 if self.hwio else torch.float32
+        self.cm = 2 if self.pair else 1                      # stored channels per logical channel
+        self.kp = 64 if self.hwio else 32                    # padded im2col width of conv1_1
         self.rnd = ops.EPI_ROUND_TF32 if precision == "tf32" else 0
         self.layers = encoder_layers()
         self.layout, self.n_flat = flat_layout(num_classes)
@@ -113,10 +126,13 @@ class Engine:
         self.grads = torch.zeros(self.n_flat, **z)
         self.adam_m = torch.zeros(self.n_flat, **z)
         self.adam_v = torch.zeros(self.n_flat, **z)
+        self.w_hi = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=self.device) if self.hwio else None
+        self.w_lo = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=self.device) if self.pair else None
         self.global_step = 0
         self.loss_buf = torch.zeros(2, **z)   # [0] = sum of per-pixel CE, [1] = L2 regularisation loss
         self.packed = {}
         self._packed_dirty = True
+        self._shadow_dirty = True
         self._arenas = {}
         self.world = 1
         self.allreduce = None  # callable(flat_grad) installed by the data-parallel wrapper
@@ -136,6 +152,7 @@ class Engine:
                 raise ValueError("shape mismatch for %s: %s vs %s" % (name, tuple(t.shape), self.layout[name][1]))
             self.view(name).copy_(t.to(self.device))
         self._packed_dirty = True
+        self._shadow_dirty = True
 
     def state_dict(self):
         return OrderedDict((n, self.view(n).detach().cpu().clone()) for n in self.layout)
@@ -144,18 +161,24 @@ class Engine:
         return OrderedDict((n, self.view(n, self.grads).detach().cpu().clone()) for n in self.layout)
 
     def repack(self):
-        """fp32 master weights (TF HWIO) -> tensor-core operand layouts (fprop + dgrad) of every encoder layer."""
+        """Derived tensor-core operands of the parameters.  hwio modes: only conv1_1 (27 -> 64 im2col columns) and the
+        upscore8 phase-GEMM operands are packed (the rest is the shadow written by Adam); legacy tf32 modes: fprop and
+        dgrad operand copies of every encoder layer."""
+        if self.hwio and self._shadow_dirty:
+            ops.shadow_weights(self.params, self.w_hi, self.w_lo)
+            self._shadow_dirty = False
         for name, k, cin, cout in self.layers:
             w = self.view(_wname(name))
             if name == "conv1_1":
                 # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
-                self.packed[name] = ops.pack_weights(w, 1, 27, cout, 0, self.dt, cin_pad=self.kp, split=self.x3) + (None, None)
-            else:
+                self.packed[name] = ops.pack_weights(w, 1, 27, cout, 0, self.dt, cin_pad=self.kp,
+                                                     split=self.x3 or self.pair) + (None, None)
+            elif not self.hwio:
                 f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3)
                 d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3)
                 self.packed[name] = f + d
         self.packed["up8"] = ops.upscore_tc_pack(self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
-                                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8, split=self.x3,
+                                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8, split=self.dec3,
                                                  out=self.packed.get("up8"))
         self._packed_dirty = False
 
@@ -178,25 +201,49 @@ class Engine:
             arena[name] = t
         return t
 
-    def _split(self, arena, name, x):
-        """3xTF32 operands of x: (x, lo) with lo = round_tf32(x - trunc_tf32(x)) in an arena buffer -- the tensor core
-        truncates x to its tf32 high part by itself; (x, None) in the single-pass modes."""
-        if not self.x3:
+    def _act(self, arena, name, N, h, w, c):
+        """Encoder activation buffer [N,h,w,c] in the mode's storage format ([N,h,w,2c] bf16 for hi/lo pairs)."""
+        return self._buf(arena, name, (N, h, w, c * self.cm), self.tdt)
+
+    def _split(self, arena, name, x, force=False):
+        """3xTF32 operands of an fp32 tensor x: (x, lo) with lo = round_tf32(x - trunc_tf32(x)) in an arena buffer --
+        the tensor core truncates x to its tf32 high part by itself; (x, None) when the mode is single-pass."""
+        if not (self.x3 or force):
             return x, None
         lo = self._buf(arena, name + ".lo", x.shape, torch.float32)
         capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), None, capi.ptr(lo), x.numel(), ops._stream()))
         return x, lo
 
+    def _wview(self, name):
+        """(hi, lo) bf16 shadow views of an encoder weight tensor in TF layout."""
+        return self.view(_wname(name), self.w_hi), (self.view(_wname(name), self.w_lo) if self.pair else None)
+
+    def _conv(self, A, name, x, k, cin, cout, out, bias, flags, **kw):
+        """Encoder convolution of layer `name` (forward direction) in the mode's operand format."""
+        if name == "conv1_1":
+            wp, wlo = self.packed[name][0], self.packed[name][1]
+            xl = self._split(A, "in_" + name, x)[1] if self.x3 else None
+            return ops.conv_gemm(x, wp, cout, 1, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo,
+                                 pair=self.pair, **kw)
+        if self.hwio:
+            wh, wl = self._wview(name)
+            return ops.conv_gemm(x, wh, cout, k, bias=bias, flags=flags, out=out, wp_lo=wl, pair=self.pair, w_mode=1,
+                                 **kw)
+        wp, wlo = self.packed[name][0], self.packed[name][1]
+        xl = self._split(A, "in_" + name, x)[1]
+        return ops.conv_gemm(x, wp, cout, k, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo, **kw)
+
     # ------------------------------------------------------------------ forward
     def forward(self, images, keep_prob=1.0, seed=0, train=False):
-        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (an arena buffer)."""
-        if self._packed_dirty:
+        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (a view of an arena buffer)."""
+        if self._packed_dirty or (self.hwio and self._shadow_dirty):
             self.repack()
         N, H, W, _ = images.shape
         A = self._arena(N, H, W)
         A["_shape"] = (N, H, W)
-        x = self._buf(A, "im2col", (N, H, W, self.kp), self.tdt)
-        p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, self.dt)
+        pair = self.pair
+        x = self._act(A, "im2col", N, H, W, self.kp)
+        p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, ops.BF16X2 if pair else self.dt)
         capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
         if self.precision == "tf32":   # single-pass tf32: operands pre-rounded (the MMA truncates)
             capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), capi.ptr(x), None, x.numel(), ops._stream()))
@@ -206,41 +253,35 @@ class Engine:
             for i in range(1, n + 1):
                 name, k, cin, _ = self.layers[li]
                 li += 1
-                wp, wlo = self.packed[name][0], self.packed[name][1]
-                out = self._buf(A, name, (N, h, w, cout), self.tdt)
-                xh, xl = self._split(A, "in_" + name, x)
-                bias = self.view(name + "/biases")
-                ops.conv_gemm(xh, wp, cout, 1 if name == "conv1_1" else 3, bias=bias,
-                              flags=ops.EPI_BIAS | ops.EPI_RELU | self.rnd, out=out, x_lo=xl, wp_lo=wlo)
+                out = self._act(A, name, N, h, w, cout)
+                self._conv(A, name, x, k, cin, cout, out, self.view(name + "/biases"), ops.EPI_BIAS | ops.EPI_RELU)
                 x = out
             h, w = (h + 1) // 2, (w + 1) // 2
-            pooled = self._buf(A, "pool%d" % b, (N, h, w, cout), self.tdt)
-            ops.maxpool_fwd(x, out=pooled)
+            pooled = self._act(A, "pool%d" % b, N, h, w, cout)
+            ops.maxpool_fwd(x, out=pooled, pair=pair)
             x = pooled
         drop = train and keep_prob < 1.0
         for name, k, cin, cout in self.layers[-2:]:
-            wp, wlo = self.packed[name][0], self.packed[name][1]
-            out = self._buf(A, name, (N, h, w, cout), self.tdt)
-            xh, xl = self._split(A, "in_" + name, x)
-            flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0) | self.rnd
-            ops.conv_gemm(xh, wp, cout, k, bias=self.view(name + "/biases"), flags=flags, out=out, x_lo=xl, wp_lo=wlo,
-                          keep_prob=keep_prob if drop else 1.0, seed=self.dropout_seed(seed, name))
+            out = self._act(A, name, N, h, w, cout)
+            flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0)
+            self._conv(A, name, x, k, cin, cout, out, self.view(name + "/biases"), flags,
+                       keep_prob=keep_prob if drop else 1.0, seed=self.dropout_seed(seed, name))
             x = out
         C = self.C
         f32 = torch.float32
         s3 = ops.score_head_fwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), self.view("pool3_1x1/bias"),
-                                POOL3_SCALE, out=self._buf(A, "s3", (N, H // 8, W // 8, C), f32))
+                                POOL3_SCALE, out=self._buf(A, "s3", (N, H // 8, W // 8, C), f32), pair=pair)
         s4 = ops.score_head_fwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), self.view("pool4_1x1/bias"),
-                                POOL4_SCALE, out=self._buf(A, "s4", (N, H // 16, W // 16, C), f32))
+                                POOL4_SCALE, out=self._buf(A, "s4", (N, H // 16, W // 16, C), f32), pair=pair)
         s7 = ops.score_head_fwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), self.view("fc7_1x1/bias"), 1.0,
-                                out=self._buf(A, "s7", (N, H // 32, W // 32, C), f32))
+                                out=self._buf(A, "s7", (N, H // 32, W // 32, C), f32), pair=pair)
         f4 = ops.upscore_fwd(s7, self.view("fc7_conv2d_trans/kernel"), self.view("fc7_conv2d_trans/bias"), 2, skip=s4,
                              out=self._buf(A, "f4", (N, H // 16, W // 16, C), f32))
         f3 = ops.upscore_fwd(f4, self.view("fc7_pool4_conv2d_trans/kernel"), self.view("fc7_pool4_conv2d_trans/bias"),
                              2, skip=s3, out=self._buf(A, "f3", (N, H // 8, W // 8, C), f32))
         # upscore8 on the tensor cores (phase GEMM): padded blocked logits [N, H+8, W+8, CP]; A["logits"] is the view
         f3p = self._pad4(A, "f3p", f3)
-        x_lo = self._split(A, "f3p", f3p)[1]
+        x_lo = self._split(A, "f3p", f3p, force=self.dec3)[1]
         zp = A.get("logits_p")
         if zp is None:
             zp = A["logits_p"] = ops.upscore_tc_alloc(N, H // 8, W // 8, C, 8, self.device)
@@ -270,7 +311,8 @@ class Engine:
         labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2)."""
         N, H, W, _ = images.shape
         C = self.C
-        logits = self.forward(images, keep_prob, seed, train=True)
+        pair = self.pair
+        self.forward(images, keep_prob, seed, train=True)
         A = self._arena(N, H, W)
         G = self.grads
         f32 = torch.float32
@@ -285,7 +327,7 @@ class Engine:
         ops.softmax_xent(zp, labels.view(torch.uint8), self.loss_buf[0:1], dzp, grad_scale=1.0 / npx, dbias=dc8,
                          pad=4, num_classes=C)
         # decoder backward; upscore8 on the tensor cores
-        dz_lo = self._split(A, "dlogits_p", dzp)[1]
+        dz_lo = self._split(A, "dlogits_p", dzp, force=self.dec3)[1]
         f3p = A["f3p"] if C % 4 else A["f3"]
         f3_lo = A.get("f3p.lo")
         ops.upscore_tc_dw(f3p, dzp, C, 8, self.view("fc7_pool4_pool3_conv2d_trans/kernel", G), x_lo=f3_lo,
@@ -307,15 +349,17 @@ class Engine:
         # score heads: ds3 = df3, ds4 = df4 (the adds fan the gradient out unchanged)
         dpool3 = self._buf(A, "d_pool3_head", A["pool3"].shape, self.tdt)
         ops.score_head_bwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), df3, POOL3_SCALE,
-                           self.view("pool3_1x1/kernel", G).view(256, C), self.view("pool3_1x1/bias", G), dpool3)
+                           self.view("pool3_1x1/kernel", G).view(256, C), self.view("pool3_1x1/bias", G), dpool3,
+                           pair=pair)
         dpool4 = self._buf(A, "d_pool4_head", A["pool4"].shape, self.tdt)
         ops.score_head_bwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), df4, POOL4_SCALE,
-                           self.view("pool4_1x1/kernel", G).view(512, C), self.view("pool4_1x1/bias", G), dpool4)
+                           self.view("pool4_1x1/kernel", G).view(512, C), self.view("pool4_1x1/bias", G), dpool4,
+                           pair=pair)
         # fc7 output: dropout + ReLU backward folded into the head's dx (mask = fc7 > 0, scale 1/keep_prob)
         dy = self._buf(A, "d_fc7", A["fc7"].shape, self.tdt)
         ops.score_head_bwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), ds7, 1.0,
                            self.view("fc7_1x1/kernel", G).view(4096, C), self.view("fc7_1x1/bias", G), dy,
-                           mask=True, mask_scale=inv_keep)
+                           mask=True, mask_scale=inv_keep, pair=pair)
         if l2_rate != 0.0:
             for kname in DECODER_KERNELS:
                 ops.l2_reg(self.view(kname).reshape(-1), self.view(kname, G).reshape(-1), self.loss_buf[1:2], l2_rate)
@@ -324,34 +368,37 @@ class Engine:
             name, k, cin, cout = self.layers[li]
             x_in = self._layer_input(A, li)
             gw = self.view(_wname(name), G)
-            ops.bias_grad(dy, self.view(name + "/biases", G))
+            ops.bias_grad(dy, self.view(name + "/biases", G), pair=pair)
             dyh, dyl = self._split(A, "dy_" + name, dy)
+            xl = A["in_%s.lo" % name] if self.x3 else None
             if name == "conv1_1":
-                xh, xl = (x_in, A["in_conv1_1.lo"]) if self.x3 else (x_in, None)
-                ops.wgrad_gemm(xh, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl)
+                ops.wgrad_gemm(x_in, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl, pair=pair)
                 break
-            xh, xl = (x_in, A["in_%s.lo" % name]) if self.x3 else (x_in, None)
-            ops.wgrad_gemm(xh, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl)
-            wpd, wpd_lo = self.packed[name][2], self.packed[name][3]
+            ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair)
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
+            if self.hwio:
+                wh, wl = self._wview(name)
+                wkw = dict(wp_lo=wl, pair=pair, w_mode=2)
+            else:
+                wh = self.packed[name][2]
+                wkw = dict(x_lo=dyl, wp_lo=self.packed[name][3])
             if self._input_is_pool(li):
                 # x_in is a pool output: no ReLU mask here (the pool backward applies it); add the score-head
                 # gradient at pool3 / pool4 (AddN of the two consumers)
                 pool_idx = self._pool_index(li)
                 res = dpool3 if pool_idx == 3 else (dpool4 if pool_idx == 4 else None)
-                ops.conv_gemm(dyh, wpd, cin, k, flags=(ops.EPI_RESIDUAL if res is not None else 0) | self.rnd,
-                              residual=res, out=dx,
-                              x_lo=dyl, wp_lo=wpd_lo)
+                ops.conv_gemm(dyh, wh, cin, k, flags=(ops.EPI_RESIDUAL if res is not None else 0) | self.rnd,
+                              residual=res, out=dx, **wkw)
                 src = A[prev_name]  # pre-pool activation (post-ReLU)
                 dpre = self._buf(A, "dpre_" + prev_name, src.shape, self.tdt)
-                ops.maxpool_bwd(src, dx, out=dpre)
+                ops.maxpool_bwd(src, dx, out=dpre, pair=pair)
                 dy = dpre
             else:
                 # ReLU (and for fc6 -> dropout) backward of the producer fused as an epilogue mask on its output
                 scale = inv_keep if prev_name == "fc6" else 1.0
-                ops.conv_gemm(dyh, wpd, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
-                              x_lo=dyl, wp_lo=wpd_lo)
+                ops.conv_gemm(dyh, wh, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
+                              **wkw)
                 dy = dx
         return self.loss_buf
 
@@ -378,7 +425,8 @@ class Engine:
             self.allreduce(self.grads)
         t = self.global_step + 1
         lr_t = float(lr) * float(np.sqrt(1.0 - BETA2 ** t) / (1.0 - BETA1 ** t))
-        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world)
+        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world,
+                 w_hi=self.w_hi, w_lo=self.w_lo)
         self.global_step = t
         self._packed_dirty = True
 

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _capi as capi
-from ._capi import BF16, F32, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32  # noqa: F401
+from ._capi import BF16, F32, BF16X2, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32  # noqa: F401
 
 _workspaces = {}
 
@@ -51,7 +51,20 @@ TIMER = None
 
 
 def torch_dtype(dtype):
-    return torch.bfloat16 if dtype == BF16 else torch.float32
+    return torch.float32 if dtype == F32 else torch.bfloat16
+
+
+def to_pair(x):
+    """fp32 [..., C] -> bf16 hi/lo pair [..., 2C] (FCN8_BF16X2): hi = bf16(x), lo = bf16(x - hi). Test helper."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def from_pair(xp):
+    """bf16 hi/lo pair [..., 2C] -> fp32 [..., C]."""
+    Cc = xp.shape[-1] // 2
+    return xp[..., :Cc].float() + xp[..., Cc:].float()
 
 
 def dtype_of(t):
@@ -91,7 +104,7 @@ def preprocess_im2col(images, dtype):
     if images.dtype != torch.uint8 or images.dim() != 4 or images.shape[3] != 3:
         raise ValueError("images must be uint8 [N,H,W,3]")
     N, H, W, _ = images.shape
-    kp = 64 if dtype == BF16 else 32
+    kp = {BF16: 64, F32: 32, BF16X2: 128}[dtype]   # BF16X2: 64 hi + 64 lo columns
     out = torch.empty((N, H, W, kp), dtype=torch_dtype(dtype), device=images.device)
     p = capi.PreprocessParams(capi.ptr(images), capi.ptr(out), N, H, W, dtype)
     capi.check(capi.load().fcn8_preprocess_im2col(C.byref(p), _stream()))
@@ -122,17 +135,30 @@ def split_tf32(x):
 
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
-              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0):
-    """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h)."""
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0):
+    """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
+    pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
+    the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF
+    weight tensor itself (fprop / dgrad), no packing."""
     _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo)
     N, H, W, cin = x.shape
-    dtype = dtype_of(x)
-    if out is None:
-        out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
-    nseg = 3 if x_lo is not None else 1
-    p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
-                        capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
-                        mask_scale, keep_prob, seed, force_splits, force_bn)
+    if pair:
+        cin //= 2
+        dtype = BF16
+        if out is None:
+            out = torch.empty((N, H, W, 2 * cout), dtype=torch.bfloat16, device=x.device)
+        p = capi.ConvParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
+                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, 3, flags,
+                            mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
+                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode)
+    else:
+        dtype = dtype_of(x)
+        if out is None:
+            out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
+        nseg = 3 if x_lo is not None else 1
+        p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
+                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
+                            mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode)
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
@@ -143,14 +169,21 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
     return out
 
 
-def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0):
-    """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows)."""
+def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0, pair=False):
+    """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows).
+    pair=True: x / dy are bf16 hi/lo pair tensors [N,H,W,2C]; error-compensated product."""
     _chk_cuda(x, dy, out, x_lo, dy_lo)
     N, H, W, cin = x.shape
     cout = dy.shape[3]
-    nseg = 3 if x_lo is not None else 1
-    p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin,
-                         cout, ksize, rows_valid, dtype_of(x), nseg, force_splits, force_bn)
+    if pair:
+        cin //= 2
+        cout //= 2
+        p = capi.WgradParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(dy), capi.ptr(dy, cout), capi.ptr(out), N, H, W,
+                             cin, cout, ksize, rows_valid, BF16, 3, force_splits, force_bn, 2 * cin, 2 * cout)
+    else:
+        nseg = 3 if x_lo is not None else 1
+        p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin,
+                             cout, ksize, rows_valid, dtype_of(x), nseg, force_splits, force_bn, 0, 0)
     lib = capi.load()
     nbytes = lib.fcn8_wgrad_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
@@ -161,32 +194,36 @@ def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_spl
     return out
 
 
-def maxpool_fwd(x, out=None):
+def _fmt(t, pair):
+    return BF16X2 if pair else dtype_of(t)
+
+
+def maxpool_fwd(x, out=None, pair=False):
     _chk_cuda(x, out)
     N, H, W, Cc = x.shape
     if out is None:
         out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, Cc), dtype=x.dtype, device=x.device)
-    p = capi.PoolParams(capi.ptr(x), capi.ptr(out), None, N, H, W, Cc, dtype_of(x))
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(out), None, N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair))
     capi.check(capi.load().fcn8_maxpool_fwd(C.byref(p), _stream()))
     return out
 
 
-def maxpool_bwd(x, dy, out=None):
+def maxpool_bwd(x, dy, out=None, pair=False):
     """Gradient w.r.t. the pre-ReLU producer of x: routes dy to the first arg-max where x > 0."""
     _chk_cuda(x, dy, out)
     N, H, W, Cc = x.shape
     if out is None:
         out = torch.empty_like(x)
-    p = capi.PoolParams(capi.ptr(x), capi.ptr(dy), capi.ptr(out), N, H, W, Cc, dtype_of(x))
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(dy), capi.ptr(out), N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair))
     capi.check(capi.load().fcn8_maxpool_bwd(C.byref(p), _stream()))
     return out
 
 
-def bias_grad(dy, out):
+def bias_grad(dy, out, pair=False):
     _chk_cuda(dy, out)
     Cc = dy.shape[-1]
     P = dy.numel() // Cc
-    p = capi.BiasGradParams(capi.ptr(dy), capi.ptr(out), P, Cc, dtype_of(dy))
+    p = capi.BiasGradParams(capi.ptr(dy), capi.ptr(out), P, Cc // 2 if pair else Cc, _fmt(dy, pair))
     lib = capi.load()
     nbytes = lib.fcn8_bias_grad_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, dy.device)
@@ -194,26 +231,30 @@ def bias_grad(dy, out):
     return out
 
 
-def score_head_fwd(x, K, b, scale, out=None):
+def score_head_fwd(x, K, b, scale, out=None, pair=False):
     _chk_cuda(x, K, b, out)
     cin = x.shape[-1]
     Cc = K.shape[-1]
     P = x.numel() // cin
+    if pair:
+        cin //= 2
     if out is None:
         out = torch.empty(tuple(x.shape[:-1]) + (Cc,), dtype=torch.float32, device=x.device)
     p = capi.HeadParams(capi.ptr(x), capi.ptr(K), capi.ptr(b), capi.ptr(out), None, None, None, P, cin, Cc, scale,
-                        dtype_of(x), 0, 1.0)
+                        _fmt(x, pair), 0, 1.0)
     capi.check(capi.load().fcn8_score_head_fwd(C.byref(p), _stream()))
     return out
 
 
-def score_head_bwd(x, K, ds, scale, dK, db, dx=None, mask=False, mask_scale=1.0):
+def score_head_bwd(x, K, ds, scale, dK, db, dx=None, mask=False, mask_scale=1.0, pair=False):
     _chk_cuda(x, K, ds, dK, db, dx)
     cin = x.shape[-1]
     Cc = K.shape[-1]
     P = x.numel() // cin
+    if pair:
+        cin //= 2
     p = capi.HeadParams(capi.ptr(x), capi.ptr(K), None, capi.ptr(ds), capi.ptr(dK), capi.ptr(db), capi.ptr(dx), P, cin,
-                        Cc, scale, dtype_of(x), 1 if mask else 0, mask_scale)
+                        Cc, scale, _fmt(x, pair), 1 if mask else 0, mask_scale)
     lib = capi.load()
     nbytes = lib.fcn8_score_head_bwd_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device)
@@ -353,10 +394,17 @@ def confusion_matrix(pred, labels_onehot, conf):
                                                  pred.numel(), Cc, _stream()))
 
 
-def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-    _chk_cuda(p, g, m, v)
+def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w_hi=None, w_lo=None):
+    """TF-form Adam over a flat buffer; w_hi / w_lo (bf16, same length): tensor-core shadow refreshed in the pass."""
+    _chk_cuda(p, g, m, v, w_hi, w_lo)
     capi.check(capi.load().fcn8_adam(capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), p.numel(), lr_t, beta1,
-                                     beta2, eps, grad_scale, _stream()))
+                                     beta2, eps, grad_scale, capi.ptr(w_hi), capi.ptr(w_lo), _stream()))
+
+
+def shadow_weights(p, w_hi, w_lo=None):
+    """w_hi = bf16(p), w_lo = bf16(p - w_hi)."""
+    _chk_cuda(p, w_hi, w_lo)
+    capi.check(capi.load().fcn8_shadow_weights(capi.ptr(p), capi.ptr(w_hi), capi.ptr(w_lo), p.numel(), _stream()))
 
 
 def l2_reg(w, g, loss_sum, rate):

@@ -38,7 +38,10 @@ enum {
   FCN8_ERR_UNSUPPORTED = -5
 };
 
-enum { FCN8_BF16 = 0, FCN8_F32 = 1 };
+/* activation storage formats.  FCN8_BF16X2 ("fp32-equivalent"): a tensor [N,H,W,2C] of bf16 whose first C channels
+ * of every pixel are hi = bf16(v) and the next C channels lo = bf16(v - hi); v' = hi + lo carries 16-17 mantissa
+ * bits and the GEMMs form hi*hi + hi*lo + lo*hi on the bf16 tensor cores (nseg = 3). */
+enum { FCN8_BF16 = 0, FCN8_F32 = 1, FCN8_BF16X2 = 2 };
 
 /* epilogue flags of fcn8_conv_gemm (bit-or) */
 enum {
@@ -92,6 +95,15 @@ typedef struct {
   uint32_t seed;
   int32_t force_splits; /* 0 = heuristic */
   int32_t force_bn;     /* 0 = heuristic, else 64/128/256 */
+  /* --- optional (zero = the defaults above) --- */
+  int32_t x_ld;         /* pixel stride of x / x_lo in elements (0 = Cin; 2*Cin for a FCN8_BF16X2 tensor) */
+  int32_t out_ld;       /* pixel stride of out / out_lo / mask_src / residual (0 = Cout) */
+  void* out_lo;         /* FCN8_BF16 only: also store lo = bf16(v - bf16(v)) (hi/lo pair output) */
+  const void* residual_lo;
+  /* w_mode 0: wp is the packed operand of fcn8_pack_weights.  FCN8_BF16 only: w_mode 1 (fprop) / 2 (dgrad): wp (and
+   * wp_lo) is a bf16 copy of the weight tensor in its TF layout [k,k,Cin_w,Cout_w] read in place -- fprop: Cin_w = Cin,
+   * Cout_w = Cout; dgrad: Cin_w = Cout, Cout_w = Cin (rotation and transposition happen in the TMA coordinates). */
+  int32_t w_mode;
 } Fcn8ConvParams;
 size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -111,6 +123,8 @@ typedef struct {
   int32_t dtype, nseg;
   int32_t force_splits;
   int32_t force_bn;
+  int32_t x_ld;  /* pixel strides in elements, 0 = Cin / Cout */
+  int32_t dy_ld;
 } Fcn8WgradParams;
 size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p);
 int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -271,7 +285,11 @@ int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot,
  * g' = g*grad_scale;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;  p -= lr_t * m / (sqrt(v) + eps),
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* stream);
+                  float eps, float grad_scale, void* w_hi, void* w_lo, void* stream);
+/* w_hi / w_lo (optional, bf16 [n]): the tensor-core shadow of the parameters, w_hi = bf16(p), w_lo = bf16(p - w_hi),
+ * refreshed by fcn8_adam in the same pass; the GEMMs read it in TF layout (Fcn8ConvParams.w_mode 1 / 2), so no
+ * per-step re-packing exists.  fcn8_shadow_weights builds it after a weight load. */
+int32_t fcn8_shadow_weights(const float* p, void* w_hi, void* w_lo, size_t n, void* stream);
 /* L2 regulariser of the six decoder kernels (:179..232, :250-251): g += rate*w;  loss_sum += 0.5*rate*sum w^2. */
 int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float rate, void* stream);
 

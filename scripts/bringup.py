@@ -484,6 +484,161 @@ def upscore_tc_stride2():
     return ok
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 / bf16 hi-lo pair modes that read the TF-layout (HWIO) weight shadow in place (no packing)
+def _shadow(w, pair):
+    from fcn8s_tensorflow_b200 import ops
+    hi = torch.empty(w.numel(), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if pair else None
+    ops.shadow_weights(w.reshape(-1), hi, lo)
+    return hi.view(w.shape), (lo.view(w.shape) if pair else None)
+
+
+def hwio_conv_case(N, H, W, cin, cout, k, pair, tol, force_bn=0, force_splits=0):
+    """fprop (w_mode 1) with bias+ReLU, and dgrad (w_mode 2), against fp64 references on the operands' exact values."""
+    from fcn8s_tensorflow_b200 import ops
+    torch.manual_seed(21)
+    dev = torch.device("cuda")
+    w = torch.randn(k, k, cin, cout, device=dev) / (k * k * cin) ** 0.5
+    b = torch.randn(cout, device=dev)
+    wh, wl = _shadow(w, pair)
+    wq = (wh.double() + wl.double()) if pair else wh.double()
+    x32 = torch.randn(N, H, W, cin, device=dev)
+    x = ops.to_pair(x32) if pair else x32.to(torch.bfloat16)
+    xq = ops.from_pair(x).double() if pair else x.double()
+    y = ops.conv_gemm(x, wh, cout, k, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1,
+                      force_bn=force_bn, force_splits=force_splits)
+    torch.cuda.synchronize()
+    ref = ref_conv(xq, wq, b, relu=True)
+    got = ops.from_pair(y) if pair else y
+    tag = "N%d %dx%d Cin%d Cout%d k%d pair%d bn%d sp%d" % (N, H, W, cin, cout, k, pair, force_bn, force_splits)
+    ok = report("hwio fprop " + tag, got, ref, tol)
+    # dgrad: dy has cout channels, result cin channels
+    dy32 = torch.randn(N, H, W, cout, device=dev)
+    dy = ops.to_pair(dy32) if pair else dy32.to(torch.bfloat16)
+    dyq = ops.from_pair(dy).double() if pair else dy.double()
+    dx = ops.conv_gemm(dy, wh, cin, k, wp_lo=wl, pair=pair, w_mode=2, force_bn=force_bn if cin % max(force_bn, 1) == 0 else 0,
+                       force_splits=force_splits)
+    torch.cuda.synchronize()
+    refd = F.conv_transpose2d(dyq.permute(0, 3, 1, 2), wq.permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
+    ok &= report("hwio dgrad " + tag, ops.from_pair(dx) if pair else dx, refd, tol)
+    return ok
+
+
+@case
+def hwio_bf16():
+    ok = hwio_conv_case(1, 8, 16, 64, 64, 1, False, 1e-2)
+    ok &= hwio_conv_case(1, 8, 16, 64, 64, 3, False, 1e-2)
+    ok &= hwio_conv_case(2, 16, 32, 128, 256, 3, False, 1e-2)
+    ok &= hwio_conv_case(2, 16, 32, 64, 512, 3, False, 1e-2, force_bn=256)
+    ok &= hwio_conv_case(2, 16, 32, 256, 128, 3, False, 1e-2, force_bn=128)
+    ok &= hwio_conv_case(1, 4, 8, 512, 256, 7, False, 1e-2)              # split-K path
+    ok &= hwio_conv_case(3, 20, 36, 64, 128, 3, False, 1e-2)             # ragged tiles
+    return ok
+
+
+@case
+def hwio_pair():
+    # hi/lo pair operands: products carry ~2^-17 relative error per element, reductions average it down
+    ok = hwio_conv_case(1, 8, 16, 64, 64, 1, True, 2e-5)
+    ok &= hwio_conv_case(2, 16, 32, 128, 256, 3, True, 2e-5)
+    ok &= hwio_conv_case(2, 16, 32, 64, 512, 3, True, 2e-5, force_bn=256)
+    ok &= hwio_conv_case(1, 4, 8, 512, 256, 7, True, 2e-5)               # split-K path with pair epilogue
+    ok &= hwio_conv_case(3, 20, 36, 64, 128, 3, True, 2e-5)
+    return ok
+
+
+@case
+def pair_epilogues_and_wgrad():
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(22)
+    ok = True
+    N, H, W, cin, cout, k = 2, 16, 32, 128, 128, 3
+    w = torch.randn(k, k, cin, cout, device=dev) / (k * k * cin) ** 0.5
+    wh, wl = _shadow(w, True)
+    wq = wh.double() + wl.double()
+    x = ops.to_pair(torch.randn(N, H, W, cin, device=dev))
+    xq = ops.from_pair(x).double()
+    msrc = ops.to_pair(torch.randn(N, H, W, cout, device=dev).clamp_min(0))
+    res = ops.to_pair(torch.randn(N, H, W, cout, device=dev))
+    base = ref_conv(xq, wq)
+    y = ops.conv_gemm(x, wh, cout, k, flags=ops.EPI_MASK, mask_src=msrc, mask_scale=2.0, wp_lo=wl, pair=True, w_mode=1)
+    ok &= report("pair mask epilogue", ops.from_pair(y), base * (ops.from_pair(msrc).double() > 0) * 2.0, 2e-5)
+    y = ops.conv_gemm(x, wh, cout, k, flags=ops.EPI_RESIDUAL, residual=res, wp_lo=wl, pair=True, w_mode=1)
+    ok &= report("pair residual epilogue", ops.from_pair(y), base + ops.from_pair(res).double(), 2e-5)
+    # wgrad on pairs
+    for (n_, h_, w_, ci, co, kk, rv) in ((2, 16, 32, 128, 256, 3, 0), (3, 20, 36, 64, 64, 3, 0), (2, 16, 16, 64, 64, 1, 27)):
+        xx = ops.to_pair(torch.randn(n_, h_, w_, ci, device=dev))
+        dy = ops.to_pair(torch.randn(n_, h_, w_, co, device=dev))
+        rows = kk * kk * ci
+        rvv = rv if rv else rows
+        dw = torch.full((rvv, co), float("nan"), device=dev)
+        ops.wgrad_gemm(xx, dy, kk, dw, rows_valid=rv, pair=True)
+        xpd = F.pad(ops.from_pair(xx).double().permute(0, 3, 1, 2), (kk // 2,) * 4)
+        cols = F.unfold(xpd, kk).view(n_, ci, kk * kk, h_ * w_)
+        ref = torch.einsum("nctp,npo->tco", cols, ops.from_pair(dy).double().reshape(n_, h_ * w_, co)).reshape(rows, co)[:rvv]
+        ok &= report("pair wgrad Cin%d Cout%d k%d" % (ci, co, kk), dw, ref, 2e-5)
+    return ok
+
+
+@case
+def pair_elementwise():
+    """Feed, pooling, bias-gradient, score heads and the Adam shadow in the bf16 hi/lo pair format."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(23)
+    ok = True
+    img = torch.randint(0, 256, (2, 10, 14, 3), dtype=torch.uint8, device=dev)
+    mean = torch.tensor([103.939, 116.779, 123.68], device=dev, dtype=torch.float64)
+    bgr = img.double().flip(-1) - mean
+    xp = F.pad(bgr.permute(0, 3, 1, 2), (1, 1, 1, 1))
+    cols = F.unfold(xp, 3).view(2, 3, 9, 10, 14).permute(0, 3, 4, 2, 1).reshape(2, 10, 14, 27)
+    out = ops.preprocess_im2col(img, ops.BF16X2)
+    ok &= report("preprocess pair", ops.from_pair(out)[..., :27], cols, 2e-5)
+    ok &= bool((ops.from_pair(out)[..., 27:] == 0).all().item())
+    x = ops.to_pair(torch.randn(2, 9, 13, 64, device=dev).clamp_min(0))
+    y = ops.maxpool_fwd(x, pair=True)
+    xr = ops.from_pair(x).double().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2, ceil_mode=True)
+    ok &= report("maxpool fwd pair", ops.from_pair(y), yr.permute(0, 2, 3, 1), 0.0)
+    dy = ops.to_pair(torch.randn(2, 5, 7, 64, device=dev))
+    dx = ops.maxpool_bwd(x, dy, pair=True)
+    yr.backward(ops.from_pair(dy).double().permute(0, 3, 1, 2))
+    ok &= report("maxpool bwd pair", ops.from_pair(dx), xr.grad.permute(0, 2, 3, 1) * (ops.from_pair(x).double() > 0), 0.0)
+    for Cc in (64, 4096):
+        g = ops.to_pair(torch.randn(1000, Cc, device=dev))
+        db = torch.empty(Cc, device=dev)
+        ops.bias_grad(g, db, pair=True)
+        ok &= report("bias_grad pair C%d" % Cc, db, ops.from_pair(g).double().sum(0), 1e-5)
+    Cc = 20
+    xh = ops.to_pair(torch.randn(2, 6, 10, 256, device=dev).clamp_min(0))
+    xq = ops.from_pair(xh).double()
+    K = torch.randn(256, Cc, device=dev) * 0.05
+    b = torch.randn(Cc, device=dev)
+    s = ops.score_head_fwd(xh, K, b, 0.01, pair=True)
+    ok &= report("head fwd pair", s.reshape(-1, Cc), 0.01 * (xq.reshape(-1, 256) @ K.double()) + b.double(), 1e-5)
+    ds = torch.randn_like(s)
+    dK, dbb, dxp = torch.empty_like(K), torch.empty_like(b), torch.empty_like(xh)
+    ops.score_head_bwd(xh, K, ds, 0.01, dK, dbb, dxp, mask=True, mask_scale=2.0, pair=True)
+    ok &= report("head bwd dK pair", dK, 0.01 * xq.reshape(-1, 256).t() @ ds.double().reshape(-1, Cc), 1e-5)
+    refdx = 0.01 * (ds.double().reshape(-1, Cc) @ K.double().t()).reshape(xq.shape) * (xq > 0) * 2.0
+    ok &= report("head bwd dx pair", ops.from_pair(dxp), refdx, 2e-5)
+    # Adam refreshes the shadow
+    n = 100003
+    p = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    hi = torch.empty(n, dtype=torch.bfloat16, device=dev)
+    lo = torch.empty_like(hi)
+    ops.adam(p, g, m, v, 1e-3, w_hi=hi, w_lo=lo)
+    ok &= bool((hi == p.to(torch.bfloat16)).all().item())
+    ok &= bool((lo == (p - hi.float()).to(torch.bfloat16)).all().item())
+    ok &= report("shadow hi+lo ~ p", hi.float() + lo.float(), p, 2e-5)
+    return ok
+
+
 def main():
     args = sys.argv[1:]
     if not args or args[0] == "list":
