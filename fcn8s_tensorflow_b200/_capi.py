@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfcn8s_sm100.so")
 
 BF16, F32, BF16X2 = 0, 1, 2
-EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32 = 1, 2, 4, 8, 16, 64
+EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32, EPI_COLSUM = 1, 2, 4, 8, 16, 64, 128
 
 EXPORTS = [
     "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_preprocess_im2col",
@@ -40,7 +40,7 @@ class ConvParams(C.Structure):
                 ("ksize", C.c_int32), ("dtype", C.c_int32), ("nseg", C.c_int32), ("flags", C.c_int32),
                 ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
                 ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32),
-                ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32)]
+                ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32), ("colsum", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -59,7 +59,7 @@ class PackParams(C.Structure):
 
 class PoolParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("y", C.c_void_p), ("dx", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32),
-                ("W", C.c_int32), ("C", C.c_int32), ("dtype", C.c_int32)]
+                ("W", C.c_int32), ("C", C.c_int32), ("dtype", C.c_int32), ("db", C.c_void_p)]
 
 
 class BiasGradParams(C.Structure):

@@ -182,7 +182,9 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   pl->tiles_n = p->Cout / bn;
   const long long tiles = (long long)pl->m_tiles * pl->tiles_n;
   int splits = 1;
-  if (p->force_splits > 0) {
+  if (p->flags & FCN8_EPI_COLSUM) {
+    splits = 1;  // the fused column sums live in the GEMM kernel's epilogue, not in the split-K reduce
+  } else if (p->force_splits > 0) {
     splits = p->force_splits;
   } else if (tiles * 2 <= sms) {
     splits = (int)(sms / tiles);
@@ -357,6 +359,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if ((p->flags & FCN8_EPI_MASK) && !p->mask_src) return fail(FCN8_ERR_BAD_SHAPE, "conv: MASK flag without mask_src");
   if ((p->flags & FCN8_EPI_RESIDUAL) && !p->residual)
     return fail(FCN8_ERR_BAD_SHAPE, "conv: RESIDUAL flag without residual");
+  if ((p->flags & FCN8_EPI_COLSUM) && (!p->colsum || p->Cout > kColsumMax))
+    return fail(FCN8_ERR_BAD_SHAPE, "conv: COLSUM flag needs colsum and Cout <= %d", kColsumMax);
   if (p->nseg == 3 && (!p->x_lo || !p->wp_lo)) return fail(FCN8_ERR_BAD_SHAPE, "conv: nseg=3 needs x_lo and wp_lo");
   ConvPlan pl;
   int rc = plan_conv(p, &pl);
@@ -408,7 +412,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.tiles_n = pl.tiles_n;
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
-  a.flags = p->flags & (31 | 64);
+  a.flags = p->flags & (31 | 64 | 128);
+  a.colsum = p->colsum;
   const int out_ld = p->out_ld > 0 ? p->out_ld : p->Cout;
   a.osW = out_ld;
   a.osH = (long long)p->W * out_ld;
@@ -569,7 +574,7 @@ int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream) {
   int rc = check_pool(p);
   if (rc) return rc;
   if (!p->dx || !aligned16(p->dx)) return fail(FCN8_ERR_BAD_SHAPE, "pool bwd: dx missing / unaligned");
-  cudaError_t e = launch_maxpool_bwd(p->x, p->y, p->dx, p->N, p->H, p->W, p->C, p->dtype, (cudaStream_t)stream);
+  cudaError_t e = launch_maxpool_bwd(p->x, p->y, p->dx, p->db, p->N, p->H, p->W, p->C, p->dtype, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "maxpool_bwd launch");
 }
 

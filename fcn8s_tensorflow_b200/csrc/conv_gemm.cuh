@@ -30,7 +30,10 @@ enum EpilogueFlags : int {
   EPI_RESIDUAL = 16, // + residual[index]                      (gradient fan-in at pool3 / pool4)
   EPI_PARTIAL = 32,  // raw fp32 partial sums to the split-K workspace, no epilogue math
   EPI_ROUND_TF32 = 64,  // fp32 outputs rounded to the nearest tf32 (single-pass tf32 mode: the MMA truncates operands)
+  EPI_COLSUM = 128,     // colsum[col] += sum over rows of the final values (the bias gradient of the layer whose dY
+                        // this dgrad produces): per-CTA shared-memory accumulation, one global atomic per column
 };
+constexpr int kColsumMax = 4096;  // widest dgrad output (fc6 activations)
 
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t u;
@@ -93,6 +96,7 @@ struct ConvGemmArgs {
   // to out_lo at the same element index; residual_lo is the low half of the residual.
   void* out_lo;
   const void* residual_lo;
+  float* colsum;  // EPI_COLSUM target [tiles_n * BN] fp32, accumulated with atomics (caller zeroes)
 };
 
 struct TensorMaps3 {
@@ -108,7 +112,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 for manual alignment
+  static constexpr int kColsumBytes = kColsumMax * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kColsumBytes + 1024;  // +1024: manual alignment
 };
 
 constexpr int kGemmThreads = 192;
@@ -128,15 +133,36 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Epilogue math on 32 consecutive columns of one output row. `idx` = element index of column c0 of this row.
+// Sum of f[j] over the 32 lanes of the warp, delivered to lane j (transpose-reduce: 31 shuffles).
+__device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = up ? f[j] : f[j + s];
+      const float keep = up ? f[j + s] : f[j];
+      f[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return f[0];
+}
+
 template <bool TF32>
 __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
-                                               int ncols, size_t dense_idx) {
+                                               int ncols, size_t dense_idx, bool valid, float* colsum_s, int lane) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-  if (g.flags & EPI_PARTIAL) {
-    // handled by caller
+  if (!valid) {  // rows outside the tensor take part only in the (warp-collective) column sums, as zeros
+    if (g.flags & EPI_COLSUM) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = 0.f;
+      const float cs = warp_colsum32(f, lane);
+      atomicAdd(&colsum_s[c0 + lane], cs);
+    }
+    return;
   }
   if (g.flags & EPI_BIAS) {
     const float4* b4 = reinterpret_cast<const float4*>(g.bias + c0);
@@ -227,6 +253,13 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     }
   }
   OutT* o = reinterpret_cast<OutT*>(g.out) + idx;
+  if (g.flags & EPI_COLSUM) {
+    float t[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = f[i];
+    const float cs = warp_colsum32(t, lane);
+    atomicAdd(&colsum_s[c0 + lane], cs);
+  }
   if constexpr (TF32) {
     if (g.flags & EPI_ROUND_TF32) {
 #pragma unroll
@@ -271,9 +304,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   uint64_t* acc_full = empty_bar + Cfg::kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* colsum_s = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (g.flags & EPI_COLSUM)
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
 
   const int m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
   const int total_tiles = m_tiles * g.tiles_n * g.splits;
@@ -437,24 +473,24 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        if (valid) {
-          const int c0 = nb * BN + c;
-          if (g.flags & EPI_PARTIAL) {
+        const int c0 = nb * BN + c;
+        if (g.flags & EPI_PARTIAL) {
+          if (valid) {
             const size_t idx = pix * g.ldc + c0;
             float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          } else {
-            size_t idx = row_off + c0;
-            if (g.out_mode) {
-              const int bdy = c0 / g.blk_row;
-              idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
-            }
-            const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
-            if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0);
           }
+        } else {
+          size_t idx = row_off + c0;
+          if (g.out_mode) {
+            const int bdy = c0 / g.blk_row;
+            idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
+          }
+          const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
+          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane);
         }
       }
       tc_fence_before();
@@ -473,6 +509,11 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL))
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {
+      const float t = colsum_s[c];
+      if (t != 0.f) atomicAdd(g.colsum + c, t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

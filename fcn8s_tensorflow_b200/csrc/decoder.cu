@@ -53,44 +53,56 @@ __device__ __forceinline__ void st_px(void* x, long long p, int C, int c, float 
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ score heads
-// One warp per pixel: lanes stride over Cin, each keeps C partial sums, then a butterfly reduction.
+// 1x1 convolutions Cin -> C <= 32 classes (fcn8s_tensorflow.py:171-200) and their gradients.  0.84 GFLOP per c2 step:
+// HBM-bound on the activation tensors, so these are CUDA-core kernels whose job is to touch x / dx exactly once,
+// coalesced, with K and ds staged in shared memory.
+constexpr int kHeadTP = 32;    // pixels per CTA tile
+constexpr int kHeadKC = 128;   // input channels per shared-memory chunk (fwd)
+
+// fwd: CTA = 128 threads = 32 pixels x 4 class groups (classes q, q+4, ...).
 template <int FMT>
-__global__ void head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
-                                float* __restrict__ s, long long P, int Cin, int C, float scale) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long p = warp0; p < P; p += nwarps) {
-    float acc[CMAX];
+__global__ void __launch_bounds__(128)
+head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
+                float* __restrict__ s, long long P, int Cin, int C, float scale) {
+  __shared__ float xs[kHeadTP][kHeadKC + 1];
+  __shared__ float Ks[kHeadKC][CMAX];
+  const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
+  const int pl = threadIdx.x >> 2, q = threadIdx.x & 3;
+  float acc[CMAX / 4];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-    for (int ci = lane; ci < Cin; ci += 32) {
-      const float xv = ld_px<FMT>(x, p, Cin, ci);
-      const float* kr = K + static_cast<size_t>(ci) * C;
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) acc[c] = fmaf(xv, __ldg(kr + c), acc[c]);
+  for (int j = 0; j < CMAX / 4; ++j) acc[j] = 0.f;
+  for (int k0 = 0; k0 < Cin; k0 += kHeadKC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHeadTP * kHeadKC; i += 128) {
+      const int r = i / kHeadKC, c = i % kHeadKC;
+      xs[r][c] = (p0 + r < P && k0 + c < Cin) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
     }
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      if (c < C) {
-        float v = acc[c];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        acc[c] = v;
-      }
+    for (int i = threadIdx.x; i < kHeadKC * C; i += 128) {
+      const int r = i / C, c = i % C;
+      Ks[r][c] = (k0 + r < Cin) ? __ldg(K + static_cast<size_t>(k0 + r) * C + c) : 0.f;
     }
-    if (lane == 0) {
+    __syncthreads();
+#pragma unroll 4
+    for (int ci = 0; ci < kHeadKC; ++ci) {
+      const float xv = xs[pl][ci];
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) s[p * C + c] = scale * acc[c] + b[c];
+      for (int j = 0; j < CMAX / 4; ++j)
+        if (q + 4 * j < C) acc[j] = fmaf(xv, Ks[ci][q + 4 * j], acc[j]);
     }
+  }
+  if (p0 + pl < P) {
+#pragma unroll
+    for (int j = 0; j < CMAX / 4; ++j)
+      if (q + 4 * j < C) s[(p0 + pl) * C + q + 4 * j] = scale * acc[j] + b[q + 4 * j];
   }
 }
 
-// dK / db partials: block (bx, by) covers pixels [bx*ppb, ...) and input channels [by*blockDim, ...).
+// dK / db partials: CTA (bx, by) covers pixels [bx*ppb, ...) and input channels [by*256, ...); thread = one input
+// channel holding C accumulators; ds rows are broadcast from shared memory, x is read coalesced, 4 pixels in flight.
 template <int FMT>
-__global__ void head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws,
-                                  long long P, int Cin, int C, long long ppb) {
+__global__ void __launch_bounds__(256)
+head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws, long long P,
+                  int Cin, int C, long long ppb) {
   __shared__ float sds[64][CMAX];
   const int ci = blockIdx.y * blockDim.x + threadIdx.x;
   const long long p0 = blockIdx.x * ppb;
@@ -101,14 +113,18 @@ __global__ void head_bwd_w_kernel(const void* __restrict__ x, const float* __res
   for (long long pc = p0; pc < p1; pc += 64) {
     const int np = static_cast<int>((p1 - pc < 64) ? (p1 - pc) : 64);
     __syncthreads();
-    for (int i = threadIdx.x; i < np * C; i += blockDim.x) sds[i / C][i % C] = ds[pc * C + i];
+    for (int i = threadIdx.x; i < 64 * C; i += blockDim.x) sds[i / C][i % C] = (i < np * C) ? ds[pc * C + i] : 0.f;
     __syncthreads();
     if (ci < Cin) {
-      for (int q = 0; q < np; ++q) {
-        const float xv = ld_px<FMT>(x, pc + q, Cin, ci);
+      for (int q = 0; q < np; q += 4) {
+        float xv[4];
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) acc[c] = fmaf(xv, sds[q][c], acc[c]);
+        for (int u = 0; u < 4; ++u) xv[u] = (q + u < np) ? ld_px<FMT>(x, pc + q + u, Cin, ci) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) acc[c] = fmaf(xv[u], sds[q + u][c], acc[c]);
       }
     }
   }
@@ -140,39 +156,44 @@ __global__ void rows_colsum_kernel(const float* __restrict__ ds, float* __restri
     ws[static_cast<size_t>(blockIdx.x) * C + threadIdx.x] = t;
   }
 }
-// dx[p][ci] = scale * sum_c ds[p][c] * K[ci][c]  (* relu/dropout mask of x)
+// dx[p][ci] = scale * sum_c ds[p][c] * K[ci][c]  (* relu/dropout mask of x).  CTA (bx, by) = 32 pixels x 256 input
+// channels; thread = one input channel with its K row in registers, ds rows broadcast from shared memory; every
+// x / dx access is a coalesced row of 256 channels.
 template <int FMT>
-__global__ void head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
-                                  void* __restrict__ dx, long long P, int Cin, int C, float scale, int mask,
-                                  float mask_scale) {
-  const size_t total = static_cast<size_t>(P) * Cin;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const long long p = i / Cin;
-    const int ci = static_cast<int>(i - p * Cin);
-    const float* kr = K + static_cast<size_t>(ci) * C;
-    const float* dp = ds + p * C;
+__global__ void __launch_bounds__(256)
+head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
+                  void* __restrict__ dx, long long P, int Cin, int C, float scale, int mask, float mask_scale) {
+  __shared__ float sds[kHeadTP][CMAX];
+  const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
+  const int np = static_cast<int>((P - p0 < kHeadTP) ? (P - p0) : kHeadTP);
+  const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < np * C; i += blockDim.x) sds[i / C][i % C] = ds[p0 * C + i];
+  float kr[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) kr[c] = (c < C && ci < Cin) ? __ldg(K + static_cast<size_t>(ci) * C + c) * scale : 0.f;
+  __syncthreads();
+  if (ci >= Cin) return;
+  for (int q = 0; q < np; ++q) {
     float a = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c)
-      if (c < C) a = fmaf(__ldg(dp + c), __ldg(kr + c), a);
-    a *= scale;
-    if (mask) a = (ld_px<FMT>(x, p, Cin, ci) > 0.f) ? a * mask_scale : 0.f;
-    st_px<FMT>(dx, p, Cin, ci, a);
+      if (c < C) a = fmaf(sds[q][c], kr[c], a);
+    if (mask) a = (ld_px<FMT>(x, p0 + q, Cin, ci) > 0.f) ? a * mask_scale : 0.f;
+    st_px<FMT>(dx, p0 + q, Cin, ci, a);
   }
 }
 
 cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
                             float scale, int dtype, cudaStream_t st) {
-  const int blocks = grid_for(static_cast<size_t>(P) * 32, 256);
-#define CALL(F) { count_launch(); head_fwd_kernel<F><<<blocks, 256, 0, st>>>(x, K, b, s, P, Cin, C, scale); }
+  const int blocks = static_cast<int>((P + kHeadTP - 1) / kHeadTP);
+#define CALL(F) { count_launch(); head_fwd_kernel<F><<<blocks, 128, 0, st>>>(x, K, b, s, P, Cin, C, scale); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();
 }
 int head_bwd_blocks(long long P) {
-  long long nb = (P + 127) / 128;
-  if (nb > 128) nb = 128;
+  long long nb = (P + 63) / 64;
+  if (nb > 512) nb = 512;
   if (nb < 1) nb = 1;
   return static_cast<int>(nb);
 }
@@ -193,8 +214,8 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   e = launch_colsum(ws_b, db, nb, C, 1.f, 0, st);
   if (e != cudaSuccess) return e;
   if (dx) {
-    const int blocks = grid_for(static_cast<size_t>(P) * Cin, 256);
-#define CALL(F) { count_launch(); head_bwd_x_kernel<F><<<blocks, 256, 0, st>>>(x, K, ds, dx, P, Cin, C, scale, mask, mask_scale); }
+    dim3 gx(static_cast<unsigned>((P + kHeadTP - 1) / kHeadTP), (Cin + 255) / 256);
+#define CALL(F) { count_launch(); head_bwd_x_kernel<F><<<gx, 256, 0, st>>>(x, K, ds, dx, P, Cin, C, scale, mask, mask_scale); }
     FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   }

@@ -169,14 +169,23 @@ __global__ void maxpool_fwd_kernel(const typename Act<FMT>::T* __restrict__ x, t
   }
 }
 
+template <int NV>
+__device__ __forceinline__ float bm_pos(const float (&f)[4][NV], int e) {
+  return fmaxf(fmaxf(f[0][e], f[1][e]), fmaxf(f[2][e], f[3][e]));
+}
 // dx[window position] = dy if it is the first maximum of the window (scan order) and x > 0, else 0.
 template <int FMT>
 __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
                                    const typename Act<FMT>::T* __restrict__ dy, typename Act<FMT>::T* __restrict__ dx,
-                                   int N, int H, int W, int C) {
+                                   float* __restrict__ db, int N, int H, int W, int C) {
   using V = Act<FMT>;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
+  // bias gradient of the producing conv: the grid stride is a multiple of CV, so a thread always works on the same
+  // channel vector and can keep its column sums in registers
+  float bsum[V::N];
+#pragma unroll
+  for (int e = 0; e < V::N; ++e) bsum[e] = 0.f;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int cv = static_cast<int>(i % CV);
@@ -220,6 +229,19 @@ __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (inb[k]) V::store(dx + off[k], C, o[k]);
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) bsum[e] += (bm_pos(f, e) > 0.f) ? g[e] : 0.f;
+  }
+  if (db) {
+    extern __shared__ float sdb[];  // [C]
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sdb[c] = 0.f;
+    __syncthreads();
+    const int cv = static_cast<int>((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) % CV);
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) atomicAdd(&sdb[cv * V::N + e], bsum[e]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      if (sdb[c] != 0.f) atomicAdd(db + c, sdb[c]);
   }
 }
 
@@ -233,11 +255,12 @@ cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int 
 #undef CALL
   return cudaGetLastError();
 }
-cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
-                               cudaStream_t st) {
+cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* db, int N, int H, int W, int C,
+                               int dtype, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
-  const int blocks = grid_for(total, 256);
-#define CALL(F) { count_launch(); maxpool_bwd_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), N, H, W, C); }
+  const int blocks = grid_for(total, 256);   // 256 % CV == 0 for every VGG width, so the grid stride keeps cv fixed
+  const size_t sm = db ? static_cast<size_t>(C) * sizeof(float) : 0;
+#define CALL(F) { count_launch(); maxpool_bwd_kernel<F><<<blocks, 256, sm, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), db, N, H, W, C); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();

@@ -16,8 +16,8 @@ inline void count_launch() { ++g_launch_count; }
 // elementwise.cu
 cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st);
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
-cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, int dtype,
-                               cudaStream_t st);
+cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* db, int N, int H, int W, int C,
+                               int dtype, cudaStream_t st);
 int bias_grad_blocks(long long P, int C);
 cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st);
 cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st);

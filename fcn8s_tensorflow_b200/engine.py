@@ -64,16 +64,20 @@ def variable_shapes(num_classes):
 
 
 def flat_layout(num_classes):
-    """Flat-buffer layout in backward-completion order (decoder | fc7 | fc6 | conv5_3 ... conv1_1) so that a gradient
-    all-reduce can start on the big fc6/fc7 blocks while the conv backward still runs.  Every tensor starts on a
-    256-byte boundary.  Returns (OrderedDict name -> (offset_elems, shape), total_elems)."""
+    """Flat-buffer layout in backward-completion order (decoder | fc7 W | fc6 W | conv5_3 W ... conv1_1 W | encoder
+    biases fc7 ... conv1_1) so that a gradient all-reduce can start on the big fc6/fc7 blocks while the conv backward
+    still runs.  The encoder biases form one contiguous block at the end: their gradients are accumulated with atomics
+    by the fused dgrad / max-pool-backward epilogues, so the block is zeroed with one fill per step.  Every tensor
+    starts on a 256-byte boundary.  Returns (OrderedDict name -> (offset_elems, shape), total_elems)."""
     shapes = variable_shapes(num_classes)
     order = []
     for base in ["fc7_pool4_pool3_conv2d_trans", "pool3_1x1", "fc7_pool4_conv2d_trans", "pool4_1x1",
                  "fc7_conv2d_trans", "fc7_1x1"]:
         order += [base + "/kernel", base + "/bias"]
     for name, _, _, _ in reversed(encoder_layers()):
-        order += [_wname(name), name + "/biases"]
+        order.append(_wname(name))
+    for name, _, _, _ in reversed(encoder_layers()):
+        order.append(name + "/biases")
     assert set(order) == set(shapes)
     layout = OrderedDict()
     off = 0
@@ -121,6 +125,7 @@ class Engine:
         self.rnd = ops.EPI_ROUND_TF32 if precision == "tf32" else 0
         self.layers = encoder_layers()
         self.layout, self.n_flat = flat_layout(num_classes)
+        self.bias_block = self.layout["fc7/biases"][0]       # encoder biases: [bias_block, n_flat)
         z = dict(dtype=torch.float32, device=self.device)
         self.params = torch.zeros(self.n_flat, **z)
         self.grads = torch.zeros(self.n_flat, **z)
@@ -317,6 +322,7 @@ class Engine:
         G = self.grads
         f32 = torch.float32
         self.loss_buf.zero_()
+        G[self.bias_block:].zero_()   # encoder bias gradients are accumulated by fused epilogues (atomics)
         zp = A["logits_p"]
         dzp = A.get("dlogits_p")
         if dzp is None:   # zero border, never written again
@@ -368,7 +374,8 @@ class Engine:
             name, k, cin, cout = self.layers[li]
             x_in = self._layer_input(A, li)
             gw = self.view(_wname(name), G)
-            ops.bias_grad(dy, self.view(name + "/biases", G), pair=pair)
+            if name == "fc7":   # every other bias gradient is fused into the kernel that produces that layer's dY
+                ops.bias_grad(dy, self.view(name + "/biases", G), pair=pair)
             dyh, dyl = self._split(A, "dy_" + name, dy)
             xl = A["in_%s.lo" % name] if self.x3 else None
             if name == "conv1_1":
@@ -377,6 +384,7 @@ class Engine:
             ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair)
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
+            prev_db = self.view(prev_name + "/biases", G)
             if self.hwio:
                 wh, wl = self._wview(name)
                 wkw = dict(wp_lo=wl, pair=pair, w_mode=2)
@@ -392,13 +400,13 @@ class Engine:
                               residual=res, out=dx, **wkw)
                 src = A[prev_name]  # pre-pool activation (post-ReLU)
                 dpre = self._buf(A, "dpre_" + prev_name, src.shape, self.tdt)
-                ops.maxpool_bwd(src, dx, out=dpre, pair=pair)
+                ops.maxpool_bwd(src, dx, out=dpre, pair=pair, db=prev_db)
                 dy = dpre
             else:
                 # ReLU (and for fc6 -> dropout) backward of the producer fused as an epilogue mask on its output
                 scale = inv_keep if prev_name == "fc6" else 1.0
                 ops.conv_gemm(dyh, wh, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
-                              **wkw)
+                              colsum=prev_db, **wkw)
                 dy = dx
         return self.loss_buf
 

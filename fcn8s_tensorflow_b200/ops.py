@@ -8,7 +8,8 @@ import ctypes as C
 import torch
 
 from . import _capi as capi
-from ._capi import BF16, F32, BF16X2, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32  # noqa: F401
+from ._capi import (BF16, F32, BF16X2, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL,  # noqa: F401
+                    EPI_ROUND_TF32, EPI_COLSUM)
 
 _workspaces = {}
 
@@ -135,12 +136,14 @@ def split_tf32(x):
 
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
-              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0):
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None):
     """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
     pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
     the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF
     weight tensor itself (fprop / dgrad), no packing."""
-    _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo)
+    _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo, colsum)
+    if colsum is not None:
+        flags |= EPI_COLSUM
     N, H, W, cin = x.shape
     if pair:
         cin //= 2
@@ -150,7 +153,7 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, 3, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
-                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode)
+                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum))
     else:
         dtype = dtype_of(x)
         if out is None:
@@ -158,7 +161,8 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         nseg = 3 if x_lo is not None else 1
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
-                            mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode)
+                            mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode,
+                            capi.ptr(colsum))
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
@@ -203,18 +207,20 @@ def maxpool_fwd(x, out=None, pair=False):
     N, H, W, Cc = x.shape
     if out is None:
         out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, Cc), dtype=x.dtype, device=x.device)
-    p = capi.PoolParams(capi.ptr(x), capi.ptr(out), None, N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair))
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(out), None, N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair), None)
     capi.check(capi.load().fcn8_maxpool_fwd(C.byref(p), _stream()))
     return out
 
 
-def maxpool_bwd(x, dy, out=None, pair=False):
-    """Gradient w.r.t. the pre-ReLU producer of x: routes dy to the first arg-max where x > 0."""
-    _chk_cuda(x, dy, out)
+def maxpool_bwd(x, dy, out=None, pair=False, db=None):
+    """Gradient w.r.t. the pre-ReLU producer of x: routes dy to the first arg-max where x > 0.
+    db (fp32 [C], accumulated): bias gradient of that producer (sum of the result over pixels)."""
+    _chk_cuda(x, dy, out, db)
     N, H, W, Cc = x.shape
     if out is None:
         out = torch.empty_like(x)
-    p = capi.PoolParams(capi.ptr(x), capi.ptr(dy), capi.ptr(out), N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair))
+    p = capi.PoolParams(capi.ptr(x), capi.ptr(dy), capi.ptr(out), N, H, W, Cc // 2 if pair else Cc, _fmt(x, pair),
+                        capi.ptr(db))
     capi.check(capi.load().fcn8_maxpool_bwd(C.byref(p), _stream()))
     return out
 

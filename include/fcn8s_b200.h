@@ -50,7 +50,9 @@ enum {
   FCN8_EPI_DROPOUT = 4,
   FCN8_EPI_MASK = 8,
   FCN8_EPI_RESIDUAL = 16,
-  FCN8_EPI_ROUND_TF32 = 64 /* FCN8_F32 only: round outputs to the nearest tf32 (the MMA truncates its operands) */
+  FCN8_EPI_ROUND_TF32 = 64, /* FCN8_F32 only: round outputs to the nearest tf32 (the MMA truncates its operands) */
+  FCN8_EPI_COLSUM = 128     /* colsum[co] += sum over pixels of the stored values: the BiasAddGrad of the layer whose
+                               dY this dgrad call produces, fused into its epilogue (fp32 atomics, caller zeroes) */
 };
 
 int32_t fcn8_version(void);
@@ -104,6 +106,7 @@ typedef struct {
    * wp_lo) is a bf16 copy of the weight tensor in its TF layout [k,k,Cin_w,Cout_w] read in place -- fprop: Cin_w = Cin,
    * Cout_w = Cout; dgrad: Cin_w = Cout, Cout_w = Cin (rotation and transposition happen in the TMA coordinates). */
   int32_t w_mode;
+  float* colsum;        /* FCN8_EPI_COLSUM target, [Cout] fp32 */
 } Fcn8ConvParams;
 size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -157,6 +160,7 @@ typedef struct {
   void* dx;       /* bwd only */
   int32_t N, H, W, C;
   int32_t dtype;
+  float* db;      /* bwd only, optional: db[c] += sum over pixels of dx (bias gradient of the producing conv) */
 } Fcn8PoolParams;
 int32_t fcn8_maxpool_fwd(const Fcn8PoolParams* p, void* stream);
 int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream);
