@@ -21,6 +21,7 @@ EXPORTS = [
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
     "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
+    "fcn8_set_step_scalars",
 ]
 
 
@@ -40,7 +41,8 @@ class ConvParams(C.Structure):
                 ("ksize", C.c_int32), ("dtype", C.c_int32), ("nseg", C.c_int32), ("flags", C.c_int32),
                 ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
                 ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32),
-                ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32), ("colsum", C.c_void_p)]
+                ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32), ("colsum", C.c_void_p),
+                ("seed_ptr", C.c_void_p)]
 
 
 class WgradParams(C.Structure):
@@ -134,7 +136,8 @@ def load():
     lib.fcn8_upscore_tc_cp.restype = C.c_int32
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
-    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+    lib.fcn8_set_step_scalars.argtypes = [vp, C.c_float, C.c_uint32, vp]
     lib.fcn8_shadow_weights.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_l2_reg.argtypes = [vp, vp, vp, sz, C.c_float, vp]
     _lib = lib

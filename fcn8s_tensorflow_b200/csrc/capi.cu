@@ -414,6 +414,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.kb_per_split = pl.kb_per_split;
   a.flags = p->flags & (31 | 64 | 128);
   a.colsum = p->colsum;
+  a.seed_ptr = p->seed_ptr;
   const int out_ld = p->out_ld > 0 ? p->out_ld : p->Cout;
   a.osW = out_ld;
   a.osH = (long long)p->W * out_ld;
@@ -667,14 +668,20 @@ int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot,
   return e == cudaSuccess ? 0 : cuda_fail(e, "confusion launch");
 }
 
+int32_t fcn8_set_step_scalars(float* scalars, float lr_t, uint32_t seed, void* stream) {
+  if (!scalars) return fail(FCN8_ERR_BAD_SHAPE, "set_step_scalars: null pointer");
+  cudaError_t e = launch_set_step_scalars(scalars, lr_t, seed, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "set_step_scalars launch");
+}
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* w_hi, void* w_lo, void* stream) {
+                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, void* stream) {
   if (!p || !g || !m || !v) return fail(FCN8_ERR_BAD_SHAPE, "adam: null pointer");
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (w_hi && !aligned16(w_hi)) ||
       (w_lo && !aligned16(w_lo)))
     return fail(FCN8_ERR_BAD_ALIGN, "adam: pointers must be 16-byte aligned");
   if (w_lo && !w_hi) return fail(FCN8_ERR_BAD_SHAPE, "adam: w_lo without w_hi");
-  cudaError_t e = launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, w_hi, w_lo, (cudaStream_t)stream);
+  cudaError_t e =
+      launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, w_hi, w_lo, lr_ptr, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam launch");
 }
 int32_t fcn8_shadow_weights(const float* p, void* w_hi, void* w_lo, size_t n, void* stream) {

@@ -97,6 +97,9 @@ struct ConvGemmArgs {
   void* out_lo;
   const void* residual_lo;
   float* colsum;  // EPI_COLSUM target [tiles_n * BN] fp32, accumulated with atomics (caller zeroes)
+  // Per-step dropout seed in device memory (CUDA-graph replays cannot change kernel arguments):
+  // effective seed = *seed_ptr * 2 + seed when seed_ptr != nullptr.
+  const uint32_t* seed_ptr;
 };
 
 struct TensorMaps3 {
@@ -150,7 +153,8 @@ __device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
 
 template <bool TF32>
 __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
-                                               int ncols, size_t dense_idx, bool valid, float* colsum_s, int lane) {
+                                               int ncols, size_t dense_idx, bool valid, float* colsum_s, int lane,
+                                               uint32_t seed) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
@@ -223,7 +227,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
   if (g.flags & EPI_DROPOUT) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      f[i] = dropout_keep(g.seed, static_cast<uint64_t>(dense_idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
+      f[i] = dropout_keep(seed, static_cast<uint64_t>(dense_idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
   }
   if (g.flags & EPI_MASK) {
     const OutT* m = reinterpret_cast<const OutT*>(g.mask_src) + idx;
@@ -451,6 +455,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     int as = 0;
     uint32_t aphase = 0;
     const size_t out_elems = static_cast<size_t>(g.N) * g.H * g.W * g.ldc;
+    const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int nb = t % g.tiles_n;
       const int mt = (t / g.tiles_n) % m_tiles;
@@ -490,7 +495,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
             idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
           }
           const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
-          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane);
+          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane, seed);
         }
       }
       tc_fence_before();

@@ -463,6 +463,7 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int
   using V = Act<FMT == 2 ? 0 : FMT>;
   using T = typename V::T;
   const size_t nv = n_elems / V::N;
+  const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t idx = i * V::N;
@@ -503,7 +504,7 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int
     if (g.flags & EPI_DROPOUT) {
 #pragma unroll
       for (int e = 0; e < V::N; ++e)
-        f[e] = dropout_keep(g.seed, static_cast<uint64_t>(idx) + e, g.keep_threshold) ? f[e] * g.inv_keep : 0.f;
+        f[e] = dropout_keep(seed, static_cast<uint64_t>(idx) + e, g.keep_threshold) ? f[e] * g.inv_keep : 0.f;
     }
     if (g.flags & EPI_MASK) {
       float m[V::N];
@@ -576,7 +577,9 @@ __device__ __forceinline__ void store_shadow4(__nv_bfloat16* hi, __nv_bfloat16* 
 }
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps, float gscale,
-                            __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo) {
+                            __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo,
+                            const float* __restrict__ lr_ptr) {
+  if (lr_ptr) lr_t = __ldg(lr_ptr);  // per-step value in device memory (CUDA-graph replays keep kernel arguments)
   const size_t n4 = n / 4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -613,8 +616,18 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
-                        float eps, float gscale, void* w_hi, void* w_lo, cudaStream_t st) {
-  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo)); }
+                        float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, cudaStream_t st) {
+  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo), lr_ptr); }
+  return cudaGetLastError();
+}
+// scalars[0] = lr_t (float), scalars[1] = dropout seed (uint32 bits): written by a kernel (arguments by value) so that
+// a host running many steps ahead of the device never races with a staging buffer.
+__global__ void set_step_scalars_kernel(float* scalars, float lr_t, uint32_t seed) {
+  scalars[0] = lr_t;
+  reinterpret_cast<uint32_t*>(scalars)[1] = seed;
+}
+cudaError_t launch_set_step_scalars(float* scalars, float lr_t, uint32_t seed, cudaStream_t st) {
+  { count_launch(); set_step_scalars_kernel<<<1, 1, 0, st>>>(scalars, lr_t, seed); }
   return cudaGetLastError();
 }
 // w_hi = bf16(p), w_lo = bf16(p - w_hi): the tensor-core shadow of the fp32 parameters (after load_weights).

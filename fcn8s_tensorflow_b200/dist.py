@@ -44,16 +44,36 @@ def shard_batch(images, labels, rank, world):
 
 
 class GradientAllReduce:
-    """Callable installed as `Engine.allreduce`: sums the flat gradient buffer over all ranks in one collective.
-    The 1/world average is applied by the consumer (Adam's grad_scale), not here."""
+    """Installed as `Engine.allreduce`: sums the flat gradient buffer over all ranks.  The 1/world average is applied
+    by the consumer (Adam's grad_scale), not here.
 
-    def __init__(self, group=None):
+    The buffer is laid out in backward-completion order (engine.flat_layout), so the engine calls `start(head)` on the
+    [decoder | fc7 | fc6] prefix (89 % of the bytes) as soon as the fc6 filter gradient has been enqueued -- that
+    collective then runs on NCCL's stream underneath the conv5 -> conv1 backward -- and `start(tail)` + `finish()` just
+    before Adam.  Logically still one all-reduce of one buffer per step, issued as two chunks.  `overlap=False` (or
+    FCN8_DP_OVERLAP=0) issues it as a single blocking collective after the backward pass."""
+
+    def __init__(self, group=None, overlap=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.overlap = (os.environ.get("FCN8_DP_OVERLAP", "1") != "0") if overlap is None else bool(overlap)
+        self.pending = []
+
+    def start(self, chunk):
+        """Enqueue the all-reduce of a contiguous slice of the flat gradient (async; ordered after the work already
+        enqueued on the current stream)."""
+        if self.world > 1 and chunk.numel():
+            self.pending.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Make the current stream wait for every started chunk."""
+        for w in self.pending:
+            w.wait()
+        self.pending = []
 
     def __call__(self, flat_grad):
-        if self.world > 1:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.start(flat_grad)
+        self.finish()
         return flat_grad
 
 
@@ -71,6 +91,7 @@ def broadcast_parameters(engine, src=0, group=None):
         for t in (engine.params, engine.adam_m, engine.adam_v):
             dist.broadcast(t, src=src, group=group)
         engine._packed_dirty = True
+        engine._shadow_dirty = True
 
 
 def max_over_ranks(value, device):

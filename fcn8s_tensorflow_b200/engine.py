@@ -9,6 +9,7 @@ library raises.
 
 Precision modes: see `Engine`.  The decoder (score heads, transposed convs, loss) is fp32 in every mode.
 """
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -140,7 +141,15 @@ class Engine:
         self._shadow_dirty = True
         self._arenas = {}
         self.world = 1
-        self.allreduce = None  # callable(flat_grad) installed by the data-parallel wrapper
+        self.allreduce = None  # dist.GradientAllReduce installed by the data-parallel wrapper
+        self._reduced_upto = 0  # elements of self.grads whose all-reduce has already been started this step
+        # per-step scalars in device memory ([0] lr_t, [1] dropout seed bits): a captured step can be replayed
+        self.step_scalars = torch.zeros(4, **z)
+        self.use_graphs = os.environ.get("FCN8_GRAPHS", "1") != "0"
+        self._graphs = {}           # (shape, keep_prob, l2_rate) -> (CUDAGraph, kernel launches per replay)
+        self._warm = {}
+        self.graph_launches = 0     # kernels launched through graph replays (fcn8_launch_count() does not see those)
+        self.head_elems = self.layout["conv5_3/filter"][0]   # [decoder | fc7 W | fc6 W] prefix of the flat buffer
 
     # ------------------------------------------------------------------ parameters
     def view(self, name, buf=None):
@@ -174,13 +183,15 @@ class Engine:
             self._shadow_dirty = False
         for name, k, cin, cout in self.layers:
             w = self.view(_wname(name))
+            old = self.packed.get(name)   # refilled in place: a captured CUDA graph keeps reading the same buffers
             if name == "conv1_1":
                 # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
                 self.packed[name] = ops.pack_weights(w, 1, 27, cout, 0, self.dt, cin_pad=self.kp,
-                                                     split=self.x3 or self.pair) + (None, None)
+                                                     split=self.x3 or self.pair,
+                                                     out=old[0:2] if old else None) + (None, None)
             elif not self.hwio:
-                f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3)
-                d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3)
+                f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3, out=old[0:2] if old else None)
+                d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3, out=old[2:4] if old else None)
                 self.packed[name] = f + d
         self.packed["up8"] = ops.upscore_tc_pack(self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
                                                  self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8, split=self.dec3,
@@ -239,10 +250,13 @@ class Engine:
         return ops.conv_gemm(x, wp, cout, k, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo, **kw)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, images, keep_prob=1.0, seed=0, train=False):
-        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (a view of an arena buffer)."""
+    def forward(self, images, keep_prob=1.0, seed=0, train=False, _scalars_set=False):
+        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (a view of an arena buffer).
+        The dropout seed is read by the kernels from `step_scalars` (set here unless the caller already did)."""
         if self._packed_dirty or (self.hwio and self._shadow_dirty):
             self.repack()
+        if train and keep_prob < 1.0 and not _scalars_set:
+            ops.set_step_scalars(self.step_scalars, 0.0, seed)
         N, H, W, _ = images.shape
         A = self._arena(N, H, W)
         A["_shape"] = (N, H, W)
@@ -270,7 +284,8 @@ class Engine:
             out = self._act(A, name, N, h, w, cout)
             flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0)
             self._conv(A, name, x, k, cin, cout, out, self.view(name + "/biases"), flags,
-                       keep_prob=keep_prob if drop else 1.0, seed=self.dropout_seed(seed, name))
+                       keep_prob=keep_prob if drop else 1.0, seed=1 if name == "fc7" else 0,
+                       seed_ptr=self.step_scalars[1:2] if drop else None)
             x = out
         C = self.C
         f32 = torch.float32
@@ -308,16 +323,18 @@ class Engine:
 
     @staticmethod
     def dropout_seed(seed, layer):
+        """Seed of the counter-based dropout mask of `layer` for step seed `seed` (host replica: rng.py); the kernels
+        form the same value from the device scalar: *seed_ptr * 2 + (layer == fc7)."""
         return (int(seed) * 2 + (1 if layer == "fc7" else 0)) & 0xFFFFFFFF
 
     # ------------------------------------------------------------------ loss + backward
-    def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0):
+    def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0, _scalars_set=False):
         """Forward + backward of optimizer/total_loss (fcn8s_tensorflow.py:250-257) into self.grads.
         labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2)."""
         N, H, W, _ = images.shape
         C = self.C
         pair = self.pair
-        self.forward(images, keep_prob, seed, train=True)
+        self.forward(images, keep_prob, seed, train=True, _scalars_set=_scalars_set)
         A = self._arena(N, H, W)
         G = self.grads
         f32 = torch.float32
@@ -382,6 +399,10 @@ class Engine:
                 ops.wgrad_gemm(x_in, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl, pair=pair)
                 break
             ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair)
+            if name == "fc6" and self.allreduce is not None and getattr(self.allreduce, "overlap", False):
+                # decoder, fc7 and fc6 gradients (89 % of the buffer) are final: reduce them under the conv backward
+                self.allreduce.start(G[:self.head_elems])
+                self._reduced_upto = self.head_elems
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
             prev_db = self.view(prev_name + "/biases", G)
@@ -427,24 +448,76 @@ class Engine:
         return A[self.layers[li - 1][0]]
 
     # ------------------------------------------------------------------ optimiser
+    def _lr_t(self, lr, t):
+        return float(lr) * float(np.sqrt(1.0 - BETA2 ** t) / (1.0 - BETA1 ** t))
+
+    def _reduce_and_adam(self, lr_t):
+        if self.allreduce is not None:
+            self.allreduce.start(self.grads[self._reduced_upto:])
+            self.allreduce.finish()
+            self._reduced_upto = 0
+        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world,
+                 w_hi=self.w_hi, w_lo=self.w_lo, lr_ptr=self.step_scalars[0:1])
+
     def adam_step(self, lr):
         """TF-form Adam over the flat buffer (one launch), then global_step += 1 (fcn8s_tensorflow.py:256-257)."""
-        if self.allreduce is not None:
-            self.allreduce(self.grads)
         t = self.global_step + 1
-        lr_t = float(lr) * float(np.sqrt(1.0 - BETA2 ** t) / (1.0 - BETA1 ** t))
-        ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world,
-                 w_hi=self.w_hi, w_lo=self.w_lo)
+        lr_t = self._lr_t(lr, t)
+        ops.set_step_scalars(self.step_scalars, lr_t, 0)
+        self._reduce_and_adam(lr_t)
         self.global_step = t
         self._packed_dirty = True
 
+    def _step_body(self, images, labels, keep_prob, l2_rate):
+        """Everything one training `sess.run` does on the device, reading lr_t / seed from `step_scalars`: this is the
+        unit that is captured into a CUDA graph."""
+        self.loss_and_backward(images, labels, keep_prob, l2_rate, 0, _scalars_set=True)
+        self._reduce_and_adam(0.0)
+        self._packed_dirty = True
+        self.repack()     # derived operands of the updated parameters, ready for the next step's forward
+
     def train_step(self, images, labels, lr, keep_prob=0.5, l2_rate=0.0, seed=None):
         """One `sess.run([train_op, total_loss, global_step])` (fcn8s_tensorflow.py:565-572).
-        Returns the device tensor loss_buf; total_loss = loss_buf[0] / (N*H*W) + loss_buf[1] (see `loss_value`)."""
+        Returns the device tensor loss_buf; total_loss = loss_buf[0] / (N*H*W) + loss_buf[1] (see `loss_value`).
+
+        After two eager steps per (shape, keep_prob, l2_rate) the whole step (~250 kernel launches and the gradient
+        all-reduce) is captured into a CUDA graph and replayed: the batch is copied into fixed input buffers and the
+        two per-step scalars (lr_t, dropout seed) are written to device memory by a 1-thread kernel, so the host's
+        cost per step is three launches.  FCN8_GRAPHS=0 (or an installed ops.TIMER) keeps the eager path."""
         if seed is None:
             seed = self.global_step
-        self.loss_and_backward(images, labels, keep_prob, l2_rate, seed)
-        self.adam_step(lr)
+        t = self.global_step + 1
+        lr_t = self._lr_t(lr, t)
+        key = (tuple(images.shape), float(keep_prob), float(l2_rate))
+        graphs = self.use_graphs and ops.TIMER is None
+        if graphs:
+            A = self._arena(images.shape[0], images.shape[1], images.shape[2])
+            xin = self._buf(A, "x_in", images.shape, torch.uint8)
+            yin = self._buf(A, "y_in", labels.shape, torch.uint8)
+            xin.copy_(images)
+            yin.copy_(labels.view(torch.uint8))
+            images, labels = xin, yin
+        ops.set_step_scalars(self.step_scalars, lr_t, seed)
+        entry = self._graphs.get(key) if graphs else None
+        if entry is not None:
+            if self._packed_dirty or (self.hwio and self._shadow_dirty):
+                self.repack()     # weights were replaced (load_weights) since the last step
+            entry[0].replay()
+            self.graph_launches += entry[1]
+        elif graphs and self._warm.get(key, 0) >= 2:
+            torch.cuda.synchronize(self.device)
+            l0 = self.lib.fcn8_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._step_body(images, labels, keep_prob, l2_rate)
+            n = int(self.lib.fcn8_launch_count() - l0)
+            self._graphs[key] = (g, n)
+            g.replay()
+            self.graph_launches += n
+        else:
+            self._warm[key] = self._warm.get(key, 0) + 1
+            self._step_body(images, labels, keep_prob, l2_rate)
+        self.global_step = t
         return self.loss_buf
 
     def loss_value(self, images_shape):

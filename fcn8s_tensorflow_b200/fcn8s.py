@@ -138,22 +138,45 @@ class FCN8s:
         dev.copy_(pin, non_blocking=True)
         return dev
 
-    def _images_to_device(self, images):
+    def _check_images(self, images):
         a = np.asarray(images)
         if a.ndim != 4 or a.shape[-1] != 3:
             raise ValueError("images must have shape (batch, height, width, 3), got %s" % (a.shape,))
         if a.dtype != np.uint8:
             a = np.clip(np.rint(a), 0, 255).astype(np.uint8)
-        return self._to_device(a, "images")
+        return a
 
-    def _labels_to_device(self, labels):
+    def _check_labels(self, labels):
         a = np.asarray(labels)
         if a.ndim != 4 or a.shape[-1] != self.num_classes:
             raise ValueError("labels must be one-hot with shape (batch, height, width, %d), got %s"
                              % (self.num_classes, a.shape,))
         if a.dtype != np.bool_ and a.dtype != np.uint8:
             a = a.astype(np.uint8)
-        return self._to_device(a, "labels")
+        return a
+
+    def _images_to_device(self, images):
+        return self._to_device(self._check_images(images), "images")
+
+    def _labels_to_device(self, labels):
+        return self._to_device(self._check_labels(labels), "labels")
+
+    def _loss_read_begin(self, shape):
+        """Async D2H of the step's loss pair into a pinned slot; returns a token for `_loss_read_end`."""
+        if not hasattr(self, "_loss_slots"):
+            self._loss_slots = [(torch.empty(2, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+            self._loss_i = 0
+        host, ev = self._loss_slots[self._loss_i]
+        self._loss_i ^= 1
+        host.copy_(self.engine.loss_buf, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.engine.device))
+        return host, ev, float(shape[0] * shape[1] * shape[2])
+
+    @staticmethod
+    def _loss_read_end(token):
+        host, ev, npx = token
+        ev.synchronize()
+        return float(host[0]) / npx + float(host[1])
 
     # ------------------------------------------------------------------ metrics (fcn8s_tensorflow.py:273-322, 371-397)
     def _initialize_metrics(self, metrics):
@@ -237,21 +260,39 @@ class FCN8s:
             if len(metrics) > 0:
                 evaluation_writer = SummaryWriter(os.path.join(summaries_dir, (summaries_name or 'summaries') + '_eval'))
 
+        from .feed import Feeder
         for epoch in range(1, epochs + 1):
             loss_history = deque(maxlen=training_loss_display_averaging)
             tr = trange(steps_per_epoch, file=sys.stdout)
             tr.set_description('Epoch {}/{}'.format(epoch, epochs))
-            for train_step in tr:
-                batch_images, batch_labels = next(train_generator)
-                current_loss = self.train_on_batch(batch_images, batch_labels, learning_rate, keep_prob, l2_regularization)
-                if training_writer is not None and (self.g_step - 1) % summaries_frequency == 0:
-                    training_writer.add_scalar('total_loss', current_loss, self.g_step)
-                    training_writer.add_scalar('learning_rate', learning_rate, self.g_step)
-                self.variables_updated = True
+            # The feed is prefetched (feed.py) and each step's loss is fetched one step late, so the device never
+            # waits for the host: `pending` is the (loss token, step, learning rate) of the previous step.
+            feeder = Feeder(self, train_generator, steps_per_epoch)
+            pending = None
+
+            def account(p):
+                current_loss = self._loss_read_end(p[0])
+                if training_writer is not None and (p[1] - 1) % summaries_frequency == 0:
+                    training_writer.add_scalar('total_loss', current_loss, p[1])
+                    training_writer.add_scalar('learning_rate', p[2], p[1])
                 loss_history.append(current_loss)
                 self.training_loss = float(np.mean(np.array(loss_history)))
-                tr.set_postfix(ordered_dict={'loss': self.training_loss, 'learning rate': learning_rate})
+                tr.set_postfix(ordered_dict={'loss': self.training_loss, 'learning rate': p[2]})
+
+            for train_step in tr:
+                x, y = feeder.get()
+                self.engine.train_step(x, y, learning_rate, keep_prob, l2_regularization)
+                feeder.release()
+                token = self._loss_read_begin(x.shape)
+                self.g_step = self.engine.global_step
+                self.variables_updated = True
+                if pending is not None:
+                    account(pending)
+                pending = (token, self.g_step, learning_rate)
                 learning_rate = learning_rate_schedule(self.g_step)
+            if pending is not None:
+                account(pending)
+            feeder.close()
 
             if (len(metrics) > 0) and (epoch % eval_frequency == 0):
                 if eval_dataset == 'train':
@@ -316,14 +357,22 @@ class FCN8s:
         loss_sum, loss_count = 0.0, 0
         tr = trange(num_batches, file=sys.stdout)
         tr.set_description(description)
+        from .feed import Feeder
+        feeder = Feeder(self, data_generator, num_batches)
+        pending = None
         for step in tr:
-            batch_images, batch_labels = next(data_generator)
-            x = self._images_to_device(batch_images)
-            y = self._labels_to_device(batch_labels)
+            x, y = feeder.get()
             self.engine.eval_step(x, y, self._conf, l2_regularization)
-            if 'loss' in self.metric_names:
-                loss_sum += self.engine.loss_value(x.shape)   # tf.metrics.mean over per-batch total_loss, :284
+            feeder.release()
+            if 'loss' in self.metric_names:       # tf.metrics.mean over per-batch total_loss, :284 (read one step late)
+                token = self._loss_read_begin(x.shape)
+                if pending is not None:
+                    loss_sum += self._loss_read_end(pending)
+                pending = token
                 loss_count += 1
+        if pending is not None:
+            loss_sum += self._loss_read_end(pending)
+        feeder.close()
         cm = self._conf.cpu().numpy()
         self.metric_values = self._metric_values_from(loss_sum, loss_count, cm)
         evaluation_results_string = ''

@@ -1,0 +1,97 @@
+"""Prefetching feed for the `FCN8s` train / evaluate loops.
+
+The reference pulls `next(generator)` synchronously inside the step loop and lets `sess.run` copy the numpy feeds to
+the device every step (fcn8s_tensorflow.py:551-572, 683-689), so the GPU idles during PNG decoding and the H2D copy.
+Here a background thread pulls exactly `count` batches from the generator (never more, so a generator shared between
+training and evaluation is consumed in the reference's order), stages each in pinned host memory and issues the H2D
+copy on a side CUDA stream; the step loop only makes the compute stream wait on the copy's event.  Slots are recycled
+once the step that consumed them has been enqueued (event on the compute stream).
+"""
+import queue
+import threading
+
+import numpy as np
+import torch
+
+
+class _Slot:
+    def __init__(self):
+        self.pin = {}
+        self.dev = {}
+        self.copied = torch.cuda.Event()
+        self.consumed = None  # event recorded on the compute stream after the consuming step was enqueued
+
+
+class Feeder:
+    def __init__(self, model, generator, count, depth=3):
+        self.model = model
+        self.generator = generator
+        self.count = int(count)
+        self.device = model.engine.device
+        # pinned staging slots and the copy stream live on the model: allocating page-locked memory costs
+        # milliseconds, and a Feeder is created per epoch / per evaluation
+        cache = model.__dict__.setdefault("_feed_cache", {})
+        if "stream" not in cache:
+            cache["stream"] = torch.cuda.Stream(device=self.device)
+            cache["slots"] = [_Slot() for _ in range(depth)]
+        self.copy_stream = cache["stream"]
+        self.free = queue.Queue()
+        for slot in cache["slots"]:
+            self.free.put(slot)
+        self.ready = queue.Queue()
+        self.current = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _stage(self, slot, key, a):
+        a = np.ascontiguousarray(a)
+        if a.dtype == np.bool_:
+            a = a.view(np.uint8)
+        pin = slot.pin.get(key)
+        if pin is None or tuple(pin.shape) != a.shape:
+            pin = slot.pin[key] = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype).pin_memory()
+            slot.dev[key] = torch.empty(a.shape, dtype=pin.dtype, device=self.device)
+        pin.copy_(torch.from_numpy(a))
+        slot.dev[key].copy_(pin, non_blocking=True)
+        return slot.dev[key]
+
+    def _run(self):
+        try:
+            torch.cuda.set_device(self.device)
+            for _ in range(self.count):
+                images, labels = next(self.generator)
+                images = self.model._check_images(images)
+                labels = self.model._check_labels(labels)
+                slot = self.free.get()
+                slot.copied.synchronize()            # the pinned buffers are free once their last H2D has finished
+                with torch.cuda.stream(self.copy_stream):
+                    if slot.consumed is not None:     # the device buffers are free once their last step was enqueued
+                        self.copy_stream.wait_event(slot.consumed)
+                    x = self._stage(slot, "images", images)
+                    y = self._stage(slot, "labels", labels)
+                    slot.copied.record(self.copy_stream)
+                self.ready.put((slot, x, y))
+        except BaseException as e:  # noqa: BLE001 -- re-raised in the consumer
+            self.ready.put(e)
+
+    def get(self):
+        """Next (images, labels) device pair; the current stream waits for its copy."""
+        item = self.ready.get()
+        if isinstance(item, BaseException):
+            raise item
+        slot, x, y = item
+        torch.cuda.current_stream(self.device).wait_event(slot.copied)
+        self.current = slot
+        return x, y
+
+    def release(self):
+        """Call after the step that uses the current batch has been enqueued."""
+        slot = self.current
+        if slot.consumed is None:
+            slot.consumed = torch.cuda.Event()
+        slot.consumed.record(torch.cuda.current_stream(self.device))
+        self.current = None
+        self.free.put(slot)
+
+    def close(self):
+        self.thread.join(timeout=30)

@@ -112,16 +112,19 @@ def preprocess_im2col(images, dtype):
     return out
 
 
-def pack_weights(w, ksize, cin, cout, mode, dtype, cin_pad=None, split=False):
+def pack_weights(w, ksize, cin, cout, mode, dtype, cin_pad=None, split=False, out=None):
     """fp32 HWIO weights -> tensor-core operand layout (mode 0 fprop [Cout][taps*CinPad], mode 1 dgrad
-    [Cin][taps*Cout]). Returns (packed, packed_lo or None)."""
+    [Cin][taps*Cout]). Returns (packed, packed_lo or None); `out` = an earlier result to refill in place."""
     _chk_cuda(w)
     taps = ksize * ksize
     if cin_pad is None:
         cin_pad = cin
     shape = (cout, taps * cin_pad) if mode == 0 else (cin, taps * cout)
-    out = torch.empty(shape, dtype=torch_dtype(dtype), device=w.device)
-    lo = torch.empty_like(out) if split else None
+    if out is not None:
+        out, lo = out
+    else:
+        out = torch.empty(shape, dtype=torch_dtype(dtype), device=w.device)
+        lo = torch.empty_like(out) if split else None
     p = capi.PackParams(capi.ptr(w), capi.ptr(out), capi.ptr(lo), ksize, cin, cout, cin_pad, mode, dtype)
     capi.check(capi.load().fcn8_pack_weights(C.byref(p), _stream()))
     return out, lo
@@ -136,7 +139,7 @@ def split_tf32(x):
 
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
-              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None):
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None, seed_ptr=None):
     """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
     pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
     the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF
@@ -153,7 +156,8 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, 3, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
-                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum))
+                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum),
+                            capi.ptr(seed_ptr))
     else:
         dtype = dtype_of(x)
         if out is None:
@@ -162,7 +166,7 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode,
-                            capi.ptr(colsum))
+                            capi.ptr(colsum), capi.ptr(seed_ptr))
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
@@ -400,11 +404,19 @@ def confusion_matrix(pred, labels_onehot, conf):
                                                  pred.numel(), Cc, _stream()))
 
 
-def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w_hi=None, w_lo=None):
-    """TF-form Adam over a flat buffer; w_hi / w_lo (bf16, same length): tensor-core shadow refreshed in the pass."""
-    _chk_cuda(p, g, m, v, w_hi, w_lo)
+def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w_hi=None, w_lo=None, lr_ptr=None):
+    """TF-form Adam over a flat buffer; w_hi / w_lo (bf16, same length): tensor-core shadow refreshed in the pass.
+    lr_ptr: device fp32 scalar overriding lr_t (see set_step_scalars)."""
+    _chk_cuda(p, g, m, v, w_hi, w_lo, lr_ptr)
     capi.check(capi.load().fcn8_adam(capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), p.numel(), lr_t, beta1,
-                                     beta2, eps, grad_scale, capi.ptr(w_hi), capi.ptr(w_lo), _stream()))
+                                     beta2, eps, grad_scale, capi.ptr(w_hi), capi.ptr(w_lo), capi.ptr(lr_ptr),
+                                     _stream()))
+
+
+def set_step_scalars(scalars, lr_t, seed):
+    """scalars (fp32 [>=2], device): [0] = lr_t, [1] = dropout seed bits."""
+    _chk_cuda(scalars)
+    capi.check(capi.load().fcn8_set_step_scalars(capi.ptr(scalars), lr_t, int(seed) & 0xFFFFFFFF, _stream()))
 
 
 def shadow_weights(p, w_hi, w_lo=None):

@@ -107,6 +107,7 @@ typedef struct {
    * Cout_w = Cout; dgrad: Cin_w = Cout, Cout_w = Cin (rotation and transposition happen in the TMA coordinates). */
   int32_t w_mode;
   float* colsum;        /* FCN8_EPI_COLSUM target, [Cout] fp32 */
+  const uint32_t* seed_ptr; /* optional device scalar: dropout seed = *seed_ptr * 2 + seed (see fcn8_set_step_scalars) */
 } Fcn8ConvParams;
 size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -289,7 +290,11 @@ int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot,
  * g' = g*grad_scale;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;  p -= lr_t * m / (sqrt(v) + eps),
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* w_hi, void* w_lo, void* stream);
+                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, void* stream);
+/* Per-step scalars in device memory so that a captured CUDA graph of the whole training step can be replayed with a
+ * new learning rate and dropout seed (the reference feeds both every step, fcn8s_tensorflow.py:558-562):
+ * scalars[0] = lr_t (read by fcn8_adam through lr_ptr), scalars[1] = seed bits (read through Fcn8ConvParams.seed_ptr). */
+int32_t fcn8_set_step_scalars(float* scalars, float lr_t, uint32_t seed, void* stream);
 /* w_hi / w_lo (optional, bf16 [n]): the tensor-core shadow of the parameters, w_hi = bf16(p), w_lo = bf16(p - w_hi),
  * refreshed by fcn8_adam in the same pass; the GEMMs read it in TF layout (Fcn8ConvParams.w_mode 1 / 2), so no
  * per-step re-packing exists.  fcn8_shadow_weights builds it after a weight load. */

@@ -177,6 +177,31 @@ def test_batch_independence_and_determinism(cuda_device, problem):
     assert rel(single[0], full[1]) <= 1e-6
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_matches_eager_steps(cuda_device, problem, precision):
+    """train_step captures the whole step into a CUDA graph after two eager steps; six steps with per-step learning
+    rates and dropout seeds must give the same parameters and losses as six eager steps (the bias-gradient and loss
+    reductions use atomics, so 'same' is to fp32 summation-order noise, not bitwise)."""
+    x = torch.from_numpy(problem["images"]).to(cuda_device)
+    y = torch.from_numpy(problem["labels"].view(np.uint8)).to(cuda_device)
+    lrs = [1e-4, 1e-4, 3e-4, 1e-4, 5e-5, 2e-4]
+    out = {}
+    for graphs in (False, True):
+        e = make_engine(cuda_device, precision, problem["weights"])
+        e.use_graphs = graphs
+        losses = []
+        for lr in lrs:
+            e.train_step(x, y, lr, keep_prob=0.5, l2_rate=0.01)
+            losses.append(e.loss_value(x.shape))
+        torch.cuda.synchronize()
+        assert (len(e._graphs) == 1) == graphs and (e.graph_launches > 0) == graphs
+        out[graphs] = (e.params.clone(), losses, e.global_step)
+    assert out[True][2] == out[False][2] == len(lrs)
+    tol = 1e-5 if precision == "fp32" else 2e-3   # bf16: a rounding-order flip of one bf16 activation is allowed
+    assert np.allclose(out[True][1], out[False][1], rtol=tol, atol=0)
+    assert rel_l2(out[True][0], out[False][0]) <= tol
+
+
 def test_kitti_two_class_shape(cuda_device):
     """BASELINE config 5 geometry (KITTI road, 2 classes) at a x32 size, labels [bg, ~bg] as
     batch_generator_KITTI.py:82-84 builds them."""

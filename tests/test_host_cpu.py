@@ -139,7 +139,10 @@ def _gloo_worker(rank, world, port, out):
     fdist.attach(e)
     fdist.broadcast_parameters(e, src=0)
     g = torch.arange(10, dtype=torch.float32) * (rank + 1)
-    e.allreduce(g)
+    e.allreduce.start(g[:6])       # the engine's two-chunk protocol: head under the backward pass, tail before Adam
+    e.allreduce.start(g[6:])
+    e.allreduce.finish()
+    assert not e.allreduce.pending
     avg = g / e.world     # what Adam's grad_scale = 1/world does
     t = fdist.max_over_ranks(float(rank + 1), torch.device("cpu"))
     out.put((rank, e.world, e.params.tolist(), avg.tolist(), t, e._packed_dirty))
