@@ -16,7 +16,8 @@ EXPORTS = [
     "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_preprocess_im2col",
     "fcn8_conv_gemm_workspace_bytes", "fcn8_conv_gemm", "fcn8_wgrad_gemm_workspace_bytes", "fcn8_wgrad_gemm",
     "fcn8_pack_weights", "fcn8_split_tf32", "fcn8_maxpool_fwd", "fcn8_maxpool_bwd", "fcn8_bias_grad_workspace_bytes",
-    "fcn8_bias_grad", "fcn8_score_head_fwd", "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
+    "fcn8_bias_grad", "fcn8_score_head_fwd_workspace_bytes", "fcn8_score_head_fwd",
+    "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
     "fcn8_upscore_fwd", "fcn8_upscore_bwd_workspace_bytes", "fcn8_upscore_bwd", "fcn8_softmax_xent",
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
@@ -42,7 +43,7 @@ class ConvParams(C.Structure):
                 ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
                 ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32),
                 ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32), ("colsum", C.c_void_p),
-                ("seed_ptr", C.c_void_p)]
+                ("seed_ptr", C.c_void_p), ("algo", C.c_int32)]
 
 
 class WgradParams(C.Structure):
@@ -119,7 +120,8 @@ def load():
     lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
-                     ("fcn8_score_head_bwd", HeadParams), ("fcn8_upscore_bwd", UpscoreParams),
+                     ("fcn8_score_head_fwd", HeadParams), ("fcn8_score_head_bwd", HeadParams),
+                     ("fcn8_upscore_bwd", UpscoreParams),
                      ("fcn8_upscore_tc_dw", UpscoreTcParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp, sz, vp]
         getattr(lib, name).restype = C.c_int32
@@ -127,7 +129,7 @@ def load():
         getattr(lib, name + "_workspace_bytes").restype = sz
     for name, pt in [("fcn8_preprocess_im2col", PreprocessParams), ("fcn8_pack_weights", PackParams),
                      ("fcn8_maxpool_fwd", PoolParams), ("fcn8_maxpool_bwd", PoolParams),
-                     ("fcn8_score_head_fwd", HeadParams), ("fcn8_upscore_fwd", UpscoreParams),
+                     ("fcn8_upscore_fwd", UpscoreParams),
                      ("fcn8_softmax_xent", SoftmaxParams), ("fcn8_upscore_tc_pack", UpscorePackParams),
                      ("fcn8_upscore_tc_fwd", UpscoreTcParams), ("fcn8_upscore_tc_dx", UpscoreTcParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp]

@@ -213,6 +213,19 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
   return cudaGetLastError();
 }
 
+template <int BN>
+cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HaloSmem<BN>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  { count_launch(); conv_halo_kernel<BN><<<grid, kGemmThreads, HaloSmem<BN>::kBytes, st>>>(maps, a); }
+  return cudaGetLastError();
+}
+
 template <int BN, bool TF32>
 constexpr int wgrad_smem_bytes() {
   constexpr int CH = TF32 ? 32 : 64;
@@ -306,7 +319,7 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
     splits = (int)(sms / tiles);  // floor: tiles * splits <= #SMs, one full wave (ceil would leave a 2nd, ~empty wave)
     const int max_by_k = pl->total_pb / 8 > 0 ? pl->total_pb / 8 : 1;
     if (splits > max_by_k) splits = max_by_k;
-    if (splits > 64) splits = 64;
+    if (splits > sms) splits = sms;
   }
   if (splits > pl->total_pb) splits = pl->total_pb;
   pl->pb_per_split = (pl->total_pb + splits - 1) / splits;
@@ -369,6 +382,21 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if (need > workspace_bytes || (need && !workspace))
     return fail(FCN8_ERR_WORKSPACE, "conv: workspace %zu < required %zu", workspace_bytes, need);
 
+  // Halo-tile kernel for the L2-traffic-bound 3x3 layers (few input channels: the activation patch is loaded once per
+  // tile instead of once per tap).  algo: 0 = heuristic, 1 = per-tap kernel, 2 = halo kernel.
+  const bool halo_ok = p->dtype == FCN8_BF16 && p->ksize == 3 && p->w_mode != 0 && p->Cin % 64 == 0;
+  const bool use_halo = halo_ok && (p->algo >= 2 || (p->algo == 0 && p->Cin <= 128));
+  if (p->algo >= 2 && !halo_ok) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs bf16, 3x3, w_mode 1/2");
+  if (use_halo) {
+    pl.lbw = 3;
+    pl.lbh = 4;
+    pl.lbn = 0;
+    pl.tiles_x = (p->W + 7) >> 3;
+    pl.tiles_y = (p->H + 15) >> 4;
+    pl.tiles_b = p->N;
+    pl.m_tiles = pl.tiles_x * pl.tiles_y * pl.tiles_b;
+    pl.splits = 1;
+  }
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
   const int ktot = p->ksize * p->ksize * p->Cin;
@@ -376,8 +404,11 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   const void* ws[3] = {p->wp, p->wp_lo, p->wp};
   const int taps = p->ksize * p->ksize;
   for (int s = 0; s < p->nseg; ++s) {
-    rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
-                        false, p->x_ld);
+    if (use_halo)
+      rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 16, 18, 1, false, p->x_ld);
+    else
+      rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh,
+                          1 << pl.lbn, false, p->x_ld);
     if (rc) return rc;
     if (p->w_mode == 0)
       rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
@@ -431,6 +462,14 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   }
   ConvGemmArgs kernel_args = a;
   if (pl.splits > 1) kernel_args.flags = EPI_PARTIAL;
+  if (use_halo) {
+    const long long tiles = (long long)pl.m_tiles * pl.tiles_n;
+    const int hgrid = (int)(tiles < num_sms() ? tiles : num_sms());
+    cudaError_t he = pl.BN == 256 ? launch_halo_t<256>(maps, a, hgrid, (cudaStream_t)stream)
+                   : pl.BN == 128 ? launch_halo_t<128>(maps, a, hgrid, (cudaStream_t)stream)
+                                  : launch_halo_t<64>(maps, a, hgrid, (cudaStream_t)stream);
+    return he == cudaSuccess ? 0 : cuda_fail(he, "conv_halo launch");
+  }
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
@@ -594,11 +633,18 @@ int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t work
   return e == cudaSuccess ? 0 : cuda_fail(e, "bias_grad launch");
 }
 
-int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* stream) {
+size_t fcn8_score_head_fwd_workspace_bytes(const Fcn8HeadParams* p) {
+  const int slices = head_fwd_slices(p->P, p->Cin);
+  return slices > 1 ? (size_t)slices * p->P * p->C * sizeof(float) : 0;
+}
+int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream) {
   if (!p || !p->x || !p->K || !p->b || !p->s) return fail(FCN8_ERR_BAD_SHAPE, "head fwd: null pointer");
   if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head: num_classes=%d not in [1,32]", p->C);
+  const size_t need = fcn8_score_head_fwd_workspace_bytes(p);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(FCN8_ERR_WORKSPACE, "head fwd: workspace %zu < required %zu", workspace_bytes, need);
   cudaError_t e = launch_head_fwd(p->x, p->K, p->b, p->s, p->P, p->Cin, p->C, p->scale, p->dtype,
-                                  (cudaStream_t)stream);
+                                  static_cast<float*>(workspace), (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "head fwd launch");
 }
 size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p) {

@@ -295,6 +295,71 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Epilogue warps (4 warps, one TMEM lane quarter each) of the implicit-GEMM convolution kernels: persistent loop over
+// the CTA's tiles, TMEM -> registers -> epilogue math -> global.
+template <int BN, bool TF32>
+__device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
+                                                   uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
+                                                   int warp, int lane) {
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    const size_t out_elems = static_cast<size_t>(g.N) * g.H * g.W * g.ldc;
+    const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nb = t % g.tiles_n;
+      const int mt = (t / g.tiles_n) % m_tiles;
+      const int sp = t / (g.tiles_n * m_tiles);
+      const int tx = mt % g.tiles_x;
+      const int ty = (mt / g.tiles_x) % g.tiles_y;
+      const int tb = mt / (g.tiles_x * g.tiles_y);
+      const int x = (tx << g.lbw) + (row & ((1 << g.lbw) - 1));
+      const int y = (ty << g.lbh) + ((row >> g.lbw) & ((1 << g.lbh) - 1));
+      const int n = (tb << g.lbn) + (row >> (g.lbw + g.lbh));
+      const bool valid = (x < g.W) && (y < g.H) && (n < g.N);
+      const size_t pix = (static_cast<size_t>(n) * g.H + y) * g.W + x;
+      const size_t row_off = static_cast<size_t>(n) * g.osN + static_cast<size_t>(y) * g.osH +
+                             static_cast<size_t>(x) * g.osW;
+      mbar_wait(&acc_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        const int c0 = nb * BN + c;
+        if (g.flags & EPI_PARTIAL) {
+          if (valid) {
+            const size_t idx = pix * g.ldc + c0;
+            float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
+        } else {
+          size_t idx = row_off + c0;
+          if (g.out_mode) {
+            const int bdy = c0 / g.blk_row;
+            idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
+          }
+          const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
+          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane, seed);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+// ------------------------------------------------------------------------------------------------------------------
 template <int BN, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
@@ -450,62 +515,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
   } else {
     // ============================== epilogue ==============================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    int as = 0;
-    uint32_t aphase = 0;
-    const size_t out_elems = static_cast<size_t>(g.N) * g.H * g.W * g.ldc;
-    const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int nb = t % g.tiles_n;
-      const int mt = (t / g.tiles_n) % m_tiles;
-      const int sp = t / (g.tiles_n * m_tiles);
-      const int tx = mt % g.tiles_x;
-      const int ty = (mt / g.tiles_x) % g.tiles_y;
-      const int tb = mt / (g.tiles_x * g.tiles_y);
-      const int x = (tx << g.lbw) + (row & ((1 << g.lbw) - 1));
-      const int y = (ty << g.lbh) + ((row >> g.lbw) & ((1 << g.lbh) - 1));
-      const int n = (tb << g.lbn) + (row >> (g.lbw + g.lbh));
-      const bool valid = (x < g.W) && (y < g.H) && (n < g.N);
-      const size_t pix = (static_cast<size_t>(n) * g.H + y) * g.W + x;
-      const size_t row_off = static_cast<size_t>(n) * g.osN + static_cast<size_t>(y) * g.osH +
-                             static_cast<size_t>(x) * g.osW;
-      mbar_wait(&acc_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        const int c0 = nb * BN + c;
-        if (g.flags & EPI_PARTIAL) {
-          if (valid) {
-            const size_t idx = pix * g.ldc + c0;
-            float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          }
-        } else {
-          size_t idx = row_off + c0;
-          if (g.out_mode) {
-            const int bdy = c0 / g.blk_row;
-            idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
-          }
-          const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
-          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane, seed);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
-      }
-    }
+    conv_epilogue_loop<BN, TF32>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane);
   }
 
   tc_fence_before();
@@ -515,6 +525,190 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
   if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL))
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {
+      const float t = colsum_s[c];
+      if (t != 0.f) atomicAdd(g.colsum + c, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv_halo_kernel: the same 3x3 stride-1 SAME convolution for the layers whose implicit GEMM is bound by L2 -> shared
+// memory traffic (few channels: conv1_x, conv2_x): the nine taps of a tile read nine shifted windows of the SAME
+// activation patch, so the patch is loaded ONCE with its one-pixel halo -- a TMA box of 18 rows x 16 pixels x 128 B
+// (64 bf16 channels) for a tile of 16 rows x 8 pixels -- and every tap's A operand is a UMMA descriptor that starts
+// (kh*16 + kw) rows into that box: the 8-row core-matrix groups of the 128 output pixels are the patch rows, 2048 B
+// (= 16 pixels) apart (SBO), so groups and the 128-byte swizzle phase of every row stay address-consistent.
+// A traffic per tile drops from 9 x 16 KB to 36 KB; B (weights, TF layout as in conv_gemm_kernel) is streamed through
+// its own ring.  bf16 operands only (kind::f16); epilogue shared with conv_gemm_kernel.
+struct HaloCfg {
+  static constexpr int kABytes = 18 * 16 * 128;  // 36,864
+  static constexpr int kAStages = 2;
+};
+template <int BN>
+struct HaloSmem {
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kBytes =
+      HaloCfg::kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumMax * 4 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
+  using HS = HaloSmem<BN>;
+  constexpr int kAS = HaloCfg::kAStages, kBS = HS::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + kAS * HaloCfg::kABytes;
+  uint8_t* bar_base = smem_b + kBS * HS::kBBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* a_empty = a_full + kAS;
+  uint64_t* b_full = a_empty + kAS;
+  uint64_t* b_empty = b_full + kBS;
+  uint64_t* acc_full = b_empty + kBS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* colsum_s = reinterpret_cast<float*>(bar_base + HS::kBarBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g.flags & EPI_COLSUM)
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
+
+  const int m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  const int total_tiles = m_tiles * g.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+    for (int s = 0; s < kAS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kBS; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nb = t % g.tiles_n;
+        const int mt = t / g.tiles_n;
+        const int tx = mt % g.tiles_x;
+        const int ty = (mt / g.tiles_x) % g.tiles_y;
+        const int n0 = mt / (g.tiles_x * g.tiles_y);
+        const int x0 = tx << 3, y0 = ty << 4;
+        for (int seg = 0; seg < g.nseg; ++seg) {
+          for (int cb = 0; cb < g.cblocks; ++cb) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_expect_tx(&a_full[as], HaloCfg::kABytes);
+            tma_load_4d(&maps.a[seg], &a_full[as], smem + as * HaloCfg::kABytes, cb * 64, x0 - 1, y0 - 1, n0);
+            if (++as == kAS) {
+              as = 0;
+              aph ^= 1;
+            }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              uint8_t* sb = smem_b + bs * HS::kBBytes;
+              mbar_expect_tx(&b_full[bs], HS::kBBytes);
+              if (g.b_mode == 1) {
+                tma_load_3d(&maps.b[seg], &b_full[bs], sb, cb * 64, nb * BN, 8 - tap);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_3d(&maps.b[seg], &b_full[bs], sb + j * 8192, nb * BN + j * 64, cb * 64, tap);
+              }
+              if (++bs == kBS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const bool b_mn = g.b_mode == 2;
+      const uint32_t idesc = make_idesc(1u, 0u, b_mn ? 1u : 0u, 128u, BN);
+      int as = 0, bs = 0, acs = 0;
+      uint32_t aph = 0, bph = 0, acph = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acs], acph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acs * BN;
+        uint32_t first = 0;
+        for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + as * HaloCfg::kABytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const int kh = tap / 3, kw = tap - kh * 3;
+            // tap window: starts (kh*16 + kw) 128-byte rows into the halo box; 8-row groups 2048 B apart
+            const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
+            // (the 128-byte swizzle XOR is taken from the absolute shared-memory address bits [7,10) -- measured in
+            // scripts/bringup.py::halo_conv: a start address that is not 1024-byte aligned needs NO base-offset field)
+            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 2048);
+            const uint32_t sb = smem_u32(smem_b + bs * HS::kBBytes);
+            const uint64_t bdesc = b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
+            const uint32_t badv = b_mn ? 128u : 2u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(k > 0));
+              first = 1;
+            }
+            umma_commit(&b_empty[bs]);
+            if (++bs == kBS) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == kAS) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acs]);
+        if (++acs == 2) {
+          acs = 0;
+          acph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    conv_epilogue_loop<BN, false>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+  if (g.flags & EPI_COLSUM)
     for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {
       const float t = colsum_s[c];
       if (t != 0.f) atomicAdd(g.colsum + c, t);

@@ -59,27 +59,30 @@ __device__ __forceinline__ void st_px(void* x, long long p, int C, int c, float 
 constexpr int kHeadTP = 32;    // pixels per CTA tile
 constexpr int kHeadKC = 128;   // input channels per shared-memory chunk (fwd)
 
-// fwd: CTA = 128 threads = 32 pixels x 4 class groups (classes q, q+4, ...).
+// fwd: CTA = 128 threads = 32 pixels x 4 class groups (classes q, q+4, ...); grid.y splits Cin into slices of kslice
+// channels (fc7: 4096 channels but only 2048 pixels); the slices write partial sums [slice][P][C] that
+// head_fwd_reduce_kernel adds in a fixed order (the forward pass stays bit-reproducible).
 template <int FMT>
 __global__ void __launch_bounds__(128)
 head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
-                float* __restrict__ s, long long P, int Cin, int C, float scale) {
+                float* __restrict__ s, long long P, int Cin, int C, float scale, int kslice) {
   __shared__ float xs[kHeadTP][kHeadKC + 1];
   __shared__ float Ks[kHeadKC][CMAX];
   const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
   const int pl = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const int kbeg = blockIdx.y * kslice, kend = min(Cin, kbeg + kslice);
   float acc[CMAX / 4];
 #pragma unroll
   for (int j = 0; j < CMAX / 4; ++j) acc[j] = 0.f;
-  for (int k0 = 0; k0 < Cin; k0 += kHeadKC) {
+  for (int k0 = kbeg; k0 < kend; k0 += kHeadKC) {
     __syncthreads();
     for (int i = threadIdx.x; i < kHeadTP * kHeadKC; i += 128) {
       const int r = i / kHeadKC, c = i % kHeadKC;
-      xs[r][c] = (p0 + r < P && k0 + c < Cin) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
+      xs[r][c] = (p0 + r < P && k0 + c < kend) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
     }
     for (int i = threadIdx.x; i < kHeadKC * C; i += 128) {
       const int r = i / C, c = i % C;
-      Ks[r][c] = (k0 + r < Cin) ? __ldg(K + static_cast<size_t>(k0 + r) * C + c) : 0.f;
+      Ks[r][c] = (k0 + r < kend) ? __ldg(K + static_cast<size_t>(k0 + r) * C + c) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
@@ -93,7 +96,18 @@ head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const f
   if (p0 + pl < P) {
 #pragma unroll
     for (int j = 0; j < CMAX / 4; ++j)
-      if (q + 4 * j < C) s[(p0 + pl) * C + q + 4 * j] = scale * acc[j] + b[q + 4 * j];
+      if (q + 4 * j < C) {
+        const float v = scale * acc[j] + (blockIdx.y == 0 ? b[q + 4 * j] : 0.f);
+        s[(static_cast<size_t>(blockIdx.y) * P + p0 + pl) * C + q + 4 * j] = v;   // gridDim.y == 1: s is the output
+      }
+  }
+}
+__global__ void head_fwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ s, size_t n, int slices) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < slices; ++k) a += part[k * n + i];
+    s[i] = a;
   }
 }
 
@@ -183,12 +197,27 @@ head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const
   }
 }
 
+// enough CTAs to fill the GPU: split Cin when there are few pixel tiles (fc7 at 1/32 resolution)
+int head_fwd_slices(long long P, int Cin) {
+  const long long blocks = (P + kHeadTP - 1) / kHeadTP;
+  int ksplit = 1;
+  while (blocks * ksplit < 2 * 148 && Cin / (ksplit * 2) >= 2 * kHeadKC) ksplit *= 2;
+  return ksplit;
+}
 cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
-                            float scale, int dtype, cudaStream_t st) {
+                            float scale, int dtype, float* ws, cudaStream_t st) {
   const int blocks = static_cast<int>((P + kHeadTP - 1) / kHeadTP);
-#define CALL(F) { count_launch(); head_fwd_kernel<F><<<blocks, 128, 0, st>>>(x, K, b, s, P, Cin, C, scale); }
+  const int ksplit = head_fwd_slices(P, Cin);
+  const int kslice = (Cin + ksplit - 1) / ksplit;
+  float* dst = ksplit > 1 ? ws : s;
+  dim3 grid(blocks, ksplit);
+#define CALL(F) { count_launch(); head_fwd_kernel<F><<<grid, 128, 0, st>>>(x, K, b, dst, P, Cin, C, scale, kslice); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
+  if (ksplit > 1) {
+    const size_t n = static_cast<size_t>(P) * C;
+    { count_launch(); head_fwd_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(ws, s, n, ksplit); }
+  }
   return cudaGetLastError();
 }
 int head_bwd_blocks(long long P) {
@@ -223,95 +252,77 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
 }
 
 // ------------------------------------------------------------------------------------------------ transposed conv
-// Phase decomposition: for stride s, kernel 2s, pad s/2, the output pixel (s*J - p + dy, s*I - p + dx)
-// of block (J, I), J in [0,h], I in [0,w], depends on the 2x2 inputs (J-1+ty, I-1+tx) through taps
-// a = dy + s*(1-ty), b = dx + s*(1-tx).  One CTA handles one phase (dy,dx): its 4 filter slices [4][C][C] live in
-// shared memory and every thread produces all C channels of one output pixel.
+// CUDA-core transposed convolution for the two small 2x stages (fcn8s_tensorflow.py:204-224; 0.13 GFLOP per c2
+// step, launch-latency-bound) -- the 8x stage runs on the tensor cores (fcn8_upscore_tc_*).  Output pixel (oy, ox)
+// = (s*J - p + dy, s*I - p + dx) depends on the 2x2 inputs (J-1+ty, I-1+tx) through taps a = dy + s*(1-ty),
+// b = dx + s*(1-tx).  One thread per output element (pixel, co); the filter sits in shared memory with
+// the ci rows padded to C+1 floats so that the co-strided reads are bank-conflict free.
 __global__ void upscore_fwd_kernel(const float* __restrict__ x, const float* __restrict__ T,
                                    const float* __restrict__ bias, const float* __restrict__ skip,
                                    float* __restrict__ y, int N, int h, int w, int C, int s) {
-  extern __shared__ float sT[];  // [4][C][C]  (tap = ty*2+tx, co, ci)
-  const int p = s / 2, k = 2 * s;
-  const int dy = blockIdx.y / s, dx = blockIdx.y % s;
-  for (int i = threadIdx.x; i < 4 * C * C; i += blockDim.x) {
-    const int tap = i / (C * C), r = i % (C * C);
-    const int ty = tap >> 1, tx = tap & 1;
-    const int a = dy + s * (1 - ty), b = dx + s * (1 - tx);
-    sT[i] = T[(static_cast<size_t>(a) * k + b) * C * C + r];
+  extern __shared__ float sT[];  // [k*k][C][C+1]  (a*k+b, co, ci)
+  const int p = s / 2, k = 2 * s, CP1 = C + 1;
+  for (int i = threadIdx.x; i < k * k * C * C; i += blockDim.x) {
+    const int ci = i % C, r = i / C;
+    sT[r * CP1 + ci] = T[i];
   }
   __syncthreads();
-  const int HB = h + 1, WB = w + 1;
   const int H = h * s, W = w * s;
-  const size_t total = static_cast<size_t>(N) * HB * WB;
+  const size_t total = static_cast<size_t>(N) * H * W * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int I = static_cast<int>(i % WB);
-    const int J = static_cast<int>((i / WB) % HB);
-    const int n = static_cast<int>(i / (static_cast<size_t>(WB) * HB));
-    const int oy = s * J - p + dy, ox = s * I - p + dx;
-    if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
-    float acc[CMAX];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) acc[c] = (c < C) ? bias[c] : 0.f;
+    const int co = static_cast<int>(i % C);
+    size_t r = i / C;
+    const int ox = static_cast<int>(r % W);
+    r /= W;
+    const int oy = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const int J = (oy + p) / s, dy = (oy + p) % s, I = (ox + p) / s, dx = (ox + p) % s;
+    float acc = bias[co];
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
-      const int iy = J - 1 + (tap >> 1), ix = I - 1 + (tap & 1);
+      const int ty = tap >> 1, tx = tap & 1;
+      const int iy = J - 1 + ty, ix = I - 1 + tx;
       if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
       const float* xp = x + ((static_cast<size_t>(n) * h + iy) * w + ix) * C;
-      const float* tp = sT + tap * C * C;
-      for (int ci = 0; ci < C; ++ci) {
-        const float xv = __ldg(xp + ci);
-#pragma unroll
-        for (int co = 0; co < CMAX; ++co)
-          if (co < C) acc[co] = fmaf(xv, tp[co * C + ci], acc[co]);
-      }
+      const float* tp = sT + (((dy + s * (1 - ty)) * k + dx + s * (1 - tx)) * C + co) * CP1;
+      for (int ci = 0; ci < C; ++ci) acc = fmaf(__ldg(xp + ci), tp[ci], acc);
     }
-    const size_t o = ((static_cast<size_t>(n) * H + oy) * W + ox) * C;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) y[o + c] = acc[c] + (skip ? skip[o + c] : 0.f);
+    y[i] = acc + (skip ? skip[i] : 0.f);
   }
 }
 
-// dx[n,i,j,ci] = sum_{a,b,co} dy[n, s*i+a-p, s*j+b-p, co] * T[a,b,co,ci]; one thread per input pixel, filter rows
-// staged through shared memory one `a` at a time.
+// dx[n,i,j,ci] = sum_{a,b,co} dy[n, s*i+a-p, s*j+b-p, co] * T[a,b,co,ci]; one thread per input element (pixel, ci),
+// the filter in shared memory (ci fastest: conflict-free), dy rows broadcast across the C threads of a pixel.
 __global__ void upscore_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ T, float* __restrict__ dx,
                                      int N, int h, int w, int C, int s) {
-  extern __shared__ float sT[];  // [k][C][C] for the current a
+  extern __shared__ float sT[];  // [k*k][C][C]
   const int p = s / 2, k = 2 * s;
+  for (int i = threadIdx.x; i < k * k * C * C; i += blockDim.x) sT[i] = T[i];
+  __syncthreads();
   const int H = h * s, W = w * s;
-  const size_t total = static_cast<size_t>(N) * h * w;
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const bool active = i < total;
-  const int jx = static_cast<int>(i % w);
-  const int iy = static_cast<int>((i / w) % h);
-  const int n = static_cast<int>(i / (static_cast<size_t>(w) * h));
-  float acc[CMAX];
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) acc[c] = 0.f;
-  for (int a = 0; a < k; ++a) {
-    __syncthreads();
-    for (int q = threadIdx.x; q < k * C * C; q += blockDim.x) sT[q] = T[static_cast<size_t>(a) * k * C * C + q];
-    __syncthreads();
-    const int oy = s * iy + a - p;
-    if (!active || oy < 0 || oy >= H) continue;
-    for (int b = 0; b < k; ++b) {
-      const int ox = s * jx + b - p;
-      if (ox < 0 || ox >= W) continue;
-      const float* dp = dy + ((static_cast<size_t>(n) * H + oy) * W + ox) * C;
-      const float* tp = sT + b * C * C;
-      for (int co = 0; co < C; ++co) {
-        const float g = __ldg(dp + co);
-#pragma unroll
-        for (int ci = 0; ci < CMAX; ++ci)
-          if (ci < C) acc[ci] = fmaf(g, tp[co * C + ci], acc[ci]);
+  const size_t total = static_cast<size_t>(N) * h * w * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % C);
+    size_t r = i / C;
+    const int jx = static_cast<int>(r % w);
+    r /= w;
+    const int iy = static_cast<int>(r % h);
+    const int n = static_cast<int>(r / h);
+    float acc = 0.f;
+    for (int a = 0; a < k; ++a) {
+      const int oy = s * iy + a - p;
+      if (oy < 0 || oy >= H) continue;
+      for (int b = 0; b < k; ++b) {
+        const int ox = s * jx + b - p;
+        if (ox < 0 || ox >= W) continue;
+        const float* dp = dy + ((static_cast<size_t>(n) * H + oy) * W + ox) * C;
+        const float* tp = sT + (a * k + b) * C * C + ci;
+        for (int co = 0; co < C; ++co) acc = fmaf(__ldg(dp + co), tp[co * C], acc);
       }
     }
-  }
-  if (active) {
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) dx[i * C + c] = acc[c];
+    dx[i] = acc;
   }
 }
 
@@ -375,13 +386,20 @@ __global__ void upscore_bwd_w_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+// the whole filter must fit in shared memory: k*k*C*(C+1) floats (27 KB for the 4x4 stages at C = 20; the 16x16 stage
+// at C = 20 needs 430 KB and is therefore only reachable through the tensor-core path or with few classes)
+static size_t upscore_smem_bytes(int C, int s, bool padded) {
+  return static_cast<size_t>(4) * s * s * C * (padded ? C + 1 : C) * sizeof(float);
+}
 cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias, const float* skip, float* y, int N,
                                int h, int w, int C, int s, cudaStream_t st) {
-  const size_t blocks_total = static_cast<size_t>(N) * (h + 1) * (w + 1);
-  int gx = grid_for(blocks_total, 128, (148 * 8) / (s * s) + 1);
-  dim3 grid(gx, s * s);
-  const size_t sm = static_cast<size_t>(4) * C * C * sizeof(float);
-  { count_launch(); upscore_fwd_kernel<<<grid, 128, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s); }
+  const size_t sm = upscore_smem_bytes(C, s, true);
+  if (sm > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(upscore_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(sm));
+  if (e != cudaSuccess) return e;
+  const size_t total = static_cast<size_t>(N) * h * s * w * s * C;
+  { count_launch(); upscore_fwd_kernel<<<grid_for(total, 256, 148 * 4), 256, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s); }
   return cudaGetLastError();
 }
 int upscore_bwd_splits(int N, int h, int w, int s) {
@@ -414,10 +432,11 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
     if (e != cudaSuccess) return e;
   }
   if (dx) {
-    const size_t total = static_cast<size_t>(N) * h * w;
-    const size_t sm = static_cast<size_t>(k) * C * C * sizeof(float);
+    const size_t total = static_cast<size_t>(N) * h * w * C;
+    const size_t sm = upscore_smem_bytes(C, s, false);
+    if (sm > 200 * 1024) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(upscore_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-    { count_launch(); upscore_bwd_x_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, sm, st>>>(dy, T, dx, N, h, w, C, s); }
+    { count_launch(); upscore_bwd_x_kernel<<<grid_for(total, 128, 148 * 8), 128, sm, st>>>(dy, T, dx, N, h, w, C, s); }
   }
   return cudaGetLastError();
 }
@@ -557,7 +576,7 @@ cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* lo
                                 float* sm, long long* amax, int N, int H, int W, int C, int CP, int pad, float gscale,
                                 cudaStream_t st) {
   const long long runs = static_cast<long long>(N) * H * ((W + kLossPix - 1) / kLossPix);
-  const int blocks = static_cast<int>(runs < 148 * 8 ? runs : 148 * 8);
+  const int blocks = static_cast<int>(runs < 148 * 16 ? runs : 148 * 16);   // 16 CTAs of 128 threads per SM
   const size_t smem = static_cast<size_t>(kLossPix) * CP * sizeof(float) + static_cast<size_t>(kLossPix) * C;
   { count_launch(); softmax_xent_kernel<<<blocks, kLossPix, smem, st>>>(z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
   return cudaGetLastError();

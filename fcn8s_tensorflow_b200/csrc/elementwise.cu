@@ -88,47 +88,58 @@ struct Act<2> {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ preprocess
-// One thread per 16-byte output vector (8 bf16 / 4 fp32 im2col columns).  KP = padded im2col width: one 128-byte
-// operand row (64 bf16 / 32 fp32 columns).
+// Feed kernel: uint8 RGB -> mean-subtracted BGR, emitted as conv1_1's im2col row per pixel (27 columns padded to KP =
+// one 128-byte operand row: 64 bf16 / 32 fp32 columns).  A CTA handles 128 consecutive pixels of one image row: the
+// three input rows (with a one-pixel halo, zeros outside the image = SAME padding applied AFTER the mean subtraction)
+// are staged in shared memory as floats; each thread then assembles its pixel's row with compile-time column indices.
 template <int FMT>
-__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, typename Act<FMT>::T* __restrict__ out, int N,
-                                         int H, int W) {
+__global__ void __launch_bounds__(128)
+preprocess_im2col_kernel(const uint8_t* __restrict__ img, typename Act<FMT>::T* __restrict__ out, int N, int H, int W) {
   using A = Act<FMT>;
   constexpr int VEC = A::N;
   constexpr int KP = FMT == 1 ? 32 : 64;
-  constexpr int VPP = KP / VEC;  // vectors per pixel (8)
-  const size_t total = static_cast<size_t>(N) * H * W * VPP;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % VPP);
-    const size_t pix = i / VPP;
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>((pix / W) % H);
-    const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
-    float f[VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const int col = v * VEC + e;
-      float val = 0.f;
-      if (col < 27) {
-        const int tap = col / 3, c = col - tap * 3;
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          // c = 0,1,2 -> B,G,R = RGB channel 2,1,0 minus the ImageNet means
-          const float mean = (c == 0) ? 103.939f : (c == 1 ? 116.779f : 123.68f);
-          val = static_cast<float>(img[((static_cast<size_t>(n) * H + yy) * W + xx) * 3 + (2 - c)]) - mean;
-        }
+  constexpr int TW = 128;
+  __shared__ float tile[3][TW + 2][3];
+  const int tiles_x = (W + TW - 1) / TW;
+  const long long total_tiles = static_cast<long long>(N) * H * tiles_x;
+  for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int x0 = static_cast<int>(t % tiles_x) * TW;
+    const int y = static_cast<int>((t / tiles_x) % H);
+    const int n = static_cast<int>(t / (static_cast<long long>(tiles_x) * H));
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (TW + 2) * 3; i += TW) {
+      const int c = i % 3, xx = (i / 3) % (TW + 2), r = i / (3 * (TW + 2));
+      const int gy = y + r - 1, gx = x0 + xx - 1;
+      float v = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        // c = 0,1,2 -> B,G,R = RGB channel 2,1,0 minus the ImageNet means
+        const float mean = (c == 0) ? 103.939f : (c == 1 ? 116.779f : 123.68f);
+        v = static_cast<float>(img[((static_cast<size_t>(n) * H + gy) * W + gx) * 3 + (2 - c)]) - mean;
       }
-      f[e] = val;
+      tile[r][xx][c] = v;
     }
-    A::store(out + pix * A::ld(KP) + v * VEC, KP, f);
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x < W) {
+      const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+#pragma unroll
+      for (int v = 0; v < KP / VEC; ++v) {
+        float f[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const int col = v * VEC + e;   // compile-time after unrolling
+          f[e] = col < 27 ? tile[col / 9][threadIdx.x + (col / 3) % 3][col % 3] : 0.f;
+        }
+        A::store(out + pix * A::ld(KP) + v * VEC, KP, f);
+      }
+    }
   }
 }
 
 cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
-  const size_t total = static_cast<size_t>(N) * H * W * 8;
-  const int blocks = grid_for(total, 256);
-#define CALL(F) { count_launch(); preprocess_im2col_kernel<F><<<blocks, 256, 0, st>>>(img, static_cast<typename Act<F>::T*>(out), N, H, W); }
+  const long long tiles = static_cast<long long>(N) * H * ((W + 127) / 128);
+  const int blocks = static_cast<int>(tiles < 148 * 16 ? tiles : 148 * 16);
+#define CALL(F) { count_launch(); preprocess_im2col_kernel<F><<<blocks, 128, 0, st>>>(img, static_cast<typename Act<F>::T*>(out), N, H, W); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -321,7 +332,7 @@ __global__ void colsum_stage2(const float* __restrict__ ws, float* __restrict__ 
 }
 
 int bias_grad_blocks(long long P, int C) {
-  long long nb = (P + 255) / 256;
+  long long nb = (P + 31) / 32;
   if (nb > 592) nb = 592;
   if (nb < 1) nb = 1;
   return static_cast<int>(nb);

@@ -35,8 +35,9 @@ cudaError_t launch_shadow(const float* p, void* hi, void* lo, size_t n, cudaStre
 cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st);
 
 // decoder.cu
+int head_fwd_slices(long long P, int Cin);
 cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
-                            float scale, int dtype, cudaStream_t st);
+                            float scale, int dtype, float* ws, cudaStream_t st);
 int head_bwd_blocks(long long P);
 cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, float* dK, float* db, void* dx,
                             long long P, int Cin, int C, float scale, int dtype, int mask, float mask_scale, float* ws,

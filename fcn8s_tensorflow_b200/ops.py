@@ -139,7 +139,7 @@ def split_tf32(x):
 
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
-              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None, seed_ptr=None):
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None, seed_ptr=None, algo=0):
     """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
     pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
     the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF
@@ -157,7 +157,7 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, 3, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
                             capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum),
-                            capi.ptr(seed_ptr))
+                            capi.ptr(seed_ptr), algo)
     else:
         dtype = dtype_of(x)
         if out is None:
@@ -166,7 +166,7 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
                             capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode,
-                            capi.ptr(colsum), capi.ptr(seed_ptr))
+                            capi.ptr(colsum), capi.ptr(seed_ptr), algo)
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
@@ -252,7 +252,10 @@ def score_head_fwd(x, K, b, scale, out=None, pair=False):
         out = torch.empty(tuple(x.shape[:-1]) + (Cc,), dtype=torch.float32, device=x.device)
     p = capi.HeadParams(capi.ptr(x), capi.ptr(K), capi.ptr(b), capi.ptr(out), None, None, None, P, cin, Cc, scale,
                         _fmt(x, pair), 0, 1.0)
-    capi.check(capi.load().fcn8_score_head_fwd(C.byref(p), _stream()))
+    lib = capi.load()
+    nbytes = lib.fcn8_score_head_fwd_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x.device) if nbytes else None
+    capi.check(lib.fcn8_score_head_fwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
     return out
 
 

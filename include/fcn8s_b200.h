@@ -108,6 +108,9 @@ typedef struct {
   int32_t w_mode;
   float* colsum;        /* FCN8_EPI_COLSUM target, [Cout] fp32 */
   const uint32_t* seed_ptr; /* optional device scalar: dropout seed = *seed_ptr * 2 + seed (see fcn8_set_step_scalars) */
+  int32_t algo;         /* 0 = heuristic; 1 = per-tap implicit GEMM; 2 = halo-tile kernel (3x3, bf16, w_mode 1/2: the
+                           activation patch of a tile is loaded once with its halo and the nine taps are shifted UMMA
+                           descriptors into it) */
 } Fcn8ConvParams;
 size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -196,7 +199,8 @@ typedef struct {
   int32_t mask;
   float mask_scale;
 } Fcn8HeadParams;
-int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* stream);
+size_t fcn8_score_head_fwd_workspace_bytes(const Fcn8HeadParams* p);
+int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream);
 size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p);
 int32_t fcn8_score_head_bwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream);
 

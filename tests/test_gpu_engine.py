@@ -179,27 +179,32 @@ def test_batch_independence_and_determinism(cuda_device, problem):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_cuda_graph_replay_matches_eager_steps(cuda_device, problem, precision):
-    """train_step captures the whole step into a CUDA graph after two eager steps; six steps with per-step learning
-    rates and dropout seeds must give the same parameters and losses as six eager steps (the bias-gradient and loss
-    reductions use atomics, so 'same' is to fp32 summation-order noise, not bitwise)."""
+    """train_step captures the whole step into a CUDA graph after two eager steps and replays it with the per-step
+    learning rate / dropout seed read from device memory.  Each step is compared with an eager engine that starts from
+    exactly the same state (training itself is chaotic: Adam turns a last-bit gradient difference from the atomic
+    bias-gradient / loss reductions into a full +-lr update, so states are re-synchronised before every step)."""
     x = torch.from_numpy(problem["images"]).to(cuda_device)
     y = torch.from_numpy(problem["labels"].view(np.uint8)).to(cuda_device)
     lrs = [1e-4, 1e-4, 3e-4, 1e-4, 5e-5, 2e-4]
-    out = {}
-    for graphs in (False, True):
-        e = make_engine(cuda_device, precision, problem["weights"])
-        e.use_graphs = graphs
-        losses = []
-        for lr in lrs:
-            e.train_step(x, y, lr, keep_prob=0.5, l2_rate=0.01)
-            losses.append(e.loss_value(x.shape))
+    eager = make_engine(cuda_device, precision, problem["weights"])
+    eager.use_graphs = False
+    graph = make_engine(cuda_device, precision, problem["weights"])
+    assert graph.use_graphs
+    for i, lr in enumerate(lrs):
+        for dst, src in ((graph.params, eager.params), (graph.adam_m, eager.adam_m), (graph.adam_v, eager.adam_v)):
+            dst.copy_(src)
+        graph.global_step = eager.global_step
+        graph._packed_dirty = graph._shadow_dirty = True
+        before = eager.params.clone()
+        eager.train_step(x, y, lr, keep_prob=0.5, l2_rate=0.01)
+        graph.train_step(x, y, lr, keep_prob=0.5, l2_rate=0.01)
         torch.cuda.synchronize()
-        assert (len(e._graphs) == 1) == graphs and (e.graph_launches > 0) == graphs
-        out[graphs] = (e.params.clone(), losses, e.global_step)
-    assert out[True][2] == out[False][2] == len(lrs)
-    tol = 1e-5 if precision == "fp32" else 2e-3   # bf16: a rounding-order flip of one bf16 activation is allowed
-    assert np.allclose(out[True][1], out[False][1], rtol=tol, atol=0)
-    assert rel_l2(out[True][0], out[False][0]) <= tol
+        le, lg = eager.loss_value(x.shape), graph.loss_value(x.shape)
+        assert abs(le - lg) <= 1e-5 * abs(le), (i, le, lg)
+        step = (eager.params - before).norm().item()
+        assert (graph.params - eager.params).norm().item() <= 1e-2 * step, i
+    assert len(graph._graphs) == 1 and graph.graph_launches > 0 and not eager._graphs
+    assert graph.global_step == eager.global_step == len(lrs)
 
 
 def test_kitti_two_class_shape(cuda_device):
