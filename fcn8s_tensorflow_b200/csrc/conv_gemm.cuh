@@ -119,7 +119,8 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kColsumBytes + 1024;  // +1024: manual alignment
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
+constexpr int kEpiWarps = 8;        // two epilogue warps per TMEM lane quarter, each takes half of the tile's columns
 
 template <bool TF32>
 __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -302,6 +303,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
                                                    uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
                                                    int warp, int lane) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
@@ -325,7 +327,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
@@ -396,7 +398,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -407,8 +409,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // ============================== TMA producer (whole warp, one elected lane issues) ==============================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -431,23 +433,26 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (g.a_mode == 0) {
-            tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
-          } else {
-            const int bdy = cb / g.blk_chunks;
-            tma_load_5d(&maps.a[seg], &full_bar[stage], sa, (cb - bdy * g.blk_chunks) * CH, x0 + g.pad - kw, bdy,
-                        y0 + g.pad - kh, n0);
-          }
-          if (g.b_mode == 0) {
-            tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
-          } else if (g.b_mode == 1) {
-            tma_load_3d(&maps.b[seg], &full_bar[stage], sb, cb * CH, nb * BN, g.taps - 1 - tap);
-          } else {
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (g.a_mode == 0) {
+              tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
+            } else {
+              const int bdy = cb / g.blk_chunks;
+              tma_load_5d(&maps.a[seg], &full_bar[stage], sa, (cb - bdy * g.blk_chunks) * CH, x0 + g.pad - kw, bdy,
+                          y0 + g.pad - kh, n0);
+            }
+            if (g.b_mode == 0) {
+              tma_load_2d(&maps.b[seg], &full_bar[stage], sb, (tap * g.cblocks + cb) * CH, nb * BN);
+            } else if (g.b_mode == 1) {
+              tma_load_3d(&maps.b[seg], &full_bar[stage], sb, cb * CH, nb * BN, g.taps - 1 - tap);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_3d(&maps.b[seg], &full_bar[stage], sb + j * 8192, nb * BN + j * 64, cb * CH, tap);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_3d(&maps.b[seg], &full_bar[stage], sb + j * 8192, nb * BN + j * 64, cb * CH, tap);
+            }
           }
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -471,46 +476,54 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const bool b_mn = g.b_mode == 2;  // B = [64 k][64 n] MN-major chunks (bf16 only)
-      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, b_mn ? 1u : 0u, 128u, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t / (g.tiles_n * m_tiles);
-        const int kb0 = sp * g.kb_per_split;
-        const int kb1 = min(total_kb, kb0 + g.kb_per_split);
-        mbar_wait(&acc_empty[as], aphase ^ 1);
+    // The WHOLE warp runs this loop: its control flow and every address / descriptor are then warp-uniform and live in
+    // uniform registers, and one elected lane issues the tcgen05 instructions.  (With the loop inside `if (lane == 0)`
+    // the compiler wraps every UTCHMMA operand in ELECT + R2UR.BROADCAST: ~600 cycles of issue overhead per k-block,
+    // measured with ncu's source view, which capped the tensor pipe at ~65 % for N = 256 and ~20 % for N = 64 tiles.)
+    const bool b_mn = g.b_mode == 2;  // B = [64 k][64 n] MN-major chunks (bf16 only)
+    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, b_mn ? 1u : 0u, 128u, BN);
+    // K-major B: 128-byte rows, +32 B per MMA; MN-major B: LBO = 8 KB between 64-wide N chunks, SBO = 1 KB between
+    // 8-row K groups, +16 K-rows (2 KB) per MMA
+    const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 1024);
+    const uint64_t bdesc0 = b_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+    const uint32_t badv = b_mn ? 128u : 2u;
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int sp = t / (g.tiles_n * m_tiles);
+      const int kb0 = sp * g.kb_per_split;
+      const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+      mbar_wait(&acc_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t adesc = make_smem_desc_sw128(sa, 16, 1024);
-          // K-major B: 128-byte rows, +32 B per MMA; MN-major B: LBO = 8 KB between 64-wide N chunks, SBO = 1 KB
-          // between 8-row K groups, +16 K-rows (2 KB) per MMA
-          const uint64_t bdesc = b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
-          const uint32_t badv = b_mn ? 128u : 2u;
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint64_t adesc = adesc0 | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+        const uint64_t bdesc = bdesc0 | static_cast<uint64_t>(((sa + Cfg::kABytes) & 0x3FFFF) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // A: advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
             umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&acc_full[as]);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&acc_full[as]);
+      __syncwarp();
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {
@@ -594,7 +607,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -605,8 +618,8 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // ============================== TMA producer (whole warp, one elected lane issues) ==============================
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -619,8 +632,11 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         for (int seg = 0; seg < g.nseg; ++seg) {
           for (int cb = 0; cb < g.cblocks; ++cb) {
             mbar_wait(&a_empty[as], aph ^ 1);
-            mbar_expect_tx(&a_full[as], HaloCfg::kABytes);
-            tma_load_4d(&maps.a[seg], &a_full[as], smem + as * HaloCfg::kABytes, cb * 64, x0 - 1, y0 - 1, n0);
+            if (elect_one()) {
+              mbar_expect_tx(&a_full[as], HaloCfg::kABytes);
+              tma_load_4d(&maps.a[seg], &a_full[as], smem + as * HaloCfg::kABytes, cb * 64, x0 - 1, y0 - 1, n0);
+            }
+            __syncwarp();
             if (++as == kAS) {
               as = 0;
               aph ^= 1;
@@ -628,14 +644,17 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               uint8_t* sb = smem_b + bs * HS::kBBytes;
-              mbar_expect_tx(&b_full[bs], HS::kBBytes);
-              if (g.b_mode == 1) {
-                tma_load_3d(&maps.b[seg], &b_full[bs], sb, cb * 64, nb * BN, 8 - tap);
-              } else {
+              if (elect_one()) {
+                mbar_expect_tx(&b_full[bs], HS::kBBytes);
+                if (g.b_mode == 1) {
+                  tma_load_3d(&maps.b[seg], &b_full[bs], sb, cb * 64, nb * BN, 8 - tap);
+                } else {
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                  tma_load_3d(&maps.b[seg], &b_full[bs], sb + j * 8192, nb * BN + j * 64, cb * 64, tap);
+                  for (int j = 0; j < BN / 64; ++j)
+                    tma_load_3d(&maps.b[seg], &b_full[bs], sb + j * 8192, nb * BN + j * 64, cb * 64, tap);
+                }
               }
+              __syncwarp();
               if (++bs == kBS) {
                 bs = 0;
                 bph ^= 1;
@@ -646,55 +665,64 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       }
     }
   } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      const bool b_mn = g.b_mode == 2;
-      const uint32_t idesc = make_idesc(1u, 0u, b_mn ? 1u : 0u, 128u, BN);
-      int as = 0, bs = 0, acs = 0;
-      uint32_t aph = 0, bph = 0, acph = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&acc_empty[acs], acph ^ 1);
+    // ============================== MMA issuer (whole warp, one elected lane issues) ==============================
+    const bool b_mn = g.b_mode == 2;
+    const uint32_t idesc = make_idesc(1u, 0u, b_mn ? 1u : 0u, 128u, BN);
+    const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 2048);
+    const uint64_t bdesc0 = b_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+    const uint32_t badv = b_mn ? 128u : 2u;
+    const uint32_t sa_base = smem_u32(smem), sb_base = smem_u32(smem_b);
+    int as = 0, bs = 0, acs = 0;
+    uint32_t aph = 0, bph = 0, acph = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      mbar_wait(&acc_empty[acs], acph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acs * BN;
+      uint32_t first = 0;
+      for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
+        mbar_wait(&a_full[as], aph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acs * BN;
-        uint32_t first = 0;
-        for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + as * HaloCfg::kABytes);
-          for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t sa = sa_base + as * HaloCfg::kABytes;
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
-            const int kh = tap / 3, kw = tap - kh * 3;
-            // tap window: starts (kh*16 + kw) 128-byte rows into the halo box; 8-row groups 2048 B apart
+            // tap window: starts (kh*16 + kw) 128-byte rows into the halo box; 8-row groups 2048 B apart.  (The
+            // 128-byte swizzle XOR is taken from the absolute shared-memory address bits [7,10) -- measured in
+            // scripts/bringup.py::halo_conv: a start that is not 1024-byte aligned needs NO base-offset field.)
             const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
-            // (the 128-byte swizzle XOR is taken from the absolute shared-memory address bits [7,10) -- measured in
-            // scripts/bringup.py::halo_conv: a start address that is not 1024-byte aligned needs NO base-offset field)
-            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 2048);
-            const uint32_t sb = smem_u32(smem_b + bs * HS::kBBytes);
-            const uint64_t bdesc = b_mn ? make_smem_desc_sw128(sb, 8192, 1024) : make_smem_desc_sw128(sb, 16, 1024);
-            const uint32_t badv = b_mn ? 128u : 2u;
+            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
+            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>(((sb_base + bs * HS::kBBytes) & 0x3FFFF) >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(k > 0));
-              first = 1;
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(k > 0));
+                first = 1;
+              }
+              umma_commit(&b_empty[bs]);
             }
-            umma_commit(&b_empty[bs]);
+            __syncwarp();
+            first = 1;
             if (++bs == kBS) {
               bs = 0;
               bph ^= 1;
             }
           }
-          umma_commit(&a_empty[as]);
-          if (++as == kAS) {
-            as = 0;
-            aph ^= 1;
-          }
         }
-        umma_commit(&acc_full[acs]);
-        if (++acs == 2) {
-          acs = 0;
-          acph ^= 1;
+        if (elect_one()) umma_commit(&a_empty[as]);
+        __syncwarp();
+        if (++as == kAS) {
+          as = 0;
+          aph ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&acc_full[acs]);
+      __syncwarp();
+      if (++acs == 2) {
+        acs = 0;
+        acph ^= 1;
       }
     }
   } else {
@@ -777,7 +805,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -788,7 +816,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // TMA producer: whole warp runs the uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -826,21 +854,25 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStage;
           uint8_t* sb = sa + kAStage;
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-          for (int c = 0; c < MCH; ++c)
-            if (c < nvalid)
-              tma_load_4d(&maps.a[seg], &full_bar[stage], sa + c * kChunkBytes, ccb[c], x0 + cdx[c], y0 + cdy[c], n0);
+            for (int c = 0; c < MCH; ++c)
+              if (c < nvalid)
+                tma_load_4d(&maps.a[seg], &full_bar[stage], sa + c * kChunkBytes, ccb[c], x0 + cdx[c], y0 + cdy[c], n0);
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) {
-            const int col = nb * BN + j * CH;
-            if (g.b_mode == 0) {
-              tma_load_4d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col, x0, y0, n0);
-            } else {
-              const int bdy = col / g.blk_row;
-              tma_load_5d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col - bdy * g.blk_row, x0, bdy, y0, n0);
+            for (int j = 0; j < NCH; ++j) {
+              const int col = nb * BN + j * CH;
+              if (g.b_mode == 0) {
+                tma_load_4d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col, x0, y0, n0);
+              } else {
+                const int bdy = col / g.blk_row;
+                tma_load_5d(&maps.b[seg], &full_bar[stage], sb + j * kChunkBytes, col - bdy * g.blk_row, x0, bdy, y0,
+                            n0);
+              }
             }
           }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -849,48 +881,53 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int sp = t / (g.tiles_n * g.m_tiles);
-        const int pb0 = sp * g.pb_per_split;
-        const int pb1 = min(total_pb, pb0 + g.pb_per_split);
-        mbar_wait(&acc_empty[as], aphase ^ 1);
+    // MMA issuer: whole warp runs the uniform loop, one elected lane issues (see conv_gemm_kernel)
+    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, BN);
+    // MN-major, 128B swizzle: LBO = stride between 128-byte channel chunks, SBO = stride between 8-pixel groups
+    // (tf32: 32-byte-granule swizzle, 4-pixel / 512-byte atoms -- the only MN-major layout the tf32 MMA accepts)
+    const uint64_t desc0 = make_smem_desc_sw128(0, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int sp = t / (g.tiles_n * g.m_tiles);
+      const int pb0 = sp * g.pb_per_split;
+      const int pb1 = min(total_pb, pb0 + g.pb_per_split);
+      mbar_wait(&acc_empty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int pb = pb0; pb < pb1; ++pb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int pb = pb0; pb < pb1; ++pb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStage);
-          const uint32_t sb = sa + kAStage;
-          // MN-major, 128B swizzle: LBO = stride between 128-byte channel chunks, SBO = stride between 8-pixel groups
-          // (tf32: 32-byte-granule swizzle, 4-pixel / 512-byte atoms -- the only MN-major layout the tf32 MMA accepts)
-          const uint64_t adesc = make_smem_desc_sw128(sa, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
-          const uint64_t bdesc = make_smem_desc_sw128(sb, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
+        const uint32_t sa = smem_base + stage * kStage;
+        const uint64_t adesc = desc0 | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+        const uint64_t bdesc = desc0 | static_cast<uint64_t>(((sa + kAStage) & 0x3FFFF) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 64 / KPM; ++k) {
             const uint32_t adv = (k * KPM * 128) >> 4;
             umma_issue<TF32>(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&acc_full[as]);
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&acc_full[as]);
+      __syncwarp();
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
@@ -907,7 +944,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
                                            : g.out + static_cast<size_t>(grow) * g.ldc;
       const bool valid = (g.flags & EPI_PARTIAL) ? true : (grow < g.rows_valid);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
