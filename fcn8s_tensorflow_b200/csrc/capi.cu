@@ -87,12 +87,12 @@ int encode_w_map(CUtensorMap* m, const void* ptr, int dtype, int rows, int ktot,
 }
 
 // bf16 weight tensor in TF layout [taps][Cin_w][Cout_w] as dims (co, ci, tap); box (64 co, box_ci, 1).
-int encode_hwio_map(CUtensorMap* m, const void* ptr, int taps, int cin_w, int cout_w, int box_ci) {
+int encode_hwio_map(CUtensorMap* m, const void* ptr, int taps, int cin_w, int cout_w, int box_ci, int box_taps = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const cuuint64_t dims[3] = {(cuuint64_t)cout_w, (cuuint64_t)cin_w, (cuuint64_t)taps};
   const cuuint64_t strides[2] = {(cuuint64_t)cout_w * 2, (cuuint64_t)cin_w * cout_w * 2};
-  const cuuint32_t box[3] = {64, (cuuint32_t)box_ci, 1};
+  const cuuint32_t box[3] = {64, (cuuint32_t)box_ci, (cuuint32_t)box_taps};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -229,7 +229,8 @@ cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
 template <int BN, bool TF32>
 constexpr int wgrad_smem_bytes() {
   constexpr int CH = TF32 ? 32 : 64;
-  constexpr int stage = (128 / CH) * 8192 + (BN / CH) * 8192;
+  constexpr int chunk = WgradPix<BN, TF32>::value * 128;
+  constexpr int stage = (128 / CH) * chunk + (BN / CH) * chunk;
   constexpr int stages = (200 * 1024) / stage;
   return stages * stage + 1024 + 1024;
 }
@@ -305,7 +306,8 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   const int mch = 128 / CH;
   pl->m_tiles = (pl->total_chunks + mch - 1) / mch;
   pl->rows_pad = (size_t)pl->m_tiles * 128;
-  choose_patch(p->N, p->H, p->W, 6, &pl->lbw, &pl->lbh, &pl->lbn);
+  const int pix_log = (p->dtype == FCN8_BF16 && bn <= 128) ? 7 : 6;   // = log2(WgradPix<BN, TF32>::value)
+  choose_patch(p->N, p->H, p->W, pix_log, &pl->lbw, &pl->lbh, &pl->lbn);
   pl->pb_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->pb_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
   pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
@@ -413,9 +415,9 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     if (p->w_mode == 0)
       rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
     else if (p->w_mode == 1)
-      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64);
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64, use_halo && pl.BN == 64 ? 3 : 1);
     else
-      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, pl.BN);
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, pl.BN, use_halo && pl.BN == 64 ? 3 : 1);
     if (rc) return rc;
   }
   ConvGemmArgs a;

@@ -559,8 +559,11 @@ struct HaloCfg {
 };
 template <int BN>
 struct HaloSmem {
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  // filter taps per B pipeline stage: the three kw taps of one kh row for the narrow N = 64 tiles (12 MMAs per barrier
+  // round trip instead of 4: the MMA time of a single 128x64x64 stage is shorter than the issue + wait overhead)
+  static constexpr int kTaps = (BN == 64) ? 3 : 1;
+  static constexpr int kBBytes = kTaps * BN * 128;
+  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 4);
   static constexpr int kBarBytes = 1024;
   static constexpr int kBytes =
       HaloCfg::kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumMax * 4 + 1024;
@@ -641,17 +644,19 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
               as = 0;
               aph ^= 1;
             }
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < 9; tap += HS::kTaps) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               uint8_t* sb = smem_b + bs * HS::kBBytes;
               if (elect_one()) {
                 mbar_expect_tx(&b_full[bs], HS::kBBytes);
                 if (g.b_mode == 1) {
-                  tma_load_3d(&maps.b[seg], &b_full[bs], sb, cb * 64, nb * BN, 8 - tap);
+                  // rotated taps 8-tap ... 8-tap-(kTaps-1): one box starting at the lowest of them (slots are then in
+                  // ascending filter-tap order, i.e. descending kw -- see the MMA loop)
+                  tma_load_3d(&maps.b[seg], &b_full[bs], sb, cb * 64, nb * BN, 8 - tap - (HS::kTaps - 1));
                 } else {
 #pragma unroll
                   for (int j = 0; j < BN / 64; ++j)
-                    tma_load_3d(&maps.b[seg], &b_full[bs], sb + j * 8192, nb * BN + j * 64, cb * 64, tap);
+                    tma_load_3d(&maps.b[seg], &b_full[bs], sb + j * (HS::kTaps * 8192), nb * BN + j * 64, cb * 64, tap);
                 }
               }
               __syncwarp();
@@ -669,7 +674,8 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     const bool b_mn = g.b_mode == 2;
     const uint32_t idesc = make_idesc(1u, 0u, b_mn ? 1u : 0u, 128u, BN);
     const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 2048);
-    const uint64_t bdesc0 = b_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+    // MN-major B (fprop): the 64-wide N chunks of a tap are kTaps * 8 KB apart (LBO) when a stage holds several taps
+    const uint64_t bdesc0 = b_mn ? make_smem_desc_sw128(0, HS::kTaps * 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
     const uint32_t badv = b_mn ? 128u : 2u;
     const uint32_t sa_base = smem_u32(smem), sb_base = smem_u32(smem_b);
     int as = 0, bs = 0, acs = 0;
@@ -686,19 +692,28 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 #pragma unroll 1
         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
+          for (int kw0 = 0; kw0 < 3; kw0 += HS::kTaps) {
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
-            // tap window: starts (kh*16 + kw) 128-byte rows into the halo box; 8-row groups 2048 B apart.  (The
-            // 128-byte swizzle XOR is taken from the absolute shared-memory address bits [7,10) -- measured in
-            // scripts/bringup.py::halo_conv: a start that is not 1024-byte aligned needs NO base-offset field.)
-            const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
-            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
-            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>(((sb_base + bs * HS::kBBytes) & 0x3FFFF) >> 4);
+            const uint32_t sb = sb_base + bs * HS::kBBytes;
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(k > 0));
+              for (int j = 0; j < HS::kTaps; ++j) {
+                const int kw = kw0 + j;
+                // tap window: starts (kh*16 + kw) 128-byte rows into the halo box; 8-row groups 2048 B apart.  (The
+                // 128-byte swizzle XOR is taken from the absolute shared-memory address bits [7,10) -- measured in
+                // scripts/bringup.py::halo_conv: a start that is not 1024-byte aligned needs NO base-offset field.)
+                const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
+                const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
+                // slot of this tap inside the stage: fprop boxes hold taps in order; dgrad boxes hold the rotated taps
+                // in ascending filter order, i.e. kw descending
+                const int slot = b_mn ? j : (HS::kTaps - 1 - j);
+                const uint32_t b_addr = sb + static_cast<uint32_t>(slot) * (b_mn ? 8192u : static_cast<uint32_t>(BN) * 128u);
+                const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(j + k > 0));
+                }
                 first = 1;
               }
               umma_commit(&b_empty[bs]);
@@ -766,11 +781,19 @@ struct WgradArgs {
 };
 
 template <int BN, bool TF32>
+struct WgradPix {
+  static constexpr int value = (!TF32 && BN <= 128) ? 128 : 64;
+};
+
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
   using Cfg = GemmCfg<BN>;
   constexpr int CH = TF32 ? 32 : 64;
-  constexpr int kChunkBytes = 64 * 128;        // 64 pixels x 128 B
+  // pixels (K) per pipeline stage: 128 for the narrow bf16 tiles, whose per-stage MMA time would otherwise be shorter
+  // than the issue + barrier round trip of a stage; 64 where shared memory is tight (BN = 256) and for tf32
+  constexpr int PIX = WgradPix<BN, TF32>::value;
+  constexpr int kChunkBytes = PIX * 128;       // PIX pixels x 128 B
   constexpr int MCH = 128 / CH;                // A chunks per M tile
   constexpr int NCH = BN / CH;                 // B chunks per N tile
   constexpr int kAStage = MCH * kChunkBytes;   // 16 KB bf16 / 32 KB tf32
@@ -906,7 +929,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
         const uint64_t bdesc = desc0 | static_cast<uint64_t>(((sa + kAStage) & 0x3FFFF) >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 64 / KPM; ++k) {
+          for (int k = 0; k < PIX / KPM; ++k) {
             const uint32_t adv = (k * KPM * 128) >> 4;
             umma_issue<TF32>(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
           }
