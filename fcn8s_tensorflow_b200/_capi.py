@@ -22,7 +22,7 @@ EXPORTS = [
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
     "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
-    "fcn8_set_step_scalars",
+    "fcn8_set_step_scalars", "fcn8_set_sm_limit",
 ]
 
 
@@ -118,6 +118,7 @@ def load():
     lib.fcn8_device_check.argtypes = [C.c_int32]
     lib.fcn8_launch_count.restype = C.c_uint64
     lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
+    lib.fcn8_set_sm_limit.argtypes = [C.c_int32]
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
                      ("fcn8_score_head_fwd", HeadParams), ("fcn8_score_head_bwd", HeadParams),

@@ -125,6 +125,7 @@ void choose_patch(int N, int H, int W, int total_log, int* lbw, int* lbh, int* l
     }
 }
 
+int g_sm_limit = 0;  // fcn8_set_sm_limit: persistent GEMM grids leave SMs free for a co-running collective
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -133,7 +134,7 @@ int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 struct ConvPlan {
@@ -345,6 +346,10 @@ int32_t fcn8_device_check(int32_t dev) {
   return 0;
 }
 uint64_t fcn8_launch_count(void) { return g_launch_count; }
+int32_t fcn8_set_sm_limit(int32_t n) {
+  g_sm_limit = n > 0 ? n : 0;
+  return 0;
+}
 int32_t fcn8_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
   g_debug[key] = value;

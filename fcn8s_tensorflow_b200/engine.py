@@ -150,6 +150,8 @@ class Engine:
         self._warm = {}
         self.graph_launches = 0     # kernels launched through graph replays (fcn8_launch_count() does not see those)
         self.head_elems = self.layout["conv5_3/filter"][0]   # [decoder | fc7 W | fc6 W] prefix of the flat buffer
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.dp_reserve_sms = int(os.environ.get("FCN8_DP_RESERVE_SMS", "0"))
 
     # ------------------------------------------------------------------ parameters
     def view(self, name, buf=None):
@@ -403,6 +405,8 @@ class Engine:
                 # decoder, fc7 and fc6 gradients (89 % of the buffer) are final: reduce them under the conv backward
                 self.allreduce.start(G[:self.head_elems])
                 self._reduced_upto = self.head_elems
+                if self.dp_reserve_sms > 0:   # leave SMs to the collective's CTAs while it runs under the backward
+                    self.lib.fcn8_set_sm_limit(self.sm_count - self.dp_reserve_sms)
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
             prev_db = self.view(prev_name + "/biases", G)
@@ -429,6 +433,8 @@ class Engine:
                 ops.conv_gemm(dyh, wh, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
                               colsum=prev_db, **wkw)
                 dy = dx
+        if self.dp_reserve_sms > 0:
+            self.lib.fcn8_set_sm_limit(0)
         return self.loss_buf
 
     def _input_is_pool(self, li):

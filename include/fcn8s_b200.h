@@ -61,6 +61,10 @@ const char* fcn8_last_error(void);
 int32_t fcn8_device_check(int32_t dev);
 /* number of CUDA kernels this library has launched in this process so far (what bench.py reports as gpu_launches). */
 uint64_t fcn8_launch_count(void);
+/* Persistent GEMM kernels launch min(tiles, #SMs) CTAs with static round-robin tile assignment; while a collective
+ * (the overlapped gradient all-reduce) occupies some SMs, n > 0 caps the grids at n CTAs so that no CTA has to wait for
+ * an SM and run a whole second wave.  n = 0 restores the device's SM count.  Affects launches issued afterwards. */
+int32_t fcn8_set_sm_limit(int32_t n);
 /* bring-up knobs (descriptor variants) -- tests only. */
 int32_t fcn8_debug_set(int32_t key, int32_t value);
 
