@@ -231,6 +231,21 @@ def time_engine(precision, weights, args, rank, local_rank, world, dev):
     return out
 
 
+def ncu_traffic(precision):
+    """DRAM bytes per step of the dominant kernel family from the committed ncu metrics pass (profiles/): sum of
+    dram__bytes_read.sum + dram__bytes_write.sum over the step's conv_gemm_kernel / conv_halo_kernel launches of the
+    encoder (bf16 operand instantiations).  None when the profile is missing or was taken in another mode."""
+    path = os.path.join(ROOT, "profiles", "r01_step_kernels_v2.json")
+    if not os.path.exists(path):
+        return None, None
+    d = json.load(open(path)).get(precision)
+    if not d:
+        return None, None
+    tot = sum(v["dram_bytes"] for k, v in d.items()
+              if (k.startswith("conv_gemm_kernel") and k.endswith(", 0>")) or k.startswith("conv_halo_kernel"))
+    return tot, "profiles/r01_step_kernels_v2.json"
+
+
 def line_for(precision, r, args, world, peaks):
     n_img = world * PER_GPU_BATCH * args.steps
     value = n_img / (r["ms"] * 1e-3)
@@ -246,9 +261,12 @@ def line_for(precision, r, args, world, peaks):
         "value": value, "ms_per_step": r["ms"] / args.steps, "dtype": dtype,
         "gpu_launches": int(r["launches"]),
         "roofline": {
-            "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM fprop + dgrad, all tile widths)",
+            "bound": "tensor", "kernel": "conv_gemm_kernel + conv_halo_kernel (tcgen05 implicit-GEMM fprop + dgrad of the "
+                                         "encoder, all tile widths)",
             "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-            "traffic": None, "peak_source": peaks["source"],
+            "traffic": ncu_traffic(precision)[0], "traffic_unit": "DRAM bytes per step over the same launches "
+                                                                  "(ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": ncu_traffic(precision)[1], "peak_source": peaks["source"],
             "launches_timed": k["launches"], "kernel_ms_per_step": k["ms"] / ksteps,
             "share_of_step": k["ms"] / ksteps / step_ms,
             "note": "achieved = algorithmic 2*M*N*K FLOPs of the launches / their CUDA-event time on the launching "
