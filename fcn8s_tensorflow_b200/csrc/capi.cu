@@ -307,7 +307,7 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   const int mch = 128 / CH;
   pl->m_tiles = (pl->total_chunks + mch - 1) / mch;
   pl->rows_pad = (size_t)pl->m_tiles * 128;
-  const int pix_log = (p->dtype == FCN8_BF16 && bn <= 128) ? 7 : 6;   // = log2(WgradPix<BN, TF32>::value)
+  const int pix_log = p->dtype == FCN8_BF16 ? 7 : 6;   // = log2(WgradPix<BN, TF32>::value)
   choose_patch(p->N, p->H, p->W, pix_log, &pl->lbw, &pl->lbh, &pl->lbn);
   pl->pb_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->pb_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;

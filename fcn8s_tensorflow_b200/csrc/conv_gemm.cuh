@@ -782,7 +782,7 @@ struct WgradArgs {
 
 template <int BN, bool TF32>
 struct WgradPix {
-  static constexpr int value = (!TF32 && BN <= 128) ? 128 : 64;
+  static constexpr int value = !TF32 ? 128 : 64;
 };
 
 template <int BN, bool TF32>

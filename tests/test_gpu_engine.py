@@ -207,6 +207,30 @@ def test_cuda_graph_replay_matches_eager_steps(cuda_device, problem, precision):
     assert graph.global_step == eager.global_step == len(lrs)
 
 
+def test_full_size_logits_and_loss_parity(cuda_device):
+    """BASELINE configs[1] geometry (512x1024, 20 classes; one image so that the fp64 CPU oracle finishes in well
+    under a minute): logits of the main-line precision within the north-star's 1e-4 of the CPU graph, loss within 1e-4,
+    and batch independence at full size (image 0 of a batch of 2 equals the single-image run)."""
+    Cc, Hh, Ww = 20, 512, 1024
+    w = oracle.init_weights(Cc, seed=2, decoder_std_scale=10.0)
+    images, labels = oracle.synthetic_batch(2, Hh, Ww, Cc, seed=7)
+    with torch.no_grad():
+        ref = oracle.forward(w, images[:1], dtype=torch.float64)
+        ref_loss = float(oracle.loss_from_logits({k: v.double() for k, v in w.items()}, ref, labels[:1]))
+    e = make_engine(cuda_device, "fp32", w, classes=Cc)
+    x = torch.from_numpy(images).to(cuda_device)
+    y = torch.from_numpy(labels.view(np.uint8)).to(cuda_device)
+    e.loss_and_backward(x[:1].contiguous(), y[:1].contiguous(), keep_prob=1.0)
+    torch.cuda.synchronize()
+    one = e._arena(1, Hh, Ww)["logits"].clone()
+    err = rel(one, ref)
+    print("full-size logits max-rel %.3e" % err)
+    assert err <= 1e-4, err
+    assert abs(e.loss_value((1, Hh, Ww)) - ref_loss) <= 1e-4 * abs(ref_loss)
+    both = e.forward(x)
+    assert rel(both[0], one[0]) <= 1e-6
+
+
 def test_kitti_two_class_shape(cuda_device):
     """BASELINE config 5 geometry (KITTI road, 2 classes) at a x32 size, labels [bg, ~bg] as
     batch_generator_KITTI.py:82-84 builds them."""
