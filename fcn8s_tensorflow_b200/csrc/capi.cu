@@ -192,6 +192,19 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
     const int max_by_k = pl->total_kb / 16 > 0 ? pl->total_kb / 16 : 1;  // keep >= 16 k-blocks per split
     if (splits > max_by_k) splits = max_by_k;
     if (splits > 16) splits = 16;
+  } else if (pl->total_kb >= 256 && (size_t)p->N * p->H * p->W * p->Cout * sizeof(float) * 4 <= (160u << 20)) {
+    // deep reductions with a small output (fc6: K = 25 088, 256 tiles = 1.73 waves): a 2..4-way split-K evens out
+    // the last wave (86 % -> 99 % of the SMs busy) for ~0.3 GB of partial traffic, and shortens the round-toward-zero
+    // accumulation chains of the TMEM accumulators fourfold
+    double best_eff = (double)tiles / (double)(((tiles + sms - 1) / sms) * sms);
+    for (int s2 = 2; s2 <= 4; ++s2) {
+      const long long items = tiles * s2;
+      const double eff = (double)items / (double)(((items + sms - 1) / sms) * sms);
+      if (eff > best_eff + 0.08) {
+        best_eff = eff;
+        splits = s2;
+      }
+    }
   }
   if (splits > pl->total_kb) splits = pl->total_kb;
   pl->kb_per_split = (pl->total_kb + splits - 1) / splits;
@@ -453,6 +466,11 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.flags = p->flags & (31 | 64 | 128);
   a.colsum = p->colsum;
   a.seed_ptr = p->seed_ptr;
+  {
+    // MMAs accumulated into one TMEM accumulator: 4 per k-block of 128 operand bytes
+    const int kb_acc = use_halo ? p->nseg * 9 * (p->Cin / 64) : pl.kb_per_split;
+    a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)kb_acc * kRzBiasPerMma;
+  }
   const int out_ld = p->out_ld > 0 ? p->out_ld : p->Cout;
   a.osW = out_ld;
   a.osH = (long long)p->W * out_ld;
@@ -561,6 +579,11 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   a.splits = pl.splits;
   a.pb_per_split = pl.pb_per_split;
   a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
+  {
+    const int pix = 1 << (pl.lbw + pl.lbh + pl.lbn);
+    const int mma_per_pb = pix / (p->dtype == FCN8_BF16 ? 16 : 8);
+    a.acc_scale = g_debug[0] ? 1.f : 1.f + (float)mma_per_pb * (float)pl.pb_per_split * kRzBiasPerMma;
+  }
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
@@ -836,6 +859,7 @@ int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream) {
   a.tiles_n = ncols / BN;
   a.splits = 1;
   a.kb_per_split = p->nseg * 4;
+  a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)a.kb_per_split * kRzBiasPerMma;
   a.flags = EPI_BIAS;
   a.out_mode = 1;
   a.blk_row = s * CP;
@@ -892,6 +916,7 @@ int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream) {
   a.tiles_n = 1;
   a.splits = 1;
   a.kb_per_split = p->nseg * 4 * cblocks;
+  a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)a.kb_per_split * kRzBiasPerMma;
   a.flags = 0;
   a.a_mode = 1;
   a.blk_chunks = chunks_row;
@@ -989,6 +1014,7 @@ int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t
   a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
   a.b_mode = 1;
   a.blk_row = s * CP;
+  a.acc_scale = g_debug[0] ? 1.f : 1.f + 8.f * (float)pl.pb_per_split * kRzBiasPerMma;   // 64 px / 8 per tf32 MMA
   const long long tiles = (long long)pl.tiles_n * pl.splits;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;

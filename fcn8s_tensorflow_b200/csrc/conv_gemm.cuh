@@ -100,7 +100,12 @@ struct ConvGemmArgs {
   // Per-step dropout seed in device memory (CUDA-graph replays cannot change kernel arguments):
   // effective seed = *seed_ptr * 2 + seed when seed_ptr != nullptr.
   const uint32_t* seed_ptr;
+  // Round-toward-zero compensation: the TMEM accumulator truncates on every tcgen05.mma, an expected relative loss of
+  // kRzBiasPerMma per accumulation step given the final value (measured, scripts/bringup.py::rz_accumulation_probe).
+  // acc_scale = 1 + (MMAs accumulated into one accumulator) * kRzBiasPerMma multiplies the accumulator in the epilogue.
+  float acc_scale;
 };
+constexpr float kRzBiasPerMma = 2.1e-8f;
 
 struct TensorMaps3 {
   CUtensorMap a[3];
@@ -159,7 +164,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * g.acc_scale;
   if (!valid) {  // rows outside the tensor take part only in the (warp-collective) column sums, as zeros
     if (g.flags & EPI_COLSUM) {
 #pragma unroll
@@ -338,8 +343,9 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
             float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              o4[i] = make_float4(__uint_as_float(v[4 * i]) * g.acc_scale, __uint_as_float(v[4 * i + 1]) * g.acc_scale,
+                                  __uint_as_float(v[4 * i + 2]) * g.acc_scale,
+                                  __uint_as_float(v[4 * i + 3]) * g.acc_scale);
           }
         } else {
           size_t idx = row_off + c0;
@@ -778,6 +784,7 @@ struct WgradArgs {
   // b_mode 1: dY is the padded, blocked output gradient of a transposed convolution (5-D map (s*CP, Wb, s, Hb, N));
   // output column c = (dy, dx, co) reads row dy = c / blk_row, element c % blk_row of the blocks.
   int b_mode, blk_row;
+  float acc_scale;  // round-toward-zero compensation of the TMEM accumulation (see ConvGemmArgs::acc_scale)
 };
 
 template <int BN, bool TF32>
@@ -975,8 +982,9 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
           float4* o4 = reinterpret_cast<float4*>(dst + nb * BN + c);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            o4[i] = make_float4(__uint_as_float(v[4 * i]) * g.acc_scale, __uint_as_float(v[4 * i + 1]) * g.acc_scale,
+                                __uint_as_float(v[4 * i + 2]) * g.acc_scale,
+                                __uint_as_float(v[4 * i + 3]) * g.acc_scale);
         }
       }
       tc_fence_before();

@@ -228,7 +228,8 @@ def test_full_size_logits_and_loss_parity(cuda_device):
     assert err <= 1e-4, err
     assert abs(e.loss_value((1, Hh, Ww)) - ref_loss) <= 1e-4 * abs(ref_loss)
     both = e.forward(x)
-    assert rel(both[0], one[0]) <= 1e-6
+    # a different batch size changes the tile / split-K plan (other accumulation grouping), not the image's result
+    assert rel(both[0], one[0]) <= 5e-5
 
 
 def test_kitti_two_class_shape(cuda_device):
