@@ -51,6 +51,29 @@ def synthetic_weights(num_classes, seed=2, decoder_std_scale=1.0):
     return out
 
 
+def check_images(images):
+    """The `image_input` feed (fcn8s_tensorflow.py:558,686,765): uint8-valued RGB [n,H,W,3]; a list of [H,W,3] arrays is
+    accepted like `sess.run` accepts it.  uint8 arrays pass through without a copy."""
+    a = np.asarray(images)
+    if a.ndim != 4 or a.shape[-1] != 3:
+        raise ValueError("images must have shape (batch, height, width, 3), got %s" % (a.shape,))
+    if a.dtype != np.uint8:
+        a = np.clip(np.rint(a), 0, 255).astype(np.uint8)
+    return a
+
+
+def check_labels(labels, num_classes):
+    """The `labels_input` feed (:110,559): one-hot [n,H,W,C], bool as the generators yield it
+    (helpers/ground_truth_conversion_utils.py:84-88, batch_generator_KITTI.py:82-84) or any 0/1 integer type."""
+    a = np.asarray(labels)
+    if a.ndim != 4 or a.shape[-1] != num_classes:
+        raise ValueError("labels must be one-hot with shape (batch, height, width, %d), got %s"
+                         % (num_classes, a.shape,))
+    if a.dtype != np.bool_ and a.dtype != np.uint8:
+        a = a.astype(np.uint8)
+    return a
+
+
 def _load_npz_weights(path, num_classes):
     if os.path.isdir(path):
         cands = [os.path.join(path, f) for f in ("variables.npz", "vgg16_weights.npz", "weights.npz")]
@@ -139,21 +162,10 @@ class FCN8s:
         return dev
 
     def _check_images(self, images):
-        a = np.asarray(images)
-        if a.ndim != 4 or a.shape[-1] != 3:
-            raise ValueError("images must have shape (batch, height, width, 3), got %s" % (a.shape,))
-        if a.dtype != np.uint8:
-            a = np.clip(np.rint(a), 0, 255).astype(np.uint8)
-        return a
+        return check_images(images)
 
     def _check_labels(self, labels):
-        a = np.asarray(labels)
-        if a.ndim != 4 or a.shape[-1] != self.num_classes:
-            raise ValueError("labels must be one-hot with shape (batch, height, width, %d), got %s"
-                             % (self.num_classes, a.shape,))
-        if a.dtype != np.bool_ and a.dtype != np.uint8:
-            a = a.astype(np.uint8)
-        return a
+        return check_labels(labels, self.num_classes)
 
     def _images_to_device(self, images):
         return self._to_device(self._check_images(images), "images")

@@ -207,6 +207,26 @@ def test_cuda_graph_replay_matches_eager_steps(cuda_device, problem, precision):
     assert graph.global_step == eager.global_step == len(lrs)
 
 
+@pytest.mark.parametrize("shape", [(3, 96, 224), (1, 160, 32)])
+def test_ragged_shapes_logits_and_gradients(cuda_device, shape):
+    """Odd batch size and image sizes that are not multiples of the 128-pixel GEMM tiles (ragged tiles in every layer,
+    halo tiles cut by the border, split-K plans that differ from the other tests'): logits and all 42 gradients."""
+    n, h, w_ = shape
+    w = oracle.init_weights(C, seed=11, decoder_std_scale=10.0)
+    images, labels = oracle.synthetic_batch(n, h, w_, C, seed=3)
+    loss, logits, grads = oracle.loss_and_grads(w, images, labels, dtype=torch.float64)
+    e = make_engine(cuda_device, "fp32", w)
+    x = torch.from_numpy(images).to(cuda_device)
+    y = torch.from_numpy(labels.view(np.uint8)).to(cuda_device)
+    e.loss_and_backward(x, y, keep_prob=1.0)
+    torch.cuda.synchronize()
+    assert rel(e._arena(n, h, w_)["logits"], logits) <= LOGIT_TOL["fp32"]
+    assert abs(e.loss_value(x.shape) - float(loss)) <= 1e-4 * abs(float(loss))
+    got = e.grad_dict()
+    bad = [(k, rel_l2(got[k], v)) for k, v in grads.items() if not rel_l2(got[k], v) <= GRAD_TOL["fp32"]]
+    assert not bad, bad
+
+
 def test_full_size_logits_and_loss_parity(cuda_device):
     """BASELINE configs[1] geometry (512x1024, 20 classes; one image so that the fp64 CPU oracle finishes in well
     under a minute): logits of the main-line precision within the north-star's 1e-4 of the CPU graph, loss within 1e-4,

@@ -2,6 +2,7 @@
 layout, dropout RNG replica, loud failure without a GPU, data-parallel host logic over gloo (world size 2)."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -169,3 +170,79 @@ def test_data_parallel_host_logic_gloo_world2():
         assert params == [0.0] * 10                  # broadcast from rank 0
         assert np.allclose(avg, expect_avg)
         assert tmax == 2.0 and dirty
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Feed protocol against the reference's OWN generators (they import here; /root/reference does not exist on the GPU box)
+REFERENCE = "/root/reference"
+
+
+def _png_tree(root, n, h, w, classes, kitti=False):
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    os.makedirs(os.path.join(root, "images", "a"))
+    os.makedirs(os.path.join(root, "labels", "a"))
+    ids = []
+    for i in range(n):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        Image.fromarray(img).save(os.path.join(root, "images", "a", "um_%06d_leftImg8bit.png" % i))
+        gt = rng.integers(0, classes, size=(h, w), dtype=np.uint8)
+        ids.append(gt)
+        if kitti:   # RGB labels, background = [255, 0, 0] (batch_generator_KITTI.py:45,82)
+            rgb = np.zeros((h, w, 3), np.uint8)
+            rgb[gt == 0] = (255, 0, 0)
+            rgb[gt != 0] = (255, 0, 255)
+            Image.fromarray(rgb).save(os.path.join(root, "labels", "a", "um_%06d_leftImg8bit.png" % i))
+        else:
+            Image.fromarray(gt).save(os.path.join(root, "labels", "a", "um_%06d_gtFine_labelIds.png" % i))
+    return ids
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only mounted in the build container")
+def test_reference_batch_generators_feed_the_class_surface(tmp_path):
+    """The reference's BatchGenerator / KITTI batch_generator, run UNMODIFIED through the scipy.misc shim over a
+    synthetic PNG tree, yield batches that the engine's feed checks accept as they are (uint8 images, bool one-hot
+    labels, short last batch; batch_generator.py:244,390-391,414-415; batch_generator_KITTI.py:82-86,104-105)."""
+    from fcn8s_tensorflow_b200.compat import install_scipy_misc_shim
+    from fcn8s_tensorflow_b200.fcn8s import check_images, check_labels
+    install_scipy_misc_shim()
+    sys.path.insert(0, REFERENCE)
+    try:
+        from data_generator.batch_generator import BatchGenerator
+        from data_generator.batch_generator_KITTI import batch_generator
+    finally:
+        sys.path.remove(REFERENCE)
+    C, H, W = 5, 64, 96
+    root = str(tmp_path / "cs")
+    ids = _png_tree(root, 5, H, W, C)
+    gen = BatchGenerator(image_dirs=[os.path.join(root, "images")], image_file_extension="png",
+                         ground_truth_dirs=[os.path.join(root, "labels")], image_name_split_separator="leftImg8bit",
+                         ground_truth_suffix="gtFine_labelIds", check_existence=True, num_classes=C)
+    assert gen.get_num_files() == 5
+    g = gen.generate(batch_size=2, convert_to_one_hot=True, shuffle=False)
+    sizes = []
+    for _ in range(4):                       # 2, 2, 1 (short last batch), then the next pass starts
+        images, labels = next(g)
+        sizes.append(len(images))
+        assert images.dtype == np.uint8 and images.shape[1:] == (H, W, 3)
+        assert labels.dtype == np.bool_ and labels.shape == (len(images), H, W, C)
+        assert (labels.sum(-1) == 1).all()
+        assert check_images(images) is images and check_labels(labels, C) is labels     # accepted without a copy
+    assert sizes == [2, 2, 1, 2]
+    # one-hot content equals the ids on disk (file order = sorted glob order is not guaranteed: compare as sets)
+    g2 = gen.generate(batch_size=5, convert_to_one_hot=True, shuffle=False)
+    _, labels = next(g2)
+    got = sorted(l.argmax(-1).astype(np.uint8).tobytes() for l in labels)
+    assert got == sorted(i.tobytes() for i in ids)
+    with pytest.raises(ValueError):
+        check_labels(labels[..., :3], C)
+    with pytest.raises(ValueError):
+        check_images(np.zeros((2, H, W), np.uint8))
+    # KITTI road generator: 2 classes [background, road], resized to a x32 size
+    kroot = str(tmp_path / "kitti")
+    _png_tree(kroot, 3, 50, 70, 2, kitti=True)
+    kg = batch_generator(2, kroot, "images/a", "labels/a", image_size=(64, 96))
+    images, labels = next(kg)
+    assert images.dtype == np.uint8 and images.shape == (2, 64, 96, 3)
+    assert labels.dtype == np.bool_ and labels.shape == (2, 64, 96, 2) and (labels.sum(-1) == 1).all()
+    assert check_labels(labels, 2) is labels
