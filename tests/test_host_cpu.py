@@ -188,11 +188,11 @@ def _png_tree(root, n, h, w, classes, kitti=False):
         Image.fromarray(img).save(os.path.join(root, "images", "a", "um_%06d_leftImg8bit.png" % i))
         gt = rng.integers(0, classes, size=(h, w), dtype=np.uint8)
         ids.append(gt)
-        if kitti:   # RGB labels, background = [255, 0, 0] (batch_generator_KITTI.py:45,82)
+        if kitti:   # RGB labels named *_road_*, background = [255, 0, 0] (batch_generator_KITTI.py:39-44,82)
             rgb = np.zeros((h, w, 3), np.uint8)
             rgb[gt == 0] = (255, 0, 0)
             rgb[gt != 0] = (255, 0, 255)
-            Image.fromarray(rgb).save(os.path.join(root, "labels", "a", "um_%06d_leftImg8bit.png" % i))
+            Image.fromarray(rgb).save(os.path.join(root, "labels", "a", "um_road_%06d_leftImg8bit.png" % i))
         else:
             Image.fromarray(gt).save(os.path.join(root, "labels", "a", "um_%06d_gtFine_labelIds.png" % i))
     return ids
