@@ -22,7 +22,7 @@ EXPORTS = [
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
     "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
-    "fcn8_set_step_scalars", "fcn8_set_sm_limit",
+    "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_upscore_tc_gather", "fcn8_upscore_tc_scatter",
 ]
 
 
@@ -135,6 +135,9 @@ def load():
                      ("fcn8_upscore_tc_fwd", UpscoreTcParams), ("fcn8_upscore_tc_dx", UpscoreTcParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp]
         getattr(lib, name).restype = C.c_int32
+    i32 = C.c_int32
+    lib.fcn8_upscore_tc_gather.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.fcn8_upscore_tc_scatter.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.fcn8_upscore_tc_cp.argtypes = [C.c_int32, C.c_int32]
     lib.fcn8_upscore_tc_cp.restype = C.c_int32
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]

@@ -803,6 +803,23 @@ extern "C" {
 
 int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride) { return upscore_cp(C, stride); }
 
+int32_t fcn8_upscore_tc_gather(const float* zp, const float* skip, float* f, int32_t N, int32_t h, int32_t w,
+                               int32_t C, int32_t stride, int32_t ldf, int32_t ld_skip, void* stream) {
+  if (!zp || !f) return fail(FCN8_ERR_BAD_SHAPE, "upscore gather: null pointer");
+  if (C < 1 || C > 32 || ldf < C || (skip && ld_skip < C)) return fail(FCN8_ERR_BAD_SHAPE, "upscore gather: bad C / ld");
+  cudaError_t e = launch_upscore_gather(zp, skip, f, N, h * stride, w * stride, C, upscore_cp(C, stride), stride / 2,
+                                        ldf, ld_skip, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore gather launch");
+}
+int32_t fcn8_upscore_tc_scatter(const float* g, float* dzp, float* dbias, int32_t N, int32_t h, int32_t w, int32_t C,
+                                int32_t stride, int32_t ldg, void* stream) {
+  if (!g || !dzp) return fail(FCN8_ERR_BAD_SHAPE, "upscore scatter: null pointer");
+  if (C < 1 || C > 32 || ldg < C) return fail(FCN8_ERR_BAD_SHAPE, "upscore scatter: bad C / ld");
+  cudaError_t e = launch_upscore_scatter(g, dzp, dbias, N, h * stride, w * stride, C, upscore_cp(C, stride),
+                                         stride / 2, ldg, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore scatter launch");
+}
+
 int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream) {
   if (!p || !p->T || !p->bias || !p->w_fwd || !p->w_dx || !p->bias_big)
     return fail(FCN8_ERR_BAD_SHAPE, "upscore pack: null pointer");

@@ -641,6 +641,65 @@ cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd,
   { count_launch(); upscore_pack_kernel<<<grid_for(total, 256), 256, 0, st>>>(T, bias, w_fwd, w_fwd_lo, w_dx, w_dx_lo, bias_big, C, CP, s); }
   return cudaGetLastError();
 }
+// Interior of a padded blocked transposed-conv output (+ the skip tensor): f[n,y,x,c] = zp[n,y+pad,x+pad,c] + skip[n,y,x,c]
+// for c < C, 0 for C <= c < ldf (fcn8s_tensorflow.py:213,224: the tf.add of the skip connections).
+__global__ void upscore_gather_kernel(const float* __restrict__ zp, const float* __restrict__ skip,
+                                      float* __restrict__ f, int N, int H, int W, int C, int CP, int pad, int ldf,
+                                      int ld_skip) {
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t total = static_cast<size_t>(N) * H * W * ldf;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ldf);
+    size_t r = i / ldf;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    float v = 0.f;
+    if (c < C) {
+      v = zp[((static_cast<size_t>(n) * Hp + y + pad) * Wp + x + pad) * CP + c];
+      if (skip) v += skip[((static_cast<size_t>(n) * H + y) * W + x) * ld_skip + c];
+    }
+    f[i] = v;
+  }
+}
+// The reverse for the gradient: dzp interior = g (border and channels >= C stay zero), db[c] += sum over pixels of g.
+__global__ void upscore_scatter_kernel(const float* __restrict__ g, float* __restrict__ dzp, float* __restrict__ db,
+                                       int N, int H, int W, int C, int CP, int pad, int ldg) {
+  __shared__ float sdb[CMAX];
+  if (threadIdx.x < CMAX) sdb[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const size_t total = static_cast<size_t>(N) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    size_t r = i / C;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    const float v = g[((static_cast<size_t>(n) * H + y) * W + x) * ldg + c];
+    dzp[((static_cast<size_t>(n) * Hp + y + pad) * Wp + x + pad) * CP + c] = v;
+    if (db) atomicAdd(&sdb[c], v);
+  }
+  __syncthreads();
+  if (db && threadIdx.x < C && sdb[threadIdx.x] != 0.f) atomicAdd(db + threadIdx.x, sdb[threadIdx.x]);
+}
+cudaError_t launch_upscore_gather(const float* zp, const float* skip, float* f, int N, int H, int W, int C, int CP,
+                                  int pad, int ldf, int ld_skip, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * H * W * ldf;
+  { count_launch(); upscore_gather_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, st>>>(zp, skip, f, N, H, W, C, CP, pad, ldf, ld_skip); }
+  return cudaGetLastError();
+}
+cudaError_t launch_upscore_scatter(const float* g, float* dzp, float* db, int N, int H, int W, int C, int CP, int pad,
+                                   int ldg, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * H * W * C;
+  { count_launch(); upscore_scatter_kernel<<<grid_for(total, 256, 148 * 2), 256, 0, st>>>(g, dzp, db, N, H, W, C, CP, pad, ldg); }
+  return cudaGetLastError();
+}
+
 // dT[a][b][co][ci] = sum_split src[split][(ty,tx,ci)][(dy,dx,co)]
 __global__ void upscore_unpack_dw_kernel(const float* __restrict__ src, int nsplit, float* __restrict__ dT, int C,
                                          int CP, int s) {

@@ -52,6 +52,10 @@ cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* lo
                                 cudaStream_t st);
 cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd, float* w_fwd_lo, float* w_dx,
                                 float* w_dx_lo, float* bias_big, int C, int CP, int s, cudaStream_t st);
+cudaError_t launch_upscore_gather(const float* zp, const float* skip, float* f, int N, int H, int W, int C, int CP,
+                                  int pad, int ldf, int ld_skip, cudaStream_t st);
+cudaError_t launch_upscore_scatter(const float* g, float* dzp, float* db, int N, int H, int W, int C, int CP, int pad,
+                                   int ldg, cudaStream_t st);
 cudaError_t launch_upscore_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st);
 cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
                              cudaStream_t st);

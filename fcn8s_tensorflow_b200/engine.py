@@ -21,6 +21,9 @@ from . import ops
 VGG_BLOCKS = [(1, 64, 2), (2, 128, 2), (3, 256, 3), (4, 512, 3), (5, 512, 3)]
 POOL3_SCALE, POOL4_SCALE = 1e-4, 1e-2          # fcn8s_tensorflow.py:171,182
 BETA1, BETA2, EPS = 0.9, 0.999, 1e-8           # tf.train.AdamOptimizer defaults (:256)
+# (packed-operand key, TF variable scope, stride) of upscore2 / upscore_pool4 / upscore8 (fcn8s_tensorflow.py:204-233)
+UPSCORE_STAGES = [("up2", "fc7_conv2d_trans", 2), ("up4", "fc7_pool4_conv2d_trans", 2),
+                  ("up8", "fc7_pool4_pool3_conv2d_trans", 8)]
 DECODER_KERNELS = ["pool3_1x1/kernel", "pool4_1x1/kernel", "fc7_1x1/kernel", "fc7_conv2d_trans/kernel",
                    "fc7_pool4_conv2d_trans/kernel", "fc7_pool4_pool3_conv2d_trans/kernel"]
 
@@ -195,9 +198,9 @@ class Engine:
                 f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3, out=old[0:2] if old else None)
                 d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3, out=old[2:4] if old else None)
                 self.packed[name] = f + d
-        self.packed["up8"] = ops.upscore_tc_pack(self.view("fc7_pool4_pool3_conv2d_trans/kernel"),
-                                                 self.view("fc7_pool4_pool3_conv2d_trans/bias"), 8, split=self.dec3,
-                                                 out=self.packed.get("up8"))
+        for key, base, stride in UPSCORE_STAGES:   # phase-GEMM operands of the three transposed convolutions
+            self.packed[key] = ops.upscore_tc_pack(self.view(base + "/kernel"), self.view(base + "/bias"), stride,
+                                                   split=self.dec3, out=self.packed.get(key))
         self._packed_dirty = False
 
     # ------------------------------------------------------------------ activation arena
@@ -297,19 +300,57 @@ class Engine:
                                 POOL4_SCALE, out=self._buf(A, "s4", (N, H // 16, W // 16, C), f32), pair=pair)
         s7 = ops.score_head_fwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), self.view("fc7_1x1/bias"), 1.0,
                                 out=self._buf(A, "s7", (N, H // 32, W // 32, C), f32), pair=pair)
-        f4 = ops.upscore_fwd(s7, self.view("fc7_conv2d_trans/kernel"), self.view("fc7_conv2d_trans/bias"), 2, skip=s4,
-                             out=self._buf(A, "f4", (N, H // 16, W // 16, C), f32))
-        f3 = ops.upscore_fwd(f4, self.view("fc7_pool4_conv2d_trans/kernel"), self.view("fc7_pool4_conv2d_trans/bias"),
-                             2, skip=s3, out=self._buf(A, "f3", (N, H // 8, W // 8, C), f32))
-        # upscore8 on the tensor cores (phase GEMM): padded blocked logits [N, H+8, W+8, CP]; A["logits"] is the view
-        f3p = self._pad4(A, "f3p", f3)
-        x_lo = self._split(A, "f3p", f3p, force=self.dec3)[1]
-        zp = A.get("logits_p")
-        if zp is None:
-            zp = A["logits_p"] = ops.upscore_tc_alloc(N, H // 8, W // 8, C, 8, self.device)
-        ops.upscore_tc_fwd(f3p, self.packed["up8"], C, 8, zp, x_lo=x_lo)
+        # the three transposed convolutions as tcgen05 phase GEMMs over padded blocked tensors; the skip adds
+        # (fcn8s_tensorflow.py:213,224) ride on the gather of the block interior
+        ld4 = (C + 3) // 4 * 4
+        f4 = self._buf(A, "f4", (N, H // 16, W // 16, ld4), f32)
+        self._upscore_stage_fwd(A, "up2", self._pad4(A, "s7p", s7), 2, skip=s4, out=f4)
+        f3 = self._buf(A, "f3", (N, H // 8, W // 8, ld4), f32)
+        self._upscore_stage_fwd(A, "up4", f4, 2, skip=s3, out=f3)
+        zp = self._upscore_stage_fwd(A, "up8", f3, 8)
+        A["logits_p"] = zp
         A["logits"] = ops.upscore_tc_interior(zp, C, 8)
         return A["logits"]
+
+    def _upscore_stage_fwd(self, A, key, x, stride, skip=None, out=None):
+        """One transposed convolution: x [N,h,w,ld4] -> padded blocked A[key + "_p"]; with `out`, also the interior
+        (+ skip) as the next stage's dense input."""
+        N, h, w, _ = x.shape
+        zp = A.get(key + "_p")
+        if zp is None:
+            zp = A[key + "_p"] = ops.upscore_tc_alloc(N, h, w, self.C, stride, self.device)
+        x_lo = self._split(A, key + "_x", x, force=self.dec3)[1]
+        ops.upscore_tc_fwd(x, self.packed[key], self.C, stride, zp, x_lo=x_lo)
+        if out is not None:
+            ops.upscore_tc_gather(zp, skip, out, self.C, stride)
+        return zp
+
+    def _upscore_stage_bwd(self, A, key, base, x, g, stride, dzp=None):
+        """Backward of one transposed convolution: g = gradient of its (dense) output, or dzp already in the padded
+        blocked layout (upscore8: written by the loss kernel).  Fills dT / dbias in the flat gradient, returns dx."""
+        N, h, w, ld = x.shape
+        G = self.grads
+        if dzp is None:
+            dzp = A.get(key + "_dp")
+            if dzp is None:   # zero border / pad channels, never written again
+                dzp = A[key + "_dp"] = ops.upscore_tc_alloc(N, h, w, self.C, stride, self.device, zero=True)
+            db = self.view(base + "/bias", G)
+            db.zero_()
+            ops.upscore_tc_scatter(g, dzp, self.C, stride, dbias=db)
+        dz_lo = self._split(A, key + "_dp", dzp, force=self.dec3)[1]
+        ops.upscore_tc_dw(x, dzp, self.C, stride, self.view(base + "/kernel", G), x_lo=A.get(key + "_x.lo"),
+                          dzp_lo=dz_lo)
+        dx = self._buf(A, key + "_dx", x.shape, torch.float32)
+        ops.upscore_tc_dx(dzp, self.packed[key], self.C, stride, dx, dzp_lo=dz_lo)
+        return dx
+
+    def _dense(self, A, name, t):
+        """[..., ld4] -> dense [..., C] copy for the score-head kernels (a no-op view when C is a multiple of 4)."""
+        if t.shape[-1] == self.C:
+            return t
+        d = self._buf(A, name, tuple(t.shape[:-1]) + (self.C,), torch.float32)
+        d.copy_(t[..., :self.C])
+        return d
 
     def _pad4(self, arena, name, t):
         """[N,h,w,C] -> the same tensor with the channel stride rounded up to a multiple of 4 (zero filled): the layout
@@ -351,25 +392,11 @@ class Engine:
         dc8.zero_()
         ops.softmax_xent(zp, labels.view(torch.uint8), self.loss_buf[0:1], dzp, grad_scale=1.0 / npx, dbias=dc8,
                          pad=4, num_classes=C)
-        # decoder backward; upscore8 on the tensor cores
-        dz_lo = self._split(A, "dlogits_p", dzp, force=self.dec3)[1]
-        f3p = A["f3p"] if C % 4 else A["f3"]
-        f3_lo = A.get("f3p.lo")
-        ops.upscore_tc_dw(f3p, dzp, C, 8, self.view("fc7_pool4_pool3_conv2d_trans/kernel", G), x_lo=f3_lo,
-                          dzp_lo=dz_lo)
-        df3p = self._buf(A, "df3p", f3p.shape, f32)
-        ops.upscore_tc_dx(dzp, self.packed["up8"], C, 8, df3p, dzp_lo=dz_lo)
-        if C % 4:
-            df3 = self._buf(A, "df3", A["f3"].shape, f32)
-            df3.copy_(df3p[..., :C])
-        else:
-            df3 = df3p
-        df4 = self._buf(A, "df4", A["f4"].shape, f32)
-        ops.upscore_bwd(A["f4"], self.view("fc7_pool4_conv2d_trans/kernel"), df3, 2,
-                        self.view("fc7_pool4_conv2d_trans/kernel", G), self.view("fc7_pool4_conv2d_trans/bias", G), df4)
-        ds7 = self._buf(A, "ds7", A["s7"].shape, f32)
-        ops.upscore_bwd(A["s7"], self.view("fc7_conv2d_trans/kernel"), df4, 2,
-                        self.view("fc7_conv2d_trans/kernel", G), self.view("fc7_conv2d_trans/bias", G), ds7)
+        # decoder backward: three phase-GEMM stages; the skip adds fan the gradient out
+        df3p = self._upscore_stage_bwd(A, "up8", "fc7_pool4_pool3_conv2d_trans", A["f3"], None, 8, dzp=dzp)
+        df4p = self._upscore_stage_bwd(A, "up4", "fc7_pool4_conv2d_trans", A["f4"], df3p, 2)
+        ds7p = self._upscore_stage_bwd(A, "up2", "fc7_conv2d_trans", A["s7p"] if C % 4 else A["s7"], df4p, 2)
+        df3, df4, ds7 = self._dense(A, "df3", df3p), self._dense(A, "df4", df4p), self._dense(A, "ds7", ds7p)
         inv_keep = 1.0 / keep_prob if keep_prob < 1.0 else 1.0
         # score heads: ds3 = df3, ds4 = df4 (the adds fan the gradient out unchanged)
         dpool3 = self._buf(A, "d_pool3_head", A["pool3"].shape, self.tdt)

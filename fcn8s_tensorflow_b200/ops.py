@@ -359,6 +359,25 @@ def upscore_tc_interior(zp, num_classes, stride):
     return zp[:, p:zp.shape[1] - p, p:zp.shape[2] - p, :num_classes]
 
 
+def upscore_tc_gather(zp, skip, out, num_classes, stride):
+    """out[N, s*h, s*w, ld] = interior(zp)[..., :C] (+ skip [N, s*h, s*w, >=C]); pad channels of `out` zeroed."""
+    _chk_cuda(zp, skip, out)
+    N, H, W, ld = out.shape
+    capi.check(capi.load().fcn8_upscore_tc_gather(capi.ptr(zp), capi.ptr(skip), capi.ptr(out), N, H // stride,
+                                                  W // stride, num_classes, stride, ld,
+                                                  skip.shape[-1] if skip is not None else 0, _stream()))
+    return out
+
+
+def upscore_tc_scatter(g, dzp, num_classes, stride, dbias=None):
+    """dzp interior <- g [N, s*h, s*w, ld]; dbias[c] += sum of g over pixels (caller zeroes dzp once and dbias)."""
+    _chk_cuda(g, dzp, dbias)
+    N, H, W, ld = g.shape
+    capi.check(capi.load().fcn8_upscore_tc_scatter(capi.ptr(g), capi.ptr(dzp), capi.ptr(dbias), N, H // stride,
+                                                   W // stride, num_classes, stride, ld, _stream()))
+    return dzp
+
+
 def upscore_tc_fwd(x, packed, num_classes, stride, out, x_lo=None):
     """x [N,h,w,ldx] fp32 (channels >= C zero) -> padded blocked output `out` (see upscore_tc_alloc)."""
     _chk_cuda(x, x_lo, out)

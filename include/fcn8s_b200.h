@@ -285,6 +285,14 @@ typedef struct {
   int32_t N, h, wd, C, stride, ldx, nseg; /* x is [N,h,wd,ldx] */
 } Fcn8UpscoreTcParams;
 int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride);
+/* Skip connections around the padded tensors (tf.add, fcn8s_tensorflow.py:213,224).  (h, w) are the INPUT dims of the
+ * transposed convolution, its output is [N, stride*h, stride*w, .].
+ * gather:  f[n,y,x,c] = zp[n, y+stride/2, x+stride/2, c] + skip[n,y,x,c] (skip may be NULL), c < C; channels C..ldf-1 = 0.
+ * scatter: dzp interior = g (border / pad channels untouched: keep them zero); dbias[c] += sum over pixels of g. */
+int32_t fcn8_upscore_tc_gather(const float* zp, const float* skip, float* f, int32_t N, int32_t h, int32_t w,
+                               int32_t C, int32_t stride, int32_t ldf, int32_t ld_skip, void* stream);
+int32_t fcn8_upscore_tc_scatter(const float* g, float* dzp, float* dbias, int32_t N, int32_t h, int32_t w, int32_t C,
+                                int32_t stride, int32_t ldg, void* stream);
 int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream);
 int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream);
 int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream);
