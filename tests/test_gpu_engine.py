@@ -252,6 +252,58 @@ def test_full_size_logits_and_loss_parity(cuda_device):
     assert rel(both[0], one[0]) <= 5e-5
 
 
+def test_config4_full_resolution_inference_properties(cuda_device):
+    """BASELINE configs[3]: predict on one 2048x1024 image, 20 classes (the fp64 oracle would need minutes at this size,
+    so the checks are size-independent properties): output types / shapes of fcn8s_tensorflow.py:743-770, softmax rows
+    sum to one, argmax == argmax(softmax), bit-reproducible, and the top half of the image is unaffected by changes
+    far below it beyond the encoder's receptive field (fc6's 7x7 at 1/32 resolution sees +-(3*32+~106) px)."""
+    Cc, Hh, Ww = 20, 1024, 2048
+    w = oracle.init_weights(Cc, seed=2, decoder_std_scale=10.0)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(1, Hh, Ww, 3), dtype=np.uint8)
+    e = make_engine(cuda_device, "fp32", w, classes=Cc)
+    x = torch.from_numpy(img).to(cuda_device)
+    am = e.predict(x, argmax=True)
+    sm = e.predict(x, argmax=False)
+    assert am.dtype == torch.int64 and tuple(am.shape) == (1, Hh, Ww)
+    assert sm.dtype == torch.float32 and tuple(sm.shape) == (1, Hh, Ww, Cc)
+    assert torch.isfinite(sm).all() and (sm.sum(-1) - 1).abs().max().item() <= 1e-5
+    assert torch.equal(sm.argmax(-1), am)
+    assert torch.equal(e.predict(x, argmax=True), am)
+    img2 = img.copy()
+    img2[:, 768:, :, :] = 255 - img2[:, 768:, :, :]          # change the bottom quarter only
+    sm2 = e.predict(torch.from_numpy(img2).to(cuda_device), argmax=False)
+    assert torch.equal(sm2[:, :256], sm[:, :256])              # rows 0..255 are > 500 px away: bit-identical
+    assert not torch.equal(sm2[:, 900:], sm[:, 900:])
+
+
+def test_config5_kitti_full_size_parity(cuda_device):
+    """BASELINE configs[4] geometry: KITTI road resized to the x32 size 384x1248 (the 375x1242 originals cannot run in
+    the reference graph either), 2 classes, labels [background, road]: logits / loss of one image
+    against the fp64 oracle, and one training step of a batch of 2 runs."""
+    Hh, Ww = 384, 1248
+    w = oracle.init_weights(2, seed=3, decoder_std_scale=10.0)
+    rng = np.random.default_rng(5)
+    images = rng.integers(0, 256, size=(2, Hh, Ww, 3), dtype=np.uint8)
+    bg = rng.random((2, Hh, Ww, 1)) < 0.7
+    labels = np.concatenate((bg, np.invert(bg)), axis=3)
+    with torch.no_grad():
+        ref = oracle.forward(w, images[:1], dtype=torch.float64)
+        ref_loss = float(oracle.loss_from_logits({k: v.double() for k, v in w.items()}, ref, labels[:1]))
+    e = make_engine(cuda_device, "fp32", w, classes=2)
+    x = torch.from_numpy(images).to(cuda_device)
+    y = torch.from_numpy(labels.view(np.uint8)).to(cuda_device)
+    e.loss_and_backward(x[:1].contiguous(), y[:1].contiguous())
+    torch.cuda.synchronize()
+    err = rel(e._arena(1, Hh, Ww)["logits"], ref)
+    print("KITTI 384x1248 logits max-rel %.3e" % err)
+    assert err <= 1e-4
+    assert abs(e.loss_value((1, Hh, Ww)) - ref_loss) <= 1e-4 * abs(ref_loss)
+    e.train_step(x, y, 1e-4, keep_prob=0.5)
+    torch.cuda.synchronize()
+    assert np.isfinite(e.loss_value(x.shape)) and e.global_step == 1
+
+
 def test_kitti_two_class_shape(cuda_device):
     """BASELINE config 5 geometry (KITTI road, 2 classes) at a x32 size, labels [bg, ~bg] as
     batch_generator_KITTI.py:82-84 builds them."""
