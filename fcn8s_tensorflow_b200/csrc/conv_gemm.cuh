@@ -1,16 +1,21 @@
 // Implicit-GEMM convolution kernels on tcgen05 (sm_100a) -- device side.
 //
 //   conv_gemm_kernel : stride-1 SAME k x k convolution of an NHWC tensor as a GEMM
-//        D[pixels, Cout] = sum_{tap, cblock} A_tap[pixels, CH] * Bp[Cout, (tap, cblock)]^T
-//     used for fprop (Bp = packed forward weights) and for dgrad (Bp = rotated / in-out swapped weights).
+//        D[pixels, Cout] = sum_{tap, cblock} A_tap[pixels, CH] * B[(tap, cblock), Cout]
+//     used for fprop and for dgrad.  B is either a packed K-major operand [Cout][K] (conv1_1, decoder GEMMs) or the
+//     bf16 shadow of the TF-layout (HWIO) weight tensor read in place (b_mode 1 / 2: rotation and in/out swap of the
+//     dgrad live in the TMA coordinates).  Also carries the phase GEMMs of the transposed convolutions (blocked
+//     output / 5-D blocked A operand).
 //     Replaces TF's Conv2D / Conv2DBackpropInput behind the external VGG-16 graph the reference loads at
-//     fcn8s_tensorflow.py:127-152 and differentiates at :256-257.
+//     fcn8s_tensorflow.py:127-152 and differentiates at :256-257, and conv2d_transpose at :204-233.
+//   conv_halo_kernel : the same 3x3 convolution with one activation patch per tile and nine shifted UMMA descriptors.
 //   wgrad_gemm_kernel : D[(tap, ci), co] = sum_{pixels} X[pixel + tap, ci] * dY[pixel, co]
 //     (TF's Conv2DBackpropFilter, implied by fcn8s_tensorflow.py:257), both operands MN-major.
 //
-// Shared design: one CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
-// (one elected lane), warps 2..5 = epilogue (TMEM -> registers -> global). Persistent over tiles, smem ring of
-// kStages operand stages, 2 accumulator stages in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// Shared design: one CTA = 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both loops run by
+// the whole warp, one elected lane issues), warps 2..9 = epilogue (TMEM -> registers -> global; two warps per TMEM
+// lane quarter).  Persistent over tiles, smem ring of kStages operand stages, 2 accumulator stages in TMEM so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 // Everything is expressed in bytes: an operand row is always 128 B (64 bf16 or 32 tf32/fp32 values) with the
 // 128-byte swizzle, so one code path serves kind::f16 (bf16) and kind::tf32.
 #pragma once
