@@ -520,7 +520,34 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   return 0;
 }
 
+namespace {
+// wgrad_halo_kernel: 3x3, 64 input channels, bf16 operands (conv1_2, conv2_1)
+bool wgrad_use_halo(const Fcn8WgradParams* p) {
+  return p->dtype == FCN8_BF16 && p->ksize == 3 && p->Cin == 64 && p->Cout % 64 == 0 && p->rows_valid <= 0 &&
+         p->force_splits <= 0 && p->force_bn <= 0 && !g_debug[1];
+}
+struct WgradHaloPlan {
+  int tiles_x, tiles_y, total_patches, tiles_n, splits, patches_per_split;
+};
+void plan_wgrad_halo(const Fcn8WgradParams* p, WgradHaloPlan* pl) {
+  pl->tiles_x = (p->W + 7) >> 3;
+  pl->tiles_y = (p->H + 15) >> 4;
+  pl->total_patches = pl->tiles_x * pl->tiles_y * p->N;
+  pl->tiles_n = p->Cout / 64;
+  int splits = num_sms() / pl->tiles_n;
+  if (splits > pl->total_patches) splits = pl->total_patches;
+  if (splits < 1) splits = 1;
+  pl->patches_per_split = (pl->total_patches + splits - 1) / splits;
+  pl->splits = (pl->total_patches + pl->patches_per_split - 1) / pl->patches_per_split;
+}
+}  // namespace
+
 size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p) {
+  if (wgrad_use_halo(p)) {
+    WgradHaloPlan hp;
+    plan_wgrad_halo(p, &hp);
+    return (size_t)hp.splits * 640 * p->Cout * sizeof(float);
+  }
   WgradPlan pl;
   if (plan_wgrad(p, &pl)) return 0;
   return pl.splits > 1 ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
@@ -531,6 +558,53 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   if (!aligned16(p->x) || !aligned16(p->dy) || !aligned16(p->dw))
     return fail(FCN8_ERR_BAD_ALIGN, "wgrad: pointers must be 16-byte aligned");
   if (p->nseg == 3 && (!p->x_lo || !p->dy_lo)) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: nseg=3 needs x_lo and dy_lo");
+  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 or 3");
+  if (wgrad_use_halo(p)) {
+    if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: empty tensor");
+    WgradHaloPlan hp;
+    plan_wgrad_halo(p, &hp);
+    const size_t hneed = (size_t)hp.splits * 640 * p->Cout * sizeof(float);
+    if (hneed > workspace_bytes || !workspace)
+      return fail(FCN8_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu", workspace_bytes, hneed);
+    TensorMaps3 hm;
+    memset(&hm, 0, sizeof(hm));
+    const void* hxs[3] = {p->x, p->x, p->x_lo};
+    const void* hds[3] = {p->dy, p->dy_lo, p->dy};
+    for (int s = 0; s < p->nseg; ++s) {
+      int hrc = encode_act_map(&hm.a[s], hxs[s], FCN8_BF16, p->N, p->H, p->W, 64, 16, 18, 1, false, p->x_ld);
+      if (hrc) return hrc;
+      hrc = encode_act_map(&hm.b[s], hds[s], FCN8_BF16, p->N, p->H, p->W, p->Cout, 8, 16, 1, false, p->dy_ld);
+      if (hrc) return hrc;
+    }
+    WgradHaloArgs ha;
+    memset(&ha, 0, sizeof(ha));
+    ha.partial = static_cast<float*>(workspace);
+    ha.N = p->N;
+    ha.H = p->H;
+    ha.W = p->W;
+    ha.ldc = p->Cout;
+    ha.nseg = p->nseg;
+    ha.tiles_x = hp.tiles_x;
+    ha.tiles_y = hp.tiles_y;
+    ha.total_patches = hp.total_patches;
+    ha.patches_per_split = hp.patches_per_split;
+    ha.splits = hp.splits;
+    ha.tiles_n = hp.tiles_n;
+    ha.acc_scale = g_debug[0] ? 1.f : 1.f + 8.f * (float)(p->nseg * hp.patches_per_split) * kRzBiasPerMma;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaError_t ae = cudaFuncSetAttribute(wgrad_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            WgradHaloCfg::kSmemBytes);
+      if (ae != cudaSuccess) return cuda_fail(ae, "wgrad_halo attribute");
+      attr_done = true;
+    }
+    cudaStream_t hst = (cudaStream_t)stream;
+    { count_launch(); wgrad_halo_kernel<64><<<hp.tiles_n * hp.splits, kGemmThreads, WgradHaloCfg::kSmemBytes, hst>>>(hm, ha); }
+    cudaError_t he = cudaGetLastError();
+    if (he != cudaSuccess) return cuda_fail(he, "wgrad_halo launch");
+    he = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, hp.splits, 640, 576, p->Cout, hst);
+    return he == cudaSuccess ? 0 : cuda_fail(he, "wgrad_halo reduce launch");
+  }
   WgradPlan pl;
   int rc = plan_wgrad(p, &pl);
   if (rc) return rc;

@@ -1010,4 +1010,163 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// wgrad_halo_kernel: filter gradient of the 3x3 layers with 64 INPUT channels (conv1_2, conv2_1), where the generic
+// kernel is bound by L2 -> shared-memory traffic (N = 64 / 128 tiles, one tap-shifted copy of X per m-tile).
+// One CTA owns ALL 576 = 9 taps x 64 channels output rows of a 64-column slice and a range of 128-pixel patches:
+// per patch it loads the activation patch ONCE with its halo (the same 18 x 16-pixel box as conv_halo_kernel) plus
+// the 16 x 8-pixel dY tile, and issues 5 x 8 MMAs: accumulator j holds taps (2j, 2j+1) -- the A operand is MN-major
+// with M = 128 = two 64-channel chunks that are the two taps' windows into the patch (LBO = their byte distance), K =
+// pixels in groups of 8 (one patch row, 2048 B apart); the dY tile is the MN-major B operand.  52 KB of operands per
+// 40 MMAs instead of 5 x 48 KB.  Five accumulators = 320 TMEM columns, no double buffering (one output tile per CTA);
+// fp32 partials [split][640][Cout] go through wgrad_splitk_reduce_kernel.
+struct WgradHaloArgs {
+  float* partial;    // [splits][640][ldc]
+  int N, H, W, ldc;  // ldc = Cout
+  int nseg;
+  int tiles_x, tiles_y;          // 8 x 16 pixel patches per image
+  int total_patches, patches_per_split, splits, tiles_n;
+  float acc_scale;
+};
+struct WgradHaloCfg {
+  static constexpr int kXBytes = 18 * 16 * 128;  // halo box of X
+  static constexpr int kDyBytes = 128 * 128;     // 16 x 8 pixels x 64 co
+  static constexpr int kStage = kXBytes + kDyBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kSmemBytes = kStages * kStage + 1024 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ TensorMaps3 maps, const WgradHaloArgs g) {
+  static_assert(BN == 64, "one 64-column slice per CTA");
+  using Cfg = WgradHaloCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + Cfg::kStages * Cfg::kStage;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* acc_full = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % g.tiles_n;
+  const int sp = blockIdx.x / g.tiles_n;
+  const int p0 = sp * g.patches_per_split;
+  const int p1 = min(g.total_patches, p0 + g.patches_per_split);
+  const int per_img = g.tiles_x * g.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int seg = 0; seg < g.nseg; ++seg) {
+      for (int pt = p0; pt < p1; ++pt) {
+        const int n = pt / per_img;
+        const int r = pt - n * per_img;
+        const int x0 = (r % g.tiles_x) << 3, y0 = (r / g.tiles_x) << 4;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sx = smem + stage * Cfg::kStage;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStage);
+          tma_load_4d(&maps.a[seg], &full_bar[stage], sx, 0, x0 - 1, y0 - 1, n);
+          tma_load_4d(&maps.b[seg], &full_bar[stage], sx + Cfg::kXBytes, nb * 64, x0, y0, n);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(1u, 1u, 1u, 128u, 64);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t first = 0;
+    for (int it = 0; it < g.nseg * (p1 - p0); ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t sx = smem_base + stage * Cfg::kStage;
+      const uint32_t sdy = sx + Cfg::kXBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int t0 = 2 * j, t1 = (2 * j + 1 < 9) ? 2 * j + 1 : 2 * j;
+          const uint32_t off0 = static_cast<uint32_t>((t0 / 3) * 16 + (t0 % 3)) * 128u;
+          const uint32_t off1 = static_cast<uint32_t>((t1 / 3) * 16 + (t1 % 3)) * 128u;
+          // A: MN-major, M = two 64-channel chunks (the two taps' windows, LBO apart), K groups of 8 pixels 2048 B apart
+          const uint64_t adesc = make_smem_desc_sw128(sx + off0, off1 - off0, 2048, 2u);
+          const uint64_t bdesc = make_smem_desc_sw128(sdy, 8192, 1024, 2u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // 16 pixels per MMA = two patch rows of X (2 x 2048 B) / 16 rows of dY (2048 B)
+            umma_f16(tmem_base + j * 64, adesc + ((k * 4096u) >> 4), bdesc + ((k * 2048u) >> 4), idesc,
+                     first | static_cast<uint32_t>(k > 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      __syncwarp();
+      first = 1;
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float* dst = g.partial + static_cast<size_t>(sp) * 640 * g.ldc + nb * 64 + chalf * 32;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + j * 64 + chalf * 32 + (static_cast<uint32_t>(quarter * 32) << 16), v);
+      tmem_ld_wait();
+      float4* o4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(j * 128 + row) * g.ldc);
+      if (p1 > p0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o4[i] = make_float4(__uint_as_float(v[4 * i]) * g.acc_scale, __uint_as_float(v[4 * i + 1]) * g.acc_scale,
+                              __uint_as_float(v[4 * i + 2]) * g.acc_scale, __uint_as_float(v[4 * i + 3]) * g.acc_scale);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace fcn8
