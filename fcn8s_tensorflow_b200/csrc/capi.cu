@@ -227,16 +227,16 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
   return cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, bool RB = false>
 cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         HaloSmem<BN>::kBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HaloSmem<BN, RB>::kBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  { count_launch(); conv_halo_kernel<BN><<<grid, kGemmThreads, HaloSmem<BN>::kBytes, st>>>(maps, a); }
+  { count_launch(); conv_halo_kernel<BN, RB><<<grid, kGemmThreads, HaloSmem<BN, RB>::kBytes, st>>>(maps, a); }
   return cudaGetLastError();
 }
 
@@ -405,7 +405,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   // Halo-tile kernel for the L2-traffic-bound 3x3 layers (few input channels: the activation patch is loaded once per
   // tile instead of once per tap).  algo: 0 = heuristic, 1 = per-tap kernel, 2 = halo kernel.
   const bool halo_ok = p->dtype == FCN8_BF16 && p->ksize == 3 && p->w_mode != 0 && p->Cin % 64 == 0;
-  const bool use_halo = halo_ok && (p->algo >= 2 || (p->algo == 0 && p->Cin <= 128));
+  const bool use_halo = halo_ok && p->Cout <= 256 && (p->algo >= 2 || (p->algo == 0 && p->Cin <= 128));
   if (p->algo >= 2 && !halo_ok) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs bf16, 3x3, w_mode 1/2");
   if (use_halo) {
     pl.lbw = 3;
@@ -490,8 +490,12 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if (use_halo) {
     const long long tiles = (long long)pl.m_tiles * pl.tiles_n;
     const int hgrid = (int)(tiles < num_sms() ? tiles : num_sms());
+    if ((long long)pl.tiles_n * pl.BN > 256) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs Cout <= 256");
+    // weights resident in shared memory when the CTA's whole slice is one group of 9 taps (conv1_2 fwd / dgrad, bf16)
+    const bool resident = pl.BN == 64 && pl.tiles_n == 1 && (p->nseg == 3 ? 2 : 1) * (p->Cin / 64) <= 1 && !g_debug[2];
     cudaError_t he = pl.BN == 256 ? launch_halo_t<256>(maps, a, hgrid, (cudaStream_t)stream)
                    : pl.BN == 128 ? launch_halo_t<128>(maps, a, hgrid, (cudaStream_t)stream)
+                   : resident     ? launch_halo_t<64, true>(maps, a, hgrid, (cudaStream_t)stream)
                                   : launch_halo_t<64>(maps, a, hgrid, (cudaStream_t)stream);
     return he == cudaSuccess ? 0 : cuda_fail(he, "conv_halo launch");
   }

@@ -566,25 +566,30 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 // its own ring.  bf16 operands only (kind::f16); epilogue shared with conv_gemm_kernel.
 struct HaloCfg {
   static constexpr int kABytes = 18 * 16 * 128;  // 36,864
-  static constexpr int kAStages = 2;
 };
-template <int BN>
+// The activation patches go through a ring of 3-4 stages: a 36 KB box of 288 rows has a TMA latency of ~3000 cycles,
+// longer than the 36 MMAs that consume it, so with two stages the kernel was latency-bound (tensor pipe 43-57 %).
+// RB ("resident B", N = 64 only): when the CTA's whole weight slice is 9 taps x 8 KB (conv1_2 forward / dgrad in bf16)
+// it is loaded into shared memory ONCE and every tile only streams its activation patch.
+template <int BN, bool RB = false>
 struct HaloSmem {
   // filter taps per B pipeline stage: the three kw taps of one kh row for the narrow N = 64 tiles (12 MMAs per barrier
   // round trip instead of 4: the MMA time of a single 128x64x64 stage is shorter than the issue + wait overhead)
   static constexpr int kTaps = (BN == 64) ? 3 : 1;
   static constexpr int kBBytes = kTaps * BN * 128;
-  static constexpr int kBStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 4);
+  static constexpr int kAStages = (BN == 64) ? 4 : 3;
+  static constexpr int kBStages = RB ? 3 : (BN == 128 ? 6 : 3);   // RB: the 3 resident tap-row groups
   static constexpr int kBarBytes = 1024;
-  static constexpr int kBytes =
-      HaloCfg::kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumMax * 4 + 1024;
+  static constexpr int kColsumBytes = 1024;   // the halo layers have at most 256 output channels
+  static constexpr int kBytes = kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumBytes + 1024;
 };
 
-template <int BN>
+template <int BN, bool RB = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
-  using HS = HaloSmem<BN>;
-  constexpr int kAS = HaloCfg::kAStages, kBS = HS::kBStages;
+  static_assert(!RB || BN == 64, "resident weights only for the N = 64 tiles");
+  using HS = HaloSmem<BN, RB>;
+  constexpr int kAS = HS::kAStages, kBS = HS::kBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem + kAS * HaloCfg::kABytes;
@@ -636,6 +641,23 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      if constexpr (RB) {
+        // resident weights: groups (set, cb, kh) of three taps; set 0 = hi (maps.b[0]), set 1 = lo (maps.b[1])
+        const int nsets = g.nseg == 3 ? 2 : 1;
+        if (elect_one()) {
+          mbar_expect_tx(&b_full[0], static_cast<uint32_t>(nsets * g.cblocks * 3) * HS::kBBytes);
+          for (int set = 0; set < nsets; ++set)
+            for (int cb = 0; cb < g.cblocks; ++cb)
+              for (int kh = 0; kh < 3; ++kh) {
+                uint8_t* sb = smem_b + ((set * g.cblocks + cb) * 3 + kh) * HS::kBBytes;
+                if (g.b_mode == 1)
+                  tma_load_3d(&maps.b[set], &b_full[0], sb, cb * 64, 0, 8 - 3 * kh - 2);
+                else
+                  tma_load_3d(&maps.b[set], &b_full[0], sb, 0, cb * 64, 3 * kh);
+              }
+        }
+        __syncwarp();
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nb = t % g.tiles_n;
         const int mt = t / g.tiles_n;
@@ -655,7 +677,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
               as = 0;
               aph ^= 1;
             }
-            for (int tap = 0; tap < 9; tap += HS::kTaps) {
+            for (int tap = 0; tap < (RB ? 0 : 9); tap += HS::kTaps) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               uint8_t* sb = smem_b + bs * HS::kBBytes;
               if (elect_one()) {
@@ -691,6 +713,10 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     const uint32_t sa_base = smem_u32(smem), sb_base = smem_u32(smem_b);
     int as = 0, bs = 0, acs = 0;
     uint32_t aph = 0, bph = 0, acph = 0;
+    if constexpr (RB) {
+      mbar_wait(&b_full[0], 0);   // the resident weight slice has landed
+      tc_fence_after();
+    }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       mbar_wait(&acc_empty[acs], acph ^ 1);
       tc_fence_after();
@@ -700,13 +726,17 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
         const uint32_t sa = sa_base + as * HaloCfg::kABytes;
+        const int rb_seg = kbk / g.cblocks;
+        const int rb_group0 = ((rb_seg == 1 ? 1 : 0) * g.cblocks + (kbk - rb_seg * g.cblocks)) * 3;
 #pragma unroll 1
         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
           for (int kw0 = 0; kw0 < 3; kw0 += HS::kTaps) {
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t sb = sb_base + bs * HS::kBBytes;
+            if constexpr (!RB) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+            }
+            const uint32_t sb = sb_base + (RB ? (rb_group0 + kh) : bs) * HS::kBBytes;
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < HS::kTaps; ++j) {
@@ -727,13 +757,15 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
                 }
                 first = 1;
               }
-              umma_commit(&b_empty[bs]);
+              if constexpr (!RB) umma_commit(&b_empty[bs]);
             }
             __syncwarp();
             first = 1;
-            if (++bs == kBS) {
-              bs = 0;
-              bph ^= 1;
+            if constexpr (!RB) {
+              if (++bs == kBS) {
+                bs = 0;
+                bph ^= 1;
+              }
             }
           }
         }

@@ -564,6 +564,8 @@ def halo_conv():
         ok_a &= hwio_conv_case(3, 20, 36, 64, 128, 3, False, 1e-2, algo=algo)        # ragged tiles
         ok_a &= hwio_conv_case(1, 48, 40, 128, 256, 3, False, 1e-2, algo=algo)
         ok_a &= hwio_conv_case(2, 20, 28, 64, 128, 3, True, 2e-5, algo=algo)         # hi/lo pairs
+        ok_a &= hwio_conv_case(2, 36, 20, 64, 64, 3, True, 2e-5, algo=algo)          # pairs, weights resident in smem
+        ok_a &= hwio_conv_case(1, 40, 24, 128, 64, 3, False, 1e-2, algo=algo)        # resident, 2 channel blocks
         print(" -- algo %d -> %s" % (algo, "PASS" if ok_a else "FAIL"))
         if algo == 2:
             ok = ok_a     # algo 3 (base-offset variant) is informational
