@@ -341,6 +341,12 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
+        if (c + 32 >= (chalf + 1) * (BN / 2)) {
+          // the warp's last chunk is in registers: hand the accumulator stage back BEFORE the math and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
+        }
         const int c0 = nb * BN + c;
         if (g.flags & EPI_PARTIAL) {
           if (valid) {
@@ -362,9 +368,6 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
           if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane, seed);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -1026,7 +1029,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;

@@ -42,6 +42,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive without release semantics: the default (.release) makes the arriving thread wait until its earlier global
+// stores are visible.  The epilogue warps use this to hand a TMEM accumulator back to the MMA issuer: the only ordering
+// they need (tcgen05.ld complete -> tcgen05.mma may overwrite) is given by tcgen05.wait::ld + fence::before_thread_sync;
+// their output stores have no business delaying the next tile (ncu: 20 % of the epilogue's stall samples sat there).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
