@@ -235,7 +235,7 @@ def ncu_traffic(precision):
     """DRAM bytes per step of the dominant kernel family from the committed ncu metrics pass (profiles/): sum of
     dram__bytes_read.sum + dram__bytes_write.sum over the step's conv_gemm_kernel / conv_halo_kernel launches of the
     encoder (bf16 operand instantiations).  None when the profile is missing or was taken in another mode."""
-    path = os.path.join(ROOT, "profiles", "r01_step_kernels_v2.json")
+    path = os.path.join(ROOT, "profiles", "r01_step_kernels_final.json")
     if not os.path.exists(path):
         return None, None
     d = json.load(open(path)).get(precision)
@@ -243,7 +243,7 @@ def ncu_traffic(precision):
         return None, None
     tot = sum(v["dram_bytes"] for k, v in d.items()
               if (k.startswith("conv_gemm_kernel") and k.endswith(", 0>")) or k.startswith("conv_halo_kernel"))
-    return tot, "profiles/r01_step_kernels_v2.json"
+    return tot, "profiles/r01_step_kernels_final.json"
 
 
 def line_for(precision, r, args, world, peaks):
