@@ -21,6 +21,13 @@ namespace {
 
 thread_local char g_err[512] = "";
 int g_debug[16] = {0};
+// measurement only: device buffer of [slots][148][8] int64 wait-cycle counters, one slot per conv / wgrad launch
+long long* g_dbg_buf = nullptr;
+int g_dbg_slots = 0, g_dbg_next = 0;
+long long* next_dbg_slot() {
+  if (!g_dbg_buf || g_dbg_next >= g_dbg_slots) return nullptr;
+  return g_dbg_buf + (size_t)(g_dbg_next++) * 148 * 8;
+}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -363,6 +370,12 @@ int32_t fcn8_set_sm_limit(int32_t n) {
   g_sm_limit = n > 0 ? n : 0;
   return 0;
 }
+int32_t fcn8_debug_buffer(void* buf, int32_t slots) {
+  g_dbg_buf = static_cast<long long*>(buf);
+  g_dbg_slots = buf ? slots : 0;
+  g_dbg_next = 0;
+  return 0;
+}
 int32_t fcn8_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
   g_debug[key] = value;
@@ -440,6 +453,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   }
   ConvGemmArgs a;
   memset(&a, 0, sizeof(a));
+  a.dbg = next_dbg_slot();
   a.out = p->out;
   a.bias = p->bias;
   a.mask_src = p->mask_src;
@@ -464,6 +478,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
   a.flags = p->flags & (31 | 64 | 128);
+  if (g_debug[3] & 1) a.flags |= EPI_DBG_NOSTORE;
+  if (g_debug[3] & 2) a.flags |= EPI_DBG_NOLOAD;
   a.colsum = p->colsum;
   a.seed_ptr = p->seed_ptr;
   {
@@ -633,6 +649,7 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   }
   WgradArgs a;
   memset(&a, 0, sizeof(a));
+  a.dbg = next_dbg_slot();
   a.out = p->dw;
   a.partial = static_cast<float*>(workspace);
   a.N = p->N;

@@ -35,6 +35,8 @@ enum EpilogueFlags : int {
   EPI_RESIDUAL = 16, // + residual[index]                      (gradient fan-in at pool3 / pool4)
   EPI_PARTIAL = 32,  // raw fp32 partial sums to the split-K workspace, no epilogue math
   EPI_ROUND_TF32 = 64,  // fp32 outputs rounded to the nearest tf32 (single-pass tf32 mode: the MMA truncates operands)
+  EPI_DBG_NOSTORE = 1 << 20,  // measurement only (fcn8_debug_set(3, 1)): the epilogue skips its output stores
+  EPI_DBG_NOLOAD = 1 << 21,   // measurement only (fcn8_debug_set(3, 2)): ... and its mask / residual loads
   EPI_COLSUM = 128,     // colsum[col] += sum over rows of the final values (the bias gradient of the layer whose dY
                         // this dgrad produces): per-CTA shared-memory accumulation, one global atomic per column
 };
@@ -109,6 +111,10 @@ struct ConvGemmArgs {
   // kRzBiasPerMma per accumulation step given the final value (measured, scripts/bringup.py::rz_accumulation_probe).
   // acc_scale = 1 + (MMAs accumulated into one accumulator) * kRzBiasPerMma multiplies the accumulator in the epilogue.
   float acc_scale;
+  // measurement only (fcn8_debug_buffer): when set, CTA b writes dbg[8b + 0..3] = cycles its MMA warp spent in the
+  // tile loop / waiting for operand stages (full barriers) / waiting for a free accumulator, and k-blocks issued;
+  // dbg[8b + 4] = cycles the TMA producer waited for free stages
+  long long* dbg;
 };
 constexpr float kRzBiasPerMma = 2.1e-8f;
 
@@ -190,7 +196,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
       f[4 * i + 3] += b.w;
     }
   }
-  if (g.flags & EPI_RESIDUAL) {
+  if ((g.flags & EPI_RESIDUAL) && !(g.flags & EPI_DBG_NOLOAD)) {
     const OutT* r = reinterpret_cast<const OutT*>(g.residual) + idx;
     if constexpr (TF32) {
       const float4* r4 = reinterpret_cast<const float4*>(r);
@@ -240,7 +246,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     for (int i = 0; i < 32; ++i)
       f[i] = dropout_keep(seed, static_cast<uint64_t>(dense_idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
   }
-  if (g.flags & EPI_MASK) {
+  if ((g.flags & EPI_MASK) && !(g.flags & EPI_DBG_NOLOAD)) {
     const OutT* m = reinterpret_cast<const OutT*>(g.mask_src) + idx;
     if constexpr (TF32) {
       const float4* m4 = reinterpret_cast<const float4*>(m);
@@ -274,6 +280,13 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     for (int i = 0; i < 32; ++i) t[i] = f[i];
     const float cs = warp_colsum32(t, lane);
     atomicAdd(&colsum_s[c0 + lane], cs);
+  }
+  if (g.flags & EPI_DBG_NOSTORE) {
+    float keep = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) keep += f[i];
+    if (keep == 123.456f) *reinterpret_cast<float*>(o) = keep;   // keeps the math alive
+    return;
   }
   if constexpr (TF32) {
     if (g.flags & EPI_ROUND_TF32) {
@@ -427,6 +440,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     {
       int stage = 0;
       uint32_t phase = 0;
+      long long dbg_wait_empty = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nb = t % g.tiles_n;
         const int mt = (t / g.tiles_n) % m_tiles;
@@ -444,7 +458,9 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         int kh = tap / g.taps_w;
         int kw = tap - kh * g.taps_w;
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long tw = g.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (g.dbg) dbg_wait_empty += clock64() - tw;
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (elect_one()) {
@@ -487,6 +503,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           }
         }
       }
+      if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 4] = dbg_wait_empty;
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
@@ -506,15 +523,24 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
+    const long long dbg_t0 = g.dbg ? clock64() : 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int sp = t / (g.tiles_n * m_tiles);
       const int kb0 = sp * g.kb_per_split;
       const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+      long long tw = g.dbg ? clock64() : 0;
       mbar_wait(&acc_empty[as], aphase ^ 1);
+      if (g.dbg) dbg_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (g.dbg) tw = clock64();
         mbar_wait(&full_bar[stage], phase);
+        if (g.dbg) {
+          dbg_full += clock64() - tw;
+          ++dbg_kb;
+        }
         tc_fence_after();
         const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
         const uint64_t adesc = adesc0 | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
@@ -539,6 +565,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         as = 0;
         aphase ^= 1;
       }
+    }
+    if (g.dbg && lane == 0) {
+      g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
+      g.dbg[8 * blockIdx.x + 1] = dbg_full;
+      g.dbg[8 * blockIdx.x + 2] = dbg_acc;
+      g.dbg[8 * blockIdx.x + 3] = dbg_kb;
     }
   } else {
     // ============================== epilogue ==============================
@@ -825,6 +857,7 @@ struct WgradArgs {
   // output column c = (dy, dx, co) reads row dy = c / blk_row, element c % blk_row of the blocks.
   int b_mode, blk_row;
   float acc_scale;  // round-toward-zero compensation of the TMEM accumulation (see ConvGemmArgs::acc_scale)
+  long long* dbg;   // measurement only: per-CTA wait-cycle counters (see ConvGemmArgs::dbg)
 };
 
 template <int BN, bool TF32>
@@ -961,15 +994,24 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
+    const long long dbg_t0 = g.dbg ? clock64() : 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int sp = t / (g.tiles_n * g.m_tiles);
       const int pb0 = sp * g.pb_per_split;
       const int pb1 = min(total_pb, pb0 + g.pb_per_split);
+      long long tw = g.dbg ? clock64() : 0;
       mbar_wait(&acc_empty[as], aphase ^ 1);
+      if (g.dbg) dbg_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int pb = pb0; pb < pb1; ++pb) {
+        if (g.dbg) tw = clock64();
         mbar_wait(&full_bar[stage], phase);
+        if (g.dbg) {
+          dbg_full += clock64() - tw;
+          ++dbg_kb;
+        }
         tc_fence_after();
         const uint32_t sa = smem_base + stage * kStage;
         const uint64_t adesc = desc0 | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
@@ -994,6 +1036,12 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
         as = 0;
         aphase ^= 1;
       }
+    }
+    if (g.dbg && lane == 0) {
+      g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
+      g.dbg[8 * blockIdx.x + 1] = dbg_full;
+      g.dbg[8 * blockIdx.x + 2] = dbg_acc;
+      g.dbg[8 * blockIdx.x + 3] = dbg_kb;
     }
   } else {
     const int quarter = warp & 3;

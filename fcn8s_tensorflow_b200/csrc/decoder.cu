@@ -56,50 +56,65 @@ __device__ __forceinline__ void st_px(void* x, long long p, int C, int c, float 
 // 1x1 convolutions Cin -> C <= 32 classes (fcn8s_tensorflow.py:171-200) and their gradients.  0.84 GFLOP per c2 step:
 // HBM-bound on the activation tensors, so these are CUDA-core kernels whose job is to touch x / dx exactly once,
 // coalesced, with K and ds staged in shared memory.
-constexpr int kHeadTP = 32;    // pixels per CTA tile
-constexpr int kHeadKC = 128;   // input channels per shared-memory chunk (fwd)
+constexpr int kHeadTP = 32;    // pixels per CTA tile (bwd_x)
+constexpr int kHeadFP = 128;   // pixels per CTA tile (fwd)
+constexpr int kHeadKC = 64;    // input channels per shared-memory chunk (fwd)
 
-// fwd: CTA = 128 threads = 32 pixels x 4 class groups (classes q, q+4, ...); grid.y splits Cin into slices of kslice
-// channels (fc7: 4096 channels but only 2048 pixels); the slices write partial sums [slice][P][C] that
-// head_fwd_reduce_kernel adds in a fixed order (the forward pass stays bit-reproducible).
+// fwd: CTA = 128 threads = 32 pixel groups x 4 class groups; a thread owns 4 pixels (pg, pg+32, pg+64, pg+96) x the
+// classes q, q+4, ... : 4 + C/4 shared-memory reads feed 4*C/4 FMAs per input channel (the one-pixel version was bound
+// by its 6 reads per 5 FMAs).  grid.y splits Cin into slices of kslice channels (fc7: 4096 channels but only 2048
+// pixels); the slices write partial sums [slice][P][C] that head_fwd_reduce_kernel adds in a fixed order (the forward
+// pass stays bit-reproducible).
 template <int FMT>
 __global__ void __launch_bounds__(128)
 head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
                 float* __restrict__ s, long long P, int Cin, int C, float scale, int kslice) {
-  __shared__ float xs[kHeadTP][kHeadKC + 1];
+  __shared__ float xs[kHeadFP][kHeadKC + 1];
   __shared__ float Ks[kHeadKC][CMAX];
-  const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
-  const int pl = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const long long p0 = static_cast<long long>(blockIdx.x) * kHeadFP;
+  const int pg = threadIdx.x >> 2, q = threadIdx.x & 3;
   const int kbeg = blockIdx.y * kslice, kend = min(Cin, kbeg + kslice);
-  float acc[CMAX / 4];
+  float acc[4][CMAX / 4];
 #pragma unroll
-  for (int j = 0; j < CMAX / 4; ++j) acc[j] = 0.f;
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int j = 0; j < CMAX / 4; ++j) acc[u][j] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += kHeadKC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < kHeadTP * kHeadKC; i += 128) {
+    for (int i = threadIdx.x; i < kHeadFP * kHeadKC; i += 128) {
       const int r = i / kHeadKC, c = i % kHeadKC;
       xs[r][c] = (p0 + r < P && k0 + c < kend) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
     }
-    for (int i = threadIdx.x; i < kHeadKC * C; i += 128) {
-      const int r = i / C, c = i % C;
-      Ks[r][c] = (k0 + r < kend) ? __ldg(K + static_cast<size_t>(k0 + r) * C + c) : 0.f;
+    for (int i = threadIdx.x; i < kHeadKC * CMAX; i += 128) {
+      const int r = i / CMAX, c = i % CMAX;
+      Ks[r][c] = (k0 + r < kend && c < C) ? __ldg(K + static_cast<size_t>(k0 + r) * C + c) : 0.f;
     }
     __syncthreads();
 #pragma unroll 4
     for (int ci = 0; ci < kHeadKC; ++ci) {
-      const float xv = xs[pl][ci];
+      float xv[4], kv[CMAX / 4];
 #pragma unroll
-      for (int j = 0; j < CMAX / 4; ++j)
-        if (q + 4 * j < C) acc[j] = fmaf(xv, Ks[ci][q + 4 * j], acc[j]);
+      for (int u = 0; u < 4; ++u) xv[u] = xs[pg + 32 * u][ci];
+#pragma unroll
+      for (int j = 0; j < CMAX / 4; ++j) kv[j] = (q + 4 * j < C) ? Ks[ci][q + 4 * j] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < CMAX / 4; ++j)
+          if (q + 4 * j < C) acc[u][j] = fmaf(xv[u], kv[j], acc[u][j]);
     }
   }
-  if (p0 + pl < P) {
 #pragma unroll
-    for (int j = 0; j < CMAX / 4; ++j)
-      if (q + 4 * j < C) {
-        const float v = scale * acc[j] + (blockIdx.y == 0 ? b[q + 4 * j] : 0.f);
-        s[(static_cast<size_t>(blockIdx.y) * P + p0 + pl) * C + q + 4 * j] = v;   // gridDim.y == 1: s is the output
-      }
+  for (int u = 0; u < 4; ++u) {
+    const long long p = p0 + pg + 32 * u;
+    if (p < P) {
+#pragma unroll
+      for (int j = 0; j < CMAX / 4; ++j)
+        if (q + 4 * j < C) {
+          const float v = scale * acc[u][j] + (blockIdx.y == 0 ? b[q + 4 * j] : 0.f);
+          s[(static_cast<size_t>(blockIdx.y) * P + p) * C + q + 4 * j] = v;   // gridDim.y == 1: s is the output
+        }
+    }
   }
 }
 __global__ void head_fwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ s, size_t n, int slices) {
@@ -117,8 +132,9 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws, long long P,
                   int Cin, int C, long long ppb) {
-  __shared__ float sds[64][CMAX];
+  __shared__ __align__(16) float sds[64][CMAX];
   const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  for (int i = threadIdx.x; i < 64 * CMAX; i += blockDim.x) (&sds[0][0])[i] = 0.f;   // columns >= C stay zero
   const long long p0 = blockIdx.x * ppb;
   const long long p1 = (p0 + ppb < P) ? p0 + ppb : P;
   float acc[CMAX];
@@ -135,10 +151,18 @@ head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, floa
 #pragma unroll
         for (int u = 0; u < 4; ++u) xv[u] = (q + u < np) ? ld_px<FMT>(x, pc + q + u, Cin, ci) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+          const float4* d4 = reinterpret_cast<const float4*>(&sds[q + u][0]);   // broadcast reads, 16 B each
 #pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < C) acc[c] = fmaf(xv[u], sds[q + u][c], acc[c]);
+          for (int c4 = 0; c4 < CMAX / 4; ++c4)
+            if (4 * c4 < C) {
+              const float4 d = d4[c4];
+              acc[4 * c4 + 0] = fmaf(xv[u], d.x, acc[4 * c4 + 0]);
+              acc[4 * c4 + 1] = fmaf(xv[u], d.y, acc[4 * c4 + 1]);
+              acc[4 * c4 + 2] = fmaf(xv[u], d.z, acc[4 * c4 + 2]);
+              acc[4 * c4 + 3] = fmaf(xv[u], d.w, acc[4 * c4 + 3]);
+            }
+        }
       }
     }
   }
@@ -177,11 +201,14 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
                   void* __restrict__ dx, long long P, int Cin, int C, float scale, int mask, float mask_scale) {
-  __shared__ float sds[kHeadTP][CMAX];
+  __shared__ __align__(16) float sds[kHeadTP][CMAX];
   const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
   const int np = static_cast<int>((P - p0 < kHeadTP) ? (P - p0) : kHeadTP);
   const int ci = blockIdx.y * blockDim.x + threadIdx.x;
-  for (int i = threadIdx.x; i < np * C; i += blockDim.x) sds[i / C][i % C] = ds[p0 * C + i];
+  for (int i = threadIdx.x; i < np * CMAX; i += blockDim.x) {
+    const int r = i / CMAX, c = i % CMAX;
+    sds[r][c] = c < C ? ds[(p0 + r) * C + c] : 0.f;
+  }
   float kr[CMAX];
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) kr[c] = (c < C && ci < Cin) ? __ldg(K + static_cast<size_t>(ci) * C + c) * scale : 0.f;
@@ -189,9 +216,16 @@ head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const
   if (ci >= Cin) return;
   for (int q = 0; q < np; ++q) {
     float a = 0.f;
+    const float4* d4 = reinterpret_cast<const float4*>(&sds[q][0]);   // broadcast reads, 16 B each
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) a = fmaf(sds[q][c], kr[c], a);
+    for (int c4 = 0; c4 < CMAX / 4; ++c4)
+      if (4 * c4 < C) {
+        const float4 d = d4[c4];
+        a = fmaf(d.x, kr[4 * c4 + 0], a);
+        a = fmaf(d.y, kr[4 * c4 + 1], a);
+        a = fmaf(d.z, kr[4 * c4 + 2], a);
+        a = fmaf(d.w, kr[4 * c4 + 3], a);
+      }
     if (mask) a = (ld_px<FMT>(x, p0 + q, Cin, ci) > 0.f) ? a * mask_scale : 0.f;
     st_px<FMT>(dx, p0 + q, Cin, ci, a);
   }
@@ -199,14 +233,14 @@ head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const
 
 // enough CTAs to fill the GPU: split Cin when there are few pixel tiles (fc7 at 1/32 resolution)
 int head_fwd_slices(long long P, int Cin) {
-  const long long blocks = (P + kHeadTP - 1) / kHeadTP;
+  const long long blocks = (P + kHeadFP - 1) / kHeadFP;
   int ksplit = 1;
   while (blocks * ksplit < 2 * 148 && Cin / (ksplit * 2) >= 2 * kHeadKC) ksplit *= 2;
   return ksplit;
 }
 cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
                             float scale, int dtype, float* ws, cudaStream_t st) {
-  const int blocks = static_cast<int>((P + kHeadTP - 1) / kHeadTP);
+  const int blocks = static_cast<int>((P + kHeadFP - 1) / kHeadFP);
   const int ksplit = head_fwd_slices(P, Cin);
   const int kslice = (Cin + ksplit - 1) / ksplit;
   float* dst = ksplit > 1 ? ws : s;
@@ -445,140 +479,178 @@ size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s) {
 }
 
 // ------------------------------------------------------------------------------------------------ softmax / xent
-// One CTA works on runs of 128 consecutive pixels of one image row.  Logits (and dlogits) may live inside a padded
-// tensor [N, H+2*pad, W+2*pad, CP] (the blocked output of the tensor-core upscore8 stage); labels, softmax and argmax
-// are dense.  All global traffic is coalesced through shared memory; per-class sums of dlogits (the bias gradient of
-// the last transposed convolution) are accumulated on the way.
-constexpr int kLossPix = 128;
-__global__ void __launch_bounds__(kLossPix)
+// One thread per pixel, no shared memory: a pixel's logits are C <= 32 consecutive floats of one row of a (possibly
+// padded) tensor [N, H+2*pad, W+2*pad, CP] (the blocked output of the tensor-core upscore8 stage), so a thread's
+// float4 loads / stores touch only the sectors of its own row: the traffic is the minimum, every access is
+// independent of every other thread's, and many of them are in flight per thread.  (The earlier version staged
+// 128-pixel runs through shared memory behind two block barriers; it sat at 1.5 TB/s, bound by exposed latency.)
+// Labels (bool one-hot, dense), softmax and argmax outputs are dense.  Per-class sums of dlogits (the bias gradient of
+// the last transposed convolution) are accumulated in registers and reduced once per CTA.
+constexpr int kLossThreads = 128;
+// CM = compile-time bound on the class count (register arrays are sized by it: 4, 20 or 32)
+template <int CM>
+__global__ void __launch_bounds__(kLossThreads)
 softmax_xent_kernel(const float* __restrict__ z, const uint8_t* __restrict__ labels, float* __restrict__ loss_sum,
                     float* __restrict__ dz, float* __restrict__ dbias, float* __restrict__ sm,
                     long long* __restrict__ amax, int N, int H, int W, int C, int CP, int pad, float gscale) {
-  extern __shared__ float sbuf[];              // [kLossPix * CP] logits -> dlogits / softmax
-  uint8_t* slab = reinterpret_cast<uint8_t*>(sbuf + kLossPix * CP);  // [kLossPix * C]
-  __shared__ float sred[kLossPix / 32];
+  __shared__ float sred[kLossThreads / 32];
+  __shared__ float sdb[CMAX];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const int runs_per_row = (W + kLossPix - 1) / kLossPix;
-  const long long total_runs = static_cast<long long>(N) * H * runs_per_row;
+  const long long P = static_cast<long long>(N) * H * W;
+  const bool vec = (C & 3) == 0 && (CP & 3) == 0;   // float4 path (C = 20: 5 loads of the row's 8 float4)
+  const bool want_db = dz && dbias;
   float local_loss = 0.f;
-  float db_acc = 0.f;  // thread c < C accumulates class c
-  for (long long run = blockIdx.x; run < total_runs; run += gridDim.x) {
-    const int rx = static_cast<int>(run % runs_per_row);
-    const int y = static_cast<int>((run / runs_per_row) % H);
-    const int n = static_cast<int>(run / (static_cast<long long>(runs_per_row) * H));
-    const int x0 = rx * kLossPix;
-    const int np = min(kLossPix, W - x0);
-    const size_t zoff = ((static_cast<size_t>(n) * Hp + y + pad) * Wp + x0 + pad) * CP;
-    const size_t poff = (static_cast<size_t>(n) * H + y) * W + x0;
-    __syncthreads();
-    {
-      if ((CP & 3) == 0) {
-        const float4* src = reinterpret_cast<const float4*>(z + zoff);
-        float4* dst = reinterpret_cast<float4*>(sbuf);
-        for (int i = threadIdx.x; i < np * CP / 4; i += kLossPix) dst[i] = __ldg(src + i);
-      } else {
-        for (int i = threadIdx.x; i < np * CP; i += kLossPix) sbuf[i] = __ldg(z + zoff + i);
-      }
-      if (labels) {
-        const uint8_t* ls = labels + poff * C;
-        const int nb = np * C;
-        if ((reinterpret_cast<uintptr_t>(ls) & 3u) == 0 && (nb & 3) == 0) {
-          const uint32_t* s4 = reinterpret_cast<const uint32_t*>(ls);
-          uint32_t* d4 = reinterpret_cast<uint32_t*>(slab);
-          for (int i = threadIdx.x; i < nb / 4; i += kLossPix) d4[i] = __ldg(s4 + i);
-        } else {
-          for (int i = threadIdx.x; i < nb; i += kLossPix) slab[i] = ls[i];
+  float dbr[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) dbr[c] = 0.f;
+  if (threadIdx.x < CMAX) sdb[threadIdx.x] = 0.f;
+  for (long long p = blockIdx.x * static_cast<long long>(kLossThreads) + threadIdx.x; p < P;
+       p += static_cast<long long>(gridDim.x) * kLossThreads) {
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int n = static_cast<int>(p / (static_cast<long long>(W) * H));
+    const size_t zoff = ((static_cast<size_t>(n) * Hp + y + pad) * Wp + x + pad) * CP;
+    float v[CM];
+    if (vec) {
+      const float4* z4 = reinterpret_cast<const float4*>(z + zoff);
+#pragma unroll
+      for (int m = 0; m < CM / 4; ++m)
+        if (4 * m < C) {
+          const float4 q = __ldg(z4 + m);
+          v[4 * m] = q.x;
+          v[4 * m + 1] = q.y;
+          v[4 * m + 2] = q.z;
+          v[4 * m + 3] = q.w;
         }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CM; ++c)
+        if (c < C) v[c] = __ldg(z + zoff + c);
+    }
+    float yv[CM];
+    if (labels) {
+      const uint8_t* lp = labels + p * C;
+      if (vec) {   // C % 4 == 0: the pixel's C label bytes are 4-byte aligned
+        const uint32_t* l4 = reinterpret_cast<const uint32_t*>(lp);
+#pragma unroll
+        for (int m = 0; m < CM / 4; ++m)
+          if (4 * m < C) {
+            const uint32_t w = __ldg(l4 + m);
+            yv[4 * m] = static_cast<float>(w & 0xffu);
+            yv[4 * m + 1] = static_cast<float>((w >> 8) & 0xffu);
+            yv[4 * m + 2] = static_cast<float>((w >> 16) & 0xffu);
+            yv[4 * m + 3] = static_cast<float>(w >> 24);
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+          if (c < C) yv[c] = static_cast<float>(lp[c]);
       }
     }
-    __syncthreads();
-    if (threadIdx.x < np) {
-      float* zp = sbuf + threadIdx.x * CP;
-      float v[CMAX];
-      float mx = -INFINITY;
-      int am = 0;
+    float mx = -INFINITY;
+    int am = 0;
 #pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) {
-          v[c] = zp[c];
-          if (v[c] > mx) {
-            mx = v[c];
-            am = c;
-          }
-        }
-      float se = 0.f;
-      float e[CMAX];
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c)
-        if (c < C) {
-          e[c] = expf(v[c] - mx);
-          se += e[c];
-        }
-      const float inv = 1.f / se;
-      if (amax) amax[poff + threadIdx.x] = am;
-      if (labels) {
-        const float lse = mx + logf(se);
-        const uint8_t* lp = slab + threadIdx.x * C;
-        float ysum = 0.f, yz = 0.f;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) {
-            const float yv = static_cast<float>(lp[c]);
-            ysum += yv;
-            yz += yv * v[c];
-          }
-        local_loss += ysum * lse - yz;
-        if (dz) {
-#pragma unroll
-          for (int c = 0; c < CMAX; ++c)
-            if (c < C) zp[c] = (e[c] * inv * ysum - static_cast<float>(lp[c])) * gscale;
-          for (int c = C; c < CP; ++c) zp[c] = 0.f;
-        }
+    for (int c = 0; c < CM; ++c)
+      if (c < C && v[c] > mx) {
+        mx = v[c];
+        am = c;
       }
-      if (sm && !dz) {
+    float se = 0.f;
+    float e[CM];
 #pragma unroll
-        for (int c = 0; c < CMAX; ++c)
-          if (c < C) zp[c] = e[c] * inv;
+    for (int c = 0; c < CM; ++c) {
+      e[c] = (c < C) ? expf(v[c] - mx) : 0.f;
+      se += e[c];
+    }
+    const float inv = 1.f / se;
+    if (amax) amax[p] = am;
+    bool have_dz = false;
+    if (labels) {
+      const float lse = mx + logf(se);
+      float ysum = 0.f, yz = 0.f;
+#pragma unroll
+      for (int c = 0; c < CM; ++c)
+        if (c < C) {
+          ysum += yv[c];
+          yz += yv[c] * v[c];
+        }
+      local_loss += ysum * lse - yz;
+      if (dz) {
+#pragma unroll
+        for (int c = 0; c < CM; ++c) {
+          e[c] = (c < C) ? (e[c] * inv * ysum - yv[c]) * gscale : 0.f;
+          if (want_db && c < C) dbr[c] += e[c];
+        }
+        have_dz = true;
       }
     }
-    __syncthreads();
-    if (dz) {
+    if (have_dz) {
+      // the whole padded row is written (zeros beyond C): the transposed-convolution gradient GEMMs read CP channels
       if ((CP & 3) == 0) {
-        const float4* src = reinterpret_cast<const float4*>(sbuf);
-        float4* dst = reinterpret_cast<float4*>(dz + zoff);
-        for (int i = threadIdx.x; i < np * CP / 4; i += kLossPix) dst[i] = src[i];
+        float4* d4 = reinterpret_cast<float4*>(dz + zoff);
+#pragma unroll
+        for (int m = 0; m < CMAX / 4; ++m)
+          if (4 * m < CP) {
+            if (m < CM / 4)
+              d4[m] = make_float4(e[4 * (m < CM / 4 ? m : 0)], e[4 * (m < CM / 4 ? m : 0) + 1],
+                                  e[4 * (m < CM / 4 ? m : 0) + 2], e[4 * (m < CM / 4 ? m : 0) + 3]);
+            else
+              d4[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
       } else {
-        for (int i = threadIdx.x; i < np * CP; i += kLossPix) dz[zoff + i] = sbuf[i];
-      }
-      if (dbias && threadIdx.x < C) {
-        float a = 0.f;
-        for (int q = 0; q < np; ++q) a += sbuf[q * CP + threadIdx.x];
-        db_acc += a;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < CP) dz[zoff + c] = c < CM ? e[c < CM ? c : 0] : 0.f;
       }
     } else if (sm) {
-      float* dst = sm + poff * C;  // dense [.., C]
-      for (int i = threadIdx.x; i < np * C; i += kLossPix) dst[i] = sbuf[(i / C) * CP + (i % C)];
+      float* dst = sm + p * C;   // dense [.., C]
+      if (vec) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+        for (int m = 0; m < CM / 4; ++m)
+          if (4 * m < C)
+            d4[m] = make_float4(e[4 * m] * inv, e[4 * m + 1] * inv, e[4 * m + 2] * inv, e[4 * m + 3] * inv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+          if (c < C) dst[c] = e[c] * inv;
+      }
     }
   }
+  __syncthreads();
   if (loss_sum) {
     for (int o = 16; o > 0; o >>= 1) local_loss += __shfl_xor_sync(0xffffffffu, local_loss, o);
     if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = local_loss;
     __syncthreads();
     if (threadIdx.x == 0) {
       float t = 0.f;
-      for (int k = 0; k < kLossPix / 32; ++k) t += sred[k];
+      for (int k = 0; k < kLossThreads / 32; ++k) t += sred[k];
       atomicAdd(loss_sum, t);
     }
   }
-  if (dz && dbias && threadIdx.x < C) atomicAdd(dbias + threadIdx.x, db_acc);
+  if (want_db) {
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+      if (c < C) {
+        float a = dbr[c];
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sdb[c], a);
+      }
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(dbias + threadIdx.x, sdb[threadIdx.x]);
+  }
 }
 cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* dbias,
                                 float* sm, long long* amax, int N, int H, int W, int C, int CP, int pad, float gscale,
                                 cudaStream_t st) {
-  const long long runs = static_cast<long long>(N) * H * ((W + kLossPix - 1) / kLossPix);
-  const int blocks = static_cast<int>(runs < 148 * 16 ? runs : 148 * 16);   // 16 CTAs of 128 threads per SM
-  const size_t smem = static_cast<size_t>(kLossPix) * CP * sizeof(float) + static_cast<size_t>(kLossPix) * C;
-  { count_launch(); softmax_xent_kernel<<<blocks, kLossPix, smem, st>>>(z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
+  const long long P = static_cast<long long>(N) * H * W;
+  const long long want = (P + kLossThreads - 1) / kLossThreads;
+  const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+#define CALL(CM) { count_launch(); softmax_xent_kernel<CM><<<blocks, kLossThreads, 0, st>>>(z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
+  if (C <= 4) CALL(4)
+  else if (C <= 20) CALL(20)
+  else CALL(32)
+#undef CALL
   return cudaGetLastError();
 }
 

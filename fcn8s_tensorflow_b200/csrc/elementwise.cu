@@ -566,9 +566,47 @@ __global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, fl
     reinterpret_cast<float4*>(out)[i] = a;
   }
 }
+// Small outputs with many splits (conv1_x / conv2_x filter gradients: 1.7 K ... 150 K elements, up to 148 splits): one
+// thread per element would leave most SMs idle in a long serial loop, so 8 threads share an element's splits and a
+// shared-memory tree adds their sums in a fixed order.
+__global__ void __launch_bounds__(256)
+wgrad_splitk_reduce_wide_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
+                                size_t rows_pad, int rows_valid, int ldc) {
+  __shared__ float4 red[8][32];
+  const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
+  const size_t split_stride = rows_pad * ldc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const size_t i = static_cast<size_t>(blockIdx.x) * 32 + tx;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4)
+    for (int s = ty; s < splits; s += 8) {
+      const float4 p = *reinterpret_cast<const float4*>(partial + s * split_stride + i * 4);
+      a.x += p.x;
+      a.y += p.y;
+      a.z += p.z;
+      a.w += p.w;
+    }
+  red[ty][tx] = a;
+  __syncthreads();
+  if (ty == 0 && i < n4) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 p = red[k][tx];
+      a.x += p.x;
+      a.y += p.y;
+      a.z += p.z;
+      a.w += p.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  }
+}
 cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
                                        int ldc, cudaStream_t st) {
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
+  if (splits >= 16 && n4 <= static_cast<size_t>(148) * 256 * 2) {
+    { count_launch(); wgrad_splitk_reduce_wide_kernel<<<static_cast<unsigned>((n4 + 31) / 32), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc); }
+    return cudaGetLastError();
+  }
   { count_launch(); wgrad_splitk_reduce_kernel<<<grid_for(n4, 256), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc); }
   return cudaGetLastError();
 }

@@ -69,6 +69,10 @@ int32_t fcn8_set_sm_limit(int32_t n);
  * (the library multiplies every tcgen05 accumulator by 1 + n_mma * 2.1e-8, the expected relative loss of TMEM's
  * truncating accumulation over n_mma instructions; scripts/bringup.py::rz_accumulation_probe measures the constant). */
 int32_t fcn8_debug_set(int32_t key, int32_t value);
+/* Measurement only: `buf` = device buffer of slots*148*8 int64; every following fcn8_conv_gemm / fcn8_wgrad_gemm launch
+ * takes the next slot and its CTAs write their MMA-warp wait-cycle counters there (csrc/conv_gemm.cuh,
+ * ConvGemmArgs::dbg).  NULL switches it off. */
+int32_t fcn8_debug_buffer(void* buf, int32_t slots);
 
 /* ---- feed: fcn8s_tensorflow.py:558,686,765 (image_input) + the encoder graph's RGB->BGR / mean subtraction [EXT].
  * uint8 RGB [N,H,W,3] -> im2col of the mean-subtracted BGR image for conv1_1: out[N,H,W,KP], column tap*3+c
