@@ -234,6 +234,32 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
   return cudaGetLastError();
 }
 
+// CTA-pair variant (clusters of two CTAs, tcgen05 cta_group::2): bf16 operands, 256-column tiles; `grid` is even.
+cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<256, true>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, true>, maps, a);
+}
+
 template <int BN, bool RB = false>
 cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   static bool attr_done = false;
@@ -430,6 +456,9 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     pl.m_tiles = pl.tiles_x * pl.tiles_y * pl.tiles_b;
     pl.splits = 1;
   }
+  // CTA pairs for the 256-column bf16 tiles of the per-tap kernel (debug key 5 = 1 keeps the single-CTA kernel)
+  const bool use_pair = !use_halo && pl.BN == 256 && p->dtype == FCN8_BF16 && !g_debug[5];
+  const int b_rows = use_pair ? pl.BN / 2 : pl.BN;   // rows of the weight tile one CTA loads
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
   const int ktot = p->ksize * p->ksize * p->Cin;
@@ -444,11 +473,11 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
                           1 << pl.lbn, false, p->x_ld);
     if (rc) return rc;
     if (p->w_mode == 0)
-      rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, pl.BN);
+      rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, b_rows);
     else if (p->w_mode == 1)
       rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64, use_halo && pl.BN == 64 ? 3 : 1);
     else
-      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, pl.BN, use_halo && pl.BN == 64 ? 3 : 1);
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, b_rows, use_halo && pl.BN == 64 ? 3 : 1);
     if (rc) return rc;
   }
   ConvGemmArgs a;
@@ -520,6 +549,11 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   const bool tf32 = p->dtype == FCN8_F32;
+  if (use_pair) {
+    const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n * pl.splits;
+    const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
+    e = launch_conv_pair(maps, kernel_args, 2 * pairs, st);
+  } else
 #define FCN8_DISPATCH(BNV)                                                    \
   e = tf32 ? launch_conv_t<BNV, true>(maps, kernel_args, grid, st)          \
            : launch_conv_t<BNV, false>(maps, kernel_args, grid, st)

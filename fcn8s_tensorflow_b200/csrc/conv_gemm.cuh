@@ -123,11 +123,16 @@ struct TensorMaps3 {
   CUtensorMap b[3];
 };
 
-template <int BN>
+// PAIR: the kernel runs as clusters of two CTAs on one SM pair (tcgen05 cta_group::2).  Each CTA owns one 128-row M
+// tile and loads its own A tile but only HALF of the B tile; the leader issues M = 256 MMAs over both CTAs' shared
+// memory.  Per k-block a CTA then streams 32 KB instead of 48 KB through TMA and shared memory, and six stages fit
+// where four did -- the single-CTA kernel's main loop is bound by exactly that (wait-cycle profile: profiles/).
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = 128 * 128;  // 128 rows x 128 B
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;
+  static constexpr int kBBytes = kBRows * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
   static constexpr int kBarBytes = 1024;
@@ -321,10 +326,13 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
 // ------------------------------------------------------------------------------------------------------------------
 // Epilogue warps (4 warps, one TMEM lane quarter each) of the implicit-GEMM convolution kernels: persistent loop over
 // the CTA's tiles, TMEM -> registers -> epilogue math -> global.
-template <int BN, bool TF32>
+// PAIR (CTA pairs, see GemmCfg): `total_tiles` / `m_tiles` count PAIRS of M tiles, CTA `rank` of the pair owns M tile
+// 2 * pair + rank (a partner past the last tile computes on zero-filled operands and stores nothing), and the
+// accumulator is handed back on the leader CTA's barrier.
+template <int BN, bool TF32, bool PAIR = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
                                                    uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
-                                                   int warp, int lane) {
+                                                   int warp, int lane, uint32_t rank = 0) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
     const int row = quarter * 32 + lane;
@@ -332,9 +340,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
     uint32_t aphase = 0;
     const size_t out_elems = static_cast<size_t>(g.N) * g.H * g.W * g.ldc;
     const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t lead_acc_empty = PAIR ? map_to_cta(smem_u32(acc_empty), 0) : 0;
+    const int t_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+    for (int t = PAIR ? blockIdx.x >> 1 : blockIdx.x; t < total_tiles; t += t_step) {
       const int nb = t % g.tiles_n;
-      const int mt = (t / g.tiles_n) % m_tiles;
+      const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
       const int sp = t / (g.tiles_n * m_tiles);
       const int tx = mt % g.tiles_x;
       const int ty = (mt / g.tiles_x) % g.tiles_y;
@@ -358,7 +368,12 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
           // the warp's last chunk is in registers: hand the accumulator stage back BEFORE the math and the stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
+          if (lane == 0) {
+            if (PAIR)
+              mbar_arrive_cluster(lead_acc_empty + as * 8);
+            else
+              mbar_arrive_relaxed(&acc_empty[as]);
+          }
         }
         const int c0 = nb * BN + c;
         if (g.flags & EPI_PARTIAL) {
@@ -389,10 +404,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
   }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN, bool TF32>
+template <int BN, bool TF32, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
-  using Cfg = GemmCfg<BN>;
+  static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -409,8 +425,13 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   if (g.flags & EPI_COLSUM)
     for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
 
-  const int m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  // scheduling units: M tiles, or (PAIR) pairs of consecutive M tiles, one per CTA of the cluster
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const int real_m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  const int m_tiles = PAIR ? (real_m_tiles + 1) / 2 : real_m_tiles;
   const int total_tiles = m_tiles * g.tiles_n * g.splits;
+  const int t_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int t_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int kb_per_seg = g.taps * g.cblocks;
   const int total_kb = g.nseg * kb_per_seg;
 
@@ -420,18 +441,25 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       tma_prefetch_desc(&maps.b[s]);
     }
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], PAIR ? 2 : 1);   // pair: the leader's expect_tx arrive + the partner's plain arrive
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps);
+      mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before anything is signalled across
+  if (warp == 1) {
+    if (PAIR)
+      tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else
+      tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -441,9 +469,9 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       int stage = 0;
       uint32_t phase = 0;
       long long dbg_wait_empty = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int nb = t % g.tiles_n;
-        const int mt = (t / g.tiles_n) % m_tiles;
+        const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
         const int sp = t / (g.tiles_n * m_tiles);
         const int tx = mt % g.tiles_x;
         const int ty = (mt / g.tiles_x) % g.tiles_y;
@@ -463,7 +491,28 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           if (g.dbg) dbg_wait_empty += clock64() - tw;
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (elect_one()) {
+          if (PAIR) {
+            // operands land in this CTA's shared memory, their bytes are counted on the leader's barrier; an M tile
+            // past the end (odd tile count) reads rows outside the tensor: zero-filled by TMA
+            if (elect_one()) {
+              const uint32_t lead_bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0)
+                mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              else
+                mbar_arrive_cluster(lead_bar);
+              tma_load_4d_pair(&maps.a[seg], lead_bar, sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
+              const int nrow = nb * BN + static_cast<int>(rank) * (BN / 2);
+              if (g.b_mode == 0) {
+                tma_load_2d_pair(&maps.b[seg], lead_bar, sb, (tap * g.cblocks + cb) * CH, nrow);
+              } else if (g.b_mode == 1) {
+                tma_load_3d_pair(&maps.b[seg], lead_bar, sb, cb * CH, nrow, g.taps - 1 - tap);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  tma_load_3d_pair(&maps.b[seg], lead_bar, sb + j * 8192, nrow + j * 64, cb * CH, tap);
+              }
+            }
+          } else if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             if (g.a_mode == 0) {
               tma_load_4d(&maps.a[seg], &full_bar[stage], sa, cb * CH, x0 + kw - g.pad, y0 + kh - g.pad, n0);
@@ -505,14 +554,14 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       }
       if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 4] = dbg_wait_empty;
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == 1 && rank == 0) {
+    // ============================== MMA issuer (the leader CTA of a pair issues for both) ==============================
     // The WHOLE warp runs this loop: its control flow and every address / descriptor are then warp-uniform and live in
     // uniform registers, and one elected lane issues the tcgen05 instructions.  (With the loop inside `if (lane == 0)`
     // the compiler wraps every UTCHMMA operand in ELECT + R2UR.BROADCAST: ~600 cycles of issue overhead per k-block,
     // measured with ncu's source view, which capped the tensor pipe at ~65 % for N = 256 and ~20 % for N = 64 tiles.)
     const bool b_mn = g.b_mode == 2;  // B = [64 k][64 n] MN-major chunks (bf16 only)
-    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, b_mn ? 1u : 0u, 128u, BN);
+    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 0u, b_mn ? 1u : 0u, PAIR ? 256u : 128u, BN);
     // K-major B: 128-byte rows, +32 B per MMA; MN-major B: LBO = 8 KB between 64-wide N chunks, SBO = 1 KB between
     // 8-row K groups, +16 K-rows (2 KB) per MMA
     const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 1024);
@@ -525,7 +574,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     uint32_t aphase = 0;
     long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
     const long long dbg_t0 = g.dbg ? clock64() : 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int sp = t / (g.tiles_n * m_tiles);
       const int kb0 = sp * g.kb_per_split;
       const int kb1 = min(total_kb, kb0 + g.kb_per_split);
@@ -549,9 +598,15 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // A: advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (PAIR)
+            umma_commit_pair(&empty_bar[stage], 3);   // frees the stage in both CTAs
+          else
+            umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -559,7 +614,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&acc_full[as]);
+      if (elect_one()) {
+        if constexpr (PAIR)
+          umma_commit_pair(&acc_full[as], 3);   // the accumulator halves of both CTAs are complete
+        else
+          umma_commit(&acc_full[as]);
+      }
       __syncwarp();
       if (++as == 2) {
         as = 0;
@@ -572,16 +632,21 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;
       g.dbg[8 * blockIdx.x + 3] = dbg_kb;
     }
-  } else {
+  } else if (warp >= 2) {
     // ============================== epilogue ==============================
-    conv_epilogue_loop<BN, TF32>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane);
+    conv_epilogue_loop<BN, TF32, PAIR>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane,
+                                       rank);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // nobody leaves while the partner may still read its operands or signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR)
+      tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else
+      tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
   if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL))
     for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {

@@ -32,6 +32,36 @@ __device__ __forceinline__ float ld_px(const void* x, long long p, int C, int c)
     return __bfloat162float(b[0]) + __bfloat162float(b[C]);
   }
 }
+// 8 consecutive channels c .. c+7 of pixel p (c and C multiples of 8): 16-byte loads
+template <int FMT>
+__device__ __forceinline__ void ld_px8(const void* x, long long p, int C, int c, float (&f)[8]) {
+  if constexpr (FMT == 1) {
+    const float4* q = reinterpret_cast<const float4*>(static_cast<const float*>(x) + p * C + c);
+    const float4 a = __ldg(q), b = __ldg(q + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(x) + p * (FMT == 2 ? 2 : 1) * C + c;
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(base));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&h);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h2[j]);
+      f[2 * j] = t.x;
+      f[2 * j + 1] = t.y;
+    }
+    if constexpr (FMT == 2) {
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(base + C));
+      const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(l2[j]);
+        f[2 * j] += t.x;
+        f[2 * j + 1] += t.y;
+      }
+    }
+  }
+}
 template <int FMT>
 __device__ __forceinline__ void st_px(void* x, long long p, int C, int c, float v) {
   if constexpr (FMT == 1) {
@@ -81,9 +111,25 @@ head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const f
     for (int j = 0; j < CMAX / 4; ++j) acc[u][j] = 0.f;
   for (int k0 = kbeg; k0 < kend; k0 += kHeadKC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < kHeadFP * kHeadKC; i += 128) {
-      const int r = i / kHeadKC, c = i % kHeadKC;
-      xs[r][c] = (p0 + r < P && k0 + c < kend) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
+    if ((Cin & 7) == 0 && k0 + kHeadKC <= kend) {
+      // 8 channels (16 bytes of bf16) per load: the activation tile is the only large operand of this kernel
+      for (int i = threadIdx.x; i < kHeadFP * (kHeadKC / 8); i += 128) {
+        const int r = i / (kHeadKC / 8), c = (i % (kHeadKC / 8)) * 8;
+        float f[8];
+        if (p0 + r < P) {
+          ld_px8<FMT>(x, p0 + r, Cin, k0 + c, f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xs[r][c + j] = f[j];
+      }
+    } else {
+      for (int i = threadIdx.x; i < kHeadFP * kHeadKC; i += 128) {
+        const int r = i / kHeadKC, c = i % kHeadKC;
+        xs[r][c] = (p0 + r < P && k0 + c < kend) ? ld_px<FMT>(x, p0 + r, Cin, k0 + c) : 0.f;
+      }
     }
     for (int i = threadIdx.x; i < kHeadKC * CMAX; i += 128) {
       const int r = i / CMAX, c = i % CMAX;

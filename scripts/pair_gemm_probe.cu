@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta)
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of a CTA pair: data lands in the issuing CTA's shared memory, the bytes are counted on `bar_cluster_addr`
 // (the leader CTA's barrier).
@@ -74,6 +74,32 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
           smem_u32(bar)),
       "h"(mask)
       : "memory");
+}
+
+// Barrier wait without the suspend-time hint of ptx.cuh's mbar_wait: a tight test_wait spin.  -DSPIN_WAIT=1 uses it for
+// every wait of this file (question: do waits that are completed by a REMOTE CTA wake up late when the warp sleeps?)
+#ifndef SPIN_WAIT
+#define SPIN_WAIT 0
+#endif
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+#if SPIN_WAIT
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000ll) __trap();
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 
 template <bool PAIR>
@@ -140,7 +166,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     for (int u = unit; u < unit_tiles; u += units) {
       const int mt = PAIR ? 2 * u + rank : u;
       for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        wait_bar(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * C::kStage;
           uint8_t* sb = sa + C::kABytes;
@@ -174,11 +200,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int u = unit; u < unit_tiles; u += units) {
-        mbar_wait(&acc_empty[as], aphase ^ 1);
+        wait_bar(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          wait_bar(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = sbase + stage * C::kStage;
           const uint64_t adesc = desc0 | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
@@ -223,7 +249,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const uint32_t lead_acc_empty0 = PAIR ? map_to_cta(smem_u32(&acc_empty[0]), 0) : 0;
     for (int u = unit; u < unit_tiles; u += units) {
       const int mt = PAIR ? 2 * u + rank : u;
-      mbar_wait(&acc_full[as], aphase);
+      wait_bar(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       float* dst = D + (static_cast<size_t>(mt) * 128 + quarter * 32 + lane) * BN;

@@ -51,13 +51,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
 }
 
-// MODE 0 unicast 48 KB, 1 unicast 32 KB, 2 multicast pair
+// MODE 0 unicast 48 KB, 1 unicast 32 KB, 2 multicast pair,
+// 3 multicast pair WITHOUT the cross-CTA release of the stages (unsafe for real data; prices the multicast alone),
+// 4 pair with unicast loads but WITH the cross-CTA stage release (prices the remote barrier arrives alone)
 template <int MODE, int kStages>
 __global__ void __launch_bounds__(64, 1)
 feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -67,16 +69,19 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
   const int warp = threadIdx.x >> 5;
-  const uint32_t rank = MODE == 2 ? cluster_ctarank() : 0;
+  constexpr bool kCluster = MODE >= 2;
+  constexpr bool kMulticast = MODE == 2 || MODE == 3;
+  constexpr bool kRemoteRelease = MODE == 2 || MODE == 4;
+  const uint32_t rank = kCluster ? cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MODE == 2 ? 2 : 1);
+      mbar_init(&empty_bar[s], kRemoteRelease ? 2 : 1);
     }
     fence_mbar_init();
   }
   __syncthreads();
-  if (MODE == 2) cluster_sync_all();
+  if (kCluster) cluster_sync_all();
   const int row_a = (blockIdx.x % a_tiles) * 128;
   const uint32_t rx_bytes = MODE == 1 ? kABytes + kBBytes / 2 : kStage;
   long long t0 = clock64(), t1 = t0;
@@ -91,7 +96,7 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], rx_bytes);
           tma_load_2d(&map_a, &full_bar[stage], sa, (kb % a_kblocks) * 64, row_a);
-          if (MODE == 0) {
+          if (MODE == 0 || MODE == 4) {
             tma_load_2d(&map_b, &full_bar[stage], sb, kb * 64, 0);
           } else if (MODE == 1) {
             tma_load_2d(&map_bh, &full_bar[stage], sb, kb * 64, 0);
@@ -117,7 +122,7 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         if (elect_one()) {
           mbar_arrive(&empty_bar[stage]);
-          if (MODE == 2) mbar_arrive_remote(&empty_bar[stage], rank ^ 1);
+          if (kRemoteRelease) mbar_arrive_remote(&empty_bar[stage], rank ^ 1);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -129,7 +134,7 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if ((threadIdx.x & 31) == 0) cycles[blockIdx.x] = t1 - t0;
   }
   __syncthreads();
-  if (MODE == 2) cluster_sync_all();
+  if (kCluster) cluster_sync_all();
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -162,7 +167,7 @@ struct Variant {
 template <int MODE, int kStages>
 static void run(const Variant& v, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbh, int sms,
                 long long* d_cycles) {
-  const double rx_kb = MODE == 1 ? 32 : 48, l2_kb = MODE == 0 ? 48 : 32;
+  const double rx_kb = MODE == 1 ? 32 : 48, l2_kb = (MODE == 0 || MODE == 4) ? 48 : 32;
   const int reps = 10;
   const int smem = kStages * kStage + 1024;
   cudaFuncSetAttribute(feed_kernel<MODE, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -172,7 +177,7 @@ static void run(const Variant& v, const CUtensorMap& ma, const CUtensorMap& mb, 
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MODE == 2 ? 2 : 1;
+  attr[0].val.clusterDim.x = MODE >= 2 ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -197,7 +202,7 @@ static void run(const Variant& v, const CUtensorMap& ma, const CUtensorMap& mb, 
   for (long long c : h) sum += double(c);
   const double blocks = double(reps) * kKBlocks;
   const double cyc = sum / sms / blocks;
-  static const char* mode_name[3] = {"unicast 48K", "unicast 32K", "multicast pair"};
+  static const char* mode_name[5] = {"unicast 48K", "unicast 32K", "multicast pair", "mcast, local rel", "ucast, remote rel"};
   printf("%-14s %d stages  %-44s hold %4d: %6.0f cyc/k-block  arrive %6.1f B/clk/SM  L2 %6.2f TB/s chip (%.3f ms)\n",
          mode_name[MODE], kStages, v.name, v.delay, cyc, rx_kb * 1024 / cyc,
          l2_kb * 1024 * blocks * sms / (ms * 1e-3) / 1e12, ms);
@@ -247,7 +252,7 @@ int main() {
   run<0, 4>(v, ma, mb, mbh, sms, d_cycles);
   run<1, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
   run<2, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
-  v = own_l2; v.delay = 687;
-  run<2, 4>(v, ma, mb, mbh, sms, d_cycles);
+  run<3, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
+  run<4, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
   return 0;
 }
