@@ -295,6 +295,31 @@ cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid
   return cudaGetLastError();
 }
 
+cudaError_t launch_wgrad_pair(const TensorMaps3& maps, const WgradArgs& a, int grid, cudaStream_t st) {
+  constexpr int smem = 3 * (4 * 128 * 128) + 1024 + 1024;   // three stages of (2 + 2) 128-pixel chunks
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<256, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<256, false, true>, maps, a);
+}
+
 cudaError_t dispatch_conv(int BN, bool tf32, const TensorMaps3& maps, const ConvGemmArgs& a, int grid,
                           cudaStream_t st) {
   if (BN == 256) return tf32 ? launch_conv_t<256, true>(maps, a, grid, st) : launch_conv_t<256, false>(maps, a, grid, st);
@@ -332,6 +357,7 @@ int encode_blocked_map(CUtensorMap* m, const void* ptr, int N, int Hb, int Wb, i
 }
 
 struct WgradPlan {
+  bool pair;   // CTA-pair kernel (bf16, 256-column tiles): two M tiles per cluster
   int BN, splits, pb_per_split, total_pb;
   int lbw, lbh, lbn, pb_x, pb_y, pb_b;
   int m_tiles, tiles_n, total_chunks;
@@ -353,14 +379,16 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   const int mch = 128 / CH;
   pl->m_tiles = (pl->total_chunks + mch - 1) / mch;
   pl->rows_pad = (size_t)pl->m_tiles * 128;
-  const int pix_log = p->dtype == FCN8_BF16 ? 7 : 6;   // = log2(WgradPix<BN, TF32>::value)
+  pl->pair = bn == 256 && p->dtype == FCN8_BF16 && !g_debug[5];
+  const int pix_log = pl->pair ? 7 : (p->dtype == FCN8_BF16 ? 7 : 6);   // = log2(pixels per pipeline stage)
   choose_patch(p->N, p->H, p->W, pix_log, &pl->lbw, &pl->lbh, &pl->lbn);
   pl->pb_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->pb_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
   pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
   pl->total_pb = p->nseg * pl->pb_x * pl->pb_y * pl->pb_b;
-  const int sms = num_sms();
-  const long long tiles = (long long)pl->m_tiles * pl->tiles_n;
+  // CTAs that work at the same time: one per SM; a pair kernel schedules pairs of M tiles on SM pairs
+  const int sms = pl->pair ? num_sms() / 2 : num_sms();
+  const long long tiles = (long long)(pl->pair ? (pl->m_tiles + 1) / 2 : pl->m_tiles) * pl->tiles_n;
   int splits = 1;
   if (p->force_splits > 0) {
     splits = p->force_splits;
@@ -720,7 +748,11 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   const bool tf32 = p->dtype == FCN8_F32;
 #define FCN8_DISPATCH(BNV) \
   e = tf32 ? launch_wgrad_t<BNV, true>(maps, a, grid, st) : launch_wgrad_t<BNV, false>(maps, a, grid, st)
-  if (pl.BN == 256) {
+  if (pl.pair) {
+    const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n * pl.splits;
+    const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
+    e = launch_wgrad_pair(maps, a, 2 * pairs, st);
+  } else if (pl.BN == 256) {
     FCN8_DISPATCH(256);
   } else if (pl.BN == 128) {
     FCN8_DISPATCH(128);

@@ -930,17 +930,21 @@ struct WgradPix {
   static constexpr int value = !TF32 ? 128 : 64;
 };
 
-template <int BN, bool TF32>
+// PAIR: CTA pairs as in conv_gemm_kernel -- the two CTAs own consecutive M tiles (rows of the flattened filter), share
+// the pixel range and the N tile, and each loads half of the dY tile: 64 KB per 128-pixel stage, three stages (six
+// 64-pixel stages of 32 KB measured 8 % slower: twice the TMA operations per MMA).
+template <int BN, bool TF32, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
+  static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
   using Cfg = GemmCfg<BN>;
   constexpr int CH = TF32 ? 32 : 64;
   // pixels (K) per pipeline stage: 128 for the narrow bf16 tiles, whose per-stage MMA time would otherwise be shorter
   // than the issue + barrier round trip of a stage; 64 where shared memory is tight (BN = 256) and for tf32
-  constexpr int PIX = WgradPix<BN, TF32>::value;
+  constexpr int PIX = PAIR ? 128 : WgradPix<BN, TF32>::value;
   constexpr int kChunkBytes = PIX * 128;       // PIX pixels x 128 B
   constexpr int MCH = 128 / CH;                // A chunks per M tile
-  constexpr int NCH = BN / CH;                 // B chunks per N tile
+  constexpr int NCH = (PAIR ? BN / 2 : BN) / CH;   // B chunks per N tile that this CTA loads
   constexpr int kAStage = MCH * kChunkBytes;   // 16 KB bf16 / 32 KB tf32
   constexpr int kBStage = NCH * kChunkBytes;
   constexpr int kStage = kAStage + kBStage;
@@ -957,7 +961,11 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.m_tiles * g.tiles_n * g.splits;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const int m_sched = PAIR ? (g.m_tiles + 1) / 2 : g.m_tiles;   // scheduling units along M: tiles or pairs of tiles
+  const int total_tiles = m_sched * g.tiles_n * g.splits;
+  const int t_first = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const int t_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int pb_per_seg = g.pb_x * g.pb_y * g.pb_b;
   const int total_pb = g.nseg * pb_per_seg;
   const int cin_chunks = g.Cin / CH;
@@ -968,18 +976,25 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
       tma_prefetch_desc(&maps.b[s]);
     }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], PAIR ? 2 : 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps);
+      mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (PAIR) cluster_sync_all();
+  if (warp == 1) {
+    if (PAIR)
+      tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else
+      tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -987,10 +1002,10 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     {   // TMA producer: whole warp runs the uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = t_first; t < total_tiles; t += t_step) {
         const int nb = t % g.tiles_n;
-        const int mt = (t / g.tiles_n) % g.m_tiles;
-        const int sp = t / (g.tiles_n * g.m_tiles);
+        const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_sched) + static_cast<int>(rank) : (t / g.tiles_n) % m_sched;
+        const int sp = t / (g.tiles_n * m_sched);
         // per-chunk tap offsets for this M tile
         int ccb[MCH], cdx[MCH], cdy[MCH];
         int nvalid = 0;
@@ -1022,7 +1037,24 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStage;
           uint8_t* sb = sa + kAStage;
-          if (elect_one()) {
+          if (PAIR) {
+            // every chunk is loaded (rows past the filter read channel 0 / tap 0 and are never stored), so both CTAs
+            // always deliver kStage bytes to the leader's barrier
+            if (elect_one()) {
+              const uint32_t lead_bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+              if (rank == 0)
+                mbar_expect_tx(&full_bar[stage], 2 * kStage);
+              else
+                mbar_arrive_cluster(lead_bar);
+#pragma unroll
+              for (int c = 0; c < MCH; ++c)
+                tma_load_4d_pair(&maps.a[seg], lead_bar, sa + c * kChunkBytes, ccb[c], x0 + cdx[c], y0 + cdy[c], n0);
+#pragma unroll
+              for (int j = 0; j < NCH; ++j)
+                tma_load_4d_pair(&maps.b[seg], lead_bar, sb + j * kChunkBytes,
+                                 nb * BN + (static_cast<int>(rank) * NCH + j) * CH, x0, y0, n0);
+            }
+          } else if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
             for (int c = 0; c < MCH; ++c)
@@ -1048,9 +1080,9 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // MMA issuer: whole warp runs the uniform loop, one elected lane issues (see conv_gemm_kernel)
-    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, 128u, BN);
+    const uint32_t idesc = make_idesc(TF32 ? 2u : 1u, 1u, 1u, PAIR ? 256u : 128u, BN);
     // MN-major, 128B swizzle: LBO = stride between 128-byte channel chunks, SBO = stride between 8-pixel groups
     // (tf32: 32-byte-granule swizzle, 4-pixel / 512-byte atoms -- the only MN-major layout the tf32 MMA accepts)
     const uint64_t desc0 = make_smem_desc_sw128(0, kChunkBytes, TF32 ? 512 : 1024, TF32 ? 1u : 2u);
@@ -1061,8 +1093,8 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     uint32_t aphase = 0;
     long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
     const long long dbg_t0 = g.dbg ? clock64() : 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int sp = t / (g.tiles_n * g.m_tiles);
+    for (int t = t_first; t < total_tiles; t += t_step) {
+      const int sp = t / (g.tiles_n * m_sched);
       const int pb0 = sp * g.pb_per_split;
       const int pb1 = min(total_pb, pb0 + g.pb_per_split);
       long long tw = g.dbg ? clock64() : 0;
@@ -1085,9 +1117,15 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
 #pragma unroll
           for (int k = 0; k < PIX / KPM; ++k) {
             const uint32_t adv = (k * KPM * 128) >> 4;
-            umma_issue<TF32>(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_f16_pair(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
+            else
+              umma_issue<TF32>(d_tmem, adesc + adv, bdesc + adv, idesc, (pb > pb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (PAIR)
+            umma_commit_pair(&empty_bar[stage], 3);
+          else
+            umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -1095,7 +1133,12 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&acc_full[as]);
+      if (elect_one()) {
+        if constexpr (PAIR)
+          umma_commit_pair(&acc_full[as], 3);
+        else
+          umma_commit(&acc_full[as]);
+      }
       __syncwarp();
       if (++as == 2) {
         as = 0;
@@ -1108,24 +1151,25 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;
       g.dbg[8 * blockIdx.x + 3] = dbg_kb;
     }
-  } else {
+  } else if (warp >= 2) {
     const int quarter = warp & 3;
     const int chalf = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
     const size_t rows_pad = static_cast<size_t>(g.m_tiles) * 128;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const uint32_t lead_acc_empty = PAIR ? map_to_cta(smem_u32(acc_empty), 0) : 0;
+    for (int t = t_first; t < total_tiles; t += t_step) {
       const int nb = t % g.tiles_n;
-      const int mt = (t / g.tiles_n) % g.m_tiles;
-      const int sp = t / (g.tiles_n * g.m_tiles);
+      const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_sched) + static_cast<int>(rank) : (t / g.tiles_n) % m_sched;
+      const int sp = t / (g.tiles_n * m_sched);
       const int grow = mt * 128 + row;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       float* dst = (g.flags & EPI_PARTIAL) ? g.partial + (static_cast<size_t>(sp) * rows_pad + grow) * g.ldc
                                            : g.out + static_cast<size_t>(grow) * g.ldc;
-      const bool valid = (g.flags & EPI_PARTIAL) ? true : (grow < g.rows_valid);
+      const bool valid = (mt < g.m_tiles) && ((g.flags & EPI_PARTIAL) ? true : (grow < g.rows_valid));
 #pragma unroll 1
       for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         uint32_t v[32];
@@ -1142,7 +1186,12 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(lead_acc_empty + as * 8);
+        else
+          mbar_arrive_relaxed(&acc_empty[as]);
+      }
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -1152,9 +1201,13 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR)
+      tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else
+      tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
