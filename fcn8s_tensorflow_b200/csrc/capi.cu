@@ -15,6 +15,7 @@ using namespace fcn8;
 
 namespace fcn8 {
 unsigned long long g_launch_count = 0;
+int g_pdl_off = 1;
 }
 
 namespace {
@@ -230,7 +231,7 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  { count_launch(); conv_gemm_kernel<BN, TF32><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, a); }
+  (void)launch_k(conv_gemm_kernel<BN, TF32>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, maps, a);
   return cudaGetLastError();
 }
 
@@ -249,13 +250,15 @@ cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_off ? 1 : 2;
   count_launch();
   return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, true>, maps, a);
 }
@@ -269,7 +272,7 @@ cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  { count_launch(); conv_halo_kernel<BN, RB><<<grid, kGemmThreads, HaloSmem<BN, RB>::kBytes, st>>>(maps, a); }
+  (void)launch_k(conv_halo_kernel<BN, RB>, dim3(grid), dim3(kGemmThreads), HaloSmem<BN, RB>::kBytes, st, maps, a);
   return cudaGetLastError();
 }
 
@@ -291,7 +294,7 @@ cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  { count_launch(); wgrad_gemm_kernel<BN, TF32><<<grid, kGemmThreads, smem, st>>>(maps, a); }
+  (void)launch_k(wgrad_gemm_kernel<BN, TF32>, dim3(grid), dim3(kGemmThreads), smem, st, maps, a);
   return cudaGetLastError();
 }
 
@@ -309,13 +312,15 @@ cudaError_t launch_wgrad_pair(const TensorMaps3& maps, const WgradArgs& a, int g
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_off ? 1 : 2;
   count_launch();
   return cudaLaunchKernelEx(&cfg, wgrad_gemm_kernel<256, false, true>, maps, a);
 }
@@ -433,6 +438,7 @@ int32_t fcn8_debug_buffer(void* buf, int32_t slots) {
 int32_t fcn8_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
   g_debug[key] = value;
+  if (key == 6) g_pdl_off = !value;
   return 0;
 }
 
@@ -681,7 +687,7 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
       attr_done = true;
     }
     cudaStream_t hst = (cudaStream_t)stream;
-    { count_launch(); wgrad_halo_kernel<64><<<hp.tiles_n * hp.splits, kGemmThreads, WgradHaloCfg::kSmemBytes, hst>>>(hm, ha); }
+    (void)launch_k(wgrad_halo_kernel<64>, dim3(hp.tiles_n * hp.splits), dim3(kGemmThreads), WgradHaloCfg::kSmemBytes, hst, hm, ha);
     cudaError_t he = cudaGetLastError();
     if (he != cudaSuccess) return cuda_fail(he, "wgrad_halo launch");
     he = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, hp.splits, 640, 576, p->Cout, hst);

@@ -23,6 +23,7 @@
 
 #include <type_traits>
 
+#include "kernels.h"
 #include "ptx.cuh"
 
 namespace fcn8 {
@@ -407,6 +408,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
 template <int BN, bool TF32, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
+  pdl_launch_dependents();
   static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
@@ -462,6 +464,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     // ============================== TMA producer (whole warp, one elected lane issues) ==============================
@@ -687,6 +690,7 @@ struct HaloSmem {
 template <int BN, bool RB = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
+  pdl_launch_dependents();
   static_assert(!RB || BN == 64, "resident weights only for the N = 64 tiles");
   using HS = HaloSmem<BN, RB>;
   constexpr int kAS = HS::kAStages, kBS = HS::kBStages;
@@ -735,6 +739,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     // ============================== TMA producer (whole warp, one elected lane issues) ==============================
@@ -936,6 +941,7 @@ struct WgradPix {
 template <int BN, bool TF32, bool PAIR = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
+  pdl_launch_dependents();
   static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
   using Cfg = GemmCfg<BN>;
   constexpr int CH = TF32 ? 32 : 64;
@@ -997,6 +1003,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
   if (PAIR) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     {   // TMA producer: whole warp runs the uniform loop, one elected lane issues
@@ -1241,6 +1248,7 @@ struct WgradHaloCfg {
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 wgrad_halo_kernel(const __grid_constant__ TensorMaps3 maps, const WgradHaloArgs g) {
+  pdl_launch_dependents();
   static_assert(BN == 64, "one 64-column slice per CTA");
   using Cfg = WgradHaloCfg;
   extern __shared__ uint8_t smem_raw[];
@@ -1276,6 +1284,7 @@ wgrad_halo_kernel(const __grid_constant__ TensorMaps3 maps, const WgradHaloArgs 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
   if (warp == 0) {
     int stage = 0;

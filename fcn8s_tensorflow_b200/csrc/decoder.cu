@@ -99,6 +99,8 @@ template <int FMT>
 __global__ void __launch_bounds__(128)
 head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ b,
                 float* __restrict__ s, long long P, int Cin, int C, float scale, int kslice) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float xs[kHeadFP][kHeadKC + 1];
   __shared__ float Ks[kHeadKC][CMAX];
   const long long p0 = static_cast<long long>(blockIdx.x) * kHeadFP;
@@ -164,6 +166,8 @@ head_fwd_kernel(const void* __restrict__ x, const float* __restrict__ K, const f
   }
 }
 __global__ void head_fwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ s, size_t n, int slices) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float a = 0.f;
@@ -178,6 +182,8 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, float* __restrict__ ws, long long P,
                   int Cin, int C, long long ppb) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float sds[64][CMAX];
   const int ci = blockIdx.y * blockDim.x + threadIdx.x;
   for (int i = threadIdx.x; i < 64 * CMAX; i += blockDim.x) (&sds[0][0])[i] = 0.f;   // columns >= C stay zero
@@ -222,6 +228,8 @@ head_bwd_w_kernel(const void* __restrict__ x, const float* __restrict__ ds, floa
 // column sums of ds [P][C] -> partial [nb][C]
 __global__ void rows_colsum_kernel(const float* __restrict__ ds, float* __restrict__ ws, long long P, int C,
                                    long long ppb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long p0 = blockIdx.x * ppb;
   const long long p1 = (p0 + ppb < P) ? p0 + ppb : P;
   __shared__ float red[256];
@@ -247,6 +255,8 @@ template <int FMT>
 __global__ void __launch_bounds__(256)
 head_bwd_x_kernel(const void* __restrict__ x, const float* __restrict__ K, const float* __restrict__ ds,
                   void* __restrict__ dx, long long P, int Cin, int C, float scale, int mask, float mask_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float sds[kHeadTP][CMAX];
   const long long p0 = static_cast<long long>(blockIdx.x) * kHeadTP;
   const int np = static_cast<int>((P - p0 < kHeadTP) ? (P - p0) : kHeadTP);
@@ -291,12 +301,12 @@ cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float
   const int kslice = (Cin + ksplit - 1) / ksplit;
   float* dst = ksplit > 1 ? ws : s;
   dim3 grid(blocks, ksplit);
-#define CALL(F) { count_launch(); head_fwd_kernel<F><<<grid, 128, 0, st>>>(x, K, b, dst, P, Cin, C, scale, kslice); }
+#define CALL(F) { (void)launch_k(head_fwd_kernel<F>, dim3(grid), dim3(128), 0, st, x, K, b, dst, P, Cin, C, scale, kslice); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   if (ksplit > 1) {
     const size_t n = static_cast<size_t>(P) * C;
-    { count_launch(); head_fwd_reduce_kernel<<<grid_for(n, 256), 256, 0, st>>>(ws, s, n, ksplit); }
+    { (void)launch_k(head_fwd_reduce_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, ws, s, n, ksplit); }
   }
   return cudaGetLastError();
 }
@@ -314,17 +324,17 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
   float* ws_k = ws;                                          // [nb][Cin][C]
   float* ws_b = ws + static_cast<size_t>(nb) * Cin * C;      // [nb][C]
   dim3 grid(nb, (Cin + 255) / 256);
-#define CALL(F) { count_launch(); head_bwd_w_kernel<F><<<grid, 256, 0, st>>>(x, ds, ws_k, P, Cin, C, ppb); }
+#define CALL(F) { (void)launch_k(head_bwd_w_kernel<F>, dim3(grid), dim3(256), 0, st, x, ds, ws_k, P, Cin, C, ppb); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
-  { count_launch(); rows_colsum_kernel<<<nb, 256, 0, st>>>(ds, ws_b, P, C, ppb); }
+  { (void)launch_k(rows_colsum_kernel, dim3(nb), dim3(256), 0, st, ds, ws_b, P, C, ppb); }
   cudaError_t e = launch_colsum(ws_k, dK, nb, Cin * C, scale, 0, st);
   if (e != cudaSuccess) return e;
   e = launch_colsum(ws_b, db, nb, C, 1.f, 0, st);
   if (e != cudaSuccess) return e;
   if (dx) {
     dim3 gx(static_cast<unsigned>((P + kHeadTP - 1) / kHeadTP), (Cin + 255) / 256);
-#define CALL(F) { count_launch(); head_bwd_x_kernel<F><<<gx, 256, 0, st>>>(x, K, ds, dx, P, Cin, C, scale, mask, mask_scale); }
+#define CALL(F) { (void)launch_k(head_bwd_x_kernel<F>, dim3(gx), dim3(256), 0, st, x, K, ds, dx, P, Cin, C, scale, mask, mask_scale); }
     FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   }
@@ -340,6 +350,8 @@ cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, floa
 __global__ void upscore_fwd_kernel(const float* __restrict__ x, const float* __restrict__ T,
                                    const float* __restrict__ bias, const float* __restrict__ skip,
                                    float* __restrict__ y, int N, int h, int w, int C, int s) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sT[];  // [k*k][C][C+1]  (a*k+b, co, ci)
   const int p = s / 2, k = 2 * s, CP1 = C + 1;
   for (int i = threadIdx.x; i < k * k * C * C; i += blockDim.x) {
@@ -376,6 +388,8 @@ __global__ void upscore_fwd_kernel(const float* __restrict__ x, const float* __r
 // the filter in shared memory (ci fastest: conflict-free), dy rows broadcast across the C threads of a pixel.
 __global__ void upscore_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ T, float* __restrict__ dx,
                                      int N, int h, int w, int C, int s) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sT[];  // [k*k][C][C]
   const int p = s / 2, k = 2 * s;
   for (int i = threadIdx.x; i < k * k * C * C; i += blockDim.x) sT[i] = T[i];
@@ -409,6 +423,8 @@ __global__ void upscore_bwd_x_kernel(const float* __restrict__ dy, const float* 
 // dT[a,b,co,ci] partials: CTA (tap, split) reduces its share of the input pixels; thread owns a 2x2 (co,ci) tile.
 __global__ void upscore_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ ws,
                                      int N, int h, int w, int C, int s, int nsplit) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sx[32][CMAX];
   __shared__ float sg[32][CMAX];
   const int p = s / 2, k = 2 * s;
@@ -479,7 +495,7 @@ cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias
                                        static_cast<int>(sm));
   if (e != cudaSuccess) return e;
   const size_t total = static_cast<size_t>(N) * h * s * w * s * C;
-  { count_launch(); upscore_fwd_kernel<<<grid_for(total, 256, 148 * 4), 256, sm, st>>>(x, T, bias, skip, y, N, h, w, C, s); }
+  { (void)launch_k(upscore_fwd_kernel, dim3(grid_for(total, 256, 148 * 4)), dim3(256), sm, st, x, T, bias, skip, y, N, h, w, C, s); }
   return cudaGetLastError();
 }
 int upscore_bwd_splits(int N, int h, int w, int s) {
@@ -499,7 +515,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
   {
     const int nb = head_bwd_blocks(Pout);
     const long long ppb = (Pout + nb - 1) / nb;
-    { count_launch(); rows_colsum_kernel<<<nb, 256, 0, st>>>(dy, ws, Pout, C, ppb); }
+    { (void)launch_k(rows_colsum_kernel, dim3(nb), dim3(256), 0, st, dy, ws, Pout, C, ppb); }
     cudaError_t e = launch_colsum(ws, dbias, nb, C, 1.f, 0, st);
     if (e != cudaSuccess) return e;
   }
@@ -507,7 +523,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
   {
     const int nsplit = upscore_bwd_splits(N, h, w, s);
     dim3 grid(k * k, nsplit);
-    { count_launch(); upscore_bwd_w_kernel<<<grid, 256, 0, st>>>(x, dy, ws + 128 * CMAX, N, h, w, C, s, nsplit); }
+    { (void)launch_k(upscore_bwd_w_kernel, dim3(grid), dim3(256), 0, st, x, dy, ws + 128 * CMAX, N, h, w, C, s, nsplit); }
     cudaError_t e = launch_colsum(ws + 128 * CMAX, dT, nsplit, k * k * C * C, 1.f, 0, st);
     if (e != cudaSuccess) return e;
   }
@@ -516,7 +532,7 @@ cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, 
     const size_t sm = upscore_smem_bytes(C, s, false);
     if (sm > 200 * 1024) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(upscore_bwd_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm));
-    { count_launch(); upscore_bwd_x_kernel<<<grid_for(total, 128, 148 * 8), 128, sm, st>>>(dy, T, dx, N, h, w, C, s); }
+    { (void)launch_k(upscore_bwd_x_kernel, dim3(grid_for(total, 128, 148 * 8)), dim3(128), sm, st, dy, T, dx, N, h, w, C, s); }
   }
   return cudaGetLastError();
 }
@@ -539,6 +555,8 @@ __global__ void __launch_bounds__(kLossThreads)
 softmax_xent_kernel(const float* __restrict__ z, const uint8_t* __restrict__ labels, float* __restrict__ loss_sum,
                     float* __restrict__ dz, float* __restrict__ dbias, float* __restrict__ sm,
                     long long* __restrict__ amax, int N, int H, int W, int C, int CP, int pad, float gscale) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sred[kLossThreads / 32];
   __shared__ float sdb[CMAX];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
@@ -692,7 +710,7 @@ cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* lo
   const long long P = static_cast<long long>(N) * H * W;
   const long long want = (P + kLossThreads - 1) / kLossThreads;
   const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-#define CALL(CM) { count_launch(); softmax_xent_kernel<CM><<<blocks, kLossThreads, 0, st>>>(z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
+#define CALL(CM) { (void)launch_k(softmax_xent_kernel<CM>, dim3(blocks), dim3(kLossThreads), 0, st, z, labels, loss_sum, dz, dbias, sm, amax, N, H, W, C, CP, pad, gscale); }
   if (C <= 4) CALL(4)
   else if (C <= 20) CALL(20)
   else CALL(32)
@@ -724,6 +742,8 @@ __device__ __forceinline__ void put_split(float* hi, float* lo, size_t i, float 
 __global__ void upscore_pack_kernel(const float* __restrict__ T, const float* __restrict__ bias, float* w_fwd,
                                     float* w_fwd_lo, float* w_dx, float* w_dx_lo, float* bias_big, int C, int CP,
                                     int s) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = 2 * s;
   const int ncols = s * s * CP;
   const size_t n_fwd = static_cast<size_t>(ncols) * 128;
@@ -756,7 +776,7 @@ __global__ void upscore_pack_kernel(const float* __restrict__ T, const float* __
 cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd, float* w_fwd_lo, float* w_dx,
                                 float* w_dx_lo, float* bias_big, int C, int CP, int s, cudaStream_t st) {
   const size_t total = static_cast<size_t>(s) * s * CP * (128 + 256 + 1);
-  { count_launch(); upscore_pack_kernel<<<grid_for(total, 256), 256, 0, st>>>(T, bias, w_fwd, w_fwd_lo, w_dx, w_dx_lo, bias_big, C, CP, s); }
+  { (void)launch_k(upscore_pack_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, T, bias, w_fwd, w_fwd_lo, w_dx, w_dx_lo, bias_big, C, CP, s); }
   return cudaGetLastError();
 }
 // Interior of a padded blocked transposed-conv output (+ the skip tensor): f[n,y,x,c] = zp[n,y+pad,x+pad,c] + skip[n,y,x,c]
@@ -764,6 +784,8 @@ cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd,
 __global__ void upscore_gather_kernel(const float* __restrict__ zp, const float* __restrict__ skip,
                                       float* __restrict__ f, int N, int H, int W, int C, int CP, int pad, int ldf,
                                       int ld_skip) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Wp = W + 2 * pad, Hp = H + 2 * pad;
   const size_t total = static_cast<size_t>(N) * H * W * ldf;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -785,6 +807,8 @@ __global__ void upscore_gather_kernel(const float* __restrict__ zp, const float*
 // The reverse for the gradient: dzp interior = g (border and channels >= C stay zero), db[c] += sum over pixels of g.
 __global__ void upscore_scatter_kernel(const float* __restrict__ g, float* __restrict__ dzp, float* __restrict__ db,
                                        int N, int H, int W, int C, int CP, int pad, int ldg) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sdb[CMAX];
   if (threadIdx.x < CMAX) sdb[threadIdx.x] = 0.f;
   __syncthreads();
@@ -808,19 +832,21 @@ __global__ void upscore_scatter_kernel(const float* __restrict__ g, float* __res
 cudaError_t launch_upscore_gather(const float* zp, const float* skip, float* f, int N, int H, int W, int C, int CP,
                                   int pad, int ldf, int ld_skip, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * H * W * ldf;
-  { count_launch(); upscore_gather_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, st>>>(zp, skip, f, N, H, W, C, CP, pad, ldf, ld_skip); }
+  { (void)launch_k(upscore_gather_kernel, dim3(grid_for(total, 256, 148 * 8)), dim3(256), 0, st, zp, skip, f, N, H, W, C, CP, pad, ldf, ld_skip); }
   return cudaGetLastError();
 }
 cudaError_t launch_upscore_scatter(const float* g, float* dzp, float* db, int N, int H, int W, int C, int CP, int pad,
                                    int ldg, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * H * W * C;
-  { count_launch(); upscore_scatter_kernel<<<grid_for(total, 256, 148 * 2), 256, 0, st>>>(g, dzp, db, N, H, W, C, CP, pad, ldg); }
+  { (void)launch_k(upscore_scatter_kernel, dim3(grid_for(total, 256, 148 * 2)), dim3(256), 0, st, g, dzp, db, N, H, W, C, CP, pad, ldg); }
   return cudaGetLastError();
 }
 
 // dT[a][b][co][ci] = sum_split src[split][(ty,tx,ci)][(dy,dx,co)]
 __global__ void upscore_unpack_dw_kernel(const float* __restrict__ src, int nsplit, float* __restrict__ dT, int C,
                                          int CP, int s) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int k = 2 * s;
   const int ncols = s * s * CP;
   const int total = k * k * C * C;
@@ -836,13 +862,15 @@ __global__ void upscore_unpack_dw_kernel(const float* __restrict__ src, int nspl
 }
 cudaError_t launch_upscore_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st) {
   const int total = 4 * s * s * C * C;
-  { count_launch(); upscore_unpack_dw_kernel<<<(total + 255) / 256, 256, 0, st>>>(src, nsplit, dT, C, CP, s); }
+  { (void)launch_k(upscore_unpack_dw_kernel, dim3((total + 255) / 256), dim3(256), 0, st, src, nsplit, dT, C, CP, s); }
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ confusion matrix
 __global__ void confusion_kernel(const long long* __restrict__ pred, const uint8_t* __restrict__ onehot,
                                  unsigned long long* __restrict__ conf, long long P, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ unsigned int hist[CMAX * CMAX];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
   __syncthreads();
@@ -866,7 +894,7 @@ __global__ void confusion_kernel(const long long* __restrict__ pred, const uint8
 }
 cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
                              cudaStream_t st) {
-  { count_launch(); confusion_kernel<<<grid_for(P, 256, 148 * 4), 256, 0, st>>>(pred, onehot, conf, P, C); }
+  { (void)launch_k(confusion_kernel, dim3(grid_for(P, 256, 148 * 4)), dim3(256), 0, st, pred, onehot, conf, P, C); }
   return cudaGetLastError();
 }
 

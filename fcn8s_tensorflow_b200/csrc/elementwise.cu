@@ -95,6 +95,8 @@ struct Act<2> {
 template <int FMT>
 __global__ void __launch_bounds__(128)
 preprocess_im2col_kernel(const uint8_t* __restrict__ img, typename Act<FMT>::T* __restrict__ out, int N, int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   using A = Act<FMT>;
   constexpr int VEC = A::N;
   constexpr int KP = FMT == 1 ? 32 : 64;
@@ -139,7 +141,7 @@ preprocess_im2col_kernel(const uint8_t* __restrict__ img, typename Act<FMT>::T* 
 cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W, int dtype, cudaStream_t st) {
   const long long tiles = static_cast<long long>(N) * H * ((W + 127) / 128);
   const int blocks = static_cast<int>(tiles < 148 * 16 ? tiles : 148 * 16);
-#define CALL(F) { count_launch(); preprocess_im2col_kernel<F><<<blocks, 128, 0, st>>>(img, static_cast<typename Act<F>::T*>(out), N, H, W); }
+#define CALL(F) { (void)launch_k(preprocess_im2col_kernel<F>, dim3(blocks), dim3(128), 0, st, img, static_cast<typename Act<F>::T*>(out), N, H, W); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -149,6 +151,8 @@ cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W
 template <int FMT>
 __global__ void maxpool_fwd_kernel(const typename Act<FMT>::T* __restrict__ x, typename Act<FMT>::T* __restrict__ y,
                                    int N, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   using V = Act<FMT>;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
@@ -189,6 +193,8 @@ template <int FMT>
 __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
                                    const typename Act<FMT>::T* __restrict__ dy, typename Act<FMT>::T* __restrict__ dx,
                                    float* __restrict__ db, int N, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   using V = Act<FMT>;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
   const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
@@ -261,7 +267,7 @@ static inline int act_vec(int dtype) { return dtype == 1 ? 4 : 8; }
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
   const int blocks = grid_for(total, 256);
-#define CALL(F) { count_launch(); maxpool_fwd_kernel<F><<<blocks, 256, 0, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<typename Act<F>::T*>(y), N, H, W, C); }
+#define CALL(F) { (void)launch_k(maxpool_fwd_kernel<F>, dim3(blocks), dim3(256), 0, st, static_cast<const typename Act<F>::T*>(x), static_cast<typename Act<F>::T*>(y), N, H, W, C); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -271,7 +277,7 @@ cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* d
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
   const int blocks = grid_for(total, 256);   // 256 % CV == 0 for every VGG width, so the grid stride keeps cv fixed
   const size_t sm = db ? static_cast<size_t>(C) * sizeof(float) : 0;
-#define CALL(F) { count_launch(); maxpool_bwd_kernel<F><<<blocks, 256, sm, st>>>(static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), db, N, H, W, C); }
+#define CALL(F) { (void)launch_k(maxpool_bwd_kernel<F>, dim3(blocks), dim3(256), sm, st, static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), db, N, H, W, C); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -282,6 +288,8 @@ cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* d
 template <int FMT>
 __global__ void bias_grad_stage1(const typename Act<FMT>::T* __restrict__ dy, float* __restrict__ ws, long long P,
                                  int C, int cvb, long long rpb) {
+  pdl_launch_dependents();
+  pdl_wait();
   using V = Act<FMT>;
   extern __shared__ float sred[];  // [RL][cvb*VN]
   const int RL = blockDim.x / cvb;
@@ -316,6 +324,8 @@ __global__ void bias_grad_stage1(const typename Act<FMT>::T* __restrict__ dy, fl
 // out[c] = scale * sum_b ws[b][c]: one warp per column group so that the nb partial rows are read in parallel.
 __global__ void colsum_stage2(const float* __restrict__ ws, float* __restrict__ out, int nb, int C, float scale,
                               int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5, nparts = blockDim.x >> 5;
   __shared__ float red[8][33];
@@ -338,7 +348,7 @@ int bias_grad_blocks(long long P, int C) {
   return static_cast<int>(nb);
 }
 cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st) {
-  { count_launch(); colsum_stage2<<<(C + 31) / 32, 256, 0, st>>>(ws, out, nb, C, scale, accumulate); }
+  { (void)launch_k(colsum_stage2, dim3((C + 31) / 32), dim3(256), 0, st, ws, out, nb, C, scale, accumulate); }
   return cudaGetLastError();
 }
 cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st) {
@@ -350,7 +360,7 @@ cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int 
   dim3 grid(nb, CV / cvb);
   const int RL = 256 / cvb;
   const size_t sm = static_cast<size_t>(RL) * cvb * vec * sizeof(float);
-#define CALL(F) { count_launch(); bias_grad_stage1<F><<<grid, 256, sm, st>>>(static_cast<const typename Act<F>::T*>(dy), ws, P, C, cvb, rpb); }
+#define CALL(F) { (void)launch_k(bias_grad_stage1<F>, dim3(grid), dim3(256), sm, st, static_cast<const typename Act<F>::T*>(dy), ws, P, C, cvb, rpb); }
   FCN8_FMT_DISPATCH(dtype, CALL);
 #undef CALL
   return launch_colsum(ws, db, nb, C, 1.f, 0, st);
@@ -388,6 +398,8 @@ __device__ __forceinline__ void store_packed(T* out, T* out_lo, size_t idx, floa
 template <typename T>
 __global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ out, T* __restrict__ out_lo, int taps,
                                   int Cin, int Cout, int CinPad) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
@@ -407,6 +419,8 @@ __global__ void pack_fprop_kernel(const float* __restrict__ w, T* __restrict__ o
 template <typename T>
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, T* __restrict__ out_lo, int taps,
                                   int Cin, int Cout) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t total = static_cast<size_t>(taps) * Cin * Cout;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -424,19 +438,19 @@ cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int 
   if (mode == 0) {
     dim3 grid((Cout + 31) / 32, (CinPad + 31) / 32, taps), block(32, 8);
     if (dtype == 0)
-      { count_launch(); pack_fprop_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
+      { (void)launch_k(pack_fprop_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, st, w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
                                                                Cout, CinPad); }
     else
-      { count_launch(); pack_fprop_kernel<float><<<grid, block, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+      { (void)launch_k(pack_fprop_kernel<float>, dim3(grid), dim3(block), 0, st, w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
                                                        Cin, Cout, CinPad); }
   } else {
     const size_t total = static_cast<size_t>(taps) * Cin * Cout;
     const int blocks = grid_for(total, 256);
     if (dtype == 0)
-      { count_launch(); pack_dgrad_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
+      { (void)launch_k(pack_dgrad_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, w, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), taps, Cin,
                                                                Cout); }
     else
-      { count_launch(); pack_dgrad_kernel<float><<<blocks, 256, 0, st>>>(w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
+      { (void)launch_k(pack_dgrad_kernel<float>, dim3(blocks), dim3(256), 0, st, w, static_cast<float*>(out), static_cast<float*>(out_lo), taps,
                                                        Cin, Cout); }
   }
   return cudaGetLastError();
@@ -447,6 +461,8 @@ cudaError_t launch_pack(const float* w, void* out, void* out_lo, int ksize, int 
 // both:          hi = trunc(x), lo = rna(x - hi)
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
                                   size_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -461,7 +477,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
-  { count_launch(); split_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(x, hi, lo, n / 4); }
+  { (void)launch_k(split_tf32_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, st, x, hi, lo, n / 4); }
   return cudaGetLastError();
 }
 
@@ -471,6 +487,8 @@ cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cu
 template <int FMT>
 __global__ void conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n_elems, int ldc,
                                           ConvGemmArgs g) {
+  pdl_launch_dependents();
+  pdl_wait();
   using V = Act<FMT == 2 ? 0 : FMT>;
   using T = typename V::T;
   const size_t nv = n_elems / V::N;
@@ -542,7 +560,7 @@ cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n
                                       const ConvGemmArgs& g, int dtype, cudaStream_t st) {
   const int fmt = dtype == 1 ? 1 : (g.out_lo ? 2 : 0);
   const int blocks = grid_for(n_elems / act_vec(dtype), 256);
-#define CALL(F) { count_launch(); conv_splitk_reduce_kernel<F><<<blocks, 256, 0, st>>>(partial, splits, n_elems, ldc, g); }
+#define CALL(F) { (void)launch_k(conv_splitk_reduce_kernel<F>, dim3(blocks), dim3(256), 0, st, partial, splits, n_elems, ldc, g); }
   FCN8_FMT_DISPATCH(fmt, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -551,6 +569,8 @@ cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n
 // wgrad: out[r][c] = sum_s partial[s][r][c] for r < rows_valid (partial has rows_pad rows per split).
 __global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
                                            size_t rows_pad, int rows_valid, int ldc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
   const size_t split_stride = rows_pad * ldc;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -572,6 +592,8 @@ __global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, fl
 __global__ void __launch_bounds__(256)
 wgrad_splitk_reduce_wide_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
                                 size_t rows_pad, int rows_valid, int ldc) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float4 red[8][32];
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
   const size_t split_stride = rows_pad * ldc;
@@ -604,10 +626,10 @@ cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int spl
                                        int ldc, cudaStream_t st) {
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
   if (splits >= 16 && n4 <= static_cast<size_t>(148) * 256 * 2) {
-    { count_launch(); wgrad_splitk_reduce_wide_kernel<<<static_cast<unsigned>((n4 + 31) / 32), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc); }
+    { (void)launch_k(wgrad_splitk_reduce_wide_kernel, dim3(static_cast<unsigned>((n4 + 31) / 32)), dim3(256), 0, st, partial, out, splits, rows_pad, rows_valid, ldc); }
     return cudaGetLastError();
   }
-  { count_launch(); wgrad_splitk_reduce_kernel<<<grid_for(n4, 256), 256, 0, st>>>(partial, out, splits, rows_pad, rows_valid, ldc); }
+  { (void)launch_k(wgrad_splitk_reduce_kernel, dim3(grid_for(n4, 256)), dim3(256), 0, st, partial, out, splits, rows_pad, rows_valid, ldc); }
   return cudaGetLastError();
 }
 
@@ -628,6 +650,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps, float gscale,
                             __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo,
                             const float* __restrict__ lr_ptr) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (lr_ptr) lr_t = __ldg(lr_ptr);  // per-step value in device memory (CUDA-graph replays keep kernel arguments)
   const size_t n4 = n / 4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
@@ -666,22 +690,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
                         float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, cudaStream_t st) {
-  { count_launch(); adam_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo), lr_ptr); }
+  { (void)launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, 256, 148 * 8)), dim3(256), 0, st, p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo), lr_ptr); }
   return cudaGetLastError();
 }
 // scalars[0] = lr_t (float), scalars[1] = dropout seed (uint32 bits): written by a kernel (arguments by value) so that
 // a host running many steps ahead of the device never races with a staging buffer.
 __global__ void set_step_scalars_kernel(float* scalars, float lr_t, uint32_t seed) {
+  pdl_launch_dependents();
+  pdl_wait();
   scalars[0] = lr_t;
   reinterpret_cast<uint32_t*>(scalars)[1] = seed;
 }
 cudaError_t launch_set_step_scalars(float* scalars, float lr_t, uint32_t seed, cudaStream_t st) {
-  { count_launch(); set_step_scalars_kernel<<<1, 1, 0, st>>>(scalars, lr_t, seed); }
+  { (void)launch_k(set_step_scalars_kernel, dim3(1), dim3(1), 0, st, scalars, lr_t, seed); }
   return cudaGetLastError();
 }
 // w_hi = bf16(p), w_lo = bf16(p - w_hi): the tensor-core shadow of the fp32 parameters (after load_weights).
 __global__ void shadow_kernel(const float* __restrict__ p, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                               size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n4 = n / 4;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x)
@@ -693,12 +721,14 @@ __global__ void shadow_kernel(const float* __restrict__ p, __nv_bfloat16* __rest
     }
 }
 cudaError_t launch_shadow(const float* p, void* hi, void* lo, size_t n, cudaStream_t st) {
-  { count_launch(); shadow_kernel<<<grid_for(n / 4 + 1, 256, 148 * 8), 256, 0, st>>>(p, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n); }
+  { (void)launch_k(shadow_kernel, dim3(grid_for(n / 4 + 1, 256, 148 * 8)), dim3(256), 0, st, p, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n); }
   return cudaGetLastError();
 }
 
 __global__ void l2_reg_kernel(const float* __restrict__ w, float* __restrict__ g, float* __restrict__ loss, size_t n,
                               float rate) {
+  pdl_launch_dependents();
+  pdl_wait();
   float s = 0.f;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -717,7 +747,7 @@ __global__ void l2_reg_kernel(const float* __restrict__ w, float* __restrict__ g
   }
 }
 cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st) {
-  { count_launch(); l2_reg_kernel<<<grid_for(n, 256, 64), 256, 0, st>>>(w, g, loss, n, rate); }
+  { (void)launch_k(l2_reg_kernel, dim3(grid_for(n, 256, 64)), dim3(256), 0, st, w, g, loss, n, rate); }
   return cudaGetLastError();
 }
 

@@ -30,14 +30,6 @@ constexpr int kBBytes = 256 * 128;
 constexpr int kStage = kABytes + kBBytes;
 constexpr int kKBlocks = 72;         // K = 4608
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
                                                uint16_t mask) {
   asm volatile(
@@ -46,12 +38,13 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* m, uint64_t* b
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+// remote arrive with a CLUSTER-scope release (ptx.cuh's mbar_arrive_cluster uses the default CTA scope): mode 5
+__device__ __forceinline__ void mbar_arrive_remote_release_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -59,7 +52,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 
 // MODE 0 unicast 48 KB, 1 unicast 32 KB, 2 multicast pair,
 // 3 multicast pair WITHOUT the cross-CTA release of the stages (unsafe for real data; prices the multicast alone),
-// 4 pair with unicast loads but WITH the cross-CTA stage release (prices the remote barrier arrives alone)
+// 4 pair with unicast loads but WITH the cross-CTA stage release (prices the remote barrier arrives alone),
+// 5 as 4, the remote arrive with .release.cluster instead of the default CTA-scope release
 template <int MODE, int kStages>
 __global__ void __launch_bounds__(64, 1)
 feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -71,7 +65,7 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   constexpr bool kCluster = MODE >= 2;
   constexpr bool kMulticast = MODE == 2 || MODE == 3;
-  constexpr bool kRemoteRelease = MODE == 2 || MODE == 4;
+  constexpr bool kRemoteRelease = MODE == 2 || MODE >= 4;
   const uint32_t rank = kCluster ? cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -96,7 +90,7 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], rx_bytes);
           tma_load_2d(&map_a, &full_bar[stage], sa, (kb % a_kblocks) * 64, row_a);
-          if (MODE == 0 || MODE == 4) {
+          if (MODE == 0 || MODE >= 4) {
             tma_load_2d(&map_b, &full_bar[stage], sb, kb * 64, 0);
           } else if (MODE == 1) {
             tma_load_2d(&map_bh, &full_bar[stage], sb, kb * 64, 0);
@@ -122,7 +116,12 @@ feed_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
         if (elect_one()) {
           mbar_arrive(&empty_bar[stage]);
-          if (kRemoteRelease) mbar_arrive_remote(&empty_bar[stage], rank ^ 1);
+          if (kRemoteRelease) {
+            if (MODE == 5)
+              mbar_arrive_remote_release_cluster(&empty_bar[stage], rank ^ 1);
+            else
+              mbar_arrive_cluster(map_to_cta(smem_u32(&empty_bar[stage]), rank ^ 1));
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -167,7 +166,7 @@ struct Variant {
 template <int MODE, int kStages>
 static void run(const Variant& v, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbh, int sms,
                 long long* d_cycles) {
-  const double rx_kb = MODE == 1 ? 32 : 48, l2_kb = (MODE == 0 || MODE == 4) ? 48 : 32;
+  const double rx_kb = MODE == 1 ? 32 : 48, l2_kb = (MODE == 0 || MODE >= 4) ? 48 : 32;
   const int reps = 10;
   const int smem = kStages * kStage + 1024;
   cudaFuncSetAttribute(feed_kernel<MODE, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -202,7 +201,8 @@ static void run(const Variant& v, const CUtensorMap& ma, const CUtensorMap& mb, 
   for (long long c : h) sum += double(c);
   const double blocks = double(reps) * kKBlocks;
   const double cyc = sum / sms / blocks;
-  static const char* mode_name[5] = {"unicast 48K", "unicast 32K", "multicast pair", "mcast, local rel", "ucast, remote rel"};
+  static const char* mode_name[6] = {"unicast 48K", "unicast 32K", "multicast pair", "mcast, local rel", "ucast, remote rel",
+                                     "ucast, rel.cluster"};
   printf("%-14s %d stages  %-44s hold %4d: %6.0f cyc/k-block  arrive %6.1f B/clk/SM  L2 %6.2f TB/s chip (%.3f ms)\n",
          mode_name[MODE], kStages, v.name, v.delay, cyc, rx_kb * 1024 / cyc,
          l2_kb * 1024 * blocks * sms / (ms * 1e-3) / 1e12, ms);
@@ -254,5 +254,6 @@ int main() {
   run<2, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
   run<3, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
   run<4, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
+  run<5, 4>(own_l2, ma, mb, mbh, sms, d_cycles);
   return 0;
 }
