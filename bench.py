@@ -242,7 +242,7 @@ def ncu_traffic(precision):
     if not d:
         return None, None
     tot = sum(v["dram_bytes"] for k, v in d.items()
-              if (k.startswith("conv_gemm_kernel") and k.endswith(", 0>")) or k.startswith("conv_halo_kernel"))
+              if (k.startswith("conv_gemm_kernel") and (k.endswith(", 0>") or k.endswith(", 0, 1>"))) or k.startswith("conv_halo_kernel"))
     return tot, "profiles/r01_step_kernels_final.json"
 
 
