@@ -13,7 +13,7 @@ BF16, F32, BF16X2 = 0, 1, 2
 EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32, EPI_COLSUM = 1, 2, 4, 8, 16, 64, 128
 
 EXPORTS = [
-    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_debug_buffer", "fcn8_preprocess_im2col",
+    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_debug_buffer", "fcn8_crc32c", "fcn8_preprocess_im2col",
     "fcn8_conv_gemm_workspace_bytes", "fcn8_conv_gemm", "fcn8_wgrad_gemm_workspace_bytes", "fcn8_wgrad_gemm",
     "fcn8_pack_weights", "fcn8_split_tf32", "fcn8_maxpool_fwd", "fcn8_maxpool_bwd", "fcn8_bias_grad_workspace_bytes",
     "fcn8_bias_grad", "fcn8_score_head_fwd_workspace_bytes", "fcn8_score_head_fwd",
@@ -119,6 +119,8 @@ def load():
     lib.fcn8_launch_count.restype = C.c_uint64
     lib.fcn8_debug_set.argtypes = [C.c_int32, C.c_int32]
     lib.fcn8_debug_buffer.argtypes = [C.c_void_p, C.c_int32]
+    lib.fcn8_crc32c.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+    lib.fcn8_crc32c.restype = C.c_uint32
     lib.fcn8_set_sm_limit.argtypes = [C.c_int32]
     for kv in filter(None, os.environ.get("FCN8_DEBUG", "").split(",")):   # measurement switches, e.g. "3=1"
         k, v = kv.split("=")

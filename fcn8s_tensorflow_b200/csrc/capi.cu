@@ -429,6 +429,39 @@ int32_t fcn8_set_sm_limit(int32_t n) {
   g_sm_limit = n > 0 ? n : 0;
   return 0;
 }
+// CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), slicing-by-8, host code: the checksum TensorFlow's
+// tensor-bundle checkpoints carry per table block and per tensor (tf_bundle.py).  `crc` = running value (0 to start).
+uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc) {
+  static uint32_t table[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xffu];
+    ready = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7u)) {
+    c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
+    --n;
+  }
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;   // little-endian host (x86-64 / aarch64)
+    c = table[7][w & 0xff] ^ table[6][(w >> 8) & 0xff] ^ table[5][(w >> 16) & 0xff] ^ table[4][(w >> 24) & 0xff] ^
+        table[3][(w >> 32) & 0xff] ^ table[2][(w >> 40) & 0xff] ^ table[1][(w >> 48) & 0xff] ^ table[0][w >> 56];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
+  return ~c;
+}
 int32_t fcn8_debug_buffer(void* buf, int32_t slots) {
   g_dbg_buf = static_cast<long long*>(buf);
   g_dbg_slots = buf ? slots : 0;

@@ -7,9 +7,13 @@ and the same generator protocol (`next(gen)` -> uint8 images [n,H,W,3], bool one
 data_generator/batch_generator.py:414-415).  What replaces `tf.Session.run` is `engine.Engine`.
 
 Differences that are inherent to leaving TensorFlow (documented in INTEGRATION.md):
-  * `vgg16_dir` / `model_load_dir` / `variables_load_dir` point at `.npz` weight files (TF variable names as keys,
-    TF layouts) or use the `synthetic[:seed]` scheme; reading TF SavedModel / tensor-bundle files is not implemented.
-  * `save()` writes `<dir>/<reference-style name>/variables.npz` for both savers.
+  * `vgg16_dir` / `model_load_dir` / `variables_load_dir` are read as TensorFlow tensor bundles (a SavedModel's
+    `variables/variables.index` + `.data-00000-of-00001`, or a `train_saver` prefix) by `tf_bundle.py`, without
+    TensorFlow and by TF variable name; `.npz` files keyed the same way and the `synthetic[:seed]` scheme also work.
+    The TF1 graph in `saved_model.pb` is never read: the graph is the engine.
+  * `save()` writes the same variable files under the reference's directory names (`variables/variables.*` for
+    `saver='saved_model'`, `variables.*` + `checkpoint` for `'train_saver'`), including the Adam slots and
+    `optimizer/global_step`; it does not write a `saved_model.pb`.
   * extra keyword-only constructor arguments select the precision mode and the device.
 """
 import os
@@ -74,16 +78,21 @@ def check_labels(labels, num_classes):
     return a
 
 
-def _load_npz_weights(path, num_classes):
+def _load_npz_weights(path, num_classes=None):
+    """Variables by TF name from `path`: a TensorFlow tensor bundle -- a SavedModel directory
+    (`variables/variables.index` + `.data-00000-of-00001`, what fcn8s_tensorflow.py:74,134 load and :922-925 writes), a
+    `train_saver` directory or prefix (:926-944) -- read without TensorFlow by tf_bundle.py; or an .npz keyed the same
+    way.  The TF1 graph in `saved_model.pb` is not needed: the graph is this engine."""
+    from . import tf_bundle
+    prefix = tf_bundle.find_bundle(path)
+    if prefix is not None:
+        return dict(tf_bundle.read_bundle(prefix))
     if os.path.isdir(path):
         cands = [os.path.join(path, f) for f in ("variables.npz", "vgg16_weights.npz", "weights.npz")]
         found = [c for c in cands if os.path.exists(c)]
         if not found:
-            if os.path.exists(os.path.join(path, "saved_model.pb")):
-                raise NotImplementedError(
-                    "%s is a TensorFlow SavedModel; reading TF SavedModel / tensor-bundle files is not implemented "
-                    "(convert the variables to an .npz keyed by TF variable names, see INTEGRATION.md)" % path)
-            raise FileNotFoundError("no variables.npz / vgg16_weights.npz under %s" % path)
+            raise FileNotFoundError("no TensorFlow variables (variables/variables.index) and no variables.npz / "
+                                    "vgg16_weights.npz under %s" % path)
         path = found[0]
     data = np.load(path)
     return {k: data[k] for k in data.files}
@@ -471,15 +480,28 @@ class FCN8s:
         for n in e.layout:   # Adam slots are global variables in the reference and are saved with the model
             arrays[n + "/Adam"] = e.view(n, e.adam_m).cpu().numpy()
             arrays[n + "/Adam_1"] = e.view(n, e.adam_v).cpu().numpy()
-        arrays["optimizer/global_step"] = np.asarray(e.global_step, np.int64)
-        np.savez(os.path.join(out_dir, 'variables.npz'), **arrays)
+        arrays["optimizer/global_step"] = np.asarray(e.global_step, np.int32)       # tf.Variable(0) at :246
+        arrays["optimizer/beta1_power"] = np.asarray(0.9 ** e.global_step, np.float32)
+        arrays["optimizer/beta2_power"] = np.asarray(0.999 ** e.global_step, np.float32)
+        # The reference writes TensorFlow files: SavedModelBuilder puts the variables under variables/variables.*
+        # (:922-925), tf.train.Saver under the prefix <dir>/variables plus a `checkpoint` state file (:926-934).  Both
+        # are tensor bundles; tf_bundle.py writes them without TensorFlow (tf.train.load_checkpoint reads them).
+        from . import tf_bundle
+        if saver == 'saved_model':
+            tf_bundle.write_bundle(os.path.join(out_dir, 'variables', 'variables'), arrays)
+        else:
+            tf_bundle.write_bundle(os.path.join(out_dir, 'variables'), arrays)
+            with open(os.path.join(out_dir, 'checkpoint'), 'w') as f:
+                f.write('model_checkpoint_path: "variables"\nall_model_checkpoint_paths: "variables"\n')
         self.variables_updated = False
         return out_dir
 
     def _restore_optimizer(self, data):
         e = self.engine
-        if "optimizer/global_step" in data:
-            e.global_step = int(data["optimizer/global_step"])
+        for key in ("optimizer/global_step", "global_step"):
+            if key in data:
+                e.global_step = int(data[key])
+                break
         for n in e.layout:
             if n + "/Adam" in data:
                 e.view(n, e.adam_m).copy_(torch.from_numpy(np.asarray(data[n + "/Adam"])).to(e.device))

@@ -68,6 +68,10 @@ int32_t fcn8_set_sm_limit(int32_t n);
 /* bring-up knobs -- tests only.  key 0, value 1: disable the round-toward-zero compensation of the GEMM accumulators
  * (the library multiplies every tcgen05 accumulator by 1 + n_mma * 2.1e-8, the expected relative loss of TMEM's
  * truncating accumulation over n_mma instructions; scripts/bringup.py::rz_accumulation_probe measures the constant). */
+/* Host-side CRC-32C (Castagnoli) of `n` bytes, continuing from `crc` (0 to start): the checksum of TensorFlow's
+ * tensor-bundle checkpoint files (fcn8s_tensorflow.py:74,134,922-934 read / write them through tf.saved_model and
+ * tf.train.Saver); used by fcn8s_tensorflow_b200/tf_bundle.py.  No device work. */
+uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc);
 int32_t fcn8_debug_set(int32_t key, int32_t value);
 /* Measurement only: `buf` = device buffer of slots*148*8 int64; every following fcn8_conv_gemm / fcn8_wgrad_gemm launch
  * takes the next slot and its CTAs write their MMA-warp wait-cycle counters there (csrc/conv_gemm.cuh,
