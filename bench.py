@@ -10,6 +10,7 @@ Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of 
 host cores instead (TensorFlow 1.x cannot run here).
 """
 import argparse
+import re
 import json
 import os
 import subprocess
@@ -241,8 +242,9 @@ def ncu_traffic(precision):
     d = json.load(open(path)).get(precision)
     if not d:
         return None, None
+    # conv_gemm_kernel<BN, TF32 = 0, PAIR> are the bf16-operand instantiations (the tf32 ones serve the decoder)
     tot = sum(v["dram_bytes"] for k, v in d.items()
-              if (k.startswith("conv_gemm_kernel") and (k.endswith(", 0>") or k.endswith(", 0, 1>"))) or k.startswith("conv_halo_kernel"))
+              if re.match(r"conv_gemm_kernel<\d+, 0, [01]>", k) or k.startswith("conv_halo_kernel"))
     return tot, "profiles/r01_step_kernels_final.json"
 
 
