@@ -12,6 +12,11 @@
 //   wgrad_gemm_kernel : D[(tap, ci), co] = sum_{pixels} X[pixel + tap, ci] * dY[pixel, co]
 //     (TF's Conv2DBackpropFilter, implied by fcn8s_tensorflow.py:257), both operands MN-major.
 //
+//   PAIR variants of conv_gemm_kernel and wgrad_gemm_kernel (bf16 operands, 256-column tiles): clusters of two CTAs on
+//     one SM pair, tcgen05 cta_group::2 -- each CTA owns a 128-row M tile and loads its own A tile plus HALF of the B
+//     tile, the leader CTA issues M = 256 MMAs over both CTAs' shared memory (protocol: ptx.cuh, "CTA pairs";
+//     measurements that led there: profiles/r01_probes.md).
+//
 // Shared design: one CTA = 10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both loops run by
 // the whole warp, one elected lane issues), warps 2..9 = epilogue (TMEM -> registers -> global; two warps per TMEM
 // lane quarter).  Persistent over tiles, smem ring of kStages operand stages, 2 accumulator stages in TMEM so the

@@ -65,13 +65,18 @@ uint64_t fcn8_launch_count(void);
  * (the overlapped gradient all-reduce) occupies some SMs, n > 0 caps the grids at n CTAs so that no CTA has to wait for
  * an SM and run a whole second wave.  n = 0 restores the device's SM count.  Affects launches issued afterwards. */
 int32_t fcn8_set_sm_limit(int32_t n);
-/* bring-up knobs -- tests only.  key 0, value 1: disable the round-toward-zero compensation of the GEMM accumulators
- * (the library multiplies every tcgen05 accumulator by 1 + n_mma * 2.1e-8, the expected relative loss of TMEM's
- * truncating accumulation over n_mma instructions; scripts/bringup.py::rz_accumulation_probe measures the constant). */
 /* Host-side CRC-32C (Castagnoli) of `n` bytes, continuing from `crc` (0 to start): the checksum of TensorFlow's
  * tensor-bundle checkpoint files (fcn8s_tensorflow.py:74,134,922-934 read / write them through tf.saved_model and
  * tf.train.Saver); used by fcn8s_tensorflow_b200/tf_bundle.py.  No device work. */
 uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc);
+/* Bring-up / measurement knobs -- tests and profiling only (also settable as FCN8_DEBUG="key=value,..." at load time):
+ *   0 = 1: no round-toward-zero compensation of the GEMM accumulators (the library multiplies every tcgen05
+ *          accumulator by 1 + n_mma * 2.1e-8, the expected relative loss of TMEM's truncating accumulation over n_mma
+ *          instructions; scripts/bringup.py::rz_accumulation_probe measures the constant)
+ *   1 = 1: no wgrad_halo_kernel          2 = 1: no resident-weights variant of conv_halo_kernel<64>
+ *   3    : bit 0: conv epilogues skip their output stores, bit 1: ... and their mask / residual loads (timing only)
+ *   5 = 1: single-CTA kernels instead of the CTA-pair (cta_group::2) variants of conv_gemm / wgrad_gemm
+ *   6 = 1: launch every kernel with the programmatic-dependent-launch attribute (kernels.h) */
 int32_t fcn8_debug_set(int32_t key, int32_t value);
 /* Measurement only: `buf` = device buffer of slots*148*8 int64; every following fcn8_conv_gemm / fcn8_wgrad_gemm launch
  * takes the next slot and its CTAs write their MMA-warp wait-cycle counters there (csrc/conv_gemm.cuh,
