@@ -552,6 +552,38 @@ def hwio_pair():
 
 
 @case
+def cta_pair_kernels():
+    """CTA-pair (cta_group::2) variants of the per-tap conv kernel and of the filter-gradient kernel: odd numbers of M
+    tiles (the last pair has a partner that computes on zero-filled rows), ragged tiles, split-K, bf16 and hi/lo pair
+    operands -- against the fp64 references, and bit-for-bit against the single-CTA kernels (same accumulation order)."""
+    from fcn8s_tensorflow_b200 import _capi, ops
+    lib = _capi.load()
+    ok = hwio_conv_case(3, 20, 36, 256, 256, 3, False, 1e-2, algo=1)      # 17 M tiles, ragged, Cin = Cout = 256
+    ok &= hwio_conv_case(1, 8, 16, 256, 512, 3, False, 1e-2, algo=1)      # a single M tile, two N tiles
+    ok &= hwio_conv_case(3, 20, 36, 128, 256, 3, True, 2e-5, algo=1)      # hi/lo pair operands (3 segments)
+    ok &= hwio_conv_case(1, 4, 8, 512, 256, 7, False, 1e-2)               # split-K partials
+    ok &= wgrad_case(3, 20, 36, 128, 256, 3, 0, 1e-2)                     # 9 M tiles (odd), 256 columns
+    ok &= wgrad_case(2, 16, 32, 256, 512, 3, 0, 1e-2)                     # 18 M tiles, two N tiles
+    ok &= wgrad_case(1, 8, 16, 64, 256, 1, 0, 1e-2)                       # half an M tile
+    # pair vs single-CTA kernel on the same inputs
+    torch.manual_seed(33)
+    dev = torch.device("cuda")
+    w = torch.randn(3, 3, 256, 256, device=dev) / 48.0
+    wh, _ = _shadow(w, False)
+    x = torch.randn(3, 20, 36, 256, device=dev).to(torch.bfloat16)
+    y_pair = ops.conv_gemm(x, wh, 256, 3, w_mode=1, algo=1)
+    lib.fcn8_debug_set(5, 1)
+    try:
+        y_single = ops.conv_gemm(x, wh, 256, 3, w_mode=1, algo=1)
+    finally:
+        lib.fcn8_debug_set(5, 0)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(y_pair, y_single))
+    print("  %-58s %s" % ("pair kernel == single-CTA kernel, bit for bit", "OK" if same else "FAIL"))
+    return ok and same
+
+
+@case
 def halo_conv():
     """Halo-tile kernel (algo 2): shifted UMMA descriptors into one activation patch, against the same references."""
     ok = True
