@@ -29,6 +29,7 @@ import torch
 
 from . import _capi as capi
 from .engine import Engine, variable_shapes
+from .summaries import SUMMARY_VARIABLES, write_variable_summaries
 
 
 def synthetic_weights(num_classes, seed=2, decoder_std_scale=1.0):
@@ -307,6 +308,11 @@ class FCN8s:
                 token = self._loss_read_begin(x.shape)
                 self.g_step = self.engine.global_step
                 self.variables_updated = True
+                if training_writer is not None and (self.g_step - 1) % summaries_frequency == 0:
+                    # variable summaries of _build_summary_ops (:331-350), reduced on the device (summaries.py)
+                    e = self.engine
+                    write_variable_summaries(training_writer, {n: e.view(n, e.params) for n, _ in SUMMARY_VARIABLES},
+                                             self.g_step)
                 if pending is not None:
                     account(pending)
                 pending = (token, self.g_step, learning_rate)

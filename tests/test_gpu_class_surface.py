@@ -155,3 +155,30 @@ def test_generator_is_consumed_exactly_like_the_reference(cuda_device, weights):
           eval_dataset='train', eval_frequency=1, metrics={'loss'}, record_summaries=False)
     assert pulled == list(range(8))     # 2 epochs x (2 train + 2 eval) batches, nothing prefetched beyond that
     quiet(m.close)
+
+
+def test_training_and_evaluation_summaries_are_the_references(cuda_device, weights, tmp_path):
+    """`record_summaries=True` (fcn8s_tensorflow.py:531-563, 606-608): `total_loss`, `learning_rate` and the variable
+    summaries of `_build_summary_ops` (:331-350) every `summaries_frequency` steps; `mean_loss` / `mean_iou` /
+    `accuracy` after each evaluation."""
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from fcn8s_tensorflow_b200.summaries import SUMMARY_VARIABLES
+    m = make_model(cuda_device, weights, precision="bf16")
+    quiet(m.train, batches([2], 7), epochs=1, steps_per_epoch=3, learning_rate_schedule=lambda s: 1e-4, keep_prob=1.0,
+          eval_dataset='train', eval_frequency=1, metrics={'loss', 'mean_iou', 'accuracy'}, record_summaries=True,
+          summaries_frequency=2, summaries_dir=str(tmp_path), summaries_name='run')
+    tr = EventAccumulator(os.path.join(str(tmp_path), 'run'), size_guidance={"histograms": 0, "scalars": 0})
+    tr.Reload()
+    tags = tr.Tags()
+    assert [e.step for e in tr.Scalars('total_loss')] == [1, 3] and len(tr.Scalars('learning_rate')) == 2
+    for _, scope in SUMMARY_VARIABLES:
+        assert scope + '/mean' in tags['scalars'] and scope + '/histogram' in tags['histograms']
+    w = m.engine.state_dict()['fc6/weights'].double()
+    ev = tr.Scalars('fc6/kernel/stddev')[-1]
+    assert ev.step == 3 and abs(ev.value - float((w - w.mean()).square().mean().sqrt())) <= 1e-4 * abs(ev.value)
+    hv = tr.Histograms('fc6/kernel/histogram')[-1].histogram_value
+    assert hv.num == w.numel() and abs(hv.min - float(w.min())) <= 1e-6
+    ev_ = EventAccumulator(os.path.join(str(tmp_path), 'run_eval'))
+    ev_.Reload()
+    assert set(ev_.Tags()['scalars']) == {'mean_loss', 'mean_iou', 'accuracy'}
+    quiet(m.close)

@@ -246,3 +246,48 @@ def test_reference_batch_generators_feed_the_class_surface(tmp_path):
     assert images.dtype == np.uint8 and images.shape == (2, 64, 96, 3)
     assert labels.dtype == np.bool_ and labels.shape == (2, 64, 96, 2) and (labels.sum(-1) == 1).all()
     assert check_labels(labels, 2) is labels
+
+
+def test_variable_summaries_match_tensorflow_buckets_and_reference_tags(tmp_path):
+    """helpers/tf_variable_summaries.py:3-20 + fcn8s_tensorflow.py:331-350: mean / population stddev / max / min and a
+    histogram over TensorFlow's default buckets, one set per variable under the reference's scopes."""
+    import torch
+    from fcn8s_tensorflow_b200 import summaries as S
+    limits = S.tf_bucket_limits()
+    assert len(limits) == 1550 and limits[774] == 0.0 and limits[775] == 1e-12 and limits[773] == -1e-12
+    assert np.all(np.diff(limits) > 0) and abs(limits[776] / limits[775] - 1.1) < 1e-12
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(7, 5, 300, generator=g) * 0.01
+    x[0, 0, 0] = 0.0
+    x[0, 0, 1] = 1e-12                      # exactly on a bucket limit: belongs to the bucket that STARTS there
+    st = S.variable_stats(x).numpy()
+    xn = x.numpy().astype(np.float64)
+    assert np.allclose(st, [xn.mean(), np.sqrt(np.mean((xn - xn.mean()) ** 2)), xn.max(), xn.min()], rtol=1e-6)
+    h = S.variable_histogram(x)
+    counts, _ = np.histogram(xn.reshape(-1), bins=limits)       # [edge_j, edge_j+1): bucket j+1 of the TF scheme
+    full = np.concatenate([[0], counts])
+    nz = np.nonzero(full)[0]
+    assert h["bucket_limits"] == limits[nz[0]:nz[-1] + 1].tolist()
+    assert h["bucket_counts"] == full[nz[0]:nz[-1] + 1].astype(float).tolist()
+    assert h["num"] == xn.size and abs(h["sum"] - xn.sum()) < 1e-9 and abs(h["sum_squares"] - (xn ** 2).sum()) < 1e-9
+    assert h["min"] == xn.min() and h["max"] == xn.max()
+
+    from torch.utils.tensorboard import SummaryWriter
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    names = [n for n, _ in S.SUMMARY_VARIABLES]
+    assert len(names) == 20 and names[12:16] == ["fc7/weights", "fc7/biases", "fc6/weights", "fc6/biases"]
+    tensors = {n: torch.randn(4, 3, generator=g) for n in names}
+    w = SummaryWriter(str(tmp_path))
+    S.write_variable_summaries(w, tensors, 11)
+    w.close()
+    acc = EventAccumulator(str(tmp_path), size_guidance={"histograms": 0, "scalars": 0})
+    acc.Reload()
+    tags = acc.Tags()
+    for _, scope in S.SUMMARY_VARIABLES:
+        for t in ("mean", "stddev", "max", "min"):
+            assert "%s/%s" % (scope, t) in tags["scalars"]
+        assert "%s/histogram" % scope in tags["histograms"]
+    ev = acc.Scalars("fc6/kernel/max")[0]
+    assert ev.step == 11 and abs(ev.value - float(tensors["fc6/weights"].max())) < 1e-6
+    hv = acc.Histograms("conv3_3/bias/histogram")[0].histogram_value
+    assert hv.num == 12 and abs(hv.sum - float(tensors["conv3_3/biases"].double().sum())) < 1e-6
