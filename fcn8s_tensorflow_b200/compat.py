@@ -1,7 +1,8 @@
 """Compatibility shim that lets the reference's data generators run unmodified on current SciPy.
 
 `data_generator/batch_generator.py:247,254,399,406` and `data_generator/batch_generator_KITTI.py:71,78` call
-`scipy.misc.imread / imresize / imsave`, which SciPy removed in 1.2/1.3.  `install_scipy_misc_shim()` adds PIL-backed
+`scipy.misc.imread / imresize / imsave`, and `helpers/visualization_utils.py:45-47` `scipy.misc.toimage`, which SciPy
+removed in 1.2/1.3.  `install_scipy_misc_shim()` adds PIL-backed
 stand-ins with the same call signatures to the `scipy.misc` module (only the names that are missing), so a user keeps
 feeding `FCN8s.train / evaluate` from `BatchGenerator(...).generate(...)` / `batch_generator(...)` as before.
 """
@@ -49,11 +50,23 @@ def _imsave(path, arr, format=None):
     Image.fromarray(a if a.dtype == np.uint8 else _bytescale(a)).save(path, format=format)
 
 
+def _toimage(arr, high=255, low=0, cmin=None, cmax=None, pal=None, mode=None, channel_axis=None):
+    """scipy.misc.toimage for the cases the reference uses: uint8 [H,W], [H,W,3] or [H,W,4] arrays become PIL images
+    unchanged (SciPy's byte-scaling is the identity on uint8 data); other dtypes are byte-scaled first."""
+    from PIL import Image
+    a = np.asarray(arr)
+    if a.dtype != np.uint8:
+        a = _bytescale(a)
+    if mode is None:
+        mode = {2: 'L', 3: {3: 'RGB', 4: 'RGBA'}.get(a.shape[-1])}.get(a.ndim)
+    return Image.fromarray(a, mode=mode)
+
+
 def install_scipy_misc_shim():
-    """Add imread / imresize / imsave to scipy.misc when they are missing. Returns the names that were added."""
+    """Add imread / imresize / imsave / toimage to scipy.misc when they are missing. Returns the names added."""
     import scipy.misc as misc
     added = []
-    for name, fn in (("imread", _imread), ("imresize", _imresize), ("imsave", _imsave)):
+    for name, fn in (("imread", _imread), ("imresize", _imresize), ("imsave", _imsave), ("toimage", _toimage)):
         if not hasattr(misc, name):
             setattr(misc, name, fn)
             added.append(name)

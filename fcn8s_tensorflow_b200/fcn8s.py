@@ -79,6 +79,27 @@ def check_labels(labels, num_classes):
     return a
 
 
+def print_segmentation_onto_image(image, segmentation, color_map):
+    """The overlay of helpers/visualization_utils.py:7-52 on a class-id map: an RGBA layer holding `color_map[class]`
+    at every pixel of that class is pasted over the RGB image with itself as the mask (PIL `Image.paste`, the operation
+    and therefore the rounding the reference uses).  `segmentation`: int [H, W] (the reference takes one-hot / softmax
+    [1, H, W, C] and arg-maxes it first).  Returns uint8 [H, W, 3]."""
+    from PIL import Image
+    image = np.asarray(image, dtype=np.uint8)
+    segmentation = np.asarray(segmentation)
+    if image.shape[:2] != segmentation.shape[-2:]:
+        raise ValueError("'image' and 'prediction' must have the same height and width, but image has spatial "
+                         "dimensions ({}, {}) and prediction has spatial dimensions ({}, {}).".format(
+                             image.shape[0], image.shape[1], segmentation.shape[-2], segmentation.shape[-1]))
+    layer = np.zeros((image.shape[0], image.shape[1], 4), dtype=np.uint8)
+    for segmentation_class, color_value in color_map.items():
+        layer[segmentation == segmentation_class] = color_value
+    layer = Image.fromarray(layer, mode="RGBA")
+    out = Image.fromarray(image)
+    out.paste(layer, box=None, mask=layer)
+    return np.asarray(out, dtype=np.uint8)
+
+
 def _load_npz_weights(path, num_classes=None):
     """Variables by TF name from `path`: a TensorFlow tensor bundle -- a SavedModel directory
     (`variables/variables.index` + `.data-00000-of-00001`, what fcn8s_tensorflow.py:74,134 load and :922-925 writes), a
@@ -441,12 +462,7 @@ class FCN8s:
             image = np.asarray(img, dtype=np.uint8)
             h, w, _ = image.shape
             seg = self.predict([image], argmax=True)[0]
-            # helpers/visualization_utils.py:7-52: paste an RGBA colour layer per class over the image
-            overlay = np.zeros((h, w, 4), np.uint8)
-            for cls, rgba in color_map.items():
-                overlay[seg == cls] = np.asarray(rgba, np.uint8)
-            base = Image.fromarray(image).convert('RGBA')
-            processed = np.asarray(Image.alpha_composite(base, Image.fromarray(overlay, 'RGBA')).convert('RGB'))
+            processed = print_segmentation_onto_image(image, seg, color_map)
             if include_unprocessed_image:
                 axis = 0 if arrangement == 'vertical' else 1
                 processed = np.concatenate([processed, image], axis=axis)

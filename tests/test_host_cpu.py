@@ -1,6 +1,8 @@
 """CPU tier for the host side: C-ABI library loads and exports every declared symbol (no compute calls), flat-buffer
 layout, dropout RNG replica, loud failure without a GPU, data-parallel host logic over gloo (world size 2)."""
+import contextlib
 import ctypes
+import io
 import os
 import sys
 import re
@@ -291,3 +293,61 @@ def test_variable_summaries_match_tensorflow_buckets_and_reference_tags(tmp_path
     assert ev.step == 11 and abs(ev.value - float(tensors["fc6/weights"].max())) < 1e-6
     hv = acc.Histograms("conv3_3/bias/histogram")[0].histogram_value
     assert hv.num == 12 and abs(hv.sum - float(tensors["conv3_3/biases"].double().sum())) < 1e-6
+
+
+def test_overlay_matches_the_references_helper_bit_for_bit():
+    """`print_segmentation_onto_image` (helpers/visualization_utils.py:7-52) through the fixture generated by importing
+    the reference's own function (tests/golden/make_golden.py::reference_overlay)."""
+    from fcn8s_tensorflow_b200.fcn8s import print_segmentation_onto_image
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_overlay.npz"))
+    color_map = {int(k): tuple(int(x) for x in v) for k, v in zip(g["classes"], g["colors"])}
+    out = print_segmentation_onto_image(g["image"], g["segmentation"], color_map)
+    assert out.dtype == np.uint8 and np.array_equal(out, g["overlay"])
+    untouched = g["segmentation"] == 0                     # class 0 is not in the colour map
+    assert np.array_equal(out[untouched], g["image"][untouched])
+    with pytest.raises(ValueError, match="must have the same height and width"):
+        print_segmentation_onto_image(g["image"], g["segmentation"][:-1], color_map)
+
+
+def test_predict_and_save_file_handling_without_a_device(tmp_path):
+    """fcn8s_tensorflow.py:772-855 with `predict` stubbed: every `*.png` of images_dir is read, optionally resized,
+    overlaid, optionally stacked with the unprocessed image (vertical / horizontal) and written under the same name;
+    an existing results directory is replaced."""
+    from PIL import Image
+    from fcn8s_tensorflow_b200.fcn8s import FCN8s, print_segmentation_onto_image
+    rng = np.random.default_rng(3)
+    src = tmp_path / "images"
+    src.mkdir()
+    imgs = {}
+    for name, (h, w) in {"a.png": (32, 64), "b.png": (48, 32)}.items():
+        imgs[name] = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        Image.fromarray(imgs[name]).save(str(src / name))
+    (src / "ignored.jpg").write_bytes(b"not an image")
+    color_map = {1: (0, 255, 0, 127), 2: (255, 0, 0, 200)}
+
+    def fake_predict(images, argmax=True):
+        assert argmax is True and len(images) == 1
+        return np.stack([(im[..., 0] // 86).astype(np.int64) for im in images])      # classes 0..2 from the red channel
+
+    m = object.__new__(FCN8s)          # no engine, no device: only the file handling is under test
+    m.predict = fake_predict
+    out = tmp_path / "results"
+    out.mkdir()
+    (out / "stale.txt").write_text("x")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.predict_and_save(str(out), str(src), color_map)
+    assert sorted(os.listdir(out)) == ["a.png", "b.png"]
+    for name, im in imgs.items():
+        got = np.asarray(Image.open(str(out / name)).convert("RGB"))
+        assert np.array_equal(got, print_segmentation_onto_image(im, fake_predict([im])[0], color_map))
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.predict_and_save(str(out), str(src), color_map, include_unprocessed_image=True, arrangement='vertical')
+    got = np.asarray(Image.open(str(out / "a.png")).convert("RGB"))
+    assert got.shape == (64, 64, 3) and np.array_equal(got[32:], imgs["a.png"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.predict_and_save(str(out), str(src), color_map, resize=(32, 32), include_unprocessed_image=True,
+                           arrangement='horizontal')
+    got = np.asarray(Image.open(str(out / "b.png")).convert("RGB"))
+    resized = np.asarray(Image.open(str(src / "b.png")).convert("RGB").resize((32, 32), Image.BILINEAR))
+    assert got.shape == (32, 64, 3) and np.array_equal(got[:, 32:], resized)
+    assert np.array_equal(got[:, :32], print_segmentation_onto_image(resized, fake_predict([resized])[0], color_map))
