@@ -52,7 +52,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 // pair == false: one CTA per SM, cta_group::1, M = 128.
 // pair == true : clusters of two CTAs (one SM pair), cta_group::2, M = 256 = 128 rows of A per CTA, each CTA holds
 //                half of B (N/2 rows); the leader CTA issues, both tensor cores run, D = 128 lanes x N columns per CTA.
-template <bool A_TMEM, bool PAIR>
+template <bool A_TMEM, bool PAIR, bool TF32 = false>
 __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs g, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(ProbeArgs g, long long* c
             } else if (A_TMEM) {
               umma_f16_ts(tmem_base, tmem_base + 256 + (i & 15) * 8, bd[i], g.idesc, acc);
             } else {
-              umma_f16(tmem_base, ad[i], bd[i], g.idesc, acc);
+              if (TF32)
+                umma_tf32(tmem_base, ad[i], bd[i], g.idesc, acc);
+              else
+                umma_f16(tmem_base, ad[i], bd[i], g.idesc, acc);
             }
           }
           if (g.commit_every_blk) {
@@ -170,6 +173,7 @@ struct Config {
   int a_mn, b_mn, N, a_tmem, commit;
   int M = 128;
   int pair = 0;
+  int tf32 = 0;   // kind::tf32 (fp32-stored operands, K = 8 per MMA: the same 32 bytes per row)
 };
 
 typedef void (*KernelFn)(ProbeArgs, long long*);
@@ -205,6 +209,8 @@ int main() {
   cudaMemset(d_cycles, 0, sizeof(long long) * sms);
   const int kSmem = 200 * 1024;
   KernelFn k_ss = probe_kernel<false, false>, k_ts = probe_kernel<true, false>, k_pair = probe_kernel<false, true>;
+  KernelFn k_tf32 = probe_kernel<false, false, true>;
+  cudaFuncSetAttribute(k_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   cudaFuncSetAttribute(k_ss, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   cudaFuncSetAttribute(k_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   cudaFuncSetAttribute(k_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
@@ -231,6 +237,12 @@ int main() {
       {"PAIR M=256  A MN-major  B MN-major  N=256                   ", 1, 1, 256, 0, 1, 256, 1},
       {"PAIR M=256  A K-major   B K-major   N=128                   ", 0, 0, 128, 0, 1, 256, 1},
       {"PAIR M=256  A K-major   B K-major   N=64                    ", 0, 0, 64, 0, 1, 256, 1},
+      {"PAIR M=256  A MN-major  B MN-major  N=128                   ", 1, 1, 128, 0, 1, 256, 1},
+      {"M=128  A K-major   B K-major   N=32                         ", 0, 0, 32, 0, 1},
+      {"M=128  A in TMEM   B K-major   N=32                         ", 0, 0, 32, 1, 1},
+      {"TF32  M=128  A K-major  B K-major  N=256 (K=8 per MMA)      ", 0, 0, 256, 0, 1, 128, 0, 1},
+      {"TF32  M=128  A K-major  B K-major  N=128                    ", 0, 0, 128, 0, 1, 128, 0, 1},
+      {"TF32  M=128  A K-major  B K-major  N=64 (decoder dgrad)     ", 0, 0, 64, 0, 1, 128, 0, 1},
   };
   printf("device %s, %d SMs, nominal SM clock %d MHz; bf16 x bf16 -> fp32, K=16 per MMA, 64-deep blocks, every SM busy\n",
          prop.name, sms, clock_khz / 1000);
@@ -245,7 +257,7 @@ int main() {
     const int rows_a = c.pair ? 128 : c.M;
     const int rows_b = c.pair ? c.N / 2 : c.N;
     ProbeArgs g{};
-    g.idesc = make_idesc(1u, c.a_mn, c.b_mn, c.M, c.N);
+    g.idesc = make_idesc(c.tf32 ? 2u : 1u, c.a_mn, c.b_mn, c.M, c.N);
     g.adesc0 = c.a_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
     g.bdesc0 = c.b_mn ? make_smem_desc_sw128(0, 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
     g.a_adv = c.a_mn ? 2048 : 32;
@@ -257,7 +269,7 @@ int main() {
     g.a_bytes = g.blks * g.a_blk;
     g.a_tmem = c.a_tmem;
     g.commit_every_blk = c.commit;
-    KernelFn fn = c.pair ? k_pair : (c.a_tmem ? k_ts : k_ss);
+    KernelFn fn = c.tf32 ? k_tf32 : (c.pair ? k_pair : (c.a_tmem ? k_ts : k_ss));
     const int grid = sms;
     launch(fn, grid, c.pair, kSmem, g, d_cycles);   // warm-up
     launch(fn, grid, c.pair, kSmem, g, d_cycles);
@@ -289,8 +301,8 @@ int main() {
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     const double issuers = c.pair ? grid / 2 : grid;
-    const double flops = 10.0 * issuers * n_mma * 2.0 * c.M * c.N * 16;
-    const double floor_cyc = (c.pair ? 128.0 : double(c.M < 128 ? 128 : c.M)) * c.N / 256.0;
+    const double flops = 10.0 * issuers * n_mma * 2.0 * c.M * c.N * (c.tf32 ? 8 : 16);
+    const double floor_cyc = (c.pair ? 128.0 : double(c.M < 128 ? 128 : c.M)) * c.N / 256.0;   // tf32: same cycles, half the K
     printf("%-60s %10.1f %10.1f %10.1f %12.1f\n", c.name, floor_cyc, mean, worst, flops / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
