@@ -149,9 +149,11 @@ def _encode_header():
     return _pb_varint_field(1, 1) + _pb_bytes_field(3, _pb_varint_field(1, 1))
 
 
-def _encode_entry(dtype_id, shape, offset, size, masked_crc):
+def _encode_entry(dtype_id, shape, offset, size, masked_crc, shard_id=0):
     dims = b"".join(_pb_bytes_field(2, _pb_varint_field(1, int(d))) for d in shape)   # TensorShapeProto.dim[].size
     out = _pb_varint_field(1, dtype_id) + _pb_bytes_field(2, dims)
+    if shard_id:
+        out += _pb_varint_field(3, shard_id)
     if offset:
         out += _pb_varint_field(4, offset)
     out += _pb_varint_field(5, size)

@@ -166,3 +166,22 @@ def test_weight_loader_finds_the_references_three_layouts(tmp_path):
     assert all(np.array_equal(got[k], w[k]) for k in w)
     with pytest.raises(FileNotFoundError):
         _load_npz_weights(str(tmp_path))
+
+
+def test_reader_handles_sharded_bundles(tmp_path):
+    """tf.train.Saver(sharded=True) / large SavedModels spread the tensors over data-0000i-of-0000n files; the index
+    names the shard of every tensor."""
+    prefix = str(tmp_path / "variables")
+    a = np.arange(6, dtype=np.float32).reshape(2, 3)
+    b = np.arange(5, dtype=np.int64)
+    open(tb.data_path(prefix, 0, 2), "wb").write(a.tobytes())
+    open(tb.data_path(prefix, 1, 2), "wb").write(b"\x00" * 16 + b.tobytes())      # b starts at offset 16 of shard 1
+    header = tb._pb_varint_field(1, 2) + tb._pb_bytes_field(3, tb._pb_varint_field(1, 1))    # num_shards = 2
+    items = [(b"", header),
+             (b"a", tb._encode_entry(1, a.shape, 0, a.nbytes, tb.mask_crc(tb.crc32c(a)))),
+             (b"b", tb._encode_entry(9, b.shape, 16, b.nbytes, tb.mask_crc(tb.crc32c(b)), shard_id=1))]
+    tb.write_table(prefix + ".index", items)
+    entries, shards = tb.list_bundle(prefix)
+    assert shards == 2 and entries["b"]["shard_id"] == 1 and entries["b"]["offset"] == 16
+    got = tb.read_bundle(prefix)
+    assert np.array_equal(got["a"], a) and np.array_equal(got["b"], b) and got["b"].dtype == np.int64
