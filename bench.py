@@ -1,18 +1,24 @@
 #!/usr/bin/env python
-"""FCN-8s training throughput on B200 -- BASELINE.json's metric: train images/sec @1024x512, 20 classes.
+"""FCN-8s throughput on B200 -- BASELINE.json's metric (train images/sec @1024x512, 20 classes) and its other configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16|tf32] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c3|c4|c5] [--precision fp32|bf16] [--impl reference]
 
-A step = one pass of the hot path over one synthetic Cityscapes-shaped batch: uint8 feed pre-processing, VGG-16
-encoder, decoder, softmax-CE loss, full backward, (N>1: one NCCL all-reduce of the flat gradient buffer) and the fused
-Adam update.  Workload = BASELINE configs[1]: 4 images of 512x1024x3 per GPU, 20 classes; weak scaling over N GPUs.
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference graph (oracle/) on the
-host cores instead (TensorFlow 1.x cannot run here).
+Workloads (BASELINE.json `configs`, SURVEY.md section 8 notation):
+  c2 (default)  configs[1]: train, 4 images of 512x1024x3 per GPU, 20 classes, fp32(-equivalent); bf16 under `alt`
+  c3            configs[2]: train, 2 images of 512x1024x3 per GPU (batch 16 on 8 GPUs), 20 classes, bf16
+  c4            configs[3]: inference, 1 image of 1024x2048x3, 20 classes, `predict` (argmax; softmax as a second number);
+                roofline = HBM bytes of the decoder's logits path
+  c5            configs[4]: train, 2 images of 384x1248x3 per GPU (batch 8 on 4 GPUs), 2 classes (KITTI road resized to
+                the x32 size the graph needs), e2e fed by the KITTI batch generator over a synthetic PNG tree
+A train step = uint8 feed pre-processing, VGG-16 encoder, decoder, softmax-CE loss, full backward, (N>1: one NCCL
+all-reduce of the flat gradient buffer) and the fused Adam update; weak scaling over N GPUs.  Prints ONE JSON line
+(rank 0).  `--impl reference` times the CPU restatement of the reference graph (oracle/) on the host cores on the same
+config, always at the config's full image size (TensorFlow 1.x cannot run here).
 """
 import argparse
-import re
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -21,10 +27,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, C, PER_GPU_BATCH = 512, 1024, 20, 4
-FWD_GFLOP_PER_IMAGE = 445.04
-TRAIN_GFLOP_PER_IMAGE = 1333.31
-METRIC = "FCN-8s train images/sec @1024x512 20-class"
+CONFIGS = {
+    "c2": dict(kind="train", H=512, W=1024, C=20, per_gpu=4, precision="fp32", alt="bf16", keep_prob=0.5,
+               fwd_gflop=445.04, train_gflop=1333.31,
+               metric="FCN-8s train images/sec @1024x512 20-class",
+               workload="BASELINE configs[1]: FCN-8s train step, 4 images of 512x1024x3 per GPU, 20 classes, keep_prob "
+                        "0.5, Adam lr 1e-4, synthetic uint8 images + bool one-hot labels, He-init encoder"),
+    "c3": dict(kind="train", H=512, W=1024, C=20, per_gpu=2, precision="bf16", alt=None, keep_prob=0.5,
+               fwd_gflop=445.04, train_gflop=1333.31,
+               metric="FCN-8s train images/sec @1024x512 20-class",
+               workload="BASELINE configs[2]: FCN-8s train step, 2 images of 512x1024x3 per GPU (batch 16 on 8 GPUs), "
+                        "20 classes, bf16, keep_prob 0.5, Adam lr 1e-4, data-parallel NCCL all-reduce"),
+    "c4": dict(kind="predict", H=1024, W=2048, C=20, per_gpu=1, precision="fp32", alt="bf16", keep_prob=1.0,
+               fwd_gflop=1780.16, train_gflop=None,
+               metric="FCN-8s inference images/sec @2048x1024 20-class",
+               workload="BASELINE configs[3]: FCN8s.predict (argmax) on 1 image of 1024x2048x3, 20 classes, batch 1"),
+    "c5": dict(kind="train", H=384, W=1248, C=2, per_gpu=2, precision="fp32", alt="bf16", keep_prob=0.5,
+               fwd_gflop=405.07, train_gflop=1213.57,
+               metric="FCN-8s train images/sec @1248x384 2-class (KITTI road)",
+               workload="BASELINE configs[4]: FCN-8s train step on KITTI road (375x1242 resized by the generator to the "
+                        "x32 size 384x1248), 2 classes, 2 images per GPU (batch 8 on 4 GPUs), keep_prob 0.5"),
+}
 
 
 def measured_peaks():
@@ -32,7 +55,7 @@ def measured_peaks():
     if os.path.exists(path):
         d = json.load(open(path))
         return dict(tflops=d["bf16_tflops_sustained"], tflops_burst=d["bf16_tflops"], hbm=d["hbm_gbs"],
-                    source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)")
+                    source="MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step; hbm_gbs)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
 
 
@@ -82,69 +105,138 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_feed(n, seed):
+def synthetic_feed(cfg, n, seed):
+    """uint8 images [n,H,W,3] + bool one-hot labels [n,H,W,C] in the generators' formats
+    (helpers/ground_truth_conversion_utils.py:84-88; KITTI: [background, ~background], batch_generator_KITTI.py:82-84)."""
     import numpy as np
     rng = np.random.default_rng(seed)
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
     images = rng.integers(0, 256, size=(n, H, W, 3), dtype=np.uint8)
-    ids = rng.integers(0, C, size=(n, H, W))
-    labels = np.eye(C, dtype=bool)[ids]          # what convert_IDs_to_one_hot yields (bool one-hot)
+    if C == 2:
+        bg = rng.random((n, H, W, 1)) < 0.7
+        labels = np.concatenate((bg, np.invert(bg)), axis=3)
+    else:
+        ids = rng.integers(0, C, size=(n, H, W))
+        labels = np.eye(C, dtype=bool)[ids]
     return images, labels
 
 
 # ---------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_step_fn(weights_np, sample):
-    """Returns (fn, images_per_step): fn() runs one train step of the CPU oracle on a bounded sample."""
+def cpu_reference_step_fn(cfg, weights_np):
+    """fn() runs one step of the CPU oracle on ONE full-size image of the config (train: forward + backward + TF-form
+    Adam with keep_prob as in the product arm; predict: forward + softmax + argmax).  Returns (fn, sample text)."""
+    import numpy as np
     import torch
     from oracle import fcn8s_oracle as oracle
     torch.set_num_threads(os.cpu_count() or 1)
-    w = {k: torch.from_numpy(v.copy()) for k, v in weights_np.items()}
+    w = {k: torch.from_numpy(np.array(v, copy=True)) for k, v in weights_np.items()}
+    images, labels = synthetic_feed(cfg, 1, 123)
+    H, W = cfg["H"], cfg["W"]
+    if cfg["kind"] == "predict":
+        def fn():
+            return oracle.predict(w, images, argmax=True, dtype=torch.float32)
+        return fn, ("FCN8s.predict (argmax) of 1 image of %dx%d per step, torch-CPU fp32 restatement of the reference "
+                    "graph (TF1 unavailable)" % (H, W))
     m = {k: torch.zeros_like(v) for k, v in w.items()}
     v_ = {k: torch.zeros_like(v) for k, v in w.items()}
-    h, wd = sample
-    images, labels = synthetic_feed(1, 123)
-    images, labels = images[:, :h, :wd], labels[:, :h, :wd]
     state = {"step": 0}
+    rng = np.random.default_rng(9)
+    kp = cfg["keep_prob"]
 
     def fn():
-        loss, state["step"] = oracle.train_step(w, m, v_, state["step"], images, labels, 1e-4, keep_prob=1.0,
-                                                dtype=torch.float32)
+        masks = None
+        if kp < 1.0:   # tf.nn.dropout's Bernoulli(keep_prob) masks on fc6 / fc7, drawn per step like the product arm
+            shape = (1, H // 32, W // 32, 4096)
+            masks = tuple(torch.from_numpy(rng.random(shape) < kp) for _ in range(2))
+        loss, state["step"] = oracle.train_step(w, m, v_, state["step"], images, labels, 1e-4, keep_prob=kp,
+                                                dropout_masks=masks, dtype=torch.float32)
         return loss
-    return fn, (h * wd) / float(H * W)
+    return fn, ("1 train step (forward, backward of all 42 variables, Adam; keep_prob %.1f) on 1 image of %dx%d, %d "
+                "classes, per step (batch 1), torch-CPU fp32 restatement of the reference graph (TF1 unavailable)"
+                % (kp, H, W, cfg["C"]))
 
 
-def run_reference(args):
+def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from fcn8s_tensorflow_b200.fcn8s import synthetic_weights
-    total = args.steps + args.warmup
-    # ~12 s per full 512x1024 image on 8 cores; keep the whole run within a few minutes
-    sample = (512, 1024) if total <= 12 else ((256, 512) if total <= 48 else (128, 256))
-    fn, img_per_step = cpu_reference_step_fn(synthetic_weights(C, 2), sample)
+    fn, desc = cpu_reference_step_fn(cfg, synthetic_weights(cfg["C"], 2))
     for _ in range(args.warmup):
         fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         fn()
     dt = time.perf_counter() - t0
-    value = img_per_step * args.steps / dt
-    desc = "1 image crop of %dx%d px per step (%.3f of a 512x1024 image), batch 1, torch-CPU fp32" % (
-        sample[0], sample[1], img_per_step)
+    value = args.steps / dt          # one full-size image per step
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "FCN-8s train step 512x1024x3, 20 classes (BASELINE configs[1]); CPU restatement of "
-                               "the reference TF1 graph (TensorFlow 1.x not installable here), bounded sample",
-                   "sample": desc},
+        "config": {"workload": cfg["workload"] + " -- CPU restatement of the reference TF1 graph on the host cores "
+                               "(TensorFlow 1.x not installable here), bounded sample: one full-size image per step",
+                   "config": args.config, "height": cfg["H"], "width": cfg["W"], "classes": cfg["C"],
+                   "keep_prob": cfg["keep_prob"], "sample": desc},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ---------------------------------------------------------------------------------------------------- product arm
-def time_engine(precision, weights, args, rank, local_rank, world, dev):
-    """Device-resident timed loop + e2e loop for one precision mode. Returns a dict of numbers."""
+def dp_parity_check(dev, rank, world, precision):
+    """N > 1 only, before anything is timed: the averaged shard gradients after the engine's two-chunk all-reduce equal
+    the single-GPU gradients of the concatenated batch, and the replicas stay bit-identical after two Adam steps
+    (scripts/dp_check.py at one small shape).  Raises on failure; the numbers go into the JSON line."""
+    import numpy as np
+    import torch
+    import torch.distributed as tdist
+    from fcn8s_tensorflow_b200 import dist as fdist
+    from fcn8s_tensorflow_b200.engine import Engine
+    from fcn8s_tensorflow_b200.fcn8s import synthetic_weights
+    C, per, H, W = 5, 2, 64, 96
+    N = per * world
+    rng = np.random.default_rng(0)
+    images = rng.integers(0, 256, size=(N, H, W, 3), dtype=np.uint8)
+    labels = np.eye(C, dtype=np.uint8)[rng.integers(0, C, size=(N, H, W))]
+    weights = synthetic_weights(C, 2, decoder_std_scale=10.0)
+    e = Engine(C, precision=precision, device=dev)
+    e.load_weights(weights)
+    fdist.attach(e)
+    fdist.broadcast_parameters(e)
+    xi, yi = fdist.shard_batch(images, labels, rank, world)
+    x = torch.from_numpy(np.ascontiguousarray(xi)).to(dev)
+    y = torch.from_numpy(np.ascontiguousarray(yi)).to(dev)
+    e.loss_and_backward(x, y, keep_prob=1.0)
+    e._start_reduce(e._reduced_upto, e.n_flat)
+    e.allreduce.finish()
+    e._reduced_upto = 0
+    torch.cuda.synchronize()
+    avg = ((e.g16.float() if e.g16 is not None else e.grads) / world).clone()
+    ref = Engine(C, precision=precision, device=dev)
+    ref.load_weights(weights)
+    ref.loss_and_backward(torch.from_numpy(images).to(dev), torch.from_numpy(labels).to(dev), keep_prob=1.0)
+    torch.cuda.synchronize()
+    err = float((avg - ref.grads).norm() / ref.grads.norm())
+    for _ in range(2):
+        e.train_step(x, y, 1e-4, keep_prob=0.5)
+    torch.cuda.synchronize()
+    other = e.params.clone()
+    tdist.broadcast(other, src=0)
+    same = bool(torch.equal(e.params, other))
+    tol = 2e-4 if (precision == "fp32" and e.g16 is None) else 2e-2
+    flag = torch.tensor([1 if (err <= tol and same) else 0], device=dev)
+    tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+    out = {"grad_rel_l2_vs_single_gpu": err, "tol": tol, "replicas_identical_after_2_steps": same,
+           "grad_comm": e.grad_comm, "shape": "%d x %dx%d, %d classes" % (N, H, W, C)}
+    del e, ref
+    torch.cuda.empty_cache()
+    if not int(flag.item()):
+        raise SystemExit("data-parallel parity check failed: %s" % json.dumps(out))
+    return out
+
+
+def time_train(cfg, precision, weights, args, rank, local_rank, world, dev, config_name):
+    """Device-resident timed loop + e2e loop of a train config for one precision mode."""
     import torch
     import torch.distributed as tdist
     from fcn8s_tensorflow_b200 import _capi as capi
@@ -153,9 +245,12 @@ def time_engine(precision, weights, args, rank, local_rank, world, dev):
     from fcn8s_tensorflow_b200.fcn8s import FCN8s
 
     lib = capi.load()
-    model = FCN8s(weights=weights, precision=precision, device=dev, data_parallel=world > 1)
+    model = FCN8s(weights=weights, precision=precision, device=dev, data_parallel=world > 1,
+                  backward_terms=args.backward_terms)
     eng = model.engine
-    images, labels = synthetic_feed(PER_GPU_BATCH, 1000 + rank)
+    per = cfg["per_gpu"]
+    kp = cfg["keep_prob"]
+    images, labels = synthetic_feed(cfg, per, 1000 + rank)
     x = torch.from_numpy(images).to(dev)
     y = torch.from_numpy(labels.view("uint8")).to(dev)
     lr = 1e-4
@@ -165,23 +260,44 @@ def time_engine(precision, weights, args, rank, local_rank, world, dev):
             tdist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n_warm, n_steps):
+        for _ in range(n_warm):
+            eng.train_step(x, y, lr, keep_prob=kp)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(n_steps):
+            eng.train_step(x, y, lr, keep_prob=kp)
+        b.record()
+        barrier()
+        return fdist.max_over_ranks(a.elapsed_time(b), dev)
+
     for _ in range(args.warmup):
-        eng.train_step(x, y, lr, keep_prob=0.5)
+        eng.train_step(x, y, lr, keep_prob=kp)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = lib.fcn8_launch_count() + eng.graph_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        eng.train_step(x, y, lr, keep_prob=0.5)
-    e1.record()
-    barrier()
-    ms = fdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms = timed(0, args.steps)
     launches = lib.fcn8_launch_count() + eng.graph_launches - l0
     clk = clocks.stop()
     loss = eng.loss_value(x.shape)
+    out = dict(ms=ms, launches=launches, clocks=clk, loss=loss)
+    if world > 1 and not args.profile:
+        # exposed cost of the gradient all-reduce: the same steps with the collective removed (replicas diverge, this
+        # is a timing probe only), re-captured as a new CUDA graph
+        saved = eng.allreduce
+        eng.allreduce = None
+        eng._graphs.clear()
+        eng._warm.clear()
+        ms_nc = timed(3, args.steps)
+        eng.allreduce = saved
+        eng._graphs.clear()
+        eng._warm.clear()
+        fdist.broadcast_parameters(eng)
+        out["allreduce_exposed_ms"] = (ms - ms_nc) / args.steps
+        out["ms_per_step_without_allreduce"] = ms_nc / args.steps
     # per-kernel CUDA-event timing of the tensor-core GEMMs: the same steps, run eagerly right after the timed region
     # (events cannot be recorded inside the replayed CUDA graph the timed region uses)
     timer = ops.KernelTimer()
@@ -190,42 +306,114 @@ def time_engine(precision, weights, args, rank, local_rank, world, dev):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(k_steps):
-        eng.train_step(x, y, lr, keep_prob=0.5)
+        eng.train_step(x, y, lr, keep_prob=kp)
     e3.record()
     barrier()
     ops.TIMER = None
     ksum = timer.summary()
     ksum["_steps"] = k_steps
     ksum["_ms"] = e2.elapsed_time(e3)
-
+    out["kernels"] = ksum
+    out["mem_gb"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     if args.profile:
-        return dict(ms=ms, launches=launches, clocks=clk, kernels=ksum, loss=loss, e2e_ms=float("nan"), h2d=0, d2h=0,
-                    mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+        out.update(e2e_ms=float("nan"), h2d=0, d2h=0)
+        return out
     # end to end through the public class surface: FCN8s.train() pulling host numpy batches from a generator
     # (pinned staging + H2D of every batch on a side stream, loss D2H every step), exactly the user's call
     import contextlib
     import io
-
-    def host_batches():
-        while True:
-            yield images, labels
+    feed_note = "host numpy batches from a python generator (the generator protocol of data_generator/batch_generator.py)"
+    if config_name == "c5":
+        # the KITTI feed path: PNG files -> resize -> [background, road] labels (generators.py = the reference's
+        # batch_generator_KITTI protocol), one generator per rank over its own synthetic tree
+        import tempfile
+        from fcn8s_tensorflow_b200 import generators
+        root = os.path.join(tempfile.gettempdir(), "fcn8_kitti_rank%d" % rank)
+        idir, ldir = generators.write_synthetic_kitti_tree(root, 16, seed=rank)
+        gen = generators.batch_generator(per, root, idir, ldir, image_size=(cfg["H"], cfg["W"]))
+        feed_note = ("generators.batch_generator (batch_generator_KITTI protocol): 16 synthetic 375x1242 PNG pairs per "
+                     "rank, decoded + bilinearly resized to 384x1248 + colour-matched on the host every step")
+    else:
+        def host_batches():
+            while True:
+                yield images, labels
+        gen = host_batches()
 
     def run_train(n):
         with contextlib.redirect_stdout(io.StringIO()):      # tqdm progress goes to stdout like the reference's
-            model.train(host_batches(), epochs=1, steps_per_epoch=n, learning_rate_schedule=lambda step: lr,
-                        keep_prob=0.5, record_summaries=False)
+            model.train(gen, epochs=1, steps_per_epoch=n, learning_rate_schedule=lambda step: lr,
+                        keep_prob=kp, record_summaries=False)
 
     run_train(min(args.warmup, 3))
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     run_train(args.steps)
     e1.record()
     barrier()
     e2e_ms = fdist.max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)), dev)
-    out = dict(ms=ms, launches=launches, clocks=clk, kernels=ksum, loss=loss, e2e_ms=e2e_ms,
-               h2d=int(images.nbytes + labels.nbytes), d2h=int(eng.loss_buf.numel() * 4),
-               mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    out.update(e2e_ms=e2e_ms, h2d=int(images.nbytes + labels.nbytes), d2h=int(eng.loss_buf.numel() * 4),
+               feed=feed_note, mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    model.engine = None
+    del model, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_predict(cfg, precision, weights, args, rank, local_rank, world, dev):
+    """configs[3]: FCN8s.predict on one full-resolution image; device-resident loop, per-kernel timing, e2e."""
+    import torch
+    from fcn8s_tensorflow_b200 import _capi as capi
+    from fcn8s_tensorflow_b200 import ops
+    from fcn8s_tensorflow_b200.fcn8s import FCN8s
+    lib = capi.load()
+    model = FCN8s(weights=weights, precision=precision, device=dev)
+    eng = model.engine
+    images, _ = synthetic_feed(cfg, cfg["per_gpu"], 1000 + rank)
+    x = torch.from_numpy(images).to(dev)
+
+    def loop(n, argmax):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            eng.predict(x, argmax=argmax)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b)
+
+    loop(args.warmup, True)
+    loop(max(1, args.warmup // 2), False)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = lib.fcn8_launch_count()
+    ms = loop(args.steps, True)
+    launches = lib.fcn8_launch_count() - l0
+    clk = clocks.stop()
+    ms_sm = loop(args.steps, False)
+    timer = ops.KernelTimer()
+    ops.TIMER = timer
+    k_steps = max(1, min(args.steps, 5))
+    loop(k_steps, True)
+    ksum_am = timer.summary()
+    loop(k_steps, False)
+    ksum_sm = timer.summary()
+    ops.TIMER = None
+    out = dict(ms=ms, ms_softmax=ms_sm, launches=launches, clocks=clk, kernels=ksum_am, kernels_softmax=ksum_sm,
+               ksteps=k_steps, mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    if not args.profile:
+        # e2e: the user's call -- host uint8 image in, host int64 class map out (H2D + forward + argmax + D2H)
+        for _ in range(2):
+            model.predict(images, argmax=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = model.predict(images, argmax=True)
+        out["e2e_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["h2d"], out["d2h"] = int(images.nbytes), int(res.nbytes)
+    else:
+        out.update(e2e_ms=float("nan"), h2d=0, d2h=0)
     model.engine = None
     del model, eng
     torch.cuda.empty_cache()
@@ -236,53 +424,112 @@ def ncu_traffic(precision):
     """DRAM bytes per step of the dominant kernel family from the committed ncu metrics pass (profiles/): sum of
     dram__bytes_read.sum + dram__bytes_write.sum over the step's conv_gemm_kernel / conv_halo_kernel launches of the
     encoder (bf16 operand instantiations).  None when the profile is missing or was taken in another mode."""
-    path = os.path.join(ROOT, "profiles", "r01_step_kernels_final.json")
-    if not os.path.exists(path):
-        return None, None
-    d = json.load(open(path)).get(precision)
-    if not d:
-        return None, None
-    # conv_gemm_kernel<BN, TF32 = 0, PAIR> are the bf16-operand instantiations (the tf32 ones serve the decoder)
-    tot = sum(v["dram_bytes"] for k, v in d.items()
-              if re.match(r"conv_gemm_kernel<\d+, 0, [01]>", k) or k.startswith("conv_halo_kernel"))
-    return tot, "profiles/r01_step_kernels_final.json"
+    for name in ("r02_step_kernels.json", "r01_step_kernels_final.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        d = json.load(open(path)).get(precision)
+        if not d:
+            continue
+        # conv_gemm_kernel<BN, TF32 = 0, ...> are the bf16-operand instantiations of the encoder / decoder GEMMs
+        tot = sum(v["dram_bytes"] for k, v in d.items()
+                  if re.match(r"conv_gemm_kernel<\d+, 0", k) or k.startswith("conv_halo_kernel"))
+        return tot, "profiles/" + name
+    return None, None
 
 
-def line_for(precision, r, args, world, peaks):
-    n_img = world * PER_GPU_BATCH * args.steps
+DTYPE_TEXT = {"fp32": "fp32-equivalent (bf16 hi/lo pair storage, error-compensated hi*hi+hi*lo+lo*hi products on the "
+                      "bf16 tensor cores, fp32 accumulate; logits within 1e-4 of the fp64 CPU graph)",
+              "bf16": "bf16"}
+
+
+def train_line(cfg, precision, r, args, world, peaks):
+    n_img = world * cfg["per_gpu"] * args.steps
     value = n_img / (r["ms"] * 1e-3)
     k = r["kernels"].get("conv_gemm", dict(launches=0, flops=0.0, ms=1.0))
     kw = r["kernels"].get("wgrad_gemm", dict(launches=0, flops=0.0, ms=1.0))
     ksteps = r["kernels"].get("_steps", args.steps)
     step_ms = r["ms"] / args.steps
     achieved = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["launches"] else 0.0
-    dtype = {"fp32": "fp32-equivalent (bf16 hi/lo pair storage, error-compensated hi*hi+hi*lo+lo*hi products on the "
-                     "bf16 tensor cores, fp32 accumulate; logits within 1e-4 of the fp64 CPU graph)",
-             "tf32x3": "fp32 storage, 3xTF32 error-compensated products", "tf32": "tf32", "bf16": "bf16"}[precision]
-    return {
-        "value": value, "ms_per_step": r["ms"] / args.steps, "dtype": dtype,
-        "gpu_launches": int(r["launches"]),
+    traffic, traffic_src = ncu_traffic(precision) if args.config == "c2" else (None, None)
+    dtype = DTYPE_TEXT[precision]
+    if precision == "fp32" and args.backward_terms != 3:
+        dtype += "; NON-DEFAULT backward: %d bf16 product(s) per algorithmic product in dgrad / wgrad" % args.backward_terms
+    line = {
+        "value": value, "ms_per_step": step_ms, "dtype": dtype, "gpu_launches": int(r["launches"]),
         "roofline": {
             "bound": "tensor", "kernel": "conv_gemm_kernel + conv_halo_kernel (tcgen05 implicit-GEMM fprop + dgrad of the "
                                          "encoder, all tile widths)",
             "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-            "traffic": ncu_traffic(precision)[0], "traffic_unit": "DRAM bytes per step over the same launches "
-                                                                  "(ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-            "traffic_source": ncu_traffic(precision)[1], "peak_source": peaks["source"],
+            "traffic": traffic, "traffic_unit": "DRAM bytes per step over the same launches "
+                                                "(ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": traffic_src, "peak_source": peaks["source"],
             "launches_timed": k["launches"], "kernel_ms_per_step": k["ms"] / ksteps,
             "share_of_step": k["ms"] / ksteps / step_ms,
-            "note": "achieved = algorithmic 2*M*N*K FLOPs of the launches / their CUDA-event time on the launching "
-                    "stream, timed live in this run over %d eager steps right after the timed region (the timed "
-                    "region replays a CUDA graph of the step, inside which events cannot be recorded)" % ksteps
-                    + ("; the fp32-equivalent mode executes 3 bf16 MMAs per algorithmic product, so its own ceiling "
-                       "is peak/3" if precision == "fp32" else ""),
+            "timing": "per-launch CUDA events on the launching stream over %d EAGER steps run right after the timed "
+                      "region in the same process (the timed region replays a CUDA graph of the step, inside which "
+                      "events cannot be recorded); achieved = algorithmic 2*M*N*K FLOPs of the launches / their time"
+                      % ksteps
+                      + ("; the fp32-equivalent mode executes 3 bf16 MMAs per algorithmic product, so its own ceiling "
+                         "is peak/3" if precision == "fp32" and args.backward_terms == 3 else ""),
             "wgrad_gemm": {"achieved": kw["flops"] / (kw["ms"] * 1e-3) / 1e12 if kw["launches"] else 0.0,
                            "kernel_ms_per_step": kw["ms"] / ksteps, "share_of_step": kw["ms"] / ksteps / step_ms},
-            "whole_step_tflops_per_gpu": value / world * TRAIN_GFLOP_PER_IMAGE / 1e3,
+            "whole_step_tflops_per_gpu": value / world * cfg["train_gflop"] / 1e3,
+            "whole_step_frac_of_peak": value / world * cfg["train_gflop"] / 1e3 / peaks["tflops"],
         },
         "e2e": {"value": n_img / (r["e2e_ms"] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": r["h2d"],
-                "d2h_bytes_per_step": r["d2h"]},
+                "d2h_bytes_per_step": r["d2h"], "feed": r.get("feed")},
         "clocks": r["clocks"], "final_loss": r["loss"], "peak_mem_gb": r["mem_gb"],
+    }
+    if "allreduce_exposed_ms" in r:
+        line["allreduce"] = {"exposed_ms_per_step": r["allreduce_exposed_ms"],
+                             "ms_per_step_without_allreduce": r["ms_per_step_without_allreduce"],
+                             "how": "same steps re-timed with the collective removed from the captured step"}
+    return line
+
+
+def predict_line(cfg, precision, r, args, peaks):
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    n = cfg["per_gpu"]
+    value = n * args.steps / (r["ms"] * 1e-3)
+    # decoder logits path = the kernels that turn f3 [n, H/8, W/8, C] into the predictor's output
+    f3_bytes = n * (H // 8) * (W // 8) * C * 4
+    out_bytes = {"argmax": n * H * W * 8, "softmax": n * H * W * C * 4}
+
+    def path(ks, which):
+        tags = [t for t in ("upscore8", "predictor", "upscore8_fused") if t in ks]
+        ms = sum(ks[t]["ms"] for t in tags) / r["ksteps"]
+        algo = f3_bytes + out_bytes[which]
+        return {"kernels_timed": tags, "ms": ms, "algorithmic_bytes": algo,
+                "achieved_gbs": algo / (ms * 1e-3) / 1e9 if ms > 0 else 0.0}
+    pa, ps = path(r["kernels"], "argmax"), path(r["kernels_softmax"], "softmax")
+    conv = r["kernels"].get("conv_gemm", dict(launches=0, flops=0.0, ms=1.0))
+    conv_tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["launches"] else 0.0
+    return {
+        "value": value, "ms_per_step": r["ms"] / args.steps, "dtype": DTYPE_TEXT[precision],
+        "gpu_launches": int(r["launches"]),
+        "roofline": {
+            "bound": "hbm", "kernel": "decoder logits path of predict(argmax): upscore8 transposed convolution (16x16 / 8 "
+                                      "phase GEMM) -> argmax; kernels: " + ", ".join(pa["kernels_timed"]),
+            "achieved": pa["achieved_gbs"], "peak": peaks["hbm"], "unit": "GB/s", "frac": pa["achieved_gbs"] / peaks["hbm"],
+            "traffic": None, "peak_source": peaks["source"], "kernel_ms_per_image": pa["ms"],
+            "algorithmic_bytes_per_launch": pa["algorithmic_bytes"],
+            "algorithmic_bytes": "read f3 [n,H/8,W/8,C] fp32 + write the int64 class map [n,H,W] (fcn8s_tensorflow.py:269)",
+            "softmax_output": {"achieved": ps["achieved_gbs"], "frac": ps["achieved_gbs"] / peaks["hbm"],
+                               "kernel_ms_per_image": ps["ms"], "algorithmic_bytes_per_launch": ps["algorithmic_bytes"],
+                               "images_per_s": n * args.steps / (r["ms_softmax"] * 1e-3),
+                               "note": "predict(argmax=False): fp32 softmax [n,H,W,C] out (:268)"},
+            "encoder_conv_gemm": {"achieved_tflops": conv_tf, "frac_of_bf16_peak": conv_tf / peaks["tflops"],
+                                  "kernel_ms_per_image": conv["ms"] / r["ksteps"],
+                                  "share_of_step": conv["ms"] / r["ksteps"] / (r["ms"] / args.steps)},
+            "whole_forward_tflops": value * cfg["fwd_gflop"] / 1e3,
+            "timing": "per-launch CUDA events on the launching stream over %d predict calls right after the timed "
+                      "region, same process" % r["ksteps"],
+        },
+        "e2e": {"value": n * args.steps / (r["e2e_ms"] * 1e-3), "unit": "images/s", "h2d_bytes_per_step": r["h2d"],
+                "d2h_bytes_per_step": r["d2h"],
+                "feed": "FCN8s.predict(host uint8 image) -> host int64 class map: H2D, forward, argmax, D2H per call"},
+        "clocks": r["clocks"], "peak_mem_gb": r["mem_gb"],
     }
 
 
@@ -292,15 +539,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "tf32", "tf32x3"],
-                    help="main line; the other of fp32/bf16 is reported under 'alt'")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"],
+                    help="main line (default: the config's); the other of fp32/bf16 is reported under 'alt'")
+    ap.add_argument("--backward-terms", type=int, default=3, choices=[1, 2, 3],
+                    help="fp32 mode only, NON-DEFAULT measurement: bf16 products per algorithmic product in backward")
     ap.add_argument("--no-alt", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="ncu-friendly run: no warm-up floor, no e2e loop, no alt, no CPU baseline (never a bench value)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, cfg)
     if args.profile:
         args.no_alt = args.no_cpu_baseline = True
     else:
@@ -315,32 +566,43 @@ def main():
     rank, local_rank, world = fdist.init("nccl")
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if cfg["kind"] == "predict" and world > 1:
+        raise SystemExit("config c4 is single-GPU inference (replicas only)")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     peaks = measured_peaks()
-    weights = synthetic_weights(C, 2)
-    main_r = time_engine(args.precision, weights, args, rank, local_rank, world, dev)
-    line = {"metric": METRIC, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    precision = args.precision or cfg["precision"]
+    weights = synthetic_weights(cfg["C"], 2)
+    dp = dp_parity_check(dev, rank, world, precision) if world > 1 else None
+
+    def run(p):
+        if cfg["kind"] == "predict":
+            return predict_line(cfg, p, time_predict(cfg, p, weights, args, rank, local_rank, world, dev), args, peaks)
+        return train_line(cfg, p, time_train(cfg, p, weights, args, rank, local_rank, world, dev, args.config), args,
+                          world, peaks)
+
+    line = {"metric": cfg["metric"], "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic"}
-    line.update(line_for(args.precision, main_r, args, world, peaks))
+    line.update(run(precision))
     line["config"] = {
-        "workload": "BASELINE configs[1]: FCN-8s train step, %d images of 512x1024x3 per GPU, 20 classes, keep_prob "
-                    "0.5, Adam lr 1e-4, synthetic uint8 images + bool one-hot labels, He-init encoder" % PER_GPU_BATCH,
-        "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "height": H, "width": W, "classes": C,
-        "parallelism": "dp%d: one NCCL all-reduce of the 134.5M-element flat gradient buffer per step" % world
-                       if world > 1 else "single GPU",
-        "l2_flush": "not needed: every step streams > 2 GB of activations and 2 GB of optimizer state, far above "
-                    "the 126 MB L2 (inputs larger than L2)",
-        "train_gflop_per_image": TRAIN_GFLOP_PER_IMAGE,
+        "workload": cfg["workload"], "config": args.config, "kind": cfg["kind"],
+        "per_gpu_batch": cfg["per_gpu"], "global_batch": cfg["per_gpu"] * world, "height": cfg["H"], "width": cfg["W"],
+        "classes": cfg["C"], "keep_prob": cfg["keep_prob"],
+        "parallelism": ("dp%d: one NCCL all-reduce of the flat gradient buffer per step" % world) if world > 1
+                       else "single GPU",
+        "l2_flush": "not needed: every step streams > 1 GB of activations (and 4 GB of optimizer state when "
+                    "training), far above the 126 MB L2 (inputs larger than L2)",
+        "gflop_per_image": cfg["train_gflop"] if cfg["kind"] == "train" else cfg["fwd_gflop"],
     }
-    if not args.no_alt and args.precision in ("fp32", "bf16"):
-        alt_p = "bf16" if args.precision == "fp32" else "fp32"
-        alt_r = time_engine(alt_p, weights, args, rank, local_rank, world, dev)
-        line["alt"] = line_for(alt_p, alt_r, args, world, peaks)
-        line["alt"]["note"] = "same workload and run, precision mode '%s' (BASELINE configs[2] trains in bf16)" % alt_p
+    if dp is not None:
+        line["dp_check"] = dp
+    alt_p = cfg["alt"] if precision == cfg["precision"] else cfg["precision"]
+    if not args.no_alt and alt_p and alt_p != precision:
+        line["alt"] = run(alt_p)
+        line["alt"]["note"] = "same workload and run, precision mode '%s'" % alt_p
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded sample of the same workload on the host cores: one untimed step, then whole steps for ~10 s
-        fn, img_per_step = cpu_reference_step_fn(weights, (512, 1024))
+        fn, desc = cpu_reference_step_fn(cfg, weights)
         fn()
         n_cpu = 0
         t0 = time.perf_counter()
@@ -348,11 +610,8 @@ def main():
             fn()
             n_cpu += 1
         dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": n_cpu * img_per_step / dt, "unit": "images/s", "cores": os.cpu_count(),
-                                "kind": "port",
-                                "sample": "%d train steps on 1 image of 512x1024 (batch 1) after one warm-up step, "
-                                          "torch-CPU fp32 restatement of the reference graph (TF1 unavailable), %.1f s"
-                                          % (n_cpu, dt)}
+        line["cpu_baseline"] = {"value": n_cpu / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "%d steps after one warm-up step, %.1f s: %s" % (n_cpu, dt, desc)}
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -23,6 +23,7 @@ EXPORTS = [
     "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
     "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
     "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_upscore_tc_gather", "fcn8_upscore_tc_scatter",
+    "fcn8_cast_bf16",
 ]
 
 
@@ -148,7 +149,9 @@ def load():
     lib.fcn8_upscore_tc_cp.restype = C.c_int32
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
-    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+    lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,
+                              vp]
+    lib.fcn8_cast_bf16.argtypes = [vp, vp, sz, vp]
     lib.fcn8_set_step_scalars.argtypes = [vp, C.c_float, C.c_uint32, vp]
     lib.fcn8_shadow_weights.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_l2_reg.argtypes = [vp, vp, vp, sz, C.c_float, vp]

@@ -133,6 +133,12 @@ void choose_patch(int N, int H, int W, int total_log, int* lbw, int* lbh, int* l
     }
 }
 
+// cudaFuncSetAttribute is per device: the "already set" flags of the launchers are indexed by the current device
+int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
 int g_sm_limit = 0;  // fcn8_set_sm_limit: persistent GEMM grids leave SMs free for a co-running collective
 int num_sms() {
   static int n = 0;
@@ -157,7 +163,7 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cin=%d must be a multiple of %d", p->Cin, CH);
   if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "conv: Cout=%d must be a multiple of 64", p->Cout);
   if (!(p->ksize & 1)) return fail(FCN8_ERR_BAD_SHAPE, "conv: ksize must be odd");
-  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "conv: nseg must be 1 or 3");
+  if (p->nseg < 1 || p->nseg > 3) return fail(FCN8_ERR_UNSUPPORTED, "conv: nseg must be 1, 2 or 3");
   if (p->dtype != FCN8_BF16 && (p->w_mode || p->out_lo || p->residual_lo))
     return fail(FCN8_ERR_UNSUPPORTED, "conv: w_mode / out_lo / residual_lo need FCN8_BF16 operands");
   if (p->w_mode < 0 || p->w_mode > 2) return fail(FCN8_ERR_BAD_SHAPE, "conv: w_mode must be 0, 1 or 2");
@@ -224,7 +230,8 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
 template <int BN, bool TF32>
 cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -238,7 +245,8 @@ cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
 // CTA-pair variant (clusters of two CTAs, tcgen05 cta_group::2): bf16 operands, 256-column tiles; `grid` is even.
 cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<256, true>;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -265,7 +273,8 @@ cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int
 
 template <int BN, bool RB = false>
 cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          HaloSmem<BN, RB>::kBytes);
@@ -286,7 +295,8 @@ constexpr int wgrad_smem_bytes() {
 }
 template <int BN, bool TF32>
 cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
   constexpr int smem = wgrad_smem_bytes<BN, TF32>();
   if (!attr_done) {
     cudaError_t e =
@@ -300,7 +310,8 @@ cudaError_t launch_wgrad_t(const TensorMaps3& maps, const WgradArgs& a, int grid
 
 cudaError_t launch_wgrad_pair(const TensorMaps3& maps, const WgradArgs& a, int grid, cudaStream_t st) {
   constexpr int smem = 3 * (4 * 128 * 128) + 1024 + 1024;   // three stages of (2 + 2) 128-pixel chunks
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<256, false, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -373,7 +384,7 @@ int plan_wgrad(const Fcn8WgradParams* p, WgradPlan* pl) {
   if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: empty tensor");
   if (p->Cin % CH) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cin=%d must be a multiple of %d", p->Cin, CH);
   if (p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: Cout=%d must be a multiple of 64", p->Cout);
-  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 or 3");
+  if (p->nseg < 1 || p->nseg > 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1, 2 or 3");
   int bn = p->force_bn ? p->force_bn : (p->Cout % 256 == 0 ? 256 : (p->Cout % 128 == 0 ? 128 : 64));
   if (p->dtype == FCN8_F32 && bn == 256 && !p->force_bn) bn = 128;  // keep >= 3 smem stages with 4-byte operands
   if ((bn != 64 && bn != 128 && bn != 256) || p->Cout % bn)
@@ -500,7 +511,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     return fail(FCN8_ERR_BAD_SHAPE, "conv: RESIDUAL flag without residual");
   if ((p->flags & FCN8_EPI_COLSUM) && (!p->colsum || p->Cout > kColsumMax))
     return fail(FCN8_ERR_BAD_SHAPE, "conv: COLSUM flag needs colsum and Cout <= %d", kColsumMax);
-  if (p->nseg == 3 && (!p->x_lo || !p->wp_lo)) return fail(FCN8_ERR_BAD_SHAPE, "conv: nseg=3 needs x_lo and wp_lo");
+  if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->wp_lo))
+    return fail(FCN8_ERR_BAD_SHAPE, "conv: nseg=3 needs x_lo and wp_lo (nseg=2: wp_lo)");
   ConvPlan pl;
   int rc = plan_conv(p, &pl);
   if (rc) return rc;
@@ -604,7 +616,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     const int hgrid = (int)(tiles < num_sms() ? tiles : num_sms());
     if ((long long)pl.tiles_n * pl.BN > 256) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs Cout <= 256");
     // weights resident in shared memory when the CTA's whole slice is one group of 9 taps (conv1_2 fwd / dgrad, bf16)
-    const bool resident = pl.BN == 64 && pl.tiles_n == 1 && (p->nseg == 3 ? 2 : 1) * (p->Cin / 64) <= 1 && !g_debug[2];
+    const bool resident = pl.BN == 64 && pl.tiles_n == 1 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 1 && !g_debug[2];
     cudaError_t he = pl.BN == 256 ? launch_halo_t<256>(maps, a, hgrid, (cudaStream_t)stream)
                    : pl.BN == 128 ? launch_halo_t<128>(maps, a, hgrid, (cudaStream_t)stream)
                    : resident     ? launch_halo_t<64, true>(maps, a, hgrid, (cudaStream_t)stream)
@@ -678,8 +690,9 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   if (!p || !p->x || !p->dy || !p->dw) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: null pointer");
   if (!aligned16(p->x) || !aligned16(p->dy) || !aligned16(p->dw))
     return fail(FCN8_ERR_BAD_ALIGN, "wgrad: pointers must be 16-byte aligned");
-  if (p->nseg == 3 && (!p->x_lo || !p->dy_lo)) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: nseg=3 needs x_lo and dy_lo");
-  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1 or 3");
+  if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->dy_lo))
+    return fail(FCN8_ERR_BAD_SHAPE, "wgrad: nseg=3 needs x_lo and dy_lo (nseg=2: dy_lo)");
+  if (p->nseg < 1 || p->nseg > 3) return fail(FCN8_ERR_UNSUPPORTED, "wgrad: nseg must be 1, 2 or 3");
   if (wgrad_use_halo(p)) {
     if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "wgrad: empty tensor");
     WgradHaloPlan hp;
@@ -712,7 +725,8 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     ha.splits = hp.splits;
     ha.tiles_n = hp.tiles_n;
     ha.acc_scale = g_debug[0] ? 1.f : 1.f + 8.f * (float)(p->nseg * hp.patches_per_split) * kRzBiasPerMma;
-    static bool attr_done = false;
+    static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
     if (!attr_done) {
       cudaError_t ae = cudaFuncSetAttribute(wgrad_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             WgradHaloCfg::kSmemBytes);
@@ -949,15 +963,24 @@ int32_t fcn8_set_step_scalars(float* scalars, float lr_t, uint32_t seed, void* s
   cudaError_t e = launch_set_step_scalars(scalars, lr_t, seed, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "set_step_scalars launch");
 }
+int32_t fcn8_cast_bf16(const float* x, void* out, size_t n, void* stream) {
+  if (!x || !out) return fail(FCN8_ERR_BAD_SHAPE, "cast_bf16: null pointer");
+  if (!aligned16(x) || !aligned16(out)) return fail(FCN8_ERR_BAD_ALIGN, "cast_bf16: pointers must be 16-byte aligned");
+  cudaError_t e = launch_cast_bf16(x, out, n, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cast_bf16 launch");
+}
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, void* stream) {
-  if (!p || !g || !m || !v) return fail(FCN8_ERR_BAD_SHAPE, "adam: null pointer");
+                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, const void* g_bf16,
+                  void* stream) {
+  if (!p || (!g && !g_bf16) || !m || !v) return fail(FCN8_ERR_BAD_SHAPE, "adam: null pointer");
+  if (g_bf16 && (reinterpret_cast<uintptr_t>(g_bf16) & 7u)) return fail(FCN8_ERR_BAD_ALIGN, "adam: g_bf16 alignment");
+  if (!g) g = p;   // never read when g_bf16 is set; keeps the alignment check below meaningful
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v) || (w_hi && !aligned16(w_hi)) ||
       (w_lo && !aligned16(w_lo)))
     return fail(FCN8_ERR_BAD_ALIGN, "adam: pointers must be 16-byte aligned");
   if (w_lo && !w_hi) return fail(FCN8_ERR_BAD_SHAPE, "adam: w_lo without w_hi");
   cudaError_t e =
-      launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, w_hi, w_lo, lr_ptr, (cudaStream_t)stream);
+      launch_adam(p, g, m, v, n, lr_t, beta1, beta2, eps, grad_scale, w_hi, w_lo, lr_ptr, g_bf16, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "adam launch");
 }
 int32_t fcn8_shadow_weights(const float* p, void* w_hi, void* w_lo, size_t n, void* stream) {

@@ -753,7 +753,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       uint32_t aph = 0, bph = 0;
       if constexpr (RB) {
         // resident weights: groups (set, cb, kh) of three taps; set 0 = hi (maps.b[0]), set 1 = lo (maps.b[1])
-        const int nsets = g.nseg == 3 ? 2 : 1;
+        const int nsets = g.nseg >= 2 ? 2 : 1;
         if (elect_one()) {
           mbar_expect_tx(&b_full[0], static_cast<uint32_t>(nsets * g.cblocks * 3) * HS::kBBytes);
           for (int set = 0; set < nsets; ++set)

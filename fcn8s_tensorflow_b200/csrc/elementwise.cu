@@ -649,7 +649,7 @@ __device__ __forceinline__ void store_shadow4(__nv_bfloat16* hi, __nv_bfloat16* 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr_t, float b1, float b2, float eps, float gscale,
                             __nv_bfloat16* __restrict__ w_hi, __nv_bfloat16* __restrict__ w_lo,
-                            const float* __restrict__ lr_ptr) {
+                            const float* __restrict__ lr_ptr, const __nv_bfloat16* __restrict__ g16) {
   pdl_launch_dependents();
   pdl_wait();
   if (lr_ptr) lr_t = __ldg(lr_ptr);  // per-step value in device memory (CUDA-graph replays keep kernel arguments)
@@ -657,7 +657,15 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
-    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 gg;
+    if (g16) {   // gradients that went through a bf16 all-reduce (data-parallel option): 8 B instead of 16 B per 4
+      const uint2 q = reinterpret_cast<const uint2*>(g16)[i];
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+      gg = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gg = reinterpret_cast<const float4*>(g)[i];
+    }
     float4 mm = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
 #define FCN8_ADAM1(c)                                  \
@@ -677,7 +685,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   // tail (n not a multiple of 4)
   if (blockIdx.x == 0) {
     for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-      const float gr = g[i] * gscale;
+      const float gr = (g16 ? __bfloat162float(g16[i]) : g[i]) * gscale;
       m[i] = b1 * m[i] + (1.f - b1) * gr;
       v[i] = b2 * v[i] + (1.f - b2) * gr * gr;
       p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
@@ -689,8 +697,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
-                        float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, cudaStream_t st) {
-  { (void)launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, 256, 148 * 8)), dim3(256), 0, st, p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo), lr_ptr); }
+                        float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, const void* g16,
+                        cudaStream_t st) {
+  { (void)launch_k(adam_kernel, dim3(grid_for(n / 4 + 1, 256, 148 * 8)), dim3(256), 0, st, p, g, m, v, n, lr_t, b1, b2, eps, gscale, static_cast<__nv_bfloat16*>(w_hi), static_cast<__nv_bfloat16*>(w_lo), lr_ptr, static_cast<const __nv_bfloat16*>(g16)); }
+  return cudaGetLastError();
+}
+// out = bf16(x): the flat gradient buffer in the wire format of the bf16 all-reduce option (n multiple of 4 handled
+// vectorised, the tail scalar).
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t n4 = n / 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) out[i] = __float2bfloat16_rn(x[i]);
+}
+cudaError_t launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
+  { (void)launch_k(cast_bf16_kernel, dim3(grid_for(n / 4 + 1, 256, 148 * 8)), dim3(256), 0, st, x, static_cast<__nv_bfloat16*>(out), n); }
   return cudaGetLastError();
 }
 // scalars[0] = lr_t (float), scalars[1] = dropout seed (uint32 bits): written by a kernel (arguments by value) so that

@@ -58,7 +58,9 @@ cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n
 cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
                                        int ldc, cudaStream_t st);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
-                        float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, cudaStream_t st);
+                        float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, const void* g16,
+                        cudaStream_t st);
+cudaError_t launch_cast_bf16(const float* x, void* out, size_t n, cudaStream_t st);
 cudaError_t launch_set_step_scalars(float* scalars, float lr_t, uint32_t seed, cudaStream_t st);
 cudaError_t launch_shadow(const float* p, void* hi, void* lo, size_t n, cudaStream_t st);
 cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st);

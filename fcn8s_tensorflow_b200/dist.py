@@ -81,7 +81,11 @@ def attach(engine, group=None):
     """Make `engine` data-parallel over the default (or given) process group."""
     ar = GradientAllReduce(group)
     engine.world = ar.world
+    engine.rank = dist.get_rank(group) if dist.is_initialized() else 0
     engine.allreduce = ar if ar.world > 1 else None
+    if engine.allreduce is not None and getattr(engine, "grad_comm", "fp32") == "bf16":
+        # wire copy of the flat gradient: the collective moves 269 MB instead of 538 MB per step
+        engine.g16 = torch.zeros(engine.n_flat, dtype=torch.bfloat16, device=engine.device)
     return engine
 
 
@@ -90,8 +94,20 @@ def broadcast_parameters(engine, src=0, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         for t in (engine.params, engine.adam_m, engine.adam_v):
             dist.broadcast(t, src=src, group=group)
+        step = torch.tensor([engine.global_step], dtype=torch.int64, device=engine.params.device)
+        dist.broadcast(step, src=src, group=group)
+        engine.global_step = int(step.item())
         engine._packed_dirty = True
         engine._shadow_dirty = True
+
+
+def all_reduce_metrics(loss_pair, conf, group=None):
+    """Evaluation under data parallelism: sum the per-rank (loss sum, batch count) pair and the confusion matrix so
+    that every rank reports the metrics of the whole evaluation set (and takes the same save-best decisions)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(loss_pair, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(conf, op=dist.ReduceOp.SUM, group=group)
+    return loss_pair, conf
 
 
 def max_over_ranks(value, device):

@@ -9,6 +9,7 @@ library raises.
 
 Precision modes: see `Engine`.  The decoder (score heads, transposed convs, loss) is fp32 in every mode.
 """
+import functools
 import os
 from collections import OrderedDict
 
@@ -92,6 +93,19 @@ def flat_layout(num_classes):
     return layout, off
 
 
+def _on_device(fn):
+    """Run an Engine method with the engine's device current: every launch goes to `torch.cuda.current_stream()` and
+    the library's runtime calls target the current device, so an Engine built with device='cuda:1' must not depend on
+    the caller having called `torch.cuda.set_device(1)`."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class Engine:
     """Precision modes (`precision=`), all with fp32 accumulation in TMEM, fp32 master weights / gradients / Adam:
 
@@ -106,7 +120,12 @@ class Engine:
 
     MODES = ("bf16", "fp32", "tf32x3", "tf32")
 
-    def __init__(self, num_classes, precision="bf16", device=None):
+    def __init__(self, num_classes, precision="bf16", device=None, backward_terms=3, grad_comm=None):
+        """backward_terms (precision "fp32" only): bf16 products per algorithmic product in the BACKWARD GEMMs (dgrad and
+        filter gradients of the encoder): 3 = hi*hi + hi*lo + lo*hi like the forward pass (default); 2 / 1 are the
+        measured, non-default "fp32 forward / reduced backward" modes (one operand, or both, rounded to bf16).
+        grad_comm: wire format of the data-parallel gradient all-reduce, "fp32" or "bf16" (default: bf16 in the bf16
+        precision mode, fp32 otherwise)."""
         if not torch.cuda.is_available():
             raise capi.Fcn8Error("fcn8s_tensorflow_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if precision not in self.MODES:
@@ -115,7 +134,17 @@ class Engine:
             raise ValueError("num_classes must be in [1, 32]")
         self.lib = capi.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        capi.check(self.lib.fcn8_device_check(self.device.index or 0))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        capi.check(self.lib.fcn8_device_check(self.device.index))
+        if backward_terms not in (1, 2, 3):
+            raise ValueError("backward_terms must be 1, 2 or 3")
+        self.bt = int(backward_terms) if precision == "fp32" else 3
+        self.grad_comm = grad_comm or os.environ.get("FCN8_GRAD_COMM") or ("bf16" if precision == "bf16" else "fp32")
+        if self.grad_comm not in ("fp32", "bf16"):
+            raise ValueError("grad_comm must be 'fp32' or 'bf16'")
+        self.rank = 0
+        self.g16 = None          # bf16 wire copy of the flat gradient (allocated by dist.attach when grad_comm == bf16)
         self.C = num_classes
         self.precision = precision
         self.pair = precision == "fp32"                      # bf16 hi/lo pair activations
@@ -162,6 +191,7 @@ class Engine:
         buf = self.params if buf is None else buf
         return buf[off:off + int(np.prod(shape))].view(shape)
 
+    @_on_device
     def load_weights(self, weights):
         """weights: mapping TF variable name -> array/tensor in TF layout. Missing names raise KeyError."""
         for name in self.layout:
@@ -173,12 +203,15 @@ class Engine:
         self._packed_dirty = True
         self._shadow_dirty = True
 
+    @_on_device
     def state_dict(self):
         return OrderedDict((n, self.view(n).detach().cpu().clone()) for n in self.layout)
 
+    @_on_device
     def grad_dict(self):
         return OrderedDict((n, self.view(n, self.grads).detach().cpu().clone()) for n in self.layout)
 
+    @_on_device
     def repack(self):
         """Derived tensor-core operands of the parameters.  hwio modes: only conv1_1 (27 -> 64 im2col columns) and the
         upscore8 phase-GEMM operands are packed (the rest is the shadow written by Adam); legacy tf32 modes: fprop and
@@ -255,6 +288,7 @@ class Engine:
         return ops.conv_gemm(x, wp, cout, k, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo, **kw)
 
     # ------------------------------------------------------------------ forward
+    @_on_device
     def forward(self, images, keep_prob=1.0, seed=0, train=False, _scalars_set=False):
         """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (a view of an arena buffer).
         The dropout seed is read by the kernels from `step_scalars` (set here unless the caller already did)."""
@@ -371,6 +405,7 @@ class Engine:
         return (int(seed) * 2 + (1 if layer == "fc7" else 0)) & 0xFFFFFFFF
 
     # ------------------------------------------------------------------ loss + backward
+    @_on_device
     def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0, _scalars_set=False):
         """Forward + backward of optimizer/total_loss (fcn8s_tensorflow.py:250-257) into self.grads.
         labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2)."""
@@ -425,12 +460,13 @@ class Engine:
             dyh, dyl = self._split(A, "dy_" + name, dy)
             xl = A["in_%s.lo" % name] if self.x3 else None
             if name == "conv1_1":
-                ops.wgrad_gemm(x_in, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl, pair=pair)
+                ops.wgrad_gemm(x_in, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl, pair=pair,
+                               nseg=self.bt)
                 break
-            ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair)
+            ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair, nseg=self.bt)
             if name == "fc6" and self.allreduce is not None and getattr(self.allreduce, "overlap", False):
                 # decoder, fc7 and fc6 gradients (89 % of the buffer) are final: reduce them under the conv backward
-                self.allreduce.start(G[:self.head_elems])
+                self._start_reduce(0, self.head_elems)
                 self._reduced_upto = self.head_elems
                 if self.dp_reserve_sms > 0:   # leave SMs to the collective's CTAs while it runs under the backward
                     self.lib.fcn8_set_sm_limit(self.sm_count - self.dp_reserve_sms)
@@ -439,7 +475,7 @@ class Engine:
             prev_db = self.view(prev_name + "/biases", G)
             if self.hwio:
                 wh, wl = self._wview(name)
-                wkw = dict(wp_lo=wl, pair=pair, w_mode=2)
+                wkw = dict(wp_lo=wl, pair=pair, w_mode=2, nseg=self.bt)
             else:
                 wh = self.packed[name][2]
                 wkw = dict(x_lo=dyl, wp_lo=self.packed[name][3])
@@ -484,14 +520,27 @@ class Engine:
     def _lr_t(self, lr, t):
         return float(lr) * float(np.sqrt(1.0 - BETA2 ** t) / (1.0 - BETA1 ** t))
 
+    def _start_reduce(self, lo, hi):
+        """Start the all-reduce of flat-gradient elements [lo, hi) in the wire format `grad_comm` (bf16: the slice is
+        cast into the bf16 wire buffer first -- one more pass over it, for half the bytes on NVLink)."""
+        if hi <= lo:
+            return
+        if self.g16 is not None:
+            ops.cast_bf16(self.grads[lo:hi], self.g16[lo:hi])
+            self.allreduce.start(self.g16[lo:hi])
+        else:
+            self.allreduce.start(self.grads[lo:hi])
+
     def _reduce_and_adam(self, lr_t):
         if self.allreduce is not None:
-            self.allreduce.start(self.grads[self._reduced_upto:])
+            self._start_reduce(self._reduced_upto, self.n_flat)
             self.allreduce.finish()
             self._reduced_upto = 0
         ops.adam(self.params, self.grads, self.adam_m, self.adam_v, lr_t, BETA1, BETA2, EPS, 1.0 / self.world,
-                 w_hi=self.w_hi, w_lo=self.w_lo, lr_ptr=self.step_scalars[0:1])
+                 w_hi=self.w_hi, w_lo=self.w_lo, lr_ptr=self.step_scalars[0:1],
+                 g_bf16=self.g16 if self.allreduce is not None else None)
 
+    @_on_device
     def adam_step(self, lr):
         """TF-form Adam over the flat buffer (one launch), then global_step += 1 (fcn8s_tensorflow.py:256-257)."""
         t = self.global_step + 1
@@ -509,6 +558,7 @@ class Engine:
         self._packed_dirty = True
         self.repack()     # derived operands of the updated parameters, ready for the next step's forward
 
+    @_on_device
     def train_step(self, images, labels, lr, keep_prob=0.5, l2_rate=0.0, seed=None):
         """One `sess.run([train_op, total_loss, global_step])` (fcn8s_tensorflow.py:565-572).
         Returns the device tensor loss_buf; total_loss = loss_buf[0] / (N*H*W) + loss_buf[1] (see `loss_value`).
@@ -518,7 +568,8 @@ class Engine:
         two per-step scalars (lr_t, dropout seed) are written to device memory by a 1-thread kernel, so the host's
         cost per step is three launches.  FCN8_GRAPHS=0 (or an installed ops.TIMER) keeps the eager path."""
         if seed is None:
-            seed = self.global_step
+            # data parallel: every rank draws its own dropout masks (seed = f(step, rank)), like independent replicas
+            seed = self.global_step * self.world + self.rank
         t = self.global_step + 1
         lr_t = self._lr_t(lr, t)
         key = (tuple(images.shape), float(keep_prob), float(l2_rate))
@@ -559,6 +610,7 @@ class Engine:
         return v[0] / float(N * H * W) + v[1]
 
     # ------------------------------------------------------------------ predictor / evaluation
+    @_on_device
     def predict(self, images, argmax=True):
         """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1."""
         N, H, W, _ = images.shape
@@ -572,6 +624,7 @@ class Engine:
             ops.softmax_xent(zp, softmax=out, pad=4, num_classes=self.C)
         return out
 
+    @_on_device
     def eval_step(self, images, labels, conf, l2_rate=0.0):
         """One metric update (fcn8s_tensorflow.py:685-689): forward at keep_prob 1, total_loss, argmax, confusion
         matrix accumulate (conf: int64 [C,C] device tensor, conf[label, prediction])."""

@@ -63,7 +63,11 @@ def check_images(images):
     if a.ndim != 4 or a.shape[-1] != 3:
         raise ValueError("images must have shape (batch, height, width, 3), got %s" % (a.shape,))
     if a.dtype != np.uint8:
-        a = np.clip(np.rint(a), 0, 255).astype(np.uint8)
+        q = np.clip(np.rint(a), 0, 255)
+        if not np.array_equal(q, a):
+            warnings.warn("image feed is not uint8-valued; it is rounded / clipped to 0..255 (the reference feeds raw "
+                          "8-bit images, fcn8s_tensorflow.py:558)", stacklevel=3)
+        a = q.astype(np.uint8)
     return a
 
 
@@ -123,7 +127,10 @@ def _load_npz_weights(path, num_classes=None):
 class FCN8s:
 
     def __init__(self, model_load_dir=None, tags=None, vgg16_dir=None, num_classes=None, variables_load_dir=None, *,
-                 precision="bf16", device=None, seed=2, weights=None, data_parallel=False):
+                 precision="fp32", device=None, seed=2, weights=None, data_parallel=False, backward_terms=3,
+                 grad_comm=None):
+        # precision: "fp32" (default, like the reference: the fp32-equivalent mode that meets the 1e-4 logit contract)
+        # or the opt-in reduced-precision "bf16" (BASELINE configs[2]); see engine.Engine.
         # fcn8s_tensorflow.py:40-41
         if (weights is None) and (model_load_dir is None) and (vgg16_dir is None or num_classes is None):
             raise ValueError("You must provide either both `model_load_dir` and `tags` or both `vgg16_dir` and `num_classes`.")
@@ -161,7 +168,8 @@ class FCN8s:
                 if k.startswith("conv") or k.startswith("fc6") or k.startswith("fc7/"):
                     weights[k] = enc[k]
 
-        self.engine = Engine(num_classes, precision=precision, device=device)
+        self.engine = Engine(num_classes, precision=precision, device=device, backward_terms=backward_terms,
+                             grad_comm=grad_comm)
         self.engine.load_weights(weights)
         if data_parallel:
             from . import dist as _dist
@@ -171,6 +179,8 @@ class FCN8s:
             self._restore_optimizer(adam_state)
         if variables_load_dir is not None and model_load_dir is None:
             self.load_variables(variables_load_dir)
+        if data_parallel:    # the optimiser state / global step restored above must also be identical on every rank
+            _dist.broadcast_parameters(self.engine)
         self._conf = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=self.engine.device)
         self._metric_set = set()
         self._stage = {}
@@ -322,25 +332,27 @@ class FCN8s:
                 self.training_loss = float(np.mean(np.array(loss_history)))
                 tr.set_postfix(ordered_dict={'loss': self.training_loss, 'learning rate': p[2]})
 
-            for train_step in tr:
-                x, y = feeder.get()
-                self.engine.train_step(x, y, learning_rate, keep_prob, l2_regularization)
-                feeder.release()
-                token = self._loss_read_begin(x.shape)
-                self.g_step = self.engine.global_step
-                self.variables_updated = True
-                if training_writer is not None and (self.g_step - 1) % summaries_frequency == 0:
-                    # variable summaries of _build_summary_ops (:331-350), reduced on the device (summaries.py)
-                    e = self.engine
-                    write_variable_summaries(training_writer, {n: e.view(n, e.params) for n, _ in SUMMARY_VARIABLES},
-                                             self.g_step)
+            try:
+                for train_step in tr:
+                    x, y = feeder.get()
+                    self.engine.train_step(x, y, learning_rate, keep_prob, l2_regularization)
+                    feeder.release()
+                    token = self._loss_read_begin(x.shape)
+                    self.g_step = self.engine.global_step
+                    self.variables_updated = True
+                    if training_writer is not None and (self.g_step - 1) % summaries_frequency == 0:
+                        # variable summaries of _build_summary_ops (:331-350), reduced on the device (summaries.py)
+                        e = self.engine
+                        write_variable_summaries(training_writer,
+                                                 {n: e.view(n, e.params) for n, _ in SUMMARY_VARIABLES}, self.g_step)
+                    if pending is not None:
+                        account(pending)
+                    pending = (token, self.g_step, learning_rate)
+                    learning_rate = learning_rate_schedule(self.g_step)
                 if pending is not None:
                     account(pending)
-                pending = (token, self.g_step, learning_rate)
-                learning_rate = learning_rate_schedule(self.g_step)
-            if pending is not None:
-                account(pending)
-            feeder.close()
+            finally:
+                feeder.close()     # stops and joins the prefetch thread also when the loop raises
 
             if (len(metrics) > 0) and (epoch % eval_frequency == 0):
                 if eval_dataset == 'train':
@@ -408,19 +420,28 @@ class FCN8s:
         from .feed import Feeder
         feeder = Feeder(self, data_generator, num_batches)
         pending = None
-        for step in tr:
-            x, y = feeder.get()
-            self.engine.eval_step(x, y, self._conf, l2_regularization)
-            feeder.release()
-            if 'loss' in self.metric_names:       # tf.metrics.mean over per-batch total_loss, :284 (read one step late)
-                token = self._loss_read_begin(x.shape)
-                if pending is not None:
-                    loss_sum += self._loss_read_end(pending)
-                pending = token
-                loss_count += 1
-        if pending is not None:
-            loss_sum += self._loss_read_end(pending)
-        feeder.close()
+        try:
+            for step in tr:
+                x, y = feeder.get()
+                self.engine.eval_step(x, y, self._conf, l2_regularization)
+                feeder.release()
+                if 'loss' in self.metric_names:   # tf.metrics.mean over per-batch total_loss, :284 (read one step late)
+                    token = self._loss_read_begin(x.shape)
+                    if pending is not None:
+                        loss_sum += self._loss_read_end(pending)
+                    pending = token
+                    loss_count += 1
+            if pending is not None:
+                loss_sum += self._loss_read_end(pending)
+        finally:
+            feeder.close()
+        if self.engine.world > 1:
+            # data parallel: every rank evaluated its own shard; the metrics (and every save-best decision taken from
+            # them) are those of the whole evaluation set on every rank
+            from . import dist as _dist
+            pair = torch.tensor([loss_sum, float(loss_count)], dtype=torch.float64, device=self.engine.device)
+            _dist.all_reduce_metrics(pair, self._conf)
+            loss_sum, loss_count = float(pair[0]), int(round(float(pair[1])))
         cm = self._conf.cpu().numpy()
         self.metric_values = self._metric_values_from(loss_sum, loss_count, cm)
         evaluation_results_string = ''
@@ -503,8 +524,10 @@ class FCN8s:
             arrays[n + "/Adam"] = e.view(n, e.adam_m).cpu().numpy()
             arrays[n + "/Adam_1"] = e.view(n, e.adam_v).cpu().numpy()
         arrays["optimizer/global_step"] = np.asarray(e.global_step, np.int32)       # tf.Variable(0) at :246
-        arrays["optimizer/beta1_power"] = np.asarray(0.9 ** e.global_step, np.float32)
-        arrays["optimizer/beta2_power"] = np.asarray(0.999 ** e.global_step, np.float32)
+        # tf.train.AdamOptimizer keeps beta^(t+1) in these accumulators after t steps (initialised to beta, multiplied
+        # after every step), so a restore in TensorFlow continues with the right bias correction
+        arrays["optimizer/beta1_power"] = np.asarray(0.9 ** (e.global_step + 1), np.float32)
+        arrays["optimizer/beta2_power"] = np.asarray(0.999 ** (e.global_step + 1), np.float32)
         # The reference writes TensorFlow files: SavedModelBuilder puts the variables under variables/variables.*
         # (:922-925), tf.train.Saver under the prefix <dir>/variables plus a `checkpoint` state file (:926-934).  Both
         # are tensor bundles; tf_bundle.py writes them without TensorFlow (tf.train.load_checkpoint reads them).
@@ -524,6 +547,12 @@ class FCN8s:
             if key in data:
                 e.global_step = int(data[key])
                 break
+        if "optimizer/beta1_power" in data:
+            want = 0.9 ** (e.global_step + 1)
+            got = float(np.asarray(data["optimizer/beta1_power"]))
+            if abs(got - want) > 1e-3 * want:
+                warnings.warn("optimizer/beta1_power = %g does not match global_step %d (expected %g); the engine "
+                              "derives the Adam bias correction from global_step" % (got, e.global_step, want))
         for n in e.layout:
             if n + "/Adam" in data:
                 e.view(n, e.adam_m).copy_(torch.from_numpy(np.asarray(data[n + "/Adam"])).to(e.device))

@@ -54,6 +54,14 @@ class Feeder:
             cache["stream"] = torch.cuda.Stream(device=self.device)
             cache["slots"] = [_Slot() for _ in range(depth)]
         self.copy_stream = cache["stream"]
+        prev = cache.get("feeder")
+        if prev is not None and prev.thread.is_alive():
+            # an earlier Feeder's thread is still staging (its loop raised, or close() timed out): it may hold the
+            # cached slots, so this one gets fresh ones instead of sharing pinned / device buffers with it
+            prev.stop.set()
+            cache["slots"] = [_Slot() for _ in range(depth)]
+        cache["feeder"] = self
+        self.stop = threading.Event()
         self.free = queue.Queue()
         for slot in cache["slots"]:
             self.free.put(slot)
@@ -69,6 +77,11 @@ class Feeder:
         pin = slot.pin.get(key)
         if pin is None or tuple(pin.shape) != a.shape:
             pin = slot.pin[key] = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype).pin_memory()
+            old = slot.dev.get(key)
+            if old is not None:     # last used on the compute stream: the allocator must not recycle it before that
+                old.record_stream(torch.cuda.current_stream(self.device))
+                if slot.consumed is not None:
+                    slot.consumed.synchronize()
             slot.dev[key] = torch.empty(a.shape, dtype=pin.dtype, device=self.device)
         _parallel_copy(pin.numpy(), a)
         slot.dev[key].copy_(pin, non_blocking=True)
@@ -78,10 +91,14 @@ class Feeder:
         try:
             torch.cuda.set_device(self.device)
             for _ in range(self.count):
+                if self.stop.is_set():
+                    return
                 images, labels = next(self.generator)
                 images = self.model._check_images(images)
                 labels = self.model._check_labels(labels)
                 slot = self.free.get()
+                if self.stop.is_set():
+                    return
                 slot.copied.synchronize()            # the pinned buffers are free once their last H2D has finished
                 with torch.cuda.stream(self.copy_stream):
                     if slot.consumed is not None:     # the device buffers are free once their last step was enqueued
@@ -113,4 +130,7 @@ class Feeder:
         self.free.put(slot)
 
     def close(self):
+        """Stop the prefetch thread (it exits before pulling another batch) and wait for it."""
+        self.stop.set()
+        self.free.put(_Slot())          # wakes a thread blocked on an empty free queue
         self.thread.join(timeout=30)

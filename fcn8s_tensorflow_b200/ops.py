@@ -139,11 +139,13 @@ def split_tf32(x):
 
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
-              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None, seed_ptr=None, algo=0):
+              seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None,
+              seed_ptr=None, algo=0, nseg=3):
     """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
     pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
-    the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF
-    weight tensor itself (fprop / dgrad), no packing."""
+    the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo); nseg = 2 / 1 keep only the first two / one of those
+    products (the measured reduced-backward modes).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF weight tensor
+    itself (fprop / dgrad), no packing."""
     _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo, colsum)
     if colsum is not None:
         flags |= EPI_COLSUM
@@ -154,7 +156,7 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
         if out is None:
             out = torch.empty((N, H, W, 2 * cout), dtype=torch.bfloat16, device=x.device)
         p = capi.ConvParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
-                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, 3, flags,
+                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
                             mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
                             capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum),
                             capi.ptr(seed_ptr), algo)
@@ -177,7 +179,8 @@ def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=No
     return out
 
 
-def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0, pair=False):
+def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0, pair=False,
+               nseg=3):
     """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows).
     pair=True: x / dy are bf16 hi/lo pair tensors [N,H,W,2C]; error-compensated product."""
     _chk_cuda(x, dy, out, x_lo, dy_lo)
@@ -187,7 +190,7 @@ def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_spl
         cin //= 2
         cout //= 2
         p = capi.WgradParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(dy), capi.ptr(dy, cout), capi.ptr(out), N, H, W,
-                             cin, cout, ksize, rows_valid, BF16, 3, force_splits, force_bn, 2 * cin, 2 * cout)
+                             cin, cout, ksize, rows_valid, BF16, nseg, force_splits, force_bn, 2 * cin, 2 * cout)
     else:
         nseg = 3 if x_lo is not None else 1
         p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin,
@@ -310,7 +313,13 @@ def softmax_xent(logits, labels=None, loss_sum=None, dlogits=None, softmax=None,
     p = capi.SoftmaxParams(capi.ptr(logits), capi.ptr(labels), capi.ptr(loss_sum), capi.ptr(dlogits),
                            capi.ptr(dbias), capi.ptr(softmax), capi.ptr(argmax), N, Hp - 2 * pad, Wp - 2 * pad, Cc,
                            CP, pad, grad_scale)
+    e0 = TIMER.start() if TIMER is not None else None
     capi.check(capi.load().fcn8_softmax_xent(C.byref(p), _stream()))
+    if e0 is not None:   # HBM-bound: the "work" recorded is algorithmic bytes, not FLOPs
+        px = N * (Hp - 2 * pad) * (Wp - 2 * pad)
+        nbytes = px * Cc * 4 + (px * Cc if labels is not None else 0) + (px * Cc * 4 if dlogits is not None else 0) + \
+            (px * Cc * 4 if softmax is not None else 0) + (px * 8 if argmax is not None else 0)
+        TIMER.stop("predictor" if dlogits is None else "loss", float(nbytes), e0)
 
 
 def upscore_tc_cp(num_classes, stride):
@@ -387,7 +396,8 @@ def upscore_tc_fwd(x, packed, num_classes, stride, out, x_lo=None):
     capi.check(capi.load().fcn8_upscore_tc_fwd(C.byref(p), _stream()))
     if e0 is not None:
         N, h, w, _ = x.shape
-        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+        TIMER.stop("upscore8" if stride == 8 else "upscore_tc",
+                   2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
     return out
 
 
@@ -426,13 +436,22 @@ def confusion_matrix(pred, labels_onehot, conf):
                                                  pred.numel(), Cc, _stream()))
 
 
-def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w_hi=None, w_lo=None, lr_ptr=None):
+def adam(p, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, w_hi=None, w_lo=None, lr_ptr=None,
+         g_bf16=None):
     """TF-form Adam over a flat buffer; w_hi / w_lo (bf16, same length): tensor-core shadow refreshed in the pass.
-    lr_ptr: device fp32 scalar overriding lr_t (see set_step_scalars)."""
-    _chk_cuda(p, g, m, v, w_hi, w_lo, lr_ptr)
+    lr_ptr: device fp32 scalar overriding lr_t (see set_step_scalars).  g_bf16: the gradient as a bf16 buffer (what a
+    bf16 all-reduce leaves), read instead of g."""
+    _chk_cuda(p, g, m, v, w_hi, w_lo, lr_ptr, g_bf16)
     capi.check(capi.load().fcn8_adam(capi.ptr(p), capi.ptr(g), capi.ptr(m), capi.ptr(v), p.numel(), lr_t, beta1,
                                      beta2, eps, grad_scale, capi.ptr(w_hi), capi.ptr(w_lo), capi.ptr(lr_ptr),
-                                     _stream()))
+                                     capi.ptr(g_bf16), _stream()))
+
+
+def cast_bf16(x, out):
+    """out (bf16, same length) = bf16(x) for a flat fp32 buffer (wire format of the bf16 gradient all-reduce)."""
+    _chk_cuda(x, out)
+    capi.check(capi.load().fcn8_cast_bf16(capi.ptr(x), capi.ptr(out), x.numel(), _stream()))
+    return out
 
 
 def set_step_scalars(scalars, lr_t, seed):

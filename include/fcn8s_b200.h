@@ -99,7 +99,9 @@ int32_t fcn8_preprocess_im2col(const Fcn8PreprocessParams* p, void* stream);
  * out[N,H,W,Cout] = epilogue( sum_{kh,kw,ci} x[N, y+kh-pad, x+kw-pad, ci] * wp[co][(kh*k+kw)*Cin + ci] ).
  * fprop: wp from fcn8_pack_weights(mode 0), flags BIAS|RELU(|DROPOUT).  dgrad (autodiff of the same op, :257):
  * x = dY, wp from fcn8_pack_weights(mode 1), flags MASK (ReLU/dropout backward against `mask_src`) and/or RESIDUAL.
- * nseg == 3 (FCN8_F32 only): x_lo / wp_lo are the low halves of the tf32 split (fcn8_split_tf32). */
+ * nseg == 3: x_lo / wp_lo are the low halves of the operands (tf32 split: fcn8_split_tf32; bf16 pairs: the lo planes);
+ * nseg == 2 forms only x*w + x*w_lo (x rounded to its high half, weights exact), nseg == 1 only x*w -- the reduced
+ * products of the measured "fp32 forward / 2- or 1-term backward" modes (Engine(backward_terms=...)). */
 typedef struct {
   const void* x;
   const void* x_lo;
@@ -321,7 +323,12 @@ int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot,
  * g' = g*grad_scale;  m = b1*m + (1-b1)*g';  v = b2*v + (1-b2)*g'^2;  p -= lr_t * m / (sqrt(v) + eps),
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller. */
 int32_t fcn8_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, void* stream);
+                  float eps, float grad_scale, void* w_hi, void* w_lo, const float* lr_ptr, const void* g_bf16,
+                  void* stream);
+/* Data-parallel option (new functionality, the reference has no collective): the flat gradient goes over NVLink as
+ * bf16 (half the bytes of the one all-reduce per step).  fcn8_cast_bf16 writes out = bf16(x); fcn8_adam then reads the
+ * reduced gradient from g_bf16 (bf16 [n]) instead of g (which may be NULL). */
+int32_t fcn8_cast_bf16(const float* x, void* out, size_t n, void* stream);
 /* Per-step scalars in device memory so that a captured CUDA graph of the whole training step can be replayed with a
  * new learning rate and dropout seed (the reference feeds both every step, fcn8s_tensorflow.py:558-562):
  * scalars[0] = lr_t (read by fcn8_adam through lr_ptr), scalars[1] = seed bits (read through Fcn8ConvParams.seed_ptr). */

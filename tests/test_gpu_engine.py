@@ -252,6 +252,126 @@ def test_full_size_logits_and_loss_parity(cuda_device):
     assert rel(both[0], one[0]) <= 5e-5
 
 
+def _distribution_case(name, Cc, Hh, Ww):
+    """(weights, image) of the extra input / weight distributions the accumulator's round-toward-zero compensation
+    (ConvGemmArgs::acc_scale, measured on He-normal weights and uniform-random images) has to hold on."""
+    rng = np.random.default_rng(21)
+    if name == "reference_init":
+        # the reference's own decoder initialisers, sigma 1e-3 / 1e-2 (fcn8s_tensorflow.py:159-160): logits ~1e-3
+        return oracle.init_weights(Cc, seed=4, decoder_std_scale=1.0), rng.integers(0, 256, (1, Hh, Ww, 3), dtype=np.uint8)
+    if name == "sparse_image":
+        # a black image with 2 % lit pixels: after the mean subtraction almost every conv1_1 window is the same
+        # constant, i.e. long runs of identical same-sign products
+        img = np.zeros((1, Hh, Ww, 3), np.uint8)
+        lit = rng.random((1, Hh, Ww)) < 0.02
+        img[lit] = rng.integers(1, 256, (int(lit.sum()), 3), dtype=np.uint8)
+        return oracle.init_weights(Cc, seed=5, decoder_std_scale=10.0), img
+    if name == "positive_weights":
+        # all-positive encoder weights (mean 1/fan_in, so that activations neither explode nor die) and positive
+        # biases: every partial sum of every accumulator grows monotonically -- the worst case for a truncating add
+        w = oracle.init_weights(Cc, seed=6, decoder_std_scale=10.0)
+        for k, v in w.items():
+            enc = k.startswith("conv") or k.startswith("fc6") or k.startswith("fc7/")
+            if enc and v.dim() == 4:
+                fan_in = v.shape[0] * v.shape[1] * v.shape[2]
+                w[k] = (v.abs() * (np.sqrt(np.pi / 2.0) / np.sqrt(2.0 / fan_in) / fan_in)).float()
+            elif enc:
+                w[k] = v.abs() + 0.5
+        return w, rng.integers(128, 256, (1, Hh, Ww, 3), dtype=np.uint8)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("case", ["reference_init", "sparse_image", "positive_weights"])
+def test_full_size_logits_on_other_distributions(cuda_device, case):
+    """The 1e-4 logit bar at the benchmark geometry (512x1024, 20 classes) on three more weight / input distributions
+    than the He-normal + uniform-random one the round-toward-zero compensation constant was measured on."""
+    Cc, Hh, Ww = 20, 512, 1024
+    w, img = _distribution_case(case, Cc, Hh, Ww)
+    with torch.no_grad():
+        ref = oracle.forward(w, img, dtype=torch.float64)
+    e = make_engine(cuda_device, "fp32", w, classes=Cc)
+    got = e.forward(torch.from_numpy(img).to(cuda_device))
+    torch.cuda.synchronize()
+    err = rel(got, ref)
+    print("full-size logits max-rel %.3e (%s), max|ref| %.3e" % (err, case, ref.abs().max().item()))
+    assert torch.isfinite(got).all()
+    assert err <= 1e-4, (case, err)
+
+
+def test_full_size_loss_and_every_gradient(cuda_device):
+    """BASELINE configs[1] geometry, one image (so that the fp64 CPU oracle's backward finishes in about a minute):
+    loss and all 42 gradients of the main-line precision against the fp64 CPU graph."""
+    Cc, Hh, Ww = 20, 512, 1024
+    w = oracle.init_weights(Cc, seed=2, decoder_std_scale=10.0)
+    images, labels = oracle.synthetic_batch(1, Hh, Ww, Cc, seed=9)
+    loss, logits, grads = oracle.loss_and_grads(w, images, labels, dtype=torch.float64)
+    e = make_engine(cuda_device, "fp32", w, classes=Cc)
+    x = torch.from_numpy(images).to(cuda_device)
+    y = torch.from_numpy(labels.view(np.uint8)).to(cuda_device)
+    e.loss_and_backward(x, y, keep_prob=1.0)
+    torch.cuda.synchronize()
+    assert rel(e._arena(1, Hh, Ww)["logits"], logits) <= 1e-4
+    assert abs(e.loss_value(x.shape) - float(loss)) <= 1e-4 * abs(float(loss))
+    got = e.grad_dict()
+    worst = ("", 0.0)
+    bad = []
+    for k, v in grads.items():
+        err = rel_l2(got[k], v)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+        if not err <= GRAD_TOL["fp32"]:
+            bad.append((k, err))
+    print("full-size gradients: worst rel-l2 %.3e (%s)" % (worst[1], worst[0]))
+    assert not bad, bad
+
+
+def test_adam_is_elementwise_exact_on_its_own_gradients(cuda_device, problem):
+    """The fused Adam kernel against the TF-form update evaluated in fp64 on the ENGINE'S OWN gradients (so the check
+    isolates the optimiser arithmetic from GEMM rounding): m, v per element to 1e-6 relative, the parameter update to
+    1e-5 of the learning rate, over two steps with different learning rates; the bf16 shadow equals bf16(params)."""
+    e = make_engine(cuda_device, "fp32", problem["weights"])
+    e.use_graphs = False
+    x = torch.from_numpy(problem["images"]).to(cuda_device)
+    y = torch.from_numpy(problem["labels"].view(np.uint8)).to(cuda_device)
+    p = e.params.double().clone()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for t, lr in ((1, 1e-4), (2, 3e-5)):
+        e.loss_and_backward(x, y, keep_prob=1.0)
+        g = e.grads.double().clone()
+        e.adam_step(lr)
+        torch.cuda.synchronize()
+        lr_t = lr * np.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        p = p - lr_t * m / (v.sqrt() + 1e-8)
+        assert (e.adam_m.double() - m).abs().max().item() <= 1e-6 * m.abs().max().item()
+        assert (e.adam_v.double() - v).abs().max().item() <= 1e-6 * v.abs().max().item()
+        assert (e.params.double() - p).abs().max().item() <= 1e-5 * lr + 1e-7 * p.abs().max().item()
+        p = e.params.double().clone()      # follow the engine's fp32 state; the update itself is what is checked
+        m, v = e.adam_m.double().clone(), e.adam_v.double().clone()
+    assert e.global_step == 2
+    assert torch.equal(e.w_hi, e.params.to(torch.bfloat16))
+    assert torch.equal(e.w_lo, (e.params - e.w_hi.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("terms,tol", [(2, 2e-2), (1, 1.5e-1)])
+def test_reduced_backward_modes_keep_the_forward_exact(cuda_device, problem, terms, tol):
+    """Engine(backward_terms=2 | 1): NON-default measured modes -- forward (logits, loss) stays the fp32-equivalent
+    3-product path, only dgrad / wgrad drop cross terms; gradients stay within `tol` (rel-L2) of the fp64 graph."""
+    from fcn8s_tensorflow_b200.engine import Engine
+    e = Engine(C, precision="fp32", device=cuda_device, backward_terms=terms)
+    e.load_weights(problem["weights"])
+    x = torch.from_numpy(problem["images"]).to(cuda_device)
+    y = torch.from_numpy(problem["labels"].view(np.uint8)).to(cuda_device)
+    e.loss_and_backward(x, y, keep_prob=1.0)
+    torch.cuda.synchronize()
+    assert rel(e._arena(N, H, W)["logits"], problem["logits"]) <= LOGIT_TOL["fp32"]
+    got = e.grad_dict()
+    errs = {k: rel_l2(got[k], v) for k, v in problem["grads"].items()}
+    print("backward_terms=%d: worst gradient rel-l2 %.3e" % (terms, max(errs.values())))
+    assert max(errs.values()) <= tol, sorted(errs.items(), key=lambda t: -t[1])[:3]
+
+
 def test_config4_full_resolution_inference_properties(cuda_device):
     """BASELINE configs[3]: predict on one 2048x1024 image, 20 classes (the fp64 oracle would need minutes at this size,
     so the checks are size-independent properties): output types / shapes of fcn8s_tensorflow.py:743-770, softmax rows

@@ -139,8 +139,13 @@ def _gloo_worker(rank, world, port, out):
     e.adam_m = torch.zeros(10)
     e.adam_v = torch.zeros(10)
     e.world, e.allreduce, e._packed_dirty = 1, None, False
+    e.global_step = 7 + rank          # restored from a checkpoint on rank 0 only: the broadcast makes it 7 everywhere
     fdist.attach(e)
     fdist.broadcast_parameters(e, src=0)
+    assert e.global_step == 7 and e.rank == rank
+    pair, conf = fdist.all_reduce_metrics(torch.tensor([1.5 * (rank + 1), 1.0], dtype=torch.float64),
+                                          torch.full((2, 2), rank + 1, dtype=torch.int64))
+    assert pair.tolist() == [4.5, 2.0] and conf.tolist() == [[3, 3], [3, 3]]
     g = torch.arange(10, dtype=torch.float32) * (rank + 1)
     e.allreduce.start(g[:6])       # the engine's two-chunk protocol: head under the backward pass, tail before Adam
     e.allreduce.start(g[6:])
@@ -248,6 +253,43 @@ def test_reference_batch_generators_feed_the_class_surface(tmp_path):
     assert images.dtype == np.uint8 and images.shape == (2, 64, 96, 3)
     assert labels.dtype == np.bool_ and labels.shape == (2, 64, 96, 2) and (labels.sum(-1) == 1).all()
     assert check_labels(labels, 2) is labels
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only mounted in the build container")
+def test_shipped_kitti_generator_equals_the_references_batch_for_batch(tmp_path):
+    """fcn8s_tensorflow_b200.generators.batch_generator (what bench.py --config c5 feeds from on the GPU box, where
+    /root/reference does not exist) against data_generator/batch_generator_KITTI.py:8-107 run through the scipy.misc
+    shim: same files, same shuffles (python `random`), same flips (numpy RNG), bit-identical batches over two passes,
+    including the short last batch and the bilinear label resize before the colour match."""
+    import random
+    from fcn8s_tensorflow_b200.compat import install_scipy_misc_shim
+    from fcn8s_tensorflow_b200 import generators
+    install_scipy_misc_shim()
+    sys.path.insert(0, REFERENCE)
+    try:
+        from data_generator.batch_generator_KITTI import batch_generator as ref_generator
+    finally:
+        sys.path.remove(REFERENCE)
+    root = str(tmp_path / "kitti")
+    idir, ldir = generators.write_synthetic_kitti_tree(root, 5, height=75, width=142, seed=3)
+    for flip in (False, 0.5):
+        random.seed(11)
+        np.random.seed(5)
+        ref = ref_generator(2, root, idir, ldir, image_size=(64, 128), flip=flip)
+        want = [next(ref) for _ in range(7)]
+        random.seed(11)
+        np.random.seed(5)
+        mine = generators.batch_generator(2, root, idir, ldir, image_size=(64, 128), flip=flip)
+        got = [next(mine) for _ in range(7)]
+        assert [len(b[0]) for b in got] == [2, 2, 1, 2, 2, 1, 2]
+        for (wi, wl), (gi, gl) in zip(want, got):
+            assert gi.dtype == np.uint8 and gl.dtype == np.bool_ and gl.shape[-1] == 2
+            assert np.array_equal(wi, gi) and np.array_equal(wl, gl)
+        assert any(gl[..., 1].any() for _, gl in got) and any(gl[..., 0].any() for _, gl in got)
+    # images only (labels_subdir=None) yields bare image batches, like the reference (:106-107)
+    random.seed(1)
+    only = next(generators.batch_generator(3, root, idir, None, image_size=(32, 64)))
+    assert isinstance(only, np.ndarray) and only.shape == (3, 32, 64, 3)
 
 
 def test_variable_summaries_match_tensorflow_buckets_and_reference_tags(tmp_path):
