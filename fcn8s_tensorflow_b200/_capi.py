@@ -10,20 +10,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfcn8s_sm100.so")
 
 BF16, F32, BF16X2 = 0, 1, 2
-EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32, EPI_COLSUM = 1, 2, 4, 8, 16, 64, 128
+EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL, EPI_ROUND_TF32, EPI_COLSUM, EPI_POOL = 1, 2, 4, 8, 16, 64, 128, 256
 
 EXPORTS = [
-    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_debug_buffer", "fcn8_crc32c", "fcn8_preprocess_im2col",
+    "fcn8_version", "fcn8_last_error", "fcn8_device_check", "fcn8_launch_count", "fcn8_debug_set", "fcn8_debug_buffer",
+    "fcn8_crc32c", "fcn8_preprocess_im2col",
     "fcn8_conv_gemm_workspace_bytes", "fcn8_conv_gemm", "fcn8_wgrad_gemm_workspace_bytes", "fcn8_wgrad_gemm",
     "fcn8_pack_weights", "fcn8_split_tf32", "fcn8_maxpool_fwd", "fcn8_maxpool_bwd", "fcn8_bias_grad_workspace_bytes",
-    "fcn8_bias_grad", "fcn8_score_head_fwd_workspace_bytes", "fcn8_score_head_fwd",
-    "fcn8_score_head_bwd_workspace_bytes", "fcn8_score_head_bwd",
-    "fcn8_upscore_fwd", "fcn8_upscore_bwd_workspace_bytes", "fcn8_upscore_bwd", "fcn8_softmax_xent",
-    "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg",
-    "fcn8_upscore_tc_cp", "fcn8_upscore_tc_pack", "fcn8_upscore_tc_fwd", "fcn8_upscore_tc_dx",
-    "fcn8_upscore_tc_dw_workspace_bytes", "fcn8_upscore_tc_dw", "fcn8_shadow_weights",
-    "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_upscore_tc_gather", "fcn8_upscore_tc_scatter",
-    "fcn8_cast_bf16",
+    "fcn8_bias_grad", "fcn8_head_pack", "fcn8_deconv_cp", "fcn8_deconv_pack", "fcn8_deconv_fwd", "fcn8_deconv_loss",
+    "fcn8_deconv_dx", "fcn8_deconv_dw_workspace_bytes", "fcn8_deconv_dw",
+    "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg", "fcn8_shadow_weights",
+    "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_cast_bf16",
 ]
 
 
@@ -44,7 +41,9 @@ class ConvParams(C.Structure):
                 ("mask_scale", C.c_float), ("keep_prob", C.c_float), ("seed", C.c_uint32),
                 ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32), ("out_ld", C.c_int32),
                 ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p), ("w_mode", C.c_int32), ("colsum", C.c_void_p),
-                ("seed_ptr", C.c_void_p), ("algo", C.c_int32)]
+                ("seed_ptr", C.c_void_p), ("algo", C.c_int32), ("out_scale", C.c_float), ("colsum_n", C.c_int32),
+                ("pool_out", C.c_void_p), ("pool_out_lo", C.c_void_p), ("pool_ld", C.c_int32),
+                ("x_sH", C.c_int64), ("x_sN", C.c_int64), ("out_sH", C.c_int64), ("out_sN", C.c_int64)]
 
 
 class WgradParams(C.Structure):
@@ -52,7 +51,8 @@ class WgradParams(C.Structure):
                 ("dw", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
                 ("Cout", C.c_int32), ("ksize", C.c_int32), ("rows_valid", C.c_int32), ("dtype", C.c_int32),
                 ("nseg", C.c_int32), ("force_splits", C.c_int32), ("force_bn", C.c_int32), ("x_ld", C.c_int32),
-                ("dy_ld", C.c_int32)]
+                ("dy_ld", C.c_int32), ("out_cols", C.c_int32), ("out_scale", C.c_float),
+                ("x_sH", C.c_int64), ("x_sN", C.c_int64), ("dy_sH", C.c_int64), ("dy_sN", C.c_int64)]
 
 
 class PackParams(C.Structure):
@@ -70,36 +70,17 @@ class BiasGradParams(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("db", C.c_void_p), ("P", C.c_int64), ("C", C.c_int32), ("dtype", C.c_int32)]
 
 
-class HeadParams(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("K", C.c_void_p), ("b", C.c_void_p), ("s", C.c_void_p), ("dK", C.c_void_p),
-                ("db", C.c_void_p), ("dx", C.c_void_p), ("P", C.c_int64), ("Cin", C.c_int32), ("C", C.c_int32),
-                ("scale", C.c_float), ("dtype", C.c_int32), ("mask", C.c_int32), ("mask_scale", C.c_float)]
-
-
-class UpscoreParams(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("T", C.c_void_p), ("bias", C.c_void_p), ("skip", C.c_void_p), ("y", C.c_void_p),
-                ("dx", C.c_void_p), ("dT", C.c_void_p), ("dbias", C.c_void_p), ("N", C.c_int32), ("h", C.c_int32),
-                ("w", C.c_int32), ("C", C.c_int32), ("stride", C.c_int32)]
-
-
-class SoftmaxParams(C.Structure):
-    _fields_ = [("logits", C.c_void_p), ("labels", C.c_void_p), ("loss_sum", C.c_void_p), ("dlogits", C.c_void_p),
-                ("dbias", C.c_void_p), ("softmax", C.c_void_p), ("argmax", C.c_void_p), ("N", C.c_int32),
-                ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("CP", C.c_int32), ("pad", C.c_int32),
-                ("grad_scale", C.c_float)]
-
-
-class UpscorePackParams(C.Structure):
-    _fields_ = [("T", C.c_void_p), ("bias", C.c_void_p), ("w_fwd", C.c_void_p), ("w_fwd_lo", C.c_void_p),
-                ("w_dx", C.c_void_p), ("w_dx_lo", C.c_void_p), ("bias_big", C.c_void_p), ("C", C.c_int32),
-                ("stride", C.c_int32)]
-
-
-class UpscoreTcParams(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("w", C.c_void_p), ("w_lo", C.c_void_p),
-                ("bias_big", C.c_void_p), ("zp", C.c_void_p), ("zp_lo", C.c_void_p), ("dx", C.c_void_p),
-                ("dT", C.c_void_p), ("N", C.c_int32), ("h", C.c_int32), ("wd", C.c_int32), ("C", C.c_int32),
-                ("stride", C.c_int32), ("ldx", C.c_int32), ("nseg", C.c_int32)]
+class DeconvParams(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("x_ld", C.c_int32), ("x_sH", C.c_int64), ("x_sN", C.c_int64),
+                ("w", C.c_void_p), ("w_lo", C.c_void_p), ("bias_big", C.c_void_p),
+                ("out", C.c_void_p), ("out_lo", C.c_void_p), ("out_ld", C.c_int32), ("out_sH", C.c_int64),
+                ("out_sN", C.c_int64), ("skip", C.c_void_p), ("skip_lo", C.c_void_p),
+                ("dz", C.c_void_p), ("dz_lo", C.c_void_p), ("dT", C.c_void_p), ("colsum", C.c_void_p),
+                ("colsum_n", C.c_int32), ("N", C.c_int32), ("h", C.c_int32), ("wd", C.c_int32), ("C", C.c_int32),
+                ("stride", C.c_int32), ("nseg", C.c_int32),
+                ("labels", C.c_void_p), ("loss_sum", C.c_void_p), ("dbias", C.c_void_p), ("dz_hi_out", C.c_void_p),
+                ("dz_lo_out", C.c_void_p), ("logits", C.c_void_p), ("softmax", C.c_void_p), ("argmax", C.c_void_p),
+                ("conf", C.c_void_p), ("grad_scale", C.c_float)]
 
 
 _lib = None
@@ -128,25 +109,22 @@ def load():
         lib.fcn8_debug_set(int(k), int(v))
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
-                     ("fcn8_score_head_fwd", HeadParams), ("fcn8_score_head_bwd", HeadParams),
-                     ("fcn8_upscore_bwd", UpscoreParams),
-                     ("fcn8_upscore_tc_dw", UpscoreTcParams)]:
+                     ("fcn8_deconv_dw", DeconvParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp, sz, vp]
         getattr(lib, name).restype = C.c_int32
         getattr(lib, name + "_workspace_bytes").argtypes = [C.POINTER(pt)]
         getattr(lib, name + "_workspace_bytes").restype = sz
     for name, pt in [("fcn8_preprocess_im2col", PreprocessParams), ("fcn8_pack_weights", PackParams),
                      ("fcn8_maxpool_fwd", PoolParams), ("fcn8_maxpool_bwd", PoolParams),
-                     ("fcn8_upscore_fwd", UpscoreParams),
-                     ("fcn8_softmax_xent", SoftmaxParams), ("fcn8_upscore_tc_pack", UpscorePackParams),
-                     ("fcn8_upscore_tc_fwd", UpscoreTcParams), ("fcn8_upscore_tc_dx", UpscoreTcParams)]:
+                     ("fcn8_deconv_fwd", DeconvParams), ("fcn8_deconv_loss", DeconvParams),
+                     ("fcn8_deconv_dx", DeconvParams)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp]
         getattr(lib, name).restype = C.c_int32
     i32 = C.c_int32
-    lib.fcn8_upscore_tc_gather.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
-    lib.fcn8_upscore_tc_scatter.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
-    lib.fcn8_upscore_tc_cp.argtypes = [C.c_int32, C.c_int32]
-    lib.fcn8_upscore_tc_cp.restype = C.c_int32
+    lib.fcn8_deconv_cp.argtypes = [i32]
+    lib.fcn8_deconv_cp.restype = i32
+    lib.fcn8_deconv_pack.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.fcn8_head_pack.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     lib.fcn8_split_tf32.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_confusion_matrix.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,

@@ -59,13 +59,15 @@ EncodeTiledFn get_encode() {
 
 // NHWC activation map: dims (C, W, H, N), box (CH, bw, bh, bn), 128B swizzle, OOB -> 0 (= SAME zero padding).
 int encode_act_map(CUtensorMap* m, const void* ptr, int dtype, int N, int H, int W, int C, int bw, int bh, int bn,
-                   bool atom32 = false, int ld = 0) {
+                   bool atom32 = false, int ld = 0, long long sH = 0, long long sN = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int es = dtype == FCN8_BF16 ? 2 : 4;
   if (ld <= 0) ld = C;
+  if (sH <= 0) sH = (long long)W * ld;     // row / image strides in elements (strided views: see Fcn8ConvParams)
+  if (sN <= 0) sN = (long long)H * sH;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es};
+  const cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)sH * es, (cuuint64_t)sN * es};
   const cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dtype == FCN8_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
@@ -139,6 +141,9 @@ int cur_dev() {
   cudaGetDevice(&dev);
   return dev & 63;
 }
+// expected relative loss per tcgen05.mma of a round-toward-zero TMEM accumulation at full magnitude (see
+// ConvGemmArgs::rz_c); fcn8_debug_set(7, v) overrides it with v * 1e-10 for calibration runs, (0, 1) switches it off
+float rz_per_mma();
 int g_sm_limit = 0;  // fcn8_set_sm_limit: persistent GEMM grids leave SMs free for a co-running collective
 int num_sms() {
   static int n = 0;
@@ -149,6 +154,11 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
+
+float rz_per_mma() {
+  if (g_debug[0]) return 0.f;
+  return g_debug[7] > 0 ? (float)g_debug[7] * 1e-10f : kRzBiasPerMma;
 }
 
 struct ConvPlan {
@@ -169,6 +179,11 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   if (p->w_mode < 0 || p->w_mode > 2) return fail(FCN8_ERR_BAD_SHAPE, "conv: w_mode must be 0, 1 or 2");
   if (p->w_mode == 2 && p->Cout % 64) return fail(FCN8_ERR_BAD_SHAPE, "conv: dgrad w_mode needs Cout %% 64 == 0");
   choose_patch(p->N, p->H, p->W, 7, &pl->lbw, &pl->lbh, &pl->lbn);
+  if (p->flags & FCN8_EPI_POOL) {   // 8 x 16 pixel tiles: a 2x2 pooling window is four lanes of one epilogue warp
+    pl->lbw = 3;
+    pl->lbh = 4;
+    pl->lbn = 0;
+  }
   pl->tiles_x = (p->W + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->tiles_y = (p->H + (1 << pl->lbh) - 1) >> pl->lbh;
   pl->tiles_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
@@ -197,8 +212,8 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   pl->tiles_n = p->Cout / bn;
   const long long tiles = (long long)pl->m_tiles * pl->tiles_n;
   int splits = 1;
-  if (p->flags & FCN8_EPI_COLSUM) {
-    splits = 1;  // the fused column sums live in the GEMM kernel's epilogue, not in the split-K reduce
+  if (p->flags & (FCN8_EPI_COLSUM | FCN8_EPI_POOL)) {
+    splits = 1;  // the fused column sums / pooling live in the GEMM kernel's epilogue, not in the split-K reduce
   } else if (p->force_splits > 0) {
     splits = p->force_splits;
   } else if (tiles * 2 <= sms) {
@@ -501,7 +516,13 @@ size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p) {
 }
 
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!p || !p->x || !p->wp || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "conv: null pointer");
+  if (!p || !p->x || !p->wp || (!p->out && !((p->flags & FCN8_EPI_POOL) && p->pool_out)))
+    return fail(FCN8_ERR_BAD_SHAPE, "conv: null pointer");
+  if (p->flags & FCN8_EPI_POOL) {
+    if (p->dtype != FCN8_BF16 || !p->pool_out || (p->H & 1) || (p->W & 1) || !aligned16(p->pool_out) ||
+        (p->pool_out_lo && !aligned16(p->pool_out_lo)))
+      return fail(FCN8_ERR_BAD_SHAPE, "conv: POOL needs bf16 operands, pool_out (16-byte aligned) and even H, W");
+  }
   if (!aligned16(p->x) || !aligned16(p->wp) || !aligned16(p->out) || (p->bias && !aligned16(p->bias)) ||
       (p->mask_src && !aligned16(p->mask_src)) || (p->residual && !aligned16(p->residual)))
     return fail(FCN8_ERR_BAD_ALIGN, "conv: pointers must be 16-byte aligned");
@@ -541,15 +562,22 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
   const int ktot = p->ksize * p->ksize * p->Cin;
-  const void* xs[3] = {p->x, p->x, p->x_lo};
-  const void* ws[3] = {p->wp, p->wp_lo, p->wp};
+  // segment order: the low-order products first, hi*hi last (ConvGemmArgs::rz_c)
+  const void* xs[3] = {p->x, p->x_lo, p->x};
+  const void* ws[3] = {p->wp_lo, p->wp, p->wp};
+  if (p->nseg == 2) {
+    xs[1] = p->x;
+  } else if (p->nseg == 1) {
+    ws[0] = p->wp;
+  }
   const int taps = p->ksize * p->ksize;
   for (int s = 0; s < p->nseg; ++s) {
     if (use_halo)
-      rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 16, 18, 1, false, p->x_ld);
+      rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 16, 18, 1, false, p->x_ld, p->x_sH,
+                          p->x_sN);
     else
       rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh,
-                          1 << pl.lbn, false, p->x_ld);
+                          1 << pl.lbn, false, p->x_ld, p->x_sH, p->x_sN);
     if (rc) return rc;
     if (p->w_mode == 0)
       rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, b_rows);
@@ -585,20 +613,27 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   a.tiles_n = pl.tiles_n;
   a.splits = pl.splits;
   a.kb_per_split = pl.kb_per_split;
-  a.flags = p->flags & (31 | 64 | 128);
+  a.flags = p->flags & (31 | 64 | 128 | 256);
   if (g_debug[3] & 1) a.flags |= EPI_DBG_NOSTORE;
   if (g_debug[3] & 2) a.flags |= EPI_DBG_NOLOAD;
   a.colsum = p->colsum;
+  a.colsum_n = p->colsum_n;
   a.seed_ptr = p->seed_ptr;
-  {
-    // MMAs accumulated into one TMEM accumulator: 4 per k-block of 128 operand bytes
-    const int kb_acc = use_halo ? p->nseg * 9 * (p->Cin / 64) : pl.kb_per_split;
-    a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)kb_acc * kRzBiasPerMma;
-  }
+  a.acc_scale = p->out_scale != 0.f ? p->out_scale : 1.f;
+  a.rz_c = 4.f * rz_per_mma();   // per k-block of 128 operand bytes = 4 MMAs
+  if (use_halo) a.kb_per_split = pl.total_kb;   // a halo tile accumulates every segment
   const int out_ld = p->out_ld > 0 ? p->out_ld : p->Cout;
   a.osW = out_ld;
-  a.osH = (long long)p->W * out_ld;
-  a.osN = (long long)p->H * p->W * out_ld;
+  a.osH = p->out_sH > 0 ? p->out_sH : (long long)p->W * out_ld;
+  a.osN = p->out_sN > 0 ? p->out_sN : (long long)p->H * a.osH;
+  if (p->flags & FCN8_EPI_POOL) {
+    const int pld = p->pool_ld > 0 ? p->pool_ld : out_ld;
+    a.pool_out = p->pool_out;
+    a.pool_out_lo = p->pool_out_lo;
+    a.psW = pld;
+    a.psH = (long long)(p->W / 2) * pld;
+    a.psN = (long long)(p->H / 2) * a.psH;
+  }
   a.b_mode = p->w_mode == 1 ? 2 : (p->w_mode == 2 ? 1 : 0);
   a.out_lo = p->out_lo;
   a.residual_lo = p->residual_lo;
@@ -657,7 +692,11 @@ namespace {
 // wgrad_halo_kernel: 3x3, 64 input channels, bf16 operands (conv1_2, conv2_1)
 bool wgrad_use_halo(const Fcn8WgradParams* p) {
   return p->dtype == FCN8_BF16 && p->ksize == 3 && p->Cin == 64 && p->Cout % 64 == 0 && p->rows_valid <= 0 &&
-         p->force_splits <= 0 && p->force_bn <= 0 && !g_debug[1];
+         p->force_splits <= 0 && p->force_bn <= 0 && !g_debug[1] && p->out_cols <= 0 && p->x_sH <= 0 && p->dy_sH <= 0;
+}
+// score heads: the class dimension is padded to 64 columns, only the first out_cols go to dw [rows][out_cols]
+bool wgrad_clip(const Fcn8WgradParams* p) {
+  return (p->out_cols > 0 && p->out_cols < p->Cout) || (p->out_scale != 0.f && p->out_scale != 1.f);
 }
 struct WgradHaloPlan {
   int tiles_x, tiles_y, total_patches, tiles_n, splits, patches_per_split;
@@ -683,7 +722,7 @@ size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p) {
   }
   WgradPlan pl;
   if (plan_wgrad(p, &pl)) return 0;
-  return pl.splits > 1 ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
+  return (pl.splits > 1 || wgrad_clip(p)) ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
 }
 
 int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t workspace_bytes, void* stream) {
@@ -702,8 +741,10 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
       return fail(FCN8_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu", workspace_bytes, hneed);
     TensorMaps3 hm;
     memset(&hm, 0, sizeof(hm));
-    const void* hxs[3] = {p->x, p->x, p->x_lo};
-    const void* hds[3] = {p->dy, p->dy_lo, p->dy};
+    const void* hxs[3] = {p->x, p->x_lo, p->x};      // low-order products first (ConvGemmArgs::rz_c)
+    const void* hds[3] = {p->dy_lo, p->dy, p->dy};
+    if (p->nseg == 2) hxs[1] = p->x;
+    if (p->nseg == 1) hds[0] = p->dy;
     for (int s = 0; s < p->nseg; ++s) {
       int hrc = encode_act_map(&hm.a[s], hxs[s], FCN8_BF16, p->N, p->H, p->W, 64, 16, 18, 1, false, p->x_ld);
       if (hrc) return hrc;
@@ -724,7 +765,7 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     ha.patches_per_split = hp.patches_per_split;
     ha.splits = hp.splits;
     ha.tiles_n = hp.tiles_n;
-    ha.acc_scale = g_debug[0] ? 1.f : 1.f + 8.f * (float)(p->nseg * hp.patches_per_split) * kRzBiasPerMma;
+    ha.acc_scale = 1.f + 8.f * (float)hp.patches_per_split * rz_per_mma();   // the hi*hi segment's MMAs
     static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[cur_dev()];
     if (!attr_done) {
@@ -737,13 +778,15 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     (void)launch_k(wgrad_halo_kernel<64>, dim3(hp.tiles_n * hp.splits), dim3(kGemmThreads), WgradHaloCfg::kSmemBytes, hst, hm, ha);
     cudaError_t he = cudaGetLastError();
     if (he != cudaSuccess) return cuda_fail(he, "wgrad_halo launch");
-    he = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, hp.splits, 640, 576, p->Cout, hst);
+    he = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, hp.splits, 640, 576, p->Cout, p->Cout,
+                                    1.f, hst);
     return he == cudaSuccess ? 0 : cuda_fail(he, "wgrad_halo reduce launch");
   }
   WgradPlan pl;
   int rc = plan_wgrad(p, &pl);
   if (rc) return rc;
-  const size_t need = pl.splits > 1 ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
+  const bool via_partial = pl.splits > 1 || wgrad_clip(p);   // clipped / scaled outputs always go through the reduce
+  const size_t need = via_partial ? (size_t)pl.splits * pl.rows_pad * p->Cout * sizeof(float) : 0;
   if (need > workspace_bytes || (need && !workspace))
     return fail(FCN8_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu", workspace_bytes, need);
   const int rows_all = p->ksize * p->ksize * p->Cin;
@@ -751,15 +794,17 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
 
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
-  const void* xs[3] = {p->x, p->x, p->x_lo};
-  const void* ds[3] = {p->dy, p->dy_lo, p->dy};
+  const void* xs[3] = {p->x, p->x_lo, p->x};        // low-order products first (ConvGemmArgs::rz_c)
+  const void* ds[3] = {p->dy_lo, p->dy, p->dy};
+  if (p->nseg == 2) xs[1] = p->x;
+  if (p->nseg == 1) ds[0] = p->dy;
   for (int s = 0; s < p->nseg; ++s) {
     const bool atom32 = p->dtype == FCN8_F32;  // MN-major tf32 operands need the 32-byte-granule swizzle
     rc = encode_act_map(&maps.a[s], xs[s], p->dtype, p->N, p->H, p->W, p->Cin, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
-                        atom32, p->x_ld);
+                        atom32, p->x_ld, p->x_sH, p->x_sN);
     if (rc) return rc;
     rc = encode_act_map(&maps.b[s], ds[s], p->dtype, p->N, p->H, p->W, p->Cout, 1 << pl.lbw, 1 << pl.lbh,
-                        1 << pl.lbn, atom32, p->dy_ld);
+                        1 << pl.lbn, atom32, p->dy_ld, p->dy_sH, p->dy_sN);
     if (rc) return rc;
   }
   WgradArgs a;
@@ -788,11 +833,12 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   a.pb_b = pl.pb_b;
   a.splits = pl.splits;
   a.pb_per_split = pl.pb_per_split;
-  a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
+  a.flags = via_partial ? EPI_PARTIAL : 0;
   {
+    // the hi*hi segment's share of a split's MMAs truncates at full magnitude (on average 1 / nseg of them)
     const int pix = 1 << (pl.lbw + pl.lbh + pl.lbn);
     const int mma_per_pb = pix / (p->dtype == FCN8_BF16 ? 16 : 8);
-    a.acc_scale = g_debug[0] ? 1.f : 1.f + (float)mma_per_pb * (float)pl.pb_per_split * kRzBiasPerMma;
+    a.acc_scale = 1.f + (float)mma_per_pb * (float)pl.pb_per_split / (float)p->nseg * rz_per_mma();
   }
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
   const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
@@ -814,9 +860,10 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   }
 #undef FCN8_DISPATCH
   if (e != cudaSuccess) return cuda_fail(e, "wgrad_gemm launch");
-  if (pl.splits > 1) {
+  if (via_partial) {
     e = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, pl.splits, pl.rows_pad, rows_valid,
-                                   p->Cout, st);
+                                   p->Cout, p->out_cols > 0 ? p->out_cols : p->Cout,
+                                   p->out_scale != 0.f ? p->out_scale : 1.f, st);
     if (e != cudaSuccess) return cuda_fail(e, "wgrad split-K reduce launch");
   }
   return 0;
@@ -877,78 +924,6 @@ int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t work
   return e == cudaSuccess ? 0 : cuda_fail(e, "bias_grad launch");
 }
 
-size_t fcn8_score_head_fwd_workspace_bytes(const Fcn8HeadParams* p) {
-  const int slices = head_fwd_slices(p->P, p->Cin);
-  return slices > 1 ? (size_t)slices * p->P * p->C * sizeof(float) : 0;
-}
-int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!p || !p->x || !p->K || !p->b || !p->s) return fail(FCN8_ERR_BAD_SHAPE, "head fwd: null pointer");
-  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head: num_classes=%d not in [1,32]", p->C);
-  const size_t need = fcn8_score_head_fwd_workspace_bytes(p);
-  if (need > workspace_bytes || (need && !workspace))
-    return fail(FCN8_ERR_WORKSPACE, "head fwd: workspace %zu < required %zu", workspace_bytes, need);
-  cudaError_t e = launch_head_fwd(p->x, p->K, p->b, p->s, p->P, p->Cin, p->C, p->scale, p->dtype,
-                                  static_cast<float*>(workspace), (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "head fwd launch");
-}
-size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p) {
-  const size_t nb = head_bwd_blocks(p->P);
-  return (nb * p->Cin * p->C + nb * p->C) * sizeof(float);
-}
-int32_t fcn8_score_head_bwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!p || !p->x || !p->K || !p->s || !p->dK || !p->db) return fail(FCN8_ERR_BAD_SHAPE, "head bwd: null pointer");
-  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head: num_classes=%d not in [1,32]", p->C);
-  if (workspace_bytes < fcn8_score_head_bwd_workspace_bytes(p) || !workspace)
-    return fail(FCN8_ERR_WORKSPACE, "head bwd: workspace too small");
-  cudaError_t e = launch_head_bwd(p->x, p->K, p->s, p->dK, p->db, p->dx, p->P, p->Cin, p->C, p->scale, p->dtype,
-                                  p->mask, p->mask_scale, static_cast<float*>(workspace), (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "head bwd launch");
-}
-
-static int check_upscore(const Fcn8UpscoreParams* p) {
-  if (!p || !p->x || !p->T || !p->y) return fail(FCN8_ERR_BAD_SHAPE, "upscore: null pointer");
-  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "upscore: num_classes=%d not in [1,32]", p->C);
-  if (p->stride < 2 || (p->stride & 1)) return fail(FCN8_ERR_BAD_SHAPE, "upscore: stride must be even");
-  if (p->N <= 0 || p->h <= 0 || p->w <= 0) return fail(FCN8_ERR_BAD_SHAPE, "upscore: empty tensor");
-  return 0;
-}
-int32_t fcn8_upscore_fwd(const Fcn8UpscoreParams* p, void* stream) {
-  int rc = check_upscore(p);
-  if (rc) return rc;
-  if (!p->bias) return fail(FCN8_ERR_BAD_SHAPE, "upscore fwd: bias missing");
-  cudaError_t e = launch_upscore_fwd(p->x, p->T, p->bias, p->skip, p->y, p->N, p->h, p->w, p->C, p->stride,
-                                     (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore fwd launch");
-}
-size_t fcn8_upscore_bwd_workspace_bytes(const Fcn8UpscoreParams* p) {
-  return upscore_bwd_ws_floats(p->N, p->h, p->w, p->C, p->stride) * sizeof(float);
-}
-int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_upscore(p);
-  if (rc) return rc;
-  if (!p->dT || !p->dbias) return fail(FCN8_ERR_BAD_SHAPE, "upscore bwd: dT / dbias missing");
-  if (workspace_bytes < fcn8_upscore_bwd_workspace_bytes(p) || !workspace)
-    return fail(FCN8_ERR_WORKSPACE, "upscore bwd: workspace too small");
-  cudaError_t e = launch_upscore_bwd(p->x, p->T, p->y, p->dx, p->dT, p->dbias, p->N, p->h, p->w, p->C, p->stride,
-                                     static_cast<float*>(workspace), (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore bwd launch");
-}
-
-int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream) {
-  if (!p || !p->logits) return fail(FCN8_ERR_BAD_SHAPE, "softmax: null pointer");
-  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "softmax: num_classes=%d not in [1,32]", p->C);
-  if (p->CP < p->C || p->pad < 0) return fail(FCN8_ERR_BAD_SHAPE, "softmax: CP < C or negative pad");
-  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "softmax: empty tensor");
-  if ((p->loss_sum || p->dlogits) && !p->labels) return fail(FCN8_ERR_BAD_SHAPE, "softmax: loss needs labels");
-  if (p->dlogits && p->softmax) return fail(FCN8_ERR_UNSUPPORTED, "softmax: dlogits and softmax are exclusive");
-  if ((p->CP & 3) == 0 && (!aligned16(p->logits) || (p->dlogits && !aligned16(p->dlogits))))
-    return fail(FCN8_ERR_BAD_ALIGN, "softmax: logits / dlogits must be 16-byte aligned");
-  cudaError_t e = launch_softmax_xent(p->logits, p->labels, p->loss_sum, p->dlogits, p->dbias, p->softmax,
-                                      reinterpret_cast<long long*>(p->argmax), p->N, p->H, p->W, p->C, p->CP, p->pad,
-                                      p->grad_scale, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "softmax launch");
-}
-
 int32_t fcn8_confusion_matrix(const int64_t* pred, const uint8_t* labels_onehot, unsigned long long* conf, int64_t P,
                               int32_t C, void* stream) {
   if (!pred || !labels_onehot || !conf) return fail(FCN8_ERR_BAD_SHAPE, "confusion: null pointer");
@@ -999,149 +974,278 @@ int32_t fcn8_l2_reg(const float* w, float* g, float* loss_sum, size_t n, float r
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------------------------
-// Transposed convolutions on the tensor cores (phase GEMM).
+// Decoder on the tensor cores (fcn8s_tensorflow.py:164-235 and its autodiff).  The three transposed convolutions are
+// phase GEMMs over bf16 hi / lo planes: for stride s, kernel 2s, pad s/2 every s x s output block (J, I),
+// J in [0,h], I in [0,w], depends on the 2x2 inputs (J-1+ty, I-1+tx):
+//   Zblock[(dy,dx,co)] = sum_{(ty,tx,ci)} x[J-1+ty, I-1+tx, ci] * T[dy+s(1-ty), dx+s(1-tx), co, ci]
+// rows = blocks, K = 4 taps x 64 channels (classes zero-padded to one 128-byte operand row), N = s*s*CP columns.
+//   fwd  (s = 2): the block columns are scattered to the dense output in the epilogue, + skip tensor (tf.add :213,224)
+//   loss (s = 8): CP = 32, a 256-column tile is one block row of 8 pixels: softmax-CE / gradient / softmax / argmax /
+//                 confusion matrix in the epilogue, logits are not written unless asked for
+//   dx:  A = dz planes in the padded blocked layout [N, s(h+1), s(w+1), CP] through a 5-D TMA map, K = 4 * s*s*CP
+//   dw:  dWbig[(ty,tx,ci), (dy,dx,co)] = sum_blocks Xnbr * dZblock (wgrad kernel, dz as the 5-D B operand), un-permuted
+// The 1x1 score heads run through fcn8_conv_gemm / fcn8_wgrad_gemm with the class dimension padded to 64
+// (fcn8_head_pack); see INTEGRATION.md.
 namespace {
-int upscore_cp(int C, int s) {
-  const int q = 32 / s > 4 ? 32 / s : 4;  // s*CP must be a whole number of 128-byte chunks
-  return (C + q - 1) / q * q;
-}
-int check_upscore_tc(const Fcn8UpscoreTcParams* p, const char* what) {
+int deconv_cp(int s) { return s == 8 ? 32 : 64; }
+int check_deconv(const Fcn8DeconvParams* p, const char* what) {
   if (!p) return fail(FCN8_ERR_BAD_SHAPE, "%s: null params", what);
   if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "%s: num_classes=%d not in [1,32]", what, p->C);
-  if (p->stride != 2 && p->stride != 4 && p->stride != 8)
-    return fail(FCN8_ERR_UNSUPPORTED, "%s: stride must be 2, 4 or 8", what);
+  if (p->stride != 2 && p->stride != 8) return fail(FCN8_ERR_UNSUPPORTED, "%s: stride must be 2 or 8", what);
   if (p->N <= 0 || p->h <= 0 || p->wd <= 0) return fail(FCN8_ERR_BAD_SHAPE, "%s: empty tensor", what);
-  if (p->nseg != 1 && p->nseg != 3) return fail(FCN8_ERR_BAD_SHAPE, "%s: nseg must be 1 or 3", what);
-  if (p->ldx % 4 || p->ldx < p->C) return fail(FCN8_ERR_BAD_SHAPE, "%s: ldx=%d must be a multiple of 4 >= C", what, p->ldx);
+  if (p->nseg < 1 || p->nseg > 3) return fail(FCN8_ERR_BAD_SHAPE, "%s: nseg must be 1, 2 or 3", what);
   return 0;
 }
-// x [N,h,w,ldx] fp32 as the (C, W, H, N) map with a 32-float box: channels >= ldx are zero-filled by TMA.
-int encode_dec_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int ld, int bw, int bh, int bn,
-                       bool atom32) {
-  return encode_act_map(m, ptr, FCN8_F32, N, H, W, ld, bw, bh, bn, atom32);
+// zp planes [N][s*Hb][s*Wb][CP] bf16 seen as dims (s*CP, Wb, s, Hb, N); box (64, bw, 1, bh, bn) = bw*bh*bn blocks x 128 B
+int encode_blocked_map(CUtensorMap* m, const void* ptr, int N, int Hb, int Wb, int s, int CP, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t row = (cuuint64_t)s * CP * 2;       // bytes of one block row
+  const cuuint64_t line = (cuuint64_t)Wb * row;        // bytes of one padded image row
+  const cuuint64_t dims[5] = {(cuuint64_t)s * CP, (cuuint64_t)Wb, (cuuint64_t)s, (cuuint64_t)Hb, (cuuint64_t)N};
+  const cuuint64_t strides[4] = {row, line, (cuuint64_t)s * line, (cuuint64_t)s * Hb * line};
+  const cuuint32_t box[5] = {64, (cuuint32_t)bw, 1, (cuuint32_t)bh, (cuuint32_t)bn};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(blocked N%d Hb%d Wb%d s%d CP%d) failed: %d", N, Hb, Wb, s, CP,
+                (int)r);
+  return 0;
+}
+// operand pointers of segment i in the order low-order products first (ConvGemmArgs::rz_c): (a, b_lo), (a_lo, b), (a, b)
+void seg_ptrs(int nseg, const void* a, const void* a_lo, const void* b, const void* b_lo, const void* as[3],
+              const void* bs[3]) {
+  as[0] = a; as[1] = a_lo; as[2] = a;
+  bs[0] = b_lo; bs[1] = b; bs[2] = b;
+  if (nseg == 2) as[1] = a;
+  if (nseg == 1) bs[0] = b;
+}
+
+cudaError_t launch_conv_loss(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, bool pair, cudaStream_t st) {
+  static bool attr_done_dev[64][2] = {};
+  bool& attr_done = attr_done_dev[cur_dev()][pair ? 1 : 0];
+  if (pair) {
+    using Cfg = GemmCfg<256, true>;
+    if (!attr_done) {
+      cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, true, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+      if (e != cudaSuccess) return e;
+      attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl_off ? 1 : 2;
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, true, 1>, maps, a);
+  }
+  using Cfg = GemmCfg<256>;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, false, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  (void)launch_k(conv_gemm_kernel<256, false, false, 1>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, maps, a);
+  return cudaGetLastError();
+}
+
+// common part of fwd / loss: A = x planes (2x2 taps over the (h+1) x (w+1) block grid), B = packed w_fwd
+int setup_deconv_fwd(const Fcn8DeconvParams* p, int BN, TensorMaps3* maps, ConvGemmArgs* a) {
+  const int s = p->stride, CP = deconv_cp(s);
+  const int Hb = p->h + 1, Wb = p->wd + 1;
+  const int ncols = s * s * CP;
+  int lbw, lbh, lbn;
+  choose_patch(p->N, Hb, Wb, 7, &lbw, &lbh, &lbn);
+  memset(maps, 0, sizeof(*maps));
+  const void* xs[3];
+  const void* ws[3];
+  seg_ptrs(p->nseg, p->x, p->x_lo, p->w, p->w_lo, xs, ws);
+  const int b_rows = BN;
+  for (int i = 0; i < p->nseg; ++i) {
+    int rc = encode_act_map(&maps->a[i], xs[i], FCN8_BF16, p->N, p->h, p->wd, 64, 1 << lbw, 1 << lbh, 1 << lbn, false,
+                            p->x_ld, p->x_sH, p->x_sN);
+    if (rc) return rc;
+    rc = encode_w_map(&maps->b[i], ws[i], FCN8_BF16, ncols, 256, b_rows);
+    if (rc) return rc;
+  }
+  memset(a, 0, sizeof(*a));
+  a->bias = p->bias_big;
+  a->N = p->N;
+  a->H = Hb;
+  a->W = Wb;
+  a->ldc = ncols;
+  a->taps = 4;
+  a->taps_w = 2;
+  a->pad = 1;
+  a->cblocks = 1;
+  a->nseg = p->nseg;
+  a->lbw = lbw;
+  a->lbh = lbh;
+  a->lbn = lbn;
+  a->tiles_x = (Wb + (1 << lbw) - 1) >> lbw;
+  a->tiles_y = (Hb + (1 << lbh) - 1) >> lbh;
+  a->tiles_b = (p->N + (1 << lbn) - 1) >> lbn;
+  a->tiles_n = ncols / BN;
+  a->splits = 1;
+  a->kb_per_split = p->nseg * 4;
+  a->acc_scale = 1.f;
+  a->rz_c = 4.f * rz_per_mma();
+  a->flags = EPI_BIAS;
+  a->blk_s = s;
+  a->blk_cp = CP;
+  a->out_H = s * p->h;
+  a->out_W = s * p->wd;
+  return 0;
 }
 }  // namespace
 
 extern "C" {
 
-int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride) { return upscore_cp(C, stride); }
+int32_t fcn8_deconv_cp(int32_t stride) { return deconv_cp(stride); }
 
-int32_t fcn8_upscore_tc_gather(const float* zp, const float* skip, float* f, int32_t N, int32_t h, int32_t w,
-                               int32_t C, int32_t stride, int32_t ldf, int32_t ld_skip, void* stream) {
-  if (!zp || !f) return fail(FCN8_ERR_BAD_SHAPE, "upscore gather: null pointer");
-  if (C < 1 || C > 32 || ldf < C || (skip && ld_skip < C)) return fail(FCN8_ERR_BAD_SHAPE, "upscore gather: bad C / ld");
-  cudaError_t e = launch_upscore_gather(zp, skip, f, N, h * stride, w * stride, C, upscore_cp(C, stride), stride / 2,
-                                        ldf, ld_skip, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore gather launch");
-}
-int32_t fcn8_upscore_tc_scatter(const float* g, float* dzp, float* dbias, int32_t N, int32_t h, int32_t w, int32_t C,
-                                int32_t stride, int32_t ldg, void* stream) {
-  if (!g || !dzp) return fail(FCN8_ERR_BAD_SHAPE, "upscore scatter: null pointer");
-  if (C < 1 || C > 32 || ldg < C) return fail(FCN8_ERR_BAD_SHAPE, "upscore scatter: bad C / ld");
-  cudaError_t e = launch_upscore_scatter(g, dzp, dbias, N, h * stride, w * stride, C, upscore_cp(C, stride),
-                                         stride / 2, ldg, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore scatter launch");
+int32_t fcn8_deconv_pack(const float* T, const float* bias, int32_t C, int32_t stride, void* w_fwd, void* w_fwd_lo,
+                         void* w_dx, void* w_dx_lo, float* bias_big, void* stream) {
+  if (!T || !bias || !w_fwd || !w_dx || !bias_big) return fail(FCN8_ERR_BAD_SHAPE, "deconv pack: null pointer");
+  if (C < 1 || C > 32) return fail(FCN8_ERR_UNSUPPORTED, "deconv pack: num_classes=%d not in [1,32]", C);
+  if (stride != 2 && stride != 8) return fail(FCN8_ERR_UNSUPPORTED, "deconv pack: stride must be 2 or 8");
+  cudaError_t e = launch_deconv_pack(T, bias, w_fwd, w_fwd_lo, w_dx, w_dx_lo, bias_big, C, deconv_cp(stride), stride,
+                                     (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "deconv pack launch");
 }
 
-int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream) {
-  if (!p || !p->T || !p->bias || !p->w_fwd || !p->w_dx || !p->bias_big)
-    return fail(FCN8_ERR_BAD_SHAPE, "upscore pack: null pointer");
-  if (p->C < 1 || p->C > 32) return fail(FCN8_ERR_UNSUPPORTED, "upscore pack: num_classes=%d not in [1,32]", p->C);
-  if (p->stride != 2 && p->stride != 4 && p->stride != 8)
-    return fail(FCN8_ERR_UNSUPPORTED, "upscore pack: stride must be 2, 4 or 8");
-  cudaError_t e = launch_upscore_pack(p->T, p->bias, p->w_fwd, p->w_fwd_lo, p->w_dx, p->w_dx_lo, p->bias_big, p->C,
-                                      upscore_cp(p->C, p->stride), p->stride, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore pack launch");
+int32_t fcn8_head_pack(const float* K, const float* bias, int32_t Cin, int32_t C, void* w_hi, void* w_lo, float* bias64,
+                       void* stream) {
+  if (!K || !w_hi) return fail(FCN8_ERR_BAD_SHAPE, "head pack: null pointer");
+  if (C < 1 || C > 32) return fail(FCN8_ERR_UNSUPPORTED, "head pack: num_classes=%d not in [1,32]", C);
+  cudaError_t e = launch_head_pack(K, bias, Cin, C, w_hi, w_lo, bias64, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "head pack launch");
 }
 
-// zp[n, s*J + dy, s*I + dx, co] = sum_{ty,tx,ci} x[n, J-1+ty, I-1+tx, ci] * T[dy + s(1-ty), dx + s(1-tx), co, ci] + bias
-int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream) {
-  int rc = check_upscore_tc(p, "upscore_tc_fwd");
+// stride-2 stages (upscore2, upscore_pool4): dense output planes + skip tensor in the epilogue
+int32_t fcn8_deconv_fwd(const Fcn8DeconvParams* p, void* stream) {
+  int rc = check_deconv(p, "deconv_fwd");
   if (rc) return rc;
-  if (!p->x || !p->w || !p->bias_big || !p->zp) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: null pointer");
-  if (p->nseg == 3 && (!p->x_lo || !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: nseg=3 needs x_lo, w_lo");
-  const int s = p->stride, CP = upscore_cp(p->C, s);
-  const int Hb = p->h + 1, Wb = p->wd + 1;
+  if (!p->x || !p->w || !p->bias_big || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "deconv_fwd: null pointer");
+  if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "deconv_fwd: lo operands");
+  const int s = p->stride, CP = deconv_cp(s);
   const int ncols = s * s * CP;
-  const int BN = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
-  if (ncols % BN) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_fwd: %d columns not tileable", ncols);
-  int lbw, lbh, lbn;
-  choose_patch(p->N, Hb, Wb, 7, &lbw, &lbh, &lbn);
+  const int BN = ncols % 256 == 0 ? 256 : 128;
   TensorMaps3 maps;
-  memset(&maps, 0, sizeof(maps));
-  const void* xs[3] = {p->x, p->x, p->x_lo};
-  const void* ws[3] = {p->w, p->w_lo, p->w};
-  for (int i = 0; i < p->nseg; ++i) {
-    rc = encode_dec_act_map(&maps.a[i], xs[i], p->N, p->h, p->wd, p->ldx, 1 << lbw, 1 << lbh, 1 << lbn, false);
-    if (rc) return rc;
-    rc = encode_w_map(&maps.b[i], ws[i], FCN8_F32, ncols, 128, BN);
-    if (rc) return rc;
-  }
   ConvGemmArgs a;
-  memset(&a, 0, sizeof(a));
-  a.out = p->zp;
-  a.bias = p->bias_big;
-  a.N = p->N;
-  a.H = Hb;
-  a.W = Wb;
-  a.ldc = ncols;
-  a.taps = 4;
-  a.taps_w = 2;
-  a.pad = 1;
-  a.cblocks = 1;
-  a.nseg = p->nseg;
-  a.lbw = lbw;
-  a.lbh = lbh;
-  a.lbn = lbn;
-  a.tiles_x = (Wb + (1 << lbw) - 1) >> lbw;
-  a.tiles_y = (Hb + (1 << lbh) - 1) >> lbh;
-  a.tiles_b = (p->N + (1 << lbn) - 1) >> lbn;
-  a.tiles_n = ncols / BN;
-  a.splits = 1;
-  a.kb_per_split = p->nseg * 4;
-  a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)a.kb_per_split * kRzBiasPerMma;
-  a.flags = EPI_BIAS;
-  a.out_mode = 1;
-  a.blk_row = s * CP;
-  a.osW = (long long)s * CP;
-  a.os_dy = (long long)Wb * s * CP;
-  a.osH = (long long)s * a.os_dy;
-  a.osN = (long long)Hb * a.osH;
+  rc = setup_deconv_fwd(p, BN, &maps, &a);
+  if (rc) return rc;
+  a.out = p->out;
+  a.out_lo = p->out_lo;
+  a.out_mode = 2;
+  const int out_ld = p->out_ld > 0 ? p->out_ld : CP;
+  a.osW = out_ld;
+  a.osH = p->out_sH > 0 ? p->out_sH : (long long)a.out_W * out_ld;
+  a.osN = p->out_sN > 0 ? p->out_sN : (long long)a.out_H * a.osH;
+  if (p->skip) {
+    a.flags |= EPI_RESIDUAL;
+    a.residual = p->skip;
+    a.residual_lo = p->skip_lo;
+  }
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_b * a.tiles_n;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  cudaError_t e = dispatch_conv(BN, true, maps, a, grid, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_fwd launch");
+  cudaError_t e = dispatch_conv(BN, false, maps, a, grid, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "deconv_fwd launch");
 }
 
-// dx[n,i,j,ci] = sum_{ty,tx} sum_{dy,dx,co} dzp[n, s(i+1-ty)+dy, s(j+1-tx)+dx, co] * T[dy+s(1-ty), dx+s(1-tx), co, ci]
-int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream) {
-  int rc = check_upscore_tc(p, "upscore_tc_dx");
+// stride-8 stage (upscore8) with the loss / predictor fused into its epilogue
+int32_t fcn8_deconv_loss(const Fcn8DeconvParams* p, void* stream) {
+  int rc = check_deconv(p, "deconv_loss");
   if (rc) return rc;
-  if (!p->zp || !p->w || !p->dx) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dx: null pointer");
-  if (p->nseg == 3 && (!p->zp_lo || !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dx: nseg=3 needs zp_lo, w_lo");
-  const int s = p->stride, CP = upscore_cp(p->C, s);
+  if (p->stride != 8) return fail(FCN8_ERR_UNSUPPORTED, "deconv_loss: stride must be 8");
+  if (!p->x || !p->w || !p->bias_big) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: null pointer");
+  if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: lo operands");
+  if ((p->loss_sum || p->dz_hi_out || p->conf) && !p->labels) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: needs labels");
+  if (!p->loss_sum && !p->dz_hi_out && !p->conf && !p->logits && !p->softmax && !p->argmax)
+    return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: no output requested");
+  if ((p->dz_hi_out && !aligned16(p->dz_hi_out)) || (p->dz_lo_out && !aligned16(p->dz_lo_out)))
+    return fail(FCN8_ERR_BAD_ALIGN, "deconv_loss: dz planes must be 16-byte aligned");
+  TensorMaps3 maps;
+  ConvGemmArgs a;
+  rc = setup_deconv_fwd(p, 256, &maps, &a);
+  if (rc) return rc;
+  a.flags = 0;     // the loss epilogue adds the bias itself
+  a.labels = p->labels;
+  a.loss_sum = p->loss_sum;
+  a.dbias = p->dbias;
+  a.dz_hi = static_cast<__nv_bfloat16*>(p->dz_hi_out);
+  a.dz_lo = static_cast<__nv_bfloat16*>(p->dz_lo_out);
+  a.logits = p->logits;
+  a.softmax = p->softmax;
+  a.argmax = reinterpret_cast<long long*>(p->argmax);
+  a.conf = reinterpret_cast<unsigned long long*>(p->conf);
+  a.num_classes = p->C;
+  a.gscale = p->grad_scale;
+  const bool pair = !g_debug[5];
+  const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_b;
+  cudaError_t e;
+  if (pair) {
+    const long long units = (long long)((m_tiles + 1) / 2) * a.tiles_n;
+    const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
+    // each CTA of a pair loads half of the 256-row weight tile
+    for (int i = 0; i < p->nseg; ++i) {
+      const void* xs[3];
+      const void* ws[3];
+      seg_ptrs(p->nseg, p->x, p->x_lo, p->w, p->w_lo, xs, ws);
+      rc = encode_w_map(&maps.b[i], ws[i], FCN8_BF16, 8 * 8 * 32, 256, 128);
+      if (rc) return rc;
+    }
+    e = launch_conv_loss(maps, a, 2 * pairs, true, (cudaStream_t)stream);
+  } else {
+    const long long tiles = (long long)m_tiles * a.tiles_n;
+    e = launch_conv_loss(maps, a, (int)(tiles < num_sms() ? tiles : num_sms()), false, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? 0 : cuda_fail(e, "deconv_loss launch");
+}
+
+// dx[n,i,j,ci] = sum_{ty,tx} sum_{dy,dx,co} dz[n, s(i+1-ty)+dy, s(j+1-tx)+dx, co] * T[dy+s(1-ty), dx+s(1-tx), co, ci]
+int32_t fcn8_deconv_dx(const Fcn8DeconvParams* p, void* stream) {
+  int rc = check_deconv(p, "deconv_dx");
+  if (rc) return rc;
+  if (!p->dz || !p->w || !p->out) return fail(FCN8_ERR_BAD_SHAPE, "deconv_dx: null pointer");
+  if ((p->nseg == 3 && !p->dz_lo) || (p->nseg >= 2 && !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "deconv_dx: lo operands");
+  const int s = p->stride, CP = deconv_cp(s);
   const int Hb = p->h + 1, Wb = p->wd + 1;
-  const int chunks_row = s * CP / 32;
+  const int chunks_row = s * CP / 64;
   const int cblocks = s * chunks_row;  // k-blocks per tap
   int lbw, lbh, lbn;
   choose_patch(p->N, p->h, p->wd, 7, &lbw, &lbh, &lbn);
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
-  const void* zs[3] = {p->zp, p->zp, p->zp_lo};
-  const void* ws[3] = {p->w, p->w_lo, p->w};
+  const void* zs[3];
+  const void* ws[3];
+  seg_ptrs(p->nseg, p->dz, p->dz_lo, p->w, p->w_lo, zs, ws);
   for (int i = 0; i < p->nseg; ++i) {
-    rc = encode_blocked_map(&maps.a[i], zs[i], p->N, Hb, Wb, s, CP, 1 << lbw, 1 << lbh, 1 << lbn, false);
+    rc = encode_blocked_map(&maps.a[i], zs[i], p->N, Hb, Wb, s, CP, 1 << lbw, 1 << lbh, 1 << lbn);
     if (rc) return rc;
-    rc = encode_w_map(&maps.b[i], ws[i], FCN8_F32, 64, 4 * s * s * CP, 64);
+    rc = encode_w_map(&maps.b[i], ws[i], FCN8_BF16, 64, 4 * s * s * CP, 64);
     if (rc) return rc;
   }
   ConvGemmArgs a;
   memset(&a, 0, sizeof(a));
-  a.out = p->dx;
+  a.out = p->out;
+  a.out_lo = p->out_lo;
   a.N = p->N;
   a.H = p->h;
   a.W = p->wd;
-  a.ldc = p->ldx;
+  a.ldc = 64;
   a.taps = 4;
   a.taps_w = 2;
   a.pad = 1;
@@ -1156,35 +1260,41 @@ int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream) {
   a.tiles_n = 1;
   a.splits = 1;
   a.kb_per_split = p->nseg * 4 * cblocks;
-  a.acc_scale = g_debug[0] ? 1.f : 1.f + 4.f * (float)a.kb_per_split * kRzBiasPerMma;
+  a.acc_scale = 1.f;
+  a.rz_c = 4.f * rz_per_mma();
   a.flags = 0;
   a.a_mode = 1;
   a.blk_chunks = chunks_row;
-  a.store_cols = p->ldx;
-  a.osW = p->ldx;
-  a.osH = (long long)p->wd * p->ldx;
-  a.osN = (long long)p->h * a.osH;
+  const int out_ld = p->out_ld > 0 ? p->out_ld : 64;
+  a.osW = out_ld;
+  a.osH = p->out_sH > 0 ? p->out_sH : (long long)p->wd * out_ld;
+  a.osN = p->out_sN > 0 ? p->out_sN : (long long)p->h * a.osH;
+  if (p->colsum) {
+    a.flags |= EPI_COLSUM;
+    a.colsum = p->colsum;
+    a.colsum_n = p->colsum_n > 0 ? p->colsum_n : p->C;
+  }
   const long long tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_b;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  cudaError_t e = dispatch_conv(64, true, maps, a, grid, (cudaStream_t)stream);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_dx launch");
+  cudaError_t e = dispatch_conv(64, false, maps, a, grid, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "deconv_dx launch");
 }
 
 namespace {
-struct UpDwPlan {
+struct DeconvDwPlan {
   int BN, splits, pb_per_split, total_pb, lbw, lbh, lbn, pb_x, pb_y, pb_b, tiles_n, ncols;
 };
-void plan_updw(const Fcn8UpscoreTcParams* p, UpDwPlan* pl) {
-  const int s = p->stride, CP = upscore_cp(p->C, s);
+void plan_deconv_dw(const Fcn8DeconvParams* p, DeconvDwPlan* pl) {
+  const int s = p->stride, CP = deconv_cp(s);
   pl->ncols = s * s * CP;
-  pl->BN = pl->ncols % 128 == 0 ? 128 : 64;
+  pl->BN = 128;
   pl->tiles_n = pl->ncols / pl->BN;
-  choose_patch(p->N, p->h + 1, p->wd + 1, 6, &pl->lbw, &pl->lbh, &pl->lbn);
+  choose_patch(p->N, p->h + 1, p->wd + 1, 7, &pl->lbw, &pl->lbh, &pl->lbn);
   pl->pb_x = (p->wd + 1 + (1 << pl->lbw) - 1) >> pl->lbw;
   pl->pb_y = (p->h + 1 + (1 << pl->lbh) - 1) >> pl->lbh;
   pl->pb_b = (p->N + (1 << pl->lbn) - 1) >> pl->lbn;
   pl->total_pb = p->nseg * pl->pb_x * pl->pb_y * pl->pb_b;
-  int splits = num_sms() / pl->tiles_n;
+  int splits = num_sms() / (2 * pl->tiles_n);   // two 128-row M tiles (4 taps x 64 channels) per N tile
   const int max_by_k = pl->total_pb / 4 > 0 ? pl->total_pb / 4 : 1;
   if (splits > max_by_k) splits = max_by_k;
   if (splits > 64) splits = 64;
@@ -1194,54 +1304,54 @@ void plan_updw(const Fcn8UpscoreTcParams* p, UpDwPlan* pl) {
 }
 }  // namespace
 
-size_t fcn8_upscore_tc_dw_workspace_bytes(const Fcn8UpscoreTcParams* p) {
-  if (check_upscore_tc(p, "upscore_tc_dw")) return 0;
-  UpDwPlan pl;
-  plan_updw(p, &pl);
-  return (size_t)(pl.splits + 1) * 128 * pl.ncols * sizeof(float);
+size_t fcn8_deconv_dw_workspace_bytes(const Fcn8DeconvParams* p) {
+  if (check_deconv(p, "deconv_dw")) return 0;
+  DeconvDwPlan pl;
+  plan_deconv_dw(p, &pl);
+  return (size_t)pl.splits * 256 * pl.ncols * sizeof(float);
 }
 
-// dT[a,b,co,ci] = sum_{n,i,j} x[n,i,j,ci] * dz[n, s*i+a-p, s*j+b-p, co], computed as the phase GEMM
-// dWbig[(ty,tx,ci), (dy,dx,co)] = sum_blocks Xnbr * dZblock and un-permuted into the TF layout.
-int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_upscore_tc(p, "upscore_tc_dw");
+// dT[a,b,co,ci] = sum_{n,i,j} x[n,i,j,ci] * dz[n, s*i+a-p, s*j+b-p, co] as the phase GEMM
+// dWbig[(ty,tx,ci), (dy,dx,co)] = sum_blocks Xnbr * dZblock, un-permuted into the TF layout by the reduce kernel.
+int32_t fcn8_deconv_dw(const Fcn8DeconvParams* p, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_deconv(p, "deconv_dw");
   if (rc) return rc;
-  if (!p->x || !p->zp || !p->dT) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dw: null pointer");
-  if (p->nseg == 3 && (!p->x_lo || !p->zp_lo)) return fail(FCN8_ERR_BAD_SHAPE, "upscore_tc_dw: nseg=3 needs x_lo, zp_lo");
-  const size_t need = fcn8_upscore_tc_dw_workspace_bytes(p);
-  if (workspace_bytes < need || !workspace) return fail(FCN8_ERR_WORKSPACE, "upscore_tc_dw: workspace too small");
-  const int s = p->stride, CP = upscore_cp(p->C, s);
-  UpDwPlan pl;
-  plan_updw(p, &pl);
+  if (!p->x || !p->dz || !p->dT) return fail(FCN8_ERR_BAD_SHAPE, "deconv_dw: null pointer");
+  if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->dz_lo)) return fail(FCN8_ERR_BAD_SHAPE, "deconv_dw: lo operands");
+  const size_t need = fcn8_deconv_dw_workspace_bytes(p);
+  if (workspace_bytes < need || !workspace) return fail(FCN8_ERR_WORKSPACE, "deconv_dw: workspace too small");
+  const int s = p->stride, CP = deconv_cp(s);
+  DeconvDwPlan pl;
+  plan_deconv_dw(p, &pl);
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
-  const void* xs[3] = {p->x, p->x, p->x_lo};
-  const void* zs[3] = {p->zp, p->zp_lo, p->zp};
+  const void* xs[3];
+  const void* zs[3];
+  seg_ptrs(p->nseg, p->x, p->x_lo, p->dz, p->dz_lo, xs, zs);
   for (int i = 0; i < p->nseg; ++i) {
-    rc = encode_dec_act_map(&maps.a[i], xs[i], p->N, p->h, p->wd, p->ldx, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn, true);
+    rc = encode_act_map(&maps.a[i], xs[i], FCN8_BF16, p->N, p->h, p->wd, 64, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn, false,
+                        p->x_ld, p->x_sH, p->x_sN);
     if (rc) return rc;
-    rc = encode_blocked_map(&maps.b[i], zs[i], p->N, p->h + 1, p->wd + 1, s, CP, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn,
-                            true);
+    rc = encode_blocked_map(&maps.b[i], zs[i], p->N, p->h + 1, p->wd + 1, s, CP, 1 << pl.lbw, 1 << pl.lbh, 1 << pl.lbn);
     if (rc) return rc;
   }
-  float* dwbig = static_cast<float*>(workspace);                 // [128][ncols]
-  float* partial = dwbig + (size_t)128 * pl.ncols;               // [splits][128][ncols]
+  float* partial = static_cast<float*>(workspace);               // [splits][256][ncols]
   WgradArgs a;
   memset(&a, 0, sizeof(a));
-  a.out = dwbig;
+  a.out = partial;
   a.partial = partial;
   a.N = p->N;
   a.H = p->h + 1;
   a.W = p->wd + 1;
-  a.Cin = 32;
+  a.Cin = 64;
   a.ldc = pl.ncols;
   a.taps = 4;
   a.taps_w = 2;
   a.pad = 1;
   a.nseg = p->nseg;
-  a.rows_valid = 128;
+  a.rows_valid = 256;
   a.total_chunks = 4;
-  a.m_tiles = 1;
+  a.m_tiles = 2;
   a.tiles_n = pl.tiles_n;
   a.lbw = pl.lbw;
   a.lbh = pl.lbh;
@@ -1251,17 +1361,17 @@ int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t
   a.pb_b = pl.pb_b;
   a.splits = pl.splits;
   a.pb_per_split = pl.pb_per_split;
-  a.flags = pl.splits > 1 ? EPI_PARTIAL : 0;
+  a.flags = EPI_PARTIAL;
   a.b_mode = 1;
   a.blk_row = s * CP;
-  a.acc_scale = g_debug[0] ? 1.f : 1.f + 8.f * (float)pl.pb_per_split * kRzBiasPerMma;   // 64 px / 8 per tf32 MMA
-  const long long tiles = (long long)pl.tiles_n * pl.splits;
+  a.acc_scale = 1.f + 8.f * (float)pl.pb_per_split / (float)p->nseg * rz_per_mma();   // 128 blocks / 16 per bf16 MMA
+  const long long tiles = (long long)a.m_tiles * pl.tiles_n * pl.splits;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = dispatch_wgrad(pl.BN, true, maps, a, grid, st);
-  if (e != cudaSuccess) return cuda_fail(e, "upscore_tc_dw launch");
-  e = launch_upscore_unpack_dw(pl.splits > 1 ? partial : dwbig, pl.splits > 1 ? pl.splits : 1, p->dT, p->C, CP, s, st);
-  return e == cudaSuccess ? 0 : cuda_fail(e, "upscore_tc_dw unpack launch");
+  cudaError_t e = dispatch_wgrad(pl.BN, false, maps, a, grid, st);
+  if (e != cudaSuccess) return cuda_fail(e, "deconv_dw launch");
+  e = launch_deconv_unpack_dw(partial, pl.splits, p->dT, p->C, CP, s, st);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "deconv_dw unpack launch");
 }
 
 }  // extern "C"

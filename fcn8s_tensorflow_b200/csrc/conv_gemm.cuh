@@ -45,6 +45,8 @@ enum EpilogueFlags : int {
   EPI_DBG_NOLOAD = 1 << 21,   // measurement only (fcn8_debug_set(3, 2)): ... and its mask / residual loads
   EPI_COLSUM = 128,     // colsum[col] += sum over rows of the final values (the bias gradient of the layer whose dY
                         // this dgrad produces): per-CTA shared-memory accumulation, one global atomic per column
+  EPI_POOL = 256,       // also emit the 2x2 / stride-2 max-pool of the output (fused max-pool of conv{1_2,2_2,3_3,4_3,
+                        // 5_3}): needs the 8 x 16 pixel tile (row = y*8 + x), so that a window is 4 lanes of one warp
 };
 constexpr int kColsumMax = 4096;  // widest dgrad output (fc6 activations)
 
@@ -95,8 +97,19 @@ struct ConvGemmArgs {
   // Output addressing: element offset of row (n, y, x) = n*osN + y*osH + x*osW; column c lands at +c (out_mode 0) or,
   // for the blocked output of a transposed convolution (out_mode 1: a row is one s x s output block whose columns are
   // (dy, dx, co)), at + (c / blk_row) * os_dy + c % blk_row.  store_cols > 0 keeps only the first store_cols columns.
+  // out_mode 2: DENSE output of a transposed convolution (stride blk_s, blk_cp columns per pixel): row = block (y, x)
+  // of the (h+1) x (w+1) block grid, column c = (q, ch), q = c / blk_cp = dy * blk_s + dx, lands at channel ch of pixel
+  // (blk_s*y - blk_s/2 + dy, blk_s*x - blk_s/2 + dx) of the [N, out_H, out_W, .] tensor (strides osN / osH / osW);
+  // pixels outside are dropped.  Together with EPI_RESIDUAL this is the skip-fusion add of fcn8s_tensorflow.py:213,224
+  // in the epilogue of the transposed convolution that precedes it.
   long long osN, osH, osW, os_dy;
   int out_mode, blk_row, store_cols;
+  int blk_s, blk_cp, out_H, out_W;
+  int colsum_n;          // > 0: only the first colsum_n columns go to `colsum` (class counts < the padded width)
+  // EPI_POOL: pooled output [N, H/2, W/2, .] (same storage format as `out`), element strides per image / row / pixel
+  void* pool_out;
+  void* pool_out_lo;
+  long long psN, psH, psW;
   // A operand: a_mode 0 = NHWC map (C, W, H, N), tap (kh, kw) shifts the box by (kw - pad, kh - pad);
   // a_mode 1 = blocked 5-D map (s*CP, Wb, s, Hb, N) of a padded transposed-conv output: k-block (tap, cb) reads row
   // dy = cb / blk_chunks, chunk cb % blk_chunks of block (y + pad - kh, x + pad - kw).
@@ -116,11 +129,30 @@ struct ConvGemmArgs {
   // Round-toward-zero compensation: the TMEM accumulator truncates on every tcgen05.mma, an expected relative loss of
   // kRzBiasPerMma per accumulation step given the final value (measured, scripts/bringup.py::rz_accumulation_probe).
   // acc_scale = 1 + (MMAs accumulated into one accumulator) * kRzBiasPerMma multiplies the accumulator in the epilogue.
-  float acc_scale;
+  float acc_scale;   // base output scale (1, or the 1e-4 / 1e-2 skip scales of the score heads, fcn8s_tensorflow.py:171,182)
+  // The low-order segments of an error-compensated product (x*w_lo, x_lo*w) are accumulated FIRST, while the
+  // accumulator is still 2^-8 of its final size, and the hi*hi segment last: only its MMAs truncate at full magnitude.
+  // rz_c = expected relative loss per k-block (4 MMAs) of the hi*hi segment; the epilogue scales a tile's accumulator
+  // by acc_scale * (1 + rz_c * [hi*hi k-blocks accumulated into it]).
+  float rz_c;
   // measurement only (fcn8_debug_buffer): when set, CTA b writes dbg[8b + 0..3] = cycles its MMA warp spent in the
   // tile loop / waiting for operand stages (full barriers) / waiting for a free accumulator, and k-blocks issued;
   // dbg[8b + 4] = cycles the TMA producer waited for free stages
   long long* dbg;
+  // ---- EPI = 1 (loss / predictor epilogue of the upscore8 phase GEMM, fcn8s_tensorflow.py:226-235 + :253 / :268-269):
+  // a 256-column tile is one row (dy = tile index) of 8 output pixels x 32 padded classes of each block, so every
+  // epilogue thread holds whole pixels' logits.  Any subset of the outputs below may be requested (nullptr = skip).
+  const uint8_t* labels;        // one-hot [N, out_H, out_W, C] (bool / uint8)
+  float* loss_sum;              // += sum over pixels of softmax-CE
+  float* dbias;                 // [C] += sum over pixels of dz (gradient of the transposed convolution's bias)
+  __nv_bfloat16* dz_hi;         // dlogits in the padded blocked layout [N, 8*(h+1), 8*(w+1), 32], bf16 hi / lo planes
+  __nv_bfloat16* dz_lo;         //   (nullptr: hi only), border and channels >= C are zero
+  float* logits;                // dense [N, out_H, out_W, C]
+  float* softmax;               // dense [N, out_H, out_W, C]
+  long long* argmax;            // dense [N, out_H, out_W]
+  unsigned long long* conf;     // [C, C] confusion matrix, conf[label * C + prediction] += 1
+  int num_classes;
+  float gscale;                 // dz = (softmax - y) * gscale
 };
 constexpr float kRzBiasPerMma = 2.1e-8f;
 
@@ -182,21 +214,20 @@ __device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
 template <bool TF32>
 __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
                                                int ncols, size_t dense_idx, bool valid, float* colsum_s, int lane,
-                                               uint32_t seed) {
+                                               uint32_t seed, float acc_scale, size_t pool_idx = 0,
+                                               bool pool_writer = false) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * g.acc_scale;
-  if (!valid) {  // rows outside the tensor take part only in the (warp-collective) column sums, as zeros
-    if (g.flags & EPI_COLSUM) {
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * acc_scale;
+  const int wide = g.flags & (EPI_COLSUM | EPI_POOL);   // warp-collective parts: every lane must come along
+  if (!valid) {
+    // rows outside the tensor take part only in the warp-collective column sums / pooling, as zeros
+    if (!wide) return;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = 0.f;
-      const float cs = warp_colsum32(f, lane);
-      atomicAdd(&colsum_s[c0 + lane], cs);
-    }
-    return;
+    for (int i = 0; i < 32; ++i) f[i] = 0.f;
   }
-  if (g.flags & EPI_BIAS) {
+  if (valid && (g.flags & EPI_BIAS)) {
     const float4* b4 = reinterpret_cast<const float4*>(g.bias + c0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -207,7 +238,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
       f[4 * i + 3] += b.w;
     }
   }
-  if ((g.flags & EPI_RESIDUAL) && !(g.flags & EPI_DBG_NOLOAD)) {
+  if (valid && (g.flags & EPI_RESIDUAL) && !(g.flags & EPI_DBG_NOLOAD)) {
     const OutT* r = reinterpret_cast<const OutT*>(g.residual) + idx;
     if constexpr (TF32) {
       const float4* r4 = reinterpret_cast<const float4*>(r);
@@ -257,7 +288,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     for (int i = 0; i < 32; ++i)
       f[i] = dropout_keep(seed, static_cast<uint64_t>(dense_idx) + i, g.keep_threshold) ? f[i] * g.inv_keep : 0.f;
   }
-  if ((g.flags & EPI_MASK) && !(g.flags & EPI_DBG_NOLOAD)) {
+  if (valid && (g.flags & EPI_MASK) && !(g.flags & EPI_DBG_NOLOAD)) {
     const OutT* m = reinterpret_cast<const OutT*>(g.mask_src) + idx;
     if constexpr (TF32) {
       const float4* m4 = reinterpret_cast<const float4*>(m);
@@ -288,7 +319,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
   if (g.flags & EPI_COLSUM) {
     float t[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) t[i] = f[i];
+    for (int i = 0; i < 32; ++i) t[i] = valid ? f[i] : 0.f;
     const float cs = warp_colsum32(t, lane);
     atomicAdd(&colsum_s[c0 + lane], cs);
   }
@@ -296,10 +327,11 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     float keep = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) keep += f[i];
-    if (keep == 123.456f) *reinterpret_cast<float*>(o) = keep;   // keeps the math alive
+    if (valid && keep == 123.456f) *reinterpret_cast<float*>(o) = keep;   // keeps the math alive
     return;
   }
   if constexpr (TF32) {
+    if (!valid) return;
     if (g.flags & EPI_ROUND_TF32) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = round_tf32(f[i]);
@@ -309,20 +341,174 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
     for (int i = 0; i < 8; ++i)
       if (4 * i < ncols) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   } else {
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-    uint32_t hi[16];
+    uint32_t hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) hi[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
     if (g.out_lo) {
-      uint4* l4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.out_lo) + idx);
-      uint32_t lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[i]));
         lo[i] = pack_bf16x2(f[2 * i] - h.x, f[2 * i + 1] - h.y);
       }
+    }
+    if (valid && g.out) {   // (out == nullptr: inference with a fused pool keeps only the pooled tensor)
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+      if (g.out_lo) {
+        uint4* l4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.out_lo) + idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+      }
+    }
+    if (g.flags & EPI_POOL) {
+      // 2x2 max over the STORED values (hi, or hi + lo for pairs: exactly what a stand-alone pool of the stored tensor
+      // would see); the window's other three pixels are lanes ^1 (x) and ^8 (y) of this warp (tile row = y*8 + x)
+      float m[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[i]));
+        if (g.out_lo) {
+          const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo[i]));
+          h.x += l.x;
+          h.y += l.y;
+        }
+        m[2 * i] = h.x;
+        m[2 * i + 1] = h.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 1));
+        m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 8));
+      }
+      if (pool_writer) {
+        uint32_t ph[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ph[i] = pack_bf16x2(m[2 * i], m[2 * i + 1]);
+        uint4* p4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.pool_out) + pool_idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p4[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+        if (g.pool_out_lo) {
+          uint32_t pl[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ph[i]));
+            pl[i] = pack_bf16x2(m[2 * i] - h.x, m[2 * i + 1] - h.y);
+          }
+          uint4* q4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.pool_out_lo) + pool_idx);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) q4[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Loss / predictor epilogue of the upscore8 phase GEMM (EPI = 1): the thread's TMEM row is one 8 x 8 output block, the
+// tile's 256 columns are row dy = `dy` of that block (8 pixels x 32 padded classes), this warp handles pixels
+// dx = 4*chalf .. 4*chalf+3.  Per pixel: logits = acc * scale + bias  ->  softmax-CE (fcn8s_tensorflow.py:253), its
+// gradient, softmax / argmax (:268-269), confusion-matrix update (:280-301) -- whichever outputs are requested.
+// The loss gradient follows TensorFlow's fused op: backprop = softmax - labels (NOT softmax * sum(labels) - labels; the
+// two agree for one-hot labels, which is all the reference's generators produce).
+struct LossAcc {
+  float loss;
+  float db[32];
+};
+__device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const uint32_t (&v)[32], float acc_scale,
+                                                    const float* bias, int n, int oy, int ox, size_t pad_idx,
+                                                    LossAcc& acc, unsigned int* hist) {
+  const int C = g.num_classes;
+  float z[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) z[c] = (c < C) ? __uint_as_float(v[c]) * acc_scale + bias[c] : -INFINITY;
+  const size_t p = (static_cast<size_t>(n) * g.out_H + oy) * g.out_W + ox;
+  if (g.logits) {
+    float* dst = g.logits + p * C;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) dst[c] = z[c];
+  }
+  float mx = z[0];
+  int am = 0;
+#pragma unroll
+  for (int c = 1; c < 32; ++c)
+    if (c < C && z[c] > mx) {
+      mx = z[c];
+      am = c;
+    }
+  if (g.argmax) g.argmax[p] = am;
+  if (!(g.labels || g.softmax)) return;
+  float e[32];
+  float se = 0.f;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    e[c] = (c < C) ? __expf(z[c] - mx) : 0.f;
+    se += e[c];
+  }
+  const float inv = 1.f / se;
+  if (g.softmax) {
+    float* dst = g.softmax + p * C;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) dst[c] = e[c] * inv;
+  }
+  if (!g.labels) return;
+  const uint8_t* lp = g.labels + p * C;
+  float yv[32];
+  if ((C & 3) == 0) {   // the pixel's C label bytes are 4-byte aligned
+    const uint32_t* l4 = reinterpret_cast<const uint32_t*>(lp);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const uint32_t w = (4 * m < C) ? __ldg(l4 + m) : 0u;
+      yv[4 * m] = static_cast<float>(w & 0xffu);
+      yv[4 * m + 1] = static_cast<float>((w >> 8) & 0xffu);
+      yv[4 * m + 2] = static_cast<float>((w >> 16) & 0xffu);
+      yv[4 * m + 3] = static_cast<float>(w >> 24);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) yv[c] = (c < C) ? static_cast<float>(__ldg(lp + c)) : 0.f;
+  }
+  if (g.loss_sum) {
+    const float lse = mx + __logf(se);
+    float ysum = 0.f, yz = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) {
+        ysum += yv[c];
+        yz += yv[c] * z[c];
+      }
+    acc.loss += ysum * lse - yz;
+  }
+  if (g.conf) {   // labels_argmax (first maximum), fcn8s_tensorflow.py:280
+    int gt = 0;
+    float best = yv[0];
+#pragma unroll
+    for (int c = 1; c < 32; ++c)
+      if (c < C && yv[c] > best) {
+        best = yv[c];
+        gt = c;
+      }
+    atomicAdd(&hist[gt * C + am], 1u);
+  }
+  if (g.dz_hi) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float d0 = (c < C) ? (e[c] * inv - yv[c]) * g.gscale : 0.f;
+      const float d1 = (c + 1 < C) ? (e[c + 1] * inv - yv[c + 1]) * g.gscale : 0.f;
+      acc.db[c] += d0;
+      acc.db[c + 1] += d1;
+      hi[c >> 1] = pack_bf16x2(d0, d1);
+      const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[c >> 1]));
+      lo[c >> 1] = pack_bf16x2(d0 - h.x, d1 - h.y);
+    }
+    uint4* h4 = reinterpret_cast<uint4*>(g.dz_hi + pad_idx);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+    if (g.dz_lo) {
+      uint4* l4 = reinterpret_cast<uint4*>(g.dz_lo + pad_idx);
 #pragma unroll
       for (int i = 0; i < 4; ++i) l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
     }
@@ -330,12 +516,14 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Epilogue warps (4 warps, one TMEM lane quarter each) of the implicit-GEMM convolution kernels: persistent loop over
-// the CTA's tiles, TMEM -> registers -> epilogue math -> global.
+// Epilogue warps (8 warps: two per TMEM lane quarter, each takes half of the tile's columns) of the implicit-GEMM
+// convolution kernels: persistent loop over the CTA's tiles, TMEM -> registers -> epilogue math -> global.
 // PAIR (CTA pairs, see GemmCfg): `total_tiles` / `m_tiles` count PAIRS of M tiles, CTA `rank` of the pair owns M tile
 // 2 * pair + rank (a partner past the last tile computes on zero-filled operands and stores nothing), and the
 // accumulator is handed back on the leader CTA's barrier.
-template <int BN, bool TF32, bool PAIR = false>
+// EPI = 1: the loss / predictor epilogue above instead of the generic one (BN = 256 only); `colsum_s` then holds
+// [0] the CTA's loss sum, [32..64) its class sums of dz, [64..64 + C*C) its confusion-matrix histogram.
+template <int BN, bool TF32, bool PAIR = false, int EPI = 0>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
                                                    uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
                                                    int warp, int lane, uint32_t rank = 0) {
@@ -348,6 +536,15 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
     const uint32_t seed = g.seed_ptr ? (__ldg(g.seed_ptr) * 2u + g.seed) : g.seed;
     const uint32_t lead_acc_empty = PAIR ? map_to_cta(smem_u32(acc_empty), 0) : 0;
     const int t_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const int kb_per_seg = g.taps * g.cblocks;
+    const int total_kb = g.nseg * kb_per_seg;
+    const int kb_hi0 = total_kb - kb_per_seg;   // the hi*hi segment is the last one
+    LossAcc lacc;
+    if constexpr (EPI == 1) {
+      lacc.loss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) lacc.db[c] = 0.f;
+    }
     for (int t = PAIR ? blockIdx.x >> 1 : blockIdx.x; t < total_tiles; t += t_step) {
       const int nb = t % g.tiles_n;
       const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
@@ -362,6 +559,9 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
       const size_t pix = (static_cast<size_t>(n) * g.H + y) * g.W + x;
       const size_t row_off = static_cast<size_t>(n) * g.osN + static_cast<size_t>(y) * g.osH +
                              static_cast<size_t>(x) * g.osW;
+      const int kb0 = sp * g.kb_per_split;
+      const int kb1 = min(total_kb, kb0 + g.kb_per_split);
+      const float acc_scale = g.acc_scale * (1.f + g.rz_c * static_cast<float>(max(0, kb1 - max(kb0, kb_hi0))));
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -382,24 +582,50 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
           }
         }
         const int c0 = nb * BN + c;
-        if (g.flags & EPI_PARTIAL) {
+        if constexpr (EPI == 1) {
+          // block (y, x) of image n, block row dy = nb, pixel dx = c / 32 of the row
+          const int dx = c >> 5;
+          const int oy = 8 * y - 4 + nb, ox = 8 * x - 4 + dx;
+          if (valid && oy >= 0 && oy < g.out_H && ox >= 0 && ox < g.out_W) {
+            const size_t pad_idx = ((static_cast<size_t>(n) * (8 * g.H) + 8 * y + nb) * (8 * g.W) + 8 * x + dx) * 32;
+            loss_epilogue_pixel(g, v, acc_scale, g.bias, n, oy, ox, pad_idx, lacc,
+                                reinterpret_cast<unsigned int*>(colsum_s) + 64);
+          }
+        } else if (g.flags & EPI_PARTIAL) {
           if (valid) {
             const size_t idx = pix * g.ldc + c0;
             float4* o4 = reinterpret_cast<float4*>(g.partial + static_cast<size_t>(sp) * out_elems + idx);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              o4[i] = make_float4(__uint_as_float(v[4 * i]) * g.acc_scale, __uint_as_float(v[4 * i + 1]) * g.acc_scale,
-                                  __uint_as_float(v[4 * i + 2]) * g.acc_scale,
-                                  __uint_as_float(v[4 * i + 3]) * g.acc_scale);
+              o4[i] = make_float4(__uint_as_float(v[4 * i]) * acc_scale, __uint_as_float(v[4 * i + 1]) * acc_scale,
+                                  __uint_as_float(v[4 * i + 2]) * acc_scale,
+                                  __uint_as_float(v[4 * i + 3]) * acc_scale);
           }
         } else {
           size_t idx = row_off + c0;
-          if (g.out_mode) {
+          bool vrow = valid;
+          if (g.out_mode == 1) {
             const int bdy = c0 / g.blk_row;
             idx = row_off + static_cast<size_t>(bdy) * g.os_dy + (c0 - bdy * g.blk_row);
+          } else if (g.out_mode == 2) {
+            const int q = c0 / g.blk_cp;
+            const int bdy = q / g.blk_s, bdx = q - bdy * g.blk_s;
+            const int oy = g.blk_s * y - (g.blk_s >> 1) + bdy, ox = g.blk_s * x - (g.blk_s >> 1) + bdx;
+            vrow = valid && oy >= 0 && oy < g.out_H && ox >= 0 && ox < g.out_W;
+            idx = static_cast<size_t>(n) * g.osN + static_cast<size_t>(oy) * g.osH + static_cast<size_t>(ox) * g.osW +
+                  (c0 - q * g.blk_cp);
           }
           const int ncols = g.store_cols > 0 ? min(32, g.store_cols - c0) : 32;
-          if (ncols > 0) epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, valid, colsum_s, lane, seed);
+          size_t pool_idx = 0;
+          bool pool_writer = false;
+          if (g.flags & EPI_POOL) {
+            pool_writer = valid && !(lane & 9);   // even x, even y of the 8 x 16 tile: the window's top-left pixel
+            pool_idx = static_cast<size_t>(n) * g.psN + static_cast<size_t>(y >> 1) * g.psH +
+                       static_cast<size_t>(x >> 1) * g.psW + c0;
+          }
+          if (ncols > 0)
+            epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, vrow, colsum_s, lane, seed, acc_scale,
+                                 pool_idx, pool_writer);
         }
       }
       if (++as == 2) {
@@ -407,14 +633,31 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
         aphase ^= 1;
       }
     }
+    if constexpr (EPI == 1) {
+      // CTA-level reduction of the loss and the class sums of dz (flushed to global memory by the kernel's tail)
+      if (g.loss_sum) {
+        float l = lacc.loss;
+        for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+        if (lane == 0) atomicAdd(&colsum_s[0], l);
+      }
+      if (g.dz_hi && g.dbias) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float a = lacc.db[c];
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0 && c < g.num_classes) atomicAdd(&colsum_s[32 + c], a);
+        }
+      }
+    }
   }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN, bool TF32, bool PAIR = false>
+template <int BN, bool TF32, bool PAIR = false, int EPI = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
   pdl_launch_dependents();
   static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
+  static_assert(EPI == 0 || (!TF32 && BN == 256), "loss epilogue: bf16 operands, one block row per 256-column tile");
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
   extern __shared__ uint8_t smem_raw[];
@@ -429,8 +672,11 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (g.flags & EPI_COLSUM)
+  if (EPI == 1) {
+    for (int c = threadIdx.x; c < 64 + 32 * 32; c += kGemmThreads) colsum_s[c] = 0.f;   // loss, dz class sums, histogram
+  } else if (g.flags & EPI_COLSUM) {
     for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
+  }
 
   // scheduling units: M tiles, or (PAIR) pairs of consecutive M tiles, one per CTA of the cluster
   const uint32_t rank = PAIR ? cluster_ctarank() : 0;
@@ -642,8 +888,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
   } else if (warp >= 2) {
     // ============================== epilogue ==============================
-    conv_epilogue_loop<BN, TF32, PAIR>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane,
-                                       rank);
+    conv_epilogue_loop<BN, TF32, PAIR, EPI>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp,
+                                            lane, rank);
   }
 
   tc_fence_before();
@@ -656,11 +902,21 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     else
       tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
-  if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL))
-    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {
+  if (EPI == 1) {
+    if (threadIdx.x == 0 && g.loss_sum) atomicAdd(g.loss_sum, colsum_s[0]);
+    if (threadIdx.x < g.num_classes && g.dz_hi && g.dbias) atomicAdd(g.dbias + threadIdx.x, colsum_s[32 + threadIdx.x]);
+    if (g.conf) {
+      const unsigned int* hist = reinterpret_cast<const unsigned int*>(colsum_s) + 64;
+      for (int c = threadIdx.x; c < g.num_classes * g.num_classes; c += kGemmThreads)
+        if (hist[c]) atomicAdd(g.conf + c, static_cast<unsigned long long>(hist[c]));
+    }
+  } else if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL)) {
+    const int ncs = g.colsum_n > 0 ? min(g.colsum_n, g.tiles_n * BN) : g.tiles_n * BN;
+    for (int c = threadIdx.x; c < ncs; c += kGemmThreads) {
       const float t = colsum_s[c];
       if (t != 0.f) atomicAdd(g.colsum + c, t);
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -904,11 +1160,13 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
   }
-  if (g.flags & EPI_COLSUM)
-    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) {
+  if (g.flags & EPI_COLSUM) {
+    const int ncs = g.colsum_n > 0 ? min(g.colsum_n, g.tiles_n * BN) : g.tiles_n * BN;
+    for (int c = threadIdx.x; c < ncs; c += kGemmThreads) {
       const float t = colsum_s[c];
       if (t != 0.f) atomicAdd(g.colsum + c, t);
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -566,7 +566,8 @@ cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n
   return cudaGetLastError();
 }
 
-// wgrad: out[r][c] = sum_s partial[s][r][c] for r < rows_valid (partial has rows_pad rows per split).
+// wgrad: out[r][c] = scale * sum_s partial[s][r][c] for r < rows_valid, c < out_cols (partial has rows_pad rows of ldc
+// columns per split; out is [rows_valid][out_cols]).
 __global__ void wgrad_splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
                                            size_t rows_pad, int rows_valid, int ldc) {
   pdl_launch_dependents();
@@ -622,8 +623,30 @@ wgrad_splitk_reduce_wide_kernel(const float* __restrict__ partial, float* __rest
     reinterpret_cast<float4*>(out)[i] = a;
   }
 }
+// Column-clipped / scaled variant (score heads: 64 padded class columns -> out [rows][out_cols], scale = the skip
+// scale): one thread per output element, splits summed in order.
+__global__ void wgrad_splitk_reduce_clip_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
+                                                size_t rows_pad, int rows_valid, int ldc, int out_cols, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t n = static_cast<size_t>(rows_valid) * out_cols;
+  const size_t split_stride = rows_pad * ldc;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t r = i / out_cols;
+    const int c = static_cast<int>(i - r * out_cols);
+    float a = 0.f;
+    for (int s = 0; s < splits; ++s) a += partial[s * split_stride + r * ldc + c];
+    out[i] = a * scale;
+  }
+}
 cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
-                                       int ldc, cudaStream_t st) {
+                                       int ldc, int out_cols, float scale, cudaStream_t st) {
+  if (out_cols != ldc || scale != 1.f) {
+    const size_t n = static_cast<size_t>(rows_valid) * out_cols;
+    { (void)launch_k(wgrad_splitk_reduce_clip_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, partial, out, splits, rows_pad, rows_valid, ldc, out_cols, scale); }
+    return cudaGetLastError();
+  }
   const size_t n4 = static_cast<size_t>(rows_valid) * ldc / 4;
   if (splits >= 16 && n4 <= static_cast<size_t>(148) * 256 * 2) {
     { (void)launch_k(wgrad_splitk_reduce_wide_kernel, dim3(static_cast<unsigned>((n4 + 31) / 32)), dim3(256), 0, st, partial, out, splits, rows_pad, rows_valid, ldc); }

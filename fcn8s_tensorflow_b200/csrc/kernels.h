@@ -56,7 +56,7 @@ cudaError_t launch_split_tf32(const float* x, float* hi, float* lo, size_t n, cu
 cudaError_t launch_conv_splitk_reduce(const float* partial, int splits, size_t n_elems, int ldc,
                                       const ConvGemmArgs& g, int dtype, cudaStream_t st);
 cudaError_t launch_wgrad_splitk_reduce(const float* partial, float* out, int splits, size_t rows_pad, int rows_valid,
-                                       int ldc, cudaStream_t st);
+                                       int ldc, int out_cols, float scale, cudaStream_t st);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, size_t n, float lr_t, float b1, float b2,
                         float eps, float gscale, void* w_hi, void* w_lo, const float* lr_ptr, const void* g16,
                         cudaStream_t st);
@@ -66,28 +66,11 @@ cudaError_t launch_shadow(const float* p, void* hi, void* lo, size_t n, cudaStre
 cudaError_t launch_l2_reg(const float* w, float* g, float* loss, size_t n, float rate, cudaStream_t st);
 
 // decoder.cu
-int head_fwd_slices(long long P, int Cin);
-cudaError_t launch_head_fwd(const void* x, const float* K, const float* b, float* s, long long P, int Cin, int C,
-                            float scale, int dtype, float* ws, cudaStream_t st);
-int head_bwd_blocks(long long P);
-cudaError_t launch_head_bwd(const void* x, const float* K, const float* ds, float* dK, float* db, void* dx,
-                            long long P, int Cin, int C, float scale, int dtype, int mask, float mask_scale, float* ws,
-                            cudaStream_t st);
-cudaError_t launch_upscore_fwd(const float* x, const float* T, const float* bias, const float* skip, float* y, int N,
-                               int h, int w, int C, int s, cudaStream_t st);
-size_t upscore_bwd_ws_floats(int N, int h, int w, int C, int s);
-cudaError_t launch_upscore_bwd(const float* x, const float* T, const float* dy, float* dx, float* dT, float* dbias,
-                               int N, int h, int w, int C, int s, float* ws, cudaStream_t st);
-cudaError_t launch_softmax_xent(const float* z, const uint8_t* labels, float* loss_sum, float* dz, float* dbias,
-                                float* sm, long long* amax, int N, int H, int W, int C, int CP, int pad, float gscale,
-                                cudaStream_t st);
-cudaError_t launch_upscore_pack(const float* T, const float* bias, float* w_fwd, float* w_fwd_lo, float* w_dx,
-                                float* w_dx_lo, float* bias_big, int C, int CP, int s, cudaStream_t st);
-cudaError_t launch_upscore_gather(const float* zp, const float* skip, float* f, int N, int H, int W, int C, int CP,
-                                  int pad, int ldf, int ld_skip, cudaStream_t st);
-cudaError_t launch_upscore_scatter(const float* g, float* dzp, float* db, int N, int H, int W, int C, int CP, int pad,
-                                   int ldg, cudaStream_t st);
-cudaError_t launch_upscore_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st);
+cudaError_t launch_deconv_pack(const float* T, const float* bias, void* w_fwd, void* w_fwd_lo, void* w_dx, void* w_dx_lo,
+                               float* bias_big, int C, int CP, int s, cudaStream_t st);
+cudaError_t launch_head_pack(const float* K, const float* bias, int Cin, int C, void* w_hi, void* w_lo, float* bias64,
+                             cudaStream_t st);
+cudaError_t launch_deconv_unpack_dw(const float* src, int nsplit, float* dT, int C, int CP, int s, cudaStream_t st);
 cudaError_t launch_confusion(const long long* pred, const uint8_t* onehot, unsigned long long* conf, long long P, int C,
                              cudaStream_t st);
 

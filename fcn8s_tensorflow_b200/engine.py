@@ -7,7 +7,9 @@ the stream; every arithmetic operation is a hand-written sm_100a kernel reached 
 (include/fcn8s_b200.h).  There is no CPU path: constructing an Engine without a CUDA device or without the built
 library raises.
 
-Precision modes: see `Engine`.  The decoder (score heads, transposed convs, loss) is fp32 in every mode.
+Precision modes: see `Engine`.  The decoder (score heads, transposed convolutions) runs on the same tcgen05 GEMM
+kernels over bf16 hi / lo planes; the skip adds, the softmax-cross-entropy, its gradient, softmax / argmax and the
+confusion matrix live in the epilogues of the transposed-convolution kernels that precede them.
 """
 import functools
 import os
@@ -25,6 +27,9 @@ BETA1, BETA2, EPS = 0.9, 0.999, 1e-8           # tf.train.AdamOptimizer defaults
 # (packed-operand key, TF variable scope, stride) of upscore2 / upscore_pool4 / upscore8 (fcn8s_tensorflow.py:204-233)
 UPSCORE_STAGES = [("up2", "fc7_conv2d_trans", 2), ("up4", "fc7_pool4_conv2d_trans", 2),
                   ("up8", "fc7_pool4_pool3_conv2d_trans", 8)]
+# (packed-operand key, TF variable scope, encoder tensor, input channels, skip scale) of the 1x1 score heads (:171-200)
+HEADS = [("h3", "pool3_1x1", "pool3", 256, POOL3_SCALE), ("h4", "pool4_1x1", "pool4", 512, POOL4_SCALE),
+         ("h7", "fc7_1x1", "fc7", 4096, 1.0)]
 DECODER_KERNELS = ["pool3_1x1/kernel", "pool4_1x1/kernel", "fc7_1x1/kernel", "fc7_conv2d_trans/kernel",
                    "fc7_pool4_conv2d_trans/kernel", "fc7_pool4_pool3_conv2d_trans/kernel"]
 
@@ -107,23 +112,21 @@ def _on_device(fn):
 
 
 class Engine:
-    """Precision modes (`precision=`), all with fp32 accumulation in TMEM, fp32 master weights / gradients / Adam:
+    """Precision modes (`precision=`), both with fp32 accumulation in TMEM, fp32 master weights / gradients / Adam:
 
-      "bf16"    activations + tensor-core operands bf16.
       "fp32"    fp32-equivalent: activations and weights are bf16 hi/lo PAIRS (FCN8_BF16X2: v ~ hi + lo, 16-17
-                mantissa bits) and every GEMM forms the error-compensated hi*hi + hi*lo + lo*hi on the bf16 tensor
-                cores (3 MMAs per product at the bf16 rate = half the cost of 3xTF32).  Meets the 1e-4 logit tolerance.
-      "tf32x3"  fp32 activations, 3xTF32 error-compensated products (kind::tf32, 6x the bf16 cost).
-      "tf32"    fp32 activations, single tf32 pass.
-    In "bf16" / "fp32" the GEMMs read a bf16 (hi/lo) shadow of the flat parameter buffer in its TF layout directly
-    (refreshed by the Adam kernel), so there is no per-step weight packing."""
+                mantissa bits) and every GEMM forms the error-compensated hi*lo + lo*hi + hi*hi on the bf16 tensor
+                cores (3 MMAs per product, the low-order products first).  Meets the 1e-4 logit tolerance.
+      "bf16"    activations + tensor-core operands bf16, one MMA per product.
+    The GEMMs read a bf16 (hi/lo) shadow of the flat parameter buffer in its TF layout directly (refreshed by the Adam
+    kernel), so there is no per-step weight packing of the encoder."""
 
-    MODES = ("bf16", "fp32", "tf32x3", "tf32")
+    MODES = ("bf16", "fp32")
 
     def __init__(self, num_classes, precision="bf16", device=None, backward_terms=3, grad_comm=None):
         """backward_terms (precision "fp32" only): bf16 products per algorithmic product in the BACKWARD GEMMs (dgrad and
-        filter gradients of the encoder): 3 = hi*hi + hi*lo + lo*hi like the forward pass (default); 2 / 1 are the
-        measured, non-default "fp32 forward / reduced backward" modes (one operand, or both, rounded to bf16).
+        filter gradients): 3 = like the forward pass (default); 2 / 1 are the measured, non-default "fp32 forward /
+        reduced backward" modes (one operand, or both, rounded to bf16).
         grad_comm: wire format of the data-parallel gradient all-reduce, "fp32" or "bf16" (default: bf16 in the bf16
         precision mode, fp32 otherwise)."""
         if not torch.cuda.is_available():
@@ -139,23 +142,22 @@ class Engine:
         capi.check(self.lib.fcn8_device_check(self.device.index))
         if backward_terms not in (1, 2, 3):
             raise ValueError("backward_terms must be 1, 2 or 3")
-        self.bt = int(backward_terms) if precision == "fp32" else 3
+        self.C = num_classes
+        self.precision = precision
+        self.pair = precision == "fp32"                      # bf16 hi/lo pair activations
+        self.nseg = 3 if self.pair else 1                    # MMAs per product, forward
+        self.bt = int(backward_terms) if self.pair else 1    # MMAs per product, backward
         self.grad_comm = grad_comm or os.environ.get("FCN8_GRAD_COMM") or ("bf16" if precision == "bf16" else "fp32")
         if self.grad_comm not in ("fp32", "bf16"):
             raise ValueError("grad_comm must be 'fp32' or 'bf16'")
         self.rank = 0
         self.g16 = None          # bf16 wire copy of the flat gradient (allocated by dist.attach when grad_comm == bf16)
-        self.C = num_classes
-        self.precision = precision
-        self.pair = precision == "fp32"                      # bf16 hi/lo pair activations
-        self.hwio = precision in ("bf16", "fp32")            # GEMMs read the TF-layout weight shadow
-        self.x3 = precision == "tf32x3"                      # legacy 3xTF32 encoder products
-        self.dec3 = precision in ("fp32", "tf32x3")          # 3xTF32 in the (fp32) decoder GEMMs
-        self.dt = ops.BF16 if self.hwio else ops.F32         # tensor-core operand type of the encoder
-        self.tdt = torch.bfloat16 if self.hwio else torch.float32
+        self.dt = ops.BF16
+        self.tdt = torch.bfloat16
         self.cm = 2 if self.pair else 1                      # stored channels per logical channel
-        self.kp = 64 if self.hwio else 32                    # padded im2col width of conv1_1
-        self.rnd = ops.EPI_ROUND_TF32 if precision == "tf32" else 0
+        self.kp = 64                                         # padded im2col width of conv1_1
+        self.conv_algo = int(os.environ.get("FCN8_CONV_ALGO", "0"))   # diagnostics: 1 = per-tap kernels only
+        self.fuse_pool = os.environ.get("FCN8_FUSE_POOL", "1") != "0"
         self.layers = encoder_layers()
         self.layout, self.n_flat = flat_layout(num_classes)
         self.bias_block = self.layout["fc7/biases"][0]       # encoder biases: [bias_block, n_flat)
@@ -164,7 +166,7 @@ class Engine:
         self.grads = torch.zeros(self.n_flat, **z)
         self.adam_m = torch.zeros(self.n_flat, **z)
         self.adam_v = torch.zeros(self.n_flat, **z)
-        self.w_hi = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=self.device) if self.hwio else None
+        self.w_hi = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=self.device)
         self.w_lo = torch.zeros(self.n_flat, dtype=torch.bfloat16, device=self.device) if self.pair else None
         self.global_step = 0
         self.loss_buf = torch.zeros(2, **z)   # [0] = sum of per-pixel CE, [1] = L2 regularisation loss
@@ -213,27 +215,22 @@ class Engine:
 
     @_on_device
     def repack(self):
-        """Derived tensor-core operands of the parameters.  hwio modes: only conv1_1 (27 -> 64 im2col columns) and the
-        upscore8 phase-GEMM operands are packed (the rest is the shadow written by Adam); legacy tf32 modes: fprop and
-        dgrad operand copies of every encoder layer."""
-        if self.hwio and self._shadow_dirty:
+        """Derived tensor-core operands of the parameters: the encoder reads the bf16 shadow written by Adam; only conv1_1
+        (27 -> 64 im2col columns), the three score heads (classes padded to 64 columns) and the phase-GEMM operands
+        of the three transposed convolutions -- 0.2 % of the parameters -- are packed."""
+        if self._shadow_dirty:
             ops.shadow_weights(self.params, self.w_hi, self.w_lo)
             self._shadow_dirty = False
-        for name, k, cin, cout in self.layers:
-            w = self.view(_wname(name))
-            old = self.packed.get(name)   # refilled in place: a captured CUDA graph keeps reading the same buffers
-            if name == "conv1_1":
-                # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
-                self.packed[name] = ops.pack_weights(w, 1, 27, cout, 0, self.dt, cin_pad=self.kp,
-                                                     split=self.x3 or self.pair,
-                                                     out=old[0:2] if old else None) + (None, None)
-            elif not self.hwio:
-                f = ops.pack_weights(w, k, cin, cout, 0, self.dt, split=self.x3, out=old[0:2] if old else None)
-                d = ops.pack_weights(w, k, cin, cout, 1, self.dt, split=self.x3, out=old[2:4] if old else None)
-                self.packed[name] = f + d
-        for key, base, stride in UPSCORE_STAGES:   # phase-GEMM operands of the three transposed convolutions
-            self.packed[key] = ops.upscore_tc_pack(self.view(base + "/kernel"), self.view(base + "/bias"), stride,
-                                                   split=self.dec3, out=self.packed.get(key))
+        old = self.packed.get("conv1_1")   # refilled in place: a captured CUDA graph keeps reading the same buffers
+        # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
+        self.packed["conv1_1"] = ops.pack_weights(self.view("conv1_1/filter"), 1, 27, 64, 0, self.dt, cin_pad=self.kp,
+                                                  split=self.pair, out=old)
+        for key, base, _, cin, _ in HEADS:
+            self.packed[key] = ops.head_pack(self.view(base + "/kernel").view(cin, self.C), self.view(base + "/bias"),
+                                             split=self.pair, out=self.packed.get(key))
+        for key, base, stride in UPSCORE_STAGES:
+            self.packed[key] = ops.deconv_pack(self.view(base + "/kernel"), self.view(base + "/bias"), stride,
+                                               split=self.pair, out=self.packed.get(key))
         self._packed_dirty = False
 
     # ------------------------------------------------------------------ activation arena
@@ -248,10 +245,10 @@ class Engine:
             self._arenas[key] = a
         return a
 
-    def _buf(self, arena, name, shape, dtype):
+    def _buf(self, arena, name, shape, dtype, zero=False):
         t = arena.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
             arena[name] = t
         return t
 
@@ -259,40 +256,38 @@ class Engine:
         """Encoder activation buffer [N,h,w,c] in the mode's storage format ([N,h,w,2c] bf16 for hi/lo pairs)."""
         return self._buf(arena, name, (N, h, w, c * self.cm), self.tdt)
 
-    def _split(self, arena, name, x, force=False):
-        """3xTF32 operands of an fp32 tensor x: (x, lo) with lo = round_tf32(x - trunc_tf32(x)) in an arena buffer --
-        the tensor core truncates x to its tf32 high part by itself; (x, None) when the mode is single-pass."""
-        if not (self.x3 or force):
-            return x, None
-        lo = self._buf(arena, name + ".lo", x.shape, torch.float32)
-        capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), None, capi.ptr(lo), x.numel(), ops._stream()))
-        return x, lo
+    def _planes(self, arena, name, N, h, w):
+        """Decoder activation: a bf16 hi/lo pair tensor [N,h,w,128] (64 hi | 64 lo channels, classes zero-padded);
+        returns its (hi, lo) plane views."""
+        return ops.halves(self._buf(arena, name, (N, h, w, 128), torch.bfloat16), 64)
+
+    def _padded(self, arena, name, N, h, w, stride):
+        """Zero-bordered padded blocked gradient planes of a stride-s stage (allocated and zeroed once: the kernels
+        only ever write the interior and write zeros beyond the class count)."""
+        p = arena.get(name)
+        if p is None:
+            p = arena[name] = ops.padded_alloc(N, h, w, stride, self.device)
+        return p
 
     def _wview(self, name):
         """(hi, lo) bf16 shadow views of an encoder weight tensor in TF layout."""
         return self.view(_wname(name), self.w_hi), (self.view(_wname(name), self.w_lo) if self.pair else None)
 
-    def _conv(self, A, name, x, k, cin, cout, out, bias, flags, **kw):
+    def _conv(self, name, x, k, cout, out, bias, flags, **kw):
         """Encoder convolution of layer `name` (forward direction) in the mode's operand format."""
         if name == "conv1_1":
-            wp, wlo = self.packed[name][0], self.packed[name][1]
-            xl = self._split(A, "in_" + name, x)[1] if self.x3 else None
-            return ops.conv_gemm(x, wp, cout, 1, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo,
-                                 pair=self.pair, **kw)
-        if self.hwio:
-            wh, wl = self._wview(name)
-            return ops.conv_gemm(x, wh, cout, k, bias=bias, flags=flags, out=out, wp_lo=wl, pair=self.pair, w_mode=1,
-                                 **kw)
-        wp, wlo = self.packed[name][0], self.packed[name][1]
-        xl = self._split(A, "in_" + name, x)[1]
-        return ops.conv_gemm(x, wp, cout, k, bias=bias, flags=flags | self.rnd, out=out, x_lo=xl, wp_lo=wlo, **kw)
+            wp, wlo = self.packed[name]
+            return ops.conv_gemm(x, wp, cout, 1, bias=bias, flags=flags, out=out, wp_lo=wlo, pair=self.pair, **kw)
+        wh, wl = self._wview(name)
+        return ops.conv_gemm(x, wh, cout, k, bias=bias, flags=flags, out=out, wp_lo=wl, pair=self.pair, w_mode=1,
+                             algo=self.conv_algo, **kw)
 
     # ------------------------------------------------------------------ forward
-    @_on_device
-    def forward(self, images, keep_prob=1.0, seed=0, train=False, _scalars_set=False):
-        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (a view of an arena buffer).
-        The dropout seed is read by the kernels from `step_scalars` (set here unless the caller already did)."""
-        if self._packed_dirty or (self.hwio and self._shadow_dirty):
+    def _features(self, images, keep_prob, seed, train, _scalars_set=False):
+        """images -> f3 planes (the input of upscore8).  Everything below the loss / predictor: feed pre-processing,
+        VGG-16 encoder (the 2x2 max-pools in the epilogue of the convolution that precedes them), score heads,
+        upscore2 (+ pool4 skip) and upscore_pool4 (+ pool3 skip)."""
+        if self._packed_dirty or self._shadow_dirty:
             self.repack()
         if train and keep_prob < 1.0 and not _scalars_set:
             ops.set_step_scalars(self.step_scalars, 0.0, seed)
@@ -303,100 +298,63 @@ class Engine:
         x = self._act(A, "im2col", N, H, W, self.kp)
         p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, ops.BF16X2 if pair else self.dt)
         capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
-        if self.precision == "tf32":   # single-pass tf32: operands pre-rounded (the MMA truncates)
-            capi.check(self.lib.fcn8_split_tf32(capi.ptr(x), capi.ptr(x), None, x.numel(), ops._stream()))
         h, w = H, W
         li = 0
         for b, cout, n in VGG_BLOCKS:
             for i in range(1, n + 1):
                 name, k, cin, _ = self.layers[li]
                 li += 1
-                out = self._act(A, name, N, h, w, cout)
-                self._conv(A, name, x, k, cin, cout, out, self.view(name + "/biases"), ops.EPI_BIAS | ops.EPI_RELU)
+                kw = {}
+                pooled = None
+                if i == n and self.fuse_pool:
+                    # last conv of the block: its epilogue also emits the block's max-pool; the full-resolution tensor
+                    # is only stored when the backward pass will need it
+                    pooled = self._act(A, "pool%d" % b, N, h // 2, w // 2, cout)
+                    kw = dict(pool_out=pooled, store_out=train)
+                out = self._act(A, name, N, h, w, cout) if (train or pooled is None) else None
+                self._conv(name, x, k, cout, out, self.view(name + "/biases"), ops.EPI_BIAS | ops.EPI_RELU, **kw)
                 x = out
-            h, w = (h + 1) // 2, (w + 1) // 2
-            pooled = self._act(A, "pool%d" % b, N, h, w, cout)
-            ops.maxpool_fwd(x, out=pooled, pair=pair)
+            h, w = h // 2, w // 2
+            if not self.fuse_pool:
+                pooled = self._act(A, "pool%d" % b, N, h, w, cout)
+                ops.maxpool_fwd(x, out=pooled, pair=pair)
             x = pooled
         drop = train and keep_prob < 1.0
         for name, k, cin, cout in self.layers[-2:]:
             out = self._act(A, name, N, h, w, cout)
             flags = ops.EPI_BIAS | ops.EPI_RELU | (ops.EPI_DROPOUT if drop else 0)
-            self._conv(A, name, x, k, cin, cout, out, self.view(name + "/biases"), flags,
+            self._conv(name, x, k, cout, out, self.view(name + "/biases"), flags,
                        keep_prob=keep_prob if drop else 1.0, seed=1 if name == "fc7" else 0,
                        seed_ptr=self.step_scalars[1:2] if drop else None)
             x = out
+        # score heads (fcn8s_tensorflow.py:171-200): 1x1 convolutions with the class dimension padded to 64 columns, the
+        # 1e-4 / 1e-2 skip scales folded into the accumulator scale
+        S = {}
+        for key, base, src, cin, scale in HEADS:
+            t = A[src]
+            n_, hh, ww, _ = t.shape
+            S[key] = self._buf(A, "s_" + key, (n_, hh, ww, 128), torch.bfloat16)
+            pk = self.packed[key]
+            ops.conv_gemm(t, pk["w"], 64, 1, bias=pk["bias64"], flags=ops.EPI_BIAS, out=S[key], wp_lo=pk["w_lo"],
+                          pair=pair, out_pair=True, w_mode=1, out_scale=scale, nseg=self.nseg, tag="head_gemm")
         C = self.C
-        f32 = torch.float32
-        s3 = ops.score_head_fwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), self.view("pool3_1x1/bias"),
-                                POOL3_SCALE, out=self._buf(A, "s3", (N, H // 8, W // 8, C), f32), pair=pair)
-        s4 = ops.score_head_fwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), self.view("pool4_1x1/bias"),
-                                POOL4_SCALE, out=self._buf(A, "s4", (N, H // 16, W // 16, C), f32), pair=pair)
-        s7 = ops.score_head_fwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), self.view("fc7_1x1/bias"), 1.0,
-                                out=self._buf(A, "s7", (N, H // 32, W // 32, C), f32), pair=pair)
-        # the three transposed convolutions as tcgen05 phase GEMMs over padded blocked tensors; the skip adds
-        # (fcn8s_tensorflow.py:213,224) ride on the gather of the block interior
-        ld4 = (C + 3) // 4 * 4
-        f4 = self._buf(A, "f4", (N, H // 16, W // 16, ld4), f32)
-        self._upscore_stage_fwd(A, "up2", self._pad4(A, "s7p", s7), 2, skip=s4, out=f4)
-        f3 = self._buf(A, "f3", (N, H // 8, W // 8, ld4), f32)
-        self._upscore_stage_fwd(A, "up4", f4, 2, skip=s3, out=f3)
-        zp = self._upscore_stage_fwd(A, "up8", f3, 8)
-        A["logits_p"] = zp
-        A["logits"] = ops.upscore_tc_interior(zp, C, 8)
-        return A["logits"]
+        # upscore2 + pool4 skip, upscore_pool4 + pool3 skip (:204-224): the tf.add is the residual operand of the epilogue
+        f4 = self._planes(A, "f4", N, H // 16, W // 16)
+        ops.deconv_fwd(ops.halves(S["h7"], 64), self.packed["up2"], C, 2, f4, skip=ops.halves(S["h4"], 64),
+                       nseg=self.nseg)
+        f3 = self._planes(A, "f3", N, H // 8, W // 8)
+        ops.deconv_fwd(f4, self.packed["up4"], C, 2, f3, skip=ops.halves(S["h3"], 64), nseg=self.nseg)
+        return A, f3
 
-    def _upscore_stage_fwd(self, A, key, x, stride, skip=None, out=None):
-        """One transposed convolution: x [N,h,w,ld4] -> padded blocked A[key + "_p"]; with `out`, also the interior
-        (+ skip) as the next stage's dense input."""
-        N, h, w, _ = x.shape
-        zp = A.get(key + "_p")
-        if zp is None:
-            zp = A[key + "_p"] = ops.upscore_tc_alloc(N, h, w, self.C, stride, self.device)
-        x_lo = self._split(A, key + "_x", x, force=self.dec3)[1]
-        ops.upscore_tc_fwd(x, self.packed[key], self.C, stride, zp, x_lo=x_lo)
-        if out is not None:
-            ops.upscore_tc_gather(zp, skip, out, self.C, stride)
-        return zp
-
-    def _upscore_stage_bwd(self, A, key, base, x, g, stride, dzp=None):
-        """Backward of one transposed convolution: g = gradient of its (dense) output, or dzp already in the padded
-        blocked layout (upscore8: written by the loss kernel).  Fills dT / dbias in the flat gradient, returns dx."""
-        N, h, w, ld = x.shape
-        G = self.grads
-        if dzp is None:
-            dzp = A.get(key + "_dp")
-            if dzp is None:   # zero border / pad channels, never written again
-                dzp = A[key + "_dp"] = ops.upscore_tc_alloc(N, h, w, self.C, stride, self.device, zero=True)
-            db = self.view(base + "/bias", G)
-            db.zero_()
-            ops.upscore_tc_scatter(g, dzp, self.C, stride, dbias=db)
-        dz_lo = self._split(A, key + "_dp", dzp, force=self.dec3)[1]
-        ops.upscore_tc_dw(x, dzp, self.C, stride, self.view(base + "/kernel", G), x_lo=A.get(key + "_x.lo"),
-                          dzp_lo=dz_lo)
-        dx = self._buf(A, key + "_dx", x.shape, torch.float32)
-        ops.upscore_tc_dx(dzp, self.packed[key], self.C, stride, dx, dzp_lo=dz_lo)
-        return dx
-
-    def _dense(self, A, name, t):
-        """[..., ld4] -> dense [..., C] copy for the score-head kernels (a no-op view when C is a multiple of 4)."""
-        if t.shape[-1] == self.C:
-            return t
-        d = self._buf(A, name, tuple(t.shape[:-1]) + (self.C,), torch.float32)
-        d.copy_(t[..., :self.C])
-        return d
-
-    def _pad4(self, arena, name, t):
-        """[N,h,w,C] -> the same tensor with the channel stride rounded up to a multiple of 4 (zero filled): the layout
-        the TMA maps of the decoder GEMMs need. No-op (no copy) when C is already a multiple of 4."""
-        Cc = t.shape[-1]
-        if Cc % 4 == 0:
-            return t
-        buf = arena.get(name)
-        if buf is None:
-            buf = arena[name] = torch.zeros(tuple(t.shape[:-1]) + ((Cc + 3) // 4 * 4,), dtype=t.dtype, device=t.device)
-        buf[..., :Cc].copy_(t)
-        return buf
+    @_on_device
+    def forward(self, images, keep_prob=1.0, seed=0, train=False, _scalars_set=False):
+        """images: uint8 CUDA tensor [N,H,W,3] (RGB). Returns fp32 logits [N,H,W,C] (an arena buffer).
+        The dropout seed is read by the kernels from `step_scalars` (set here unless the caller already did)."""
+        N, H, W, _ = images.shape
+        A, f3 = self._features(images, keep_prob, seed, train, _scalars_set)
+        logits = self._buf(A, "logits", (N, H, W, self.C), torch.float32)
+        ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, logits=logits)
+        return logits
 
     @staticmethod
     def dropout_seed(seed, layer):
@@ -406,47 +364,62 @@ class Engine:
 
     # ------------------------------------------------------------------ loss + backward
     @_on_device
-    def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0, _scalars_set=False):
+    def loss_and_backward(self, images, labels, keep_prob=1.0, l2_rate=0.0, seed=0, _scalars_set=False,
+                          store_logits=True):
         """Forward + backward of optimizer/total_loss (fcn8s_tensorflow.py:250-257) into self.grads.
-        labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2)."""
+        labels: uint8/bool CUDA tensor [N,H,W,C] one-hot. Returns the device scalar pair loss_buf (CE sum, L2).
+        store_logits=False (the training step): the logits never leave the upscore8 kernel's epilogue."""
         N, H, W, _ = images.shape
         C = self.C
         pair = self.pair
-        self.forward(images, keep_prob, seed, train=True, _scalars_set=_scalars_set)
-        A = self._arena(N, H, W)
+        A, f3 = self._features(images, keep_prob, seed, True, _scalars_set)
         G = self.grads
-        f32 = torch.float32
+        bt = self.bt
         self.loss_buf.zero_()
         G[self.bias_block:].zero_()   # encoder bias gradients are accumulated by fused epilogues (atomics)
-        zp = A["logits_p"]
-        dzp = A.get("dlogits_p")
-        if dzp is None:   # zero border, never written again
-            dzp = A["dlogits_p"] = ops.upscore_tc_alloc(N, H // 8, W // 8, C, 8, self.device, zero=True)
-        npx = N * H * W
-        dc8 = self.view("fc7_pool4_pool3_conv2d_trans/bias", G)
-        dc8.zero_()
-        ops.softmax_xent(zp, labels.view(torch.uint8), self.loss_buf[0:1], dzp, grad_scale=1.0 / npx, dbias=dc8,
-                         pad=4, num_classes=C)
-        # decoder backward (SURVEY.md a12.1 / a12.2): three phase-GEMM stages; the skip adds fan the gradient out
-        df3p = self._upscore_stage_bwd(A, "up8", "fc7_pool4_pool3_conv2d_trans", A["f3"], None, 8, dzp=dzp)
-        df4p = self._upscore_stage_bwd(A, "up4", "fc7_pool4_conv2d_trans", A["f4"], df3p, 2)
-        ds7p = self._upscore_stage_bwd(A, "up2", "fc7_conv2d_trans", A["s7p"] if C % 4 else A["s7"], df4p, 2)
-        df3, df4, ds7 = self._dense(A, "df3", df3p), self._dense(A, "df4", df4p), self._dense(A, "ds7", ds7p)
+        gv = lambda n: self.view(n, G)   # noqa: E731
+        dc8, dc4, dc2, db7 = (gv("fc7_pool4_pool3_conv2d_trans/bias"), gv("fc7_pool4_conv2d_trans/bias"),
+                              gv("fc7_conv2d_trans/bias"), gv("fc7_1x1/bias"))
+        for t in (dc8, dc4, dc2, db7):
+            t.zero_()
+        # upscore8 + softmax-CE + its gradient in one kernel (:226-235, :253): dz goes straight into the padded blocked
+        # planes the gradient GEMMs read; dc8 = class sums of dz
+        dz8 = self._padded(A, "dz8", N, H // 8, W // 8, 8)
+        logits = self._buf(A, "logits", (N, H, W, C), torch.float32) if store_logits else None
+        ops.deconv_loss(f3, self.packed["up8"], C, nseg=self.nseg, labels=labels.view(torch.uint8),
+                        loss_sum=self.loss_buf[0:1], dz_out=dz8 if pair else (dz8[0], None), dbias=dc8,
+                        grad_scale=1.0 / (N * H * W), logits=logits)
+        # decoder backward (SURVEY.md a12.1 / a12.2): every stage's input gradient lands in the interior of the next
+        # stage's padded planes (the skip adds fan the gradient out unchanged: the same planes feed the score heads)
+        # and its column sums are the bias gradients of the two layers whose outputs were added there
+        dz4 = self._padded(A, "dz4", N, H // 16, W // 16, 2)      # gradient of f3 = output gradient of upscore_pool4
+        dz2 = self._padded(A, "dz2", N, H // 32, W // 32, 2)      # gradient of f4 = output gradient of upscore2
+        df3, df4 = ops.padded_interior(dz4, 2), ops.padded_interior(dz2, 2)
+        ds7 = self._planes(A, "ds7", N, H // 32, W // 32)
+        S = {k: ops.halves(A["s_" + k], 64) for k in ("h3", "h4", "h7")}
+        ops.deconv_dw(f3, dz8, C, 8, gv("fc7_pool4_pool3_conv2d_trans/kernel"), nseg=bt)
+        ops.deconv_dx(dz8, self.packed["up8"], C, 8, df3, nseg=bt, colsum=dc4)
+        ops.deconv_dw(self._planes(A, "f4", N, H // 16, W // 16), dz4, C, 2, gv("fc7_pool4_conv2d_trans/kernel"), nseg=bt)
+        ops.deconv_dx(dz4, self.packed["up4"], C, 2, df4, nseg=bt, colsum=dc2)
+        ops.deconv_dw(S["h7"], dz2, C, 2, gv("fc7_conv2d_trans/kernel"), nseg=bt)
+        ops.deconv_dx(dz2, self.packed["up2"], C, 2, ds7, nseg=bt, colsum=db7)
+        gv("pool3_1x1/bias").copy_(dc4)     # f3 = upscore_pool4(f4) + c4 + s3: both biases see the same gradient
+        gv("pool4_1x1/bias").copy_(dc2)
         inv_keep = 1.0 / keep_prob if keep_prob < 1.0 else 1.0
-        # score heads: ds3 = df3, ds4 = df4 (the adds fan the gradient out unchanged)
-        dpool3 = self._buf(A, "d_pool3_head", A["pool3"].shape, self.tdt)
-        ops.score_head_bwd(A["pool3"], self.view("pool3_1x1/kernel").view(256, C), df3, POOL3_SCALE,
-                           self.view("pool3_1x1/kernel", G).view(256, C), self.view("pool3_1x1/bias", G), dpool3,
-                           pair=pair)
-        dpool4 = self._buf(A, "d_pool4_head", A["pool4"].shape, self.tdt)
-        ops.score_head_bwd(A["pool4"], self.view("pool4_1x1/kernel").view(512, C), df4, POOL4_SCALE,
-                           self.view("pool4_1x1/kernel", G).view(512, C), self.view("pool4_1x1/bias", G), dpool4,
-                           pair=pair)
-        # fc7 output: dropout + ReLU backward folded into the head's dx (mask = fc7 > 0, scale 1/keep_prob)
-        dy = self._buf(A, "d_fc7", A["fc7"].shape, self.tdt)
-        ops.score_head_bwd(A["fc7"], self.view("fc7_1x1/kernel").view(4096, C), ds7, 1.0,
-                           self.view("fc7_1x1/kernel", G).view(4096, C), self.view("fc7_1x1/bias", G), dy,
-                           mask=True, mask_scale=inv_keep, pair=pair)
+        # score heads: dK = scale * x^T ds, dx = scale * ds K^T (for fc7 with its ReLU / dropout mask)
+        dhead = {}
+        for key, base, src, cin, scale in HEADS:
+            ds = {"h3": df3, "h4": df4, "h7": ds7}[key]
+            x = A[src]
+            pk = self.packed[key]
+            ops.wgrad_gemm(x, ds[0], 1, gv(base + "/kernel").view(cin, C), dy_lo=ds[1], pair=pair, dy_pair=False,
+                           nseg=bt, out_cols=C, out_scale=scale)
+            dx = self._buf(A, "d_%s_head" % src, x.shape, self.tdt)
+            mk = dict(flags=ops.EPI_MASK, mask_src=x, mask_scale=inv_keep) if key == "h7" else {}
+            ops.conv_gemm(ds[0], pk["w"], cin, 1, x_lo=ds[1] if bt == 3 else None, wp_lo=pk["w_lo"], w_mode=2, out=dx,
+                          out_pair=pair, out_scale=scale, nseg=bt, cin=64, tag="head_gemm", **mk)
+            dhead[src] = dx
+        dy = dhead["fc7"]
         if l2_rate != 0.0:
             for kname in DECODER_KERNELS:
                 ops.l2_reg(self.view(kname).reshape(-1), self.view(kname, G).reshape(-1), self.loss_buf[1:2], l2_rate)
@@ -457,13 +430,10 @@ class Engine:
             gw = self.view(_wname(name), G)
             if name == "fc7":   # every other bias gradient is fused into the kernel that produces that layer's dY
                 ops.bias_grad(dy, self.view(name + "/biases", G), pair=pair)
-            dyh, dyl = self._split(A, "dy_" + name, dy)
-            xl = A["in_%s.lo" % name] if self.x3 else None
             if name == "conv1_1":
-                ops.wgrad_gemm(x_in, dyh, 1, gw.view(27, cout), rows_valid=27, x_lo=xl, dy_lo=dyl, pair=pair,
-                               nseg=self.bt)
+                ops.wgrad_gemm(x_in, dy, 1, gw.view(27, cout), rows_valid=27, pair=pair, nseg=bt)
                 break
-            ops.wgrad_gemm(x_in, dyh, k, gw.view(k * k * cin, cout), x_lo=xl, dy_lo=dyl, pair=pair, nseg=self.bt)
+            ops.wgrad_gemm(x_in, dy, k, gw.view(k * k * cin, cout), pair=pair, nseg=bt)
             if name == "fc6" and self.allreduce is not None and getattr(self.allreduce, "overlap", False):
                 # decoder, fc7 and fc6 gradients (89 % of the buffer) are final: reduce them under the conv backward
                 self._start_reduce(0, self.head_elems)
@@ -473,19 +443,15 @@ class Engine:
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
             prev_db = self.view(prev_name + "/biases", G)
-            if self.hwio:
-                wh, wl = self._wview(name)
-                wkw = dict(wp_lo=wl, pair=pair, w_mode=2, nseg=self.bt)
-            else:
-                wh = self.packed[name][2]
-                wkw = dict(x_lo=dyl, wp_lo=self.packed[name][3])
+            wh, wl = self._wview(name)
+            wkw = dict(wp_lo=wl, pair=pair, w_mode=2, nseg=bt, algo=self.conv_algo)
             if self._input_is_pool(li):
                 # x_in is a pool output: no ReLU mask here (the pool backward applies it); add the score-head
                 # gradient at pool3 / pool4 (AddN of the two consumers)
                 pool_idx = self._pool_index(li)
-                res = dpool3 if pool_idx == 3 else (dpool4 if pool_idx == 4 else None)
-                ops.conv_gemm(dyh, wh, cin, k, flags=(ops.EPI_RESIDUAL if res is not None else 0) | self.rnd,
-                              residual=res, out=dx, **wkw)
+                res = dhead["pool3"] if pool_idx == 3 else (dhead["pool4"] if pool_idx == 4 else None)
+                ops.conv_gemm(dy, wh, cin, k, flags=(ops.EPI_RESIDUAL if res is not None else 0), residual=res, out=dx,
+                              **wkw)
                 src = A[prev_name]  # pre-pool activation (post-ReLU)
                 dpre = self._buf(A, "dpre_" + prev_name, src.shape, self.tdt)
                 ops.maxpool_bwd(src, dx, out=dpre, pair=pair, db=prev_db)
@@ -493,7 +459,7 @@ class Engine:
             else:
                 # ReLU (and for fc6 -> dropout) backward of the producer fused as an epilogue mask on its output
                 scale = inv_keep if prev_name == "fc6" else 1.0
-                ops.conv_gemm(dyh, wh, cin, k, flags=ops.EPI_MASK | self.rnd, mask_src=x_in, mask_scale=scale, out=dx,
+                ops.conv_gemm(dy, wh, cin, k, flags=ops.EPI_MASK, mask_src=x_in, mask_scale=scale, out=dx,
                               colsum=prev_db, **wkw)
                 dy = dx
         if self.dp_reserve_sms > 0:
@@ -553,7 +519,7 @@ class Engine:
     def _step_body(self, images, labels, keep_prob, l2_rate):
         """Everything one training `sess.run` does on the device, reading lr_t / seed from `step_scalars`: this is the
         unit that is captured into a CUDA graph."""
-        self.loss_and_backward(images, labels, keep_prob, l2_rate, 0, _scalars_set=True)
+        self.loss_and_backward(images, labels, keep_prob, l2_rate, 0, _scalars_set=True, store_logits=False)
         self._reduce_and_adam(0.0)
         self._packed_dirty = True
         self.repack()     # derived operands of the updated parameters, ready for the next step's forward
@@ -563,7 +529,7 @@ class Engine:
         """One `sess.run([train_op, total_loss, global_step])` (fcn8s_tensorflow.py:565-572).
         Returns the device tensor loss_buf; total_loss = loss_buf[0] / (N*H*W) + loss_buf[1] (see `loss_value`).
 
-        After two eager steps per (shape, keep_prob, l2_rate) the whole step (~250 kernel launches and the gradient
+        After two eager steps per (shape, keep_prob, l2_rate) the whole step (~110 kernel launches and the gradient
         all-reduce) is captured into a CUDA graph and replayed: the batch is copied into fixed input buffers and the
         two per-step scalars (lr_t, dropout seed) are written to device memory by a 1-thread kernel, so the host's
         cost per step is three launches.  FCN8_GRAPHS=0 (or an installed ops.TIMER) keeps the eager path."""
@@ -584,7 +550,7 @@ class Engine:
         ops.set_step_scalars(self.step_scalars, lr_t, seed)
         entry = self._graphs.get(key) if graphs else None
         if entry is not None:
-            if self._packed_dirty or (self.hwio and self._shadow_dirty):
+            if self._packed_dirty or self._shadow_dirty:
                 self.repack()     # weights were replaced (load_weights) since the last step
             entry[0].replay()
             self.graph_launches += entry[1]
@@ -612,31 +578,28 @@ class Engine:
     # ------------------------------------------------------------------ predictor / evaluation
     @_on_device
     def predict(self, images, argmax=True):
-        """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1."""
+        """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1 -- computed in
+        the epilogue of the upscore8 kernel; the logits are never written."""
         N, H, W, _ = images.shape
-        self.forward(images, 1.0, 0, train=False)
-        zp = self._arena(N, H, W)["logits_p"]
+        A, f3 = self._features(images, 1.0, 0, False)
         if argmax:
             out = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
-            ops.softmax_xent(zp, argmax=out, pad=4, num_classes=self.C)
+            ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, argmax=out)
         else:
             out = torch.empty((N, H, W, self.C), dtype=torch.float32, device=self.device)
-            ops.softmax_xent(zp, softmax=out, pad=4, num_classes=self.C)
+            ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, softmax=out)
         return out
 
     @_on_device
     def eval_step(self, images, labels, conf, l2_rate=0.0):
-        """One metric update (fcn8s_tensorflow.py:685-689): forward at keep_prob 1, total_loss, argmax, confusion
-        matrix accumulate (conf: int64 [C,C] device tensor, conf[label, prediction])."""
-        N, H, W, _ = images.shape
-        self.forward(images, 1.0, 0, train=False)
-        zp = self._arena(N, H, W)["logits_p"]
+        """One metric update (fcn8s_tensorflow.py:685-689): forward at keep_prob 1, total_loss, argmax and the
+        confusion-matrix accumulate (conf: int64 [C,C] device tensor, conf[label, prediction]) in the epilogue of the
+        upscore8 kernel."""
+        A, f3 = self._features(images, 1.0, 0, False)
         self.loss_buf.zero_()
-        am = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
-        lab = labels.view(torch.uint8)
-        ops.softmax_xent(zp, lab, self.loss_buf[0:1], argmax=am, pad=4, num_classes=self.C)
+        ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, labels=labels.view(torch.uint8),
+                        loss_sum=self.loss_buf[0:1], conf=conf)
         if l2_rate != 0.0:
             for kname in DECODER_KERNELS:
                 ops.l2_reg(self.view(kname).reshape(-1), None, self.loss_buf[1:2], l2_rate)
-        ops.confusion_matrix(am, lab, conf)
         return self.loss_buf

@@ -9,7 +9,7 @@ import torch
 
 from . import _capi as capi
 from ._capi import (BF16, F32, BF16X2, EPI_BIAS, EPI_RELU, EPI_DROPOUT, EPI_MASK, EPI_RESIDUAL,  # noqa: F401
-                    EPI_ROUND_TF32, EPI_COLSUM)
+                    EPI_ROUND_TF32, EPI_COLSUM, EPI_POOL)
 
 _workspaces = {}
 
@@ -99,6 +99,26 @@ def _chk_cuda(*ts):
                 raise capi.Fcn8Error("tensor must be contiguous")
 
 
+def _chk_view(*ts):
+    """4-D NHWC views (possibly strided: the interior of a padded tensor, one half of a hi/lo pair tensor)."""
+    for t in ts:
+        if t is not None:
+            if not t.is_cuda:
+                raise capi.Fcn8Error("tensor is not on a CUDA device; there is no CPU path")
+            if t.dim() != 4 or t.stride(3) != 1:
+                raise capi.Fcn8Error("expected an NHWC view with contiguous channels")
+
+
+def _geom(t):
+    """(pixel stride, row stride, image stride) in elements of an NHWC view."""
+    return t.stride(2), t.stride(1), t.stride(0)
+
+
+def halves(t, c):
+    """(hi, lo) channel views of a bf16 hi/lo pair tensor [..., 2c] (FCN8_BF16X2)."""
+    return t[..., :c], t[..., c:2 * c]
+
+
 def preprocess_im2col(images, dtype):
     """uint8 RGB [N,H,W,3] -> mean-subtracted BGR im2col [N,H,W,KP] for conv1_1 (KP = 64 bf16 / 32 f32)."""
     _chk_cuda(images)
@@ -140,68 +160,92 @@ def split_tf32(x):
 
 def conv_gemm(x, wp, cout, ksize, bias=None, flags=0, mask_src=None, residual=None, mask_scale=1.0, keep_prob=1.0,
               seed=0, out=None, x_lo=None, wp_lo=None, force_splits=0, force_bn=0, pair=False, w_mode=0, colsum=None,
-              seed_ptr=None, algo=0, nseg=3):
+              seed_ptr=None, algo=0, nseg=None, out_pair=None, out_scale=0.0, colsum_n=0, pool_out=None,
+              store_out=True, cin=None, tag="conv_gemm"):
     """Stride-1 SAME k x k convolution (fprop or dgrad, see include/fcn8s_b200.h).
-    pair=True: x / out / mask_src / residual are bf16 hi/lo pair tensors [N,H,W,2C] (FCN8_BF16X2) and the product is
-    the error-compensated hi*hi + hi*lo + lo*hi (needs wp_lo); nseg = 2 / 1 keep only the first two / one of those
-    products (the measured reduced-backward modes).  w_mode 1 / 2: wp (wp_lo) is the bf16 shadow of the TF weight tensor
-    itself (fprop / dgrad), no packing."""
-    _chk_cuda(x, wp, bias, mask_src, residual, out, x_lo, wp_lo, colsum)
+    x: NHWC view (may be strided).  pair=True: x is a bf16 hi/lo pair tensor [N,H,W,2C] (FCN8_BF16X2) -- otherwise an
+    explicit `x_lo` view supplies the low plane -- and the product is the error-compensated hi*hi + hi*lo + lo*hi
+    (needs wp_lo); nseg = 2 / 1 keep only hi*(w_hi + w_lo) / hi*hi.  out_pair (default: pair): out / mask_src / residual /
+    pool_out are pair tensors [.., 2*cout].  w_mode 1 / 2: wp (wp_lo) is a bf16 weight tensor in TF layout read in place
+    (fprop / dgrad), no packing.  pool_out: also emit the 2x2 max-pool (EPI_POOL); store_out=False then keeps only it."""
+    if pair:
+        c = x.shape[3] // 2
+        x, x_lo = halves(x, c)
+    cin = x.shape[3] if cin is None else cin
+    if out_pair is None:
+        out_pair = pair
+    _chk_view(x, x_lo)
+    _chk_cuda(wp, bias, wp_lo, colsum)
+    N, H, W, _ = x.shape
+    dtype = dtype_of(x)
+    if nseg is None:
+        nseg = 3 if x_lo is not None else 1
+    if out is None and store_out:
+        out = torch.empty((N, H, W, (2 if out_pair else 1) * cout), dtype=x.dtype, device=x.device)
+
+    def hl(t):
+        if t is None:
+            return None, None
+        return halves(t, cout) if out_pair else (t, None)
+    o_hi, o_lo = hl(out)
+    r_hi, r_lo = hl(residual)
+    m_hi, _ = hl(mask_src)
+    p_hi, p_lo = hl(pool_out)
+    ref = o_hi if o_hi is not None else None
+    _chk_view(o_hi, r_hi, m_hi, p_hi)
     if colsum is not None:
         flags |= EPI_COLSUM
-    N, H, W, cin = x.shape
-    if pair:
-        cin //= 2
-        dtype = BF16
-        if out is None:
-            out = torch.empty((N, H, W, 2 * cout), dtype=torch.bfloat16, device=x.device)
-        p = capi.ConvParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
-                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
-                            mask_scale, keep_prob, seed, force_splits, force_bn, 2 * cin, 2 * cout,
-                            capi.ptr(out, cout), capi.ptr(residual, cout), w_mode, capi.ptr(colsum),
-                            capi.ptr(seed_ptr), algo)
-    else:
-        dtype = dtype_of(x)
-        if out is None:
-            out = torch.empty((N, H, W, cout), dtype=x.dtype, device=x.device)
-        nseg = 3 if x_lo is not None else 1
-        p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(out), capi.ptr(bias),
-                            capi.ptr(mask_src), capi.ptr(residual), N, H, W, cin, cout, ksize, dtype, nseg, flags,
-                            mask_scale, keep_prob, seed, force_splits, force_bn, 0, 0, None, None, w_mode,
-                            capi.ptr(colsum), capi.ptr(seed_ptr), algo)
+    if pool_out is not None:
+        flags |= EPI_POOL
+    x_ld, x_sH, x_sN = _geom(x)
+    o_ld, o_sH, o_sN = _geom(ref) if ref is not None else (0, 0, 0)
+    for t in (r_hi, m_hi):
+        if t is not None and ref is not None and _geom(t) != _geom(ref):
+            raise capi.Fcn8Error("mask_src / residual must have the geometry of out")
+    p = capi.ConvParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(wp), capi.ptr(wp_lo), capi.ptr(o_hi), capi.ptr(bias),
+                        capi.ptr(m_hi), capi.ptr(r_hi), N, H, W, cin, cout, ksize, dtype, nseg, flags, mask_scale,
+                        keep_prob, seed, force_splits, force_bn, x_ld, o_ld, capi.ptr(o_lo), capi.ptr(r_lo), w_mode,
+                        capi.ptr(colsum), capi.ptr(seed_ptr), algo, out_scale, colsum_n, capi.ptr(p_hi),
+                        capi.ptr(p_lo), p_hi.stride(2) if p_hi is not None else 0, x_sH, x_sN, o_sH, o_sN)
     lib = capi.load()
     nbytes = lib.fcn8_conv_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
     e0 = TIMER.start() if TIMER is not None else None
     capi.check(lib.fcn8_conv_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
     if e0 is not None:
-        TIMER.stop("conv_gemm", 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
+        TIMER.stop(tag, 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
     return out
 
 
 def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_splits=0, force_bn=0, pair=False,
-               nseg=3):
-    """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows).
-    pair=True: x / dy are bf16 hi/lo pair tensors [N,H,W,2C]; error-compensated product."""
-    _chk_cuda(x, dy, out, x_lo, dy_lo)
+               nseg=None, out_cols=0, out_scale=0.0, dy_pair=None):
+    """Filter gradient into `out` (fp32, HWIO-flattened [k*k*Cin, Cout] or its first rows_valid rows; [.., out_cols]
+    when out_cols is given).  x / dy: NHWC views; pair=True: x (and dy unless dy_pair=False) are bf16 hi/lo pair tensors
+    [N,H,W,2C]; otherwise x_lo / dy_lo supply the low planes.  Error-compensated product for nseg = 3."""
+    if dy_pair is None:
+        dy_pair = pair
+    if pair:
+        x, x_lo = halves(x, x.shape[3] // 2)
+    if dy_pair:
+        dy, dy_lo = halves(dy, dy.shape[3] // 2)
+    _chk_view(x, dy, x_lo, dy_lo)
+    _chk_cuda(out)
     N, H, W, cin = x.shape
     cout = dy.shape[3]
-    if pair:
-        cin //= 2
-        cout //= 2
-        p = capi.WgradParams(capi.ptr(x), capi.ptr(x, cin), capi.ptr(dy), capi.ptr(dy, cout), capi.ptr(out), N, H, W,
-                             cin, cout, ksize, rows_valid, BF16, nseg, force_splits, force_bn, 2 * cin, 2 * cout)
-    else:
-        nseg = 3 if x_lo is not None else 1
-        p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin,
-                             cout, ksize, rows_valid, dtype_of(x), nseg, force_splits, force_bn, 0, 0)
+    if nseg is None:
+        nseg = 3 if (x_lo is not None and dy_lo is not None) else 1
+    x_ld, x_sH, x_sN = _geom(x)
+    d_ld, d_sH, d_sN = _geom(dy)
+    p = capi.WgradParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(dy), capi.ptr(dy_lo), capi.ptr(out), N, H, W, cin, cout,
+                         ksize, rows_valid, dtype_of(x), nseg, force_splits, force_bn, x_ld, d_ld, out_cols, out_scale,
+                         x_sH, x_sN, d_sH, d_sN)
     lib = capi.load()
     nbytes = lib.fcn8_wgrad_gemm_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, x.device) if nbytes else None
     e0 = TIMER.start() if TIMER is not None else None
     capi.check(lib.fcn8_wgrad_gemm(C.byref(p), capi.ptr(ws), nbytes, _stream()))
     if e0 is not None:
-        TIMER.stop("wgrad_gemm", 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
+        TIMER.stop("wgrad_gemm" if out_cols == 0 else "head_gemm", 2.0 * N * H * W * cout * ksize * ksize * cin, e0)
     return out
 
 
@@ -244,188 +288,165 @@ def bias_grad(dy, out, pair=False):
     return out
 
 
-def score_head_fwd(x, K, b, scale, out=None, pair=False):
-    _chk_cuda(x, K, b, out)
-    cin = x.shape[-1]
-    Cc = K.shape[-1]
-    P = x.numel() // cin
-    if pair:
-        cin //= 2
+# ---------------------------------------------------------------------------------------------------- decoder
+def deconv_cp(stride):
+    """Channels per pixel of the padded blocked tensors of a stride-s transposed-convolution stage."""
+    return capi.load().fcn8_deconv_cp(stride)
+
+
+def head_pack(K, bias, split=True, out=None):
+    """Score-head kernel K [Cin, C] (+ bias [C]) -> dict(w, w_lo: bf16 [Cin, 64] TF-layout weight with the classes
+    zero-padded to 64; bias64: fp32 [64]).  `out`: an earlier result, refilled in place."""
+    _chk_cuda(K, bias)
+    cin, Cc = K.shape
     if out is None:
-        out = torch.empty(tuple(x.shape[:-1]) + (Cc,), dtype=torch.float32, device=x.device)
-    p = capi.HeadParams(capi.ptr(x), capi.ptr(K), capi.ptr(b), capi.ptr(out), None, None, None, P, cin, Cc, scale,
-                        _fmt(x, pair), 0, 1.0)
-    lib = capi.load()
-    nbytes = lib.fcn8_score_head_fwd_workspace_bytes(C.byref(p))
-    ws = _workspace(nbytes, x.device) if nbytes else None
-    capi.check(lib.fcn8_score_head_fwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+        out = dict(w=torch.empty((cin, 64), dtype=torch.bfloat16, device=K.device), w_lo=None,
+                   bias64=torch.empty(64, dtype=torch.float32, device=K.device))
+        if split:
+            out["w_lo"] = torch.empty_like(out["w"])
+    capi.check(capi.load().fcn8_head_pack(capi.ptr(K), capi.ptr(bias), cin, Cc, capi.ptr(out["w"]),
+                                          capi.ptr(out["w_lo"]), capi.ptr(out["bias64"]), _stream()))
     return out
 
 
-def score_head_bwd(x, K, ds, scale, dK, db, dx=None, mask=False, mask_scale=1.0, pair=False):
-    _chk_cuda(x, K, ds, dK, db, dx)
-    cin = x.shape[-1]
-    Cc = K.shape[-1]
-    P = x.numel() // cin
-    if pair:
-        cin //= 2
-    p = capi.HeadParams(capi.ptr(x), capi.ptr(K), None, capi.ptr(ds), capi.ptr(dK), capi.ptr(db), capi.ptr(dx), P, cin,
-                        Cc, scale, _fmt(x, pair), 1 if mask else 0, mask_scale)
-    lib = capi.load()
-    nbytes = lib.fcn8_score_head_bwd_workspace_bytes(C.byref(p))
-    ws = _workspace(nbytes, x.device)
-    capi.check(lib.fcn8_score_head_bwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
-    return dx
-
-
-def upscore_fwd(x, T, bias, stride, skip=None, out=None):
-    _chk_cuda(x, T, bias, skip, out)
-    N, h, w, Cc = x.shape
-    if out is None:
-        out = torch.empty((N, h * stride, w * stride, Cc), dtype=torch.float32, device=x.device)
-    p = capi.UpscoreParams(capi.ptr(x), capi.ptr(T), capi.ptr(bias), capi.ptr(skip), capi.ptr(out), None, None, None,
-                           N, h, w, Cc, stride)
-    capi.check(capi.load().fcn8_upscore_fwd(C.byref(p), _stream()))
-    return out
-
-
-def upscore_bwd(x, T, dy, stride, dT, dbias, dx=None):
-    _chk_cuda(x, T, dy, dT, dbias, dx)
-    N, h, w, Cc = x.shape
-    p = capi.UpscoreParams(capi.ptr(x), capi.ptr(T), None, None, capi.ptr(dy), capi.ptr(dx), capi.ptr(dT),
-                           capi.ptr(dbias), N, h, w, Cc, stride)
-    lib = capi.load()
-    nbytes = lib.fcn8_upscore_bwd_workspace_bytes(C.byref(p))
-    ws = _workspace(nbytes, x.device)
-    capi.check(lib.fcn8_upscore_bwd(C.byref(p), capi.ptr(ws), nbytes, _stream()))
-    return dx
-
-
-def softmax_xent(logits, labels=None, loss_sum=None, dlogits=None, softmax=None, argmax=None, grad_scale=1.0,
-                 dbias=None, pad=0, num_classes=None):
-    """Loss / predictor kernel. `logits` (and `dlogits`) are [N,Hp,Wp,CP] with Hp = H + 2*pad, Wp = W + 2*pad and
-    CP >= num_classes (pad = 0, CP = C: the dense tensor); labels / softmax / argmax are dense over [N,H,W]."""
-    _chk_cuda(logits, labels, loss_sum, dlogits, softmax, argmax, dbias)
-    if logits.dim() != 4:
-        logits = logits.view(1, 1, -1, logits.shape[-1])
-    N, Hp, Wp, CP = logits.shape
-    Cc = CP if num_classes is None else num_classes
-    p = capi.SoftmaxParams(capi.ptr(logits), capi.ptr(labels), capi.ptr(loss_sum), capi.ptr(dlogits),
-                           capi.ptr(dbias), capi.ptr(softmax), capi.ptr(argmax), N, Hp - 2 * pad, Wp - 2 * pad, Cc,
-                           CP, pad, grad_scale)
-    e0 = TIMER.start() if TIMER is not None else None
-    capi.check(capi.load().fcn8_softmax_xent(C.byref(p), _stream()))
-    if e0 is not None:   # HBM-bound: the "work" recorded is algorithmic bytes, not FLOPs
-        px = N * (Hp - 2 * pad) * (Wp - 2 * pad)
-        nbytes = px * Cc * 4 + (px * Cc if labels is not None else 0) + (px * Cc * 4 if dlogits is not None else 0) + \
-            (px * Cc * 4 if softmax is not None else 0) + (px * 8 if argmax is not None else 0)
-        TIMER.stop("predictor" if dlogits is None else "loss", float(nbytes), e0)
-
-
-def upscore_tc_cp(num_classes, stride):
-    """Channel stride of the padded blocked output of the tensor-core transposed convolution."""
-    return capi.load().fcn8_upscore_tc_cp(num_classes, stride)
-
-
-def upscore_tc_pack(T, bias, stride, split=False, out=None):
-    """T [2s,2s,C,C], bias [C] -> dict of tensor-core operands (w_fwd, w_dx, bias_big and their *_lo halves).
-    `out`: a dict returned by an earlier call, refilled in place."""
+def deconv_pack(T, bias, stride, split=True, out=None):
+    """T [2s,2s,C,C], bias [C] -> dict of phase-GEMM operands (w_fwd [s*s*CP, 256], w_dx [64, 4*s*s*CP] bf16 and their
+    *_lo halves, bias_big fp32 [s*s*CP]).  `out`: a dict returned by an earlier call, refilled in place."""
     _chk_cuda(T, bias)
     Cc = T.shape[-1]
-    CP = upscore_tc_cp(Cc, stride)
-    ncols = stride * stride * CP
-    f32 = dict(dtype=torch.float32, device=T.device)
+    ncols = stride * stride * deconv_cp(stride)
     if out is None:
-        out = dict(w_fwd=torch.empty((ncols, 128), **f32), w_dx=torch.empty((64, 4 * ncols), **f32),
-                   bias_big=torch.empty(ncols, **f32), w_fwd_lo=None, w_dx_lo=None)
+        bf = dict(dtype=torch.bfloat16, device=T.device)
+        out = dict(w_fwd=torch.empty((ncols, 256), **bf), w_dx=torch.empty((64, 4 * ncols), **bf),
+                   bias_big=torch.empty(ncols, dtype=torch.float32, device=T.device), w_fwd_lo=None, w_dx_lo=None)
         if split:
             out["w_fwd_lo"] = torch.empty_like(out["w_fwd"])
             out["w_dx_lo"] = torch.empty_like(out["w_dx"])
-    p = capi.UpscorePackParams(capi.ptr(T), capi.ptr(bias), capi.ptr(out["w_fwd"]), capi.ptr(out["w_fwd_lo"]),
-                               capi.ptr(out["w_dx"]), capi.ptr(out["w_dx_lo"]), capi.ptr(out["bias_big"]), Cc, stride)
-    capi.check(capi.load().fcn8_upscore_tc_pack(C.byref(p), _stream()))
+    capi.check(capi.load().fcn8_deconv_pack(capi.ptr(T), capi.ptr(bias), Cc, stride, capi.ptr(out["w_fwd"]),
+                                            capi.ptr(out["w_fwd_lo"]), capi.ptr(out["w_dx"]), capi.ptr(out["w_dx_lo"]),
+                                            capi.ptr(out["bias_big"]), _stream()))
     return out
 
 
-def _tc_params(x, x_lo, w, w_lo, bias_big, zp, zp_lo, dx, dT, Cc, stride):
-    N, h, wd, ldx = x.shape if x is not None else dx.shape
-    nseg = 3 if (w_lo is not None or (x_lo is not None and zp_lo is not None)) else 1
-    return capi.UpscoreTcParams(capi.ptr(x), capi.ptr(x_lo), capi.ptr(w), capi.ptr(w_lo), capi.ptr(bias_big),
-                                capi.ptr(zp), capi.ptr(zp_lo), capi.ptr(dx), capi.ptr(dT), N, h, wd, Cc, stride, ldx,
-                                nseg)
+def planes_alloc(N, h, w, device, channels=64, zero=True):
+    """A decoder activation as bf16 hi / lo planes: (hi, lo) tensors [N,h,w,channels] (zero beyond the class count)."""
+    f = torch.zeros if zero else torch.empty
+    return (f((N, h, w, channels), dtype=torch.bfloat16, device=device),
+            f((N, h, w, channels), dtype=torch.bfloat16, device=device))
 
 
-def upscore_tc_alloc(N, h, w, num_classes, stride, device, zero=False):
-    """Padded blocked tensor [N, s*(h+1), s*(w+1), CP] of the tensor-core transposed convolution."""
-    CP = upscore_tc_cp(num_classes, stride)
-    shape = (N, stride * (h + 1), stride * (w + 1), CP)
-    return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
+def planes_from_float(x, channels=64):
+    """fp32 [N,h,w,C] -> (hi, lo) planes [N,h,w,channels] (test helper)."""
+    N, h, w, Cc = x.shape
+    hi, lo = planes_alloc(N, h, w, x.device, channels)
+    hi[..., :Cc] = x.to(torch.bfloat16)
+    lo[..., :Cc] = (x - hi[..., :Cc].float()).to(torch.bfloat16)
+    return hi, lo
 
 
-def upscore_tc_interior(zp, num_classes, stride):
-    """[N, s*h, s*w, C] view of the transposed convolution's output inside its padded tensor."""
+def planes_to_float(planes, num_classes):
+    return planes[0][..., :num_classes].float() + planes[1][..., :num_classes].float()
+
+
+def padded_alloc(N, h, w, stride, device):
+    """Zero-bordered padded blocked planes [N, s*(h+1), s*(w+1), CP] of a stride-s stage (gradient of its output)."""
+    cp = deconv_cp(stride)
+    return planes_alloc(N, stride * (h + 1), stride * (w + 1), device, cp)
+
+
+def padded_interior(planes, stride):
+    """[N, s*h, s*w, CP] views of the interior of padded blocked planes."""
     p = stride // 2
-    return zp[:, p:zp.shape[1] - p, p:zp.shape[2] - p, :num_classes]
+    return tuple(t[:, p:t.shape[1] - p, p:t.shape[2] - p, :] for t in planes)
 
 
-def upscore_tc_gather(zp, skip, out, num_classes, stride):
-    """out[N, s*h, s*w, ld] = interior(zp)[..., :C] (+ skip [N, s*h, s*w, >=C]); pad channels of `out` zeroed."""
-    _chk_cuda(zp, skip, out)
-    N, H, W, ld = out.shape
-    capi.check(capi.load().fcn8_upscore_tc_gather(capi.ptr(zp), capi.ptr(skip), capi.ptr(out), N, H // stride,
-                                                  W // stride, num_classes, stride, ld,
-                                                  skip.shape[-1] if skip is not None else 0, _stream()))
+def _deconv_params(x=None, w=None, w_lo=None, bias_big=None, out=None, skip=None, dz=None, dT=None, colsum=None,
+                   colsum_n=0, N=0, h=0, wd=0, Cc=0, stride=0, nseg=3, **loss):
+    """x / out / skip / dz: (hi, lo) tuples of NHWC views."""
+    x_hi, x_lo = x if x is not None else (None, None)
+    o_hi, o_lo = out if out is not None else (None, None)
+    s_hi, s_lo = skip if skip is not None else (None, None)
+    z_hi, z_lo = dz if dz is not None else (None, None)
+    _chk_view(x_hi, x_lo, o_hi, o_lo, s_hi, s_lo)
+    _chk_cuda(z_hi, z_lo, w, w_lo)
+    x_ld, x_sH, x_sN = _geom(x_hi) if x_hi is not None else (0, 0, 0)
+    o_ld, o_sH, o_sN = _geom(o_hi) if o_hi is not None else (0, 0, 0)
+    if s_hi is not None and _geom(s_hi) != _geom(o_hi):
+        raise capi.Fcn8Error("skip planes must have the geometry of out")
+    dzo = loss.get("dz_out") or (None, None)
+    return capi.DeconvParams(capi.ptr(x_hi), capi.ptr(x_lo), x_ld, x_sH, x_sN, capi.ptr(w), capi.ptr(w_lo),
+                             capi.ptr(bias_big), capi.ptr(o_hi), capi.ptr(o_lo), o_ld, o_sH, o_sN, capi.ptr(s_hi),
+                             capi.ptr(s_lo), capi.ptr(z_hi), capi.ptr(z_lo), capi.ptr(dT), capi.ptr(colsum), colsum_n,
+                             N, h, wd, Cc, stride, nseg, capi.ptr(loss.get("labels")), capi.ptr(loss.get("loss_sum")),
+                             capi.ptr(loss.get("dbias")), capi.ptr(dzo[0]), capi.ptr(dzo[1]),
+                             capi.ptr(loss.get("logits")), capi.ptr(loss.get("softmax")), capi.ptr(loss.get("argmax")),
+                             capi.ptr(loss.get("conf")), loss.get("grad_scale", 1.0))
+
+
+def _deconv_flops(N, h, w, stride, Cc):
+    return 2.0 * N * h * w * 4 * stride * stride * Cc * Cc
+
+
+def deconv_fwd(x, packed, num_classes, stride, out, skip=None, nseg=3):
+    """Stride-2 transposed convolution of planes x [N,h,w,.] into dense planes out [N,2h,2w,.] (+ skip planes)."""
+    N, h, w, _ = x[0].shape
+    p = _deconv_params(x=x if nseg == 3 else (x[0], None), w=packed["w_fwd"], w_lo=packed["w_fwd_lo"] if nseg > 1 else None,
+                       bias_big=packed["bias_big"], out=out, skip=skip, N=N, h=h, wd=w, Cc=num_classes, stride=stride,
+                       nseg=nseg)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(capi.load().fcn8_deconv_fwd(C.byref(p), _stream()))
+    if e0 is not None:
+        TIMER.stop("deconv", _deconv_flops(N, h, w, stride, num_classes), e0)
     return out
 
 
-def upscore_tc_scatter(g, dzp, num_classes, stride, dbias=None):
-    """dzp interior <- g [N, s*h, s*w, ld]; dbias[c] += sum of g over pixels (caller zeroes dzp once and dbias)."""
-    _chk_cuda(g, dzp, dbias)
-    N, H, W, ld = g.shape
-    capi.check(capi.load().fcn8_upscore_tc_scatter(capi.ptr(g), capi.ptr(dzp), capi.ptr(dbias), N, H // stride,
-                                                   W // stride, num_classes, stride, ld, _stream()))
-    return dzp
-
-
-def upscore_tc_fwd(x, packed, num_classes, stride, out, x_lo=None):
-    """x [N,h,w,ldx] fp32 (channels >= C zero) -> padded blocked output `out` (see upscore_tc_alloc)."""
-    _chk_cuda(x, x_lo, out)
-    w_lo = packed["w_fwd_lo"] if x_lo is not None else None
-    p = _tc_params(x, x_lo, packed["w_fwd"], w_lo, packed["bias_big"], out, None, None, None, num_classes, stride)
+def deconv_loss(x, packed, num_classes, nseg=3, labels=None, loss_sum=None, dz_out=None, dbias=None, grad_scale=1.0,
+                logits=None, softmax=None, argmax=None, conf=None):
+    """upscore8 (stride 8) with the loss / predictor fused into its epilogue; see fcn8_deconv_loss."""
+    N, h, w, _ = x[0].shape
+    _chk_cuda(labels, loss_sum, dbias, logits, softmax, argmax, conf)
+    if dz_out is not None:
+        _chk_cuda(dz_out[0], dz_out[1])
+    p = _deconv_params(x=x if nseg == 3 else (x[0], None), w=packed["w_fwd"], w_lo=packed["w_fwd_lo"] if nseg > 1 else None,
+                       bias_big=packed["bias_big"], N=N, h=h, wd=w, Cc=num_classes, stride=8, nseg=nseg, labels=labels,
+                       loss_sum=loss_sum, dz_out=dz_out, dbias=dbias, grad_scale=grad_scale, logits=logits,
+                       softmax=softmax, argmax=argmax, conf=conf)
     e0 = TIMER.start() if TIMER is not None else None
-    capi.check(capi.load().fcn8_upscore_tc_fwd(C.byref(p), _stream()))
+    capi.check(capi.load().fcn8_deconv_loss(C.byref(p), _stream()))
     if e0 is not None:
-        N, h, w, _ = x.shape
-        TIMER.stop("upscore8" if stride == 8 else "upscore_tc",
-                   2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+        px = N * 64 * h * w   # HBM-side work: algorithmic bytes of the requested outputs + the input planes
+        nbytes = N * h * w * num_classes * 4 + (px * num_classes if labels is not None else 0) + \
+            (px * num_classes * 4 if dz_out is not None else 0) + (px * num_classes * 4 if logits is not None else 0) + \
+            (px * num_classes * 4 if softmax is not None else 0) + (px * 8 if argmax is not None else 0)
+        TIMER.stop("upscore8_fused", float(nbytes), e0)
+
+
+def deconv_dx(dz, packed, num_classes, stride, out, nseg=3, colsum=None, shape=None):
+    """Input gradient of a stride-s stage from padded blocked dz planes into planes `out` [N,h,w,.] (may be the
+    interior view of the next stage's padded planes); colsum[c] += sum over pixels of the result."""
+    N, h, w, _ = out[0].shape
+    p = _deconv_params(dz=dz if nseg == 3 else (dz[0], None), w=packed["w_dx"], w_lo=packed["w_dx_lo"] if nseg > 1 else None,
+                       out=out, colsum=colsum, N=N, h=h, wd=w, Cc=num_classes, stride=stride, nseg=nseg)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(capi.load().fcn8_deconv_dx(C.byref(p), _stream()))
+    if e0 is not None:
+        TIMER.stop("deconv", _deconv_flops(N, h, w, stride, num_classes), e0)
     return out
 
 
-def upscore_tc_dx(dzp, packed, num_classes, stride, dx, dzp_lo=None):
-    """Input gradient of the transposed convolution from the padded blocked dz (zero border) into dx [N,h,w,ldx]."""
-    _chk_cuda(dzp, dzp_lo, dx)
-    w_lo = packed["w_dx_lo"] if dzp_lo is not None else None
-    p = _tc_params(None, None, packed["w_dx"], w_lo, None, dzp, dzp_lo, dx, None, num_classes, stride)
-    e0 = TIMER.start() if TIMER is not None else None
-    capi.check(capi.load().fcn8_upscore_tc_dx(C.byref(p), _stream()))
-    if e0 is not None:
-        N, h, w, _ = dx.shape
-        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
-    return dx
-
-
-def upscore_tc_dw(x, dzp, num_classes, stride, dT, x_lo=None, dzp_lo=None):
-    """Filter gradient dT [2s,2s,C,C] (TF layout) of the transposed convolution."""
-    _chk_cuda(x, dzp, dT, x_lo, dzp_lo)
-    p = _tc_params(x, x_lo, None, None, None, dzp, dzp_lo, None, dT, num_classes, stride)
+def deconv_dw(x, dz, num_classes, stride, dT, nseg=3):
+    """Filter gradient dT [2s,2s,C,C] (TF layout, fp32) of a stride-s stage from planes x and padded blocked dz planes."""
+    N, h, w, _ = x[0].shape
+    _chk_cuda(dT)
+    p = _deconv_params(x=x if nseg == 3 else (x[0], None), dz=dz if nseg > 1 else (dz[0], None), dT=dT, N=N, h=h, wd=w,
+                       Cc=num_classes, stride=stride, nseg=nseg)
     lib = capi.load()
-    nbytes = lib.fcn8_upscore_tc_dw_workspace_bytes(C.byref(p))
-    ws = _workspace(nbytes, x.device)
+    nbytes = lib.fcn8_deconv_dw_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, x[0].device)
     e0 = TIMER.start() if TIMER is not None else None
-    capi.check(lib.fcn8_upscore_tc_dw(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    capi.check(lib.fcn8_deconv_dw(C.byref(p), capi.ptr(ws), nbytes, _stream()))
     if e0 is not None:
-        N, h, w, _ = x.shape
-        TIMER.stop("upscore_tc", 2.0 * N * h * w * 4 * stride * stride * num_classes * num_classes, e0)
+        TIMER.stop("deconv", _deconv_flops(N, h, w, stride, num_classes), e0)
     return dT
 
 

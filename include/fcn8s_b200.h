@@ -51,8 +51,11 @@ enum {
   FCN8_EPI_MASK = 8,
   FCN8_EPI_RESIDUAL = 16,
   FCN8_EPI_ROUND_TF32 = 64, /* FCN8_F32 only: round outputs to the nearest tf32 (the MMA truncates its operands) */
-  FCN8_EPI_COLSUM = 128     /* colsum[co] += sum over pixels of the stored values: the BiasAddGrad of the layer whose
+  FCN8_EPI_COLSUM = 128,    /* colsum[co] += sum over pixels of the stored values: the BiasAddGrad of the layer whose
                                dY this dgrad call produces, fused into its epilogue (fp32 atomics, caller zeroes) */
+  FCN8_EPI_POOL = 256       /* FCN8_BF16 only: also emit the 2x2 / stride-2 SAME max-pool of the output to pool_out
+                               (the encoder's MaxPool fused into the epilogue of conv{1_2,2_2,3_3,4_3,5_3}); H and W
+                               must be even; out may be NULL (inference: keep only the pooled tensor) */
 };
 
 int32_t fcn8_version(void);
@@ -132,6 +135,15 @@ typedef struct {
   int32_t algo;         /* 0 = heuristic; 1 = per-tap implicit GEMM; 2 = halo-tile kernel (3x3, bf16, w_mode 1/2: the
                            activation patch of a tile is loaded once with its halo and the nine taps are shifted UMMA
                            descriptors into it) */
+  float out_scale;      /* 0 = 1: the accumulator is multiplied by it before bias / residual (the 1e-4 / 1e-2 skip
+                           scales of the score heads, fcn8s_tensorflow.py:171,182, and of their input gradients) */
+  int32_t colsum_n;     /* 0 = Cout: only the first colsum_n columns are added to colsum */
+  void* pool_out;       /* FCN8_EPI_POOL: [N, H/2, W/2, pool_ld] in the storage format of out (pool_out_lo: lo half) */
+  void* pool_out_lo;
+  int32_t pool_ld;      /* 0 = out_ld */
+  /* strided views (elements; 0 = dense NHWC): row / image strides of x (and x_lo) and of out (and out_lo, mask_src,
+   * residual) -- e.g. the interior of a zero-bordered padded tensor of the transposed-convolution stages */
+  int64_t x_sH, x_sN, out_sH, out_sN;
 } Fcn8ConvParams;
 size_t fcn8_conv_gemm_workspace_bytes(const Fcn8ConvParams* p);
 int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -153,6 +165,10 @@ typedef struct {
   int32_t force_bn;
   int32_t x_ld;  /* pixel strides in elements, 0 = Cin / Cout */
   int32_t dy_ld;
+  int32_t out_cols;  /* 0 = Cout: only the first out_cols columns of every row are written, dw is [rows][out_cols]
+                        (score heads: Cout is the class count padded to 64) */
+  float out_scale;   /* 0 = 1 */
+  int64_t x_sH, x_sN, dy_sH, dy_sN;   /* strided views as in Fcn8ConvParams (0 = dense) */
 } Fcn8WgradParams;
 size_t fcn8_wgrad_gemm_workspace_bytes(const Fcn8WgradParams* p);
 int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t workspace_bytes, void* stream);
@@ -201,118 +217,78 @@ typedef struct {
 size_t fcn8_bias_grad_workspace_bytes(const Fcn8BiasGradParams* p);
 int32_t fcn8_bias_grad(const Fcn8BiasGradParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- decoder 1x1 score heads: fcn8s_tensorflow.py:171-200 (tf.multiply scale + tf.layers.conv2d 1x1 + bias).
- * fwd: s[p][c] = scale * sum_ci x[p][ci] * K[ci][c] + b[c]            (x in `dtype`, everything else fp32)
- * bwd: dK[ci][c] = scale * sum_p x[p][ci]*ds[p][c]; db[c] = sum_p ds[p][c];
- *      dx[p][ci] = scale * sum_c ds[p][c]*K[ci][c]  (* (x>0)*mask_scale if mask != 0: dropout+ReLU backward of fc7) */
-typedef struct {
-  const void* x;
-  const float* K;
-  const float* b;
-  float* s;        /* fwd out / bwd: ds in */
-  float* dK;
-  float* db;
-  void* dx;        /* `dtype` */
-  int64_t P;
-  int32_t Cin, C;
-  float scale;
-  int32_t dtype;
-  int32_t mask;
-  float mask_scale;
-} Fcn8HeadParams;
-size_t fcn8_score_head_fwd_workspace_bytes(const Fcn8HeadParams* p);
-int32_t fcn8_score_head_fwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream);
-size_t fcn8_score_head_bwd_workspace_bytes(const Fcn8HeadParams* p);
-int32_t fcn8_score_head_bwd(const Fcn8HeadParams* p, void* workspace, size_t workspace_bytes, void* stream);
+/* ---- decoder on the tensor cores: fcn8s_tensorflow.py:164-235 and its autodiff (:257), loss :253, predictor :268-269,
+ * metrics :280-301.  All decoder activations are bf16 hi / lo PLANES: two bf16 tensors of the same geometry with
+ * v ~ hi + lo; a pixel's channel vector is one 128-byte operand row (64 channels, classes zero-padded).
+ *
+ * 1x1 score heads (:171-200, tf.multiply scale + tf.layers.conv2d 1x1 + bias): fcn8_head_pack turns the kernel
+ * K [1,1,Cin,C] into a TF-layout weight tensor with the class dimension zero-padded to 64, w[ci][c64] (bf16 hi / lo),
+ * and bias64; then
+ *   s   = fcn8_conv_gemm (ksize 1, Cout 64, w_mode 1, BIAS, out_scale = the skip scale, out / out_lo = the planes)
+ *   dX  = fcn8_conv_gemm (x = ds planes, Cin 64, Cout = Cin_head, w_mode 2, out_scale = scale, MASK for fc7)
+ *   dK  = fcn8_wgrad_gemm(x, dy = ds planes, Cout 64, out_cols = C, out_scale = scale)
+ *   db  = the column sums the kernel that produced ds emitted (FCN8_EPI_COLSUM / Fcn8DeconvParams.colsum). */
+int32_t fcn8_head_pack(const float* K, const float* bias, int32_t Cin, int32_t C, void* w_hi, void* w_lo, float* bias64,
+                       void* stream);
 
-/* ---- transposed convolutions: fcn8s_tensorflow.py:204-233 (tf.layers.conv2d_transpose k=2s, stride s, 'same')
- * plus the skip adds :213,:224.   T[a][b][co][ci] (TF layout), all fp32.
- * fwd: y[n, s*i+a-p, s*j+b-p, co] = sum x[n,i,j,ci]*T[a,b,co,ci] + bias[co] (+ skip[...]),  p = s/2.
- * bwd: dx = strided conv of dy with T;  dT[a,b,co,ci] = sum x*dy;  dbias = sum dy. */
+/* Transposed convolutions (tf.layers.conv2d_transpose k = 2s, stride s, 'same'; kernel T [2s,2s,C_out,C_in] in TF layout)
+ * as phase GEMMs on tcgen05: every s x s output block (J, I), J in [0,h], I in [0,w], is one GEMM row,
+ *   Zblock[(dy,dx,co)] = sum_{(ty,tx,ci)} x[J-1+ty, I-1+tx, ci] * T[dy+s(1-ty), dx+s(1-tx), co, ci],
+ * K = 4 taps x 64 channels, N = s*s*CP columns (CP = fcn8_deconv_cp(s): 64 for s = 2, 32 for s = 8).
+ *   fcn8_deconv_pack  T, bias -> w_fwd [s*s*CP][256], w_dx [64][4*s*s*CP] (bf16 hi / lo), bias_big [s*s*CP]
+ *   fcn8_deconv_fwd   (s = 2: upscore2 :204-211, upscore_pool4 :215-222) dense output planes [N, s*h, s*w, .]; the skip
+ *                     tensor (tf.add :213 / :224) is added in the epilogue
+ *   fcn8_deconv_loss  (s = 8: upscore8 :226-235) with the loss / predictor in the epilogue -- any subset of: loss_sum +=
+ *                     sum over pixels of softmax-CE with `labels` (one-hot uint8 [N,8h,8w,C]); the loss gradient
+ *                     dz = (softmax - labels) * grad_scale as bf16 planes in the padded blocked layout
+ *                     [N, 8(h+1), 8(w+1), 32] (interior only: zero the planes once) and dbias[C] += its class sums;
+ *                     logits / softmax fp32 [N,8h,8w,C]; argmax int64 [N,8h,8w]; conf[label*C + prediction] += 1
+ *   fcn8_deconv_dx    input gradient from dz planes in the padded blocked layout [N, s(h+1), s(w+1), CP] (zero border,
+ *                     zero beyond C) into out planes [N,h,w,64] (+ colsum[c] += column sums: the bias gradient of the
+ *                     layer below)
+ *   fcn8_deconv_dw    dT [2s,2s,C,C] fp32 from x planes and dz planes
+ * nseg = 3: hi*hi + hi*lo + lo*hi; 1: hi planes only (the bf16 precision mode). */
 typedef struct {
-  const float* x;  /* [N,h,w,C] */
-  const float* T;  /* [2s,2s,C,C] */
-  const float* bias;
-  const float* skip; /* [N,h*s,w*s,C] or NULL */
-  float* y;        /* fwd out / bwd: dy in */
-  float* dx;
-  float* dT;
-  float* dbias;
-  int32_t N, h, w, C, stride;
-} Fcn8UpscoreParams;
-int32_t fcn8_upscore_fwd(const Fcn8UpscoreParams* p, void* stream);
-size_t fcn8_upscore_bwd_workspace_bytes(const Fcn8UpscoreParams* p);
-int32_t fcn8_upscore_bwd(const Fcn8UpscoreParams* p, void* workspace, size_t workspace_bytes, void* stream);
-
-/* ---- loss / predictor: fcn8s_tensorflow.py:253 (softmax_cross_entropy_with_logits + reduce_mean), :268-269.
- * logits (and dlogits, same layout): pixel (n,y,x) at ((n*(H+2*pad) + y+pad)*(W+2*pad) + x+pad)*CP, CP >= C -- pad = 0,
- * CP = C is the dense [N,H,W,C] tensor; pad = 4, CP = fcn8_upscore_tc_cp(C, 8) is the padded output of
- * fcn8_upscore_tc_fwd.  labels: uint8 dense [N,H,W,C] one-hot as yielded by the generators (numpy bool), used as fp32
- * weights y_c like TF does.
- * loss_sum (fp32 scalar, accumulated; caller zeroes) += sum_p (sum_c y_c)*lse(z) - sum_c y_c z_c;
- * dlogits[p][c] = (softmax_c * sum_c y_c - y_c) * grad_scale   (grad_scale = 1/(N*H*W)), channels C..CP-1 = 0;
- * dbias[c] (accumulated; caller zeroes) += sum_p dlogits[p][c]  (bias gradient of the last transposed conv);
- * softmax fp32 dense [N,H,W,C] / argmax int64 dense [N,H,W] (first max) for predict().  Any output may be NULL;
- * softmax and dlogits are mutually exclusive. */
-typedef struct {
-  const float* logits;
+  const void* x;       /* input planes [N,h,w,.]: 64 readable channels per pixel, zero beyond C */
+  const void* x_lo;
+  int32_t x_ld;        /* pixel stride of x in elements */
+  int64_t x_sH, x_sN;  /* row / image strides in elements (0 = dense) */
+  const void* w;       /* packed operand: w_fwd (fwd, loss) or w_dx (dx) */
+  const void* w_lo;
+  const float* bias_big;
+  void* out;           /* fwd: [N, s*h, s*w, .] planes; dx: [N,h,w,.] planes */
+  void* out_lo;
+  int32_t out_ld;
+  int64_t out_sH, out_sN;
+  const void* skip;    /* fwd: same geometry as out */
+  const void* skip_lo;
+  const void* dz;      /* dx, dw: padded blocked planes */
+  const void* dz_lo;
+  float* dT;           /* dw */
+  float* colsum;       /* dx, optional */
+  int32_t colsum_n;    /* 0 = C */
+  int32_t N, h, wd, C, stride, nseg;   /* x is [N,h,wd,.] */
+  /* fcn8_deconv_loss outputs / inputs (NULL = not requested) */
   const uint8_t* labels;
   float* loss_sum;
-  float* dlogits;
   float* dbias;
+  void* dz_hi_out;
+  void* dz_lo_out;
+  float* logits;
   float* softmax;
   int64_t* argmax;
-  int32_t N, H, W, C, CP, pad;
+  uint64_t* conf;
   float grad_scale;
-} Fcn8SoftmaxParams;
-int32_t fcn8_softmax_xent(const Fcn8SoftmaxParams* p, void* stream);
+} Fcn8DeconvParams;
+int32_t fcn8_deconv_cp(int32_t stride);
+int32_t fcn8_deconv_pack(const float* T, const float* bias, int32_t C, int32_t stride, void* w_fwd, void* w_fwd_lo,
+                         void* w_dx, void* w_dx_lo, float* bias_big, void* stream);
+int32_t fcn8_deconv_fwd(const Fcn8DeconvParams* p, void* stream);
+int32_t fcn8_deconv_loss(const Fcn8DeconvParams* p, void* stream);
+int32_t fcn8_deconv_dx(const Fcn8DeconvParams* p, void* stream);
+size_t fcn8_deconv_dw_workspace_bytes(const Fcn8DeconvParams* p);
+int32_t fcn8_deconv_dw(const Fcn8DeconvParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- transposed convolutions on the tensor cores (tf.layers.conv2d_transpose k=2s, stride s, 'same',
- * fcn8s_tensorflow.py:204-233, and its autodiff :257) as phase GEMMs on tcgen05 (kind::tf32; nseg = 3: 3xTF32):
- * an s x s block of outputs depends on a 2x2 input neighbourhood, so with rows = blocks (J,I), J in [0,h], I in [0,w],
- *   Zblock[(dy,dx,co)] = sum_{(ty,tx,ci)} x[n, J-1+ty, I-1+tx, ci] * T[dy+s(1-ty), dx+s(1-tx), co, ci] + bias[co].
- * The blocks tile a PADDED tensor zp[N, s*(h+1), s*(w+1), CP] whose interior [s/2 : s/2+s*h, s/2 : s/2+s*w] is the
- * transposed convolution's output (pixel (oy,ox) at zp[n, oy+s/2, ox+s/2, :]); CP = fcn8_upscore_tc_cp(C, s).
- * The border of zp holds don't-care values after fwd and MUST be zero in the dz passed to dx / dw.
- * x / dx: [N,h,w,ldx] fp32, ldx a multiple of 4 >= C, channels >= C zero.
- * Operands come from fcn8_upscore_tc_pack (w_fwd [s*s*CP][128], w_dx [64][4*s*s*CP], bias_big [s*s*CP]; the *_lo
- * arrays are the low halves of the tf32 split, NULL for single-pass tf32). */
-typedef struct {
-  const float* T;     /* [2s,2s,C,C] (kh,kw,out,in) */
-  const float* bias;  /* [C] */
-  float* w_fwd;
-  float* w_fwd_lo;
-  float* w_dx;
-  float* w_dx_lo;
-  float* bias_big;
-  int32_t C, stride;
-} Fcn8UpscorePackParams;
-typedef struct {
-  const float* x;
-  const float* x_lo;
-  const float* w;     /* fwd: w_fwd, dx: w_dx */
-  const float* w_lo;
-  const float* bias_big;
-  float* zp;          /* fwd: output; dx / dw: dz input */
-  const float* zp_lo;
-  float* dx;
-  float* dT;          /* dw: [2s,2s,C,C] TF layout */
-  int32_t N, h, wd, C, stride, ldx, nseg; /* x is [N,h,wd,ldx] */
-} Fcn8UpscoreTcParams;
-int32_t fcn8_upscore_tc_cp(int32_t C, int32_t stride);
-/* Skip connections around the padded tensors (tf.add, fcn8s_tensorflow.py:213,224).  (h, w) are the INPUT dims of the
- * transposed convolution, its output is [N, stride*h, stride*w, .].
- * gather:  f[n,y,x,c] = zp[n, y+stride/2, x+stride/2, c] + skip[n,y,x,c] (skip may be NULL), c < C; channels C..ldf-1 = 0.
- * scatter: dzp interior = g (border / pad channels untouched: keep them zero); dbias[c] += sum over pixels of g. */
-int32_t fcn8_upscore_tc_gather(const float* zp, const float* skip, float* f, int32_t N, int32_t h, int32_t w,
-                               int32_t C, int32_t stride, int32_t ldf, int32_t ld_skip, void* stream);
-int32_t fcn8_upscore_tc_scatter(const float* g, float* dzp, float* dbias, int32_t N, int32_t h, int32_t w, int32_t C,
-                                int32_t stride, int32_t ldg, void* stream);
-int32_t fcn8_upscore_tc_pack(const Fcn8UpscorePackParams* p, void* stream);
-int32_t fcn8_upscore_tc_fwd(const Fcn8UpscoreTcParams* p, void* stream);
-int32_t fcn8_upscore_tc_dx(const Fcn8UpscoreTcParams* p, void* stream);
-size_t fcn8_upscore_tc_dw_workspace_bytes(const Fcn8UpscoreTcParams* p);
-int32_t fcn8_upscore_tc_dw(const Fcn8UpscoreTcParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- streaming metrics: fcn8s_tensorflow.py:280-301 (labels_argmax, tf.metrics.mean_iou / accuracy); the device
  * analogue of cityscapesscripts/evaluation/addToConfusionMatrix_impl.c:3-16: conf[gt*C + pred] += 1 (uint64). */

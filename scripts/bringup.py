@@ -342,150 +342,6 @@ def elementwise_kernels():
     return ok
 
 
-@case
-def decoder_kernels():
-    from fcn8s_tensorflow_b200 import ops
-    dev = torch.device("cuda")
-    ok = True
-    torch.manual_seed(6)
-    for Cc in (20, 3, 2):
-        for dtype in (0, 1):
-            tdt = ops.torch_dtype(dtype)
-            x = torch.randn(2, 6, 10, 256, device=dev).clamp_min(0).to(tdt)
-            K = torch.randn(256, Cc, device=dev) * 0.05
-            b = torch.randn(Cc, device=dev)
-            s = ops.score_head_fwd(x, K, b, 0.01)
-            ref = 0.01 * (x.double().reshape(-1, 256) @ K.double()) + b.double()
-            ok &= report("head fwd C%d dt%d" % (Cc, dtype), s.reshape(-1, Cc), ref, 1e-5)
-            ds = torch.randn_like(s)
-            dK = torch.empty_like(K)
-            db = torch.empty_like(b)
-            dx = torch.empty_like(x)
-            ops.score_head_bwd(x, K, ds, 0.01, dK, db, dx, mask=True, mask_scale=2.0)
-            ok &= report("head bwd dK", dK, 0.01 * x.double().reshape(-1, 256).t() @ ds.double().reshape(-1, Cc), 1e-5)
-            ok &= report("head bwd db", db, ds.double().reshape(-1, Cc).sum(0), 1e-5)
-            refdx = 0.01 * (ds.double().reshape(-1, Cc) @ K.double().t()).reshape(x.shape) * (x.double() > 0) * 2.0
-            ok &= report("head bwd dx", dx, refdx, 1e-5 if dtype else 5e-3)
-        for s_, (h, w) in ((2, (5, 7)), (2, (16, 32)), (8, (4, 6))):
-            if s_ == 8 and Cc > 4:
-                continue   # the CUDA-core path keeps the whole filter in shared memory; 8x at C=20 is tensor-core only
-            k = 2 * s_
-            x = torch.randn(2, h, w, Cc, device=dev)
-            T = torch.randn(k, k, Cc, Cc, device=dev) * 0.1
-            bias = torch.randn(Cc, device=dev)
-            skip = torch.randn(2, h * s_, w * s_, Cc, device=dev)
-            y = ops.upscore_fwd(x, T, bias, s_, skip=skip)
-            xr = x.double().permute(0, 3, 1, 2).requires_grad_(True)
-            Tr = T.double().permute(3, 2, 0, 1).contiguous().requires_grad_(True)   # [ci, co, a, b]
-            yr = F.conv_transpose2d(xr, Tr, stride=s_, padding=s_ // 2) + bias.double().view(1, -1, 1, 1)
-            ok &= report("upscore fwd C%d s%d" % (Cc, s_), y, yr.permute(0, 2, 3, 1) + skip.double(), 1e-5)
-            dy = torch.randn_like(y)
-            yr.backward(dy.double().permute(0, 3, 1, 2))
-            dT = torch.empty_like(T)
-            dbias = torch.empty_like(bias)
-            dx = torch.empty_like(x)
-            ops.upscore_bwd(x, T, dy, s_, dT, dbias, dx)
-            ok &= report("upscore bwd dx", dx, xr.grad.permute(0, 2, 3, 1), 1e-5)
-            ok &= report("upscore bwd dT", dT, Tr.grad.permute(2, 3, 1, 0), 1e-5)
-            ok &= report("upscore bwd dbias", dbias, dy.double().sum((0, 1, 2)), 1e-5)
-        # softmax / xent: dense layout (pad 0, CP = C) and the padded layout of the tensor-core upscore8 stage
-        P = 5000
-        for pad, CP, (n_, h_, w_) in ((0, Cc, (1, 1, P)), (4, (Cc + 3) // 4 * 4, (2, 24, 160)), (4, (Cc + 3) // 4 * 4, (1, 8, 96))):
-            P = n_ * h_ * w_
-            zfull = torch.randn(n_, h_ + 2 * pad, w_ + 2 * pad, CP, device=dev) * 3
-            z = zfull[:, pad:pad + h_, pad:pad + w_, :Cc].reshape(P, Cc)
-            ids = torch.randint(0, Cc, (P,), device=dev)
-            onehot = F.one_hot(ids, Cc).to(torch.uint8).view(n_, h_, w_, Cc)
-            loss = torch.zeros(1, device=dev)
-            dzfull = torch.zeros_like(zfull)
-            dbias = torch.zeros(Cc, device=dev)
-            sm = torch.empty(n_, h_, w_, Cc, device=dev)
-            am = torch.empty(n_, h_, w_, dtype=torch.int64, device=dev)
-            ops.softmax_xent(zfull, onehot, loss, dzfull, None, am, grad_scale=1.0 / P, dbias=dbias, pad=pad,
-                             num_classes=Cc)
-            ops.softmax_xent(zfull, softmax=sm, pad=pad, num_classes=Cc)
-            zr = z.double().requires_grad_(True)
-            lr = F.cross_entropy(zr, ids, reduction="sum")
-            lr.backward()
-            dz = dzfull[:, pad:pad + h_, pad:pad + w_, :Cc].reshape(P, Cc)
-            ok &= report("xent loss C%d pad%d" % (Cc, pad), loss, lr.detach().view(1), 1e-5)
-            ok &= report("xent dz", dz, zr.grad / P, 1e-5)
-            ok &= report("xent dbias", dbias, (zr.grad / P).sum(0), 1e-4)
-            ok &= report("softmax", sm.view(P, Cc), F.softmax(z.double(), -1), 1e-5)
-            ok &= bool((am.view(P) == z.argmax(-1)).all().item())
-            if pad:
-                border = dzfull.clone()
-                border[:, pad:pad + h_, pad:pad + w_, :] = 0
-                ok &= bool((border == 0).all().item()) and bool((dzfull[..., Cc:] == 0).all().item())
-        am = am.view(-1)
-        onehot = onehot.view(P, Cc)
-        conf = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
-        ops.confusion_matrix(am, onehot, conf)
-        refc = torch.zeros(Cc, Cc, dtype=torch.int64, device=dev)
-        refc.view(-1).index_add_(0, ids * Cc + am, torch.ones(P, dtype=torch.int64, device=dev))
-        ok &= bool((conf == refc).all().item())
-        print("  confusion matrix C%d exact: %s" % (Cc, bool((conf == refc).all().item())))
-    return ok
-
-
-def upscore_tc_case(Cc, s_, N, h, w, nseg, tol):
-    """Tensor-core transposed convolution (phase GEMM) fwd / dx / dw vs fp64 conv_transpose2d autograd."""
-    from fcn8s_tensorflow_b200 import ops
-    dev = torch.device("cuda")
-    torch.manual_seed(11)
-    k = 2 * s_
-    ldx = (Cc + 3) // 4 * 4
-    x = torch.zeros(N, h, w, ldx, device=dev)
-    x[..., :Cc] = torch.randn(N, h, w, Cc, device=dev)
-    T = torch.randn(k, k, Cc, Cc, device=dev) * 0.1
-    bias = torch.randn(Cc, device=dev)
-    packed = ops.upscore_tc_pack(T, bias, s_, split=(nseg == 3))
-    zp = ops.upscore_tc_alloc(N, h, w, Cc, s_, dev)
-    x_lo = ops.split_tf32(x)[1] if nseg == 3 else None
-    ops.upscore_tc_fwd(x, packed, Cc, s_, zp, x_lo=x_lo)
-    y = ops.upscore_tc_interior(zp, Cc, s_)
-    xr = x[..., :Cc].double().permute(0, 3, 1, 2).requires_grad_(True)
-    Tr = T.double().permute(3, 2, 0, 1).contiguous().requires_grad_(True)   # [ci, co, a, b]
-    yr = F.conv_transpose2d(xr, Tr, stride=s_, padding=s_ // 2) + bias.double().view(1, -1, 1, 1)
-    tag = "C%d s%d N%d %dx%d seg%d" % (Cc, s_, N, h, w, nseg)
-    ok = report("upscore_tc fwd " + tag, y, yr.permute(0, 2, 3, 1), tol)
-    dy = torch.randn(N, h * s_, w * s_, Cc, device=dev)
-    yr.backward(dy.double().permute(0, 3, 1, 2))
-    dzp = ops.upscore_tc_alloc(N, h, w, Cc, s_, dev, zero=True)
-    ops.upscore_tc_interior(dzp, Cc, s_).copy_(dy)
-    dzp_lo = ops.split_tf32(dzp)[1] if nseg == 3 else None
-    dx = torch.full((N, h, w, ldx), float("nan"), device=dev)
-    ops.upscore_tc_dx(dzp, packed, Cc, s_, dx, dzp_lo=dzp_lo)
-    # dx reduces over K = 4*s*s*CP (5120 at s=8, C=20): the TMEM accumulator rounds toward zero on every MMA, which
-    # costs ~2^-25 per accumulation step (measured: error grows linearly with K), so the 3xTF32 bound here is 1e-4
-    ok &= report("upscore_tc dx  " + tag, dx[..., :Cc], xr.grad.permute(0, 2, 3, 1), max(tol, 1e-4))
-    ok &= bool((dx[..., Cc:] == 0).all().item())
-    dT = torch.full_like(T, float("nan"))
-    ops.upscore_tc_dw(x, dzp, Cc, s_, dT, x_lo=x_lo, dzp_lo=dzp_lo)
-    ok &= report("upscore_tc dT  " + tag, dT, Tr.grad.permute(2, 3, 1, 0), tol)
-    return ok
-
-
-@case
-def upscore_tc_stride8():
-    ok = True
-    for Cc in (20, 3, 2):
-        ok &= upscore_tc_case(Cc, 8, 2, 4, 6, 3, 2e-6)
-        ok &= upscore_tc_case(Cc, 8, 1, 9, 17, 1, 2e-3)
-    ok &= upscore_tc_case(20, 8, 3, 16, 24, 3, 2e-6)      # several m-tiles, ragged
-    ok &= upscore_tc_case(5, 8, 2, 8, 12, 3, 2e-6)
-    return ok
-
-
-@case
-def upscore_tc_stride2():
-    ok = True
-    for Cc in (20, 3):
-        ok &= upscore_tc_case(Cc, 2, 2, 5, 7, 3, 2e-6)
-        ok &= upscore_tc_case(Cc, 2, 2, 16, 32, 1, 2e-3)
-    return ok
-
-
 # ---------------------------------------------------------------------------------------------------------------------
 # bf16 / bf16 hi-lo pair modes that read the TF-layout (HWIO) weight shadow in place (no packing)
 def _shadow(w, pair):
@@ -640,7 +496,7 @@ def pair_epilogues_and_wgrad():
 
 @case
 def pair_elementwise():
-    """Feed, pooling, bias-gradient, score heads and the Adam shadow in the bf16 hi/lo pair format."""
+    """Feed, pooling, bias-gradient and the Adam shadow in the bf16 hi/lo pair format."""
     from fcn8s_tensorflow_b200 import ops
     dev = torch.device("cuda")
     torch.manual_seed(23)
@@ -667,19 +523,6 @@ def pair_elementwise():
         db = torch.empty(Cc, device=dev)
         ops.bias_grad(g, db, pair=True)
         ok &= report("bias_grad pair C%d" % Cc, db, ops.from_pair(g).double().sum(0), 1e-5)
-    Cc = 20
-    xh = ops.to_pair(torch.randn(2, 6, 10, 256, device=dev).clamp_min(0))
-    xq = ops.from_pair(xh).double()
-    K = torch.randn(256, Cc, device=dev) * 0.05
-    b = torch.randn(Cc, device=dev)
-    s = ops.score_head_fwd(xh, K, b, 0.01, pair=True)
-    ok &= report("head fwd pair", s.reshape(-1, Cc), 0.01 * (xq.reshape(-1, 256) @ K.double()) + b.double(), 1e-5)
-    ds = torch.randn_like(s)
-    dK, dbb, dxp = torch.empty_like(K), torch.empty_like(b), torch.empty_like(xh)
-    ops.score_head_bwd(xh, K, ds, 0.01, dK, dbb, dxp, mask=True, mask_scale=2.0, pair=True)
-    ok &= report("head bwd dK pair", dK, 0.01 * xq.reshape(-1, 256).t() @ ds.double().reshape(-1, Cc), 1e-5)
-    refdx = 0.01 * (ds.double().reshape(-1, Cc) @ K.double().t()).reshape(xq.shape) * (xq > 0) * 2.0
-    ok &= report("head bwd dx pair", ops.from_pair(dxp), refdx, 2e-5)
     # Adam refreshes the shadow
     n = 100003
     p = torch.randn(n, device=dev)
@@ -692,6 +535,243 @@ def pair_elementwise():
     ok &= bool((hi == p.to(torch.bfloat16)).all().item())
     ok &= bool((lo == (p - hi.float()).to(torch.bfloat16)).all().item())
     ok &= report("shadow hi+lo ~ p", hi.float() + lo.float(), p, 2e-5)
+    return ok
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Decoder on the tensor cores: score heads, transposed convolutions as phase GEMMs over bf16 hi/lo planes, the loss /
+# predictor epilogue, the fused max-pool, the reduced-product modes
+def ref_deconv(x, T, bias, s):
+    """tf.layers.conv2d_transpose(k = 2s, stride s, 'same') in fp64: x [N,h,w,C], T [2s,2s,Cout,Cin] -> [N,sh,sw,C]."""
+    y = F.conv_transpose2d(x.double().permute(0, 3, 1, 2), T.double().permute(3, 2, 0, 1), bias.double(), stride=s,
+                           padding=s // 2)
+    return y.permute(0, 2, 3, 1)
+
+
+def _pair_q(t):
+    """value an fp32 tensor takes when stored as a bf16 hi/lo pair."""
+    hi = t.to(torch.bfloat16)
+    return hi.double() + (t - hi.float()).to(torch.bfloat16).double()
+
+
+@case
+def decoder_heads():
+    """1x1 score heads through fcn8_conv_gemm / fcn8_wgrad_gemm with the classes padded to 64 columns: forward with
+    the skip scale and bias, input gradient (with the fc7 mask), kernel gradient clipped to C columns."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(41)
+    ok = True
+    for pair, tol in ((True, 2e-5), (False, 1e-2)):
+        for Cc, cin, scale in ((20, 256, 1e-2), (5, 512, 1.0), (2, 4096, 1e-4)):
+            N, h, w = 2, 6, 10
+            x32 = torch.randn(N, h, w, cin, device=dev).clamp_min(0)
+            x = ops.to_pair(x32) if pair else x32.to(torch.bfloat16)
+            xq = ops.from_pair(x).double() if pair else x.double()
+            K = torch.randn(cin, Cc, device=dev) * 0.05
+            b = torch.randn(Cc, device=dev)
+            pk = ops.head_pack(K, b, split=pair)
+            Kq = (pk["w"].double() + (pk["w_lo"].double() if pair else 0))[:, :Cc]
+            nseg = 3 if pair else 1
+            S = torch.full((N, h, w, 128), float("nan"), dtype=torch.bfloat16, device=dev)
+            ops.conv_gemm(x, pk["w"], 64, 1, bias=pk["bias64"], flags=ops.EPI_BIAS, out=S, wp_lo=pk["w_lo"], pair=pair,
+                          out_pair=True, w_mode=1, out_scale=scale, nseg=nseg)
+            got = ops.from_pair(S)
+            ref = scale * (xq.reshape(-1, cin) @ Kq) + b.double()
+            tag = "C%d Cin%d pair%d" % (Cc, cin, pair)
+            ok &= report("head fwd " + tag, got[..., :Cc].reshape(-1, Cc), ref, tol)
+            ok &= bool((got[..., Cc:] == 0).all().item())
+            # backward: ds planes as a strided interior view of a padded tensor (what the engine passes)
+            ds32 = torch.randn(N, h, w, Cc, device=dev)
+            pad = ops.planes_alloc(N, h + 2, w + 2, dev, 64)
+            dsv = tuple(t[:, 1:-1, 1:-1, :] for t in pad)
+            dsv[0][..., :Cc] = ds32.to(torch.bfloat16)
+            dsv[1][..., :Cc] = (ds32 - dsv[0][..., :Cc].float()).to(torch.bfloat16)
+            dsq = (dsv[0].double() + (dsv[1].double() if pair else 0))[..., :Cc]
+            dK = torch.full((cin, Cc), float("nan"), device=dev)
+            ops.wgrad_gemm(x, dsv[0], 1, dK, dy_lo=dsv[1], pair=pair, dy_pair=False, nseg=nseg, out_cols=Cc,
+                           out_scale=scale)
+            ok &= report("head dK " + tag, dK, scale * xq.reshape(-1, cin).t() @ dsq.reshape(-1, Cc), tol)
+            dx = torch.empty_like(x)
+            ops.conv_gemm(dsv[0], pk["w"], cin, 1, x_lo=dsv[1] if pair else None, wp_lo=pk["w_lo"], w_mode=2, out=dx,
+                          out_pair=pair, out_scale=scale, nseg=nseg, cin=64, flags=ops.EPI_MASK, mask_src=x,
+                          mask_scale=2.0)
+            refdx = scale * (dsq.reshape(-1, Cc) @ Kq.t()).reshape(xq.shape) * (xq > 0) * 2.0
+            ok &= report("head dx " + tag, ops.from_pair(dx) if pair else dx, refdx, tol)
+    return ok
+
+
+def deconv_case(Cc, s, N, h, w, nseg, tol):
+    """fwd (s = 2: dense + skip; s = 8: every output of the loss epilogue), dx (+ column sums) and dT of one stage."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(50 + s + Cc)
+    ok = True
+    tag = "C%d s%d N%d %dx%d seg%d" % (Cc, s, N, h, w, nseg)
+    T = torch.randn(2 * s, 2 * s, Cc, Cc, device=dev) * 0.2
+    bias = torch.randn(Cc, device=dev)
+    pk = ops.deconv_pack(T, bias, s, split=nseg > 1)
+    Tq = _pair_q(T) if nseg == 3 else T.to(torch.bfloat16).double()
+    x32 = torch.randn(N, h, w, Cc, device=dev)
+    xp = ops.planes_from_float(x32)
+    xq = ops.planes_to_float(xp, Cc).double() if nseg == 3 else xp[0][..., :Cc].double()
+    H, W = s * h, s * w
+    ref = ref_deconv(xq, Tq, bias, s)
+    if s == 2:
+        skip32 = torch.randn(N, H, W, Cc, device=dev)
+        skp = ops.planes_from_float(skip32)
+        out_t = torch.full((N, H, W, 128), float("nan"), dtype=torch.bfloat16, device=dev)
+        out = ops.halves(out_t, 64)
+        ops.deconv_fwd(xp, pk, Cc, s, out, skip=skp, nseg=nseg)
+        got = ops.planes_to_float(out, 64)
+        ok &= report("deconv fwd+skip " + tag, got[..., :Cc], ref + ops.planes_to_float(skp, Cc).double(), tol)
+        ok &= bool((got[..., Cc:] == 0).all().item())
+    else:
+        ids = torch.randint(0, Cc, (N, H, W), device=dev)
+        onehot = F.one_hot(ids, Cc).to(torch.uint8)
+        # a few rows that are not one-hot: TF's fused op still back-propagates softmax - labels
+        onehot[0, 0, :4] = 0
+        onehot[0, 1, :4, :min(2, Cc)] = 1
+        logits = torch.full((N, H, W, Cc), float("nan"), device=dev)
+        sm = torch.full((N, H, W, Cc), float("nan"), device=dev)
+        am = torch.full((N, H, W), -1, dtype=torch.int64, device=dev)
+        loss = torch.zeros(1, device=dev)
+        dbias = torch.zeros(Cc, device=dev)
+        conf = torch.zeros((Cc, Cc), dtype=torch.int64, device=dev)
+        dz = ops.padded_alloc(N, h, w, 8, dev)
+        gs = 1.0 / (N * H * W)
+        ops.deconv_loss(xp, pk, Cc, nseg=nseg, labels=onehot, loss_sum=loss, dz_out=dz, dbias=dbias, grad_scale=gs,
+                        logits=logits, softmax=sm, argmax=am, conf=conf)
+        torch.cuda.synchronize()
+        ok &= report("loss-epilogue logits " + tag, logits, ref, tol)
+        z = logits.double()    # the rest is checked against the kernel's own logits (tight)
+        y = onehot.double()
+        lse = torch.logsumexp(z, -1)
+        ok &= report("loss sum", loss, ((y.sum(-1) * lse) - (y * z).sum(-1)).sum().view(1), 1e-5)
+        ok &= report("softmax", sm, torch.softmax(z, -1), 1e-5)
+        ok &= bool(torch.equal(am, z.argmax(-1)))
+        dzi = ops.padded_interior(dz, 8)
+        dz_ref = (torch.softmax(z, -1) - y) * gs
+        ok &= report("dz planes", ops.planes_to_float(dzi, Cc), dz_ref, 2e-5)
+        ok &= report("dbias", dbias, dz_ref.sum((0, 1, 2)), 1e-4)
+        full = dz[0].float() + dz[1].float()
+        border = full.clone()
+        border[:, 4:-4, 4:-4, :Cc] = 0
+        ok &= bool((border == 0).all().item())
+        cm = torch.zeros((Cc, Cc), dtype=torch.int64, device=dev)
+        cm.index_put_((onehot.argmax(-1).reshape(-1), am.reshape(-1)), torch.ones(N * H * W, dtype=torch.int64, device=dev),
+                      accumulate=True)
+        same = bool(torch.equal(cm, conf))
+        print("  %-44s %s" % ("confusion matrix (epilogue) exact", "OK" if same else "FAIL"))
+        ok &= same
+        # each output alone (other pointers NULL)
+        am2 = torch.empty_like(am)
+        ops.deconv_loss(xp, pk, Cc, nseg=nseg, argmax=am2)
+        sm2 = torch.empty_like(sm)
+        ops.deconv_loss(xp, pk, Cc, nseg=nseg, softmax=sm2)
+        ok &= bool(torch.equal(am2, am)) and bool(torch.equal(sm2, sm))
+    # backward of the stage from a dense output gradient g
+    g32 = torch.randn(N, H, W, Cc, device=dev)
+    dzp = ops.padded_alloc(N, h, w, s, dev)
+    gi = ops.padded_interior(dzp, s)
+    gi[0][..., :Cc] = g32.to(torch.bfloat16)
+    gi[1][..., :Cc] = (g32 - gi[0][..., :Cc].float()).to(torch.bfloat16)
+    gq = ops.planes_to_float(gi, Cc).double() if nseg == 3 else gi[0][..., :Cc].double()
+    xr = xq.clone().requires_grad_(True)
+    Tr = Tq.clone().requires_grad_(True)
+    ref_deconv(xr, Tr, bias, s).backward(gq)
+    nxt = ops.planes_alloc(N, h + 2, w + 2, dev, 64)          # dx lands in the interior of a padded tensor
+    dxv = tuple(t[:, 1:-1, 1:-1, :] for t in nxt)
+    cs = torch.zeros(Cc, device=dev)
+    ops.deconv_dx(dzp, pk, Cc, s, dxv, nseg=nseg, colsum=cs)
+    got = ops.planes_to_float(dxv, Cc)
+    ok &= report("deconv dx " + tag, got, xr.grad, tol)
+    ok &= report("deconv dx colsum", cs, got.double().sum((0, 1, 2)), 1e-4)
+    dT = torch.full_like(T, float("nan"))
+    ops.deconv_dw(xp, dzp, Cc, s, dT, nseg=nseg)
+    ok &= report("deconv dT " + tag, dT, Tr.grad, tol)
+    return ok
+
+
+@case
+def deconv_stride2():
+    ok = deconv_case(20, 2, 2, 6, 10, 3, 2e-5)
+    ok &= deconv_case(5, 2, 3, 9, 13, 3, 2e-5)      # ragged tiles of blocks
+    ok &= deconv_case(2, 2, 1, 16, 32, 1, 1e-2)     # bf16 mode (hi planes only)
+    return ok
+
+
+@case
+def deconv_stride8_loss():
+    ok = deconv_case(20, 8, 2, 6, 10, 3, 2e-5)
+    ok &= deconv_case(5, 8, 1, 9, 13, 3, 2e-5)      # C % 4 != 0: byte label path
+    ok &= deconv_case(2, 8, 2, 12, 8, 3, 2e-5)
+    ok &= deconv_case(20, 8, 1, 16, 32, 1, 1e-2)    # bf16 mode; 561 blocks = 5 M tiles (odd: pair partner past the end)
+    return ok
+
+
+@case
+def fused_pool():
+    """EPI_POOL: the 2x2 max-pool emitted by the conv epilogue equals the stand-alone pool of the stored tensor bit for
+    bit, for the halo kernels, the per-tap CTA-pair kernel, bf16 and hi/lo pair storage, with and without the
+    full-resolution store."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(61)
+    ok = True
+    for (N, H, W, cin, cout, pair) in ((2, 32, 48, 64, 64, False), (1, 20, 36, 64, 128, True), (3, 12, 20, 256, 256, False),
+                                        (2, 4, 6, 512, 512, True), (1, 16, 8, 128, 128, False)):
+        w = torch.randn(3, 3, cin, cout, device=dev) / (9 * cin) ** 0.5
+        b = torch.randn(cout, device=dev)
+        wh, wl = _shadow(w, pair)
+        x32 = torch.randn(N, H, W, cin, device=dev)
+        x = ops.to_pair(x32) if pair else x32.to(torch.bfloat16)
+        cm = 2 if pair else 1
+        y_ref = ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1)
+        p_ref = ops.maxpool_fwd(y_ref, pair=pair)
+        pooled = torch.full((N, H // 2, W // 2, cm * cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        y = ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1,
+                          pool_out=pooled)
+        pooled2 = torch.full_like(pooled, float("nan"))
+        ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1,
+                      pool_out=pooled2, store_out=False)
+        torch.cuda.synchronize()
+        # the tile shape differs from the unfused run's, the accumulation order inside a tile does not
+        same = bool(torch.equal(y, y_ref)) and bool(torch.equal(pooled, p_ref)) and bool(torch.equal(pooled2, p_ref))
+        print("  fused pool N%d %dx%d Cin%d Cout%d pair%d: %s" % (N, H, W, cin, cout, pair, "OK" if same else "FAIL"))
+        if not same:
+            a = ops.from_pair(pooled) if pair else pooled
+            r = ops.from_pair(p_ref) if pair else p_ref
+            report("   pooled vs stand-alone pool", a, r, 0.0)
+            report("   full-res vs unfused", ops.from_pair(y) if pair else y, ops.from_pair(y_ref) if pair else y_ref, 0.0)
+        ok &= same
+    return ok
+
+
+@case
+def reduced_products():
+    """nseg = 2 / 1 on pair operands (the measured reduced-backward modes): x * (w_hi + w_lo) and x_hi * w_hi."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(62)
+    ok = True
+    N, H, W, cin, cout, k = 2, 16, 32, 128, 128, 3
+    w = torch.randn(k, k, cin, cout, device=dev) / (k * k * cin) ** 0.5
+    wh, wl = _shadow(w, True)
+    dy = ops.to_pair(torch.randn(N, H, W, cout, device=dev))
+    dyh = dy[..., :cout].double()
+    for nseg, wq in ((2, wh.double() + wl.double()), (1, wh.double())):
+        dx = ops.conv_gemm(dy, wh, cin, k, wp_lo=wl, pair=True, w_mode=2, nseg=nseg)
+        ref = F.conv_transpose2d(dyh.permute(0, 3, 1, 2), wq.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+        ok &= report("dgrad nseg %d" % nseg, ops.from_pair(dx), ref, 2e-5)
+    x = ops.to_pair(torch.randn(N, H, W, cin, device=dev))
+    xh = x[..., :cin].double()
+    for nseg, dq in ((2, ops.from_pair(dy).double()), (1, dyh)):
+        dw = torch.empty(k * k * cin, cout, device=dev)
+        ops.wgrad_gemm(x, dy, k, dw, pair=True, nseg=nseg)
+        cols = F.unfold(F.pad(xh.permute(0, 3, 1, 2), (1,) * 4), k).view(N, cin, k * k, H * W)
+        ref = torch.einsum("nctp,npo->tco", cols, dq.reshape(N, H * W, cout)).reshape(k * k * cin, cout)
+        ok &= report("wgrad nseg %d" % nseg, dw, ref, 2e-5)
     return ok
 
 

@@ -16,11 +16,11 @@ images, labels = oracle.synthetic_batch(N, H, W, C, seed=7)
 dev = torch.device("cuda", 0)
 with torch.no_grad():
     logits, inter = oracle.forward(weights, images, dtype=torch.float64, return_intermediates=True)
-for precision in sys.argv[1:] or ["fp32", "tf32x3"]:
+for precision in sys.argv[1:] or ["fp32"]:
     e = Engine(C, precision=precision, device=dev)
     e.load_weights(weights)
     x = torch.from_numpy(images).to(dev)
-    e.forward(x)
+    e.forward(x, train=True)   # train=True: the pre-pool activations are stored too
     torch.cuda.synchronize()
     A = e._arena(N, H, W)
     print("==== %s" % precision)

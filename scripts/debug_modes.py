@@ -14,7 +14,7 @@ C, N, H, W = 5, 2, 64, 96
 weights = oracle.init_weights(C, seed=2, decoder_std_scale=10.0)
 images, labels = oracle.synthetic_batch(N, H, W, C, seed=0)
 dev = torch.device("cuda", 0)
-for precision in sys.argv[1:] or ["tf32", "bf16"]:
+for precision in sys.argv[1:] or ["bf16"]:
     logits, inter = oracle.forward(weights, images, dtype=torch.float64, return_intermediates=True, storage=precision)
     e = Engine(C, precision=precision, device=dev)
     e.load_weights(weights)

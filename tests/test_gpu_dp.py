@@ -41,8 +41,9 @@ def test_engine_on_a_device_that_is_not_the_current_one(cuda_device):
         dev = torch.device("cuda", d)
         e = Engine(5, precision="fp32", device=dev)
         e.load_weights(w)
+        logits = e.forward(torch.from_numpy(img).to(dev)).cpu()
         e.train_step(torch.from_numpy(img).to(dev), torch.from_numpy(lab).to(dev), 1e-4, keep_prob=1.0)
         assert torch.cuda.current_device() == 0
         torch.cuda.synchronize(dev)
-        outs.append((e._arena(1, 64, 96)["logits"].cpu(), e.loss_value((1, 64, 96))))
+        outs.append((logits, e.loss_value((1, 64, 96))))
     assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]

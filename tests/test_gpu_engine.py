@@ -3,18 +3,18 @@ the CPU oracle (oracle/fcn8s_oracle.py, fp64) on the same seeded inputs and weig
 
 Tolerances are relative per tensor (absolute values are meaningless because the reference's skip scales 1e-4 / 1e-2
 and sigma=1e-3 initialisers make some tensors tiny, SURVEY.md section 7 "hard parts"):
-  logits: max|got - ref| / max|ref|   -- "fp32" (bf16 hi/lo pairs, 3 bf16 MMAs per product) and "tf32x3" (3xTF32)
-          1e-4 (the tolerance BASELINE.json's north_star states), "tf32" 1e-2, "bf16" 3e-2.
-  gradients: ||got - ref||_2 / ||ref||_2 -- "fp32" 1e-2 (measured 4e-5..4e-4), "tf32" 1.5e-1 (measured <= 1.1e-1),
-          "bf16" 4e-1 (measured 1.8e-1 .. 2.6e-1).  Gradients are NOT continuous in the activations: one ReLU /
-          max-pool decision that flips inside rounding noise shifts every upstream gradient (the oracle's own fp32
-          evaluation differs from its fp64 evaluation by 2.5e-3 in this norm on this very problem because a single
-          fc6 unit flips).  With tf32 / bf16 activation storage 2e-4 / 1.5e-3 of the units flip per layer on these
-          random weights (scripts/debug_modes.py, also against the quantisation-aware oracle
-          `oracle.forward(storage=...)`: rounding differences amplify chaotically after ~3 layers), which is a
-          norm-wise gradient difference of sqrt(flips x layers) ~ 5 % / 12-25 %.  So for the reduced-precision modes
-          the e2e gradient check is a WIRING check; the per-kernel precision checks live in
-          tests/test_gpu_kernels.py where masks are explicit inputs.
+  logits: max|got - ref| / max|ref|   -- "fp32" (bf16 hi/lo pairs, 3 bf16 MMAs per product) 1e-4 (the tolerance
+          BASELINE.json's north_star states), "bf16" 3e-2.
+  gradients: ||got - ref||_2 / ||ref||_2 -- "fp32" 1e-2 (measured 4e-5 where no unit flips, 2e-3..6e-3 in the layers
+          below conv3_2), "bf16" 4e-1 (measured 1.8e-1 .. 2.6e-1).  Gradients are NOT continuous in the activations:
+          one ReLU / max-pool decision that flips inside rounding noise changes that unit's gradient by 100 % and
+          shifts every upstream gradient.  With 2e-5 relative forward error about 2e-5 of the units flip: a handful
+          among the ~10^6 units of the conv1 / conv2 layers of these test images, none among the 10^4 of conv5, which
+          is a norm-wise difference of sqrt(flips / units) ~ 4e-3 below conv3_2 and nothing above (the oracle's own
+          fp32 evaluation differs from its fp64 evaluation by 2.5e-3 for the same reason).  With bf16 activation
+          storage 1.5e-3 of the units flip per layer (12-25 % in this norm), so for the bf16 mode the e2e gradient
+          check is a WIRING check; the per-kernel precision checks live in tests/test_gpu_kernels.py where masks are
+          explicit inputs.
 """
 import numpy as np
 import pytest
@@ -24,8 +24,8 @@ from oracle import fcn8s_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = {"fp32": 1e-4, "tf32x3": 1e-4, "tf32": 1e-2, "bf16": 3e-2}
-GRAD_TOL = {"fp32": 1e-2, "tf32x3": 1e-2, "tf32": 1.5e-1, "bf16": 4e-1}
+LOGIT_TOL = {"fp32": 1e-4, "bf16": 3e-2}
+GRAD_TOL = {"fp32": 1e-2, "bf16": 4e-1}
 C = 5
 N, H, W = 2, 64, 96
 
@@ -59,7 +59,7 @@ def make_engine(cuda_device, precision, weights, classes=C):
     return e
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_forward_logits(cuda_device, problem, precision):
     e = make_engine(cuda_device, precision, problem["weights"])
     x = torch.from_numpy(problem["images"]).to(cuda_device)
@@ -71,7 +71,7 @@ def test_forward_logits(cuda_device, problem, precision):
     assert err <= LOGIT_TOL[precision], "logits rel err %.3e > %.1e (%s)" % (err, LOGIT_TOL[precision], precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_loss_and_every_gradient(cuda_device, problem, precision):
     e = make_engine(cuda_device, precision, problem["weights"])
     x = torch.from_numpy(problem["images"]).to(cuda_device)
