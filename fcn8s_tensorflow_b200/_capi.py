@@ -21,6 +21,7 @@ EXPORTS = [
     "fcn8_deconv_dx", "fcn8_deconv_dw_workspace_bytes", "fcn8_deconv_dw",
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg", "fcn8_shadow_weights",
     "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_cast_bf16",
+    "fcn8_conv1_fwd", "fcn8_conv1_wgrad_workspace_bytes", "fcn8_conv1_wgrad",
 ]
 
 
@@ -70,6 +71,13 @@ class BiasGradParams(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("db", C.c_void_p), ("P", C.c_int64), ("C", C.c_int32), ("dtype", C.c_int32)]
 
 
+class Conv1Params(C.Structure):
+    _fields_ = [("images", C.c_void_p), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("w", C.c_void_p),
+                ("w_lo", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p), ("out_lo", C.c_void_p),
+                ("out_ld", C.c_int32), ("dy", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_ld", C.c_int32),
+                ("dw", C.c_void_p), ("pair", C.c_int32)]
+
+
 class DeconvParams(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_lo", C.c_void_p), ("x_ld", C.c_int32), ("x_sH", C.c_int64), ("x_sN", C.c_int64),
                 ("w", C.c_void_p), ("w_lo", C.c_void_p), ("bias_big", C.c_void_p),
@@ -109,7 +117,7 @@ def load():
         lib.fcn8_debug_set(int(k), int(v))
     vp, sz = C.c_void_p, C.c_size_t
     for name, pt in [("fcn8_conv_gemm", ConvParams), ("fcn8_wgrad_gemm", WgradParams), ("fcn8_bias_grad", BiasGradParams),
-                     ("fcn8_deconv_dw", DeconvParams)]:
+                     ("fcn8_deconv_dw", DeconvParams), ("fcn8_conv1_wgrad", Conv1Params)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp, sz, vp]
         getattr(lib, name).restype = C.c_int32
         getattr(lib, name + "_workspace_bytes").argtypes = [C.POINTER(pt)]
@@ -117,7 +125,7 @@ def load():
     for name, pt in [("fcn8_preprocess_im2col", PreprocessParams), ("fcn8_pack_weights", PackParams),
                      ("fcn8_maxpool_fwd", PoolParams), ("fcn8_maxpool_bwd", PoolParams),
                      ("fcn8_deconv_fwd", DeconvParams), ("fcn8_deconv_loss", DeconvParams),
-                     ("fcn8_deconv_dx", DeconvParams)]:
+                     ("fcn8_deconv_dx", DeconvParams), ("fcn8_conv1_fwd", Conv1Params)]:
         getattr(lib, name).argtypes = [C.POINTER(pt), vp]
         getattr(lib, name).restype = C.c_int32
     i32 = C.c_int32

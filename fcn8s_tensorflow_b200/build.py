@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfcn8s_sm100.so")
-SOURCES = ["capi.cu", "elementwise.cu", "decoder.cu"]
-HEADERS = ["ptx.cuh", "conv_gemm.cuh", "kernels.h", os.path.join("..", "..", "include", "fcn8s_b200.h")]
+SOURCES = ["capi.cu", "elementwise.cu", "decoder.cu", "conv1.cu"]
+HEADERS = ["ptx.cuh", "conv_gemm.cuh", "kernels.h", "conv1.h", os.path.join("..", "..", "include", "fcn8s_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "../../include/fcn8s_b200.h"
+#include "conv1.h"
 #include "conv_gemm.cuh"
 #include "kernels.h"
 
@@ -1372,6 +1373,114 @@ int32_t fcn8_deconv_dw(const Fcn8DeconvParams* p, void* workspace, size_t worksp
   if (e != cudaSuccess) return cuda_fail(e, "deconv_dw launch");
   e = launch_deconv_unpack_dw(partial, pl.splits, p->dT, p->C, CP, s, st);
   return e == cudaSuccess ? 0 : cuda_fail(e, "deconv_dw unpack launch");
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv1_1 straight from the uint8 image (conv1.cu): the im2col operand exists only in shared memory.
+namespace {
+// rows [P][ld] bf16 seen as a 2-D map (64 columns, P rows), box (64, 128)
+int encode_rows_map(CUtensorMap* m, const void* ptr, long long P, int ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const cuuint64_t dims[2] = {64, (cuuint64_t)P};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FCN8_ERR_CUDA, "cuTensorMapEncodeTiled(rows P %lld ld %d) failed: %d", P, ld, (int)r);
+  return 0;
+}
+int check_conv1(const Fcn8Conv1Params* p, const char* what) {
+  if (!p || !p->images) return fail(FCN8_ERR_BAD_SHAPE, "%s: null pointer", what);
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0) return fail(FCN8_ERR_BAD_SHAPE, "%s: empty tensor", what);
+  if (((long long)p->N * p->H * p->W) % 128) return fail(FCN8_ERR_BAD_SHAPE, "%s: N*H*W must be a multiple of 128", what);
+  return 0;
+}
+int conv1_grid(const Fcn8Conv1Params* p) {
+  const long long tiles = (long long)p->N * p->H * p->W / 128;
+  return (int)(tiles < num_sms() ? tiles : num_sms());
+}
+}  // namespace
+
+extern "C" {
+
+int32_t fcn8_conv1_fwd(const Fcn8Conv1Params* p, void* stream) {
+  int rc = check_conv1(p, "conv1_fwd");
+  if (rc) return rc;
+  if (!p->w || !p->bias || !p->out || (p->pair && (!p->w_lo || !p->out_lo)))
+    return fail(FCN8_ERR_BAD_SHAPE, "conv1_fwd: null pointer");
+  if (!aligned16(p->out) || (p->out_lo && !aligned16(p->out_lo)) || !aligned16(p->w) || !aligned16(p->bias))
+    return fail(FCN8_ERR_BAD_ALIGN, "conv1_fwd: pointers must be 16-byte aligned");
+  CUtensorMap mh, ml;
+  memset(&ml, 0, sizeof(ml));
+  rc = encode_w_map(&mh, p->w, FCN8_BF16, 64, 64, 64);
+  if (rc) return rc;
+  if (p->pair) {
+    rc = encode_w_map(&ml, p->w_lo, FCN8_BF16, 64, 64, 64);
+    if (rc) return rc;
+  } else {
+    ml = mh;
+  }
+  Conv1Args a;
+  memset(&a, 0, sizeof(a));
+  a.img = p->images;
+  a.N = p->N;
+  a.H = p->H;
+  a.W = p->W;
+  a.tiles = (int)((long long)p->N * p->H * p->W / 128);
+  a.pair = p->pair ? 1 : 0;
+  a.out = static_cast<__nv_bfloat16*>(p->out);
+  a.out_lo = static_cast<__nv_bfloat16*>(p->out_lo);
+  a.bias = p->bias;
+  a.out_ld = p->out_ld > 0 ? p->out_ld : 64;
+  a.rz_c = 4.f * rz_per_mma();
+  cudaError_t e = launch_conv1_fwd(mh, ml, a, conv1_grid(p), cur_dev(), (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "conv1_fwd launch");
+}
+
+size_t fcn8_conv1_wgrad_workspace_bytes(const Fcn8Conv1Params* p) {
+  if (check_conv1(p, "conv1_wgrad")) return 0;
+  return (size_t)conv1_grid(p) * (p->pair ? 2 : 1) * 4096 * sizeof(float);
+}
+
+int32_t fcn8_conv1_wgrad(const Fcn8Conv1Params* p, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_conv1(p, "conv1_wgrad");
+  if (rc) return rc;
+  if (!p->dy || !p->dw || (p->pair && !p->dy_lo)) return fail(FCN8_ERR_BAD_SHAPE, "conv1_wgrad: null pointer");
+  const size_t need = fcn8_conv1_wgrad_workspace_bytes(p);
+  if (workspace_bytes < need || !workspace) return fail(FCN8_ERR_WORKSPACE, "conv1_wgrad: workspace too small");
+  const long long P = (long long)p->N * p->H * p->W;
+  const int ld = p->dy_ld > 0 ? p->dy_ld : 64;
+  CUtensorMap mh, ml;
+  rc = encode_rows_map(&mh, p->dy, P, ld);
+  if (rc) return rc;
+  if (p->pair) {
+    rc = encode_rows_map(&ml, p->dy_lo, P, ld);
+    if (rc) return rc;
+  } else {
+    ml = mh;
+  }
+  Conv1Args a;
+  memset(&a, 0, sizeof(a));
+  a.img = p->images;
+  a.N = p->N;
+  a.H = p->H;
+  a.W = p->W;
+  a.tiles = (int)(P / 128);
+  a.pair = p->pair ? 1 : 0;
+  a.partial = static_cast<float*>(workspace);
+  const int grid = conv1_grid(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = launch_conv1_wgrad(mh, ml, a, grid, cur_dev(), st);
+  if (e != cudaSuccess) return cuda_fail(e, "conv1_wgrad launch");
+  // rows 0..26 of every [64][64] partial are the filter taps (kh, kw, c) in TF order
+  e = launch_wgrad_splitk_reduce(static_cast<const float*>(workspace), p->dw, grid * (p->pair ? 2 : 1), 64, 27, 64, 64,
+                                 1.f, st);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "conv1_wgrad reduce launch");
 }
 
 }  // extern "C"

@@ -158,6 +158,7 @@ class Engine:
         self.kp = 64                                         # padded im2col width of conv1_1
         self.conv_algo = int(os.environ.get("FCN8_CONV_ALGO", "0"))   # diagnostics: 1 = per-tap kernels only
         self.fuse_pool = os.environ.get("FCN8_FUSE_POOL", "1") != "0"
+        self.conv1_direct = os.environ.get("FCN8_CONV1_IM2COL", "0") == "0"   # conv1_1 from the uint8 image (conv1.cu)
         self.layers = encoder_layers()
         self.layout, self.n_flat = flat_layout(num_classes)
         self.bias_block = self.layout["fc7/biases"][0]       # encoder biases: [bias_block, n_flat)
@@ -295,9 +296,12 @@ class Engine:
         A = self._arena(N, H, W)
         A["_shape"] = (N, H, W)
         pair = self.pair
-        x = self._act(A, "im2col", N, H, W, self.kp)
-        p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, ops.BF16X2 if pair else self.dt)
-        capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
+        A["images"] = images
+        x = None
+        if not self.conv1_direct:   # the global-im2col variant of conv1_1 (kept for A/B measurements)
+            x = self._act(A, "im2col", N, H, W, self.kp)
+            p = capi.PreprocessParams(capi.ptr(images), capi.ptr(x), N, H, W, ops.BF16X2 if pair else self.dt)
+            capi.check(self.lib.fcn8_preprocess_im2col(ops.C.byref(p), ops._stream()))
         h, w = H, W
         li = 0
         for b, cout, n in VGG_BLOCKS:
@@ -312,7 +316,10 @@ class Engine:
                     pooled = self._act(A, "pool%d" % b, N, h // 2, w // 2, cout)
                     kw = dict(pool_out=pooled, store_out=train)
                 out = self._act(A, name, N, h, w, cout) if (train or pooled is None) else None
-                self._conv(name, x, k, cout, out, self.view(name + "/biases"), ops.EPI_BIAS | ops.EPI_RELU, **kw)
+                if name == "conv1_1" and self.conv1_direct:
+                    ops.conv1_fwd(images, self.packed[name], self.view(name + "/biases"), out, pair=pair)
+                else:
+                    self._conv(name, x, k, cout, out, self.view(name + "/biases"), ops.EPI_BIAS | ops.EPI_RELU, **kw)
                 x = out
             h, w = h // 2, w // 2
             if not self.fuse_pool:
@@ -431,7 +438,10 @@ class Engine:
             if name == "fc7":   # every other bias gradient is fused into the kernel that produces that layer's dY
                 ops.bias_grad(dy, self.view(name + "/biases", G), pair=pair)
             if name == "conv1_1":
-                ops.wgrad_gemm(x_in, dy, 1, gw.view(27, cout), rows_valid=27, pair=pair, nseg=bt)
+                if self.conv1_direct:
+                    ops.conv1_wgrad(A["images"], dy, gw.view(27, cout), pair=pair)
+                else:
+                    ops.wgrad_gemm(x_in, dy, 1, gw.view(27, cout), rows_valid=27, pair=pair, nseg=bt)
                 break
             ops.wgrad_gemm(x_in, dy, k, gw.view(k * k * cin, cout), pair=pair, nseg=bt)
             if name == "fc6" and self.allreduce is not None and getattr(self.allreduce, "overlap", False):
@@ -477,7 +487,7 @@ class Engine:
     def _layer_input(self, A, li):
         name = self.layers[li][0]
         if name == "conv1_1":
-            return A["im2col"]
+            return A.get("im2col")
         if self._input_is_pool(li):
             return A["pool%d" % self._pool_index(li)]
         return A[self.layers[li - 1][0]]

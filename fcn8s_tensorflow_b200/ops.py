@@ -249,6 +249,38 @@ def wgrad_gemm(x, dy, ksize, out, rows_valid=0, x_lo=None, dy_lo=None, force_spl
     return out
 
 
+def conv1_fwd(images, packed, bias, out, pair=False):
+    """conv1_1 + bias + ReLU straight from the uint8 image [N,H,W,3] (im2col operand built in shared memory).
+    packed: (w, w_lo) of pack_weights(conv1_1/filter as [27, 64], ksize 1, cin_pad 64); out: [N,H,W,64] bf16 or the
+    hi/lo pair tensor [N,H,W,128]."""
+    _chk_cuda(images, packed[0], packed[1], bias, out)
+    N, H, W, _ = images.shape
+    p = capi.Conv1Params(capi.ptr(images), N, H, W, capi.ptr(packed[0]), capi.ptr(packed[1]), capi.ptr(bias),
+                         capi.ptr(out), capi.ptr(out, 64) if pair else None, out.shape[3], None, None, 0, None,
+                         1 if pair else 0)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(capi.load().fcn8_conv1_fwd(C.byref(p), _stream()))
+    if e0 is not None:
+        TIMER.stop("conv1", 2.0 * N * H * W * 64 * 27, e0)
+    return out
+
+
+def conv1_wgrad(images, dy, dw, pair=False):
+    """conv1_1/filter gradient dw [27, 64] (fp32, TF order) from the uint8 image and dy ([N,H,W,64] bf16 or pair)."""
+    _chk_cuda(images, dy, dw)
+    N, H, W, _ = images.shape
+    p = capi.Conv1Params(capi.ptr(images), N, H, W, None, None, None, None, None, 0, capi.ptr(dy),
+                         capi.ptr(dy, 64) if pair else None, dy.shape[3], capi.ptr(dw), 1 if pair else 0)
+    lib = capi.load()
+    nbytes = lib.fcn8_conv1_wgrad_workspace_bytes(C.byref(p))
+    ws = _workspace(nbytes, images.device)
+    e0 = TIMER.start() if TIMER is not None else None
+    capi.check(lib.fcn8_conv1_wgrad(C.byref(p), capi.ptr(ws), nbytes, _stream()))
+    if e0 is not None:
+        TIMER.stop("conv1", 2.0 * N * H * W * 64 * 27, e0)
+    return dw
+
+
 def _fmt(t, pair):
     return BF16X2 if pair else dtype_of(t)
 

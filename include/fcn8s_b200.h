@@ -98,6 +98,30 @@ typedef struct {
 } Fcn8PreprocessParams;
 int32_t fcn8_preprocess_im2col(const Fcn8PreprocessParams* p, void* stream);
 
+/* ---- conv1_1 straight from the uint8 image: the feed (:558,686,765), the encoder graph's RGB->BGR / mean subtraction
+ * and its first 3x3 convolution 3 -> 64 + bias + ReLU [EXT], and that convolution's filter gradient (:257), with the
+ * 27-column im2col operand built in shared memory (csrc/conv1.cu).  w / w_lo: fcn8_pack_weights(mode 0, ksize 1,
+ * Cin 27, CinPad 64) of conv1_1/filter seen as [27][64] (bf16, K-major [64 co][64 k]).  pair != 0: hi / lo operands and
+ * a hi / lo output (out, out_lo with pixel stride out_ld); dy / dy_lo likewise.  N*H*W must be a multiple of 128. */
+typedef struct {
+  const uint8_t* images;  /* [N,H,W,3] RGB */
+  int32_t N, H, W;
+  const void* w;
+  const void* w_lo;
+  const float* bias;      /* [64] */
+  void* out;              /* fwd: [N,H,W,out_ld] bf16 */
+  void* out_lo;
+  int32_t out_ld;         /* 0 = 64 */
+  const void* dy;         /* wgrad: [N,H,W,dy_ld] bf16 */
+  const void* dy_lo;
+  int32_t dy_ld;          /* 0 = 64 */
+  float* dw;              /* wgrad: [27][64] fp32 = conv1_1/filter in TF layout */
+  int32_t pair;
+} Fcn8Conv1Params;
+int32_t fcn8_conv1_fwd(const Fcn8Conv1Params* p, void* stream);
+size_t fcn8_conv1_wgrad_workspace_bytes(const Fcn8Conv1Params* p);
+int32_t fcn8_conv1_wgrad(const Fcn8Conv1Params* p, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- encoder convolutions (external VGG-16 graph loaded at fcn8s_tensorflow.py:127-152; conv kxk stride 1 SAME):
  * out[N,H,W,Cout] = epilogue( sum_{kh,kw,ci} x[N, y+kh-pad, x+kw-pad, ci] * wp[co][(kh*k+kw)*Cin + ci] ).
  * fprop: wp from fcn8_pack_weights(mode 0), flags BIAS|RELU(|DROPOUT).  dgrad (autodiff of the same op, :257):

@@ -776,6 +776,40 @@ def reduced_products():
 
 
 @case
+def conv1_direct():
+    """conv1_1 from the uint8 image (im2col operand built in shared memory): forward (bias + ReLU) and the filter
+    gradient, bf16 and hi/lo pair, against fp64 references; borders, several images, N*H*W = k * 128."""
+    from fcn8s_tensorflow_b200 import ops
+    dev = torch.device("cuda")
+    torch.manual_seed(71)
+    ok = True
+    mean = torch.tensor([103.939, 116.779, 123.68], device=dev, dtype=torch.float64)
+    for (N, H, W) in ((1, 32, 32), (2, 64, 96), (3, 32, 160)):
+        img = torch.randint(0, 256, (N, H, W, 3), dtype=torch.uint8, device=dev)
+        bgr = img.double().flip(-1) - mean
+        w = torch.randn(3, 3, 3, 64, device=dev) * 0.1
+        b = torch.randn(64, device=dev)
+        for pair, tol in ((True, 2e-5), (False, 1e-2)):
+            pk = ops.pack_weights(w, 1, 27, 64, 0, ops.BF16, cin_pad=64, split=pair)
+            wq = (pk[0].double() + (pk[1].double() if pair else 0))[:, :27].t().reshape(3, 3, 3, 64)
+            xq = _pair_q(bgr.float()) if pair else bgr.float().to(torch.bfloat16).double()
+            out = torch.full((N, H, W, 128 if pair else 64), float("nan"), dtype=torch.bfloat16, device=dev)
+            ops.conv1_fwd(img, pk, b, out, pair=pair)
+            ref = ref_conv(xq, wq, b, relu=True)
+            tag = "N%d %dx%d pair%d" % (N, H, W, pair)
+            ok &= report("conv1 fwd " + tag, ops.from_pair(out) if pair else out, ref, tol)
+            dy32 = torch.randn(N, H, W, 64, device=dev)
+            dy = ops.to_pair(dy32) if pair else dy32.to(torch.bfloat16)
+            dyq = ops.from_pair(dy).double() if pair else dy.double()
+            dw = torch.full((27, 64), float("nan"), device=dev)
+            ops.conv1_wgrad(img, dy, dw, pair=pair)
+            cols = F.unfold(F.pad(xq.permute(0, 3, 1, 2), (1,) * 4), 3).view(N, 3, 9, H * W)   # [n, c, tap, p]
+            refw = torch.einsum("nctp,npo->tco", cols, dyq.reshape(N, H * W, 64)).reshape(27, 64)
+            ok &= report("conv1 wgrad " + tag, dw, refw, tol)
+    return ok
+
+
+@case
 def rz_accumulation_probe():
     """TMEM accumulation rounds toward zero on every tcgen05.mma: with all-positive operands the result falls short of
     the exact sum by ~n_mma * c.  Measures c (library compensation disabled through fcn8_debug_set(0, 1)) and checks

@@ -46,7 +46,7 @@ def test_ctypes_structs_match_header_layout():
     for cname, cls in [("Fcn8PreprocessParams", _capi.PreprocessParams), ("Fcn8ConvParams", _capi.ConvParams),
                        ("Fcn8WgradParams", _capi.WgradParams), ("Fcn8PackParams", _capi.PackParams),
                        ("Fcn8PoolParams", _capi.PoolParams), ("Fcn8BiasGradParams", _capi.BiasGradParams),
-                       ("Fcn8DeconvParams", _capi.DeconvParams)]:
+                       ("Fcn8DeconvParams", _capi.DeconvParams), ("Fcn8Conv1Params", _capi.Conv1Params)]:
         body = dict((n, b) for b, n in re.findall(r"typedef struct \{([^}]*)\}\s*(\w+);", hdr))[cname]
         fields = []
         for decl in body.split(";"):
