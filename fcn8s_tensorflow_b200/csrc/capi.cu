@@ -243,35 +243,38 @@ int plan_conv(const Fcn8ConvParams* p, ConvPlan* pl) {
   return 0;
 }
 
-template <int BN, bool TF32>
+// PROMO: promoted accumulation (ConvGemmArgs::promo_kb), bf16 operands only
+template <int BN, bool TF32, bool PROMO = false>
 cudaError_t launch_conv_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, TF32, false, 0, PROMO>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  (void)launch_k(conv_gemm_kernel<BN, TF32>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, maps, a);
+  (void)launch_k(conv_gemm_kernel<BN, TF32, false, 0, PROMO>, dim3(grid), dim3(PROMO ? kPromoThreads : kGemmThreads),
+                 Cfg::kSmemBytes, st, maps, a);
   return cudaGetLastError();
 }
 
 // CTA-pair variant (clusters of two CTAs, tcgen05 cta_group::2): bf16 operands, 256-column tiles; `grid` is even.
+template <bool PROMO = false>
 cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<256, true>;
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[cur_dev()];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, true>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<256, false, true, 0, PROMO>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(PROMO ? kPromoThreads : kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -284,7 +287,7 @@ cudaError_t launch_conv_pair(const TensorMaps3& maps, const ConvGemmArgs& a, int
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl_off ? 1 : 2;
   count_launch();
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, true>, maps, a);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, false, true, 0, PROMO>, maps, a);
 }
 
 template <int BN, bool RB = false>
@@ -645,6 +648,12 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     a.inv_keep = 1.f / p->keep_prob;
     a.keep_threshold = (uint32_t)((double)p->keep_prob * 16777216.0);
   }
+  // promoted accumulation for the error-compensated products whose hi*hi segment is longer than one chunk
+  // (debug key 9: > 0 = chunk length in k-blocks, < 0 = off)
+  const int promo_kb = g_debug[9] < 0 ? 0 : (g_debug[9] > 0 ? g_debug[9] : kPromoKbDefault);
+  const bool promo = !use_halo && p->dtype == FCN8_BF16 && p->nseg == 3 && promo_kb > 0 &&
+                     (pl.total_kb / p->nseg > promo_kb) && (pl.kb_per_split > promo_kb);
+  a.promo_kb = promo ? promo_kb : 0;
   ConvGemmArgs kernel_args = a;
   if (pl.splits > 1) kernel_args.flags = EPI_PARTIAL;
   if (use_halo) {
@@ -667,11 +676,13 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if (use_pair) {
     const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n * pl.splits;
     const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
-    e = launch_conv_pair(maps, kernel_args, 2 * pairs, st);
+    e = promo ? launch_conv_pair<true>(maps, kernel_args, 2 * pairs, st)
+              : launch_conv_pair<false>(maps, kernel_args, 2 * pairs, st);
   } else
 #define FCN8_DISPATCH(BNV)                                                    \
-  e = tf32 ? launch_conv_t<BNV, true>(maps, kernel_args, grid, st)          \
-           : launch_conv_t<BNV, false>(maps, kernel_args, grid, st)
+  e = tf32    ? launch_conv_t<BNV, true>(maps, kernel_args, grid, st)         \
+      : promo ? launch_conv_t<BNV, false, true>(maps, kernel_args, grid, st)  \
+              : launch_conv_t<BNV, false>(maps, kernel_args, grid, st)
   if (pl.BN == 256) {
     FCN8_DISPATCH(256);
   } else if (pl.BN == 128) {

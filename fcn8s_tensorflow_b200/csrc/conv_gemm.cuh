@@ -135,6 +135,13 @@ struct ConvGemmArgs {
   // rz_c = expected relative loss per k-block (4 MMAs) of the hi*hi segment; the epilogue scales a tile's accumulator
   // by acc_scale * (1 + rz_c * [hi*hi k-blocks accumulated into it]).
   float rz_c;
+  // Promoted accumulation (PROMO kernels): the hi*hi segment of a tile is accumulated in CHUNKS of promo_kb k-blocks
+  // (4 MMAs each), every chunk into a fresh TMEM accumulator stage; the epilogue warps drain each finished chunk into
+  // an fp32 running sum in registers (round-to-nearest adds) while the next chunk accumulates into the other stage,
+  // and write the total back to tensor memory before the tile's epilogue.  The truncating adds of the tensor core then
+  // only ever see accumulators of <= 4 * promo_kb MMAs: the round-toward-zero loss is bounded by the chunk length
+  // instead of growing with K (and with it the dependence of the bias on the sign structure of the data).
+  int promo_kb;
   // measurement only (fcn8_debug_buffer): when set, CTA b writes dbg[8b + 0..3] = cycles its MMA warp spent in the
   // tile loop / waiting for operand stages (full barriers) / waiting for a free accumulator, and k-blocks issued;
   // dbg[8b + 4] = cycles the TMA producer waited for free stages
@@ -154,7 +161,18 @@ struct ConvGemmArgs {
   int num_classes;
   float gscale;                 // dz = (softmax - y) * gscale
 };
-constexpr float kRzBiasPerMma = 2.1e-8f;
+constexpr float kRzBiasPerMma = 0.f;   // no statistical correction by default (promoted accumulation bounds the loss)
+
+// Chunk structure of a promoted tile over k-blocks [kb0, kb1): a new chunk starts at every kb = kb_hi0 + j * P that
+// lies strictly inside (max(kb0, kb_hi0), kb1) -- the low-order segments and the first P hi*hi k-blocks share chunk 0.
+__device__ __forceinline__ bool promo_boundary(int kb, int kb0, int kb_hi0, int P) {
+  return kb > kb0 && kb > kb_hi0 && (kb - kb_hi0) % P == 0;
+}
+__device__ __forceinline__ int promo_chunks(int kb0, int kb1, int kb_hi0, int P) {
+  const int lo = max(kb0, kb_hi0);
+  if (kb1 - 1 <= lo) return 1;
+  return 1 + (kb1 - 1 - kb_hi0) / P - (lo - kb_hi0) / P;
+}
 
 struct TensorMaps3 {
   CUtensorMap a[3];
@@ -180,6 +198,11 @@ struct GemmCfg {
 
 constexpr int kGemmThreads = 320;  // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
 constexpr int kEpiWarps = 8;        // two epilogue warps per TMEM lane quarter, each takes half of the tile's columns
+// PROMO kernels: three warpgroups -- warps 0..3 = TMA producer, MMA issuer and two idle warps (72 registers per thread
+// after setmaxnreg.dec), warps 4..11 = epilogue (216 registers after setmaxnreg.inc: BN / 2 running sums per thread)
+constexpr int kPromoThreads = 384;
+constexpr int kPromoKbDefault = 12;   // 48 MMAs per chunk: worst-case (same-sign) truncation loss ~3e-6 per layer
+constexpr int kPromoCtlRegs = 72, kPromoEpiRegs = 216;
 
 template <bool TF32>
 __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -342,9 +365,11 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
       if (4 * i < ncols) o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
   } else {
     uint32_t hi[16], lo[16];
+    // hi/lo pair storage format: also when only the pooled tensor is kept (inference: out == out_lo == nullptr)
+    const bool pair_fmt = g.out_lo != nullptr || g.pool_out_lo != nullptr;
 #pragma unroll
     for (int i = 0; i < 16; ++i) hi[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-    if (g.out_lo) {
+    if (pair_fmt) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[i]));
@@ -368,7 +393,7 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[i]));
-        if (g.out_lo) {
+        if (pair_fmt) {
           const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lo[i]));
           h.x += l.x;
           h.y += l.y;
@@ -523,12 +548,12 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
 // accumulator is handed back on the leader CTA's barrier.
 // EPI = 1: the loss / predictor epilogue above instead of the generic one (BN = 256 only); `colsum_s` then holds
 // [0] the CTA's loss sum, [32..64) its class sums of dz, [64..64 + C*C) its confusion-matrix histogram.
-template <int BN, bool TF32, bool PAIR = false, int EPI = 0>
+template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
                                                    uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
                                                    int warp, int lane, uint32_t rank = 0) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp handles
+    const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns this warp handles
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
@@ -562,6 +587,55 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
       const int kb0 = sp * g.kb_per_split;
       const int kb1 = min(total_kb, kb0 + g.kb_per_split);
       const float acc_scale = g.acc_scale * (1.f + g.rz_c * static_cast<float>(max(0, kb1 - max(kb0, kb_hi0))));
+      if constexpr (PROMO) {
+        // every chunk but the last: drain the finished accumulator stage into the running sum, hand the stage back
+        const int nch = promo_chunks(kb0, kb1, kb_hi0, g.promo_kb);
+        if (nch > 1) {
+          float sums[BN / 2];
+#pragma unroll
+          for (int i = 0; i < BN / 2; ++i) sums[i] = 0.f;
+#pragma unroll 1
+          for (int ch = 0; ch + 1 < nch; ++ch) {
+            mbar_wait(&acc_full[as], aphase);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * (BN / 2);
+#pragma unroll
+            for (int q = 0; q < BN / 64; ++q) {
+              uint32_t v[32];
+              tmem_ld32(ta + q * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sums[q * 32 + i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR)
+                mbar_arrive_cluster(lead_acc_empty + as * 8);
+              else
+                mbar_arrive_relaxed(&acc_empty[as]);
+            }
+            if (++as == 2) {
+              as = 0;
+              aphase ^= 1;
+            }
+          }
+          // last chunk: total = running sum + this accumulator, written back in place (this warp's own lanes / columns)
+          mbar_wait(&acc_full[as], aphase);
+          tc_fence_after();
+          const uint32_t ta = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16) + chalf * (BN / 2);
+#pragma unroll
+          for (int q = 0; q < BN / 64; ++q) {
+            uint32_t v[32];
+            tmem_ld32(ta + q * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(sums[q * 32 + i] + __uint_as_float(v[i]));
+            tmem_st32(ta + q * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -652,12 +726,15 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
   }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN, bool TF32, bool PAIR = false, int EPI = 0>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false>
+__global__ void __launch_bounds__(PROMO ? kPromoThreads : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
   pdl_launch_dependents();
   static_assert(!PAIR || (!TF32 && BN == 256), "CTA pairs: bf16 operands, 256-column tiles");
   static_assert(EPI == 0 || (!TF32 && BN == 256), "loss epilogue: bf16 operands, one block row per 256-column tile");
+  static_assert(!PROMO || (EPI == 0 && !TF32), "promoted accumulation: bf16 operands, generic epilogue");
+  constexpr int kThreads = PROMO ? kPromoThreads : kGemmThreads;
+  constexpr int kEpiWarp0 = PROMO ? 4 : 2;
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
   extern __shared__ uint8_t smem_raw[];
@@ -673,9 +750,9 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (EPI == 1) {
-    for (int c = threadIdx.x; c < 64 + 32 * 32; c += kGemmThreads) colsum_s[c] = 0.f;   // loss, dz class sums, histogram
+    for (int c = threadIdx.x; c < 64 + 32 * 32; c += kThreads) colsum_s[c] = 0.f;   // loss, dz class sums, histogram
   } else if (g.flags & EPI_COLSUM) {
-    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kThreads) colsum_s[c] = 0.f;
   }
 
   // scheduling units: M tiles, or (PAIR) pairs of consecutive M tiles, one per CTA of the cluster
@@ -717,6 +794,10 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched from here on
 
+  // (PROMO: the register re-partitioning sits INSIDE the two role branches, so that the compiler allocates the control
+  // warps' code against 72 registers and the epilogue's against 216)
+  if (warp < kEpiWarp0) {
+  if constexpr (PROMO) setmaxnreg_dec<kPromoCtlRegs>();
   if (warp == 0) {
     // ============================== TMA producer (whole warp, one elected lane issues) ==============================
     {
@@ -836,8 +917,31 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       mbar_wait(&acc_empty[as], aphase ^ 1);
       if (g.dbg) dbg_acc += clock64() - tw;
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
+      uint32_t d_tmem = tmem_base + as * BN;
+      int kb_first = kb0;   // first k-block of the current accumulation chunk (PROMO: chunks, else the whole tile)
       for (int kb = kb0; kb < kb1; ++kb) {
+        if constexpr (PROMO) {
+          if (promo_boundary(kb, kb0, total_kb - kb_per_seg, g.promo_kb)) {
+            // chunk complete: publish this accumulator stage, continue in the other one from zero
+            if (elect_one()) {
+              if constexpr (PAIR)
+                umma_commit_pair(&acc_full[as], 3);
+              else
+                umma_commit(&acc_full[as]);
+            }
+            __syncwarp();
+            if (++as == 2) {
+              as = 0;
+              aphase ^= 1;
+            }
+            if (g.dbg) tw = clock64();
+            mbar_wait(&acc_empty[as], aphase ^ 1);
+            if (g.dbg) dbg_acc += clock64() - tw;
+            tc_fence_after();
+            d_tmem = tmem_base + as * BN;
+            kb_first = kb;
+          }
+        }
         if (g.dbg) tw = clock64();
         mbar_wait(&full_bar[stage], phase);
         if (g.dbg) {
@@ -853,9 +957,9 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
           for (int k = 0; k < 4; ++k) {
             // A: advance 32 bytes along K inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
             if constexpr (PAIR)
-              umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
             else
-              umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_issue<TF32>(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, (kb > kb_first || k > 0) ? 1u : 0u);
           }
           if constexpr (PAIR)
             umma_commit_pair(&empty_bar[stage], 3);   // frees the stage in both CTAs
@@ -886,10 +990,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;
       g.dbg[8 * blockIdx.x + 3] = dbg_kb;
     }
-  } else if (warp >= 2) {
+  }
+  } else {
     // ============================== epilogue ==============================
-    conv_epilogue_loop<BN, TF32, PAIR, EPI>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp,
-                                            lane, rank);
+    if constexpr (PROMO) setmaxnreg_inc<kPromoEpiRegs>();
+    conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles,
+                                                   warp, lane, rank);
   }
 
   tc_fence_before();
@@ -907,12 +1013,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     if (threadIdx.x < g.num_classes && g.dz_hi && g.dbias) atomicAdd(g.dbias + threadIdx.x, colsum_s[32 + threadIdx.x]);
     if (g.conf) {
       const unsigned int* hist = reinterpret_cast<const unsigned int*>(colsum_s) + 64;
-      for (int c = threadIdx.x; c < g.num_classes * g.num_classes; c += kGemmThreads)
+      for (int c = threadIdx.x; c < g.num_classes * g.num_classes; c += kThreads)
         if (hist[c]) atomicAdd(g.conf + c, static_cast<unsigned long long>(hist[c]));
     }
   } else if ((g.flags & EPI_COLSUM) && !(g.flags & EPI_PARTIAL)) {
     const int ncs = g.colsum_n > 0 ? min(g.colsum_n, g.tiles_n * BN) : g.tiles_n * BN;
-    for (int c = threadIdx.x; c < ncs; c += kGemmThreads) {
+    for (int c = threadIdx.x; c < ncs; c += kThreads) {
       const float t = colsum_s[c];
       if (t != 0.f) atomicAdd(g.colsum + c, t);
     }

@@ -73,9 +73,12 @@ int32_t fcn8_set_sm_limit(int32_t n);
  * tf.train.Saver); used by fcn8s_tensorflow_b200/tf_bundle.py.  No device work. */
 uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc);
 /* Bring-up / measurement knobs -- tests and profiling only (also settable as FCN8_DEBUG="key=value,..." at load time):
- *   0 = 1: no round-toward-zero compensation of the GEMM accumulators (the library multiplies every tcgen05
- *          accumulator by 1 + n_mma * 2.1e-8, the expected relative loss of TMEM's truncating accumulation over n_mma
- *          instructions; scripts/bringup.py::rz_accumulation_probe measures the constant)
+ *   7 = c: experiment only -- multiply every tcgen05 accumulator by 1 + n_mma * c * 1e-10 (a statistical correction of
+ *          TMEM's truncating accumulation; OFF by default: the loss is bounded structurally instead, key 9); 0 = 1: off
+ *   9    : promoted accumulation of the error-compensated (3-product) convolutions: the hi*hi segment is accumulated
+ *          in chunks of P k-blocks (4 MMAs each) that the epilogue warps add up in fp32 registers with round-to-
+ *          nearest adds (csrc/conv_gemm.cuh, ConvGemmArgs::promo_kb).  0 = library default (12), P > 0 = chunk length,
+ *          < 0 = off (one TMEM accumulation per tile; scripts/promo_sweep.py measures what that costs in accuracy)
  *   1 = 1: no wgrad_halo_kernel          2 = 1: no resident-weights variant of conv_halo_kernel<64>
  *   3    : bit 0: conv epilogues skip their output stores, bit 1: ... and their mask / residual loads (timing only)
  *   5 = 1: single-CTA kernels instead of the CTA-pair (cta_group::2) variants of conv_gemm / wgrad_gemm

@@ -619,7 +619,7 @@ def deconv_case(Cc, s, N, h, w, nseg, tol):
     ref = ref_deconv(xq, Tq, bias, s)
     if s == 2:
         skip32 = torch.randn(N, H, W, Cc, device=dev)
-        skp = ops.planes_from_float(skip32)
+        skp = ops.halves(ops.to_pair(F.pad(skip32, (0, 64 - Cc))), 64)    # same geometry as the output planes
         out_t = torch.full((N, H, W, 128), float("nan"), dtype=torch.bfloat16, device=dev)
         out = ops.halves(out_t, 64)
         ops.deconv_fwd(xp, pk, Cc, s, out, skip=skp, nseg=nseg)
@@ -727,7 +727,9 @@ def fused_pool():
         x32 = torch.randn(N, H, W, cin, device=dev)
         x = ops.to_pair(x32) if pair else x32.to(torch.bfloat16)
         cm = 2 if pair else 1
-        y_ref = ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1)
+        # (one split: the fused variant never splits K, and a split-K sum differs in its last bit)
+        y_ref = ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1,
+                              force_splits=1)
         p_ref = ops.maxpool_fwd(y_ref, pair=pair)
         pooled = torch.full((N, H // 2, W // 2, cm * cout), float("nan"), dtype=torch.bfloat16, device=dev)
         y = ops.conv_gemm(x, wh, cout, 3, bias=b, flags=ops.EPI_BIAS | ops.EPI_RELU, wp_lo=wl, pair=pair, w_mode=1,
@@ -737,7 +739,9 @@ def fused_pool():
                       pool_out=pooled2, store_out=False)
         torch.cuda.synchronize()
         # the tile shape differs from the unfused run's, the accumulation order inside a tile does not
-        same = bool(torch.equal(y, y_ref)) and bool(torch.equal(pooled, p_ref)) and bool(torch.equal(pooled2, p_ref))
+        val = (lambda t: ops.from_pair(t)) if pair else (lambda t: t.float())      # (+0 / -0 low halves compare equal)
+        same = bool(torch.equal(val(y), val(y_ref))) and bool(torch.equal(val(pooled), val(p_ref))) and \
+            bool(torch.equal(val(pooled2), val(p_ref)))
         print("  fused pool N%d %dx%d Cin%d Cout%d pair%d: %s" % (N, H, W, cin, cout, pair, "OK" if same else "FAIL"))
         if not same:
             a = ops.from_pair(pooled) if pair else pooled
@@ -810,39 +814,54 @@ def conv1_direct():
 
 
 @case
-def rz_accumulation_probe():
-    """TMEM accumulation rounds toward zero on every tcgen05.mma: with all-positive operands the result falls short of
-    the exact sum by ~n_mma * c.  Measures c (library compensation disabled through fcn8_debug_set(0, 1)) and checks
-    that the compensated result is unbiased.  The library constant is kRzBiasPerMma = 2.1e-8."""
+def promoted_accumulation():
+    """The TMEM accumulator truncates (rounds toward zero) on every tcgen05.mma: with all-positive operands -- the worst
+    case, every partial sum has the same sign -- an accumulation of n MMAs falls short of the exact sum by ~n * 7e-8
+    relative.  The PROMO kernels cut the hi*hi segment into chunks of promo_kb k-blocks, each accumulated from zero and
+    added to an fp32 register sum with round-to-nearest adds (ConvGemmArgs::promo_kb), which bounds the loss by the
+    chunk length.  Measured here: mean signed relative error without promotion (fcn8_debug_set(9, -1)), with the
+    library default, and with 3-k-block chunks; plus mixed-sign cases against fp64 with many short chunks (chunk
+    bookkeeping of the MMA issuer / epilogue warps, pair and single-CTA kernels, split-K partials, ragged tiles)."""
     from fcn8s_tensorflow_b200 import _capi as capi
     from fcn8s_tensorflow_b200 import ops
     lib = capi.load()
     dev = torch.device("cuda")
     torch.manual_seed(31)
     ok = True
-    for cin in (2048, 8192):
-        x = (torch.rand(2, 16, 32, cin, device=dev) + 0.5).to(torch.bfloat16)
-        w = ((torch.rand(1, 1, cin, 64, device=dev) + 0.5) / cin)
-        wh, _ = _shadow(w, False)
-        ref = ref_conv(x.double(), wh.double())
-        n_mma = cin // 16
-        wp32 = ops.pack_weights(w, 1, cin, 64, 0, ops.F32)[0]
-        lib.fcn8_debug_set(0, 1)
-        y0 = ops.conv_gemm(x.float(), wp32, 64, 1, force_splits=1)   # tf32 kind, fp32 out, one accumulator per tile
-        lib.fcn8_debug_set(0, 0)
-        y1 = ops.conv_gemm(x.float(), wp32, 64, 1, force_splits=1)
-        torch.cuda.synchronize()
-        wq = ops.pack_weights(w, 1, cin, 64, 0, ops.F32)[0].double().t().reshape(1, 1, cin, 64)
-        ref32 = ref_conv(x.double(), wq)
-        n_mma32 = cin // 8
-        r0 = (y0.double() / ref32 - 1).mean().item()
-        r1 = (y1.double() / ref32 - 1).mean().item()
-        print("  Cin %5d: %4d tf32 MMAs per accumulator: mean relative error raw %+.3e (c = %.3e per MMA), "
-              "compensated %+.3e" % (cin, n_mma32, r0, -r0 / n_mma32, r1))
-        # all-positive operands are the worst case (c ~ 4.5e-8); the library constant 2.1e-8 is the value that cancels
-        # the bias on the network's mixed-sign data (scripts/debug_fullsize.py), so here it removes about half
-        ok &= abs(r1) <= 0.7 * abs(r0) + 2e-7
-        del ref, n_mma, wh
+    for (n, h, w_, cin, k, cout, force_bn, force_splits) in ((2, 16, 32, 4096, 1, 256, 0, 1), (3, 20, 36, 512, 3, 512, 0, 0),
+                                                           (2, 16, 32, 1024, 1, 128, 128, 1), (2, 16, 32, 1024, 1, 64, 64, 1),
+                                                           (4, 4, 8, 512, 7, 256, 0, 0)):
+        x32 = torch.rand(n, h, w_, cin, device=dev) + 0.5
+        wt = (torch.rand(k, k, cin, cout, device=dev) + 0.5) / (k * k * cin)
+        wh, wl = _shadow(wt, True)
+        x = ops.to_pair(x32)
+        ref = ref_conv(ops.from_pair(x).double(), wh.double() + wl.double())
+        errs = []
+        for P in (-1, 0, 3):
+            lib.fcn8_debug_set(9, P)
+            try:
+                y = ops.conv_gemm(x, wh, cout, k, wp_lo=wl, pair=True, w_mode=1, force_bn=force_bn,
+                                  force_splits=force_splits, algo=1)
+                torch.cuda.synchronize()
+            finally:
+                lib.fcn8_debug_set(9, 0)
+            errs.append((ops.from_pair(y).double() / ref - 1).mean().item())
+        n_mma = k * k * cin // 16
+        print("  N%d %dx%d Cin%d k%d Cout%d bn%d: %5d hi*hi MMAs: mean signed rel error  unpromoted %+.2e  default %+.2e  "
+              "3-block chunks %+.2e" % (n, h, w_, cin, k, cout, force_bn, n_mma, errs[0], errs[1], errs[2]))
+        good = abs(errs[1]) <= 5e-6 and abs(errs[2]) <= 2e-6
+        if not good:
+            print("    FAIL")
+        ok &= good
+    lib.fcn8_debug_set(9, 3)
+    try:
+        ok &= hwio_conv_case(3, 20, 36, 256, 256, 3, True, 2e-5, algo=1)      # pair kernel, odd tile count, ragged
+        ok &= hwio_conv_case(1, 4, 8, 512, 256, 7, True, 2e-5)                # split-K partials of promoted tiles
+        ok &= hwio_conv_case(2, 16, 32, 256, 128, 3, True, 2e-5, force_bn=128)
+        ok &= hwio_conv_case(2, 16, 32, 256, 64, 3, True, 2e-5, force_bn=64)
+        ok &= hwio_conv_case(2, 16, 32, 256, 256, 3, True, 2e-5, force_bn=256, algo=1)
+    finally:
+        lib.fcn8_debug_set(9, 0)
     return ok
 
 
