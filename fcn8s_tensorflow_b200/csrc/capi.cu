@@ -651,7 +651,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   // promoted accumulation for the error-compensated products whose hi*hi segment is longer than one chunk
   // (debug key 9: > 0 = chunk length in k-blocks, < 0 = off)
   const int promo_kb = g_debug[9] < 0 ? 0 : (g_debug[9] > 0 ? g_debug[9] : kPromoKbDefault);
-  const bool promo = !use_halo && p->dtype == FCN8_BF16 && p->nseg == 3 && promo_kb > 0 &&
+  // (forward only: the 1e-4 bar is on logits and loss; the dgrad sums are mixed-sign and their bar is 1e-2)
+  const bool promo = !use_halo && p->dtype == FCN8_BF16 && p->nseg == 3 && promo_kb > 0 && p->w_mode != 2 &&
                      (pl.total_kb / p->nseg > promo_kb) && (pl.kb_per_split > promo_kb);
   a.promo_kb = promo ? promo_kb : 0;
   ConvGemmArgs kernel_args = a;
