@@ -3,9 +3,9 @@
     FCN8_GRAPHS=0 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,\
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none --csv --log-file X.csv \
         python bench.py --profile --precision P --steps 1 --warmup 1
-    python scripts/step_table.py X.csv P profiles/r01_launches_P_TAG.md [profiles/r01_step_kernels_TAG.json]
+    python scripts/step_table.py X.csv P profiles/rNN_launches_P_TAG.md [profiles/rNN_step_kernels_TAG.json]
 
-The last complete step of the capture is used (a step starts at preprocess_im2col_kernel).  The JSON (appended to /
+The last complete step of the capture is used (a step starts at set_step_scalars_kernel).  The JSON (appended to /
 updated per precision) is what bench.py reads for roofline.traffic.
 """
 import collections
@@ -35,7 +35,7 @@ def main():
         elif m.startswith("sm__pipe_tensor"):
             d["tensor"] = v
     seq = list(launches.values())
-    starts = [i for i, d in enumerate(seq) if d["name"].startswith("preprocess_im2col")]
+    starts = [i for i, d in enumerate(seq) if d["name"].startswith("set_step_scalars")]
     step = seq[starts[-2]:starts[-1]]
     agg = collections.OrderedDict()
     for d in step:
