@@ -705,7 +705,7 @@ namespace {
 // wgrad_halo_kernel: 3x3, 64 input channels, bf16 operands (conv1_2, conv2_1)
 bool wgrad_use_halo(const Fcn8WgradParams* p) {
   return p->dtype == FCN8_BF16 && p->ksize == 3 && p->Cin == 64 && p->Cout % 64 == 0 && p->rows_valid <= 0 &&
-         p->force_splits <= 0 && p->force_bn <= 0 && !g_debug[1] && p->out_cols <= 0 && p->x_sH <= 0 && p->dy_sH <= 0;
+         p->force_splits <= 0 && p->force_bn <= 0 && !g_debug[1] && p->out_cols <= 0;
 }
 // score heads: the class dimension is padded to 64 columns, only the first out_cols go to dw [rows][out_cols]
 bool wgrad_clip(const Fcn8WgradParams* p) {
@@ -759,9 +759,11 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     if (p->nseg == 2) hxs[1] = p->x;
     if (p->nseg == 1) hds[0] = p->dy;
     for (int s = 0; s < p->nseg; ++s) {
-      int hrc = encode_act_map(&hm.a[s], hxs[s], FCN8_BF16, p->N, p->H, p->W, 64, 16, 18, 1, false, p->x_ld);
+      int hrc = encode_act_map(&hm.a[s], hxs[s], FCN8_BF16, p->N, p->H, p->W, 64, 16, 18, 1, false, p->x_ld, p->x_sH,
+                               p->x_sN);
       if (hrc) return hrc;
-      hrc = encode_act_map(&hm.b[s], hds[s], FCN8_BF16, p->N, p->H, p->W, p->Cout, 8, 16, 1, false, p->dy_ld);
+      hrc = encode_act_map(&hm.b[s], hds[s], FCN8_BF16, p->N, p->H, p->W, p->Cout, 8, 16, 1, false, p->dy_ld, p->dy_sH,
+                           p->dy_sN);
       if (hrc) return hrc;
     }
     WgradHaloArgs ha;
@@ -1190,6 +1192,8 @@ int32_t fcn8_deconv_loss(const Fcn8DeconvParams* p, void* stream) {
     return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: no output requested");
   if ((p->dz_hi_out && !aligned16(p->dz_hi_out)) || (p->dz_lo_out && !aligned16(p->dz_lo_out)))
     return fail(FCN8_ERR_BAD_ALIGN, "deconv_loss: dz planes must be 16-byte aligned");
+  if ((p->C & 3) == 0 && ((p->logits && !aligned16(p->logits)) || (p->softmax && !aligned16(p->softmax))))
+    return fail(FCN8_ERR_BAD_ALIGN, "deconv_loss: logits / softmax must be 16-byte aligned (128-bit stores)");
   TensorMaps3 maps;
   ConvGemmArgs a;
   rc = setup_deconv_fwd(p, 256, &maps, &a);

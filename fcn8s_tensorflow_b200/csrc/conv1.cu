@@ -15,7 +15,10 @@
 //   wgrad   : dW[(hi | lo) 64 k, 64 co] += A'[128 px, (hi | lo) 64 k]^T * dY[128 px, 64 co]: the SAME shared-memory tile
 //             read MN-major, hi and lo halves side by side as the two 64-row chunks of one M = 128 operand; one TMEM
 //             accumulator per CTA over all its tiles, partials reduced by wgrad_splitk_reduce.
-// Warp roles (10 warps): 0 = TMA (weights / dY), 1 = TMEM allocator + MMA issuer, 2..5 = epilogue, 6..9 = builders.
+// Warp roles (18 warps): 0 = TMA (weights / dY), 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (two warps per TMEM
+// lane quarter, 32 columns each; the filter gradient only uses 2..5), 10..17 = builders in two groups of 128 threads
+// that take alternate tiles: building a tile is one global-load latency plus ~250 instructions per thread, and the
+// layer is bound by its 0.5 GB of output (forward) / dY (gradient) only if two tiles are always under construction.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -101,7 +104,7 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 8);
     }
     mbar_init(w_full, 1);
     fence_mbar_init();
@@ -165,10 +168,11 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
         aphase ^= 1;
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ============================== epilogue: bias + ReLU, bf16 / hi-lo pair store ==============================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int c = ((warp - 2) >> 2) * 32;     // this warp's half of the 64 output channels
     const float acc_scale = 1.f + g.rz_c;
     int as = 0;
     uint32_t aphase = 0;
@@ -177,16 +181,13 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
+      {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        if (c == 32) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
-        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(&acc_empty[as]);
         uint32_t hi[16], lo[16];
         const float4* b4 = reinterpret_cast<const float4*>(g.bias + c);
 #pragma unroll
@@ -219,19 +220,17 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
     }
   } else {
     // ============================== builders: the im2col tile, in shared memory ==============================
-    const int r = threadIdx.x - 6 * 32;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+    const int r = (threadIdx.x - kC1Builder0 * 32) & 127;
+    const int group = (warp - kC1Builder0) >> 2;     // group 0 builds the CTA's even tiles, group 1 the odd ones
+    for (int it = group; static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x < g.tiles; it += 2) {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
+      const int stage = it % kStages;
+      const uint32_t phase = static_cast<uint32_t>(it / kStages) & 1u;
       mbar_wait(&a_empty[stage], phase ^ 1);
       uint8_t* a_hi = a_base + stage * kStageBytes;
-      build_row(g, static_cast<long long>(t) * 128 + r, r, a_hi, PAIR ? a_hi + kC1Tile : nullptr);
+      build_row(g, t * 128 + r, r, a_hi, PAIR ? a_hi + kC1Tile : nullptr);
       fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core
       mbar_arrive(&a_full[stage]);
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
   }
   tc_fence_before();
@@ -359,20 +358,18 @@ conv1_wgrad_kernel(const __grid_constant__ CUtensorMap dy_hi, const __grid_const
                                : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  } else {
-    const int r = threadIdx.x - 6 * 32;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < g.tiles; t += gridDim.x) {
+  } else if (warp >= kC1Builder0) {
+    const int r = (threadIdx.x - kC1Builder0 * 32) & 127;
+    const int group = (warp - kC1Builder0) >> 2;
+    for (int it = group; it < my_tiles; it += 2) {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
+      const int stage = it % kStages;
+      const uint32_t phase = static_cast<uint32_t>(it / kStages) & 1u;
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* a_hi = smem + stage * kStageBytes;
-      build_row(g, static_cast<long long>(t) * 128 + r, r, a_hi, PAIR ? a_hi + kC1Tile : nullptr);
+      build_row(g, t * 128 + r, r, a_hi, PAIR ? a_hi + kC1Tile : nullptr);
       fence_proxy_async_smem();
       mbar_arrive(&a_full[stage]);
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
   }
   tc_fence_before();

@@ -7,7 +7,8 @@
 
 namespace fcn8 {
 
-constexpr int kC1Threads = 320;
+constexpr int kC1Threads = 576;      // 18 warps: TMA, MMA, 8 epilogue, 8 builders (conv1.cu)
+constexpr int kC1Builder0 = 10;      // first builder warp
 constexpr int kC1Tile = 128 * 128;   // bytes of one [128 rows][64 bf16] operand tile
 
 struct Conv1Args {

@@ -448,11 +448,18 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
 #pragma unroll
   for (int c = 0; c < 32; ++c) z[c] = (c < C) ? __uint_as_float(v[c]) * acc_scale + bias[c] : -INFINITY;
   const size_t p = (static_cast<size_t>(n) * g.out_H + oy) * g.out_W + ox;
+  const bool vec4 = (C & 3) == 0;   // a pixel's C floats are then 16-byte aligned: 128-bit stores
   if (g.logits) {
     float* dst = g.logits + p * C;
+    if (vec4) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < C) dst[c] = z[c];
+      for (int m = 0; m < 8; ++m)
+        if (4 * m < C) reinterpret_cast<float4*>(dst)[m] = make_float4(z[4 * m], z[4 * m + 1], z[4 * m + 2], z[4 * m + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) dst[c] = z[c];
+    }
   }
   float mx = z[0];
   int am = 0;
@@ -474,9 +481,17 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
   const float inv = 1.f / se;
   if (g.softmax) {
     float* dst = g.softmax + p * C;
+    if (vec4) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < C) dst[c] = e[c] * inv;
+      for (int m = 0; m < 8; ++m)
+        if (4 * m < C)
+          reinterpret_cast<float4*>(dst)[m] =
+              make_float4(e[4 * m] * inv, e[4 * m + 1] * inv, e[4 * m + 2] * inv, e[4 * m + 3] * inv);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) dst[c] = e[c] * inv;
+    }
   }
   if (!g.labels) return;
   const uint8_t* lp = g.labels + p * C;
