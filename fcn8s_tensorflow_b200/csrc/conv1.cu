@@ -89,6 +89,7 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+  uint8_t* store_s = reinterpret_cast<uint8_t*>(bars) + 1024;   // 8 x 2 KB: coalesced epilogue stores (warp_store_frag64)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -204,14 +205,9 @@ conv1_fwd_kernel(const __grid_constant__ CUtensorMap wmap_hi, const __grid_const
           lo[2 * i] = pack_bf16x2(f0 - h0.x, f1 - h0.y);
           lo[2 * i + 1] = pack_bf16x2(f2 - h1.x, f3 - h1.y);
         }
-        uint4* o4 = reinterpret_cast<uint4*>(g.out + p * g.out_ld + c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-        if (PAIR) {
-          uint4* l4 = reinterpret_cast<uint4*>(g.out_lo + p * g.out_ld + c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
+        uint8_t* stage = store_s + (warp - 2) * kStoreWarpBytes;
+        warp_store_frag64(stage, hi, g.out + p * g.out_ld + c, true, lane);
+        if (PAIR) warp_store_frag64(stage, lo, g.out_lo + p * g.out_ld + c, true, lane);
       }
       if (++as == 2) {
         as = 0;
@@ -383,7 +379,7 @@ conv1_wgrad_kernel(const __grid_constant__ CUtensorMap dy_hi, const __grid_const
 // ------------------------------------------------------------------------------------------------------------------
 template <bool PAIR>
 constexpr int conv1_fwd_smem() {
-  return 16384 + 4 * (PAIR ? 2 * kC1Tile : kC1Tile) + 1024 + 1024;
+  return 16384 + 4 * (PAIR ? 2 * kC1Tile : kC1Tile) + 1024 + 8 * kStoreWarpBytes + 1024;
 }
 template <bool PAIR>
 constexpr int conv1_wgrad_smem() {

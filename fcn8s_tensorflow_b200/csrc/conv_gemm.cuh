@@ -144,7 +144,8 @@ struct ConvGemmArgs {
   int promo_kb;
   // measurement only (fcn8_debug_buffer): when set, CTA b writes dbg[8b + 0..3] = cycles its MMA warp spent in the
   // tile loop / waiting for operand stages (full barriers) / waiting for a free accumulator, and k-blocks issued;
-  // dbg[8b + 4] = cycles the TMA producer waited for free stages
+  // dbg[8b + 4] = cycles the TMA producer waited for free stages; [5] = (halo kernels) waiting for weight stages;
+  // [6] / [7] = cycles the first epilogue warp waited for a finished accumulator / spent in its tile loop
   long long* dbg;
   // ---- EPI = 1 (loss / predictor epilogue of the upscore8 phase GEMM, fcn8s_tensorflow.py:226-235 + :253 / :268-269):
   // a 256-column tile is one row (dy = tile index) of 8 output pixels x 32 padded classes of each block, so every
@@ -183,6 +184,8 @@ struct TensorMaps3 {
 // tile and loads its own A tile but only HALF of the B tile; the leader issues M = 256 MMAs over both CTAs' shared
 // memory.  Per k-block a CTA then streams 32 KB instead of 48 KB through TMA and shared memory, and six stages fit
 // where four did -- the single-CTA kernel's main loop is bound by exactly that (wait-cycle profile: profiles/).
+constexpr int kEpiWarpsC = 8;           // (= kEpiWarps, declared below)
+constexpr int kStoreWarpBytes = 2048;   // 32 rows x 64 B: one epilogue warp's fragment of one bf16 plane
 template <int BN, bool PAIR = false>
 struct GemmCfg {
   static constexpr int kStages = PAIR ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
@@ -193,7 +196,8 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
   static constexpr int kBarBytes = 1024;
   static constexpr int kColsumBytes = kColsumMax * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kColsumBytes + 1024;  // +1024: manual alignment
+  static constexpr int kStoreBytes = kEpiWarpsC * kStoreWarpBytes;   // per-warp staging of the coalesced epilogue stores
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kColsumBytes + kStoreBytes + 1024;  // +1024: manual alignment
 };
 
 constexpr int kGemmThreads = 320;  // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue
@@ -234,19 +238,54 @@ __device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
   return f[0];
 }
 
+// Coalesced store of a warp's bf16 fragment: lane l holds 64 bytes (32 values) of ITS row; written directly, one
+// STG.128 of the warp touches 32 different 128-byte lines with 16 bytes each (ncu, round 2: the LSU queue backs up and
+// the epilogue warps of the narrow-tile kernels are >95 % busy with it).  Instead the fragment goes through a per-warp
+// 2 KB staging tile in shared memory (16-byte chunks XOR-swizzled by (row >> 1) & 3: both passes conflict-free) and
+// leaves as four STG.128 in which four consecutive lanes cover one row's 64 contiguous bytes: 8 lines per instruction,
+// whole 32-byte sectors only.  Row addresses travel by shuffle (dst = this lane's row, `ok` = row inside the tensor);
+// every lane of the warp must call.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void warp_store_frag64(uint8_t* stage, const uint32_t (&w)[16], const void* dst, bool ok,
+                                                  int lane) {
+  const uint32_t sbase = smem_u32(stage);
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(sbase + lane * 64 + ((j ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+  __syncwarp();
+  const unsigned long long mine = ok ? reinterpret_cast<unsigned long long>(dst) : 0ull;
+  const int c = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = (lane >> 2) + 8 * it;
+    const uint4 q = ld_shared_v4(sbase + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    const unsigned long long rp = __shfl_sync(0xffffffffu, mine, r);
+    if (rp) *reinterpret_cast<uint4*>(rp + c * 16) = q;
+  }
+  __syncwarp();
+}
+
 template <bool TF32>
 __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (&v)[32], size_t idx, int c0,
                                                int ncols, size_t dense_idx, bool valid, float* colsum_s, int lane,
-                                               uint32_t seed, float acc_scale, size_t pool_idx = 0,
+                                               uint32_t seed, float acc_scale, uint8_t* stage, size_t pool_idx = 0,
                                                bool pool_writer = false) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * acc_scale;
-  const int wide = g.flags & (EPI_COLSUM | EPI_POOL);   // warp-collective parts: every lane must come along
   if (!valid) {
-    // rows outside the tensor take part only in the warp-collective column sums / pooling, as zeros
-    if (!wide) return;
+    // rows outside the tensor come along as zeros: the column sums, the pooling and the staged stores are
+    // warp-collective
+    if (TF32 && !(g.flags & EPI_COLSUM)) return;
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = 0.f;
   }
@@ -376,15 +415,9 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
         lo[i] = pack_bf16x2(f[2 * i] - h.x, f[2 * i + 1] - h.y);
       }
     }
-    if (valid && g.out) {   // (out == nullptr: inference with a fused pool keeps only the pooled tensor)
-      uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o4[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-      if (g.out_lo) {
-        uint4* l4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.out_lo) + idx);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) l4[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-      }
+    if (g.out) {   // (out == nullptr: inference with a fused pool keeps only the pooled tensor)
+      warp_store_frag64(stage, hi, o, valid, lane);
+      if (g.out_lo) warp_store_frag64(stage, lo, reinterpret_cast<OutT*>(g.out_lo) + idx, valid, lane);
     }
     if (g.flags & EPI_POOL) {
       // 2x2 max over the STORED values (hi, or hi + lo for pairs: exactly what a stand-alone pool of the stored tensor
@@ -565,10 +598,12 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
 // [0] the CTA's loss sum, [32..64) its class sums of dz, [64..64 + C*C) its confusion-matrix histogram.
 template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
-                                                   uint64_t* acc_empty, float* colsum_s, int total_tiles, int m_tiles,
-                                                   int warp, int lane, uint32_t rank = 0) {
+                                                   uint64_t* acc_empty, float* colsum_s, uint8_t* store_s,
+                                                   int total_tiles, int m_tiles, int warp, int lane,
+                                                   uint32_t rank = 0) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns this warp handles
+    uint8_t* stage = store_s + (warp - (PROMO ? 4 : 2)) * kStoreWarpBytes;   // this warp's store staging tile
     const int row = quarter * 32 + lane;
     int as = 0;
     uint32_t aphase = 0;
@@ -579,6 +614,8 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
     const int kb_per_seg = g.taps * g.cblocks;
     const int total_kb = g.nseg * kb_per_seg;
     const int kb_hi0 = total_kb - kb_per_seg;   // the hi*hi segment is the last one
+    long long dbg_wait = 0;   // measurement only: cycles this warp waited for a finished accumulator
+    const long long dbg_e0 = g.dbg ? clock64() : 0;
     LossAcc lacc;
     if constexpr (EPI == 1) {
       lacc.loss = 0.f;
@@ -651,7 +688,9 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
           tmem_st_wait();
         }
       }
+      const long long dbg_tw = g.dbg ? clock64() : 0;
       mbar_wait(&acc_full[as], aphase);
+      if (g.dbg) dbg_wait += clock64() - dbg_tw;
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
@@ -713,7 +752,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
                        static_cast<size_t>(x >> 1) * g.psW + c0;
           }
           if (ncols > 0)
-            epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, vrow, colsum_s, lane, seed, acc_scale,
+            epilogue_row32<TF32>(g, v, idx, c0, ncols, pix * g.ldc + c0, vrow, colsum_s, lane, seed, acc_scale, stage,
                                  pool_idx, pool_writer);
         }
       }
@@ -721,6 +760,10 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
         as = 0;
         aphase ^= 1;
       }
+    }
+    if (g.dbg && lane == 0 && warp == (PROMO ? 4 : 2)) {   // first epilogue warp: [6] = idle cycles, [7] = loop cycles
+      g.dbg[8 * blockIdx.x + 6] = dbg_wait;
+      g.dbg[8 * blockIdx.x + 7] = clock64() - dbg_e0;
     }
     if constexpr (EPI == 1) {
       // CTA-level reduction of the loss and the class sums of dz (flushed to global memory by the kernel's tail)
@@ -761,6 +804,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* colsum_s = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);
+  uint8_t* store_s = bar_base + Cfg::kBarBytes + Cfg::kColsumBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1009,8 +1053,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   } else {
     // ============================== epilogue ==============================
     if constexpr (PROMO) setmaxnreg_inc<kPromoEpiRegs>();
-    conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles,
-                                                   warp, lane, rank);
+    conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_tiles,
+                                                   m_tiles, warp, lane, rank);
   }
 
   tc_fence_before();
@@ -1062,11 +1106,14 @@ struct HaloSmem {
   // round trip instead of 4: the MMA time of a single 128x64x64 stage is shorter than the issue + wait overhead)
   static constexpr int kTaps = (BN == 64) ? 3 : 1;
   static constexpr int kBBytes = kTaps * BN * 128;
-  static constexpr int kAStages = (BN == 64) ? 4 : 3;
-  static constexpr int kBStages = RB ? 3 : (BN == 128 ? 6 : 3);   // RB: the 3 resident tap-row groups
+  static constexpr int kAStages = 3;
+  static constexpr int kBStages = RB ? 3 : (BN == 128 ? 6 : (BN == 64 ? 4 : 3));   // RB: the 3 resident tap-row groups
   static constexpr int kBarBytes = 1024;
   static constexpr int kColsumBytes = 1024;   // the halo layers have at most 256 output channels
-  static constexpr int kBytes = kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumBytes + 1024;
+  static constexpr int kStoreBytes = kEpiWarpsC * kStoreWarpBytes;   // coalesced epilogue stores (warp_store_frag64)
+  static constexpr int kBytes = kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumBytes +
+                                kStoreBytes + 1024;
+  static_assert(kBytes <= 232448, "shared memory of the halo kernel");
 };
 
 template <int BN, bool RB = false>
@@ -1088,6 +1135,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* colsum_s = reinterpret_cast<float*>(bar_base + HS::kBarBytes);
+  uint8_t* store_s = bar_base + HS::kBarBytes + HS::kColsumBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1204,13 +1252,22 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       mbar_wait(&b_full[0], 0);   // the resident weight slice has landed
       tc_fence_after();
     }
+    long long dbg_a = 0, dbg_b = 0, dbg_acc = 0, dbg_kb = 0, tw = 0;
+    const long long dbg_t0 = g.dbg ? clock64() : 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      if (g.dbg) tw = clock64();
       mbar_wait(&acc_empty[acs], acph ^ 1);
+      if (g.dbg) dbg_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acs * BN;
       uint32_t first = 0;
       for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
+        if (g.dbg) tw = clock64();
         mbar_wait(&a_full[as], aph);
+        if (g.dbg) {
+          dbg_a += clock64() - tw;
+          ++dbg_kb;
+        }
         tc_fence_after();
         const uint32_t sa = sa_base + as * HaloCfg::kABytes;
         const int rb_seg = kbk / g.cblocks;
@@ -1220,7 +1277,9 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 #pragma unroll
           for (int kw0 = 0; kw0 < 3; kw0 += HS::kTaps) {
             if constexpr (!RB) {
+              if (g.dbg) tw = clock64();
               mbar_wait(&b_full[bs], bph);
+              if (g.dbg) dbg_b += clock64() - tw;
               tc_fence_after();
             }
             const uint32_t sb = sb_base + (RB ? (rb_group0 + kh) : bs) * HS::kBBytes;
@@ -1270,9 +1329,17 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         acph ^= 1;
       }
     }
+    if (g.dbg && lane == 0) {   // as in conv_gemm_kernel; [1] = activation patches, [5] = weight stages, [3] = patches
+      g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
+      g.dbg[8 * blockIdx.x + 1] = dbg_a;
+      g.dbg[8 * blockIdx.x + 2] = dbg_acc;
+      g.dbg[8 * blockIdx.x + 3] = dbg_kb;
+      g.dbg[8 * blockIdx.x + 5] = dbg_b;
+    }
   } else {
     // ============================== epilogue ==============================
-    conv_epilogue_loop<BN, false>(g, tmem_base, acc_full, acc_empty, colsum_s, total_tiles, m_tiles, warp, lane);
+    conv_epilogue_loop<BN, false>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_tiles, m_tiles, warp,
+                                  lane);
   }
 
   tc_fence_before();

@@ -3,7 +3,8 @@
 One eager c2 train step with fcn8_debug_buffer installed: every fcn8_conv_gemm / fcn8_wgrad_gemm launch gets a slot
 in which each CTA's MMA warp records the cycles it spent in its tile loop, waiting for operand stages (full
 barriers = the TMA feed is late) and waiting for a free accumulator (= the epilogue is late); the producer records
-its wait for free stages (= the MMAs are the slow side).  Launches served by the halo kernels leave their slot empty.
+its wait for free stages (= the MMAs are the slow side).  conv_halo_kernel reports its activation-patch waits under "operands" (k-block = one patch) and its weight-stage waits
+separately; wgrad_halo_kernel leaves its slot empty.
     python scripts/wait_profile.py [bf16|fp32]
 """
 import os
@@ -22,8 +23,9 @@ from fcn8s_tensorflow_b200.fcn8s import FCN8s, synthetic_weights  # noqa: E402
 def main():
     lib = capi.load()
     dev = torch.device("cuda", 0)
-    weights = synthetic_weights(bench.C, 2)
-    images, labels = bench.synthetic_feed(bench.PER_GPU_BATCH, 1000)
+    cfg = bench.CONFIGS["c2"]
+    weights = synthetic_weights(cfg["C"], 2)
+    images, labels = bench.synthetic_feed(cfg, cfg["per_gpu"], 1000)
     x = torch.from_numpy(images).to(dev)
     y = torch.from_numpy(labels.view("uint8")).to(dev)
     slots = 160
@@ -50,14 +52,15 @@ def main():
             s = b[i]
             live = s[:, 0] > 0
             if not bool(live.any()):
-                print("%3d %-10s %8.3f ms %7.0f TF/s   (halo kernel, not instrumented)" % (i, tag, ms, fl / ms / 1e9))
+                print("%3d %-10s %8.3f ms %7.0f TF/s   (wgrad_halo kernel, not instrumented)" % (i, tag, ms, fl / ms / 1e9))
                 continue
             tot = s[live, 0]
             print("%3d %-10s %8.3f ms %7.0f TF/s  %3d CTAs %8.1f kcyc  operands %5.1f%%  accumulator %5.1f%%  "
-                  "producer-stage %5.1f%%  %6.0f cyc/k-block"
+                  "producer-stage %5.1f%%  %6.0f cyc/k-block  (halo kernels: weight stages %5.1f%%)  epilogue warp idle %5.1f%%"
                   % (i, tag, ms, fl / ms / 1e9, int(live.sum()), tot.mean() / 1e3, 100 * (s[live, 1] / tot).mean(),
                      100 * (s[live, 2] / tot).mean(), 100 * (s[live, 4] / tot).mean(),
-                     (tot / s[live, 3].clamp(min=1)).mean()))
+                     (tot / s[live, 3].clamp(min=1)).mean(), 100 * (s[live, 5] / tot).mean(),
+                     100 * (s[live, 6] / s[live, 7].clamp(min=1)).mean()))
         model.close()
 
 
