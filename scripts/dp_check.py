@@ -36,11 +36,12 @@ def main():
             x = torch.from_numpy(np.ascontiguousarray(xi)).to(dev)
             y = torch.from_numpy(np.ascontiguousarray(yi)).to(dev)
             e.loss_and_backward(x, y, keep_prob=1.0)
-            e.allreduce.start(e.grads[e._reduced_upto:])
+            e._start_reduce(e._reduced_upto, e.n_flat)     # the tail chunk, in the engine's wire format
             e.allreduce.finish()
             e._reduced_upto = 0
             torch.cuda.synchronize()
-            avg = (e.grads / world).clone()
+            # bf16 wire format: the summed gradient lives in the bf16 wire buffer (that is what Adam reads)
+            avg = ((e.g16.float() if e.g16 is not None else e.grads) / world).clone()
             ref = Engine(C, precision=precision, device=dev)
             ref.load_weights(weights)
             ref.loss_and_backward(torch.from_numpy(images).to(dev), torch.from_numpy(labels).to(dev), keep_prob=1.0)
