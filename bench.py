@@ -297,6 +297,8 @@ def time_train(cfg, precision, weights, args, rank, local_rank, world, dev, conf
         eng._warm.clear()
         fdist.broadcast_parameters(eng)
         out["allreduce_exposed_ms"] = (ms - ms_nc) / args.steps
+        out["nccl_registered"] = bool(getattr(eng, "nccl_registered", False))
+        out["grad_comm"] = eng.grad_comm
         out["ms_per_step_without_allreduce"] = ms_nc / args.steps
     # per-kernel CUDA-event timing of the tensor-core GEMMs: the same steps, run eagerly right after the timed region
     # (events cannot be recorded inside the replayed CUDA graph the timed region uses)
@@ -484,7 +486,10 @@ def train_line(cfg, precision, r, args, world, peaks):
     if "allreduce_exposed_ms" in r:
         line["allreduce"] = {"exposed_ms_per_step": r["allreduce_exposed_ms"],
                              "ms_per_step_without_allreduce": r["ms_per_step_without_allreduce"],
-                             "how": "same steps re-timed with the collective removed from the captured step"}
+                             "how": "same steps re-timed with the collective removed from the captured step",
+                             "wire_format": r.get("grad_comm"),
+                             "nccl_registered_buffer": r.get("nccl_registered"),
+                             "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")}}
     return line
 
 

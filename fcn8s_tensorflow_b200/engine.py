@@ -187,6 +187,8 @@ class Engine:
         self.head_elems = self.layout["conv5_3/filter"][0]   # [decoder | fc7 W | fc6 W] prefix of the flat buffer
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.dp_reserve_sms = int(os.environ.get("FCN8_DP_RESERVE_SMS", "0"))
+        # ... for this many encoder layers of the backward pass after the collective was started (0 = until the end)
+        self.dp_reserve_layers = int(os.environ.get("FCN8_DP_RESERVE_LAYERS", "0"))
 
     # ------------------------------------------------------------------ parameters
     def view(self, name, buf=None):
@@ -431,6 +433,7 @@ class Engine:
             for kname in DECODER_KERNELS:
                 ops.l2_reg(self.view(kname).reshape(-1), self.view(kname, G).reshape(-1), self.loss_buf[1:2], l2_rate)
         # encoder backward
+        reserve_left = None
         for li in range(len(self.layers) - 1, -1, -1):
             name, k, cin, cout = self.layers[li]
             x_in = self._layer_input(A, li)
@@ -450,6 +453,12 @@ class Engine:
                 self._reduced_upto = self.head_elems
                 if self.dp_reserve_sms > 0:   # leave SMs to the collective's CTAs while it runs under the backward
                     self.lib.fcn8_set_sm_limit(self.sm_count - self.dp_reserve_sms)
+                    reserve_left = self.dp_reserve_layers if self.dp_reserve_layers > 0 else 1 << 30
+            elif self.dp_reserve_sms > 0 and reserve_left is not None:
+                reserve_left -= 1
+                if reserve_left <= 0:
+                    self.lib.fcn8_set_sm_limit(0)
+                    reserve_left = None
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
             prev_db = self.view(prev_name + "/biases", G)
