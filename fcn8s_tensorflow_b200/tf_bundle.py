@@ -21,9 +21,11 @@ LevelDB's):
     footer holds the metaindex and index handles padded to 40 bytes and the magic 0xdb4775248b80fb57.
   * masked crc = rotr(crc, 15) + 0xa282ead8 (mod 2^32).
 
-Parity note: TensorFlow cannot be installed here, so there is no TF-written golden file; the
-checksum is pinned by the RFC 3720 CRC-32C vectors, the container by a hand-assembled known-answer table and the
-round trip (tests/test_tf_bundle.py).
+Parity note: TensorFlow cannot be installed here, so there is no TF-written golden file.  What
+pins the format instead (tests/test_tf_bundle.py): the RFC 3720 CRC-32C vectors; TensorFlow's own CRC-32C / mask
+code and the protobuf classes generated from TensorFlow's .proto files as shipped in the `tensorboard` wheel (checksum
+and mask equal on random data, DataType enum values, TensorShapeProto / VersionDef sub-messages byte-identical); a
+hand-assembled known-answer table for the LevelDB container; and round trips.
 """
 import os
 import struct
@@ -150,14 +152,18 @@ def _encode_header():
 
 
 def _encode_entry(dtype_id, shape, offset, size, masked_crc, shard_id=0):
-    dims = b"".join(_pb_bytes_field(2, _pb_varint_field(1, int(d))) for d in shape)   # TensorShapeProto.dim[].size
+    # proto3 serialisation: fields holding their default value (0) are omitted -- byte-identical to what TensorFlow's
+    # generated classes write (checked against tensorboard's copies of them in tests/test_tf_bundle.py)
+    dims = b"".join(_pb_bytes_field(2, _pb_varint_field(1, int(d)) if int(d) else b"") for d in shape)  # dim[].size
     out = _pb_varint_field(1, dtype_id) + _pb_bytes_field(2, dims)
     if shard_id:
         out += _pb_varint_field(3, shard_id)
     if offset:
         out += _pb_varint_field(4, offset)
-    out += _pb_varint_field(5, size)
-    out += _varint((6 << 3) | 5) + struct.pack("<I", masked_crc)                      # fixed32 crc32c
+    if size:
+        out += _pb_varint_field(5, size)
+    if masked_crc:
+        out += _varint((6 << 3) | 5) + struct.pack("<I", masked_crc)                  # fixed32 crc32c
     return out
 
 

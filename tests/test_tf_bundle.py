@@ -185,3 +185,54 @@ def test_reader_handles_sharded_bundles(tmp_path):
     assert shards == 2 and entries["b"]["shard_id"] == 1 and entries["b"]["offset"] == 16
     got = tb.read_bundle(prefix)
     assert np.array_equal(got["a"], a) and np.array_equal(got["b"], b) and got["b"].dtype == np.int64
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pins against TensorFlow-team code that IS available offline: the `tensorboard` wheel ships TensorFlow's own
+# CRC-32C / mask implementation (tensorboard/compat/tensorflow_stub/pywrap_tensorflow.py, a transcription of
+# tensorflow/core/lib/hash/crc32c.h) and protobuf modules generated from TensorFlow's .proto files
+# (tensorboard/compat/proto).  tensor_bundle.proto itself is not among them, but every message it embeds is.
+def _tb_stub():
+    return pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+
+
+def test_crc_and_mask_equal_tensorflows_own_implementation():
+    stub = _tb_stub()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 64, 1000, 65537):
+        blob = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tb.crc32c(blob) == stub.crc32c(blob)
+        assert tb._crc32c_py(blob) == stub.crc32c(blob)
+        assert tb.mask_crc(tb.crc32c(blob)) == stub.masked_crc32c(blob)
+
+
+def test_dtype_ids_are_tensorflows_datatype_enum():
+    types_pb2 = pytest.importorskip("tensorboard.compat.proto.types_pb2")
+    names = {np.float32: "DT_FLOAT", np.float64: "DT_DOUBLE", np.int32: "DT_INT32", np.uint8: "DT_UINT8",
+             np.int16: "DT_INT16", np.int8: "DT_INT8", np.int64: "DT_INT64", np.bool_: "DT_BOOL", np.uint16: "DT_UINT16",
+             np.float16: "DT_HALF", np.uint32: "DT_UINT32", np.uint64: "DT_UINT64"}
+    for np_t, name in names.items():
+        assert tb._DTYPE_IDS[np.dtype(np_t)] == types_pb2.DataType.Value(name), name
+
+
+def test_embedded_messages_parse_with_tensorflows_generated_protos():
+    """BundleEntryProto.shape is a TensorShapeProto, BundleHeaderProto.version a VersionDef: the bytes this module
+    writes for them are parsed by the classes generated from TensorFlow's own .proto files, and the bytes those classes
+    serialise are what this module writes (field order included)."""
+    shape_pb2 = pytest.importorskip("tensorboard.compat.proto.tensor_shape_pb2")
+    versions_pb2 = pytest.importorskip("tensorboard.compat.proto.versions_pb2")
+    for shape in ((), (7,), (3, 3, 512, 4096), (0, 5), (1 << 33, 2)):
+        entry = tb._encode_entry(1, shape, 128, 4 * int(np.prod(shape)) if shape else 4, 0x12345678)
+        fields = {f: v for f, _, v in tb._pb_fields(entry)}
+        msg = shape_pb2.TensorShapeProto()
+        msg.ParseFromString(bytes(fields[2]))
+        assert [d.size for d in msg.dim] == list(shape) and not msg.unknown_rank
+        ref = shape_pb2.TensorShapeProto(dim=[shape_pb2.TensorShapeProto.Dim(size=d) for d in shape])
+        assert bytes(fields[2]) == ref.SerializeToString()
+        assert tb._decode_entry(entry)["shape"] == list(shape)
+    header = {f: v for f, _, v in tb._pb_fields(tb._encode_header())}
+    ver = versions_pb2.VersionDef()
+    ver.ParseFromString(bytes(header[3]))
+    assert ver.producer == 1 and ver.min_consumer == 0 and not ver.bad_consumers
+    assert bytes(header[3]) == versions_pb2.VersionDef(producer=1).SerializeToString()
+    assert header[1] == 1            # num_shards
