@@ -223,7 +223,10 @@ def dp_parity_check(dev, rank, world, precision):
     other = e.params.clone()
     tdist.broadcast(other, src=0)
     same = bool(torch.equal(e.params, other))
-    tol = 2e-4 if (precision == "fp32" and e.g16 is None) else 2e-2
+    # fp32 mode, fp32 wire: 6e-8 when no ReLU / max-pool decision flips between the sharded and the single-GPU run (a
+    # different batch size means another tile / split-K plan, i.e. another rounding of the activations); a handful of
+    # flips among the 10^6 units of conv1 / conv2 move the flat gradient by ~1e-3 (tests/test_gpu_engine.py docstring)
+    tol = 5e-3 if (precision == "fp32" and e.g16 is None) else 2e-2
     flag = torch.tensor([1 if (err <= tol and same) else 0], device=dev)
     tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
     out = {"grad_rel_l2_vs_single_gpu": err, "tol": tol, "replicas_identical_after_2_steps": same,

@@ -659,7 +659,8 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if (pl.splits > 1) kernel_args.flags = EPI_PARTIAL;
   if (use_halo) {
     const long long tiles = (long long)pl.m_tiles * pl.tiles_n;
-    const int hgrid = (int)(tiles < num_sms() ? tiles : num_sms());
+    a.dyn = g_debug[10] ? 0 : 1;   // dynamic tile scheduling, see below
+    const int hgrid = (int)((a.dyn || tiles < num_sms()) ? tiles : num_sms());
     if ((long long)pl.tiles_n * pl.BN > 256) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs Cout <= 256");
     // weights resident in shared memory when the CTA's whole slice is one group of 9 taps (conv1_2 fwd / dgrad, bf16)
     const bool resident = pl.BN == 64 && pl.tiles_n == 1 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 1 && !g_debug[2];
@@ -669,14 +670,18 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
                                   : launch_halo_t<64>(maps, a, hgrid, (cudaStream_t)stream);
     return he == cudaSuccess ? 0 : cuda_fail(he, "conv_halo launch");
   }
+  // dynamic tile scheduling (ConvGemmArgs::dyn): one CTA (pair) per tile in the grid, the resident ones take over the
+  // tiles of those not yet launched; debug key 10 = 1 keeps the static round-robin over min(tiles, #SMs) CTAs
+  const bool dyn = !g_debug[10];
+  kernel_args.dyn = dyn ? 1 : 0;
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
-  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  const int grid = (int)((dyn || total_tiles < num_sms()) ? total_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   const bool tf32 = p->dtype == FCN8_F32;
   if (use_pair) {
     const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n * pl.splits;
-    const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
+    const int pairs = (int)((dyn || units < num_sms() / 2) ? units : num_sms() / 2);
     e = promo ? launch_conv_pair<true>(maps, kernel_args, 2 * pairs, st)
               : launch_conv_pair<false>(maps, kernel_args, 2 * pairs, st);
   } else
@@ -856,7 +861,8 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     a.acc_scale = 1.f + (float)mma_per_pb * (float)pl.pb_per_split / (float)p->nseg * rz_per_mma();
   }
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
-  const int grid = (int)(total_tiles < num_sms() ? total_tiles : num_sms());
+  a.dyn = g_debug[10] ? 0 : 1;   // dynamic tile scheduling (ConvGemmArgs::dyn)
+  const int grid = (int)((a.dyn || total_tiles < num_sms()) ? total_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   const bool tf32 = p->dtype == FCN8_F32;
@@ -864,7 +870,7 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
   e = tf32 ? launch_wgrad_t<BNV, true>(maps, a, grid, st) : launch_wgrad_t<BNV, false>(maps, a, grid, st)
   if (pl.pair) {
     const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n * pl.splits;
-    const int pairs = (int)(units < num_sms() / 2 ? units : num_sms() / 2);
+    const int pairs = (int)((a.dyn || units < num_sms() / 2) ? units : num_sms() / 2);
     e = launch_wgrad_pair(maps, a, 2 * pairs, st);
   } else if (pl.BN == 256) {
     FCN8_DISPATCH(256);

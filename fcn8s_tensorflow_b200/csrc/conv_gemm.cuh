@@ -142,6 +142,12 @@ struct ConvGemmArgs {
   // only ever see accumulators of <= 4 * promo_kb MMAs: the round-toward-zero loss is bounded by the chunk length
   // instead of growing with K (and with it the dependence of the bias on the sign structure of the data).
   int promo_kb;
+  // Dynamic tile scheduling (cluster launch control): the grid holds one CTA (pair) per tile instead of one per SM; a
+  // running CTA (pair) takes the tiles of clusters that have not been launched yet (TileSched below).  While another
+  // kernel -- the overlapped NCCL all-reduce of the gradients -- holds some SMs, the resident CTAs absorb all the work
+  // instead of leaving a statically assigned share to CTAs that cannot start (which doubled the GEMMs' time under the
+  // collective).  0 = static round-robin over min(tiles, #SMs) CTAs.
+  int dyn;
   // measurement only (fcn8_debug_buffer): when set, CTA b writes dbg[8b + 0..3] = cycles its MMA warp spent in the
   // tile loop / waiting for operand stages (full barriers) / waiting for a free accumulator, and k-blocks issued;
   // dbg[8b + 4] = cycles the TMA producer waited for free stages; [5] = (halo kernels) waiting for weight stages;
@@ -207,6 +213,52 @@ constexpr int kEpiWarps = 8;        // two epilogue warps per TMEM lane quarter,
 constexpr int kPromoThreads = 384;
 constexpr int kPromoKbDefault = 12;   // 48 MMAs per chunk: worst-case (same-sign) truncation loss ~3e-6 per layer
 constexpr int kPromoCtlRegs = 72, kPromoEpiRegs = 216;
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tile scheduler shared by the three warp roles of a persistent kernel.  Static mode: tile += stride.  Dynamic mode
+// (ConvGemmArgs::dyn): the TMA producer warp of the (leader) CTA issues, when it starts tile number `it`, the cluster
+// launch control query for the tile after it; the answer is multicast into slot it % kSchedStages of every CTA of
+// the pair; every role reads it (producer: after it has issued the tile's loads, the others: before they start the
+// tile) and releases the slot on the leader's barrier.  One query is in flight ahead of the tile being loaded and none
+// is issued after a failed one.
+constexpr int kSchedStages = 4;
+struct TileSched {
+  uint32_t resp;    // shared::cta address of the answer slots (16 B each)
+  uint64_t* full;   // [kSchedStages] 16 transaction bytes each
+  uint64_t* empty;  // [kSchedStages] one arrival per consumer warp of the cluster (on the leader CTA)
+  int dyn, stride, total;
+};
+template <bool PAIR>
+__device__ __forceinline__ void sched_issue(const TileSched& s, int it, int lane) {
+  const int slot = it % kSchedStages;
+  mbar_wait(&s.empty[slot], ((static_cast<uint32_t>(it) / kSchedStages) & 1u) ^ 1u);
+  if (lane < (PAIR ? 2 : 1)) {
+    if constexpr (PAIR)
+      mbar_expect_tx_cluster(map_to_cta(smem_u32(&s.full[slot]), lane), 16);
+    else
+      mbar_expect_tx(&s.full[slot], 16);
+  }
+  __syncwarp();
+  if (lane == 0) clc_try_cancel<PAIR>(s.resp + slot * 16, smem_u32(&s.full[slot]));
+  __syncwarp();
+}
+// the tile after tile number `it` of this CTA (pair): >= total when there is none
+template <bool PAIR>
+__device__ __forceinline__ int sched_next(const TileSched& s, int it, int t, int lane) {
+  if (!s.dyn) return t + s.stride;
+  const int slot = it % kSchedStages;
+  mbar_wait(&s.full[slot], (static_cast<uint32_t>(it) / kSchedStages) & 1u);
+  const int x = clc_decode(s.resp + slot * 16);
+  fence_proxy_async_smem();   // this (generic-proxy) read is ordered before the next asynchronous write of the slot
+  __syncwarp();
+  if (lane == 0) {
+    if constexpr (PAIR)
+      mbar_arrive_cluster(map_to_cta(smem_u32(&s.empty[slot]), 0));
+    else
+      mbar_arrive(&s.empty[slot]);
+  }
+  return x < 0 ? s.total : (PAIR ? x >> 1 : x);
+}
 
 template <bool TF32>
 __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
@@ -600,7 +652,7 @@ template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
                                                    uint64_t* acc_empty, float* colsum_s, uint8_t* store_s,
                                                    int total_tiles, int m_tiles, int warp, int lane,
-                                                   uint32_t rank = 0) {
+                                                   uint32_t rank = 0, const TileSched* sched = nullptr) {
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns this warp handles
     uint8_t* stage = store_s + (warp - (PROMO ? 4 : 2)) * kStoreWarpBytes;   // this warp's store staging tile
@@ -622,7 +674,9 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
 #pragma unroll
       for (int c = 0; c < 32; ++c) lacc.db[c] = 0.f;
     }
-    for (int t = PAIR ? blockIdx.x >> 1 : blockIdx.x; t < total_tiles; t += t_step) {
+    int t_next = 0;
+    for (int t = PAIR ? blockIdx.x >> 1 : blockIdx.x, it = 0; t < total_tiles; t = t_next, ++it) {
+      t_next = sched ? sched_next<PAIR>(*sched, it, t, lane) : t + t_step;
       const int nb = t % g.tiles_n;
       const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
       const int sp = t / (g.tiles_n * m_tiles);
@@ -805,6 +859,12 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* colsum_s = reinterpret_cast<float*>(bar_base + Cfg::kBarBytes);
   uint8_t* store_s = bar_base + Cfg::kBarBytes + Cfg::kColsumBytes;
+  // tile scheduler (second half of the barrier block): answer slots, then their barriers
+  TileSched sched;
+  sched.resp = smem_u32(bar_base + 512);
+  sched.full = reinterpret_cast<uint64_t*>(bar_base + 512 + 16 * kSchedStages);
+  sched.empty = sched.full + kSchedStages;
+  sched.dyn = g.dyn;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -823,6 +883,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   const int t_step = PAIR ? gridDim.x >> 1 : gridDim.x;
   const int kb_per_seg = g.taps * g.cblocks;
   const int total_kb = g.nseg * kb_per_seg;
+  sched.stride = t_step;
+  sched.total = total_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nseg; ++s) {
@@ -836,6 +898,11 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
+    }
+    for (int s = 0; s < kSchedStages; ++s) {
+      mbar_init(&sched.full[s], 1);
+      // consumers: producer + MMA + epilogue warps of the leader, producer + epilogue warps of the partner
+      mbar_init(&sched.empty[s], PAIR ? 2 * kEpiWarps + 3 : kEpiWarps + 2);
     }
     fence_mbar_init();
   }
@@ -863,7 +930,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
       int stage = 0;
       uint32_t phase = 0;
       long long dbg_wait_empty = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
+      for (int t = t_first, it = 0; t < total_tiles; ++it) {
+        if (g.dyn && rank == 0) sched_issue<PAIR>(sched, it, lane);   // ask for the tile after this one
         const int nb = t % g.tiles_n;
         const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
         const int sp = t / (g.tiles_n * m_tiles);
@@ -945,6 +1013,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
             }
           }
         }
+        t = sched_next<PAIR>(sched, it, t, lane);
       }
       if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 4] = dbg_wait_empty;
     }
@@ -968,7 +1037,9 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     uint32_t aphase = 0;
     long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
     const long long dbg_t0 = g.dbg ? clock64() : 0;
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    int t_next = 0;
+    for (int t = t_first, it = 0; t < total_tiles; t = t_next, ++it) {
+      t_next = sched_next<PAIR>(sched, it, t, lane);
       const int sp = t / (g.tiles_n * m_tiles);
       const int kb0 = sp * g.kb_per_split;
       const int kb1 = min(total_kb, kb0 + g.kb_per_split);
@@ -1054,7 +1125,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     // ============================== epilogue ==============================
     if constexpr (PROMO) setmaxnreg_inc<kPromoEpiRegs>();
     conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_tiles,
-                                                   m_tiles, warp, lane, rank);
+                                                   m_tiles, warp, lane, rank, &sched);
   }
 
   tc_fence_before();
@@ -1144,6 +1215,13 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 
   const int m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
   const int total_tiles = m_tiles * g.tiles_n;
+  TileSched sched;   // as in conv_gemm_kernel
+  sched.resp = smem_u32(bar_base + 512);
+  sched.full = reinterpret_cast<uint64_t*>(bar_base + 512 + 16 * kSchedStages);
+  sched.empty = sched.full + kSchedStages;
+  sched.dyn = g.dyn;
+  sched.stride = gridDim.x;
+  sched.total = total_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nseg; ++s) {
@@ -1161,6 +1239,10 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], kEpiWarps);
+    }
+    for (int s = 0; s < kSchedStages; ++s) {
+      mbar_init(&sched.full[s], 1);
+      mbar_init(&sched.empty[s], kEpiWarps + 2);
     }
     fence_mbar_init();
   }
@@ -1193,7 +1275,8 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         }
         __syncwarp();
       }
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x, it = 0; t < total_tiles; ++it) {
+        if (g.dyn) sched_issue<false>(sched, it, lane);
         const int nb = t % g.tiles_n;
         const int mt = t / g.tiles_n;
         const int tx = mt % g.tiles_x;
@@ -1235,6 +1318,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
             }
           }
         }
+        t = sched_next<false>(sched, it, t, lane);
       }
     }
   } else if (warp == 1) {
@@ -1254,7 +1338,9 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
     long long dbg_a = 0, dbg_b = 0, dbg_acc = 0, dbg_kb = 0, tw = 0;
     const long long dbg_t0 = g.dbg ? clock64() : 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int t_next = 0;
+    for (int t = blockIdx.x, it = 0; t < total_tiles; t = t_next, ++it) {
+      t_next = sched_next<false>(sched, it, t, lane);
       if (g.dbg) tw = clock64();
       mbar_wait(&acc_empty[acs], acph ^ 1);
       if (g.dbg) dbg_acc += clock64() - tw;
@@ -1339,7 +1425,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   } else {
     // ============================== epilogue ==============================
     conv_epilogue_loop<BN, false>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_tiles, m_tiles, warp,
-                                  lane);
+                                  lane, 0, &sched);
   }
 
   tc_fence_before();
@@ -1379,6 +1465,7 @@ struct WgradArgs {
   int b_mode, blk_row;
   float acc_scale;  // round-toward-zero compensation of the TMEM accumulation (see ConvGemmArgs::acc_scale)
   long long* dbg;   // measurement only: per-CTA wait-cycle counters (see ConvGemmArgs::dbg)
+  int dyn;          // dynamic tile scheduling (see ConvGemmArgs::dyn)
 };
 
 template <int BN, bool TF32>
@@ -1426,6 +1513,13 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
   const int pb_per_seg = g.pb_x * g.pb_y * g.pb_b;
   const int total_pb = g.nseg * pb_per_seg;
   const int cin_chunks = g.Cin / CH;
+  TileSched sched;   // as in conv_gemm_kernel
+  sched.resp = smem_u32(bar_base + 512);
+  sched.full = reinterpret_cast<uint64_t*>(bar_base + 512 + 16 * kSchedStages);
+  sched.empty = sched.full + kSchedStages;
+  sched.dyn = g.dyn;
+  sched.stride = t_step;
+  sched.total = total_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.nseg; ++s) {
@@ -1439,6 +1533,10 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
+    }
+    for (int s = 0; s < kSchedStages; ++s) {
+      mbar_init(&sched.full[s], 1);
+      mbar_init(&sched.empty[s], PAIR ? 2 * kEpiWarps + 3 : kEpiWarps + 2);
     }
     fence_mbar_init();
   }
@@ -1460,7 +1558,8 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     {   // TMA producer: whole warp runs the uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = t_first; t < total_tiles; t += t_step) {
+      for (int t = t_first, it = 0; t < total_tiles; ++it) {
+        if (g.dyn && rank == 0) sched_issue<PAIR>(sched, it, lane);
         const int nb = t % g.tiles_n;
         const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_sched) + static_cast<int>(rank) : (t / g.tiles_n) % m_sched;
         const int sp = t / (g.tiles_n * m_sched);
@@ -1536,6 +1635,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
             phase ^= 1;
           }
         }
+        t = sched_next<PAIR>(sched, it, t, lane);
       }
     }
   } else if (warp == 1 && rank == 0) {
@@ -1551,7 +1651,9 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     uint32_t aphase = 0;
     long long dbg_full = 0, dbg_acc = 0, dbg_kb = 0;
     const long long dbg_t0 = g.dbg ? clock64() : 0;
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    int t_next = 0;
+    for (int t = t_first, it = 0; t < total_tiles; t = t_next, ++it) {
+      t_next = sched_next<PAIR>(sched, it, t, lane);
       const int sp = t / (g.tiles_n * m_sched);
       const int pb0 = sp * g.pb_per_split;
       const int pb1 = min(total_pb, pb0 + g.pb_per_split);
@@ -1617,7 +1719,9 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
     uint32_t aphase = 0;
     const size_t rows_pad = static_cast<size_t>(g.m_tiles) * 128;
     const uint32_t lead_acc_empty = PAIR ? map_to_cta(smem_u32(acc_empty), 0) : 0;
-    for (int t = t_first; t < total_tiles; t += t_step) {
+    int t_next = 0;
+    for (int t = t_first, it = 0; t < total_tiles; t = t_next, ++it) {
+      t_next = sched_next<PAIR>(sched, it, t, lane);
       const int nb = t % g.tiles_n;
       const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_sched) + static_cast<int>(rank) : (t / g.tiles_n) % m_sched;
       const int sp = t / (g.tiles_n * m_sched);

@@ -270,6 +270,45 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- cluster launch control (dynamic persistent tiles)
+// A grid of one cluster per work unit is launched; a running cluster asks the hardware to CANCEL a not-yet-launched
+// cluster and takes over its unit (scripts/clc_probe.cu is the minimal complete kernel).  The 16-byte answer lands in
+// shared memory (of every CTA of the cluster with .multicast::cluster::all) and completes 16 transaction bytes on the
+// mbarrier at the same offset.
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_addr, uint32_t bar_addr) {
+  if constexpr (CLUSTER)
+    asm volatile(
+        "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+        "[%0], [%1];" ::"r"(resp_addr), "r"(bar_addr)
+        : "memory");
+  else
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                     resp_addr),
+                 "r"(bar_addr)
+                 : "memory");
+}
+// x coordinate of the first CTA of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_decode(uint32_t resp_addr) {
+  uint32_t x, valid;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1;\n\t"
+      ".reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t"
+      "}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_addr)
+      : "memory");
+  return valid ? static_cast<int>(x) : -1;
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (64-bit): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 // layout type [61,64) (2 = SWIZZLE_128B).

