@@ -46,4 +46,6 @@ def test_engine_on_a_device_that_is_not_the_current_one(cuda_device):
         assert torch.cuda.current_device() == 0
         torch.cuda.synchronize(dev)
         outs.append((logits, e.loss_value((1, 64, 96))))
-    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+    assert torch.equal(outs[0][0], outs[1][0])          # per-tile arithmetic does not depend on the device
+    # the loss is a sum of per-CTA partial sums added with atomics: their order is not fixed (dynamic tile scheduling)
+    assert abs(outs[0][1] - outs[1][1]) <= 1e-6 * abs(outs[0][1])
