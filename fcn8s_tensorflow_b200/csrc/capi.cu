@@ -659,7 +659,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   if (pl.splits > 1) kernel_args.flags = EPI_PARTIAL;
   if (use_halo) {
     const long long tiles = (long long)pl.m_tiles * pl.tiles_n;
-    a.dyn = g_debug[10] ? 0 : 1;   // dynamic tile scheduling, see below
+    a.dyn = g_debug[10] ? 1 : 0;   // dynamic tile scheduling, see below
     const int hgrid = (int)((a.dyn || tiles < num_sms()) ? tiles : num_sms());
     if ((long long)pl.tiles_n * pl.BN > 256) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs Cout <= 256");
     // weights resident in shared memory when the CTA's whole slice is one group of 9 taps (conv1_2 fwd / dgrad, bf16)
@@ -671,8 +671,9 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     return he == cudaSuccess ? 0 : cuda_fail(he, "conv_halo launch");
   }
   // dynamic tile scheduling (ConvGemmArgs::dyn): one CTA (pair) per tile in the grid, the resident ones take over the
-  // tiles of those not yet launched; debug key 10 = 1 keeps the static round-robin over min(tiles, #SMs) CTAs
-  const bool dyn = !g_debug[10];
+  // tiles of those not yet launched; switched on with debug key 10 = 1 (the engine does when it runs data parallel); default: static round-robin over
+  // min(tiles, #SMs) CTAs, which is 2-3 % faster for the short tiles of the halo kernels when nothing else holds SMs
+  const bool dyn = g_debug[10] != 0;
   kernel_args.dyn = dyn ? 1 : 0;
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
   const int grid = (int)((dyn || total_tiles < num_sms()) ? total_tiles : num_sms());
@@ -861,7 +862,7 @@ int32_t fcn8_wgrad_gemm(const Fcn8WgradParams* p, void* workspace, size_t worksp
     a.acc_scale = 1.f + (float)mma_per_pb * (float)pl.pb_per_split / (float)p->nseg * rz_per_mma();
   }
   const long long total_tiles = (long long)pl.m_tiles * pl.tiles_n * pl.splits;
-  a.dyn = g_debug[10] ? 0 : 1;   // dynamic tile scheduling (ConvGemmArgs::dyn)
+  a.dyn = g_debug[10] ? 1 : 0;   // dynamic tile scheduling (ConvGemmArgs::dyn)
   const int grid = (int)((a.dyn || total_tiles < num_sms()) ? total_tiles : num_sms());
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;

@@ -815,7 +815,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
         aphase ^= 1;
       }
     }
-    if (g.dbg && lane == 0 && warp == (PROMO ? 4 : 2)) {   // first epilogue warp: [6] = idle cycles, [7] = loop cycles
+    if (g.dbg && lane == 0 && warp == (PROMO ? 4 : 2) && blockIdx.x < 148) {   // first epilogue warp: [6] = idle cycles, [7] = loop cycles
       g.dbg[8 * blockIdx.x + 6] = dbg_wait;
       g.dbg[8 * blockIdx.x + 7] = clock64() - dbg_e0;
     }
@@ -1015,7 +1015,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         }
         t = sched_next<PAIR>(sched, it, t, lane);
       }
-      if (g.dbg && lane == 0) g.dbg[8 * blockIdx.x + 4] = dbg_wait_empty;
+      if (g.dbg && lane == 0 && blockIdx.x < 148) g.dbg[8 * blockIdx.x + 4] = dbg_wait_empty;
     }
   } else if (warp == 1 && rank == 0) {
     // ============================== MMA issuer (the leader CTA of a pair issues for both) ==============================
@@ -1114,7 +1114,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         aphase ^= 1;
       }
     }
-    if (g.dbg && lane == 0) {
+    if (g.dbg && lane == 0 && blockIdx.x < 148) {
       g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
       g.dbg[8 * blockIdx.x + 1] = dbg_full;
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;
@@ -1415,7 +1415,7 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
         acph ^= 1;
       }
     }
-    if (g.dbg && lane == 0) {   // as in conv_gemm_kernel; [1] = activation patches, [5] = weight stages, [3] = patches
+    if (g.dbg && lane == 0 && blockIdx.x < 148) {   // as in conv_gemm_kernel; [1] = activation patches, [5] = weight stages, [3] = patches
       g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
       g.dbg[8 * blockIdx.x + 1] = dbg_a;
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;
@@ -1705,7 +1705,7 @@ wgrad_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const WgradArgs g) {
         aphase ^= 1;
       }
     }
-    if (g.dbg && lane == 0) {
+    if (g.dbg && lane == 0 && blockIdx.x < 148) {
       g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
       g.dbg[8 * blockIdx.x + 1] = dbg_full;
       g.dbg[8 * blockIdx.x + 2] = dbg_acc;

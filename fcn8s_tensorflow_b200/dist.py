@@ -107,6 +107,11 @@ def attach(engine, group=None):
     engine.nccl_registered = False
     if engine.allreduce is None:
         return engine
+    lib = getattr(engine, "lib", None)
+    if lib is not None and os.environ.get("FCN8_DYNAMIC_TILES", "1") != "0":
+        # the collective's CTAs take SMs away from the persistent GEMM kernels of the backward pass: let the resident
+        # CTAs take over the tiles of those that cannot start (cluster launch control, ConvGemmArgs::dyn)
+        lib.fcn8_debug_set(10, 1)
     if getattr(engine, "grad_comm", "fp32") == "bf16":
         # wire copy of the flat gradient: the collective moves 269 MB instead of 538 MB per step
         t, pool = _registered_zeros(engine.n_flat, torch.bfloat16, engine.device, group)

@@ -83,8 +83,9 @@ uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc);
  *   3    : bit 0: conv epilogues skip their output stores, bit 1: ... and their mask / residual loads (timing only)
  *   5 = 1: single-CTA kernels instead of the CTA-pair (cta_group::2) variants of conv_gemm / wgrad_gemm
  *   6 = 1: launch every kernel with the programmatic-dependent-launch attribute (kernels.h)
- *  10 = 1: static tile assignment (round-robin over min(tiles, #SMs) CTAs) instead of the dynamic one (cluster launch
- *          control: one CTA / CTA pair per tile in the grid, running CTAs cancel pending ones and take their tiles) */
+ *  10 = 1: dynamic tile assignment in the persistent GEMM kernels (cluster launch control: one CTA / CTA pair per tile
+ *          in the grid, running CTAs cancel pending ones and take their tiles) instead of the static round-robin over
+ *          min(tiles, #SMs) CTAs; the engine switches it on when a gradient all-reduce runs under the backward pass */
 int32_t fcn8_debug_set(int32_t key, int32_t value);
 /* Measurement only: `buf` = device buffer of slots*148*8 int64; every following fcn8_conv_gemm / fcn8_wgrad_gemm launch
  * takes the next slot and its CTAs write their MMA-warp wait-cycle counters there (csrc/conv_gemm.cuh,

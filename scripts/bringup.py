@@ -865,6 +865,45 @@ def promoted_accumulation():
     return ok
 
 
+@case
+def dynamic_tiles():
+    """Dynamic tile scheduling (cluster launch control, fcn8_debug_set(10, 1)): the grid holds one CTA / CTA pair per
+    tile, running CTAs cancel pending ones and take their tiles.  Same references as the static cases -- per-tap, pair,
+    promoted, split-K and halo forward / dgrad kernels, the filter-gradient kernels -- plus bit-for-bit equality with
+    the static schedule (a tile's arithmetic does not depend on which CTA runs it).  scripts/clc_probe.cu is the
+    stand-alone probe of the mechanism."""
+    from fcn8s_tensorflow_b200 import _capi, ops
+    lib = _capi.load()
+    torch.manual_seed(41)
+    dev = torch.device("cuda")
+    w = torch.randn(3, 3, 256, 256, device=dev) / 48.0
+    wh, wl = _shadow(w, True)
+    x = ops.to_pair(torch.randn(5, 44, 52, 256, device=dev))      # 90 M tiles: more than one wave of CTA pairs
+    w64 = torch.randn(3, 3, 64, 64, device=dev) / 24.0
+    wh64, _ = _shadow(w64, False)
+    x64 = torch.randn(3, 100, 120, 64, device=dev).to(torch.bfloat16)   # 315 halo tiles
+    y_static = ops.conv_gemm(x, wh, 256, 3, wp_lo=wl, pair=True, w_mode=1, algo=1)
+    h_static = ops.conv_gemm(x64, wh64, 64, 3, w_mode=1)
+    lib.fcn8_debug_set(10, 1)
+    try:
+        ok = hwio_conv_case(3, 20, 36, 256, 256, 3, True, 2e-5, algo=1)       # pair + promoted, odd tile count
+        ok &= hwio_conv_case(1, 4, 8, 512, 256, 7, True, 2e-5)                # split-K partials
+        ok &= hwio_conv_case(2, 16, 32, 256, 128, 3, False, 1e-2, force_bn=128)
+        ok &= hwio_conv_case(3, 20, 36, 64, 128, 3, True, 2e-5)               # halo kernels, ragged tiles
+        ok &= hwio_conv_case(2, 16, 32, 64, 64, 3, False, 1e-2)               # halo, resident weights
+        ok &= wgrad_case(3, 20, 36, 128, 256, 3, 0, 1e-2)
+        ok &= wgrad_case(2, 16, 32, 256, 512, 3, 0, 1e-2)
+        ok &= wgrad_case(1, 8, 16, 512, 256, 7, 0, 1e-2)
+        y_dyn = ops.conv_gemm(x, wh, 256, 3, wp_lo=wl, pair=True, w_mode=1, algo=1)
+        h_dyn = ops.conv_gemm(x64, wh64, 64, 3, w_mode=1)
+        torch.cuda.synchronize()
+    finally:
+        lib.fcn8_debug_set(10, 0)
+    same = bool(torch.equal(y_dyn, y_static)) and bool(torch.equal(h_dyn, h_static))
+    print("  %-58s %s" % ("dynamic schedule == static schedule, bit for bit", "OK" if same else "FAIL"))
+    return ok and same
+
+
 def main():
     args = sys.argv[1:]
     if not args or args[0] == "list":
