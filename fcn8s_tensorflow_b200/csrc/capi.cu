@@ -304,6 +304,35 @@ cudaError_t launch_halo_t(const TensorMaps3& maps, const ConvGemmArgs& a, int gr
   return cudaGetLastError();
 }
 
+// CTA-pair halo kernel (clusters of two, cta_group::2); `grid` is even
+template <int BN, bool RB = false>
+cudaError_t launch_halo_pair_t(const TensorMaps3& maps, const ConvGemmArgs& a, int grid, cudaStream_t st) {
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[cur_dev()];
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_pair_kernel<BN, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         HaloPairSmem<BN, RB>::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = HaloPairSmem<BN, RB>::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl_off ? 1 : 2;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, conv_halo_pair_kernel<BN, RB>, maps, a);
+}
+
 template <int BN, bool TF32>
 constexpr int wgrad_smem_bytes() {
   constexpr int CH = TF32 ? 32 : 64;
@@ -562,7 +591,10 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   }
   // CTA pairs for the 256-column bf16 tiles of the per-tap kernel (debug key 5 = 1 keeps the single-CTA kernel)
   const bool use_pair = !use_halo && pl.BN == 256 && p->dtype == FCN8_BF16 && !g_debug[5];
-  const int b_rows = use_pair ? pl.BN / 2 : pl.BN;   // rows of the weight tile one CTA loads
+  // CTA pairs for the narrow halo tiles too (conv_halo_pair_kernel): K-major weights (dgrad) at N = 64 / 128, MN-major
+  // weights (fprop) need N/2 >= 64 columns per CTA; debug key 11 = 1 keeps the single-CTA halo kernel
+  const bool halo_pair = use_halo && !g_debug[11] && !g_debug[5] && pl.BN <= 128 && (p->w_mode == 2 || pl.BN == 128);
+  const int b_rows = (use_pair || halo_pair) ? pl.BN / 2 : pl.BN;   // rows of the weight tile one CTA loads
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
   const int ktot = p->ksize * p->ksize * p->Cin;
@@ -662,6 +694,17 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     a.dyn = g_debug[10] ? 1 : 0;   // dynamic tile scheduling, see below
     const int hgrid = (int)((a.dyn || tiles < num_sms()) ? tiles : num_sms());
     if ((long long)pl.tiles_n * pl.BN > 256) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs Cout <= 256");
+    if (halo_pair) {
+      const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n;
+      const int pairs = (int)((a.dyn || units < num_sms() / 2) ? units : num_sms() / 2);
+      // the CTA's half of all nine taps of every (set, channel block) stays resident when it fits: 6 groups of 12 KB
+      const bool res = pl.BN == 64 && pl.tiles_n == 1 && p->w_mode == 2 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 2 &&
+                       !g_debug[2];
+      cudaError_t pe = pl.BN == 128 ? launch_halo_pair_t<128>(maps, a, 2 * pairs, (cudaStream_t)stream)
+                       : res        ? launch_halo_pair_t<64, true>(maps, a, 2 * pairs, (cudaStream_t)stream)
+                                    : launch_halo_pair_t<64>(maps, a, 2 * pairs, (cudaStream_t)stream);
+      return pe == cudaSuccess ? 0 : cuda_fail(pe, "conv_halo_pair launch");
+    }
     // weights resident in shared memory when the CTA's whole slice is one group of 9 taps (conv1_2 fwd / dgrad, bf16)
     const bool resident = pl.BN == 64 && pl.tiles_n == 1 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 1 && !g_debug[2];
     cudaError_t he = pl.BN == 256 ? launch_halo_t<256>(maps, a, hgrid, (cudaStream_t)stream)

@@ -1444,6 +1444,275 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// conv_halo_pair_kernel: conv_halo_kernel on CTA pairs (tcgen05 cta_group::2) for the narrow tiles (N = 64 / 128).
+// A single CTA's N = 64 MMA needs 4 KB of A + 2 KB of B from shared memory per 32-cycle instruction, N = 128 needs
+// 4 + 4 KB, and the TMA fills of the weight stages go through the same 128 B/clk port: the single-CTA kernel runs at
+// 85 cycles per N = 64 MMA (36 % tensor pipe) and 50 % for N = 128 (profiles/r02_launches_fp32.md).  In a pair each
+// CTA owns one 16 x 8-pixel tile and its halo patch but only HALF of the weight rows (N/2): the M = 256 MMA reads
+// 4 KB + 1 (2) KB per CTA, and the weight traffic per CTA halves -- for N = 64 with <= 2 (set, channel-block)
+// combinations the CTA's share of ALL nine taps (hi and lo) is 72 KB and stays resident for the whole kernel (RB).
+// K-major weights (dgrad, b_mode 1) for every width; MN-major weights (fprop, b_mode 2) need N/2 >= 64, i.e. BN >= 128.
+// Roles, barriers and the scheduler as in conv_gemm_kernel<.., PAIR>; epilogue shared.
+template <int BN, bool RB = false>
+struct HaloPairSmem {
+  static constexpr int kTaps = (BN == 64) ? 3 : 1;           // filter taps per weight stage (see HaloSmem)
+  static constexpr int kBRows = BN / 2;                      // weight rows this CTA holds
+  static constexpr int kBBytes = kTaps * kBRows * 128;       // one stage / one resident (set, cb, kh) group
+  static constexpr int kAStages = 3;
+  static constexpr int kBStages = RB ? 6 : 8;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kColsumBytes = 1024;
+  static constexpr int kStoreBytes = kEpiWarpsC * kStoreWarpBytes;
+  static constexpr int kBytes = kAStages * HaloCfg::kABytes + kBStages * kBBytes + kBarBytes + kColsumBytes +
+                                kStoreBytes + 1024;
+  static_assert(kBytes <= 232448, "shared memory of the pair halo kernel");
+};
+
+template <int BN, bool RB = false>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g) {
+  pdl_launch_dependents();
+  static_assert(BN == 64 || BN == 128, "pair halo tiles: N = 64 or 128");
+  static_assert(!RB || BN == 64, "resident weights only for the N = 64 tiles");
+  using HS = HaloPairSmem<BN, RB>;
+  constexpr int kAS = HS::kAStages, kBS = HS::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem + kAS * HaloCfg::kABytes;
+  uint8_t* bar_base = smem_b + kBS * HS::kBBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* a_empty = a_full + kAS;
+  uint64_t* b_full = a_empty + kAS;
+  uint64_t* b_empty = b_full + kBS;
+  uint64_t* acc_full = b_empty + kBS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* colsum_s = reinterpret_cast<float*>(bar_base + HS::kBarBytes);
+  uint8_t* store_s = bar_base + HS::kBarBytes + HS::kColsumBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  if (g.flags & EPI_COLSUM)
+    for (int c = threadIdx.x; c < g.tiles_n * BN; c += kGemmThreads) colsum_s[c] = 0.f;
+
+  const int real_m_tiles = g.tiles_x * g.tiles_y * g.tiles_b;
+  const int m_pairs = (real_m_tiles + 1) / 2;
+  const int total_units = m_pairs * g.tiles_n;
+  const int t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+  TileSched sched;
+  sched.resp = smem_u32(bar_base + 512);
+  sched.full = reinterpret_cast<uint64_t*>(bar_base + 512 + 16 * kSchedStages);
+  sched.empty = sched.full + kSchedStages;
+  sched.dyn = g.dyn;
+  sched.stride = t_step;
+  sched.total = total_units;
+  const int nsets = g.nseg >= 2 ? 2 : 1;   // distinct weight operands: segment s reads set min(s, 1)
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.nseg; ++s) {
+      tma_prefetch_desc(&maps.a[s]);
+      tma_prefetch_desc(&maps.b[s]);
+    }
+    for (int s = 0; s < kAS; ++s) {
+      mbar_init(&a_full[s], 2);    // the leader's expect_tx arrive + the partner's plain arrive
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kBS; ++s) {
+      mbar_init(&b_full[s], 2);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * kEpiWarps);
+    }
+    for (int s = 0; s < kSchedStages; ++s) {
+      mbar_init(&sched.full[s], 1);
+      mbar_init(&sched.empty[s], 2 * kEpiWarps + 3);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_pair<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs; bytes are counted on the leader's barriers) =============
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    if constexpr (RB) {
+      // this CTA's half of every weight row group (set, cb, kh), once
+      const int ngroups = nsets * g.cblocks * 3;
+      if (elect_one()) {
+        const uint32_t lead = map_to_cta(smem_u32(&b_full[0]), 0);
+        if (rank == 0)
+          mbar_expect_tx(&b_full[0], static_cast<uint32_t>(2 * ngroups) * HS::kBBytes);
+        else
+          mbar_arrive_cluster(lead);
+        for (int set = 0; set < nsets; ++set)
+          for (int cb = 0; cb < g.cblocks; ++cb)
+            for (int kh = 0; kh < 3; ++kh) {
+              uint8_t* sb = smem_b + ((set * g.cblocks + cb) * 3 + kh) * HS::kBBytes;
+              tma_load_3d_pair(&maps.b[set], lead, sb, cb * 64, static_cast<int>(rank) * HS::kBRows, 8 - 3 * kh - 2);
+            }
+      }
+      __syncwarp();
+    }
+    for (int t = t_first, it = 0; t < total_units; ++it) {
+      if (g.dyn && rank == 0) sched_issue<true>(sched, it, lane);
+      const int nb = t % g.tiles_n;
+      const int mt = 2 * (t / g.tiles_n) + static_cast<int>(rank);
+      const int tx = mt % g.tiles_x;
+      const int ty = (mt / g.tiles_x) % g.tiles_y;
+      const int n0 = mt / (g.tiles_x * g.tiles_y);   // (a partner past the last tile reads rows outside: zero fill)
+      const int x0 = tx << 3, y0 = ty << 4;
+      const int nrow = nb * BN + static_cast<int>(rank) * HS::kBRows;
+      for (int seg = 0; seg < g.nseg; ++seg) {
+        for (int cb = 0; cb < g.cblocks; ++cb) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (elect_one()) {
+            const uint32_t lead = map_to_cta(smem_u32(&a_full[as]), 0);
+            if (rank == 0)
+              mbar_expect_tx(&a_full[as], 2 * HaloCfg::kABytes);
+            else
+              mbar_arrive_cluster(lead);
+            tma_load_4d_pair(&maps.a[seg], lead, smem + as * HaloCfg::kABytes, cb * 64, x0 - 1, y0 - 1, n0);
+          }
+          __syncwarp();
+          if (++as == kAS) {
+            as = 0;
+            aph ^= 1;
+          }
+          for (int tap = 0; tap < (RB ? 0 : 9); tap += HS::kTaps) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            uint8_t* sb = smem_b + bs * HS::kBBytes;
+            if (elect_one()) {
+              const uint32_t lead = map_to_cta(smem_u32(&b_full[bs]), 0);
+              if (rank == 0)
+                mbar_expect_tx(&b_full[bs], 2 * HS::kBBytes);
+              else
+                mbar_arrive_cluster(lead);
+              if (g.b_mode == 1) {
+                tma_load_3d_pair(&maps.b[seg], lead, sb, cb * 64, nrow, 8 - tap - (HS::kTaps - 1));
+              } else {
+#pragma unroll
+                for (int j = 0; j < HS::kBRows / 64; ++j)
+                  tma_load_3d_pair(&maps.b[seg], lead, sb + j * (HS::kTaps * 8192), nrow + j * 64, cb * 64, tap);
+              }
+            }
+            __syncwarp();
+            if (++bs == kBS) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+      t = sched_next<true>(sched, it, t, lane);
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ============================== MMA issuer (leader CTA, M = 256 over both CTAs' shared memory) ==================
+    const bool b_mn = g.b_mode == 2;
+    const uint32_t idesc = make_idesc(1u, 0u, b_mn ? 1u : 0u, 256u, BN);
+    const uint64_t adesc0 = make_smem_desc_sw128(0, 16, 2048);
+    const uint64_t bdesc0 = b_mn ? make_smem_desc_sw128(0, HS::kTaps * 8192, 1024) : make_smem_desc_sw128(0, 16, 1024);
+    const uint32_t badv = b_mn ? 128u : 2u;
+    const uint32_t sa_base = smem_u32(smem), sb_base = smem_u32(smem_b);
+    int as = 0, bs = 0, acs = 0;
+    uint32_t aph = 0, bph = 0, acph = 0;
+    if constexpr (RB) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    int t_next = 0;
+    for (int t = t_first, it = 0; t < total_units; t = t_next, ++it) {
+      t_next = sched_next<true>(sched, it, t, lane);
+      mbar_wait(&acc_empty[acs], acph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acs * BN;
+      uint32_t first = 0;
+      for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        const uint32_t sa = sa_base + as * HaloCfg::kABytes;
+        const int seg = kbk / g.cblocks;
+        const int rb_group0 = ((seg >= 1 ? nsets - 1 : 0) * g.cblocks + (kbk - seg * g.cblocks)) * 3;
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int kw0 = 0; kw0 < 3; kw0 += HS::kTaps) {
+            if constexpr (!RB) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+            }
+            const uint32_t sb = sb_base + (RB ? (rb_group0 + kh) : bs) * HS::kBBytes;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < HS::kTaps; ++j) {
+                const int kw = kw0 + j;
+                const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
+                const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
+                const int slot = b_mn ? j : (HS::kTaps - 1 - j);
+                const uint32_t b_addr = sb + static_cast<uint32_t>(slot) * (b_mn ? 8192u : static_cast<uint32_t>(HS::kBRows) * 128u);
+                const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_pair(d_tmem, adesc + 2 * k, bdesc + badv * k, idesc, first | static_cast<uint32_t>(j + k > 0));
+                first = 1;
+              }
+              if constexpr (!RB) umma_commit_pair(&b_empty[bs], 3);
+            }
+            __syncwarp();
+            first = 1;
+            if constexpr (!RB) {
+              if (++bs == kBS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+        if (elect_one()) umma_commit_pair(&a_empty[as], 3);
+        __syncwarp();
+        if (++as == kAS) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      if (elect_one()) umma_commit_pair(&acc_full[acs], 3);
+      __syncwarp();
+      if (++acs == 2) {
+        acs = 0;
+        acph ^= 1;
+      }
+    }
+  } else if (warp >= 2) {
+    conv_epilogue_loop<BN, false, true>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_units, m_pairs, warp,
+                                        lane, rank, &sched);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<2 * BN>(tmem_base);
+  }
+  if (g.flags & EPI_COLSUM) {
+    const int ncs = g.colsum_n > 0 ? min(g.colsum_n, g.tiles_n * BN) : g.tiles_n * BN;
+    for (int c = threadIdx.x; c < ncs; c += kGemmThreads) {
+      const float t = colsum_s[c];
+      if (t != 0.f) atomicAdd(g.colsum + c, t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // wgrad: D[(tap,ci) rows, co cols] = sum over pixels.  A = X (shifted per tap), B = dY, both MN-major:
 // a smem "chunk" is [64 pixels][128 B of channels], 128B-swizzled, exactly what a TMA box {CH, pbw, pbh, pbn} gives.
 struct WgradArgs {

@@ -83,6 +83,7 @@ uint32_t fcn8_crc32c(const void* data, size_t n, uint32_t crc);
  *   3    : bit 0: conv epilogues skip their output stores, bit 1: ... and their mask / residual loads (timing only)
  *   5 = 1: single-CTA kernels instead of the CTA-pair (cta_group::2) variants of conv_gemm / wgrad_gemm
  *   6 = 1: launch every kernel with the programmatic-dependent-launch attribute (kernels.h)
+ *  11 = 1: single-CTA conv_halo_kernel instead of the CTA-pair variant for the 64- / 128-column halo tiles
  *  10 = 1: dynamic tile assignment in the persistent GEMM kernels (cluster launch control: one CTA / CTA pair per tile
  *          in the grid, running CTAs cancel pending ones and take their tiles) instead of the static round-robin over
  *          min(tiles, #SMs) CTAs; the engine switches it on when a gradient all-reduce runs under the backward pass */
