@@ -576,7 +576,10 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
 
   // Halo-tile kernel for the L2-traffic-bound 3x3 layers (few input channels: the activation patch is loaded once per
   // tile instead of once per tap).  algo: 0 = heuristic, 1 = per-tap kernel, 2 = halo kernel.
-  const bool halo_ok = p->dtype == FCN8_BF16 && p->ksize == 3 && p->w_mode != 0 && p->Cin % 64 == 0;
+  // (packed forward weights, w_mode 0, only through the CTA-pair halo kernel and its 64-column tiles)
+  const bool pair_halo_on = !g_debug[11] && !g_debug[5];
+  const bool halo_ok = p->dtype == FCN8_BF16 && p->ksize == 3 && p->Cin % 64 == 0 &&
+                       (p->w_mode != 0 || (pair_halo_on && p->Cout == 64 && !(p->flags & FCN8_EPI_COLSUM)));
   const bool use_halo = halo_ok && p->Cout <= 256 && (p->algo >= 2 || (p->algo == 0 && p->Cin <= 128));
   if (p->algo >= 2 && !halo_ok) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs bf16, 3x3, w_mode 1/2");
   if (use_halo) {
@@ -593,7 +596,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   const bool use_pair = !use_halo && pl.BN == 256 && p->dtype == FCN8_BF16 && !g_debug[5];
   // CTA pairs for the narrow halo tiles too (conv_halo_pair_kernel): K-major weights (dgrad) at N = 64 / 128, MN-major
   // weights (fprop) need N/2 >= 64 columns per CTA; debug key 11 = 1 keeps the single-CTA halo kernel
-  const bool halo_pair = use_halo && !g_debug[11] && !g_debug[5] && pl.BN <= 128 && (p->w_mode == 2 || pl.BN == 128);
+  const bool halo_pair = use_halo && pair_halo_on && pl.BN <= 128 && (p->w_mode != 1 || pl.BN == 128);
   const int b_rows = (use_pair || halo_pair) ? pl.BN / 2 : pl.BN;   // rows of the weight tile one CTA loads
   TensorMaps3 maps;
   memset(&maps, 0, sizeof(maps));
@@ -698,7 +701,7 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
       const long long units = (long long)((pl.m_tiles + 1) / 2) * pl.tiles_n;
       const int pairs = (int)((a.dyn || units < num_sms() / 2) ? units : num_sms() / 2);
       // the CTA's half of all nine taps of every (set, channel block) stays resident when it fits: 6 groups of 12 KB
-      const bool res = pl.BN == 64 && pl.tiles_n == 1 && p->w_mode == 2 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 2 &&
+      const bool res = pl.BN == 64 && pl.tiles_n == 1 && p->w_mode != 1 && (p->nseg >= 2 ? 2 : 1) * (p->Cin / 64) <= 2 &&
                        !g_debug[2];
       cudaError_t pe = pl.BN == 128 ? launch_halo_pair_t<128>(maps, a, 2 * pairs, (cudaStream_t)stream)
                        : res        ? launch_halo_pair_t<64, true>(maps, a, 2 * pairs, (cudaStream_t)stream)

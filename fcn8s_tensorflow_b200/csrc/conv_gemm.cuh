@@ -1451,7 +1451,8 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 // CTA owns one 16 x 8-pixel tile and its halo patch but only HALF of the weight rows (N/2): the M = 256 MMA reads
 // 4 KB + 1 (2) KB per CTA, and the weight traffic per CTA halves -- for N = 64 with <= 2 (set, channel-block)
 // combinations the CTA's share of ALL nine taps (hi and lo) is 72 KB and stays resident for the whole kernel (RB).
-// K-major weights (dgrad, b_mode 1) for every width; MN-major weights (fprop, b_mode 2) need N/2 >= 64, i.e. BN >= 128.
+// K-major weights (dgrad, b_mode 1; packed forward operand, b_mode 0) for every width; MN-major weights (fprop from the
+// TF layout, b_mode 2) need N/2 >= 64 columns per CTA, i.e. BN >= 128 -- conv1_2's forward therefore reads a packed copy.
 // Roles, barriers and the scheduler as in conv_gemm_kernel<.., PAIR>; epilogue shared.
 template <int BN, bool RB = false>
 struct HaloPairSmem {
@@ -1558,7 +1559,14 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
           for (int cb = 0; cb < g.cblocks; ++cb)
             for (int kh = 0; kh < 3; ++kh) {
               uint8_t* sb = smem_b + ((set * g.cblocks + cb) * 3 + kh) * HS::kBBytes;
-              tma_load_3d_pair(&maps.b[set], lead, sb, cb * 64, static_cast<int>(rank) * HS::kBRows, 8 - 3 * kh - 2);
+              if (g.b_mode == 1) {
+                tma_load_3d_pair(&maps.b[set], lead, sb, cb * 64, static_cast<int>(rank) * HS::kBRows, 8 - 3 * kh - 2);
+              } else {   // b_mode 0: packed K-major [Cout][(tap, ci)], one box per tap, taps in filter order
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  tma_load_2d_pair(&maps.b[set], lead, sb + j * (HS::kBRows * 128), ((3 * kh + j) * g.cblocks + cb) * 64,
+                                   static_cast<int>(rank) * HS::kBRows);
+              }
             }
       }
       __syncwarp();
@@ -1599,6 +1607,10 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
                 mbar_arrive_cluster(lead);
               if (g.b_mode == 1) {
                 tma_load_3d_pair(&maps.b[seg], lead, sb, cb * 64, nrow, 8 - tap - (HS::kTaps - 1));
+              } else if (g.b_mode == 0) {
+#pragma unroll
+                for (int j = 0; j < HS::kTaps; ++j)
+                  tma_load_2d_pair(&maps.b[seg], lead, sb + j * (HS::kBRows * 128), ((tap + j) * g.cblocks + cb) * 64, nrow);
               } else {
 #pragma unroll
                 for (int j = 0; j < HS::kBRows / 64; ++j)
@@ -1657,7 +1669,9 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
                 const int kw = kw0 + j;
                 const uint32_t a_addr = sa + static_cast<uint32_t>(kh * 16 + kw) * 128u;
                 const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
-                const int slot = b_mn ? j : (HS::kTaps - 1 - j);
+                // slot of this tap in the stage: forward operands hold the taps in filter order, the dgrad box holds
+                // the rotated taps in ascending filter order, i.e. kw descending
+                const int slot = (g.b_mode != 1) ? j : (HS::kTaps - 1 - j);
                 const uint32_t b_addr = sb + static_cast<uint32_t>(slot) * (b_mn ? 8192u : static_cast<uint32_t>(HS::kBRows) * 128u);
                 const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
 #pragma unroll

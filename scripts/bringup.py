@@ -866,6 +866,49 @@ def promoted_accumulation():
 
 
 @case
+def halo_pair_packed_forward():
+    """conv_halo_pair_kernel with the packed K-major forward operand (w_mode 0; conv1_2's forward in the fp32-equivalent
+    mode: the 32 output channels per CTA of a pair are too narrow for the MN-major operand of the TF layout): hi/lo pair
+    and bf16 operands, Cin = 64 (resident half-weights) and 128 (two channel blocks), ragged tiles, odd tile counts,
+    with and without the fused max-pool -- against fp64 and against the TF-layout path (w_mode 1)."""
+    from fcn8s_tensorflow_b200 import ops
+    torch.manual_seed(17)
+    dev = torch.device("cuda")
+    ok = True
+    for (n, h, w_, cin, pair) in ((2, 32, 48, 64, True), (3, 20, 36, 64, True), (1, 16, 8, 128, True), (2, 32, 48, 64, False),
+                                  (1, 40, 24, 128, False)):
+        w = torch.randn(3, 3, cin, 64, device=dev) / (9 * cin) ** 0.5
+        b = torch.randn(64, device=dev)
+        wp, wpl = ops.pack_weights(w, 3, cin, 64, 0, ops.BF16, split=pair)
+        wh, wl = _shadow(w, pair)
+        wq = (wp.double() + wpl.double()) if pair else wp.double()
+        wq = wq.view(64, 9, cin).permute(1, 2, 0).reshape(3, 3, cin, 64)
+        x32 = torch.randn(n, h, w_, cin, device=dev)
+        x = ops.to_pair(x32) if pair else x32.to(torch.bfloat16)
+        xq = ops.from_pair(x).double() if pair else x.double()
+        fl = ops.EPI_BIAS | ops.EPI_RELU
+        y = ops.conv_gemm(x, wp, 64, 3, bias=b, flags=fl, wp_lo=wpl, pair=pair, w_mode=0, algo=2)
+        y_tf = ops.conv_gemm(x, wh, 64, 3, bias=b, flags=fl, wp_lo=wl, pair=pair, w_mode=1, algo=2)
+        torch.cuda.synchronize()
+        got = ops.from_pair(y) if pair else y
+        tag = "N%d %dx%d Cin%d pair%d" % (n, h, w_, cin, pair)
+        ok &= report("packed fwd " + tag, got, ref_conv(xq, wq, b, relu=True), 2e-5 if pair else 1e-2)
+        ok &= report("packed == TF-layout path " + tag, got, (ops.from_pair(y_tf) if pair else y_tf).double(),
+                     1e-6 if pair else 1e-2)
+        if h % 2 == 0 and w_ % 2 == 0:
+            cm = 2 if pair else 1
+            pooled = torch.full((n, h // 2, w_ // 2, cm * 64), float("nan"), dtype=torch.bfloat16, device=dev)
+            y2 = ops.conv_gemm(x, wp, 64, 3, bias=b, flags=fl, wp_lo=wpl, pair=pair, w_mode=0, algo=2, pool_out=pooled)
+            p_ref = ops.maxpool_fwd(y, pair=pair)
+            torch.cuda.synchronize()
+            val = (lambda t: ops.from_pair(t)) if pair else (lambda t: t.float())
+            same = bool(torch.equal(val(y2), val(y))) and bool(torch.equal(val(pooled), val(p_ref)))
+            print("  %-58s %s" % ("fused pool " + tag, "OK" if same else "FAIL"))
+            ok &= same
+    return ok
+
+
+@case
 def dynamic_tiles():
     """Dynamic tile scheduling (cluster launch control, fcn8_debug_set(10, 1)): the grid holds one CTA / CTA pair per
     tile, running CTAs cancel pending ones and take their tiles.  Same references as the static cases -- per-tap, pair,

@@ -2,7 +2,7 @@
 # Round-2 wave 8: CTA-pair halo kernel.
 mkdir -p gpurun_out
 O=gpurun_out
-BRINGUP_TIMEOUT=120 timeout 900 python scripts/bringup.py halo_conv hwio_bf16 hwio_pair fused_pool pair_epilogues_and_wgrad conv_epilogues dynamic_tiles > $O/w8_bringup.log 2>&1; echo "bringup rc=$?"
+BRINGUP_TIMEOUT=120 timeout 900 python scripts/bringup.py halo_pair_packed_forward halo_conv fused_pool > $O/w8_bringup.log 2>&1; echo "bringup rc=$?"
 grep -E "FAIL|^case .* -> |Error|error" $O/w8_bringup.log | head -40
 timeout 1500 python -m pytest tests -m gpu -q -x > $O/w8_pytest.log 2>&1; echo "pytest rc=$?"
 tail -5 $O/w8_pytest.log
