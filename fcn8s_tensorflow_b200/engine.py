@@ -230,11 +230,10 @@ class Engine:
         # runs as a 1x1 conv over the 27-column im2col (padded to kp) built by the feed kernel
         self.packed["conv1_1"] = ops.pack_weights(self.view("conv1_1/filter"), 1, 27, 64, 0, self.dt, cin_pad=self.kp,
                                                   split=self.pair, out=old)
-        if self.pair:
-            # conv1_2 forward on CTA pairs (conv_halo_pair_kernel) needs K-major weights: each CTA of a pair holds 32 of
-            # the 64 output channels, too narrow for the MN-major operand read from the TF layout (36 864 elements)
-            self.packed["conv1_2"] = ops.pack_weights(self.view("conv1_2/filter"), 3, 64, 64, 0, self.dt, split=True,
-                                                      out=self.packed.get("conv1_2"))
+        # conv1_2 forward on CTA pairs (conv_halo_pair_kernel) needs K-major weights: each CTA of a pair holds 32 of the
+        # 64 output channels, too narrow for the MN-major operand read from the TF layout (36 864 elements)
+        self.packed["conv1_2"] = ops.pack_weights(self.view("conv1_2/filter"), 3, 64, 64, 0, self.dt, split=self.pair,
+                                                  out=self.packed.get("conv1_2"))
         for key, base, _, cin, _ in HEADS:
             self.packed[key] = ops.head_pack(self.view(base + "/kernel").view(cin, self.C), self.view(base + "/bias"),
                                              split=self.pair, out=self.packed.get(key))
