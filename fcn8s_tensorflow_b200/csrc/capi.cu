@@ -621,9 +621,9 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
     if (p->w_mode == 0)
       rc = encode_w_map(&maps.b[s], ws[s], p->dtype, p->Cout, ktot, b_rows);
     else if (p->w_mode == 1)
-      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64, use_halo && pl.BN == 64 ? 3 : 1);
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cin, p->Cout, 64, use_halo && (pl.BN == 64 || halo_pair) ? 3 : 1);
     else
-      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, b_rows, use_halo && pl.BN == 64 ? 3 : 1);
+      rc = encode_hwio_map(&maps.b[s], ws[s], taps, p->Cout, p->Cin, b_rows, use_halo && (pl.BN == 64 || halo_pair) ? 3 : 1);
     if (rc) return rc;
   }
   ConvGemmArgs a;

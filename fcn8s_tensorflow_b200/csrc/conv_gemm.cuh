@@ -1456,11 +1456,11 @@ conv_halo_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
 // Roles, barriers and the scheduler as in conv_gemm_kernel<.., PAIR>; epilogue shared.
 template <int BN, bool RB = false>
 struct HaloPairSmem {
-  static constexpr int kTaps = (BN == 64) ? 3 : 1;           // filter taps per weight stage (see HaloSmem)
+  static constexpr int kTaps = 3;                            // filter taps per weight stage: one kh row (see HaloSmem)
   static constexpr int kBRows = BN / 2;                      // weight rows this CTA holds
   static constexpr int kBBytes = kTaps * kBRows * 128;       // one stage / one resident (set, cb, kh) group
   static constexpr int kAStages = 3;
-  static constexpr int kBStages = RB ? 6 : 8;
+  static constexpr int kBStages = RB ? 6 : (BN == 64 ? 8 : 4);   // 96 KB of weight stages in flight
   static constexpr int kBarBytes = 1024;
   static constexpr int kColsumBytes = 1024;
   static constexpr int kStoreBytes = kEpiWarpsC * kStoreWarpBytes;
@@ -1642,14 +1642,23 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
       tc_fence_after();
     }
     int t_next = 0;
+    long long dbg_a = 0, dbg_b = 0, dbg_acc = 0, dbg_kb = 0, tw = 0;
+    const long long dbg_t0 = g.dbg ? clock64() : 0;
     for (int t = t_first, it = 0; t < total_units; t = t_next, ++it) {
       t_next = sched_next<true>(sched, it, t, lane);
+      if (g.dbg) tw = clock64();
       mbar_wait(&acc_empty[acs], acph ^ 1);
+      if (g.dbg) dbg_acc += clock64() - tw;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acs * BN;
       uint32_t first = 0;
       for (int kbk = 0; kbk < g.nseg * g.cblocks; ++kbk) {
+        if (g.dbg) tw = clock64();
         mbar_wait(&a_full[as], aph);
+        if (g.dbg) {
+          dbg_a += clock64() - tw;
+          ++dbg_kb;
+        }
         tc_fence_after();
         const uint32_t sa = sa_base + as * HaloCfg::kABytes;
         const int seg = kbk / g.cblocks;
@@ -1659,7 +1668,9 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
 #pragma unroll
           for (int kw0 = 0; kw0 < 3; kw0 += HS::kTaps) {
             if constexpr (!RB) {
+              if (g.dbg) tw = clock64();
               mbar_wait(&b_full[bs], bph);
+              if (g.dbg) dbg_b += clock64() - tw;
               tc_fence_after();
             }
             const uint32_t sb = sb_base + (RB ? (rb_group0 + kh) : bs) * HS::kBBytes;
@@ -1704,6 +1715,13 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
         acs = 0;
         acph ^= 1;
       }
+    }
+    if (g.dbg && lane == 0 && blockIdx.x < 148) {   // as in conv_halo_kernel
+      g.dbg[8 * blockIdx.x + 0] = clock64() - dbg_t0;
+      g.dbg[8 * blockIdx.x + 1] = dbg_a;
+      g.dbg[8 * blockIdx.x + 2] = dbg_acc;
+      g.dbg[8 * blockIdx.x + 3] = dbg_kb;
+      g.dbg[8 * blockIdx.x + 5] = dbg_b;
     }
   } else if (warp >= 2) {
     conv_epilogue_loop<BN, false, true>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_units, m_pairs, warp,
