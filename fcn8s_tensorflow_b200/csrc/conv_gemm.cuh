@@ -648,13 +648,21 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
 // accumulator is handed back on the leader CTA's barrier.
 // EPI = 1: the loss / predictor epilogue above instead of the generic one (BN = 256 only); `colsum_s` then holds
 // [0] the CTA's loss sum, [32..64) its class sums of dz, [64..64 + C*C) its confusion-matrix histogram.
-template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false>
+// ALT (narrow tiles, BN <= 128): the two warps of a lane quarter take ALTERNATE tiles (all BN columns each) instead
+// of half of every tile's columns.  A tile's epilogue is one dependent chain per warp (tcgen05.ld -> math -> staged
+// stores, 2000+ cycles for 32 columns) that cannot overlap with itself; with short main loops (64-column tiles: 36
+// MMAs) that latency, not the issue rate, bounded the kernel (accumulator waits of 40-57 % in the bf16 mode).  Two
+// groups working on consecutive tiles hide it; accumulator stage = tile parity = group.
+template <int BN, bool TF32, bool PAIR = false, int EPI = 0, bool PROMO = false, bool ALT = false>
 __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32_t tmem_base, uint64_t* acc_full,
                                                    uint64_t* acc_empty, float* colsum_s, uint8_t* store_s,
                                                    int total_tiles, int m_tiles, int warp, int lane,
                                                    uint32_t rank = 0, const TileSched* sched = nullptr) {
+    static_assert(!ALT || (!PROMO && EPI == 0 && BN <= 128), "alternating epilogue groups: narrow generic tiles");
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns this warp handles
+    const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns (ALT: which tiles) this warp handles
+    constexpr int kColsPerWarp = ALT ? BN : BN / 2;
+    const int col_begin = ALT ? 0 : chalf * (BN / 2);
     uint8_t* stage = store_s + (warp - (PROMO ? 4 : 2)) * kStoreWarpBytes;   // this warp's store staging tile
     const int row = quarter * 32 + lane;
     int as = 0;
@@ -677,6 +685,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
     int t_next = 0;
     for (int t = PAIR ? blockIdx.x >> 1 : blockIdx.x, it = 0; t < total_tiles; t = t_next, ++it) {
       t_next = sched ? sched_next<PAIR>(*sched, it, t, lane) : t + t_step;
+      if constexpr (ALT) {
+        if ((it & 1) != chalf) continue;   // the other group's tile
+        as = chalf;
+        aphase = (static_cast<uint32_t>(it) >> 1) & 1u;
+      }
       const int nb = t % g.tiles_n;
       const int mt = PAIR ? 2 * ((t / g.tiles_n) % m_tiles) + static_cast<int>(rank) : (t / g.tiles_n) % m_tiles;
       const int sp = t / (g.tiles_n * m_tiles);
@@ -748,11 +761,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+      for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        if (c + 32 >= (chalf + 1) * (BN / 2)) {
+        if (c + 32 >= col_begin + kColsPerWarp) {
           // the warp's last chunk is in registers: hand the accumulator stage back BEFORE the math and the stores
           tc_fence_before();
           __syncwarp();
@@ -810,9 +823,11 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
                                  pool_idx, pool_writer);
         }
       }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
+      if constexpr (!ALT) {
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
       }
     }
     if (g.dbg && lane == 0 && warp == (PROMO ? 4 : 2) && blockIdx.x < 148) {   // first epilogue warp: [6] = idle cycles, [7] = loop cycles
@@ -847,6 +862,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   static_assert(!PROMO || (EPI == 0 && !TF32), "promoted accumulation: bf16 operands, generic epilogue");
   constexpr int kThreads = PROMO ? kPromoThreads : kGemmThreads;
   constexpr int kEpiWarp0 = PROMO ? 4 : 2;
+  // narrow single-CTA tiles (score heads, decoder GEMMs, small images): alternating epilogue groups (conv_epilogue_loop)
+  constexpr bool kAlt = BN <= 128 && !TF32 && !PAIR && !PROMO && EPI == 0;
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
   extern __shared__ uint8_t smem_raw[];
@@ -897,7 +914,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);
+      mbar_init(&acc_empty[s], kAlt ? kEpiWarps / 2 : (PAIR ? 2 * kEpiWarps : kEpiWarps));
     }
     for (int s = 0; s < kSchedStages; ++s) {
       mbar_init(&sched.full[s], 1);
@@ -1124,8 +1141,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   } else {
     // ============================== epilogue ==============================
     if constexpr (PROMO) setmaxnreg_inc<kPromoEpiRegs>();
-    conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_tiles,
-                                                   m_tiles, warp, lane, rank, &sched);
+    conv_epilogue_loop<BN, TF32, PAIR, EPI, PROMO, kAlt>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s,
+                                                         total_tiles, m_tiles, warp, lane, rank, &sched);
   }
 
   tc_fence_before();
@@ -1525,7 +1542,7 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 2 * kEpiWarps);
+      mbar_init(&acc_empty[s], kEpiWarps);   // alternating epilogue groups: 4 warps per tile in each CTA
     }
     for (int s = 0; s < kSchedStages; ++s) {
       mbar_init(&sched.full[s], 1);
@@ -1724,8 +1741,8 @@ conv_halo_pair_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmAr
       g.dbg[8 * blockIdx.x + 5] = dbg_b;
     }
   } else if (warp >= 2) {
-    conv_epilogue_loop<BN, false, true>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_units, m_pairs, warp,
-                                        lane, rank, &sched);
+    conv_epilogue_loop<BN, false, true, 0, false, true>(g, tmem_base, acc_full, acc_empty, colsum_s, store_s, total_units,
+                                                        m_pairs, warp, lane, rank, &sched);
   }
 
   tc_fence_before();
