@@ -332,8 +332,13 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
                                                bool pool_writer = false) {
   using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
   float f[32];
+  if (acc_scale != 1.f) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * acc_scale;
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * acc_scale;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  }
   if (!valid) {
     // rows outside the tensor come along as zeros: the column sums, the pooling and the staged stores are
     // warp-collective
@@ -471,7 +476,24 @@ __device__ __forceinline__ void epilogue_row32(const ConvGemmArgs& g, uint32_t (
       warp_store_frag64(stage, hi, o, valid, lane);
       if (g.out_lo) warp_store_frag64(stage, lo, reinterpret_cast<OutT*>(g.out_lo) + idx, valid, lane);
     }
-    if (g.flags & EPI_POOL) {
+    if ((g.flags & EPI_POOL) && !pair_fmt) {
+      // bf16 storage: the 2x2 max of the stored values on the packed pairs (16 registers instead of 32 floats)
+      uint32_t ph[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&hi[i]);
+        uint32_t o = __shfl_xor_sync(0xffffffffu, hi[i], 1);
+        a = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&o));
+        o = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<const uint32_t*>(&a), 8);
+        a = __hmax2(a, *reinterpret_cast<const __nv_bfloat162*>(&o));
+        ph[i] = *reinterpret_cast<const uint32_t*>(&a);
+      }
+      if (pool_writer) {
+        uint4* p4 = reinterpret_cast<uint4*>(reinterpret_cast<OutT*>(g.pool_out) + pool_idx);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p4[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+      }
+    } else if (g.flags & EPI_POOL) {
       // 2x2 max over the STORED values (hi, or hi + lo for pairs: exactly what a stand-alone pool of the stored tensor
       // would see); the window's other three pixels are lanes ^1 (x) and ^8 (y) of this warp (tile row = y*8 + x)
       float m[32];
