@@ -580,7 +580,10 @@ int32_t fcn8_conv_gemm(const Fcn8ConvParams* p, void* workspace, size_t workspac
   const bool pair_halo_on = !g_debug[11] && !g_debug[5];
   const bool halo_ok = p->dtype == FCN8_BF16 && p->ksize == 3 && p->Cin % 64 == 0 &&
                        (p->w_mode != 0 || (pair_halo_on && p->Cout == 64 && !(p->flags & FCN8_EPI_COLSUM)));
-  const bool use_halo = halo_ok && p->Cout <= 256 && (p->algo >= 2 || (p->algo == 0 && p->Cin <= 128));
+  // (heuristic: up to 128 input channels; the pair kernel's 128-column dgrad tiles also pay off at 256: conv3_1's dgrad)
+  const bool use_halo = halo_ok && p->Cout <= 256 &&
+                        (p->algo >= 2 || (p->algo == 0 && (p->Cin <= 128 || (pair_halo_on && p->w_mode == 2 &&
+                                                                              p->Cout == 128 && p->Cin <= 256))));
   if (p->algo >= 2 && !halo_ok) return fail(FCN8_ERR_UNSUPPORTED, "conv: halo kernel needs bf16, 3x3, w_mode 1/2");
   if (use_halo) {
     pl.lbw = 3;

@@ -680,7 +680,7 @@ __device__ __forceinline__ void conv_epilogue_loop(const ConvGemmArgs& g, uint32
                                                    uint64_t* acc_empty, float* colsum_s, uint8_t* store_s,
                                                    int total_tiles, int m_tiles, int warp, int lane,
                                                    uint32_t rank = 0, const TileSched* sched = nullptr) {
-    static_assert(!ALT || (!PROMO && EPI == 0 && BN <= 128), "alternating epilogue groups: narrow generic tiles");
+    static_assert(!ALT || (!PROMO && (EPI == 1 || BN <= 128)), "alternating epilogue groups: narrow tiles, loss epilogue");
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int chalf = (warp - (PROMO ? 4 : 2)) >> 2;  // which half of the tile's columns (ALT: which tiles) this warp handles
     constexpr int kColsPerWarp = ALT ? BN : BN / 2;
@@ -885,7 +885,8 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
   constexpr int kThreads = PROMO ? kPromoThreads : kGemmThreads;
   constexpr int kEpiWarp0 = PROMO ? 4 : 2;
   // narrow single-CTA tiles (score heads, decoder GEMMs, small images): alternating epilogue groups (conv_epilogue_loop)
-  constexpr bool kAlt = BN <= 128 && !TF32 && !PAIR && !PROMO && EPI == 0;
+  // ... and the loss / predictor epilogue of upscore8 (~300 dependent instructions per pixel, 12-k-block main loops)
+  constexpr bool kAlt = (BN <= 128 && !TF32 && !PAIR && !PROMO && EPI == 0) || EPI == 1;
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int CH = TF32 ? 32 : 64;  // elements per 128-byte operand row
   extern __shared__ uint8_t smem_raw[];
@@ -936,7 +937,7 @@ conv_gemm_kernel(const __grid_constant__ TensorMaps3 maps, const ConvGemmArgs g)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kAlt ? kEpiWarps / 2 : (PAIR ? 2 * kEpiWarps : kEpiWarps));
+      mbar_init(&acc_empty[s], (PAIR ? 2 : 1) * (kAlt ? kEpiWarps / 2 : kEpiWarps));
     }
     for (int s = 0; s < kSchedStages; ++s) {
       mbar_init(&sched.full[s], 1);
