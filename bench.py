@@ -427,7 +427,7 @@ def time_predict(cfg, precision, weights, args, rank, local_rank, world, dev):
 
 def ncu_traffic(precision):
     """DRAM bytes per step of the dominant kernel family from the committed ncu metrics pass (profiles/): sum of
-    dram__bytes_read.sum + dram__bytes_write.sum over the step's conv_gemm_kernel / conv_halo_kernel launches of the
+    dram__bytes_read.sum + dram__bytes_write.sum over the step's conv_gemm_kernel / conv_halo(_pair)_kernel launches of the
     encoder (bf16 operand instantiations).  None when the profile is missing or was taken in another mode."""
     for name in ("r02_step_kernels.json", "r01_step_kernels_final.json"):
         path = os.path.join(ROOT, "profiles", name)
@@ -438,7 +438,8 @@ def ncu_traffic(precision):
             continue
         # conv_gemm_kernel<BN, TF32 = 0, ...> are the bf16-operand instantiations of the encoder / decoder GEMMs
         tot = sum(v["dram_bytes"] for k, v in d.items()
-                  if re.match(r"conv_gemm_kernel<\d+, 0", k) or k.startswith("conv_halo_kernel"))
+                  if re.match(r"conv_gemm_kernel<\d+, 0", k) or k.startswith("conv_halo_kernel") or
+                  k.startswith("conv_halo_pair_kernel"))
         return tot, "profiles/" + name
     return None, None
 
@@ -463,7 +464,7 @@ def train_line(cfg, precision, r, args, world, peaks):
     line = {
         "value": value, "ms_per_step": step_ms, "dtype": dtype, "gpu_launches": int(r["launches"]),
         "roofline": {
-            "bound": "tensor", "kernel": "conv_gemm_kernel + conv_halo_kernel (tcgen05 implicit-GEMM fprop + dgrad of the "
+            "bound": "tensor", "kernel": "conv_gemm_kernel + conv_halo(_pair)_kernel (tcgen05 implicit-GEMM fprop + dgrad of the "
                                          "encoder, all tile widths)",
             "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
             "traffic": traffic, "traffic_unit": "DRAM bytes per step over the same launches "
