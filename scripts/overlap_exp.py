@@ -5,6 +5,9 @@ against the baseline variant (everything but the atomically accumulated bias gra
 loss after five steps, and the CUDA-event time of graph-replayed steps.
 
     python scripts/overlap_exp.py [steps]
+
+Needs profiles/r02_overlap_experiment.patch applied (the experiment was measured slower and is not in the product:
+profiles/r02_overlap_experiment.md).
 """
 import json
 import os
