@@ -20,7 +20,7 @@ EXPORTS = [
     "fcn8_bias_grad", "fcn8_head_pack", "fcn8_deconv_cp", "fcn8_deconv_pack", "fcn8_deconv_fwd", "fcn8_deconv_loss",
     "fcn8_deconv_dx", "fcn8_deconv_dw_workspace_bytes", "fcn8_deconv_dw",
     "fcn8_confusion_matrix", "fcn8_adam", "fcn8_l2_reg", "fcn8_shadow_weights",
-    "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_cast_bf16",
+    "fcn8_set_step_scalars", "fcn8_set_sm_limit", "fcn8_cast_bf16", "fcn8_pack_labels", "fcn8_expand_labels",
     "fcn8_conv1_fwd", "fcn8_conv1_wgrad_workspace_bytes", "fcn8_conv1_wgrad",
 ]
 
@@ -88,7 +88,7 @@ class DeconvParams(C.Structure):
                 ("stride", C.c_int32), ("nseg", C.c_int32),
                 ("labels", C.c_void_p), ("loss_sum", C.c_void_p), ("dbias", C.c_void_p), ("dz_hi_out", C.c_void_p),
                 ("dz_lo_out", C.c_void_p), ("logits", C.c_void_p), ("softmax", C.c_void_p), ("argmax", C.c_void_p),
-                ("conf", C.c_void_p), ("grad_scale", C.c_float)]
+                ("conf", C.c_void_p), ("grad_scale", C.c_float), ("argmax_u8", C.c_void_p)]
 
 
 _lib = None
@@ -138,6 +138,8 @@ def load():
     lib.fcn8_adam.argtypes = [vp, vp, vp, vp, sz, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp,
                               vp]
     lib.fcn8_cast_bf16.argtypes = [vp, vp, sz, vp]
+    lib.fcn8_pack_labels.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_int32]
+    lib.fcn8_expand_labels.argtypes = [vp, vp, C.c_int64, C.c_int32, vp]
     lib.fcn8_set_step_scalars.argtypes = [vp, C.c_float, C.c_uint32, vp]
     lib.fcn8_shadow_weights.argtypes = [vp, vp, vp, sz, vp]
     lib.fcn8_l2_reg.argtypes = [vp, vp, vp, sz, C.c_float, vp]

@@ -7,6 +7,13 @@
 #include <stdio.h>
 #include <string.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "../../include/fcn8s_b200.h"
 #include "conv1.h"
 #include "conv_gemm.cuh"
@@ -527,6 +534,96 @@ int32_t fcn8_debug_buffer(void* buf, int32_t slots) {
   g_dbg_next = 0;
   return 0;
 }
+// Label feed (helpers/ground_truth_conversion_utils.py:84-88, batch_generator_KITTI.py:82-84 -> `labels` placeholder,
+// fcn8s_tensorflow.py:110,559): the generators yield bool one-hot [n,H,W,C]; host code packs a batch to one class id
+// per pixel (C bytes -> 1 byte over PCIe), fcn8_expand_labels restores the one-hot tensor on the device.
+// Returns 0 when every pixel's C bytes are exactly one-hot (one byte == 1, the others 0) and `ids` is filled,
+// 1 when some pixel is not (the caller then ships the one-hot batch as it is), < 0 on bad arguments.
+//
+// The batch is scanned as ONE flat byte string: it is one-hot iff no byte exceeds 1 and the k-th set byte (in address
+// order) lies inside row k, for every k -- then its offset in the row is the class id.  Set bytes are found 64 bytes at
+// a time (SSE2 compare + movemask on x86-64; a multiply-gather of the bytes' low bits elsewhere), so the cost is one
+// pass of loads plus ~10 instructions per pixel: about what the memcpy into pinned memory that it replaces costs.
+static inline uint64_t set_byte_mask64(const uint8_t* p, uint64_t* any) {
+#if defined(__SSE2__)
+  const __m128i one = _mm_set1_epi8(1);
+  const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+  const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + 16));
+  const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + 32));
+  const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p + 48));
+  const __m128i o = _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d));
+  *any |= static_cast<uint64_t>(_mm_cvtsi128_si64(o)) | static_cast<uint64_t>(_mm_cvtsi128_si64(_mm_srli_si128(o, 8)));
+  return static_cast<uint64_t>(static_cast<uint32_t>(_mm_movemask_epi8(_mm_cmpeq_epi8(a, one)))) |
+         (static_cast<uint64_t>(static_cast<uint32_t>(_mm_movemask_epi8(_mm_cmpeq_epi8(b, one)))) << 16) |
+         (static_cast<uint64_t>(static_cast<uint32_t>(_mm_movemask_epi8(_mm_cmpeq_epi8(c, one)))) << 32) |
+         (static_cast<uint64_t>(static_cast<uint32_t>(_mm_movemask_epi8(_mm_cmpeq_epi8(d, one)))) << 48);
+#else
+  uint64_t m = 0;
+  for (int w = 0; w < 8; ++w) {
+    uint64_t v;
+    memcpy(&v, p + 8 * w, 8);
+    *any |= v;
+    // bit 0 of each of the 8 bytes -> 8 adjacent bits (bytes are 0 / 1 in a valid batch; others are caught by `any`)
+    m |= (((v & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56) << (8 * w);
+  }
+  return m;
+#endif
+}
+// Rows [p0, p1): returns false as soon as the range cannot be one-hot.
+static bool pack_label_range(const uint8_t* onehot, int64_t p0, int64_t p1, int C, uint8_t* ids) {
+  const uint64_t uc = static_cast<uint64_t>(C);
+  const uint64_t b1 = static_cast<uint64_t>(p1) * uc;
+  uint64_t b = static_cast<uint64_t>(p0) * uc;     // flat byte position
+  int64_t k = p0;                                   // next row to receive its set byte
+  uint64_t row0 = b;                                // first byte of row k
+  uint64_t any = 0;
+  for (; b + 64 <= b1; b += 64) {
+    uint64_t m = set_byte_mask64(onehot + b, &any);
+    while (m) {
+      const uint64_t off = b + static_cast<uint64_t>(__builtin_ctzll(m)) - row0;   // wraps when the byte is before row k
+      if (off >= uc || k >= p1) return false;
+      ids[k++] = static_cast<uint8_t>(off);
+      row0 += uc;
+      m &= m - 1;
+    }
+  }
+  for (; b < b1; ++b) {
+    const uint8_t v = onehot[b];
+    any |= v;
+    if (v) {
+      const uint64_t off = b - row0;
+      if (off >= uc || k >= p1) return false;
+      ids[k++] = static_cast<uint8_t>(off);
+      row0 += uc;
+    }
+  }
+  return k == p1 && !(any & ~0x0101010101010101ull);
+}
+int32_t fcn8_pack_labels(const uint8_t* onehot, int64_t pixels, int32_t C, uint8_t* ids, int32_t threads) {
+  if (!onehot || !ids) return fail(FCN8_ERR_BAD_SHAPE, "pack_labels: null pointer");
+  if (pixels < 0 || C < 1 || C > 255) return fail(FCN8_ERR_BAD_SHAPE, "pack_labels: pixels=%lld, C=%d", (long long)pixels, C);
+  if (threads < 1) threads = 1;
+  if (threads > 16) threads = 16;
+  if (pixels < (1 << 16)) threads = 1;
+  if (threads == 1) return pack_label_range(onehot, 0, pixels, C, ids) ? 0 : 1;
+  std::atomic<int> bad(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      if (!pack_label_range(onehot, pixels * t / threads, pixels * (t + 1) / threads, C, ids)) bad.store(1);
+    });
+  for (auto& th : pool) th.join();
+  return bad.load() ? 1 : 0;
+}
+int32_t fcn8_expand_labels(const uint8_t* ids, uint8_t* onehot, int64_t pixels, int32_t C, void* stream) {
+  if (!ids || !onehot) return fail(FCN8_ERR_BAD_SHAPE, "expand_labels: null pointer");
+  if (pixels < 0 || C < 1 || C > 255) return fail(FCN8_ERR_BAD_SHAPE, "expand_labels: pixels=%lld, C=%d", (long long)pixels, C);
+  if (reinterpret_cast<uintptr_t>(onehot) & 3u) return fail(FCN8_ERR_BAD_ALIGN, "expand_labels: onehot not 4-byte aligned");
+  if (!pixels) return 0;
+  cudaError_t e = launch_expand_labels(ids, onehot, pixels, C, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "expand_labels launch");
+}
+
 int32_t fcn8_debug_set(int32_t key, int32_t value) {
   if (key < 0 || key >= 16) return fail(FCN8_ERR_BAD_SHAPE, "debug key out of range");
   g_debug[key] = value;
@@ -1244,7 +1341,7 @@ int32_t fcn8_deconv_loss(const Fcn8DeconvParams* p, void* stream) {
   if (!p->x || !p->w || !p->bias_big) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: null pointer");
   if ((p->nseg == 3 && !p->x_lo) || (p->nseg >= 2 && !p->w_lo)) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: lo operands");
   if ((p->loss_sum || p->dz_hi_out || p->conf) && !p->labels) return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: needs labels");
-  if (!p->loss_sum && !p->dz_hi_out && !p->conf && !p->logits && !p->softmax && !p->argmax)
+  if (!p->loss_sum && !p->dz_hi_out && !p->conf && !p->logits && !p->softmax && !p->argmax && !p->argmax_u8)
     return fail(FCN8_ERR_BAD_SHAPE, "deconv_loss: no output requested");
   if ((p->dz_hi_out && !aligned16(p->dz_hi_out)) || (p->dz_lo_out && !aligned16(p->dz_lo_out)))
     return fail(FCN8_ERR_BAD_ALIGN, "deconv_loss: dz planes must be 16-byte aligned");
@@ -1263,6 +1360,7 @@ int32_t fcn8_deconv_loss(const Fcn8DeconvParams* p, void* stream) {
   a.logits = p->logits;
   a.softmax = p->softmax;
   a.argmax = reinterpret_cast<long long*>(p->argmax);
+  a.argmax_u8 = p->argmax_u8;
   a.conf = reinterpret_cast<unsigned long long*>(p->conf);
   a.num_classes = p->C;
   a.gscale = p->grad_scale;

@@ -164,6 +164,7 @@ struct ConvGemmArgs {
   float* logits;                // dense [N, out_H, out_W, C]
   float* softmax;               // dense [N, out_H, out_W, C]
   long long* argmax;            // dense [N, out_H, out_W]
+  unsigned char* argmax_u8;     // the same class map as one byte per pixel
   unsigned long long* conf;     // [C, C] confusion matrix, conf[label * C + prediction] += 1
   int num_classes;
   float gscale;                 // dz = (softmax - y) * gscale
@@ -577,6 +578,7 @@ __device__ __forceinline__ void loss_epilogue_pixel(const ConvGemmArgs& g, const
       am = c;
     }
   if (g.argmax) g.argmax[p] = am;
+  if (g.argmax_u8) g.argmax_u8[p] = static_cast<unsigned char>(am);
   if (!(g.labels || g.softmax)) return;
   float e[32];
   float se = 0.f;

@@ -283,6 +283,42 @@ cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* d
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ label feed
+// onehot[p*C + c] = (ids[p] == c): the one-hot label tensor the loss epilogue reads, rebuilt on the device from the
+// class ids that crossed PCIe (fcn8_pack_labels).  One thread per 4 output bytes.
+__global__ void expand_labels_kernel(const uint8_t* __restrict__ ids, uint8_t* __restrict__ onehot, size_t nbytes, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t nwords = (nbytes + 3) / 4;
+  for (size_t w = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; w < nwords;
+       w += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b0 = 4 * w;
+    size_t p = b0 / C;
+    int c = static_cast<int>(b0 - p * C);
+    int id = (b0 < nbytes) ? __ldg(ids + p) : -1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (b0 + k < nbytes && c == id) out |= 1u << (8 * k);
+      if (++c == C) {
+        c = 0;
+        ++p;
+        id = (b0 + k + 1 < nbytes) ? __ldg(ids + p) : -1;
+      }
+    }
+    if (b0 + 4 <= nbytes) {
+      reinterpret_cast<uint32_t*>(onehot)[w] = out;
+    } else {
+      for (int k = 0; b0 + k < nbytes; ++k) onehot[b0 + k] = static_cast<uint8_t>((out >> (8 * k)) & 0xffu);
+    }
+  }
+}
+cudaError_t launch_expand_labels(const uint8_t* ids, uint8_t* onehot, long long pixels, int C, cudaStream_t st) {
+  const size_t nbytes = static_cast<size_t>(pixels) * C;
+  { (void)launch_k(expand_labels_kernel, dim3(grid_for((nbytes + 3) / 4, 256)), dim3(256), 0, st, ids, onehot, nbytes, C); }
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ bias gradient
 // Stage 1: block (bx, by) sums rows [bx*rpb, (bx+1)*rpb) of column-vector group by into ws[bx][C].
 template <int FMT>

@@ -11,7 +11,7 @@ struct ConvGemmArgs;
 // Every kernel launch of the library goes through this counter (fcn8_launch_count() in the C ABI): it is what
 // bench.py reports as gpu_launches.
 extern unsigned long long g_launch_count;
-inline void count_launch() { ++g_launch_count; }
+inline void count_launch() { __atomic_fetch_add(&g_launch_count, 1ull, __ATOMIC_RELAXED); }   // the feed thread launches too
 
 // Programmatic dependent launch (OFF by default; fcn8_debug_set(6, 1) / FCN8_DEBUG=6=1 switches it on).  Every kernel
 // of the library starts with pdl_launch_dependents() (the NEXT kernel of the stream may be scheduled as soon as all
@@ -47,6 +47,7 @@ cudaError_t launch_preprocess(const uint8_t* img, void* out, int N, int H, int W
 cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
 cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* db, int N, int H, int W, int C,
                                int dtype, cudaStream_t st);
+cudaError_t launch_expand_labels(const uint8_t* ids, uint8_t* onehot, long long pixels, int C, cudaStream_t st);
 int bias_grad_blocks(long long P, int C);
 cudaError_t launch_bias_grad(const void* dy, float* db, long long P, int C, int dtype, float* ws, cudaStream_t st);
 cudaError_t launch_colsum(const float* ws, float* out, int nb, int C, float scale, int accumulate, cudaStream_t st);

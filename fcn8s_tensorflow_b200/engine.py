@@ -620,12 +620,16 @@ class Engine:
 
     # ------------------------------------------------------------------ predictor / evaluation
     @_on_device
-    def predict(self, images, argmax=True):
+    def predict(self, images, argmax=True, compact=False):
         """fcn8s_tensorflow.py:743-770: argmax int64 [N,H,W] or softmax fp32 [N,H,W,C], keep_prob = 1 -- computed in
-        the epilogue of the upscore8 kernel; the logits are never written."""
+        the epilogue of the upscore8 kernel; the logits are never written.  compact=True: the class map as uint8
+        [N,H,W] (one byte per pixel for the trip to the host; the caller widens it to tf.argmax's int64)."""
         N, H, W, _ = images.shape
         A, f3 = self._features(images, 1.0, 0, False)
-        if argmax:
+        if argmax and compact:
+            out = torch.empty((N, H, W), dtype=torch.uint8, device=self.device)
+            ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, argmax_u8=out)
+        elif argmax:
             out = torch.empty((N, H, W), dtype=torch.int64, device=self.device)
             ops.deconv_loss(f3, self.packed["up8"], self.C, nseg=self.nseg, argmax=out)
         else:

@@ -412,7 +412,7 @@ def _deconv_params(x=None, w=None, w_lo=None, bias_big=None, out=None, skip=None
                              N, h, wd, Cc, stride, nseg, capi.ptr(loss.get("labels")), capi.ptr(loss.get("loss_sum")),
                              capi.ptr(loss.get("dbias")), capi.ptr(dzo[0]), capi.ptr(dzo[1]),
                              capi.ptr(loss.get("logits")), capi.ptr(loss.get("softmax")), capi.ptr(loss.get("argmax")),
-                             capi.ptr(loss.get("conf")), loss.get("grad_scale", 1.0))
+                             capi.ptr(loss.get("conf")), loss.get("grad_scale", 1.0), capi.ptr(loss.get("argmax_u8")))
 
 
 def _deconv_flops(N, h, w, stride, Cc):
@@ -433,23 +433,24 @@ def deconv_fwd(x, packed, num_classes, stride, out, skip=None, nseg=3):
 
 
 def deconv_loss(x, packed, num_classes, nseg=3, labels=None, loss_sum=None, dz_out=None, dbias=None, grad_scale=1.0,
-                logits=None, softmax=None, argmax=None, conf=None):
+                logits=None, softmax=None, argmax=None, conf=None, argmax_u8=None):
     """upscore8 (stride 8) with the loss / predictor fused into its epilogue; see fcn8_deconv_loss."""
     N, h, w, _ = x[0].shape
-    _chk_cuda(labels, loss_sum, dbias, logits, softmax, argmax, conf)
+    _chk_cuda(labels, loss_sum, dbias, logits, softmax, argmax, conf, argmax_u8)
     if dz_out is not None:
         _chk_cuda(dz_out[0], dz_out[1])
     p = _deconv_params(x=x if nseg == 3 else (x[0], None), w=packed["w_fwd"], w_lo=packed["w_fwd_lo"] if nseg > 1 else None,
                        bias_big=packed["bias_big"], N=N, h=h, wd=w, Cc=num_classes, stride=8, nseg=nseg, labels=labels,
                        loss_sum=loss_sum, dz_out=dz_out, dbias=dbias, grad_scale=grad_scale, logits=logits,
-                       softmax=softmax, argmax=argmax, conf=conf)
+                       softmax=softmax, argmax=argmax, conf=conf, argmax_u8=argmax_u8)
     e0 = TIMER.start() if TIMER is not None else None
     capi.check(capi.load().fcn8_deconv_loss(C.byref(p), _stream()))
     if e0 is not None:
         px = N * 64 * h * w   # HBM-side work: algorithmic bytes of the requested outputs + the input planes
         nbytes = N * h * w * num_classes * 4 + (px * num_classes if labels is not None else 0) + \
             (px * num_classes * 4 if dz_out is not None else 0) + (px * num_classes * 4 if logits is not None else 0) + \
-            (px * num_classes * 4 if softmax is not None else 0) + (px * 8 if argmax is not None else 0)
+            (px * num_classes * 4 if softmax is not None else 0) + (px * 8 if argmax is not None else 0) + \
+            (px if argmax_u8 is not None else 0)
         TIMER.stop("upscore8_fused", float(nbytes), e0)
 
 
@@ -505,6 +506,31 @@ def cast_bf16(x, out):
     _chk_cuda(x, out)
     capi.check(capi.load().fcn8_cast_bf16(capi.ptr(x), capi.ptr(out), x.numel(), _stream()))
     return out
+
+
+def pack_labels(onehot, ids, threads=4):
+    """HOST code: one-hot uint8 / bool numpy batch [..., C] -> class ids (uint8 numpy / pinned buffer `ids`, one per
+    pixel).  Returns True when every pixel was exactly one-hot (ids is valid), False otherwise."""
+    import numpy as np
+    a = onehot.view(np.uint8) if onehot.dtype == np.bool_ else onehot
+    if a.dtype != np.uint8 or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("pack_labels: contiguous uint8 / bool labels expected")
+    Cn = a.shape[-1]
+    pixels = a.size // Cn
+    if ids.size < pixels or ids.dtype != np.uint8 or not ids.flags["C_CONTIGUOUS"]:
+        raise ValueError("pack_labels: ids must be a contiguous uint8 buffer of one byte per pixel")
+    rc = capi.load().fcn8_pack_labels(a.ctypes.data, pixels, Cn, ids.ctypes.data, threads)
+    if rc < 0:
+        capi.check(rc)
+    return rc == 0
+
+
+def expand_labels(ids, onehot):
+    """onehot (uint8 CUDA tensor [..., C]) = one-hot of the class ids (uint8 CUDA tensor, one per pixel)."""
+    _chk_cuda(ids, onehot)
+    Cn = onehot.shape[-1]
+    capi.check(capi.load().fcn8_expand_labels(capi.ptr(ids), capi.ptr(onehot), onehot.numel() // Cn, Cn, _stream()))
+    return onehot
 
 
 def set_step_scalars(scalars, lr_t, seed):

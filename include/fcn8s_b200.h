@@ -273,7 +273,8 @@ int32_t fcn8_head_pack(const float* K, const float* bias, int32_t Cin, int32_t C
  *                     sum over pixels of softmax-CE with `labels` (one-hot uint8 [N,8h,8w,C]); the loss gradient
  *                     dz = (softmax - labels) * grad_scale as bf16 planes in the padded blocked layout
  *                     [N, 8(h+1), 8(w+1), 32] (interior only: zero the planes once) and dbias[C] += its class sums;
- *                     logits / softmax fp32 [N,8h,8w,C]; argmax int64 [N,8h,8w]; conf[label*C + prediction] += 1
+ *                     logits / softmax fp32 [N,8h,8w,C]; argmax int64 (and / or uint8) [N,8h,8w];
+ *                     conf[label*C + prediction] += 1
  *   fcn8_deconv_dx    input gradient from dz planes in the padded blocked layout [N, s(h+1), s(w+1), CP] (zero border,
  *                     zero beyond C) into out planes [N,h,w,64] (+ colsum[c] += column sums: the bias gradient of the
  *                     layer below)
@@ -310,6 +311,8 @@ typedef struct {
   int64_t* argmax;
   uint64_t* conf;
   float grad_scale;
+  uint8_t* argmax_u8;  /* the class map of `argmax` as one byte per pixel [N,8h,8w]: what FCN8s.predict() brings back over
+                          PCIe (1/8 of the bytes of the int64 map tf.argmax returns, widened on the host) */
 } Fcn8DeconvParams;
 int32_t fcn8_deconv_cp(int32_t stride);
 int32_t fcn8_deconv_pack(const float* T, const float* bias, int32_t C, int32_t stride, void* w_fwd, void* w_fwd_lo,
@@ -320,6 +323,17 @@ int32_t fcn8_deconv_dx(const Fcn8DeconvParams* p, void* stream);
 size_t fcn8_deconv_dw_workspace_bytes(const Fcn8DeconvParams* p);
 int32_t fcn8_deconv_dw(const Fcn8DeconvParams* p, void* workspace, size_t workspace_bytes, void* stream);
 
+
+/* ---- label feed: the `labels` placeholder (fcn8s_tensorflow.py:110, fed at :559,687) receives the generators' bool
+ * one-hot batches [n,H,W,C] (helpers/ground_truth_conversion_utils.py:84-88, batch_generator_KITTI.py:82-84), which
+ * TensorFlow widens to int32 on the host (4C bytes per pixel over PCIe).  Here the feed thread packs a batch to one
+ * class id per pixel on the host and the device restores the one-hot tensor the loss kernel reads (1 byte per pixel).
+ * fcn8_pack_labels (HOST code, `threads` worker threads, no CUDA call): returns 0 when every pixel's C bytes are
+ * exactly one-hot (a single byte equal to 1) and ids[pixels] is filled; 1 when some pixel is not -- the caller then
+ * ships the one-hot batch unchanged, so soft / multi-hot / all-zero label rows keep the reference's semantics;
+ * < 0 on bad arguments.  fcn8_expand_labels: onehot[p*C + c] = (ids[p] == c), device pointers. */
+int32_t fcn8_pack_labels(const uint8_t* onehot, int64_t pixels, int32_t C, uint8_t* ids, int32_t threads);
+int32_t fcn8_expand_labels(const uint8_t* ids, uint8_t* onehot, int64_t pixels, int32_t C, void* stream);
 
 /* ---- streaming metrics: fcn8s_tensorflow.py:280-301 (labels_argmax, tf.metrics.mean_iou / accuracy); the device
  * analogue of cityscapesscripts/evaluation/addToConfusionMatrix_impl.c:3-16: conf[gt*C + pred] += 1 (uint64). */

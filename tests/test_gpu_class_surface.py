@@ -182,3 +182,51 @@ def test_training_and_evaluation_summaries_are_the_references(cuda_device, weigh
     ev_.Reload()
     assert set(ev_.Tags()['scalars']) == {'mean_loss', 'mean_iou', 'accuracy'}
     quiet(m.close)
+
+
+def test_feed_ships_class_ids_and_restores_the_one_hot_labels_on_the_device(cuda_device):
+    """Labels with >= 8 classes cross PCIe as one id per pixel (fcn8_pack_labels on the host, fcn8_expand_labels on the
+    device): what arrives must be the generator's one-hot batch bit for bit (helpers/ground_truth_conversion_utils.py:
+    84-88 -> fcn8s_tensorflow.py:559); a batch that is not exactly one-hot travels unchanged."""
+    from fcn8s_tensorflow_b200 import ops
+    from fcn8s_tensorflow_b200.feed import Feeder
+    from fcn8s_tensorflow_b200.fcn8s import check_images, check_labels
+
+    class Stub:
+        class engine:
+            device = torch.device(cuda_device)
+        _check_images = staticmethod(check_images)
+
+        def __init__(self, Cn):
+            self.Cn = Cn
+
+        def _check_labels(self, labels):
+            return check_labels(labels, self.Cn)
+
+    rng = np.random.default_rng(11)
+    for Cn, n, h, w in ((20, 2, 32, 64), (9, 3, 17, 5), (8, 1, 8, 8)):
+        ids = rng.integers(0, Cn, size=(n, h, w))
+        onehot = np.eye(Cn, dtype=bool)[ids]
+        soft = onehot.copy()
+        soft[0, 0, 0, :] = False           # a void pixel without any class: not one-hot, must travel as it is
+        images = rng.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+        # device kernel alone
+        d_ids = torch.from_numpy(ids.astype(np.uint8)).to(cuda_device)
+        d_out = torch.full(onehot.shape, 7, dtype=torch.uint8, device=cuda_device)
+        ops.expand_labels(d_ids, d_out)
+        assert np.array_equal(d_out.cpu().numpy(), onehot.view(np.uint8))
+        # through the feeder
+        stub = Stub(Cn)
+        feeder = Feeder(stub, iter([(images, onehot), (images, soft), (images, onehot)]), 3)
+        try:
+            for expect in (onehot, soft, onehot):
+                x, y = feeder.get()
+                torch.cuda.current_stream().synchronize()
+                assert np.array_equal(x.cpu().numpy(), images)
+                assert np.array_equal(y.cpu().numpy(), expect.view(np.uint8))
+                feeder.release()
+            feeder.thread.join(timeout=30)
+            # the last batch staged was a packed one: images + one byte per pixel crossed PCIe
+            assert stub.feed_h2d_bytes_per_batch == images.nbytes + ids.size
+        finally:
+            feeder.close()

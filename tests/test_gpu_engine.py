@@ -167,6 +167,8 @@ def test_predict_and_metrics(cuda_device, problem, precision):
     sm = e.predict(x, argmax=False)
     am = e.predict(x, argmax=True)
     assert am.dtype == torch.int64 and tuple(am.shape) == (N, H, W)
+    am8 = e.predict(x, argmax=True, compact=True)     # the one-byte class map FCN8s.predict() brings over PCIe
+    assert am8.dtype == torch.uint8 and torch.equal(am8.long(), am)
     ref_sm = torch.softmax(problem["logits"], -1)
     assert rel(sm, ref_sm) <= 10 * LOGIT_TOL[precision]
     assert (sm.argmax(-1) == am).all()

@@ -38,6 +38,45 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert lib.fcn8_version() == 100
 
 
+def test_pack_labels_host_code_is_exact_and_rejects_anything_but_one_hot(lib_path):
+    """fcn8_pack_labels is HOST code (no CUDA call): one-hot bool batches as the reference's generators yield them
+    (helpers/ground_truth_conversion_utils.py:84-88, batch_generator_KITTI.py:82-84) -> one class id per pixel; any row
+    that is not exactly one-hot makes it report 1 so that the feed ships the batch unchanged."""
+    from fcn8s_tensorflow_b200 import ops
+    rng = np.random.default_rng(3)
+    for Cn, shape in ((20, (2, 64, 1024)), (2, (1, 300, 301)), (3, (1, 7, 9)), (7, (2, 5, 5)), (8, (1, 130, 130)),
+                      (9, (1, 64, 1027)), (33, (1, 50, 50)), (255, (1, 9, 9)), (1, (1, 4, 4))):
+        ids = rng.integers(0, Cn, size=shape).astype(np.uint8)
+        onehot = np.eye(Cn, dtype=bool)[ids]
+        out = np.full(shape, 251, np.uint8)
+        for threads in (1, 4):
+            assert ops.pack_labels(onehot, out, threads) and np.array_equal(out, ids), (Cn, threads)
+        u8 = np.ascontiguousarray(onehot.view(np.uint8))
+        assert ops.pack_labels(u8, out) and np.array_equal(out, ids)
+        for where in ((0, 0, 0), (shape[0] - 1, shape[1] - 1, shape[2] - 1), (0, shape[1] // 2, shape[2] // 3)):
+            empty = onehot.copy()
+            empty[where] = False                      # a pixel without a class
+            assert not ops.pack_labels(empty, out)
+            two = u8.copy()
+            two[where][int(ids[where])] = 2           # a label value other than 0 / 1
+            assert not ops.pack_labels(two, out)
+            if Cn > 1:
+                multi = onehot.copy()
+                multi[where][(int(ids[where]) + 1) % Cn] = True     # two classes on one pixel
+                assert not ops.pack_labels(multi, out)
+                moved = onehot.copy()                 # right number of set bytes, one of them in the neighbour's row
+                flat = moved.reshape(-1, Cn)
+                if flat.shape[0] > 1:
+                    flat[0, :] = False
+                    flat[1, :] = False
+                    flat[1, 0] = True
+                    if Cn > 1:
+                        flat[1, Cn - 1] = True
+                    assert not ops.pack_labels(moved, out)
+    with pytest.raises(ValueError):
+        ops.pack_labels(np.zeros((2, 2, 3), np.float32), np.zeros((2, 2), np.uint8))
+
+
 def test_ctypes_structs_match_header_layout():
     """Field order / count of the ctypes mirrors against the C structs in the header."""
     from fcn8s_tensorflow_b200 import _capi
