@@ -1073,6 +1073,10 @@ int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream) {
   int rc = check_pool(p);
   if (rc) return rc;
   if (!p->dx || !aligned16(p->dx)) return fail(FCN8_ERR_BAD_SHAPE, "pool bwd: dx missing / unaligned");
+  if (p->db) {   // a thread keeps the column sums of ONE channel vector: the grid stride must be a multiple of C / vec
+    const int CV = p->C / (p->dtype == FCN8_F32 ? 4 : 8);
+    if (CV <= 0 || 256 % CV) return fail(FCN8_ERR_UNSUPPORTED, "pool bwd: db needs C/vec (= %d) to divide 256", CV);
+  }
   cudaError_t e = launch_maxpool_bwd(p->x, p->y, p->dx, p->db, p->N, p->H, p->W, p->C, p->dtype, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "maxpool_bwd launch");
 }

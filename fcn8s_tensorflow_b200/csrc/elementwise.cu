@@ -28,8 +28,10 @@ struct Act<0> {
   using T = __nv_bfloat16;
   static constexpr int N = 8;
   static __device__ __forceinline__ int ld(int C) { return C; }
-  static __device__ __forceinline__ void load(const T* p, int, float (&f)[8]) {
-    uint4 q = *reinterpret_cast<const uint4*>(p);
+  // load = load_raw (the memory access, no dependent arithmetic: several can be in flight) + unpack
+  using Raw = uint4;
+  static __device__ __forceinline__ void load_raw(const T* p, int, Raw& q) { q = *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&f)[8]) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -37,6 +39,11 @@ struct Act<0> {
       f[2 * j] = t.x;
       f[2 * j + 1] = t.y;
     }
+  }
+  static __device__ __forceinline__ void load(const T* p, int C, float (&f)[8]) {
+    Raw q;
+    load_raw(p, C, q);
+    unpack(q, f);
   }
   static __device__ __forceinline__ void store(T* p, int, const float (&f)[8]) {
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
@@ -48,12 +55,18 @@ struct Act<1> {
   using T = float;
   static constexpr int N = 4;
   static __device__ __forceinline__ int ld(int C) { return C; }
-  static __device__ __forceinline__ void load(const T* p, int, float (&f)[4]) {
-    float4 q = *reinterpret_cast<const float4*>(p);
+  using Raw = float4;
+  static __device__ __forceinline__ void load_raw(const T* p, int, Raw& q) { q = *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&f)[4]) {
     f[0] = q.x;
     f[1] = q.y;
     f[2] = q.z;
     f[3] = q.w;
+  }
+  static __device__ __forceinline__ void load(const T* p, int C, float (&f)[4]) {
+    Raw q;
+    load_raw(p, C, q);
+    unpack(q, f);
   }
   static __device__ __forceinline__ void store(T* p, int, const float (&f)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
@@ -64,12 +77,24 @@ struct Act<2> {
   using T = __nv_bfloat16;
   static constexpr int N = 8;
   static __device__ __forceinline__ int ld(int C) { return 2 * C; }
-  static __device__ __forceinline__ void load(const T* p, int C, float (&f)[8]) {
+  struct Raw {
+    uint4 hi, lo;
+  };
+  static __device__ __forceinline__ void load_raw(const T* p, int C, Raw& q) {
+    q.hi = *reinterpret_cast<const uint4*>(p);
+    q.lo = *reinterpret_cast<const uint4*>(p + C);
+  }
+  static __device__ __forceinline__ void unpack(const Raw& q, float (&f)[8]) {
     float l[8];
-    Act<0>::load(p, C, f);
-    Act<0>::load(p + C, C, l);
+    Act<0>::unpack(q.hi, f);
+    Act<0>::unpack(q.lo, l);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] += l[j];
+  }
+  static __device__ __forceinline__ void load(const T* p, int C, float (&f)[8]) {
+    Raw q;
+    load_raw(p, C, q);
+    unpack(q, f);
   }
   static __device__ __forceinline__ void store(T* p, int C, const float (&f)[8]) {
     float l[8];
@@ -190,7 +215,7 @@ __device__ __forceinline__ float bm_pos(const float (&f)[4][NV], int e) {
 }
 // dx[window position] = dy if it is the first maximum of the window (scan order) and x > 0, else 0.
 template <int FMT>
-__global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
+__global__ void __launch_bounds__(256, FMT == 2 ? 2 : 4) maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
                                    const typename Act<FMT>::T* __restrict__ dy, typename Act<FMT>::T* __restrict__ dx,
                                    float* __restrict__ db, int N, int H, int W, int C) {
   pdl_launch_dependents();
@@ -212,9 +237,12 @@ __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
     r /= Wo;
     const int yo = static_cast<int>(r % Ho);
     const int n = static_cast<int>(r / Ho);
-    float g[V::N];
-    V::load(dy + opix * LD + cv * V::N, C, g);
-    float f[4][V::N];
+    // All five loads of the thread (dy and the window's four positions) are issued before anything depends on them:
+    // a position outside the image (odd H / W, SAME padding) loads the clamped -- valid -- address and is replaced by
+    // -inf afterwards, so that no load sits behind a branch.  (With one conditional load per position the loads of an
+    // iteration were five dependent round trips and the kernel ran at 4.2 TB/s on 25 % occupancy.)
+    typename V::Raw rg, rx[4];
+    V::load_raw(dy + opix * LD + cv * V::N, C, rg);
     bool inb[4];
     size_t off[4];
 #pragma unroll
@@ -222,9 +250,16 @@ __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
       const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
       inb[k] = (yy < H) && (xx < W);
       off[k] = ((static_cast<size_t>(n) * H + yy) * W + xx) * LD + cv * V::N;
-      if (inb[k]) {
-        V::load(x + off[k], C, f[k]);
-      } else {
+      const int yc = yy < H ? yy : H - 1, xc = xx < W ? xx : W - 1;
+      V::load_raw(x + ((static_cast<size_t>(n) * H + yc) * W + xc) * LD + cv * V::N, C, rx[k]);
+    }
+    float g[V::N];
+    V::unpack(rg, g);
+    float f[4][V::N];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      V::unpack(rx[k], f[k]);
+      if (!inb[k]) {
 #pragma unroll
         for (int e = 0; e < V::N; ++e) f[k][e] = -INFINITY;
       }
@@ -254,8 +289,20 @@ __global__ void maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
     for (int c = threadIdx.x; c < C; c += blockDim.x) sdb[c] = 0.f;
     __syncthreads();
     const int cv = static_cast<int>((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) % CV);
+    // lanes l, l + CV, ... of a warp work on the same channel vector when CV divides 32 (C = 64, 128): sum them with
+    // shuffles and let one lane per vector do the shared-memory atomics (fp32 shared atomics are CAS loops)
+    bool writer = true;
+    if (CV < 32 && (32 % CV) == 0) {
+      for (int s = 16; s >= CV; s >>= 1) {
 #pragma unroll
-    for (int e = 0; e < V::N; ++e) atomicAdd(&sdb[cv * V::N + e], bsum[e]);
+        for (int e = 0; e < V::N; ++e) bsum[e] += __shfl_xor_sync(0xffffffffu, bsum[e], s);
+      }
+      writer = (threadIdx.x & 31) < CV;
+    }
+    if (writer) {
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) atomicAdd(&sdb[cv * V::N + e], bsum[e]);
+    }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x)
       if (sdb[c] != 0.f) atomicAdd(db + c, sdb[c]);

@@ -10,8 +10,11 @@ Why it exists: the reference's generator imports `scipy.misc.imread / imresize`,
 /root/reference is not present on the GPU box, so `bench.py --config c5` (BASELINE configs[4], "batch_generator_KITTI
 feed path") needs a generator that ships with the product.  `tests/test_host_cpu.py` checks it batch-for-batch against
 the reference's own generator (run through `compat.install_scipy_misc_shim`) where the reference tree is mounted.
-Decoding + resizing of the files of one batch runs on a small thread pool (PIL releases the GIL); everything else is
-the reference's sequential logic.
+Decoding + resizing of the files runs on a small thread pool (PIL releases the GIL), one batch AHEAD: the files of
+batch k+1 are being decoded while batch k is assembled, yielded and consumed, so the consumer sees the decode latency
+of a batch only once.  The batches, their order, the reshuffle points and the use of the random generators are the
+reference's (the path list of batch k+1 is taken -- and, at the end of a pass, reshuffled -- before batch k is yielded
+instead of after; nothing else in the generator draws from `random`).
 """
 import os
 import random
@@ -22,7 +25,7 @@ from glob import glob
 import numpy as np
 
 BACKGROUND_COLOR = np.array([255, 0, 0])     # batch_generator_KITTI.py:44
-_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="fcn8-kitti-decode")
+_POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="fcn8-kitti-decode")
 
 
 def _load_resized(path, image_size):
@@ -35,6 +38,21 @@ def _load_resized(path, image_size):
     return a
 
 
+def _load_label(path, image_size):
+    """Resized label image -> bool [H, W, 2]: channel 0 = pixels of exactly the background colour, channel 1 = the rest
+    (batch_generator_KITTI.py:78-84).  Runs on the decode pool like the image files."""
+    label = _load_resized(path, image_size)
+    if label.ndim == 3 and label.shape[2] >= 3:
+        background = ((label[..., 0] == BACKGROUND_COLOR[0]) & (label[..., 1] == BACKGROUND_COLOR[1]) &
+                      (label[..., 2] == BACKGROUND_COLOR[2]))
+        if label.shape[2] > 3:     # RGBA file: np.all(label == [255, 0, 0], axis=2) cannot broadcast in the reference
+            raise ValueError("label image %s has %d channels" % (path, label.shape[2]))
+        background = background[..., None]
+    else:
+        background = np.all(label == BACKGROUND_COLOR, axis=2)[..., None]
+    return np.concatenate((background, np.invert(background)), axis=2)
+
+
 def batch_generator(batch_size, dataset_rootdir, images_subdir, labels_subdir, image_size, flip=False):
     image_paths = glob(os.path.join(dataset_rootdir, images_subdir, '*.png'))
     label_paths = None
@@ -42,22 +60,27 @@ def batch_generator(batch_size, dataset_rootdir, images_subdir, labels_subdir, i
         label_paths = {re.sub(r'_road_', '_', os.path.basename(path)): path
                        for path in glob(os.path.join(dataset_rootdir, labels_subdir, '*_road_*.png'))}
     random.shuffle(image_paths)
-    current = 0
-    while True:
-        if current >= len(image_paths):
+    state = {"current": 0}
+
+    def start_next_batch():
+        """The reference's loop head (:56-61) for the next batch + its decode jobs."""
+        if state["current"] >= len(image_paths):
             random.shuffle(image_paths)
-            current = 0
-        paths = image_paths[current:current + batch_size]
+            state["current"] = 0
+        paths = image_paths[state["current"]:state["current"] + batch_size]
+        state["current"] += batch_size
         jobs = [_POOL.submit(_load_resized, p, image_size) for p in paths]
         if label_paths is not None:
-            jobs += [_POOL.submit(_load_resized, label_paths[os.path.basename(p)], image_size) for p in paths]
+            jobs += [_POOL.submit(_load_label, label_paths[os.path.basename(p)], image_size) for p in paths]
+        return paths, jobs
+
+    ahead = start_next_batch()
+    while True:
+        paths, jobs = ahead
+        ahead = start_next_batch()
         done = [j.result() for j in jobs]
         images = done[:len(paths)]
-        labels = []
-        for label in done[len(paths):]:
-            background = np.all(label == BACKGROUND_COLOR, axis=2)[..., None]
-            labels.append(np.concatenate((background, np.invert(background)), axis=2))
-        current += batch_size
+        labels = done[len(paths):]
         for i in range(len(images)):
             if flip:
                 p = np.random.uniform(0, 1)

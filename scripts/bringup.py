@@ -311,6 +311,22 @@ def elementwise_kernels():
         yr.backward(dy.double().permute(0, 3, 1, 2))
         ref = xr.grad.permute(0, 2, 3, 1) * (x.double() > 0)
         ok &= report("maxpool bwd dt%d" % dtype, dx, ref, 0.0)
+        if dtype == 0:
+            # bias gradient of the producer, accumulated by the same kernel, for every VGG width (the lanes of a warp
+            # that share a channel vector are pre-reduced with shuffles when C < 256)
+            for Cc in (64, 128, 256, 512):
+                xc = torch.randn(2, 9, 13, Cc, device=dev).clamp_min(0).to(tdt)
+                dyc = torch.randn(2, 5, 7, Cc, device=dev).to(tdt)
+                db = torch.full((Cc,), 0.5, device=dev)
+                dxc = ops.maxpool_bwd(xc, dyc, db=db)
+                ok &= report("maxpool bwd db C%d" % Cc, db, 0.5 + dxc.double().sum((0, 1, 2)), 1e-5)
+            try:     # 192 / 8 = 24 channel vectors do not divide the 256-thread grid stride: refused, not mis-summed
+                ops.maxpool_bwd(torch.zeros(1, 4, 4, 192, device=dev).to(tdt), torch.zeros(1, 2, 2, 192, device=dev).to(tdt),
+                                db=torch.zeros(192, device=dev))
+                ok = False
+                print("  maxpool bwd db C192 was not refused: FAIL")
+            except Exception:  # noqa: BLE001
+                pass
         # bias grad
         for Cc in (64, 512, 4096):
             g = torch.randn(1000, Cc, device=dev).to(tdt)
@@ -518,6 +534,12 @@ def pair_elementwise():
     dx = ops.maxpool_bwd(x, dy, pair=True)
     yr.backward(ops.from_pair(dy).double().permute(0, 3, 1, 2))
     ok &= report("maxpool bwd pair", ops.from_pair(dx), xr.grad.permute(0, 2, 3, 1) * (ops.from_pair(x).double() > 0), 0.0)
+    for Cc in (64, 128, 512):
+        xc = ops.to_pair(torch.randn(2, 9, 13, Cc, device=dev).clamp_min(0))
+        dyc = ops.to_pair(torch.randn(2, 5, 7, Cc, device=dev))
+        db = torch.zeros(Cc, device=dev)
+        dxc = ops.maxpool_bwd(xc, dyc, pair=True, db=db)
+        ok &= report("maxpool bwd pair db C%d" % Cc, db, ops.from_pair(dxc).double().sum((0, 1, 2)), 1e-5)
     for Cc in (64, 4096):
         g = ops.to_pair(torch.randn(1000, Cc, device=dev))
         db = torch.empty(Cc, device=dev)
