@@ -214,6 +214,50 @@ __device__ __forceinline__ float bm_pos(const float (&f)[4][NV], int e) {
   return fmaxf(fmaxf(f[0][e], f[1][e]), fmaxf(f[2][e], f[3][e]));
 }
 // dx[window position] = dy if it is the first maximum of the window (scan order) and x > 0, else 0.
+//
+// bf16 formats (FMT 0 / 2): the window logic runs on PACKED bf16 pairs -- compare-to-mask (__hgt2_mask / __heq2_mask)
+// and bitwise selects, two channels per 32-bit operation, and dy's bits are copied, never converted.  (The fp32
+// formulation -- unpack 5 x 8 values, arg-max with selects, re-pack 4 x 8 values -- was ~1000 instructions per
+// iteration and made the bf16 kernel issue-bound at 3.1 TB/s.)  A hi/lo pair (FMT 2) compares lexicographically:
+// hi = bf16(v) and lo = bf16(v - hi) are both monotone in v, so (hi, lo) orders exactly like hi + lo.
+__device__ __forceinline__ uint32_t bf2_gt(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t bf2_eq(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t bit_sel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
+constexpr uint32_t kBf2NegInf = 0xff80ff80u;
+// One 32-bit word = two channels of the four window positions.  x?: values (hi words; l? = lo words when PAIR),
+// oob bit k: position k lies outside the image.  Returns w[k] = mask of the channels that position k wins (first
+// strict maximum in scan order, and the maximum is > 0).
+template <bool PAIR>
+__device__ __forceinline__ void pool_winner_masks(const uint32_t (&xh)[4], const uint32_t (&xl)[4], uint32_t (&w)[4]) {
+  uint32_t bh = xh[0], bl = PAIR ? xl[0] : 0u;
+  uint32_t g[4];
+  g[0] = 0u;
+#pragma unroll
+  for (int k = 1; k < 4; ++k) {
+    uint32_t gt = bf2_gt(xh[k], bh);
+    if (PAIR) gt |= bf2_eq(xh[k], bh) & bf2_gt(xl[k], bl);
+    g[k] = gt;
+    bh = bit_sel(gt, xh[k], bh);
+    if (PAIR) bl = bit_sel(gt, xl[k], bl);
+  }
+  uint32_t pos = bf2_gt(bh, 0u);
+  if (PAIR) pos |= bf2_eq(bh, 0u) & bf2_gt(bl, 0u);
+  w[3] = g[3] & pos;
+  w[2] = g[2] & ~g[3] & pos;
+  w[1] = g[1] & ~(g[2] | g[3]) & pos;
+  w[0] = ~(g[1] | g[2] | g[3]) & pos;
+}
+__device__ __forceinline__ uint32_t u4_get(const uint4& q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w)); }
+__device__ __forceinline__ void u4_set(uint4& q, int j, uint32_t v) {
+  if (j == 0) q.x = v;
+  else if (j == 1) q.y = v;
+  else if (j == 2) q.z = v;
+  else q.w = v;
+}
 template <int FMT>
 __global__ void __launch_bounds__(256, FMT == 2 ? 2 : 4) maxpool_bwd_kernel(const typename Act<FMT>::T* __restrict__ x,
                                    const typename Act<FMT>::T* __restrict__ dy, typename Act<FMT>::T* __restrict__ dx,
@@ -222,17 +266,16 @@ __global__ void __launch_bounds__(256, FMT == 2 ? 2 : 4) maxpool_bwd_kernel(cons
   pdl_wait();
   using V = Act<FMT>;
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, CV = C / V::N, LD = V::ld(C);
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * CV;
+  const unsigned int total = static_cast<unsigned int>(N) * Ho * Wo * CV;   // < 2^31, checked by the launcher
   // bias gradient of the producing conv: the grid stride is a multiple of CV, so a thread always works on the same
   // channel vector and can keep its column sums in registers
   float bsum[V::N];
 #pragma unroll
   for (int e = 0; e < V::N; ++e) bsum[e] = 0.f;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int cv = static_cast<int>(i % CV);
-    size_t r = i / CV;
-    const size_t opix = r;
+    unsigned int r = i / CV;
+    const unsigned int opix = r;
     const int xo = static_cast<int>(r % Wo);
     r /= Wo;
     const int yo = static_cast<int>(r % Ho);
@@ -242,53 +285,108 @@ __global__ void __launch_bounds__(256, FMT == 2 ? 2 : 4) maxpool_bwd_kernel(cons
     // -inf afterwards, so that no load sits behind a branch.  (With one conditional load per position the loads of an
     // iteration were five dependent round trips and the kernel ran at 4.2 TB/s on 25 % occupancy.)
     typename V::Raw rg, rx[4];
-    V::load_raw(dy + opix * LD + cv * V::N, C, rg);
+    V::load_raw(dy + static_cast<size_t>(opix) * LD + cv * V::N, C, rg);
     bool inb[4];
     size_t off[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
       inb[k] = (yy < H) && (xx < W);
-      off[k] = ((static_cast<size_t>(n) * H + yy) * W + xx) * LD + cv * V::N;
+      off[k] = (static_cast<size_t>(n * H + yy) * W + xx) * LD + cv * V::N;
       const int yc = yy < H ? yy : H - 1, xc = xx < W ? xx : W - 1;
-      V::load_raw(x + ((static_cast<size_t>(n) * H + yc) * W + xc) * LD + cv * V::N, C, rx[k]);
+      V::load_raw(x + (static_cast<size_t>(n * H + yc) * W + xc) * LD + cv * V::N, C, rx[k]);
     }
-    float g[V::N];
-    V::unpack(rg, g);
-    float f[4][V::N];
+    if constexpr (FMT == 0 || FMT == 2) {
+      constexpr bool PAIR = FMT == 2;
+      typename V::Raw ro[4];
+      uint32_t keep[4];    // channels (as bf16x2 masks) whose window maximum is positive: what the bias gradient sums
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      V::unpack(rx[k], f[k]);
-      if (!inb[k]) {
+      for (int j = 0; j < 4; ++j) {
+        uint32_t xh[4], xl[4], w[4];
 #pragma unroll
-        for (int e = 0; e < V::N; ++e) f[k][e] = -INFINITY;
-      }
-    }
-    float o[4][V::N];
-#pragma unroll
-    for (int e = 0; e < V::N; ++e) {
-      int best = 0;
-      float bm = f[0][e];
-#pragma unroll
-      for (int k = 1; k < 4; ++k)
-        if (f[k][e] > bm) {
-          bm = f[k][e];
-          best = k;
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (PAIR) {
+            xh[k] = inb[k] ? u4_get(rx[k].hi, j) : kBf2NegInf;
+            xl[k] = inb[k] ? u4_get(rx[k].lo, j) : 0u;
+          } else {
+            xh[k] = inb[k] ? u4_get(rx[k], j) : kBf2NegInf;
+            xl[k] = 0u;
+          }
         }
+        pool_winner_masks<PAIR>(xh, xl, w);
+        keep[j] = w[0] | w[1] | w[2] | w[3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k][e] = (k == best && bm > 0.f) ? g[e] : 0.f;
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (PAIR) {
+            u4_set(ro[k].hi, j, u4_get(rg.hi, j) & w[k]);
+            u4_set(ro[k].lo, j, u4_get(rg.lo, j) & w[k]);
+          } else {
+            u4_set(ro[k], j, u4_get(rg, j) & w[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (inb[k]) {
+          if constexpr (PAIR) {
+            *reinterpret_cast<uint4*>(dx + off[k]) = ro[k].hi;
+            *reinterpret_cast<uint4*>(dx + off[k] + C) = ro[k].lo;
+          } else {
+            *reinterpret_cast<uint4*>(dx + off[k]) = ro[k];
+          }
+        }
+      typename V::Raw rk = rg;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (PAIR) {
+          u4_set(rk.hi, j, u4_get(rg.hi, j) & keep[j]);
+          u4_set(rk.lo, j, u4_get(rg.lo, j) & keep[j]);
+        } else {
+          u4_set(rk, j, u4_get(rg, j) & keep[j]);
+        }
+      }
+      float gk[V::N];
+      V::unpack(rk, gk);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) bsum[e] += gk[e];
+    } else {
+      float g[V::N];
+      V::unpack(rg, g);
+      float f[4][V::N];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        V::unpack(rx[k], f[k]);
+        if (!inb[k]) {
+#pragma unroll
+          for (int e = 0; e < V::N; ++e) f[k][e] = -INFINITY;
+        }
+      }
+      float o[4][V::N];
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) {
+        int best = 0;
+        float bm = f[0][e];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+          if (f[k][e] > bm) {
+            bm = f[k][e];
+            best = k;
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k][e] = (k == best && bm > 0.f) ? g[e] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (inb[k]) V::store(dx + off[k], C, o[k]);
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) bsum[e] += (bm_pos(f, e) > 0.f) ? g[e] : 0.f;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (inb[k]) V::store(dx + off[k], C, o[k]);
-#pragma unroll
-    for (int e = 0; e < V::N; ++e) bsum[e] += (bm_pos(f, e) > 0.f) ? g[e] : 0.f;
   }
   if (db) {
     extern __shared__ float sdb[];  // [C]
     for (int c = threadIdx.x; c < C; c += blockDim.x) sdb[c] = 0.f;
     __syncthreads();
-    const int cv = static_cast<int>((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) % CV);
+    const int cv = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) % CV);
     // lanes l, l + CV, ... of a warp work on the same channel vector when CV divides 32 (C = 64, 128): sum them with
     // shuffles and let one lane per vector do the shared-memory atomics (fp32 shared atomics are CAS loops)
     bool writer = true;
@@ -322,7 +420,11 @@ cudaError_t launch_maxpool_fwd(const void* x, void* y, int N, int H, int W, int 
 cudaError_t launch_maxpool_bwd(const void* x, const void* dy, void* dx, float* db, int N, int H, int W, int C,
                                int dtype, cudaStream_t st) {
   const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * (C / act_vec(dtype));
-  const int blocks = grid_for(total, 256);   // 256 % CV == 0 for every VGG width, so the grid stride keeps cv fixed
+  if (total >= (1ull << 31) || static_cast<size_t>(N) * H >= (1ull << 31)) return cudaErrorInvalidValue;   // 32-bit indices
+  // 256 % CV == 0 for every VGG width, so the grid stride keeps cv fixed.  One wave of resident CTAs (launch bounds: 4
+  // per SM, 2 for the pair format): every CTA ends with C shared + C global atomics for the bias gradient, which cost
+  // as much as the main loop of a short-lived CTA on the small pools (pool3..pool5 ran at 2.4-3.5 TB/s with 2368 CTAs)
+  const int blocks = grid_for(total, 256, 148 * (dtype == 2 ? 2 : 4));
   const size_t sm = db ? static_cast<size_t>(C) * sizeof(float) : 0;
 #define CALL(F) { (void)launch_k(maxpool_bwd_kernel<F>, dim3(blocks), dim3(256), sm, st, static_cast<const typename Act<F>::T*>(x), static_cast<const typename Act<F>::T*>(dy), static_cast<typename Act<F>::T*>(dx), db, N, H, W, C); }
   FCN8_FMT_DISPATCH(dtype, CALL);
