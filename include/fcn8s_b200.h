@@ -232,7 +232,8 @@ typedef struct {
   void* dx;       /* bwd only */
   int32_t N, H, W, C;
   int32_t dtype;
-  float* db;      /* bwd only, optional: db[c] += sum over pixels of dx (bias gradient of the producing conv) */
+  float* db;      /* bwd only, optional: db[c] += sum over pixels of dx (bias gradient of the producing conv); needs
+                     C / 8 (C / 4 for FCN8_F32) to divide 256 -- every VGG width does; FCN8_ERR_UNSUPPORTED otherwise */
 } Fcn8PoolParams;
 int32_t fcn8_maxpool_fwd(const Fcn8PoolParams* p, void* stream);
 int32_t fcn8_maxpool_bwd(const Fcn8PoolParams* p, void* stream);
