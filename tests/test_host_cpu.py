@@ -38,6 +38,22 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert lib.fcn8_version() == 100
 
 
+def test_header_is_valid_c_and_a_c_client_links(lib_path, tmp_path):
+    """include/fcn8s_b200.h is the drop-in boundary: it must compile as plain C (no torch / C++ types in the
+    signatures) and a C client must link against the in-tree library and get the documented status codes."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(lib_path)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_smoke.c"), "-o", exe, "-L", libdir,
+                    "-l:" + os.path.basename(lib_path), "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and "abi ok" in r.stdout, (r.returncode, r.stdout)
+
+
 def test_pack_labels_host_code_is_exact_and_rejects_anything_but_one_hot(lib_path):
     """fcn8_pack_labels is HOST code (no CUDA call): one-hot bool batches as the reference's generators yield them
     (helpers/ground_truth_conversion_utils.py:84-88, batch_generator_KITTI.py:82-84) -> one class id per pixel; any row
