@@ -169,6 +169,19 @@ def test_product_package_never_imports_the_oracle():
             assert "import oracle" not in src and "from oracle" not in src, fn
 
 
+def test_hot_path_modules_call_no_library_compute():
+    """The training / inference path (engine, ops, feed, dist, the class surface) must reach the GPU only through the
+    C ABI: no torch.nn / functional / matmul / compile, no Triton, no cuDNN -- torch is the owner of device memory,
+    streams and the process group, nothing else."""
+    pkg = os.path.join(ROOT, "fcn8s_tensorflow_b200")
+    banned = re.compile(r"torch\.nn\b|torch\.compile|import\s+triton|cudnn|\bF\.(conv|max_pool|softmax|cross_entropy|relu)"
+                        r"|\.matmul\(|torch\.(mm|bmm|einsum|conv2d|conv_transpose2d|softmax|argmax)\(")
+    for name in ("engine.py", "ops.py", "feed.py", "dist.py", "fcn8s.py", "_capi.py"):
+        src = open(os.path.join(pkg, name)).read()
+        hits = [m.group(0) for m in banned.finditer(src)]
+        assert not hits, (name, hits)
+
+
 def test_shard_bounds():
     from fcn8s_tensorflow_b200.dist import shard_batch, shard_bounds
     assert [shard_bounds(16, r, 8) for r in (0, 7)] == [(0, 2), (14, 16)]
