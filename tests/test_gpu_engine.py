@@ -68,6 +68,32 @@ def make_engine(cuda_device, precision, weights, classes=C):
     return e
 
 
+def test_forward_against_tensorflow_graphdef_executed_by_opencv(cuda_device):
+    """The engine against an independent implementation of TensorFlow's op semantics, WITHOUT the oracle in between:
+    the full-width GraphDef of the reference's prediction graph (oracle/tf_graphdef.py) executed by OpenCV's
+    TensorFlow importer on the problem of tests/golden/oracle_small.json (the one smoke() runs); its logits and
+    arg-max are committed in tests/golden/opencv_tf_fcn8s_full.npz.  Tolerance: the north-star 1e-4 on the logits."""
+    import json
+    import os
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = np.load(os.path.join(golden, "opencv_tf_fcn8s_full.npz"))
+    meta = json.load(open(os.path.join(golden, "oracle_small.json")))
+    classes = meta["num_classes"]
+    w = oracle.init_weights(classes, seed=meta["weight_seed"], decoder_std_scale=meta["decoder_std_scale"])
+    images, _ = oracle.synthetic_batch(meta["n"], meta["h"], meta["w"], classes, seed=meta["data_seed"])
+    e = make_engine(cuda_device, "fp32", w, classes=classes)
+    x = torch.from_numpy(images).to(cuda_device)
+    ref = torch.from_numpy(g["logits"]).double()
+    logits = e.forward(x)
+    assert tuple(logits.shape) == tuple(ref.shape)
+    assert rel(logits, ref) <= LOGIT_TOL["fp32"]
+    # arg-max (tf.argmax, fcn8s_tensorflow.py:269) may only differ where the top-2 logits are closer than the tolerance
+    am = e.predict(x, argmax=True).cpu()
+    diff = am != torch.from_numpy(g["argmax"].astype(np.int64))
+    top2 = ref.topk(2, -1).values
+    assert ((top2[..., 0] - top2[..., 1])[diff] <= LOGIT_TOL["fp32"] * ref.abs().max()).all()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_forward_logits(cuda_device, problem, precision):
     e = make_engine(cuda_device, precision, problem["weights"])
