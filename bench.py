@@ -463,6 +463,9 @@ def train_line(cfg, precision, r, args, world, peaks):
     achieved = k["flops"] / (k["ms"] * 1e-3) / 1e12 if k["launches"] else 0.0
     traffic, traffic_src = ncu_traffic(precision) if args.config == "c2" else (None, None)
     dtype = DTYPE_TEXT[precision]
+    # forward convolutions always run 3 products in the fp32-equivalent mode; the conv_gemm family timed here is fprop +
+    # dgrad, so a non-default backward_terms lowers the average (reported as the default 3 only when it applies)
+    mma_per_product = (3 if args.backward_terms == 3 else (3 + args.backward_terms) / 2.0) if precision == "fp32" else 1
     if precision == "fp32" and args.backward_terms != 3:
         dtype += "; NON-DEFAULT backward: %d bf16 product(s) per algorithmic product in dgrad / wgrad" % args.backward_terms
     line = {
@@ -482,6 +485,14 @@ def train_line(cfg, precision, r, args, world, peaks):
                       % ksteps
                       + ("; the fp32-equivalent mode executes 3 bf16 MMAs per algorithmic product, so its own ceiling "
                          "is peak/3" if precision == "fp32" and args.backward_terms == 3 else ""),
+            # what the tensor pipe itself executes: `achieved` counts ALGORITHMIC flops, the fp32-equivalent mode issues
+            # 3 bf16 MMAs per algorithmic product (hi*hi + hi*lo + lo*hi), so frac <= 1/3 there by construction
+            "mma_per_product": mma_per_product,
+            "tensor_pipe_tflops": achieved * mma_per_product,
+            "tensor_pipe_frac_of_peak": achieved * mma_per_product / peaks["tflops"],
+            "peak_burst": peaks.get("tflops_burst"),
+            "tensor_pipe_frac_of_burst_peak": (achieved * mma_per_product / peaks["tflops_burst"]
+                                               if peaks.get("tflops_burst") else None),
             "wgrad_gemm": {"achieved": kw["flops"] / (kw["ms"] * 1e-3) / 1e12 if kw["launches"] else 0.0,
                            "kernel_ms_per_step": kw["ms"] / ksteps, "share_of_step": kw["ms"] / ksteps / step_ms},
             "whole_step_tflops_per_gpu": value / world * cfg["train_gflop"] / 1e3,

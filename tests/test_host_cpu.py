@@ -182,6 +182,32 @@ def test_hot_path_modules_call_no_library_compute():
         assert not hits, (name, hits)
 
 
+def test_bench_line_carries_the_contract_keys():
+    """bench.py's JSON line is assembled by train_line(): the driver's contract keys, computed from a fake result on
+    the CPU (the timing itself needs a GPU)."""
+    import json
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    args = types.SimpleNamespace(steps=20, config="c2", backward_terms=3)
+    flops = 2.0 * 4 * 890e9      # conv fprop + dgrad of 4 images, roughly
+    r = dict(ms=290.0, launches=2020, e2e_ms=292.0, h2d=8388608, d2h=8, clocks={"sm_mhz": 1700.0}, loss=2.99, mem_gb=8.1,
+             kernels={"conv_gemm": dict(launches=140, flops=5 * flops, ms=5 * 7.5),
+                      "wgrad_gemm": dict(launches=80, flops=5 * flops / 2, ms=5 * 4.5), "_steps": 5})
+    peaks = dict(tflops=1362.0, tflops_burst=1625.8, hbm=6548.8, source="test")
+    line = bench.train_line(bench.CONFIGS["c2"], "fp32", r, args, 1, peaks)
+    json.dumps(line)
+    assert abs(line["value"] - 4 * 20 / 0.290) < 1e-6 and abs(line["ms_per_step"] - 14.5) < 1e-9
+    assert line["gpu_launches"] == 2020 and line["e2e"]["h2d_bytes_per_step"] == 8388608
+    ro = line["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in ro
+    assert ro["bound"] == "tensor" and ro["unit"] == "TFLOP/s" and abs(ro["frac"] - ro["achieved"] / 1362.0) < 1e-12
+    # the fp32-equivalent mode issues three MMAs per algorithmic product: its fraction is bounded by 1/3 of the pipe
+    assert ro["mma_per_product"] == 3 and abs(ro["tensor_pipe_tflops"] - 3 * ro["achieved"]) < 1e-9
+    assert bench.train_line(bench.CONFIGS["c2"], "bf16", r, args, 1, peaks)["roofline"]["mma_per_product"] == 1
+
+
 def test_shard_bounds():
     from fcn8s_tensorflow_b200.dist import shard_batch, shard_bounds
     assert [shard_bounds(16, r, 8) for r in (0, 7)] == [(0, 2), (14, 16)]
